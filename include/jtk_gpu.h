@@ -1,0 +1,103 @@
+/*
+ * jtk_gpu.h -- C ABI of libjtkgpu.so: the B200 (sm_100a) drop-in for the per-chunk pair-HMM hot path
+ * of ban-m/jtk.  The reference has no FFI of its own: the hot path is plain Rust
+ * method calls into the un-vendored crate kiley 0.3.0.  Each entry point below names the reference call
+ * site (file:line under /root/reference) whose kiley call it replaces; INTEGRATION.md shows the Rust
+ * `extern "C"` shim a maintainer would add.
+ *
+ * Conventions (SURVEY.md section 8b "Data conventions"):
+ *   sequences  ASCII ACGT, reads already in template orientation (definitions/src/lib.rs:678)
+ *   ops        one byte per alignment column: 0 Match, 1 Mismatch, 2 Ins (read-only base),
+ *              3 Del (template-only base)          (haplotyper/src/misc.rs:167-186)
+ *   table      row-minor t[j*NUM_ROW + row], j in 0..=Lt (pseudo_mcmc.rs:125,169,439)
+ *   params     the 9+16+20 doubles of HMMParam in declaration order (definitions/src/lib.rs:102-126)
+ *   strand     1 = forward model, 0 = reverse model (pseudo_mcmc.rs:58-61)
+ * All pointers are HOST pointers unless the name says `dev`.  The caller owns every host buffer; the
+ * library never retains a host pointer past the call.  Every function returns 0 on success or a
+ * negative JTK_E* code; jtk_last_error(ctx) gives the message.  Functions are thread-safe per distinct
+ * ctx, not re-entrant on one ctx.  There is NO CPU fallback: without a CUDA device every compute call
+ * fails with JTK_ECUDA.
+ */
+#ifndef JTK_GPU_H
+#define JTK_GPU_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JTK_NUM_ROW 14   /* kiley::hmm::NUM_ROW   (pseudo_mcmc.rs:7)   */
+#define JTK_COPY_SIZE 3  /* kiley::hmm::COPY_SIZE (pseudo_mcmc.rs:172) */
+#define JTK_DEL_SIZE 3
+#define JTK_TABLE_NEG (-1.0e10) /* absolute value stored for an impossible edit */
+
+enum { JTK_OP_MATCH = 0, JTK_OP_MISMATCH = 1, JTK_OP_INS = 2, JTK_OP_DEL = 3 };
+enum {
+    JTK_OK = 0,
+    JTK_EINVAL = -1,  /* bad argument (null pointer, ops that do not span the pair, radius out of range) */
+    JTK_ECUDA = -2,   /* CUDA runtime error, or no device */
+    JTK_ENOMEM = -3,  /* device or host allocation failed */
+    JTK_ESTATE = -4   /* handle used in the wrong state */
+};
+
+/* definitions/src/lib.rs:102-126 (HMMParam) == kiley::hmm::PairHiddenMarkovModel (model_tune.rs:36-62) */
+typedef struct {
+    double mat_mat, mat_ins, mat_del;
+    double ins_mat, ins_ins, ins_del;
+    double del_mat, del_ins, del_del;
+    double mat_emit[16]; /* 4*ref + query                         */
+    double ins_emit[20]; /* 4*prev_read_base + query, prev=4: none */
+} jtk_hmm_params;
+
+typedef struct jtk_ctx jtk_ctx;
+
+/* ---- context ----------------------------------------------------------------------------------- */
+/* device < 0: use the current CUDA device.  workspace_bytes = 0: size scratch on demand. */
+int jtk_ctx_create(int device, size_t workspace_bytes, jtk_ctx **out);
+void jtk_ctx_destroy(jtk_ctx *ctx);
+const char *jtk_last_error(const jtk_ctx *ctx); /* ctx may be NULL: last error of jtk_ctx_create */
+int jtk_hmm_num_row(void);   /* kiley::hmm::NUM_ROW   */
+int jtk_hmm_copy_size(void); /* kiley::hmm::COPY_SIZE */
+int jtk_hmm_del_size(void);
+/* number of kernels launched by this ctx so far (bench.py's gpu_launches) */
+uint64_t jtk_ctx_launch_count(const jtk_ctx *ctx);
+/* device time (ms, CUDA events on the ctx stream) of the dominant kernel in the last batch call */
+float jtk_ctx_last_kernel_ms(const jtk_ctx *ctx);
+
+/* ---- level 1: kiley-shaped batch calls --------------------------------------------------------- */
+/*
+ * Batched PairHiddenMarkovModel::modification_table_antidiagonal(template, read, ops, band) -> (table, lk)
+ *   reference call site: haplotyper/src/local_clustering/pseudo_mcmc.rs:62-63 (one call per read).
+ * Pair p uses template tmpl_idx[p] (bytes tmpl_concat[tmpl_off[t] .. tmpl_off[t+1])), read
+ * read_concat[read_off[p] .. read_off[p+1]), ops ops_concat[ops_off[p] .. ops_off[p+1]) and the model
+ * chosen by strand[p].  out_lk[p] = ln P(read | template).  out_table (may be NULL) receives, at
+ * table_off[p], (Lt+1)*JTK_NUM_ROW absolute log-likelihoods (kiley's return value; the caller subtracts lk,
+ * pseudo_mcmc.rs:64).
+ */
+int jtk_hmm_modtable_batch(jtk_ctx *ctx, const jtk_hmm_params *fwd, const jtk_hmm_params *rev, int n_pairs,
+                           int n_tmpl, const uint8_t *tmpl_concat, const uint32_t *tmpl_off,
+                           const uint8_t *read_concat, const uint32_t *read_off,
+                           const uint8_t *ops_concat, const uint32_t *ops_off,
+                           const uint8_t *strand, const uint32_t *tmpl_idx, int radius,
+                           double *out_lk, double *out_table, const uint64_t *table_off);
+
+/*
+ * Batched forward likelihood with guide ops: the arithmetic of
+ * PairHiddenMarkovModel::likelihood_antidiagonal_bootstrap(template, read, band)
+ *   reference call sites: haplotyper/src/likelihood_gains.rs:27-28,282-283,301-302.
+ * ops_concat == NULL selects the bootstrap path: the guide is a banded global edit-distance alignment
+ * computed inside the library.
+ */
+int jtk_hmm_likelihood_batch(jtk_ctx *ctx, const jtk_hmm_params *fwd, const jtk_hmm_params *rev, int n_pairs,
+                             int n_tmpl, const uint8_t *tmpl_concat, const uint32_t *tmpl_off,
+                             const uint8_t *read_concat, const uint32_t *read_off,
+                             const uint8_t *ops_concat, const uint32_t *ops_off,
+                             const uint8_t *strand, const uint32_t *tmpl_idx, int radius, double *out_lk);
+
+/* in-band cell count C = sum_d w(d) of one pair (SURVEY.md section 8d work unit); <0 if ops are invalid */
+int64_t jtk_band_cell_count(const uint8_t *ops, int n_ops, int Lt, int Lr, int radius);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,170 @@
+"""ctypes loader for libjtkgpu.so (the C ABI declared in include/jtk_gpu.h).
+
+There is no CPU fallback: if the shared library is missing this module raises at first use, and if no
+CUDA device is present `Context()` raises `JtkError` (JTK_ECUDA).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libjtkgpu.so")
+
+NUM_ROW = 14
+COPY_SIZE = 3
+DEL_SIZE = 3
+TABLE_NEG = -1.0e10
+
+EXPORTS = [
+    "jtk_ctx_create", "jtk_ctx_destroy", "jtk_last_error", "jtk_hmm_num_row", "jtk_hmm_copy_size",
+    "jtk_hmm_del_size", "jtk_ctx_launch_count", "jtk_ctx_last_kernel_ms", "jtk_hmm_modtable_batch",
+    "jtk_hmm_likelihood_batch", "jtk_band_cell_count",
+]
+
+
+class JtkError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libjtkgpu error {code}: {msg}")
+        self.code = code
+
+
+class HmmParams(C.Structure):
+    """jtk_hmm_params == definitions::HMMParam (definitions/src/lib.rs:102-126)."""
+    _fields_ = [(n, C.c_double) for n in
+                ("mat_mat", "mat_ins", "mat_del", "ins_mat", "ins_ins", "ins_del", "del_mat", "del_ins", "del_del")] + \
+               [("mat_emit", C.c_double * 16), ("ins_emit", C.c_double * 20)]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m jtk_b200.build` (nvcc, sm_100a). "
+            "jtk_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, u32p, u64p = C.c_void_p, C.c_void_p, C.c_void_p
+    L.jtk_ctx_create.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.jtk_ctx_destroy.argtypes = [C.c_void_p]
+    L.jtk_ctx_destroy.restype = None
+    L.jtk_last_error.argtypes = [C.c_void_p]
+    L.jtk_last_error.restype = C.c_char_p
+    L.jtk_ctx_launch_count.argtypes = [C.c_void_p]
+    L.jtk_ctx_launch_count.restype = C.c_uint64
+    L.jtk_ctx_last_kernel_ms.argtypes = [C.c_void_p]
+    L.jtk_ctx_last_kernel_ms.restype = C.c_float
+    batch = [C.c_void_p, C.POINTER(HmmParams), C.POINTER(HmmParams), C.c_int, C.c_int, vp, u32p, vp, u32p, vp, u32p,
+             vp, u32p, C.c_int, vp]
+    L.jtk_hmm_modtable_batch.argtypes = batch + [vp, u64p]
+    L.jtk_hmm_likelihood_batch.argtypes = batch
+    L.jtk_band_cell_count.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.jtk_band_cell_count.restype = C.c_int64
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _u8(a) -> np.ndarray:
+    if isinstance(a, (bytes, bytearray)):
+        return np.frombuffer(bytes(a), dtype=np.uint8)
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def concat(seqs):
+    """list of uint8 arrays -> (concat uint8, offsets uint32[n+1])."""
+    lens = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=len(seqs))
+    off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    if off[-1] >= 2 ** 32:
+        raise ValueError("batch exceeds 4 GiB of sequence; split it")
+    cat = np.concatenate([_u8(s) for s in seqs]) if len(seqs) and off[-1] else np.zeros(0, dtype=np.uint8)
+    return np.ascontiguousarray(cat), off.astype(np.uint32)
+
+
+class Context:
+    """Owns one jtk_ctx (one CUDA device, one stream, growable device workspaces)."""
+
+    def __init__(self, device: int = -1):
+        self._h = C.c_void_p()
+        rc = lib().jtk_ctx_create(device, 0, C.byref(self._h))
+        if rc != 0:
+            raise JtkError(rc, lib().jtk_last_error(None).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().jtk_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise JtkError(rc, lib().jtk_last_error(self._h).decode())
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().jtk_ctx_launch_count(self._h))
+
+    @property
+    def last_kernel_ms(self) -> float:
+        return float(lib().jtk_ctx_last_kernel_ms(self._h))
+
+    # ---- level 1 -------------------------------------------------------------------------------
+    def modtable_batch(self, fwd: HmmParams, rev: HmmParams, templates, reads, ops, strands, tmpl_idx, radius,
+                       want_table=True):
+        """jtk_hmm_modtable_batch.  Returns (lk float64[n], tables: list of float64[(Lt+1)*14] or None)."""
+        n = len(reads)
+        tcat, toff = concat(templates)
+        rcat, roff = concat(reads)
+        ocat, ooff = concat(ops)
+        strands = _u8(strands)
+        tmpl_idx = np.ascontiguousarray(tmpl_idx, dtype=np.uint32)
+        lk = np.empty(n, dtype=np.float64)
+        tab = tab_off = None
+        if want_table:
+            sizes = np.array([(len(templates[int(t)]) + 1) * NUM_ROW for t in tmpl_idx], dtype=np.uint64)
+            tab_off = np.zeros(n + 1, dtype=np.uint64)
+            np.cumsum(sizes, out=tab_off[1:])
+            tab = np.empty(int(tab_off[-1]), dtype=np.float64)
+        self._check(lib().jtk_hmm_modtable_batch(
+            self._h, C.byref(fwd), C.byref(rev), n, len(templates), _ptr(tcat), _ptr(toff), _ptr(rcat), _ptr(roff),
+            _ptr(ocat), _ptr(ooff), _ptr(strands), _ptr(tmpl_idx), radius, _ptr(lk), _ptr(tab), _ptr(tab_off)))
+        tables = None
+        if want_table:
+            tables = [tab[int(tab_off[k]):int(tab_off[k + 1])] for k in range(n)]
+        return lk, tables
+
+    def likelihood_batch(self, fwd: HmmParams, rev: HmmParams, templates, reads, ops, strands, tmpl_idx, radius):
+        """jtk_hmm_likelihood_batch; ops=None selects the bootstrap guide."""
+        n = len(reads)
+        tcat, toff = concat(templates)
+        rcat, roff = concat(reads)
+        ocat = ooff = None
+        if ops is not None:
+            ocat, ooff = concat(ops)
+        strands = _u8(strands)
+        tmpl_idx = np.ascontiguousarray(tmpl_idx, dtype=np.uint32)
+        lk = np.empty(n, dtype=np.float64)
+        self._check(lib().jtk_hmm_likelihood_batch(
+            self._h, C.byref(fwd), C.byref(rev), n, len(templates), _ptr(tcat), _ptr(toff), _ptr(rcat), _ptr(roff),
+            _ptr(ocat), _ptr(ooff), _ptr(strands), _ptr(tmpl_idx), radius, _ptr(lk)))
+        return lk
+
+
+def band_cell_count(ops, Lt: int, Lr: int, radius: int) -> int:
+    ops = _u8(ops)
+    return int(lib().jtk_band_cell_count(_ptr(ops), len(ops), Lt, Lr, radius))

@@ -1,0 +1,117 @@
+"""Host-side mirror of the kiley::hmm call surface that ban-m/jtk uses on its per-chunk hot path.
+
+Same names, argument meaning and error behaviour as the reference call sites (the reference panics on
+failure -- `model_tune.rs:21`, `pseudo_mcmc.rs:100` -- here a `JtkError` is raised):
+
+  PairHiddenMarkovModel            fields as `haplotyper/src/model_tune.rs:50-62`
+  PairHiddenMarkovModelOnStrands   new / forward / reverse / default  (`model_tune.rs:32`, `pseudo_mcmc.rs:59-60`)
+  modification_table_antidiagonal  `haplotyper/src/local_clustering/pseudo_mcmc.rs:62-63`
+  likelihood_antidiagonal_bootstrap `haplotyper/src/likelihood_gains.rs:27-28`
+  NUM_ROW, COPY_SIZE               `pseudo_mcmc.rs:7,172`
+
+Every call goes through the C ABI of libjtkgpu.so into the sm_100a kernels; there is no CPU path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import COPY_SIZE, DEL_SIZE, NUM_ROW, Context, HmmParams, JtkError  # noqa: F401
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context()
+    return _default_ctx
+
+
+@dataclass
+class PairHiddenMarkovModel:
+    mat_mat: float = 0.97
+    mat_ins: float = 0.01
+    mat_del: float = 0.01
+    ins_mat: float = 0.97
+    ins_ins: float = 0.01
+    ins_del: float = 0.01
+    del_mat: float = 0.97
+    del_ins: float = 0.01
+    del_del: float = 0.01
+    mat_emit: List[float] = field(default_factory=lambda: [0.97 if r == q else 0.01 for r in range(4) for q in range(4)])
+    ins_emit: List[float] = field(default_factory=lambda: [0.25] * 20)
+
+    def to_c(self) -> HmmParams:
+        h = HmmParams()
+        for n in ("mat_mat", "mat_ins", "mat_del", "ins_mat", "ins_ins", "ins_del", "del_mat", "del_ins", "del_del"):
+            setattr(h, n, float(getattr(self, n)))
+        for k in range(16):
+            h.mat_emit[k] = float(self.mat_emit[k])
+        for k in range(20):
+            h.ins_emit[k] = float(self.ins_emit[k])
+        return h
+
+    @classmethod
+    def from_array(cls, a) -> "PairHiddenMarkovModel":
+        a = np.asarray(a, dtype=np.float64)
+        assert a.size == 45
+        return cls(*[float(x) for x in a[:9]], mat_emit=[float(x) for x in a[9:25]], ins_emit=[float(x) for x in a[25:45]])
+
+    def as_array(self) -> np.ndarray:
+        return np.array([self.mat_mat, self.mat_ins, self.mat_del, self.ins_mat, self.ins_ins, self.ins_del,
+                         self.del_mat, self.del_ins, self.del_del] + list(self.mat_emit) + list(self.ins_emit))
+
+    # ---- kiley-shaped single-pair calls (each is a batch of one) ------------------------------
+    def modification_table_antidiagonal(self, template, read, ops, band: int, ctx: Optional[Context] = None):
+        """-> (table float64[(Lt+1)*NUM_ROW] of absolute log-likelihoods, lk)."""
+        ctx = ctx or default_context()
+        c = self.to_c()
+        lk, tabs = ctx.modtable_batch(c, c, [template], [read], [ops], [1], [0], band)
+        return tabs[0], float(lk[0])
+
+    def likelihood_antidiagonal_bootstrap(self, template, read, band: int, ctx: Optional[Context] = None) -> float:
+        ctx = ctx or default_context()
+        c = self.to_c()
+        return float(ctx.likelihood_batch(c, c, [template], [read], None, [1], [0], band)[0])
+
+    def likelihood_antidiagonal(self, template, read, ops, band: int, ctx: Optional[Context] = None) -> float:
+        ctx = ctx or default_context()
+        c = self.to_c()
+        return float(ctx.likelihood_batch(c, c, [template], [read], [ops], [1], [0], band)[0])
+
+
+@dataclass
+class PairHiddenMarkovModelOnStrands:
+    _forward: PairHiddenMarkovModel = field(default_factory=PairHiddenMarkovModel)
+    _reverse: PairHiddenMarkovModel = field(default_factory=PairHiddenMarkovModel)
+
+    @classmethod
+    def new(cls, forward: PairHiddenMarkovModel, reverse: PairHiddenMarkovModel) -> "PairHiddenMarkovModelOnStrands":
+        return cls(forward, reverse)
+
+    @classmethod
+    def default(cls) -> "PairHiddenMarkovModelOnStrands":
+        return cls()
+
+    def forward(self) -> PairHiddenMarkovModel:
+        return self._forward
+
+    def reverse(self) -> PairHiddenMarkovModel:
+        return self._reverse
+
+    # ---- batched forms used by the haplotyper-side host code -----------------------------------
+    def modification_tables(self, template, reads: Sequence, ops: Sequence, strands: Sequence[bool], band: int,
+                            ctx: Optional[Context] = None):
+        """All reads of one chunk against its consensus: the loop of `pseudo_mcmc.rs:53-67` as one batch.
+        Returns (profiles float64[n, (Lt+1)*NUM_ROW] with lk already subtracted, lks)."""
+        ctx = ctx or default_context()
+        n = len(reads)
+        lk, tabs = ctx.modtable_batch(self._forward.to_c(), self._reverse.to_c(), [template], list(reads), list(ops),
+                                      np.asarray(strands, dtype=np.uint8), np.zeros(n, dtype=np.uint32), band)
+        prof = np.stack(tabs) - lk[:, None]
+        prof[np.stack(tabs) <= _lib.TABLE_NEG * 0.1] = _lib.TABLE_NEG
+        return prof, lk

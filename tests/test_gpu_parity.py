@@ -1,0 +1,174 @@
+"""GPU parity: the CUDA path (through the C ABI) against the f64 oracle on identical seeded inputs.
+
+Tolerances (stated per BASELINE.json north_star: |delta log-lik| <= 1e-3 relative; we hold much tighter):
+  lk                      |gpu - oracle| <= 2e-5 * |lk|  (fp32 forward, f64 exponent bookkeeping)
+  table - lk (per entry)  |gpu - oracle| <= 2e-3 absolute, and <= 1e-3 relative for |delta| >= 1
+  identity substitution   exactly 0
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from jtk_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+NEG = -1.0e9
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from jtk_b200 import _lib
+    c = _lib.Context()
+    yield c
+    c.close()
+
+
+def to_c(h):
+    from jtk_b200 import _lib
+    return _lib.HmmParams.from_buffer_copy(bytes(h))
+
+
+def random_hmm(seed):
+    rng = np.random.default_rng(seed)
+    a = np.empty(45)
+    for s in range(3):
+        a[3 * s:3 * s + 3] = rng.dirichlet([30, 2, 2]) * 0.99
+    for r in range(4):
+        e = rng.dirichlet([1, 1, 1, 1]) * 0.2
+        e[r] += 0.8
+        a[9 + 4 * r:13 + 4 * r] = e
+    for c in range(5):
+        a[25 + 4 * c:29 + 4 * c] = rng.dirichlet([3, 3, 3, 3])
+    return O.OrcHmm.from_array(a)
+
+
+def check_tables(gpu_tabs, gpu_lk, orc_tabs, orc_lk, templates, tmpl_idx):
+    worst = 0.0
+    for k in range(len(gpu_tabs)):
+        g = gpu_tabs[k].reshape(-1, 14)
+        o = orc_tabs[k].reshape(-1, 14)
+        assert abs(gpu_lk[k] - orc_lk[k]) <= 2e-5 * abs(orc_lk[k]) + 1e-6, (k, gpu_lk[k], orc_lk[k])
+        gneg, oneg = g < NEG, o < NEG
+        # impossible edits agree, except entries whose probability underflows fp32 (delta < -80)
+        dis = gneg != oneg
+        if dis.any():
+            od = o - orc_lk[k]
+            assert (od[dis & ~oneg] < -60).all() and not (dis & oneg).any(), (k, np.argwhere(dis)[:5])
+        ok = ~gneg & ~oneg
+        gd = g - gpu_lk[k]
+        od = o - orc_lk[k]
+        err = np.abs(gd - od)[ok]
+        tol = np.maximum(2e-3, 1e-3 * np.abs(od[ok]))
+        assert (err <= tol).all(), (k, float(err.max()), np.argwhere(np.abs(gd - od) * ok > 2e-3)[:5])
+        worst = max(worst, float(err.max()) if err.size else 0.0)
+        t = templates[int(tmpl_idx[k])]
+        code = np.searchsorted(synth.ACGT, t)
+        assert (gd[np.arange(len(t)), code] == 0.0).all()
+    return worst
+
+
+@pytest.mark.parametrize("L,err,R,model", [
+    (40, 0.15, 3, "default"), (40, 0.15, 14, "random"), (150, 0.1, 5, "random"), (150, 0.1, 30, "default"),
+    (300, 0.08, 10, "random"), (300, 0.2, 30, "random"), (120, 0.1, 50, "random"), (90, 0.0, 30, "default"),
+])
+def test_modtable_small_vs_oracle(ctx, L, err, R, model):
+    rng = np.random.default_rng(L * 1000 + R)
+    fwd = O.default_hmm() if model == "default" else random_hmm(1)
+    rev = O.default_hmm() if model == "default" else random_hmm(2)
+    templates = [synth.random_template(rng, L), synth.random_template(rng, L + 17)]
+    reads, ops, strands, tidx = [], [], [], []
+    for k in range(12):
+        ti = k % 2
+        q, o = synth.mutate_read(rng, templates[ti], err)
+        reads.append(q); ops.append(o); strands.append(k % 3 != 0); tidx.append(ti)
+    lk, tabs = ctx.modtable_batch(to_c(fwd), to_c(rev), templates, reads, ops, strands, tidx, R)
+    otabs, olk = O.modification_table_batch(fwd, rev, [templates[i] for i in tidx], reads, ops, strands, R)
+    check_tables(tabs, lk, otabs, olk, templates, tidx)
+
+
+def test_modtable_chunk_config0_vs_oracle(ctx):
+    """BASELINE.json configs[0]: 2 kbp chunk, 60 reads at ~8 % error, radius 30 (ONT)."""
+    d = synth.diploid_chunk(7)
+    fwd, rev = random_hmm(11), random_hmm(12)
+    n = 16  # the oracle needs ~30 ms per pair
+    reads, ops, strands = d["reads"][:n], d["ops"][:n], d["strands"][:n]
+    lk, tabs = ctx.modtable_batch(to_c(fwd), to_c(rev), [d["template"]], reads, ops, strands, np.zeros(n, np.uint32), 30)
+    otabs, olk = O.modification_table_batch(fwd, rev, [d["template"]] * n, reads, ops, strands, 30, n_threads=4)
+    worst = check_tables(tabs, lk, otabs, olk, [d["template"]], np.zeros(n, np.uint32))
+    assert worst < 2e-3
+
+
+def test_likelihood_guided_and_bootstrap(ctx):
+    rng = np.random.default_rng(77)
+    fwd, rev = random_hmm(5), random_hmm(6)
+    templates, reads, ops, strands = [], [], [], []
+    for k in range(40):
+        t = synth.random_template(rng, 103)
+        q, o = synth.mutate_read(rng, t, 0.1)
+        templates.append(t); reads.append(q); ops.append(o); strands.append(k % 2 == 0)
+    tidx = np.arange(40, dtype=np.uint32)
+    for R in (10, 25):
+        lk = ctx.likelihood_batch(to_c(fwd), to_c(rev), templates, reads, ops, strands, tidx, R)
+        lkb = ctx.likelihood_batch(to_c(fwd), to_c(rev), templates, reads, None, strands, tidx, R)
+        for k in range(40):
+            h = fwd if strands[k] else rev
+            want = O.likelihood(h, templates[k], reads[k], ops[k], R)
+            wantb = O.likelihood_bootstrap(h, templates[k], reads[k], R)
+            assert abs(lk[k] - want) <= 2e-5 * abs(want)
+            assert abs(lkb[k] - wantb) <= 2e-5 * abs(wantb)
+
+
+def test_ragged_tiny_and_long_indel(ctx):
+    """Edge cases the domain has: very short / very unequal sequences, a long insertion run (forces the
+    rescale path), reads that are pure deletions of the template."""
+    fwd = rev = O.default_hmm()
+    cases = []
+    for t, q in ((b"ACGTACGTAC", b"AC"), (b"AC", b"ACGTTTTTGA"), (b"A", b"A"), (b"A", b"C"), (b"ACGTTGCA", b"ACGTTGCA")):
+        t = np.frombuffer(t, np.uint8); q = np.frombuffer(q, np.uint8)
+        cases.append((t, q, O.edit_ops(t, q, 20)))
+    rng = np.random.default_rng(5)
+    t = synth.random_template(rng, 400)
+    ins = synth.random_template(rng, 25)
+    q = np.concatenate([t[:200], ins, t[200:]])
+    o = np.concatenate([np.zeros(200, np.uint8), np.full(25, 2, np.uint8), np.zeros(200, np.uint8)])
+    cases.append((t, q, o))
+    q2 = np.concatenate([t[:150], t[180:]])
+    o2 = np.concatenate([np.zeros(150, np.uint8), np.full(30, 3, np.uint8), np.zeros(220, np.uint8)])
+    cases.append((t, q2, o2))
+    templates = [c[0] for c in cases]
+    reads = [c[1] for c in cases]
+    ops = [c[2] for c in cases]
+    n = len(cases)
+    lk, tabs = ctx.modtable_batch(to_c(fwd), to_c(rev), templates, reads, ops, np.ones(n, np.uint8), np.arange(n), 30)
+    otabs, olk = O.modification_table_batch(fwd, rev, templates, reads, ops, np.ones(n, np.uint8), 30)
+    check_tables(tabs, lk, otabs, olk, templates, np.arange(n))
+
+
+def test_bad_ops_and_radius_are_rejected(ctx):
+    from jtk_b200 import _lib
+    h = to_c(O.default_hmm())
+    t = np.frombuffer(b"ACGT", np.uint8)
+    with pytest.raises(_lib.JtkError) as e:
+        ctx.modtable_batch(h, h, [t], [t], [np.zeros(3, np.uint8)], [1], [0], 5)
+    assert e.value.code == -1
+    with pytest.raises(_lib.JtkError):
+        ctx.modtable_batch(h, h, [t], [t], [np.zeros(4, np.uint8)], [1], [0], 500)
+    assert ctx.modtable_batch(h, h, [t], [], [], [], [], 5)[0].size == 0
+
+
+def test_kiley_shaped_single_call(ctx):
+    """hmm.PairHiddenMarkovModel mirrors the kiley method the reference calls (pseudo_mcmc.rs:62-63)."""
+    from jtk_b200 import hmm
+    rng = np.random.default_rng(2)
+    t = synth.random_template(rng, 200)
+    q, o = synth.mutate_read(rng, t, 0.1)
+    m = hmm.PairHiddenMarkovModel()
+    table, lk = m.modification_table_antidiagonal(t, q, o, 20, ctx=ctx)
+    otab, olk = O.modification_table(O.default_hmm(), t, q, o, 20)
+    assert table.shape == ((len(t) + 1) * hmm.NUM_ROW,)
+    assert abs(lk - olk) < 2e-5 * abs(olk)
+    ok = otab > NEG
+    assert np.max(np.abs((table - lk) - (otab - olk))[ok]) < 2e-3
+    lkb = m.likelihood_antidiagonal_bootstrap(t, q, 20, ctx=ctx)
+    assert abs(lkb - O.likelihood_bootstrap(O.default_hmm(), t, q, 20)) < 2e-5 * abs(olk)
