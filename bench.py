@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- pair-HMM modification-table throughput of the per-chunk hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+A step is one pass of the hot path over one batch: every read of every chunk of BASELINE.json configs[1]
+(mock diploid 200 kbp region -> 80 chunks of 2 kbp x 60 ONT-like reads at 8 % error, radius 30) is scored
+against its chunk consensus by the banded pair-HMM forward/backward, the 14-row modification table
+(table - lk) is written to HBM, and the per-column statistics that `filter_profiles` consumes
+(haplotyper/src/local_clustering/pseudo_mcmc.rs:426-474) are reduced on the device.
+
+value   GCUPS with the batch already resident in HBM (kernels only).  One cell update = all three states of
+        one in-band DP cell in one direction; a modification-table job is 2*C cell updates;
+        checkpoint / reduction work is not credited.
+e2e     the same metric through the C ABI with HOST buffers: encode + H2D of the step's inputs, kernels, D2H of
+        the likelihoods and the per-column statistics, all inside the timed region.
+Chunks are independent: rank r processes its own 80 chunks (weak scaling), no collective on the data path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_CELL = 17.0  # 3 mul + 6 FMA + 2 emission mul per cell update
+RADIUS = 30
+POS_THR = 1e-5
+# Gains fixture (expected log-lik gain per (DiffType, homopolymer length)): estimate_gain_default output is an
+# input fixture here; rows Subst, Del, Ins; MIN_REQ_FRACTION 0.5 (pseudo_mcmc.rs:140)
+GAINS_EXPECTED = np.array([[4.0, 4.0, 4.0], [3.0, 2.0, 1.5], [3.0, 2.0, 1.5]], dtype=np.float32)
+
+
+def make_workload(rank: int, n_chunks: int, n_reads: int, length: int):
+    from jtk_b200 import synth
+    chunks = synth.diploid_region(20261017 + rank, n_chunks, length=length, n_reads=n_reads, error_rate=0.08)
+    templates = [c["template"] for c in chunks]
+    reads = [r for c in chunks for r in c["reads"]]
+    ops = [o for c in chunks for o in c["ops"]]
+    strands = np.concatenate([c["strands"] for c in chunks])
+    tidx = np.repeat(np.arange(n_chunks, dtype=np.uint32), [len(c["reads"]) for c in chunks])
+    return templates, reads, ops, strands, tidx
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline_run(templates, reads, ops, strands, tidx, n_pairs, threads):
+    """Oracle (f64 restatement, kind 'port') over the first n_pairs pairs, `threads` OS threads over pairs
+    (the reference's rayon decomposition).  Returns (seconds, cell updates)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    from jtk_b200 import _lib
+    h = O.default_hmm()
+    tl = [templates[int(tidx[k])] for k in range(n_pairs)]
+    t0 = time.perf_counter()
+    O.modification_table_batch(h, h, tl, reads[:n_pairs], ops[:n_pairs], strands[:n_pairs], RADIUS,
+                               n_threads=threads, want_tables=True)
+    dt = time.perf_counter() - t0
+    cells = sum(2 * _lib.band_cell_count(ops[k], len(tl[k]), len(reads[k]), RADIUS) for k in range(n_pairs))
+    return dt, cells
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  kiley (the crate that
+    holds the arithmetic) is absent and there is no Rust toolchain, so this is the oracle port (kind 'port')."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_chunks_sample = 2
+    templates, reads, ops, strands, tidx = make_workload(0, n_chunks_sample, args.reads, args.length)
+    n_pairs = len(reads)
+    for _ in range(args.warmup):
+        cpu_baseline_run(templates, reads, ops, strands, tidx, min(n_pairs, 2 * threads), threads)
+    t = 0.0
+    cells = 0
+    for _ in range(args.steps):
+        dt, c = cpu_baseline_run(templates, reads, ops, strands, tidx, n_pairs, threads)
+        t += dt
+        cells += c
+    gcups = cells / t / 1e9
+    sample = f"{n_chunks_sample} chunks x {args.reads} reads ({n_pairs} pairs) of the same workload per step"
+    line = {
+        "impl": "reference", "metric": "pair-HMM modification-table GCUPS", "value": gcups, "unit": "GCUPS",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"BASELINE.json configs[1]: mock diploid {args.chunks * 2.5:.0f} kbp region, {args.chunks} chunks x "
+                        f"{args.reads} ONT-like reads ({args.length} bp, 8% error), radius {RADIUS}, 14-row table + column stats, per GPU",
+            "chunks_per_gpu": args.chunks, "reads_per_chunk": args.reads, "chunk_len": args.length, "radius": RADIUS,
+            "rows": 14, "parallelism": "chunks sharded over ranks, no collective",
+            "l2": "no explicit flush: each step streams ~10 GB of forward rows + 0.5 GB of profiles per GPU (>> 126 MB L2), "
+                  "so the 25 MB of inputs are evicted between steps"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chunks", type=int, default=80)
+    ap.add_argument("--reads", type=int, default=60)
+    ap.add_argument("--length", type=int, default=2000)
+    ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="pairs in the cpu_baseline sample (0: auto)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from jtk_b200 import _lib, build
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: jtk_b200 has no CPU fallback")
+    build.build()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = _lib.Context(local_rank)
+    fwd = _lib.HmmParams.from_buffer_copy(_default_params())
+    rev = fwd
+    min_req = GAINS_EXPECTED * 0.5
+
+    templates, reads, ops, strands, tidx = make_workload(rank, args.chunks, args.reads, args.length)
+    packed = _lib.pack_inputs(templates, reads, ops, strands, tidx)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg (value) ------------------------------------------------------------
+    batch = ctx.batch(templates, reads, ops, strands, tidx, RADIUS)
+    cells = batch.cell_updates
+
+    def step_resident(rows=14):
+        batch.modtable(fwd, rev, rows)
+        batch.colstats(min_req, POS_THR, fetch=False)
+
+    for _ in range(args.warmup):
+        step_resident()
+    batch.sync()
+    ctx.kernel_times()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    l0 = ctx.launch_count
+    ctx.timer_start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_resident()
+    dev_ms = ctx.timer_stop()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = ctx.launch_count - l0
+    ktimes = ctx.kernel_times()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # 9-row (clustering rows only) variant, reported as an extra
+    for _ in range(2):
+        step_resident(9)
+    batch.sync()
+    ctx.timer_start()
+    for _ in range(max(3, args.steps // 4)):
+        step_resident(9)
+    ms9 = ctx.timer_stop() / max(3, args.steps // 4)
+    ctx.kernel_times()
+
+    # ---- end-to-end leg (host buffers in, statistics out) ---------------------------------------
+    def step_e2e():
+        b = _lib.Batch(ctx, templates, reads, ops, strands, tidx, RADIUS, packed=packed)
+        b.modtable(fwd, rev, 14)
+        st = b.colstats(min_req, POS_THR, fetch=True)
+        lk = b.lk()
+        h2d = b.h2d_bytes
+        b.close()
+        return h2d, st.nbytes + lk.nbytes
+
+    for _ in range(2):
+        h2d_bytes, d2h_bytes = step_e2e()
+    barrier()
+    t1 = time.perf_counter()
+    e2e_steps = max(3, args.steps // 2)
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_ms = (time.perf_counter() - t1) * 1e3 / e2e_steps
+
+    # ---- reduce over ranks ------------------------------------------------------------------------
+    step_ms = dev_ms / args.steps
+    tot_cells = float(cells)
+    if world > 1:
+        t = torch.tensor([step_ms, e2e_ms, wall_ms / args.steps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms, e2e_ms, wall_step = [float(x) for x in t.tolist()]
+        c = torch.tensor([tot_cells], device="cuda", dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        tot_cells = float(c.item())
+    else:
+        wall_step = wall_ms / args.steps
+    value = tot_cells / (step_ms * 1e-3) / 1e9
+    e2e_value = tot_cells / (e2e_ms * 1e-3) / 1e9
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        ffma, ffma2 = ctx.measure_fp32_peak()
+        k_ms = float(np.mean(ktimes)) if len(ktimes) else step_ms
+        ach_tflops = cells * FLOPS_PER_CELL / (k_ms * 1e-3) / 1e12
+        prof_bytes = float(sum((len(templates[int(t)]) + 1) * 14 * 4 for t in tidx))
+        in_bytes = float(batch.h2d_bytes)
+        roof = {"bound": "fp32", "kernel": "modtable_kernel<2,14>", "achieved": ach_tflops, "peak": ffma,
+                "unit": "TFLOP/s", "frac": ach_tflops / ffma if ffma else None,
+                "peak_source": "measured in this run: register-resident fma.rn.f32 loop on all SMs "
+                               "(MEASURED_PEAKS.json holds only HBM and bf16 figures)",
+                "peak_ffma2": ffma2, "flops_per_cell_update": FLOPS_PER_CELL,
+                "cell_updates_per_launch": cells, "kernel_ms": k_ms, "gcups_kernel": cells / (k_ms * 1e-3) / 1e9,
+                "traffic": None,
+                "hbm": {"algorithmic_bytes_per_launch": prof_bytes + in_bytes,
+                        "achieved_gbs": (prof_bytes + in_bytes) / (k_ms * 1e-3) / 1e9,
+                        "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src}}
+        # cpu baseline: bounded sample on this box's host cores
+        threads = os.cpu_count() or 1
+        n_sample = args.cpu_sample_pairs or min(len(reads), max(60, 30 * threads))
+        cpu_s, cpu_cells = cpu_baseline_run(templates, reads, ops, strands, tidx, n_sample, threads)
+        cpu = {"value": cpu_cells / cpu_s / 1e9, "unit": "GCUPS", "cores": threads, "kind": "port",
+               "sample": f"first {n_sample} pairs of rank 0's workload, f64 oracle, {threads} threads over pairs, {cpu_s:.1f} s"}
+        line = {
+            "metric": "pair-HMM modification-table GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args),
+            "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+            "extra": {"chunks_per_s": world * args.chunks / (step_ms * 1e-3),
+                      "pairs_per_s": world * len(reads) / (step_ms * 1e-3),
+                      "wall_ms_per_step": wall_step,
+                      "rows9": {"ms_per_step": ms9, "gcups": cells / (ms9 * 1e-3) / 1e9,
+                                "chunks_per_s": args.chunks / (ms9 * 1e-3), "note": "rank 0 only"}},
+        }
+        print(json.dumps(line), flush=True)
+    batch.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _default_params() -> bytes:
+    """HMMParam::default() (definitions/src/lib.rs:128-147) as the 45 doubles of jtk_hmm_params."""
+    a = [0.97, 0.01, 0.01] * 3 + [0.97 if r == q else 0.01 for r in range(4) for q in range(4)] + [0.25] * 20
+    return np.array(a, dtype=np.float64).tobytes()
+
+
+if __name__ == "__main__":
+    main()

@@ -63,6 +63,15 @@ int jtk_hmm_del_size(void);
 uint64_t jtk_ctx_launch_count(const jtk_ctx *ctx);
 /* device time (ms, CUDA events on the ctx stream) of the dominant kernel in the last batch call */
 float jtk_ctx_last_kernel_ms(const jtk_ctx *ctx);
+/* measurement helpers (bench.py): bracket a region of work on the ctx stream with CUDA events */
+int jtk_ctx_timer_start(jtk_ctx *ctx);
+int jtk_ctx_timer_stop(jtk_ctx *ctx, float *ms); /* synchronises the stream */
+/* per-launch device times (ms) of the pair-HMM kernels launched since the last call (ring of 256);
+ * synchronises the stream; returns the number written (<= cap) or a negative error */
+int jtk_ctx_kernel_times(jtk_ctx *ctx, float *ms, int cap);
+/* FP32 FMA peak of this device measured with a register-resident FFMA loop on every SM (TFLOP/s, 2 flops/FMA):
+ * scalar fma.rn.f32 and packed fma.rn.f32x2 (the roofline denominators SURVEY.md 8d asks for) */
+int jtk_ctx_measure_fp32_peak(jtk_ctx *ctx, double *tflops_ffma, double *tflops_ffma2);
 
 /* ---- level 1: kiley-shaped batch calls --------------------------------------------------------- */
 /*
@@ -93,6 +102,58 @@ int jtk_hmm_likelihood_batch(jtk_ctx *ctx, const jtk_hmm_params *fwd, const jtk_
                              const uint8_t *read_concat, const uint32_t *read_off,
                              const uint8_t *ops_concat, const uint32_t *ops_off,
                              const uint8_t *strand, const uint32_t *tmpl_idx, int radius, double *out_lk);
+
+
+/* ---- level 2: haplotyper-shaped, device-resident chunk batches ---------------------------------- */
+/*
+ * A batch is a set of chunks (templates) with their reads, resident in HBM.  It replaces the per-read loop
+ * of pseudo_mcmc::modification_table (haplotyper/src/local_clustering/pseudo_mcmc.rs:45-68) for many chunks
+ * at once: profiles (table - lk, fp32) stay on the device and only per-column statistics or the selected
+ * probe columns cross PCIe (SURVEY.md section 7 "PCIe").
+ */
+typedef struct jtk_batch jtk_batch;
+
+/* Encode, upload.  Same input arrays as jtk_hmm_modtable_batch; ops are required. */
+int jtk_batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_concat, const uint32_t *tmpl_off,
+                     const uint8_t *read_concat, const uint32_t *read_off,
+                     const uint8_t *ops_concat, const uint32_t *ops_off,
+                     const uint8_t *strand, const uint32_t *tmpl_idx, int radius, jtk_batch **out);
+void jtk_batch_destroy(jtk_batch *b);
+/* sum over pairs of 2*C: forward + backward cell updates of one modification-table pass */
+uint64_t jtk_batch_cell_updates(const jtk_batch *b);
+/* bytes jtk_batch_create copied host->device */
+uint64_t jtk_batch_h2d_bytes(const jtk_batch *b);
+
+/* Run forward + backward + table reduction for every pair.  rows = 14 (all) or 9 (substitution, insertion
+ * and one-base deletion rows only: the rows filter_profiles reads, pseudo_mcmc.rs:447; other rows are
+ * written as impossible).  Profiles and likelihoods stay on the device.  Asynchronous w.r.t. the host
+ * until a fetch call or jtk_batch_sync. */
+int jtk_batch_modtable(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev, int rows);
+int jtk_batch_sync(jtk_batch *b);
+int jtk_batch_fetch_lk(jtk_batch *b, double *out_lk /* n_pairs */);
+/* one pair's profile (table - lk), (Lt+1)*JTK_NUM_ROW floats; impossible edits are <= -1e9 */
+int jtk_batch_fetch_profile(jtk_batch *b, int pair, float *out);
+
+/*
+ * Per-column statistics of one chunk's profiles after compress_small_gains (pseudo_mcmc.rs:141-165):
+ * an entry x of read p is zeroed when |x| < min_req[type][min(homop,H)-1] (type 0 Subst, 1 Del, 2 Ins as
+ * likelihood_gains::DiffType; min_req = Gains::expected * MIN_REQ_FRACTION), then
+ *   sum, count  over entries > pos_thr                                   (column_sum, pseudo_mcmc.rs:577-588)
+ *   sc[strand][positive]  counts over entries with |x| > 1e-4           (is_explainable_by_strandedness, :314-339)
+ */
+typedef struct {
+    double sum;
+    int32_t count;
+    uint16_t sc[4]; /* [strand*2 + is_sign_positive] */
+    int32_t pad_;
+} jtk_colstat;
+/* out receives, for template t at out + stat_off[t], (Lt+1)*JTK_NUM_ROW entries.  out == NULL: compute on the
+ * device only (no device->host copy, no synchronisation). */
+int jtk_batch_colstats(jtk_batch *b, const float *min_req /* 3*H */, int H, float pos_thr,
+                       jtk_colstat *out, const uint64_t *stat_off);
+/* compressed profile values of the reads of template t at flat positions cols[0..D): out[n_reads_t * D],
+ * reads in batch order (filter_by, pseudo_mcmc.rs:70-75) */
+int jtk_batch_gather(jtk_batch *b, int tmpl, const float *min_req, int H, const uint32_t *cols, int D, double *out);
 
 /* in-band cell count C = sum_d w(d) of one pair (SURVEY.md section 8d work unit); <0 if ops are invalid */
 int64_t jtk_band_cell_count(const uint8_t *ops, int n_ops, int Lt, int Lr, int radius);

@@ -21,8 +21,14 @@ TABLE_NEG = -1.0e10
 EXPORTS = [
     "jtk_ctx_create", "jtk_ctx_destroy", "jtk_last_error", "jtk_hmm_num_row", "jtk_hmm_copy_size",
     "jtk_hmm_del_size", "jtk_ctx_launch_count", "jtk_ctx_last_kernel_ms", "jtk_hmm_modtable_batch",
-    "jtk_hmm_likelihood_batch", "jtk_band_cell_count",
+    "jtk_hmm_likelihood_batch", "jtk_band_cell_count", "jtk_batch_create", "jtk_batch_destroy",
+    "jtk_batch_cell_updates", "jtk_batch_h2d_bytes", "jtk_batch_modtable", "jtk_batch_sync", "jtk_batch_fetch_lk",
+    "jtk_batch_fetch_profile", "jtk_batch_colstats", "jtk_batch_gather", "jtk_ctx_timer_start", "jtk_ctx_timer_stop",
+    "jtk_ctx_kernel_times", "jtk_ctx_measure_fp32_peak",
 ]
+
+COLSTAT_DTYPE = np.dtype([("sum", "<f8"), ("count", "<i4"), ("sc", "<u2", (4,)), ("pad", "<i4")])
+assert COLSTAT_DTYPE.itemsize == 24
 
 
 class JtkError(RuntimeError):
@@ -66,6 +72,24 @@ def lib() -> C.CDLL:
     L.jtk_hmm_likelihood_batch.argtypes = batch
     L.jtk_band_cell_count.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
     L.jtk_band_cell_count.restype = C.c_int64
+    L.jtk_batch_create.argtypes = [C.c_void_p, C.c_int, C.c_int, vp, u32p, vp, u32p, vp, u32p, vp, u32p, C.c_int,
+                                   C.POINTER(C.c_void_p)]
+    L.jtk_batch_destroy.argtypes = [C.c_void_p]
+    L.jtk_batch_destroy.restype = None
+    L.jtk_batch_cell_updates.argtypes = [C.c_void_p]
+    L.jtk_batch_cell_updates.restype = C.c_uint64
+    L.jtk_batch_h2d_bytes.argtypes = [C.c_void_p]
+    L.jtk_batch_h2d_bytes.restype = C.c_uint64
+    L.jtk_batch_modtable.argtypes = [C.c_void_p, C.POINTER(HmmParams), C.POINTER(HmmParams), C.c_int]
+    L.jtk_batch_sync.argtypes = [C.c_void_p]
+    L.jtk_batch_fetch_lk.argtypes = [C.c_void_p, vp]
+    L.jtk_batch_fetch_profile.argtypes = [C.c_void_p, C.c_int, vp]
+    L.jtk_batch_colstats.argtypes = [C.c_void_p, vp, C.c_int, C.c_float, vp, u64p]
+    L.jtk_batch_gather.argtypes = [C.c_void_p, C.c_int, vp, C.c_int, u32p, C.c_int, vp]
+    L.jtk_ctx_timer_start.argtypes = [C.c_void_p]
+    L.jtk_ctx_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.jtk_ctx_kernel_times.argtypes = [C.c_void_p, vp, C.c_int]
+    L.jtk_ctx_measure_fp32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -123,6 +147,29 @@ class Context:
     def last_kernel_ms(self) -> float:
         return float(lib().jtk_ctx_last_kernel_ms(self._h))
 
+    def timer_start(self):
+        self._check(lib().jtk_ctx_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self._check(lib().jtk_ctx_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def kernel_times(self) -> np.ndarray:
+        buf = np.zeros(256, dtype=np.float32)
+        n = lib().jtk_ctx_kernel_times(self._h, _ptr(buf), 256)
+        if n < 0:
+            self._check(n)
+        return buf[:n].copy()
+
+    def measure_fp32_peak(self):
+        a, b = C.c_double(), C.c_double()
+        self._check(lib().jtk_ctx_measure_fp32_peak(self._h, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
+
+    def batch(self, templates, reads, ops, strands, tmpl_idx, radius) -> "Batch":
+        return Batch(self, templates, reads, ops, strands, tmpl_idx, radius)
+
     # ---- level 1 -------------------------------------------------------------------------------
     def modtable_batch(self, fwd: HmmParams, rev: HmmParams, templates, reads, ops, strands, tmpl_idx, radius,
                        want_table=True):
@@ -163,6 +210,88 @@ class Context:
             self._h, C.byref(fwd), C.byref(rev), n, len(templates), _ptr(tcat), _ptr(toff), _ptr(rcat), _ptr(roff),
             _ptr(ocat), _ptr(ooff), _ptr(strands), _ptr(tmpl_idx), radius, _ptr(lk)))
         return lk
+
+
+class Batch:
+    """jtk_batch: chunks + reads resident in HBM (level 2 of include/jtk_gpu.h)."""
+
+    def __init__(self, ctx: Context, templates, reads, ops, strands, tmpl_idx, radius, packed=None):
+        self.ctx = ctx
+        self.n_pairs = len(reads)
+        self.n_tmpl = len(templates)
+        self.tmpl_len = np.array([len(t) for t in templates], dtype=np.int64)
+        self.tmpl_idx = np.ascontiguousarray(tmpl_idx, dtype=np.uint32)
+        self.packed = packed if packed is not None else pack_inputs(templates, reads, ops, strands, tmpl_idx)
+        tcat, toff, rcat, roff, ocat, ooff, st, ti = self.packed
+        self._h = C.c_void_p()
+        ctx._check(lib().jtk_batch_create(ctx._h, self.n_pairs, self.n_tmpl, _ptr(tcat), _ptr(toff), _ptr(rcat),
+                                          _ptr(roff), _ptr(ocat), _ptr(ooff), _ptr(st), _ptr(ti), radius,
+                                          C.byref(self._h)))
+        sizes = (self.tmpl_len + 1) * NUM_ROW
+        self.stat_off = np.zeros(self.n_tmpl + 1, dtype=np.uint64)
+        np.cumsum(sizes, out=self.stat_off[1:])
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().jtk_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def cell_updates(self) -> int:
+        return int(lib().jtk_batch_cell_updates(self._h))
+
+    @property
+    def h2d_bytes(self) -> int:
+        return int(lib().jtk_batch_h2d_bytes(self._h))
+
+    def modtable(self, fwd: HmmParams, rev: HmmParams, rows: int = 14):
+        self.ctx._check(lib().jtk_batch_modtable(self._h, C.byref(fwd), C.byref(rev), rows))
+
+    def sync(self):
+        self.ctx._check(lib().jtk_batch_sync(self._h))
+
+    def lk(self) -> np.ndarray:
+        out = np.empty(self.n_pairs, dtype=np.float64)
+        self.ctx._check(lib().jtk_batch_fetch_lk(self._h, _ptr(out)))
+        return out
+
+    def profile(self, pair: int) -> np.ndarray:
+        t = int(self.tmpl_idx[pair])
+        out = np.empty((int(self.tmpl_len[t]) + 1) * NUM_ROW, dtype=np.float32)
+        self.ctx._check(lib().jtk_batch_fetch_profile(self._h, pair, _ptr(out)))
+        return out
+
+    def colstats(self, min_req: np.ndarray, pos_thr: float = 1e-5, fetch: bool = True):
+        """min_req: float32[3, H] (rows Subst, Del, Ins).  Returns a structured array (COLSTAT_DTYPE) with all
+        templates concatenated (template t at self.stat_off[t]), or None when fetch=False."""
+        mr = np.ascontiguousarray(min_req, dtype=np.float32)
+        assert mr.ndim == 2 and mr.shape[0] == 3
+        out = np.empty(int(self.stat_off[-1]), dtype=COLSTAT_DTYPE) if fetch else None
+        self.ctx._check(lib().jtk_batch_colstats(self._h, _ptr(mr), mr.shape[1], pos_thr, _ptr(out),
+                                                 _ptr(self.stat_off)))
+        return out
+
+    def gather(self, tmpl: int, min_req: np.ndarray, cols) -> np.ndarray:
+        mr = np.ascontiguousarray(min_req, dtype=np.float32)
+        cols = np.ascontiguousarray(cols, dtype=np.uint32)
+        n_reads = int((self.tmpl_idx == tmpl).sum())
+        out = np.zeros((n_reads, len(cols)), dtype=np.float64)
+        self.ctx._check(lib().jtk_batch_gather(self._h, tmpl, _ptr(mr), mr.shape[1], _ptr(cols), len(cols), _ptr(out)))
+        return out
+
+
+def pack_inputs(templates, reads, ops, strands, tmpl_idx):
+    """Concatenate host inputs into the flat arrays the C ABI takes."""
+    tcat, toff = concat(templates)
+    rcat, roff = concat(reads)
+    ocat, ooff = concat(ops)
+    return (tcat, toff, rcat, roff, ocat, ooff, _u8(strands), np.ascontiguousarray(tmpl_idx, dtype=np.uint32))
 
 
 def band_cell_count(ops, Lt: int, Lr: int, radius: int) -> int:

@@ -15,6 +15,7 @@ int cols_per_lane_for_radius(int radius);
 cudaError_t launch_modtable(const KParams &p, int C, int grid, cudaStream_t st);
 cudaError_t launch_likelihood(const KParams &p, int C, int grid, cudaStream_t st);
 int warps_per_cta();
+cudaError_t launch_fp32_peak(int mode, int blocks, int threads, int iters, float *sink, cudaStream_t st);
 } // namespace jtk
 
 using namespace jtk;
@@ -121,26 +122,29 @@ struct jtk_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
+    static constexpr int kRing = 256;
+    cudaEvent_t ring0[kRing] = {}, ring1[kRing] = {};
+    int ring_n = 0;
     std::string err;
     uint64_t launches = 0;
     float last_ms = 0.f;
+    bool timing_pending = false;
     // device buffers
-    DevBuf<DevPair> d_pairs;
-    DevBuf<uint8_t> d_codes;
-    DevBuf<uint32_t> d_bits;
     DevBuf<float> d_models;
-    DevBuf<float2> d_frows;
+    DevBuf<float2> d_frows;   // per-warp forward rows (scratch shared by all batches of this ctx)
     DevBuf<int32_t> d_kf;
-    DevBuf<float> d_delta;
-    DevBuf<double> d_lk;
     DevBuf<int> d_counter;
+    DevBuf<float> d_minreq;
+    DevBuf<uint32_t> d_cols;
+    DevBuf<double> d_gather;
     // pinned host staging
     PinBuf<DevPair> h_pairs;
     PinBuf<uint8_t> h_codes;
     PinBuf<uint32_t> h_bits;
     PinBuf<float> h_delta;
     PinBuf<double> h_lk;
+    PinBuf<uint8_t> h_homop;
     // host scratch
     std::vector<uint32_t> tmpl_code_off;
     std::vector<uint8_t> tmp_ops;
@@ -182,7 +186,8 @@ int jtk_ctx_create(int device, size_t workspace_bytes, jtk_ctx **out) {
     ctx->device = device;
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) {
+        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->tm0)) != cudaSuccess || (e = cudaEventCreate(&ctx->tm1)) != cudaSuccess) {
         g_create_error = cudaGetErrorString(e);
         delete ctx;
         return JTK_ECUDA;
@@ -194,9 +199,13 @@ int jtk_ctx_create(int device, size_t workspace_bytes, jtk_ctx **out) {
 void jtk_ctx_destroy(jtk_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    ctx->d_pairs.release(); ctx->d_codes.release(); ctx->d_bits.release(); ctx->d_models.release();
-    ctx->d_frows.release(); ctx->d_kf.release(); ctx->d_delta.release(); ctx->d_lk.release(); ctx->d_counter.release();
+    ctx->d_models.release(); ctx->d_frows.release(); ctx->d_kf.release(); ctx->d_counter.release();
+    ctx->d_minreq.release(); ctx->d_cols.release(); ctx->d_gather.release();
     ctx->h_pairs.release(); ctx->h_codes.release(); ctx->h_bits.release(); ctx->h_delta.release(); ctx->h_lk.release();
+    ctx->h_homop.release();
+    for (int k = 0; k < jtk_ctx::kRing; k++) { if (ctx->ring0[k]) cudaEventDestroy(ctx->ring0[k]); if (ctx->ring1[k]) cudaEventDestroy(ctx->ring1[k]); }
+    if (ctx->tm0) cudaEventDestroy(ctx->tm0);
+    if (ctx->tm1) cudaEventDestroy(ctx->tm1);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -230,61 +239,115 @@ int64_t jtk_band_cell_count(const uint8_t *ops, int n_ops, int Lt, int Lr, int r
 
 } // extern "C"
 
-namespace {
 
-struct BatchShape {
-    int max_nd = 0;
-    uint64_t table_floats = 0;
+// ---------------------------------------------------------------------------------------------------
+// device-resident batch
+// ---------------------------------------------------------------------------------------------------
+struct jtk_batch {
+    jtk_ctx *ctx = nullptr;
+    int n_pairs = 0, n_tmpl = 0, radius = 0, C = 0, max_nd = 0, max_lt = 0;
+    uint64_t table_floats = 0, cell_updates = 0, h2d_bytes = 0;
+    bool has_profiles = false;
+    std::vector<DevPair> pairs;           // host copy
+    std::vector<uint32_t> tmpl_len;
+    std::vector<uint32_t> tp_start, tp_ids; // CSR template -> pairs
+    std::vector<uint32_t> homop_off;
+    DevBuf<DevPair> d_pairs;
+    DevBuf<uint8_t> d_codes;
+    DevBuf<uint32_t> d_bits;
+    DevBuf<float> d_delta;
+    DevBuf<double> d_lk;
+    DevBuf<uint32_t> d_tp_start, d_tp_ids, d_tmpl_len, d_homop_off;
+    DevBuf<uint8_t> d_homop;
+    DevBuf<unsigned long long> d_stat_off;
+    DevBuf<jtk_colstat> d_stats;
+    void release() {
+        d_pairs.release(); d_codes.release(); d_bits.release(); d_delta.release(); d_lk.release();
+        d_tp_start.release(); d_tp_ids.release(); d_tmpl_len.release(); d_homop_off.release(); d_homop.release();
+        d_stat_off.release(); d_stats.release();
+    }
 };
 
-// Encode templates / reads / guide paths into the device layout of phmm_dev.cuh (host staging buffers).
-int pack_batch(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_concat, const uint32_t *tmpl_off,
+namespace {
+
+// Encode templates / reads / guide paths into the device layout of phmm_dev.cuh (pinned staging of ctx).
+int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uint32_t *tmpl_off,
                const uint8_t *read_concat, const uint32_t *read_off, const uint8_t *ops_concat,
-               const uint32_t *ops_off, const uint8_t *strand, const uint32_t *tmpl_idx, int radius,
-               bool want_table, BatchShape &shape, size_t &code_bytes, size_t &bit_words) {
-    // sizes
-    size_t cb = 0;
+               const uint32_t *ops_off, const uint8_t *strand, const uint32_t *tmpl_idx, size_t &code_bytes,
+               size_t &bit_words, size_t &homop_bytes) {
+    const int n_pairs = b->n_pairs, n_tmpl = b->n_tmpl, radius = b->radius;
+    size_t cb = 0, hb = 0;
+    b->tmpl_len.resize((size_t)n_tmpl);
+    b->homop_off.resize((size_t)n_tmpl + 1);
     for (int t = 0; t < n_tmpl; t++) {
         if (tmpl_off[t + 1] < tmpl_off[t]) return ctx->fail(JTK_EINVAL, "tmpl_off is not monotone");
-        cb += 2 * (size_t)kCodePad + (tmpl_off[t + 1] - tmpl_off[t]) + 1;
+        const size_t L = tmpl_off[t + 1] - tmpl_off[t];
+        b->tmpl_len[t] = (uint32_t)L;
+        b->homop_off[t] = (uint32_t)hb;
+        cb += 2 * (size_t)kCodePad + L + 1;
+        hb += L + 1;
+        b->max_lt = std::max(b->max_lt, (int)L);
     }
+    b->homop_off[n_tmpl] = (uint32_t)hb;
     size_t bwords = 0;
+    std::vector<uint32_t> cnt((size_t)n_tmpl + 1, 0);
     for (int p = 0; p < n_pairs; p++) {
         if (read_off[p + 1] < read_off[p]) return ctx->fail(JTK_EINVAL, "read_off is not monotone");
         if (tmpl_idx[p] >= (uint32_t)n_tmpl) return ctx->fail(JTK_EINVAL, "tmpl_idx out of range");
         const size_t Lr = read_off[p + 1] - read_off[p];
-        const size_t Lt = tmpl_off[tmpl_idx[p] + 1] - tmpl_off[tmpl_idx[p]];
+        const size_t Lt = b->tmpl_len[tmpl_idx[p]];
         cb += 2 * (size_t)kCodePad + Lr + 2;
         bwords += (Lt + Lr + 1 + 31) / 32 + 1;
+        cnt[tmpl_idx[p] + 1]++;
     }
     if (cb >= (size_t)0xffffffffu) return ctx->fail(JTK_EINVAL, "batch too large: split it (code bytes exceed 4 GiB)");
+    b->tp_start.assign((size_t)n_tmpl + 1, 0);
+    for (int t = 0; t < n_tmpl; t++) b->tp_start[t + 1] = b->tp_start[t] + cnt[t + 1];
+    b->tp_ids.resize((size_t)n_pairs);
+    {
+        std::vector<uint32_t> fill(b->tp_start.begin(), b->tp_start.end() - 1);
+        for (int p = 0; p < n_pairs; p++) b->tp_ids[fill[tmpl_idx[p]]++] = (uint32_t)p;
+    }
     CU(ctx->h_codes.reserve(cb), "cudaMallocHost codes");
     CU(ctx->h_bits.reserve(bwords), "cudaMallocHost bits");
     CU(ctx->h_pairs.reserve((size_t)n_pairs), "cudaMallocHost pairs");
+    CU(ctx->h_homop.reserve(hb), "cudaMallocHost homop");
     uint8_t *codes = ctx->h_codes.p;
     uint32_t *bits = ctx->h_bits.p;
+    uint8_t *homop = ctx->h_homop.p;
     std::memset(codes, 4, cb);
     std::memset(bits, 0, bwords * sizeof(uint32_t));
     ctx->tmpl_code_off.resize((size_t)n_tmpl);
     size_t pos = 0;
     for (int t = 0; t < n_tmpl; t++) {
         const uint8_t *s = tmpl_concat + tmpl_off[t];
-        const size_t L = tmpl_off[t + 1] - tmpl_off[t];
+        const size_t L = b->tmpl_len[t];
         pos += kCodePad;
         ctx->tmpl_code_off[t] = (uint32_t)pos;
         for (size_t j = 1; j <= L; j++) codes[pos + j] = base_code(s[j - 1]);
         pos += L + 1 + kCodePad;
+        // homopolymer run length of every base (pseudo_mcmc.rs:195-211), 1 past the end (:153)
+        uint8_t *h = homop + b->homop_off[t];
+        size_t k = 0;
+        while (k < L) {
+            size_t e = k;
+            while (e < L && base_code(s[e]) == base_code(s[k])) e++;
+            for (size_t x = k; x < e; x++) h[x] = (uint8_t)std::min<size_t>(e - k, 255);
+            k = e;
+        }
+        h[L] = 1;
     }
     size_t bpos = 0;
-    uint64_t tab = 0;
-    shape.max_nd = 0;
+    uint64_t tab = 0, cells = 0;
+    b->max_nd = 0;
+    b->pairs.resize((size_t)n_pairs);
     for (int p = 0; p < n_pairs; p++) {
         const uint32_t ti = tmpl_idx[p];
-        const int Lt = (int)(tmpl_off[ti + 1] - tmpl_off[ti]);
+        const int Lt = (int)b->tmpl_len[ti];
         const int Lr = (int)(read_off[p + 1] - read_off[p]);
         const uint8_t *q = read_concat + read_off[p];
         pos += kCodePad;
-        DevPair &dp = ctx->h_pairs.p[p];
+        DevPair &dp = b->pairs[p];
         dp.tb_off = ctx->tmpl_code_off[ti];
         dp.rb_off = (uint32_t)pos;
         for (int i = 1; i <= Lr; i++) {
@@ -293,7 +356,6 @@ int pack_batch(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_concat
             codes[pos + i] = (uint8_t)((cx << 3) | qc);
         }
         pos += (size_t)Lr + 2 + kCodePad;
-        // guide path -> centre increments
         const uint8_t *ops;
         int n_ops;
         if (ops_concat) {
@@ -307,135 +369,399 @@ int pack_batch(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_concat
             ops = ctx->tmp_ops.data();
             n_ops = (int)ctx->tmp_ops.size();
         }
+        // guide path -> centre increments, and the in-band cell count on the way
         uint32_t *bw = bits + bpos;
         int i = 0, j = 0, s = 0;
+        auto width = [&](int cen, int d) -> uint64_t {
+            const int lo = std::max(std::max(cen - radius, 0), d - Lt), hi = std::min(std::min(cen + radius, Lr), d);
+            return hi >= lo ? (uint64_t)(hi - lo + 1) : 0;
+        };
+        uint64_t c = width(0, 0);
+        bool bad = false;
         for (int k = 0; k < n_ops; k++) {
             const uint8_t op = ops[k];
-            if (op <= JTK_OP_MISMATCH) { i++; j++; bw[(s + 1) >> 5] |= 1u << ((s + 1) & 31); s += 2; }
-            else if (op == JTK_OP_INS) { i++; bw[s >> 5] |= 1u << (s & 31); s += 1; }
-            else if (op == JTK_OP_DEL) { j++; s += 1; }
-            else return ctx->fail(JTK_EINVAL, "invalid op code in pair " + std::to_string(p));
-            if (i > Lr || j > Lt) break;
+            if (op <= JTK_OP_MISMATCH) {
+                if (i >= Lr || j >= Lt) { bad = true; break; }
+                c += width(i, s + 1);
+                i++; j++; bw[(s + 1) >> 5] |= 1u << ((s + 1) & 31); s += 2;
+                c += width(i, s);
+            } else if (op == JTK_OP_INS) {
+                if (i >= Lr) { bad = true; break; }
+                i++; bw[s >> 5] |= 1u << (s & 31); s += 1; c += width(i, s);
+            } else if (op == JTK_OP_DEL) {
+                if (j >= Lt) { bad = true; break; }
+                j++; s += 1; c += width(i, s);
+            } else return ctx->fail(JTK_EINVAL, "invalid op code in pair " + std::to_string(p));
         }
-        if (i != Lr || j != Lt)
+        if (bad || i != Lr || j != Lt)
             return ctx->fail(JTK_EINVAL, "ops of pair " + std::to_string(p) + " do not span (template, read): consumed (" +
                                              std::to_string(j) + "," + std::to_string(i) + ") of (" + std::to_string(Lt) + "," +
                                              std::to_string(Lr) + ")");
+        cells += 2 * c;
         dp.bits_off = (uint32_t)bpos;
         bpos += (size_t)(Lt + Lr + 1 + 31) / 32 + 1;
         dp.Lt = Lt; dp.Lr = Lr;
         dp.model = strand[p] ? 0 : 1;
         dp.pad_ = 0;
         dp.tab_off = tab;
-        if (want_table) tab += (uint64_t)(Lt + 1) * kNumRow;
-        shape.max_nd = std::max(shape.max_nd, Lt + Lr + 1);
+        tab += (uint64_t)(Lt + 1) * kNumRow;
+        b->max_nd = std::max(b->max_nd, Lt + Lr + 1);
     }
-    shape.table_floats = tab;
-    code_bytes = cb;
-    bit_words = bwords;
+    std::memcpy(ctx->h_pairs.p, b->pairs.data(), sizeof(DevPair) * (size_t)n_pairs);
+    b->table_floats = tab;
+    b->cell_updates = cells;
+    b->h2d_bytes = cb + bwords * sizeof(uint32_t) + hb + sizeof(DevPair) * (size_t)n_pairs + sizeof(uint32_t) * (3 * (size_t)n_tmpl + 3 + (size_t)n_pairs);
+    code_bytes = cb; bit_words = bwords; homop_bytes = hb;
     return JTK_OK;
 }
 
-int run_batch(jtk_ctx *ctx, const jtk_hmm_params *fwd, const jtk_hmm_params *rev, int n_pairs, int n_tmpl,
-              const uint8_t *tmpl_concat, const uint32_t *tmpl_off, const uint8_t *read_concat,
-              const uint32_t *read_off, const uint8_t *ops_concat, const uint32_t *ops_off, const uint8_t *strand,
-              const uint32_t *tmpl_idx, int radius, bool table, int rows, double *out_lk, double *out_table,
-              const uint64_t *table_off) {
+int batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_concat, const uint32_t *tmpl_off,
+                 const uint8_t *read_concat, const uint32_t *read_off, const uint8_t *ops_concat, const uint32_t *ops_off,
+                 const uint8_t *strand, const uint32_t *tmpl_idx, int radius, bool allow_bootstrap, jtk_batch **out) {
     if (!ctx) return JTK_EINVAL;
-    if (!fwd || !rev || !tmpl_concat || !tmpl_off || !read_concat || !read_off || !strand || !tmpl_idx || !out_lk)
-        return ctx->fail(JTK_EINVAL, "null argument");
+    if (!out) return ctx->fail(JTK_EINVAL, "out is NULL");
+    *out = nullptr;
     if (n_pairs < 0 || n_tmpl < 0) return ctx->fail(JTK_EINVAL, "negative count");
-    if (table && out_table && !table_off) return ctx->fail(JTK_EINVAL, "table_off is NULL");
-    if (n_pairs == 0) return JTK_OK;
+    if (n_pairs > 0 && (!tmpl_concat || !tmpl_off || !read_concat || !read_off || !strand || !tmpl_idx))
+        return ctx->fail(JTK_EINVAL, "null argument");
+    if (n_pairs > 0 && !allow_bootstrap && (!ops_concat || !ops_off)) return ctx->fail(JTK_EINVAL, "guide ops are required");
     const int C = cols_per_lane_for_radius(radius);
     if (radius < 0 || C == 0 || C > 4) return ctx->fail(JTK_EINVAL, "radius out of range (0..62)");
     CU(cudaSetDevice(ctx->device), "cudaSetDevice");
-    BatchShape shape;
-    size_t code_bytes = 0, bit_words = 0;
-    const bool want_table = table && out_table;
-    int rc = pack_batch(ctx, n_pairs, n_tmpl, tmpl_concat, tmpl_off, read_concat, read_off, ops_concat, ops_off, strand,
-                        tmpl_idx, radius, want_table, shape, code_bytes, bit_words);
-    if (rc) return rc;
+    jtk_batch *b = new jtk_batch();
+    b->ctx = ctx; b->n_pairs = n_pairs; b->n_tmpl = n_tmpl; b->radius = radius; b->C = C;
+    if (n_pairs == 0) { *out = b; return JTK_OK; }
+    size_t code_bytes = 0, bit_words = 0, homop_bytes = 0;
+    int rc = pack_batch(ctx, b, tmpl_concat, tmpl_off, read_concat, read_off, ops_concat, ops_off, strand, tmpl_idx,
+                        code_bytes, bit_words, homop_bytes);
+    if (rc) { b->release(); delete b; return rc; }
+    cudaStream_t st = ctx->stream;
+    cudaError_t e;
+#define CB(call, what) do { if ((e = (call)) != cudaSuccess) { b->release(); delete b; return ctx->cuda_fail(e, what); } } while (0)
+    CB(b->d_pairs.reserve((size_t)n_pairs), "cudaMalloc pairs");
+    CB(b->d_codes.reserve(code_bytes), "cudaMalloc codes");
+    CB(b->d_bits.reserve(bit_words), "cudaMalloc bits");
+    CB(b->d_lk.reserve((size_t)n_pairs), "cudaMalloc lk");
+    CB(b->d_tp_start.reserve(b->tp_start.size()), "cudaMalloc csr");
+    CB(b->d_tp_ids.reserve(b->tp_ids.size()), "cudaMalloc csr");
+    CB(b->d_tmpl_len.reserve(b->tmpl_len.size()), "cudaMalloc tmpl_len");
+    CB(b->d_homop_off.reserve(b->homop_off.size()), "cudaMalloc homop_off");
+    CB(b->d_homop.reserve(homop_bytes), "cudaMalloc homop");
+    CB(cudaMemcpyAsync(b->d_pairs.p, ctx->h_pairs.p, sizeof(DevPair) * (size_t)n_pairs, cudaMemcpyHostToDevice, st), "H2D pairs");
+    CB(cudaMemcpyAsync(b->d_codes.p, ctx->h_codes.p, code_bytes, cudaMemcpyHostToDevice, st), "H2D codes");
+    CB(cudaMemcpyAsync(b->d_bits.p, ctx->h_bits.p, bit_words * sizeof(uint32_t), cudaMemcpyHostToDevice, st), "H2D bits");
+    CB(cudaMemcpyAsync(b->d_homop.p, ctx->h_homop.p, homop_bytes, cudaMemcpyHostToDevice, st), "H2D homop");
+    CB(cudaMemcpyAsync(b->d_tp_start.p, b->tp_start.data(), sizeof(uint32_t) * b->tp_start.size(), cudaMemcpyHostToDevice, st), "H2D csr");
+    CB(cudaMemcpyAsync(b->d_tp_ids.p, b->tp_ids.data(), sizeof(uint32_t) * b->tp_ids.size(), cudaMemcpyHostToDevice, st), "H2D csr");
+    CB(cudaMemcpyAsync(b->d_tmpl_len.p, b->tmpl_len.data(), sizeof(uint32_t) * b->tmpl_len.size(), cudaMemcpyHostToDevice, st), "H2D tmpl_len");
+    CB(cudaMemcpyAsync(b->d_homop_off.p, b->homop_off.data(), sizeof(uint32_t) * b->homop_off.size(), cudaMemcpyHostToDevice, st), "H2D homop_off");
+    CB(cudaStreamSynchronize(st), "upload");
+#undef CB
+    *out = b;
+    return JTK_OK;
+}
+
+int batch_run(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev, bool table, int rows) {
+    jtk_ctx *ctx = b->ctx;
+    if (!fwd || !rev) return ctx->fail(JTK_EINVAL, "null model");
+    if (table && rows != 14 && rows != 9) return ctx->fail(JTK_EINVAL, "rows must be 14 or 9");
+    if (b->n_pairs == 0) return JTK_OK;
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
     float models[2 * kModelFloats];
     pack_model(fwd, models);
     pack_model(rev, models + kModelFloats);
-
     const int wpc = warps_per_cta();
-    int grid = (n_pairs + wpc - 1) / wpc;
+    int grid = (b->n_pairs + wpc - 1) / wpc;
     const int max_grid = ctx->sm_count * 4;
     if (grid > max_grid) grid = max_grid;
-    const int NSLOT = 32 * C;
-    KParams kp{};
-    CU(ctx->d_pairs.reserve((size_t)n_pairs), "cudaMalloc pairs");
-    CU(ctx->d_codes.reserve(code_bytes), "cudaMalloc codes");
-    CU(ctx->d_bits.reserve(bit_words), "cudaMalloc bits");
-    CU(ctx->d_models.reserve(2 * kModelFloats), "cudaMalloc models");
-    CU(ctx->d_lk.reserve((size_t)n_pairs), "cudaMalloc lk");
-    CU(ctx->d_counter.reserve(1), "cudaMalloc counter");
-    CU(ctx->h_lk.reserve((size_t)n_pairs), "cudaMallocHost lk");
+    const int NSLOT = 32 * b->C;
     cudaStream_t st = ctx->stream;
+    KParams kp{};
+    CU(ctx->d_models.reserve(2 * kModelFloats), "cudaMalloc models");
+    CU(ctx->d_counter.reserve(1), "cudaMalloc counter");
     if (table) {
         const size_t slots = (size_t)grid * wpc;
-        kp.frow_stride = (size_t)(shape.max_nd + 6) * NSLOT;
-        kp.kf_stride = (size_t)shape.max_nd + 6;
+        kp.frow_stride = (size_t)(b->max_nd + 6) * NSLOT;
+        kp.kf_stride = (size_t)b->max_nd + 6;
         CU(ctx->d_frows.reserve(slots * kp.frow_stride), "cudaMalloc forward rows");
         CU(ctx->d_kf.reserve(slots * kp.kf_stride), "cudaMalloc scale exponents");
-        if (want_table) {
-            CU(ctx->d_delta.reserve((size_t)shape.table_floats), "cudaMalloc table");
-            CU(ctx->h_delta.reserve((size_t)shape.table_floats), "cudaMallocHost table");
-        } else {
-            // the kernel always writes its table; give it a scratch area
-            uint64_t tab = 0;
-            for (int p = 0; p < n_pairs; p++) { ctx->h_pairs.p[p].tab_off = tab; tab += (uint64_t)(ctx->h_pairs.p[p].Lt + 1) * kNumRow; }
-            CU(ctx->d_delta.reserve((size_t)tab), "cudaMalloc table");
-        }
+        CU(b->d_delta.reserve((size_t)b->table_floats), "cudaMalloc profiles");
     }
-    CU(cudaMemcpyAsync(ctx->d_pairs.p, ctx->h_pairs.p, sizeof(DevPair) * (size_t)n_pairs, cudaMemcpyHostToDevice, st), "H2D pairs");
-    CU(cudaMemcpyAsync(ctx->d_codes.p, ctx->h_codes.p, code_bytes, cudaMemcpyHostToDevice, st), "H2D codes");
-    CU(cudaMemcpyAsync(ctx->d_bits.p, ctx->h_bits.p, bit_words * sizeof(uint32_t), cudaMemcpyHostToDevice, st), "H2D bits");
     CU(cudaMemcpyAsync(ctx->d_models.p, models, sizeof(models), cudaMemcpyHostToDevice, st), "H2D models");
     CU(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(int), st), "memset counter");
-    kp.pairs = ctx->d_pairs.p; kp.n_pairs = n_pairs;
-    kp.codes = ctx->d_codes.p; kp.bits = ctx->d_bits.p; kp.models = ctx->d_models.p;
-    kp.radius = radius; kp.rows = rows;
+    kp.pairs = b->d_pairs.p; kp.n_pairs = b->n_pairs;
+    kp.codes = b->d_codes.p; kp.bits = b->d_bits.p; kp.models = ctx->d_models.p;
+    kp.radius = b->radius; kp.rows = rows;
     kp.frows = ctx->d_frows.p; kp.kf = ctx->d_kf.p;
-    kp.out_delta = ctx->d_delta.p; kp.out_lk = ctx->d_lk.p; kp.counter = ctx->d_counter.p;
-    CU(cudaEventRecord(ctx->ev0, st), "event");
-    CU(table ? launch_modtable(kp, C, grid, st) : launch_likelihood(kp, C, grid, st), "kernel launch");
-    ctx->launches++;
-    CU(cudaEventRecord(ctx->ev1, st), "event");
-    CU(cudaMemcpyAsync(ctx->h_lk.p, ctx->d_lk.p, sizeof(double) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st), "D2H lk");
-    if (want_table)
-        CU(cudaMemcpyAsync(ctx->h_delta.p, ctx->d_delta.p, sizeof(float) * (size_t)shape.table_floats, cudaMemcpyDeviceToHost, st), "D2H table");
-    CU(cudaStreamSynchronize(st), "kernel execution");
-    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
-    std::memcpy(out_lk, ctx->h_lk.p, sizeof(double) * (size_t)n_pairs);
-    if (want_table) {
-        for (int p = 0; p < n_pairs; p++) {
-            const DevPair &dp = ctx->h_pairs.p[p];
-            const float *src = ctx->h_delta.p + dp.tab_off;
-            double *dst = out_table + table_off[p];
-            const double lk = out_lk[p];
-            const size_t n = (size_t)(dp.Lt + 1) * kNumRow;
-            for (size_t k = 0; k < n; k++) dst[k] = (src[k] <= -1.0e9f || !(lk > -INFINITY)) ? JTK_TABLE_NEG : lk + (double)src[k];
-        }
+    kp.out_delta = b->d_delta.p; kp.out_lk = b->d_lk.p; kp.counter = ctx->d_counter.p;
+    cudaEvent_t r0 = nullptr, r1 = nullptr;
+    if (ctx->ring_n < jtk_ctx::kRing) {
+        const int k = ctx->ring_n;
+        if (!ctx->ring0[k]) { CU(cudaEventCreate(&ctx->ring0[k]), "event"); CU(cudaEventCreate(&ctx->ring1[k]), "event"); }
+        r0 = ctx->ring0[k]; r1 = ctx->ring1[k];
+        ctx->ring_n++;
     }
+    CU(cudaEventRecord(ctx->ev0, st), "event");
+    if (r0) CU(cudaEventRecord(r0, st), "event");
+    CU(table ? launch_modtable(kp, b->C, grid, st) : launch_likelihood(kp, b->C, grid, st), "kernel launch");
+    ctx->launches++;
+    if (r1) CU(cudaEventRecord(r1, st), "event");
+    CU(cudaEventRecord(ctx->ev1, st), "event");
+    ctx->timing_pending = true;
+    if (table) b->has_profiles = true;
     return JTK_OK;
+}
+
+int batch_sync(jtk_batch *b) {
+    jtk_ctx *ctx = b->ctx;
+    CU(cudaStreamSynchronize(ctx->stream), "kernel execution");
+    if (ctx->timing_pending) { cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1); ctx->timing_pending = false; }
+    return JTK_OK;
+}
+
+// --- column statistics over the reads of each chunk (compress_small_gains + column_sum + strand counts) ---
+__device__ __forceinline__ float min_req_of(const float *min_req, int H, int row, int hl) {
+    const int type = row < 4 ? 0 : (row < 8 + JTK_COPY_SIZE ? 2 : 1); // Subst, Ins (incl. copy), Del
+    const int h = min(max(hl, 1), H);
+    return min_req[type * H + h - 1];
+}
+
+__global__ void colstats_kernel(const float *__restrict__ delta, const DevPair *__restrict__ pairs,
+                                const uint32_t *__restrict__ tp_start, const uint32_t *__restrict__ tp_ids,
+                                const uint32_t *__restrict__ tmpl_len, const uint8_t *__restrict__ homop,
+                                const uint32_t *__restrict__ homop_off, const unsigned long long *__restrict__ stat_off,
+                                const float *__restrict__ min_req, int H, float pos_thr, jtk_colstat *__restrict__ out) {
+    const int t = blockIdx.y;
+    const uint32_t n_ent = (tmpl_len[t] + 1) * kNumRow;
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_ent) return;
+    const uint32_t j = e / kNumRow, row = e % kNumRow;
+    const float thr = min_req_of(min_req, H, row, homop[homop_off[t] + j]);
+    double sum = 0.0;
+    int cnt = 0;
+    unsigned sc[4] = { 0, 0, 0, 0 };
+    for (uint32_t k = tp_start[t]; k < tp_start[t + 1]; k++) {
+        const DevPair &p = pairs[tp_ids[k]];
+        float x = delta[p.tab_off + e];
+        if (fabsf(x) < thr) x = 0.f;
+        if (x > pos_thr) { sum += (double)x; cnt++; }
+        if (fabsf(x) > 1e-4f) sc[(p.model == 0 ? 2 : 0) + (x > 0.f ? 1 : 0)]++;
+    }
+    jtk_colstat o;
+    o.sum = sum; o.count = cnt;
+    o.sc[0] = (uint16_t)min(sc[0], 65535u); o.sc[1] = (uint16_t)min(sc[1], 65535u);
+    o.sc[2] = (uint16_t)min(sc[2], 65535u); o.sc[3] = (uint16_t)min(sc[3], 65535u);
+    o.pad_ = 0;
+    out[stat_off[t] + e] = o;
+}
+
+__global__ void gather_kernel(const float *__restrict__ delta, const DevPair *__restrict__ pairs,
+                              const uint32_t *__restrict__ tp_ids, uint32_t first, uint32_t n_reads,
+                              const uint8_t *__restrict__ homop, const float *__restrict__ min_req, int H,
+                              const uint32_t *__restrict__ cols, int D, double *__restrict__ out) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_reads * (uint32_t)D) return;
+    const uint32_t r = idx / D, d = idx % D;
+    const uint32_t e = cols[d];
+    const DevPair &p = pairs[tp_ids[first + r]];
+    float x = delta[p.tab_off + e];
+    const float thr = min_req_of(min_req, H, e % kNumRow, homop[e / kNumRow]);
+    if (fabsf(x) < thr) x = 0.f;
+    out[idx] = (double)x;
 }
 
 } // namespace
 
 extern "C" {
 
+int jtk_batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_concat, const uint32_t *tmpl_off,
+                     const uint8_t *read_concat, const uint32_t *read_off, const uint8_t *ops_concat,
+                     const uint32_t *ops_off, const uint8_t *strand, const uint32_t *tmpl_idx, int radius, jtk_batch **out) {
+    return batch_create(ctx, n_pairs, n_tmpl, tmpl_concat, tmpl_off, read_concat, read_off, ops_concat, ops_off, strand,
+                        tmpl_idx, radius, false, out);
+}
+
+void jtk_batch_destroy(jtk_batch *b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    b->release();
+    delete b;
+}
+
+uint64_t jtk_batch_cell_updates(const jtk_batch *b) { return b ? b->cell_updates : 0; }
+uint64_t jtk_batch_h2d_bytes(const jtk_batch *b) { return b ? b->h2d_bytes : 0; }
+
+int jtk_batch_modtable(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev, int rows) {
+    if (!b) return JTK_EINVAL;
+    return batch_run(b, fwd, rev, true, rows);
+}
+
+int jtk_batch_sync(jtk_batch *b) { return b ? batch_sync(b) : JTK_EINVAL; }
+
+int jtk_batch_fetch_lk(jtk_batch *b, double *out_lk) {
+    if (!b) return JTK_EINVAL;
+    jtk_ctx *ctx = b->ctx;
+    if (!out_lk) return ctx->fail(JTK_EINVAL, "out_lk is NULL");
+    if (b->n_pairs == 0) return JTK_OK;
+    CU(ctx->h_lk.reserve((size_t)b->n_pairs), "cudaMallocHost lk");
+    CU(cudaMemcpyAsync(ctx->h_lk.p, b->d_lk.p, sizeof(double) * (size_t)b->n_pairs, cudaMemcpyDeviceToHost, ctx->stream), "D2H lk");
+    int rc = batch_sync(b);
+    if (rc) return rc;
+    std::memcpy(out_lk, ctx->h_lk.p, sizeof(double) * (size_t)b->n_pairs);
+    return JTK_OK;
+}
+
+int jtk_batch_fetch_profile(jtk_batch *b, int pair, float *out) {
+    if (!b) return JTK_EINVAL;
+    jtk_ctx *ctx = b->ctx;
+    if (!out || pair < 0 || pair >= b->n_pairs) return ctx->fail(JTK_EINVAL, "bad pair index");
+    if (!b->has_profiles) return ctx->fail(JTK_ESTATE, "jtk_batch_modtable has not run");
+    const DevPair &dp = b->pairs[(size_t)pair];
+    CU(cudaMemcpyAsync(out, b->d_delta.p + dp.tab_off, sizeof(float) * (size_t)(dp.Lt + 1) * kNumRow, cudaMemcpyDeviceToHost, ctx->stream), "D2H profile");
+    return batch_sync(b);
+}
+
+int jtk_batch_colstats(jtk_batch *b, const float *min_req, int H, float pos_thr, jtk_colstat *out, const uint64_t *stat_off) {
+    if (!b) return JTK_EINVAL;
+    jtk_ctx *ctx = b->ctx;
+    if (!min_req || H < 1 || !stat_off) return ctx->fail(JTK_EINVAL, "null argument");
+    if (!b->has_profiles) return ctx->fail(JTK_ESTATE, "jtk_batch_modtable has not run");
+    if (b->n_tmpl == 0) return JTK_OK;
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaStream_t st = ctx->stream;
+    uint64_t total = 0;
+    for (int t = 0; t < b->n_tmpl; t++) total = std::max<uint64_t>(total, stat_off[t] + (uint64_t)(b->tmpl_len[t] + 1) * kNumRow);
+    CU(ctx->d_minreq.reserve((size_t)3 * H), "cudaMalloc min_req");
+    CU(b->d_stat_off.reserve((size_t)b->n_tmpl), "cudaMalloc stat_off");
+    CU(b->d_stats.reserve((size_t)total), "cudaMalloc stats");
+    CU(cudaMemcpyAsync(ctx->d_minreq.p, min_req, sizeof(float) * 3 * (size_t)H, cudaMemcpyHostToDevice, st), "H2D min_req");
+    CU(cudaMemcpyAsync(b->d_stat_off.p, stat_off, sizeof(uint64_t) * (size_t)b->n_tmpl, cudaMemcpyHostToDevice, st), "H2D stat_off");
+    dim3 grid((unsigned)(((size_t)(b->max_lt + 1) * kNumRow + 255) / 256), (unsigned)b->n_tmpl);
+    colstats_kernel<<<grid, 256, 0, st>>>(b->d_delta.p, b->d_pairs.p, b->d_tp_start.p, b->d_tp_ids.p, b->d_tmpl_len.p,
+                                         b->d_homop.p, b->d_homop_off.p, b->d_stat_off.p, ctx->d_minreq.p, H, pos_thr,
+                                         b->d_stats.p);
+    CU(cudaGetLastError(), "colstats launch");
+    ctx->launches++;
+    if (!out) return JTK_OK;
+    CU(cudaMemcpyAsync(out, b->d_stats.p, sizeof(jtk_colstat) * (size_t)total, cudaMemcpyDeviceToHost, st), "D2H stats");
+    return batch_sync(b);
+}
+
+int jtk_batch_gather(jtk_batch *b, int tmpl, const float *min_req, int H, const uint32_t *cols, int D, double *out) {
+    if (!b) return JTK_EINVAL;
+    jtk_ctx *ctx = b->ctx;
+    if (tmpl < 0 || tmpl >= b->n_tmpl || !min_req || H < 1 || D < 0 || (D > 0 && (!cols || !out)))
+        return ctx->fail(JTK_EINVAL, "bad argument");
+    if (!b->has_profiles) return ctx->fail(JTK_ESTATE, "jtk_batch_modtable has not run");
+    const uint32_t first = b->tp_start[(size_t)tmpl], n_reads = b->tp_start[(size_t)tmpl + 1] - first;
+    if (D == 0 || n_reads == 0) return JTK_OK;
+    const uint32_t n_ent = (b->tmpl_len[(size_t)tmpl] + 1) * kNumRow;
+    for (int d = 0; d < D; d++)
+        if (cols[d] >= n_ent) return ctx->fail(JTK_EINVAL, "column index out of range");
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaStream_t st = ctx->stream;
+    CU(ctx->d_minreq.reserve((size_t)3 * H), "cudaMalloc min_req");
+    CU(ctx->d_cols.reserve((size_t)D), "cudaMalloc cols");
+    CU(ctx->d_gather.reserve((size_t)D * n_reads), "cudaMalloc gather");
+    CU(cudaMemcpyAsync(ctx->d_minreq.p, min_req, sizeof(float) * 3 * (size_t)H, cudaMemcpyHostToDevice, st), "H2D min_req");
+    CU(cudaMemcpyAsync(ctx->d_cols.p, cols, sizeof(uint32_t) * (size_t)D, cudaMemcpyHostToDevice, st), "H2D cols");
+    const uint32_t n = n_reads * (uint32_t)D;
+    gather_kernel<<<(n + 127) / 128, 128, 0, st>>>(b->d_delta.p, b->d_pairs.p, b->d_tp_ids.p, first, n_reads,
+                                                   b->d_homop.p + b->homop_off[(size_t)tmpl], ctx->d_minreq.p, H,
+                                                   ctx->d_cols.p, D, ctx->d_gather.p);
+    CU(cudaGetLastError(), "gather launch");
+    ctx->launches++;
+    CU(cudaMemcpyAsync(out, ctx->d_gather.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st), "D2H gather");
+    return batch_sync(b);
+}
+
+int jtk_ctx_timer_start(jtk_ctx *ctx) {
+    if (!ctx) return JTK_EINVAL;
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CU(cudaEventRecord(ctx->tm0, ctx->stream), "event");
+    return JTK_OK;
+}
+
+int jtk_ctx_timer_stop(jtk_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return JTK_EINVAL;
+    CU(cudaEventRecord(ctx->tm1, ctx->stream), "event");
+    CU(cudaStreamSynchronize(ctx->stream), "sync");
+    CU(cudaEventElapsedTime(ms, ctx->tm0, ctx->tm1), "elapsed");
+    return JTK_OK;
+}
+
+int jtk_ctx_kernel_times(jtk_ctx *ctx, float *ms, int cap) {
+    if (!ctx || (!ms && cap > 0)) return JTK_EINVAL;
+    CU(cudaStreamSynchronize(ctx->stream), "sync");
+    const int n = std::min(cap, ctx->ring_n);
+    for (int k = 0; k < n; k++) CU(cudaEventElapsedTime(&ms[k], ctx->ring0[k], ctx->ring1[k]), "elapsed");
+    ctx->ring_n = 0;
+    return n;
+}
+
+int jtk_ctx_measure_fp32_peak(jtk_ctx *ctx, double *tflops_ffma, double *tflops_ffma2) {
+    if (!ctx || !tflops_ffma || !tflops_ffma2) return JTK_EINVAL;
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const int iters = 4096, threads = 256, blocks = ctx->sm_count * 8;
+    float *sink = nullptr;
+    CU(cudaMalloc((void **)&sink, sizeof(float) * (size_t)blocks * threads), "cudaMalloc sink");
+    double best[2] = { 0, 0 };
+    for (int mode = 0; mode < 2; mode++)
+        for (int rep = 0; rep < 4; rep++) {
+            cudaEventRecord(ctx->tm0, ctx->stream);
+            cudaError_t e = launch_fp32_peak(mode, blocks, threads, iters, sink, ctx->stream);
+            cudaEventRecord(ctx->tm1, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) { cudaFree(sink); return ctx->cuda_fail(e, "fp32 peak kernel"); }
+            ctx->launches++;
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->tm0, ctx->tm1);
+            // 16 independent accumulators per thread, 2 flops per FMA (packed: 2 FMAs per instruction, 8 registers pairs)
+            const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * threads;
+            if (rep > 0) best[mode] = std::max(best[mode], flops / (ms * 1e-3) / 1e12);
+        }
+    cudaFree(sink);
+    *tflops_ffma = best[0];
+    *tflops_ffma2 = best[1];
+    return JTK_OK;
+}
+
+// ---- level 1 on top of the batch ---------------------------------------------------------------------
 int jtk_hmm_modtable_batch(jtk_ctx *ctx, const jtk_hmm_params *fwd, const jtk_hmm_params *rev, int n_pairs,
                            int n_tmpl, const uint8_t *tmpl_concat, const uint32_t *tmpl_off,
                            const uint8_t *read_concat, const uint32_t *read_off,
                            const uint8_t *ops_concat, const uint32_t *ops_off,
                            const uint8_t *strand, const uint32_t *tmpl_idx, int radius,
                            double *out_lk, double *out_table, const uint64_t *table_off) {
-    if (ctx && (!ops_concat || !ops_off)) return ctx->fail(JTK_EINVAL, "modification table needs guide ops");
-    return run_batch(ctx, fwd, rev, n_pairs, n_tmpl, tmpl_concat, tmpl_off, read_concat, read_off, ops_concat, ops_off,
-                     strand, tmpl_idx, radius, true, 14, out_lk, out_table, table_off);
+    if (!ctx) return JTK_EINVAL;
+    if (!out_lk) return ctx->fail(JTK_EINVAL, "out_lk is NULL");
+    if (out_table && !table_off) return ctx->fail(JTK_EINVAL, "table_off is NULL");
+    jtk_batch *b = nullptr;
+    int rc = batch_create(ctx, n_pairs, n_tmpl, tmpl_concat, tmpl_off, read_concat, read_off, ops_concat, ops_off, strand,
+                          tmpl_idx, radius, false, &b);
+    if (rc) return rc;
+    rc = batch_run(b, fwd, rev, true, 14);
+    if (!rc) rc = jtk_batch_fetch_lk(b, out_lk);
+    if (!rc && out_table && n_pairs > 0) {
+        cudaError_t e = ctx->h_delta.reserve((size_t)b->table_floats);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(ctx->h_delta.p, b->d_delta.p, sizeof(float) * (size_t)b->table_floats, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = ctx->cuda_fail(e, "D2H table");
+        else
+            for (int p = 0; p < n_pairs; p++) {
+                const DevPair &dp = b->pairs[(size_t)p];
+                const float *src = ctx->h_delta.p + dp.tab_off;
+                double *dst = out_table + table_off[p];
+                const double lk = out_lk[p];
+                const size_t n = (size_t)(dp.Lt + 1) * kNumRow;
+                for (size_t k = 0; k < n; k++)
+                    dst[k] = (src[k] <= -1.0e9f || !(lk > -INFINITY)) ? JTK_TABLE_NEG : lk + (double)src[k];
+            }
+    }
+    jtk_batch_destroy(b);
+    return rc;
 }
 
 int jtk_hmm_likelihood_batch(jtk_ctx *ctx, const jtk_hmm_params *fwd, const jtk_hmm_params *rev, int n_pairs,
@@ -443,8 +769,16 @@ int jtk_hmm_likelihood_batch(jtk_ctx *ctx, const jtk_hmm_params *fwd, const jtk_
                              const uint8_t *read_concat, const uint32_t *read_off,
                              const uint8_t *ops_concat, const uint32_t *ops_off,
                              const uint8_t *strand, const uint32_t *tmpl_idx, int radius, double *out_lk) {
-    return run_batch(ctx, fwd, rev, n_pairs, n_tmpl, tmpl_concat, tmpl_off, read_concat, read_off, ops_concat, ops_off,
-                     strand, tmpl_idx, radius, false, 0, out_lk, nullptr, nullptr);
+    if (!ctx) return JTK_EINVAL;
+    if (!out_lk) return ctx->fail(JTK_EINVAL, "out_lk is NULL");
+    jtk_batch *b = nullptr;
+    int rc = batch_create(ctx, n_pairs, n_tmpl, tmpl_concat, tmpl_off, read_concat, read_off, ops_concat, ops_off, strand,
+                          tmpl_idx, radius, true, &b);
+    if (rc) return rc;
+    rc = batch_run(b, fwd, rev, false, 0);
+    if (!rc) rc = jtk_batch_fetch_lk(b, out_lk);
+    jtk_batch_destroy(b);
+    return rc;
 }
 
 } // extern "C"

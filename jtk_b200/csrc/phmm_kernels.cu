@@ -416,4 +416,44 @@ cudaError_t launch_likelihood(const KParams &p, int C, int grid, cudaStream_t st
 
 int warps_per_cta() { return kWarpsPerCta; }
 
+// ---- FP32 peak micro-benchmark (roofline denominator) ---------------------------------------------------
+// 16 independent accumulators per thread so the 4-cycle FMA latency is covered at 8 warps per scheduler.
+template <int MODE>
+__global__ void __launch_bounds__(256) fp32_peak_kernel(int iters, float *sink) {
+    float a = 1.0f + 1e-7f * threadIdx.x, b = 1e-9f * (blockIdx.x + 1);
+    if (MODE == 0) {
+        float acc[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) acc[k] = (float)k;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) acc[k] = fmaf(acc[k], a, b);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; k++) s += acc[k];
+        sink[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    } else {
+        unsigned long long acc[8], aa, bb;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+        asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+#pragma unroll
+        for (int k = 0; k < 8; k++) { float lo = (float)k, hi = (float)(k + 8); asm("mov.b64 %0, {%1, %2};" : "=l"(acc[k]) : "f"(lo), "f"(hi)); }
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[k]) : "l"(aa), "l"(bb));
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[k])); s += lo + hi; }
+        sink[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    }
+}
+
+cudaError_t launch_fp32_peak(int mode, int blocks, int threads, int iters, float *sink, cudaStream_t st) {
+    if (mode == 0) fp32_peak_kernel<0><<<blocks, threads, 0, st>>>(iters, sink);
+    else fp32_peak_kernel<1><<<blocks, threads, 0, st>>>(iters, sink);
+    return cudaGetLastError();
+}
+
 } // namespace jtk
