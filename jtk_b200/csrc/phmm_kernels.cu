@@ -16,7 +16,19 @@ namespace jtk {
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kWarpsPerCta = 4;
 constexpr int kRescaleEvery = 4;
-constexpr int kRescaleBelow = -24; // rescale when max exponent on a diagonal < this
+// Scaled fp32 with one exact power-of-two scale per anti-diagonal.
+//  * forward: the largest value on a diagonal is kept in [2^kScaleLow, 2^kScaleTarget] (checked every
+//    kRescaleEvery steps, one rescale moves the exponent by at most kScaleStep).  Keeping the maximum HIGH leaves
+//    ~2^180 of range BELOW it: after a long indel the cells that carry the eventual likelihood can be 1e-40 of
+//    the locally largest (dead-end) cell.
+//  * backward: mirrors the forward schedule, B(Lr,Lt) = 2^(kProductExp - exponent(fin)), so every forward x
+//    backward product of one cell is (posterior mass) x 2^kProductExp: B = 2^kProductExp / F on the cells that
+//    matter, inside the fp32 range on both sides as long as the dead-end advantage stays below ~2^180.
+//  * a product that pairs rows on the two sides of a rescale gets its exact power-of-two correction.
+constexpr int kScaleLow = 88;
+constexpr int kScaleTarget = 100;
+constexpr int kScaleStep = 64;
+constexpr int kProductExp = 0;
 
 struct Trans { float mm, mi, md, im, ii, id, dm, di, dd; };
 
@@ -96,8 +108,8 @@ __device__ __forceinline__ void forward_pass(const DevPair &P, const uint8_t *__
             for (int c = 1; c < C; c++) v = fmaxf(v, tM[c]);
             const unsigned m = __reduce_max_sync(kFull, __float_as_uint(v));
             const int e = (int)(m >> 23) - 127;
-            if (m != 0u && e < kRescaleBelow) {
-                const int k = min(-e, 120);
+            if (m != 0u && e < kScaleLow) {
+                const int k = min(kScaleTarget - e, kScaleStep);
                 const float sc = pow2i(k);
 #pragma unroll
                 for (int c = 0; c < C; c++) { tM[c] *= sc; tD[c] *= sc; toI[c] *= sc; inMa[c] *= sc; }
@@ -147,7 +159,11 @@ __device__ __forceinline__ void backward_pass(const DevPair &P, const uint8_t *_
     const float *sEI = sm + kOffEI;
     const float4 *sEMT = reinterpret_cast<const float4 *>(sm + kOffEMT);
     const Trans a = load_trans(sm);
-    const float fin = s_ftot[0];
+    // B(Lr,Lt) = boff puts sum_cells F*B = fin * boff at about 2^kProductExp
+    const float fin_raw = s_ftot[0];
+    const int e_fin = (int)(__float_as_uint(fin_raw) >> 23) - 127;
+    const float boff = fin_raw > 0.f ? pow2i(max(-120, min(120, kProductExp - e_fin))) : 1.f;
+    const float fin = fin_raw * boff;
 
     int j[C], tc8[C];
     float BI[C], BMo[C], inD[C], inMa[C], inMb[C];
@@ -201,7 +217,7 @@ __device__ __forceinline__ void backward_pass(const DevPair &P, const uint8_t *_
                 float v = kDeltaNeg;
                 if ((ROWS == 14 || e == 1) && jj + e <= Lt) {
                     float acc = stage[((jj + e) & (kStageCols - 1)) * kStageStride + 13 + (e - 1)];
-                    if (jj + e == Lt) acc += s_ftot[e];
+                    if (jj + e == Lt) acc += s_ftot[e] * boff;
                     v = dlog(acc, ref);
                 }
                 o[10 + e] = v;
@@ -219,7 +235,7 @@ __device__ __forceinline__ void backward_pass(const DevPair &P, const uint8_t *_
         if (corr) {
             const int k0 = kf[s];
 #pragma unroll
-            for (int e = -3; e <= 3; e++) ce[e + 3] = pow2i(max(-120, min(120, k0 - kf[s + e])));
+            for (int e = -3; e <= 3; e++) ce[e + 3] = pow2i(max(-126, min(126, k0 - kf[s + e])));
         }
         float bM[C], bD[C];
         bool any_dead = false;
@@ -235,7 +251,7 @@ __device__ __forceinline__ void backward_pass(const DevPair &P, const uint8_t *_
             float m_ = a.mm * gM + a.mi * gI + a.md * gD;
             float i_ = a.im * gM + a.ii * gI + a.id * gD;
             float d_ = a.dm * gM + a.di * gI + a.dd * gD;
-            if (s == nd - 1) { m_ = 1.f; i_ = 1.f; d_ = 1.f; }
+            if (s == nd - 1) { m_ = boff; i_ = boff; d_ = boff; }
             if (!valid) { m_ = 0.f; i_ = 0.f; d_ = 0.f; }
             // ---- table reduction for cell (i, j) ----
             const int slot = lane * C + c;
@@ -253,18 +269,19 @@ __device__ __forceinline__ void backward_pass(const DevPair &P, const uint8_t *_
             const float gMm = okm ? gM : 0.f, gDm = okm ? gD : 0.f;
 #pragma unroll
             for (int e = 1; e <= NXM; e++) {
-                float2 Fe = frow[(ptrdiff_t)(s - e) * NSLOT + ((slot - e) & (NSLOT - 1))];
-                if (corr) { Fe.x *= ce[3 - e]; Fe.y *= ce[3 - e]; }
-                Xm[c][e - 1] += Fe.x * gMm + Fe.y * gDm;
+                const float2 Fe = frow[(ptrdiff_t)(s - e) * NSLOT + ((slot - e) & (NSLOT - 1))];
+                // next to a rescale the two rows carry different exponents: the exact correction goes on the product
+                if (corr) Xm[c][e - 1] += (Fe.x * gMm + Fe.y * gDm) * ce[3 - e];
+                else Xm[c][e - 1] += Fe.x * gMm + Fe.y * gDm;
             }
             if (NXP > 0) {
                 const bool okp = (unsigned)x <= (unsigned)(W + 1);
                 const float gMp = okp ? gM : 0.f, gDp = okp ? gD : 0.f;
 #pragma unroll
                 for (int e = 1; e <= NXP; e++) {
-                    float2 Fe = frow[(ptrdiff_t)(s + e) * NSLOT + ((slot + e) & (NSLOT - 1))];
-                    if (corr) { Fe.x *= ce[3 + e]; Fe.y *= ce[3 + e]; }
-                    Xp[c][e - 1] += Fe.x * gMp + Fe.y * gDp;
+                    const float2 Fe = frow[(ptrdiff_t)(s + e) * NSLOT + ((slot + e) & (NSLOT - 1))];
+                    if (corr) Xp[c][e - 1] += (Fe.x * gMp + Fe.y * gDp) * ce[3 + e];
+                    else Xp[c][e - 1] += Fe.x * gMp + Fe.y * gDp;
                 }
             }
             bM[c] = m_; bD[c] = d_;
