@@ -15,6 +15,7 @@ int cols_per_lane_for_radius(int radius);
 cudaError_t launch_modtable(const KParams &p, int C, int grid, cudaStream_t st);
 cudaError_t launch_likelihood(const KParams &p, int C, int grid, cudaStream_t st);
 int warps_per_cta();
+int frow_slots_per_row(int C);
 cudaError_t launch_fp32_peak(int mode, int blocks, int threads, int iters, float *sink, cudaStream_t st);
 } // namespace jtk
 
@@ -284,7 +285,7 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
         const size_t L = tmpl_off[t + 1] - tmpl_off[t];
         b->tmpl_len[t] = (uint32_t)L;
         b->homop_off[t] = (uint32_t)hb;
-        cb += 2 * (size_t)kCodePad + L + 1;
+        cb += 2 * (size_t)kCodePad + ((L + 1 + 3) & ~(size_t)3);
         hb += L + 1;
         b->max_lt = std::max(b->max_lt, (int)L);
     }
@@ -296,7 +297,7 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
         if (tmpl_idx[p] >= (uint32_t)n_tmpl) return ctx->fail(JTK_EINVAL, "tmpl_idx out of range");
         const size_t Lr = read_off[p + 1] - read_off[p];
         const size_t Lt = b->tmpl_len[tmpl_idx[p]];
-        cb += 2 * (size_t)kCodePad + Lr + 2;
+        cb += 2 * (size_t)kCodePad + ((Lr + 2 + 3) & ~(size_t)3);
         bwords += (Lt + Lr + 1 + 31) / 32 + 1;
         cnt[tmpl_idx[p] + 1]++;
     }
@@ -325,7 +326,7 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
         pos += kCodePad;
         ctx->tmpl_code_off[t] = (uint32_t)pos;
         for (size_t j = 1; j <= L; j++) codes[pos + j] = base_code(s[j - 1]);
-        pos += L + 1 + kCodePad;
+        pos += ((L + 1 + 3) & ~(size_t)3) + kCodePad;
         // homopolymer run length of every base (pseudo_mcmc.rs:195-211), 1 past the end (:153)
         uint8_t *h = homop + b->homop_off[t];
         size_t k = 0;
@@ -346,6 +347,9 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
         const int Lt = (int)b->tmpl_len[ti];
         const int Lr = (int)(read_off[p + 1] - read_off[p]);
         const uint8_t *q = read_concat + read_off[p];
+        // read rows: byte = ctx<<5 | qc<<2 (the byte offset into the eI table; bits 2-4 index eM rows); 16 = no base
+        const size_t rlen = ((size_t)Lr + 2 + 3) & ~(size_t)3;
+        std::memset(codes + pos, 16, 2 * (size_t)kCodePad + rlen);
         pos += kCodePad;
         DevPair &dp = b->pairs[p];
         dp.tb_off = ctx->tmpl_code_off[ti];
@@ -353,9 +357,9 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
         for (int i = 1; i <= Lr; i++) {
             const uint8_t qc = base_code(q[i - 1]);
             const uint8_t cx = i >= 2 ? base_code(q[i - 2]) : 4;
-            codes[pos + i] = (uint8_t)((cx << 3) | qc);
+            codes[pos + i] = (uint8_t)((cx << 5) | (qc << 2));
         }
-        pos += (size_t)Lr + 2 + kCodePad;
+        pos += rlen + kCodePad;
         const uint8_t *ops;
         int n_ops;
         if (ops_concat) {
@@ -474,14 +478,13 @@ int batch_run(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev
     int grid = (b->n_pairs + wpc - 1) / wpc;
     const int max_grid = ctx->sm_count * 4;
     if (grid > max_grid) grid = max_grid;
-    const int NSLOT = 32 * b->C;
     cudaStream_t st = ctx->stream;
     KParams kp{};
     CU(ctx->d_models.reserve(2 * kModelFloats), "cudaMalloc models");
     CU(ctx->d_counter.reserve(1), "cudaMalloc counter");
     if (table) {
         const size_t slots = (size_t)grid * wpc;
-        kp.frow_stride = (size_t)(b->max_nd + 6) * NSLOT;
+        kp.frow_stride = (size_t)(b->max_nd + 6) * frow_slots_per_row(b->C);
         kp.kf_stride = (size_t)b->max_nd + 6;
         CU(ctx->d_frows.reserve(slots * kp.frow_stride), "cudaMalloc forward rows");
         CU(ctx->d_kf.reserve(slots * kp.kf_stride), "cudaMalloc scale exponents");

@@ -10,6 +10,7 @@
 // value on a diagonal drops below 2^-24; the backward pass mirrors the forward schedule so that every
 // forward x backward product carries the same exponent and the table is a plain ratio of sums.
 #include "phmm_dev.cuh"
+#include <type_traits>
 
 namespace jtk {
 
@@ -29,110 +30,226 @@ constexpr int kScaleLow = 88;
 constexpr int kScaleTarget = 100;
 constexpr int kScaleStep = 64;
 constexpr int kProductExp = 0;
+constexpr int kMaxEvents = 96;  // rescale events remembered per pair for the backward fast path
+constexpr int kPrefetchRows = 3; // backward pass: rows pulled into L1 this many steps before their first use
+constexpr int kHalo = 4;        // forward rows carry 4 replicated slots on both sides: neighbours need no wrap-around
 
-struct Trans { float mm, mi, md, im, ii, id, dm, di, dd; };
+// ---- small helpers --------------------------------------------------------------------------------------
+typedef unsigned long long f2; // two packed fp32 (lo, hi) in one 64-bit register pair
 
-__device__ __forceinline__ Trans load_trans(const float *m) {
-    Trans a;
-    a.mm = m[0]; a.mi = m[1]; a.md = m[2];
-    a.im = m[3]; a.ii = m[4]; a.id = m[5];
-    a.dm = m[6]; a.di = m[7]; a.dd = m[8];
-    return a;
+__device__ __forceinline__ f2 mk2(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float lo2(f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float hi2(f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 bc2(float v) { return mk2(v, v); }
+
+__device__ __forceinline__ float lds_f32(unsigned a) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void lds_f32x4(unsigned a, f2 &x, f2 &y) {
+    asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "r"(a));
 }
 
 __device__ __forceinline__ float pow2i(int k) { // exact 2^k, k in [-126, 127]
     return __uint_as_float((unsigned)(127 + k) << 23);
 }
-
 __device__ __forceinline__ int band_lo(int cen, int r, int s, int Lt) { return max(max(cen - r, 0), s - Lt); }
 __device__ __forceinline__ int band_hi(int cen, int r, int s, int Lr) { return min(min(cen + r, Lr), s); }
 
+// four consecutive read-row codes Rb[i..i+3] as one register (byte 0 = row i); RbP = Rb - kCodePad is 4-aligned
+__device__ __forceinline__ unsigned win_up(const uint8_t *__restrict__ RbP, int i) {
+    const unsigned off = (unsigned)(i + kCodePad);
+    const unsigned *wp = reinterpret_cast<const unsigned *>(RbP) + (off >> 2);
+    return __funnelshift_r(wp[0], wp[1], (off & 3u) * 8u);
+}
+// four read-row codes Rb[a], Rb[a-1], Rb[a-2], Rb[a-3] (byte 0 = row a): the backward pass walks rows downwards
+__device__ __forceinline__ unsigned win_down(const uint8_t *__restrict__ RbP, int a) {
+    return __byte_perm(win_up(RbP, a - 3), 0u, 0x0123u);
+}
+
+// transition coefficients, paired the way the cell update consumes them
+struct Coef {
+    f2 fM, fI, fD;        // forward:  (toM, toD) = fM*M + fI*I + fD*D       = ((mm,md), (im,id), (dm,dd))
+    float f_mi, f_ii, f_di; //         toI      = mi*M + ii*I + di*D
+    f2 bM, bI, bD;        // backward: (B_M, B_D) = bM*gM + bI*gI + bD*gD   = ((mm,dm), (mi,di), (md,dd))
+    float b_im, b_ii, b_id; //         B_I      = im*gM + ii*gI + id*gD
+};
+__device__ __forceinline__ Coef load_coef(const float *t) { // t: mat_mat, mat_ins, mat_del, ins_mat, ...
+    const float mm = t[0], mi = t[1], md = t[2], im = t[3], ii = t[4], id = t[5], dm = t[6], di = t[7], dd = t[8];
+    Coef c;
+    c.fM = mk2(mm, md); c.fI = mk2(im, id); c.fD = mk2(dm, dd);
+    c.f_mi = mi; c.f_ii = ii; c.f_di = di;
+    c.bM = mk2(mm, dm); c.bI = mk2(mi, di); c.bD = mk2(md, dd);
+    c.b_im = im; c.b_ii = ii; c.b_id = id;
+    return c;
+}
+
+// per-model tables in shared memory, aligned so that a table address is (base | code bits): one LOP3 per lookup
+struct __align__(256) SmemLayout {
+    float em[2][64];  // [tc*8 + qc]   byte offset tc*32 + qc*4
+    float ei[2][64];  // [ctx*8 + qc]  byte offset = the read-row code byte (ctx<<5 | qc<<2)
+    float emt[2][32]; // [qc*4 + b]    eM(ref b, query qc)
+    float trans[2][12];
+    float stage[kWarpsPerCta][kStageCols * kStageStride];
+    float ftot[kWarpsPerCta][4];
+    unsigned short ev_s[kWarpsPerCta][kMaxEvents]; // steps at which the forward pass rescaled
+    int ev_n[kWarpsPerCta];
+};
+
+__device__ __forceinline__ void fill_tables(SmemLayout &sh, const float *__restrict__ models) {
+    for (int k = threadIdx.x; k < 2 * 64; k += blockDim.x) {
+        const int m = k >> 6, e = k & 63;
+        sh.em[m][e] = models[m * kModelFloats + kOffEM + e];
+        sh.ei[m][e] = models[m * kModelFloats + kOffEI + e];
+        if (e < 32) sh.emt[m][e] = models[m * kModelFloats + kOffEMT + e];
+        if (e < 12) sh.trans[m][e] = models[m * kModelFloats + e];
+    }
+    __syncthreads();
+}
+
+struct PairCtx { // warp-uniform view of one pair
+    const uint8_t *Tb;  // Tb[j] = code of t[j-1]
+    const uint8_t *RbP; // Rb - kCodePad
+    const uint32_t *bw;
+    int Lt, Lr, nd, r;
+    unsigned sEM, sEI, sEMT; // shared-space addresses of this pair's model tables
+};
+
 // ------------------------------------------------------------------------------------------------
 // Forward pass.  STORE: write (toM, toD) of every cell to frow[s*NSLOT + slot] and the cumulative scale
-// exponent to kf[s].  Returns the stored final value fin = (F_M+F_I+F_D)(Lr,Lt) * 2^Ktot.
-// s_ftot[d] (d = 0..3) receives (F_M+F_I+F_D)(Lr, Lt-d) * 2^Ktot (the delete-to-end rows).
+// exponent to kf[s].  s_ftot[d] (d = 0..3) receives (F_M+F_I+F_D)(Lr, Lt-d) * 2^Ktot; s_ftot[0] is the
+// final value the likelihood is read from.
 // ------------------------------------------------------------------------------------------------
-template <int C, bool STORE>
-__device__ __forceinline__ void forward_pass(const DevPair &P, const uint8_t *__restrict__ codes,
-                                             const uint32_t *__restrict__ bits, const float *sm, int r,
-                                             float2 *__restrict__ frow, int32_t *__restrict__ kf,
-                                             volatile float *s_ftot, int &Ktot) {
-    constexpr int NSLOT = 32 * C;
-    const int lane = threadIdx.x & 31;
-    const uint8_t *Tb = codes + P.tb_off;
-    const uint8_t *Rb = codes + P.rb_off;
-    const uint32_t *bw = bits + P.bits_off;
-    const int Lt = P.Lt, Lr = P.Lr, nd = Lt + Lr + 1;
-    const float *sEM = sm + kOffEM;
-    const float *sEI = sm + kOffEI;
-    const Trans a = load_trans(sm);
-
-    int j[C], tc8[C];
+template <int C> struct FwdState {
+    int j[C];
+    unsigned tcB[C], win[C];
     float toI[C], inD[C], inMa[C], inMb[C];
+};
+
+template <int C, bool STORE, bool SPECIAL>
+__device__ __forceinline__ void fwd_step(const PairCtx &pc, const Coef &a, FwdState<C> &st, const int s, const int cen,
+                                         int &K, f2 *__restrict__ &wrow, const int halo, int32_t *__restrict__ kf,
+                                         volatile float *s_ftot, unsigned short *ev_s, int &ev_n) {
+    constexpr int NSLOT = 32 * C;
+    constexpr int RS = NSLOT + 2 * kHalo;
+    const int lane = threadIdx.x & 31;
+    const int lo = band_lo(cen, pc.r, s, pc.Lt), hi = band_hi(cen, pc.r, s, pc.Lr);
+    const int W = hi - lo, A = s - lo;
+    f2 tMD[C];
+    unsigned dead = 0u;
 #pragma unroll
     for (int c = 0; c < C; c++) {
-        j[c] = lane * C + c;
-        tc8[c] = (int)Tb[j[c]] << 3;
-        toI[c] = inD[c] = inMa[c] = inMb[c] = 0.f;
+        const int x = A - st.j[c];
+        const bool valid = (unsigned)x <= (unsigned)W;
+        const unsigned w = st.win[c];
+        st.win[c] = w >> 8;
+        float em = lds_f32(st.tcB[c] | (w & 0x1cu));
+        float ei = lds_f32(pc.sEI | (w & 0xffu));
+        em = valid ? em : 0.f;
+        ei = valid ? ei : 0.f;
+        float M = em * st.inMb[c];
+        const float I = ei * st.toI[c];
+        const float D = valid ? st.inD[c] : 0.f;
+        if (SPECIAL && s == 0 && st.j[c] == 0) M = 1.f;
+        tMD[c] = fma2(a.fD, bc2(D), fma2(a.fI, bc2(I), mul2(a.fM, bc2(M))));
+        st.toI[c] = fmaf(a.f_di, D, fmaf(a.f_ii, I, a.f_mi * M));
+        if (SPECIAL && s >= pc.nd - 4 && valid && x + lo == pc.Lr && st.j[c] >= pc.Lt - 3) s_ftot[pc.Lt - st.j[c]] = M + I + D;
+        if (x > W) dead |= 1u << c;
+    }
+    if (__any_sync(kFull, dead != 0u)) { // rare: keep it a real branch, not predicated code in the hot path
+#pragma unroll
+        for (int c = 0; c < C; c++)
+            if (dead & (1u << c)) { // below the band for good: the slot moves on to column j + NSLOT
+                st.j[c] += NSLOT;
+                st.tcB[c] = pc.sEM + ((unsigned)pc.Tb[st.j[c]] << 5);
+                st.win[c] = win_up(pc.RbP, s + 1 - st.j[c]);
+            }
+    }
+    if ((s & (kRescaleEvery - 1)) == kRescaleEvery - 1 && s < pc.nd - 8) {
+        float v = lo2(tMD[0]);
+#pragma unroll
+        for (int c = 1; c < C; c++) v = fmaxf(v, lo2(tMD[c]));
+        const unsigned m = __reduce_max_sync(kFull, __float_as_uint(v));
+        const int e = (int)(m >> 23) - 127;
+        if (m != 0u && e < kScaleLow) {
+            const int k = min(kScaleTarget - e, kScaleStep);
+            const float sc = pow2i(k);
+#pragma unroll
+            for (int c = 0; c < C; c++) { tMD[c] = mul2(tMD[c], bc2(sc)); st.toI[c] *= sc; st.inMa[c] *= sc; }
+            K += k;
+            if (STORE) {
+                if (ev_n < kMaxEvents && lane == 0) ev_s[ev_n] = (unsigned short)s;
+                ev_n++;
+            }
+        }
+    }
+    if (STORE) {
+        if (lane == 0) kf[s] = K;
+#pragma unroll
+        for (int c = 0; c < C; c += 2)
+            asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(wrow + c), "l"(tMD[c]), "l"(tMD[c + 1]) : "memory");
+        if (halo != 0) { // the first / last three slots are replicated past the other end of the row
+#pragma unroll
+            for (int c = 0; c < C; c += 2)
+                asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(wrow + halo + c), "l"(tMD[c]), "l"(tMD[c + 1]) : "memory");
+        }
+        wrow += RS;
+    }
+    // hand (toM, toD) to the right-hand neighbour column (slot+1, wrapping)
+    const float rM = __shfl_sync(kFull, lo2(tMD[C - 1]), (lane + 31) & 31);
+    const float rD = __shfl_sync(kFull, hi2(tMD[C - 1]), (lane + 31) & 31);
+#pragma unroll
+    for (int c = C - 1; c >= 1; c--) { st.inMb[c] = st.inMa[c]; st.inMa[c] = lo2(tMD[c - 1]); st.inD[c] = hi2(tMD[c - 1]); }
+    st.inMb[0] = st.inMa[0]; st.inMa[0] = rM; st.inD[0] = rD;
+}
+
+template <int C, bool STORE>
+__device__ __forceinline__ void forward_pass(const PairCtx &pc, const Coef &a, float2 *__restrict__ frow,
+                                             int32_t *__restrict__ kf, volatile float *s_ftot, int &Ktot,
+                                             unsigned short *ev_s, int &ev_n) {
+    constexpr int NSLOT = 32 * C;
+    const int lane = threadIdx.x & 31;
+    const int nd = pc.nd;
+    f2 *wrow = reinterpret_cast<f2 *>(frow) + kHalo + lane * C; // this lane's slots in row 0
+    const int halo = (lane * C < 3) ? NSLOT : ((lane * C + C > NSLOT - 3) ? -NSLOT : 0);
+    ev_n = 0;
+    FwdState<C> st;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        st.j[c] = lane * C + c;
+        st.tcB[c] = pc.sEM + ((unsigned)pc.Tb[st.j[c]] << 5);
+        st.win[c] = win_up(pc.RbP, -st.j[c]);
+        st.toI[c] = st.inD[c] = st.inMa[c] = st.inMb[c] = 0.f;
     }
     if (lane < 4) s_ftot[lane] = 0.f;
     int cen = 0, K = 0;
-    for (int s = 0; s < nd; ++s) {
-        const int lo = band_lo(cen, r, s, Lt), hi = band_hi(cen, r, s, Lr);
-        const int W = hi - lo;
-        const bool tail = s >= nd - 4;
-        float tM[C], tD[C];
+    unsigned bword = pc.bw[0];
+    auto advance = [&](int s) { // centre of anti-diagonal s+1
+        cen += (bword >> (s & 31)) & 1u;
+        if (((s + 1) & 31) == 0) bword = pc.bw[(s + 1) >> 5];
+    };
+    auto reload = [&](int s) {
 #pragma unroll
-        for (int c = 0; c < C; c++) {
-            const int i = s - j[c];
-            const int x = i - lo;
-            const bool valid = (unsigned)x <= (unsigned)W;
-            const int rb = Rb[i];
-            const float em = sEM[tc8[c] | (rb & 7)];
-            const float ei = sEI[rb & 63];
-            float M = em * inMb[c], I = ei * toI[c], D = inD[c];
-            if (s == 0 && j[c] == 0) M = 1.f;
-            if (!valid) { M = 0.f; I = 0.f; D = 0.f; }
-            tM[c] = a.mm * M + a.im * I + a.dm * D;
-            toI[c] = a.mi * M + a.ii * I + a.di * D;
-            tD[c] = a.md * M + a.id * I + a.dd * D;
-            if (tail && valid && i == Lr && j[c] >= Lt - 3) s_ftot[Lt - j[c]] = M + I + D;
-            if (x > W) { // below the band for good: the slot moves on to column j + NSLOT
-                j[c] += NSLOT;
-                tc8[c] = (int)Tb[j[c]] << 3;
-            }
-        }
-        if (((s & (kRescaleEvery - 1)) == kRescaleEvery - 1) && !tail && s < nd - 8) {
-            float v = tM[0];
-#pragma unroll
-            for (int c = 1; c < C; c++) v = fmaxf(v, tM[c]);
-            const unsigned m = __reduce_max_sync(kFull, __float_as_uint(v));
-            const int e = (int)(m >> 23) - 127;
-            if (m != 0u && e < kScaleLow) {
-                const int k = min(kScaleTarget - e, kScaleStep);
-                const float sc = pow2i(k);
-#pragma unroll
-                for (int c = 0; c < C; c++) { tM[c] *= sc; tD[c] *= sc; toI[c] *= sc; inMa[c] *= sc; }
-                K += k;
-            }
-        }
-        if (STORE) {
-            if (lane == 0) kf[s] = K;
-            float2 *row = frow + (size_t)s * NSLOT + lane * C;
-            if constexpr (C == 2) {
-                *reinterpret_cast<float4 *>(row) = make_float4(tM[0], tD[0], tM[1], tD[1]);
-            } else {
-#pragma unroll
-                for (int c = 0; c < C; c++) row[c] = make_float2(tM[c], tD[c]);
-            }
-        }
-        // hand toM / toD to the right-hand neighbour column (slot+1, wrapping)
-        const float rM = __shfl_sync(kFull, tM[C - 1], (lane + 31) & 31);
-        const float rD = __shfl_sync(kFull, tD[C - 1], (lane + 31) & 31);
-#pragma unroll
-        for (int c = C - 1; c >= 1; c--) { inMb[c] = inMa[c]; inMa[c] = tM[c - 1]; inD[c] = tD[c - 1]; }
-        inMb[0] = inMa[0]; inMa[0] = rM; inD[0] = rD;
-        if (s < nd - 1) cen += (bw[s >> 5] >> (s & 31)) & 1u;
+        for (int c = 0; c < C; c++) st.win[c] = win_up(pc.RbP, s - st.j[c]);
+    };
+    int s = 0;
+    // prologue: the first four anti-diagonals (the start cell is injected at s = 0)
+    for (; s < 4 && s < nd; ++s) {
+        fwd_step<C, STORE, true>(pc, a, st, s, cen, K, wrow, halo, kf, s_ftot, ev_s, ev_n);
+        advance(s);
+    }
+    // main loop: four steps per read-row window
+    for (; s + 3 < nd - 4; s += 4) {
+        reload(s);
+        fwd_step<C, STORE, false>(pc, a, st, s, cen, K, wrow, halo, kf, s_ftot, ev_s, ev_n); advance(s);
+        fwd_step<C, STORE, false>(pc, a, st, s + 1, cen, K, wrow, halo, kf, s_ftot, ev_s, ev_n); advance(s + 1);
+        fwd_step<C, STORE, false>(pc, a, st, s + 2, cen, K, wrow, halo, kf, s_ftot, ev_s, ev_n); advance(s + 2);
+        fwd_step<C, STORE, false>(pc, a, st, s + 3, cen, K, wrow, halo, kf, s_ftot, ev_s, ev_n); advance(s + 3);
+    }
+    // epilogue: the last anti-diagonals also record the delete-to-end terms
+    for (; s < nd; ++s) {
+        if ((s & 3) == 0) reload(s);
+        fwd_step<C, STORE, true>(pc, a, st, s, cen, K, wrow, halo, kf, s_ftot, ev_s, ev_n);
+        if (s < nd - 1) advance(s);
     }
     Ktot = K;
     __syncwarp();
@@ -142,53 +259,121 @@ __device__ __forceinline__ void forward_pass(const DevPair &P, const uint8_t *__
 // Backward pass fused with the modification-table reduction.  ROWS = 14 (all rows) or 9 (rows 0-7 and
 // the one-base deletion, the only rows local_clustering reads: pseudo_mcmc.rs:447).
 // ------------------------------------------------------------------------------------------------
-template <int C, int ROWS>
-__device__ __forceinline__ void backward_pass(const DevPair &P, const uint8_t *__restrict__ codes,
-                                              const uint32_t *__restrict__ bits, const float *sm, int r,
-                                              const float2 *__restrict__ frow, const int32_t *__restrict__ kf,
-                                              float *stage, volatile float *s_ftot, float *__restrict__ out) {
+template <int C> struct BwdState {
+    int j[C];
+    unsigned tcB[C], win[C];
+    float BI[C], BMo[C], inD[C], inMa[C], inMb[C];
+    f2 S01[C], S23[C], N01[C], N23[C]; // substitution / insertion sums over the four bases
+    float Vs[C], Vn[C];
+    f2 Xp[C][3], Xm[C][3];             // (sum toM*gM, sum toD*gD) of the copy / deletion cuts
+};
+
+template <int C, int ROWS, bool CORR, bool FIRST>
+__device__ __forceinline__ void bwd_step(const PairCtx &pc, const Coef &a, BwdState<C> &st, const int s, const int lo,
+                                         const int W, const f2 *__restrict__ rp, const float *ce, const float boff,
+                                         f2 (&bMD)[C], unsigned &dead_mask) {
     constexpr int NSLOT = 32 * C;
-    constexpr int NXM = (ROWS == 14) ? 3 : 1; // deletion lengths accumulated
-    constexpr int NXP = (ROWS == 14) ? 3 : 0; // copy lengths accumulated
+    constexpr int RS = NSLOT + 2 * kHalo; // rp = this lane's first slot in row s; row s+e, slot+e is rp[e*RS + e]
+    constexpr int NXM = (ROWS == 14) ? 3 : 1;
+    constexpr int NXP = (ROWS == 14) ? 3 : 0;
+    const int A = s - lo;
+    f2 F0[C];
+#pragma unroll
+    for (int c = 0; c < C; c += 2)
+        asm("ld.global.v2.b64 {%0, %1}, [%2];" : "=l"(F0[c]), "=l"(F0[c + 1]) : "l"(rp + c));
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        const int x = A - st.j[c];
+        const bool valid = (unsigned)x <= (unsigned)W;
+        const unsigned w = st.win[c];
+        st.win[c] = w >> 8;
+        const float em = lds_f32(st.tcB[c] | (w & 0x1cu));
+        const float ei = lds_f32(pc.sEI | (w & 0xffu));
+        f2 ec01, ec23;
+        lds_f32x4(pc.sEMT | ((w & 0x1cu) << 2), ec01, ec23);
+        const float gM = em * st.inMb[c], gI = ei * st.BI[c], gD = st.inD[c];
+        f2 md = fma2(a.bD, bc2(gD), fma2(a.bI, bc2(gI), mul2(a.bM, bc2(gM))));
+        float i_ = fmaf(a.b_id, gD, fmaf(a.b_ii, gI, a.b_im * gM));
+        if (FIRST) { md = bc2(boff); i_ = boff; }
+        if (!valid) { md = 0ull; i_ = 0.f; }
+        // ---- table reduction for cell (i, j) ----
+        const float f0m = lo2(F0[c]), f0d = hi2(F0[c]);
+        const f2 U = bc2(f0m * st.inMb[c]);
+        st.S01[c] = fma2(U, ec01, st.S01[c]);
+        st.S23[c] = fma2(U, ec23, st.S23[c]);
+        st.Vs[c] = fmaf(f0d, st.inD[c], st.Vs[c]);
+        const f2 U2 = bc2(f0m * st.BMo[c]);
+        st.N01[c] = fma2(U2, ec01, st.N01[c]);
+        st.N23[c] = fma2(U2, ec23, st.N23[c]);
+        st.Vn[c] = fmaf(f0d, hi2(md), st.Vn[c]);
+        // cuts pairing this column's backward terms with forward columns j-1..j-3 (deletions) and j+1..j+3
+        // (copies).  gM/gD vanish outside x in [-1, W+1] by themselves; x = W+1 must not feed a deletion and
+        // x = -1 must not feed a copy, or a slot would alias the column NSLOT away.
+        {
+            const bool okm = x <= W;
+            const f2 g = mk2(okm ? gM : 0.f, okm ? gD : 0.f);
+#pragma unroll
+            for (int e = 1; e <= NXM; e++) {
+                f2 Fe;
+                asm("ld.global.b64 %0, [%1];" : "=l"(Fe) : "l"(rp + (c - e * RS - e)));
+                if (CORR) st.Xm[c][e - 1] = fma2(mul2(Fe, g), bc2(ce[3 - e]), st.Xm[c][e - 1]);
+                else st.Xm[c][e - 1] = fma2(Fe, g, st.Xm[c][e - 1]);
+            }
+        }
+        if (NXP > 0) {
+            const bool okp = x >= 0;
+            const f2 g = mk2(okp ? gM : 0.f, okp ? gD : 0.f);
+#pragma unroll
+            for (int e = 1; e <= NXP; e++) {
+                f2 Fe;
+                asm("ld.global.b64 %0, [%1];" : "=l"(Fe) : "l"(rp + (c + e * RS + e)));
+                if (CORR) st.Xp[c][e - 1] = fma2(mul2(Fe, g), bc2(ce[3 + e]), st.Xp[c][e - 1]);
+                else st.Xp[c][e - 1] = fma2(Fe, g, st.Xp[c][e - 1]);
+            }
+        }
+        bMD[c] = md;
+        st.BI[c] = i_; st.BMo[c] = lo2(md);
+        if (x < 0) dead_mask |= 1u << c;
+    }
+}
+
+template <int C, int ROWS>
+__device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, const float2 *__restrict__ frow,
+                                              const int32_t *__restrict__ kf, float *stage, volatile float *s_ftot,
+                                              float *__restrict__ out, const unsigned short *ev_s, const int ev_n) {
+    constexpr int NSLOT = 32 * C;
+    constexpr int RS = NSLOT + 2 * kHalo;
     const int lane = threadIdx.x & 31;
-    const uint8_t *Tb = codes + P.tb_off;
-    const uint8_t *Rb = codes + P.rb_off;
-    const uint32_t *bw = bits + P.bits_off;
-    const int Lt = P.Lt, Lr = P.Lr, nd = Lt + Lr + 1;
-    const float *sEM = sm + kOffEM;
-    const float *sEI = sm + kOffEI;
-    const float4 *sEMT = reinterpret_cast<const float4 *>(sm + kOffEMT);
-    const Trans a = load_trans(sm);
+    const int Lt = pc.Lt, Lr = pc.Lr, nd = pc.nd;
     // B(Lr,Lt) = boff puts sum_cells F*B = fin * boff at about 2^kProductExp
     const float fin_raw = s_ftot[0];
     const int e_fin = (int)(__float_as_uint(fin_raw) >> 23) - 127;
     const float boff = fin_raw > 0.f ? pow2i(max(-120, min(120, kProductExp - e_fin))) : 1.f;
     const float fin = fin_raw * boff;
 
-    int j[C], tc8[C];
-    float BI[C], BMo[C], inD[C], inMa[C], inMb[C];
-    float S[C][4], N[C][4], Vs[C], Vn[C], Xp[C][3], Xm[C][3];
+    BwdState<C> st;
 #pragma unroll
     for (int c = 0; c < C; c++) {
         const int sigma = lane * C + c;
-        j[c] = Lt - ((Lt - sigma) & (NSLOT - 1)); // largest column <= Lt owned by this slot
-        tc8[c] = (int)Tb[j[c] + 1] << 3;           // code of t[j]
-        BI[c] = BMo[c] = inD[c] = inMa[c] = inMb[c] = 0.f;
-        Vs[c] = Vn[c] = 0.f;
+        st.j[c] = Lt - ((Lt - sigma) & (NSLOT - 1)); // largest column <= Lt owned by this slot
+        st.tcB[c] = pc.sEM + ((unsigned)pc.Tb[st.j[c] + 1] << 5); // code of t[j]
+        st.win[c] = win_down(pc.RbP, (nd - 1) - st.j[c] + 1);
+        st.BI[c] = st.BMo[c] = st.inD[c] = st.inMa[c] = st.inMb[c] = 0.f;
+        st.Vs[c] = st.Vn[c] = 0.f;
+        st.S01[c] = st.S23[c] = st.N01[c] = st.N23[c] = 0ull;
 #pragma unroll
-        for (int b = 0; b < 4; b++) { S[c][b] = 0.f; N[c][b] = 0.f; }
-#pragma unroll
-        for (int e = 0; e < 3; e++) { Xp[c][e] = 0.f; Xm[c][e] = 0.f; }
+        for (int e = 0; e < 3; e++) { st.Xp[c][e] = 0ull; st.Xm[c][e] = 0ull; }
     }
     int cen = Lr;
     int blk_lo = (Lt >> 5) << 5;
 
     auto flush_col = [&](int c) {
-        float4 *st = reinterpret_cast<float4 *>(stage + (j[c] & (kStageCols - 1)) * kStageStride);
-        st[0] = make_float4(S[c][0], S[c][1], S[c][2], S[c][3]);
-        st[1] = make_float4(Vs[c], N[c][0], N[c][1], N[c][2]);
-        st[2] = make_float4(N[c][3], Vn[c], Xp[c][0], Xp[c][1]);
-        st[3] = make_float4(Xp[c][2], Xm[c][0], Xm[c][1], Xm[c][2]);
+        float4 *sg = reinterpret_cast<float4 *>(stage + (st.j[c] & (kStageCols - 1)) * kStageStride);
+        sg[0] = make_float4(lo2(st.S01[c]), hi2(st.S01[c]), lo2(st.S23[c]), hi2(st.S23[c]));
+        sg[1] = make_float4(st.Vs[c], lo2(st.N01[c]), hi2(st.N01[c]), lo2(st.N23[c]));
+        sg[2] = make_float4(hi2(st.N23[c]), st.Vn[c], lo2(st.Xp[c][0]) + hi2(st.Xp[c][0]), lo2(st.Xp[c][1]) + hi2(st.Xp[c][1]));
+        sg[3] = make_float4(lo2(st.Xp[c][2]) + hi2(st.Xp[c][2]), lo2(st.Xm[c][0]) + hi2(st.Xm[c][0]),
+                            lo2(st.Xm[c][1]) + hi2(st.Xm[c][1]), lo2(st.Xm[c][2]) + hi2(st.Xm[c][2]));
     };
     auto dlog = [](float num, float ref) -> float {
         return (num > 0.f && ref > 0.f) ? logf(num / ref) : kDeltaNeg;
@@ -197,13 +382,13 @@ __device__ __forceinline__ void backward_pass(const DevPair &P, const uint8_t *_
         __syncwarp();
         const int jj = lo_col + lane;
         if (jj >= 0 && jj <= Lt) {
-            const float4 *st = reinterpret_cast<const float4 *>(stage + (jj & (kStageCols - 1)) * kStageStride);
-            const float4 q0 = st[0], q1 = st[1], q2 = st[2], q3 = st[3];
+            const float4 *sg = reinterpret_cast<const float4 *>(stage + (jj & (kStageCols - 1)) * kStageStride);
+            const float4 q0 = sg[0], q1 = sg[1], q2 = sg[2], q3 = sg[3];
             const float s4[4] = { q0.x, q0.y, q0.z, q0.w };
             const float n4[4] = { q1.y, q1.z, q1.w, q2.x };
             const float vs = q1.x, vn = q2.y;
             const float xp[3] = { q2.z, q2.w, q3.x };
-            const int tcode = Tb[jj + 1];
+            const int tcode = pc.Tb[jj + 1];
             float ref = fin;
             if (jj < Lt) ref = s4[tcode & 3] + vs;
             float *o = out + (size_t)jj * kNumRow;
@@ -226,130 +411,121 @@ __device__ __forceinline__ void backward_pass(const DevPair &P, const uint8_t *_
         __syncwarp();
     };
 
-    for (int s = nd - 1; s >= 0; --s) {
-        const int lo = band_lo(cen, r, s, Lt), hi = band_hi(cen, r, s, Lr);
+    unsigned bword = pc.bw[(nd - 1) >> 5];
+    const f2 *rp = reinterpret_cast<const f2 *>(frow) + (ptrdiff_t)(nd - 1) * RS + kHalo + lane * C;
+    // newest rescale event at or below s+3; the fast path needs none inside rows s-2 .. s+3
+    const bool ev_over = ev_n > kMaxEvents;
+    int ei = min(ev_n, kMaxEvents) - 1;
+    int es = ei >= 0 ? (int)ev_s[ei] : -100;
+    int s = nd - 1;
+    // One anti-diagonal.  CORR: a rescale lies within rows s-2 .. s+3 (exact corrections, mirrored scaling);
+    // FIRST: s = nd-1, the terminal cell is injected.  The common case (no rescale nearby) runs in its own loop
+    // so that its register allocation is not tied to the rare path's.
+    auto body = [&](auto corr_t, auto first_t) {
+        constexpr bool CORR = decltype(corr_t)::value;
+        constexpr bool FIRST = decltype(first_t)::value;
+        const int lo = band_lo(cen, pc.r, s, Lt), hi = band_hi(cen, pc.r, s, Lr);
         const int W = hi - lo;
-        // forward x backward products pair rows s-3 .. s+3: exponents differ only next to a rescale
-        const bool corr = (ROWS == 14) ? (kf[s + 3] != kf[s - 3]) : (kf[s] != kf[s - 1]);
-        float ce[7];
-        if (corr) {
-            const int k0 = kf[s];
+        if (FIRST || (s & 3) == 3) {
 #pragma unroll
-            for (int e = -3; e <= 3; e++) ce[e + 3] = pow2i(max(-126, min(126, k0 - kf[s + e])));
+            for (int c = 0; c < C; c++) st.win[c] = win_down(pc.RbP, s - st.j[c] + 1);
         }
-        float bM[C], bD[C];
-        bool any_dead = false;
+        // the forward row that enters the 7-row window kPrefetchRows steps from now: pull it into L1 early
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(rp - (3 + kPrefetchRows) * RS));
+        f2 bMD[C];
+        unsigned dead = 0;
+        int kstep = 0; // exponent the forward pass added at step s (mirrored below)
+        if (CORR) {
+            const int kcur = kf[s];
+            kstep = kcur - kf[s - 1];
+            float ce[7];
 #pragma unroll
-        for (int c = 0; c < C; c++) {
-            const int i = s - j[c];
-            const int x = i - lo;
-            const bool valid = (unsigned)x <= (unsigned)W;
-            const int rb = Rb[i + 1]; // q[i]
-            const float em = sEM[tc8[c] | (rb & 7)];
-            const float ei = sEI[rb & 63];
-            const float gM = em * inMb[c], gI = ei * BI[c], gD = inD[c];
-            float m_ = a.mm * gM + a.mi * gI + a.md * gD;
-            float i_ = a.im * gM + a.ii * gI + a.id * gD;
-            float d_ = a.dm * gM + a.di * gI + a.dd * gD;
-            if (s == nd - 1) { m_ = boff; i_ = boff; d_ = boff; }
-            if (!valid) { m_ = 0.f; i_ = 0.f; d_ = 0.f; }
-            // ---- table reduction for cell (i, j) ----
-            const int slot = lane * C + c;
-            const float2 F0 = frow[(ptrdiff_t)s * NSLOT + slot];
-            const float4 ec = sEMT[rb & 7];
-            const float U = F0.x * inMb[c];
-            S[c][0] += U * ec.x; S[c][1] += U * ec.y; S[c][2] += U * ec.z; S[c][3] += U * ec.w;
-            Vs[c] += F0.y * inD[c];
-            const float U2 = F0.x * BMo[c];
-            N[c][0] += U2 * ec.x; N[c][1] += U2 * ec.y; N[c][2] += U2 * ec.z; N[c][3] += U2 * ec.w;
-            Vn[c] += F0.y * d_;
-            // cuts pairing this column's backward terms with forward columns j-1..j-3 (deletions) and
-            // j+1..j+3 (copies).  The masks keep a slot from aliasing the column NSLOT away.
-            const bool okm = (unsigned)(x + 1) <= (unsigned)(W + 1);
-            const float gMm = okm ? gM : 0.f, gDm = okm ? gD : 0.f;
-#pragma unroll
-            for (int e = 1; e <= NXM; e++) {
-                const float2 Fe = frow[(ptrdiff_t)(s - e) * NSLOT + ((slot - e) & (NSLOT - 1))];
-                // next to a rescale the two rows carry different exponents: the exact correction goes on the product
-                if (corr) Xm[c][e - 1] += (Fe.x * gMm + Fe.y * gDm) * ce[3 - e];
-                else Xm[c][e - 1] += Fe.x * gMm + Fe.y * gDm;
-            }
-            if (NXP > 0) {
-                const bool okp = (unsigned)x <= (unsigned)(W + 1);
-                const float gMp = okp ? gM : 0.f, gDp = okp ? gD : 0.f;
-#pragma unroll
-                for (int e = 1; e <= NXP; e++) {
-                    const float2 Fe = frow[(ptrdiff_t)(s + e) * NSLOT + ((slot + e) & (NSLOT - 1))];
-                    if (corr) Xp[c][e - 1] += (Fe.x * gMp + Fe.y * gDp) * ce[3 + e];
-                    else Xp[c][e - 1] += Fe.x * gMp + Fe.y * gDp;
-                }
-            }
-            bM[c] = m_; bD[c] = d_;
-            BI[c] = i_; BMo[c] = m_;
-            any_dead |= (x < 0);
+            for (int e = -3; e <= 3; e++) ce[e + 3] = pow2i(max(-126, min(126, kcur - kf[s + e])));
+            bwd_step<C, ROWS, true, FIRST>(pc, a, st, s, lo, W, rp, ce, boff, bMD, dead);
+        } else {
+            bwd_step<C, ROWS, false, FIRST>(pc, a, st, s, lo, W, rp, nullptr, boff, bMD, dead);
         }
-        if (__any_sync(kFull, any_dead)) {
+        if (__any_sync(kFull, dead != 0)) {
 #pragma unroll
             for (int c = 0; c < C; c++) {
-                const int x = (s - j[c]) - lo;
-                if (x < 0) { // above the band for good: stage the finished sums, move to column j - NSLOT
-                    if (j[c] >= 0 && j[c] <= Lt) flush_col(c);
-                    j[c] -= NSLOT;
-                    tc8[c] = (int)Tb[j[c] + 1] << 3;
-                    Vs[c] = Vn[c] = 0.f;
+                if (dead & (1u << c)) { // above the band for good: stage the finished sums, move to column j - NSLOT
+                    if (st.j[c] >= 0 && st.j[c] <= Lt) flush_col(c);
+                    st.j[c] -= NSLOT;
+                    st.tcB[c] = pc.sEM + ((unsigned)pc.Tb[st.j[c] + 1] << 5);
+                    st.win[c] = win_down(pc.RbP, (s - 1) - st.j[c] + 1);
+                    st.Vs[c] = st.Vn[c] = 0.f;
+                    st.S01[c] = st.S23[c] = st.N01[c] = st.N23[c] = 0ull;
 #pragma unroll
-                    for (int b = 0; b < 4; b++) { S[c][b] = 0.f; N[c][b] = 0.f; }
-#pragma unroll
-                    for (int e = 0; e < 3; e++) { Xp[c][e] = 0.f; Xm[c][e] = 0.f; }
+                    for (int e = 0; e < 3; e++) { st.Xp[c][e] = 0ull; st.Xm[c][e] = 0ull; }
                 }
             }
             const int jhi = s - lo;
             while (blk_lo > jhi) { emit_block(blk_lo); blk_lo -= 32; }
         }
-        // hand B_M / B_D to the left-hand neighbour column (slot-1, wrapping)
-        const float rM = __shfl_sync(kFull, bM[0], (lane + 1) & 31);
-        const float rD = __shfl_sync(kFull, bD[0], (lane + 1) & 31);
+        // hand (B_M, B_D) to the left-hand neighbour column (slot-1, wrapping)
+        const float rM = __shfl_sync(kFull, lo2(bMD[0]), (lane + 1) & 31);
+        const float rD = __shfl_sync(kFull, hi2(bMD[0]), (lane + 1) & 31);
 #pragma unroll
-        for (int c = 0; c < C - 1; c++) { inMb[c] = inMa[c]; inMa[c] = bM[c + 1]; inD[c] = bD[c + 1]; }
-        inMb[C - 1] = inMa[C - 1]; inMa[C - 1] = rM; inD[C - 1] = rD;
+        for (int c = 0; c < C - 1; c++) { st.inMb[c] = st.inMa[c]; st.inMa[c] = lo2(bMD[c + 1]); st.inD[c] = hi2(bMD[c + 1]); }
+        st.inMb[C - 1] = st.inMa[C - 1]; st.inMa[C - 1] = rM; st.inD[C - 1] = rD;
         if (s > 0) {
-            const int k = kf[s] - kf[s - 1]; // mirror of the forward rescale at step s
-            if (k != 0) {
-                const float sc = pow2i(k);
+            if (CORR && kstep != 0) { // mirror of the forward rescale at step s
+                const float sc = pow2i(kstep);
 #pragma unroll
-                for (int c = 0; c < C; c++) { BI[c] *= sc; BMo[c] *= sc; inD[c] *= sc; inMa[c] *= sc; inMb[c] *= sc; }
+                for (int c = 0; c < C; c++) { st.BI[c] *= sc; st.BMo[c] *= sc; st.inD[c] *= sc; st.inMa[c] *= sc; st.inMb[c] *= sc; }
             }
-            cen -= (bw[(s - 1) >> 5] >> ((s - 1) & 31)) & 1u;
+            cen -= (bword >> ((s - 1) & 31)) & 1u;
+            if (((s - 1) & 31) == 0 && s > 1) bword = pc.bw[(s - 2) >> 5];
+        }
+        --s;
+        rp -= RS;
+    };
+    using T = std::true_type;
+    using F = std::false_type;
+    body(T{}, T{});
+    while (s >= 0) {
+        while (es > s + 3) { ei--; es = ei >= 0 ? (int)ev_s[ei] : -100; }
+        if (!ev_over && es < s - 2) {
+            const int s_end = max(es + 3, 0); // rows down to here see no rescale inside s-2 .. s+3
+            while (s >= s_end) body(F{}, F{});
+        } else {
+            body(T{}, F{});
         }
     }
     // columns still alive after s = 0 (column 0), then the remaining blocks
 #pragma unroll
     for (int c = 0; c < C; c++)
-        if (j[c] >= 0 && j[c] <= Lt) flush_col(c);
+        if (st.j[c] >= 0 && st.j[c] <= Lt) flush_col(c);
     while (blk_lo >= 0) { emit_block(blk_lo); blk_lo -= 32; }
 }
 
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-struct __align__(16) SmemLayout {
-    float models[2 * kModelFloats];
-    float stage[kWarpsPerCta][kStageCols * kStageStride];
-    float ftot[kWarpsPerCta][4];
-};
+__device__ __forceinline__ PairCtx make_pair_ctx(const KParams &p, const DevPair &P, SmemLayout &sh) {
+    PairCtx pc;
+    pc.Tb = p.codes + P.tb_off;
+    pc.RbP = p.codes + P.rb_off - kCodePad;
+    pc.bw = p.bits + P.bits_off;
+    pc.Lt = P.Lt; pc.Lr = P.Lr; pc.nd = P.Lt + P.Lr + 1; pc.r = p.radius;
+    pc.sEM = (unsigned)__cvta_generic_to_shared(&sh.em[P.model][0]);
+    pc.sEI = (unsigned)__cvta_generic_to_shared(&sh.ei[P.model][0]);
+    pc.sEMT = (unsigned)__cvta_generic_to_shared(&sh.emt[P.model][0]);
+    return pc;
+}
 
 template <int C, int ROWS>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) modtable_kernel(KParams p) {
     __shared__ SmemLayout sh;
-    for (int k = threadIdx.x; k < 2 * kModelFloats; k += blockDim.x) sh.models[k] = p.models[k];
-    __syncthreads();
+    fill_tables(sh, p.models);
     constexpr int NSLOT = 32 * C;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t wslot = (size_t)blockIdx.x * kWarpsPerCta + warp;
-    float2 *frow = p.frows + wslot * p.frow_stride + 3 * NSLOT; // row 0 (3 zero rows below)
+    constexpr int RS = NSLOT + 2 * kHalo;
+    float2 *frow = p.frows + wslot * p.frow_stride + 3 * RS; // row 0 (3 zero rows below)
     int32_t *kf = p.kf + wslot * p.kf_stride + 3;
     // rows -3..-1 (before the first anti-diagonal) read as zero, exponent 0
-    for (int k = lane; k < 3 * NSLOT; k += 32) frow[k - 3 * NSLOT] = make_float2(0.f, 0.f);
+    for (int k = lane; k < 3 * RS; k += 32) frow[k - 3 * RS] = make_float2(0.f, 0.f);
     if (lane < 3) kf[lane - 3] = 0;
     __syncwarp();
     for (;;) {
@@ -358,19 +534,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) modtable_kernel(KParams p) 
         pi = __shfl_sync(kFull, pi, 0);
         if (pi >= p.n_pairs) break;
         const DevPair P = p.pairs[pi];
-        const int nd = P.Lt + P.Lr + 1;
-        const float *sm = sh.models + P.model * kModelFloats;
+        const PairCtx pc = make_pair_ctx(p, P, sh);
+        const Coef a = load_coef(sh.trans[P.model]);
         int Ktot;
-        forward_pass<C, true>(P, p.codes, p.bits, sm, p.radius, frow, kf, sh.ftot[warp], Ktot);
+        int ev_n;
+        forward_pass<C, true>(pc, a, frow, kf, sh.ftot[warp], Ktot, sh.ev_s[warp], ev_n);
         // rows / exponents just past the last anti-diagonal read as zero / Ktot
-        for (int k = lane; k < 3 * NSLOT; k += 32) frow[(size_t)nd * NSLOT + k] = make_float2(0.f, 0.f);
-        if (lane < 3) kf[nd + lane] = Ktot;
+        for (int k = lane; k < 3 * RS; k += 32) frow[(size_t)pc.nd * RS + k] = make_float2(0.f, 0.f);
+        if (lane < 3) kf[pc.nd + lane] = Ktot;
         __syncwarp();
         const float fin = sh.ftot[warp][0];
         if (lane == 0)
             p.out_lk[pi] = fin > 0.f ? log((double)fin) - (double)Ktot * 0.6931471805599453 : -INFINITY;
-        backward_pass<C, ROWS>(P, p.codes, p.bits, sm, p.radius, frow, kf, sh.stage[warp], sh.ftot[warp],
-                               p.out_delta + P.tab_off);
+        backward_pass<C, ROWS>(pc, a, frow, kf, sh.stage[warp], sh.ftot[warp], p.out_delta + P.tab_off, sh.ev_s[warp], ev_n);
         __syncwarp();
     }
 }
@@ -378,8 +554,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) modtable_kernel(KParams p) 
 template <int C>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) likelihood_kernel(KParams p) {
     __shared__ SmemLayout sh;
-    for (int k = threadIdx.x; k < 2 * kModelFloats; k += blockDim.x) sh.models[k] = p.models[k];
-    __syncthreads();
+    fill_tables(sh, p.models);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (;;) {
         int pi = 0;
@@ -387,9 +562,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) likelihood_kernel(KParams p
         pi = __shfl_sync(kFull, pi, 0);
         if (pi >= p.n_pairs) break;
         const DevPair P = p.pairs[pi];
-        const float *sm = sh.models + P.model * kModelFloats;
+        const PairCtx pc = make_pair_ctx(p, P, sh);
+        const Coef a = load_coef(sh.trans[P.model]);
         int Ktot;
-        forward_pass<C, false>(P, p.codes, p.bits, sm, p.radius, nullptr, nullptr, sh.ftot[warp], Ktot);
+        int ev_n;
+        forward_pass<C, false>(pc, a, nullptr, nullptr, sh.ftot[warp], Ktot, nullptr, ev_n);
         const float fin = sh.ftot[warp][0];
         if (lane == 0)
             p.out_lk[pi] = fin > 0.f ? log((double)fin) - (double)Ktot * 0.6931471805599453 : -INFINITY;
@@ -400,7 +577,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) likelihood_kernel(KParams p
 // host-callable launchers ---------------------------------------------------------------------------
 int cols_per_lane_for_radius(int radius) {
     // the slot ring must satisfy 2r + 4 <= 32*C
-    for (int c = 1; c <= 8; c *= 2)
+    for (int c = 2; c <= 8; c *= 2)
         if (2 * radius + 4 <= 32 * c) return c;
     return 0;
 }
@@ -414,7 +591,6 @@ static cudaError_t launch_modtable_c(const KParams &p, int rows, int grid, cudaS
 
 cudaError_t launch_modtable(const KParams &p, int C, int grid, cudaStream_t st) {
     switch (C) {
-    case 1: return launch_modtable_c<1>(p, p.rows, grid, st);
     case 2: return launch_modtable_c<2>(p, p.rows, grid, st);
     case 4: return launch_modtable_c<4>(p, p.rows, grid, st);
     default: return cudaErrorInvalidValue;
@@ -423,7 +599,6 @@ cudaError_t launch_modtable(const KParams &p, int C, int grid, cudaStream_t st) 
 
 cudaError_t launch_likelihood(const KParams &p, int C, int grid, cudaStream_t st) {
     switch (C) {
-    case 1: likelihood_kernel<1><<<grid, kWarpsPerCta * 32, 0, st>>>(p); break;
     case 2: likelihood_kernel<2><<<grid, kWarpsPerCta * 32, 0, st>>>(p); break;
     case 4: likelihood_kernel<4><<<grid, kWarpsPerCta * 32, 0, st>>>(p); break;
     default: return cudaErrorInvalidValue;
@@ -432,6 +607,7 @@ cudaError_t launch_likelihood(const KParams &p, int C, int grid, cudaStream_t st
 }
 
 int warps_per_cta() { return kWarpsPerCta; }
+int frow_slots_per_row(int C) { return 32 * C + 2 * kHalo; }
 
 // ---- FP32 peak micro-benchmark (roofline denominator) ---------------------------------------------------
 // 16 independent accumulators per thread so the 4-cycle FMA latency is covered at 8 warps per scheduler.
