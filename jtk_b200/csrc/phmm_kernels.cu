@@ -31,7 +31,7 @@ constexpr int kScaleTarget = 100;
 constexpr int kScaleStep = 64;
 constexpr int kProductExp = 0;
 constexpr int kMaxEvents = 96;  // rescale events remembered per pair for the backward fast path
-constexpr int kPrefetchRows = 3; // backward pass: rows pulled into L1 this many steps before their first use
+constexpr int kPrefetchRows = 4; // backward pass: rows pulled into L1 this many steps before their first use
 constexpr int kHalo = 4;        // forward rows carry 4 replicated slots on both sides: neighbours need no wrap-around
 
 // ---- small helpers --------------------------------------------------------------------------------------
@@ -41,6 +41,8 @@ __device__ __forceinline__ f2 mk2(float lo, float hi) { f2 r; asm("mov.b64 %0, {
 __device__ __forceinline__ float lo2(f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
 __device__ __forceinline__ float hi2(f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// acc += a * b, accumulator tied in place (keeps loop-carried sums out of the register allocator's copy lists)
+__device__ __forceinline__ void acc2(f2 &acc, f2 a, f2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 bc2(float v) { return mk2(v, v); }
 
@@ -299,12 +301,12 @@ __device__ __forceinline__ void bwd_step(const PairCtx &pc, const Coef &a, BwdSt
         // ---- table reduction for cell (i, j) ----
         const float f0m = lo2(F0[c]), f0d = hi2(F0[c]);
         const f2 U = bc2(f0m * st.inMb[c]);
-        st.S01[c] = fma2(U, ec01, st.S01[c]);
-        st.S23[c] = fma2(U, ec23, st.S23[c]);
+        acc2(st.S01[c], U, ec01);
+        acc2(st.S23[c], U, ec23);
         st.Vs[c] = fmaf(f0d, st.inD[c], st.Vs[c]);
         const f2 U2 = bc2(f0m * st.BMo[c]);
-        st.N01[c] = fma2(U2, ec01, st.N01[c]);
-        st.N23[c] = fma2(U2, ec23, st.N23[c]);
+        acc2(st.N01[c], U2, ec01);
+        acc2(st.N23[c], U2, ec23);
         st.Vn[c] = fmaf(f0d, hi2(md), st.Vn[c]);
         // cuts pairing this column's backward terms with forward columns j-1..j-3 (deletions) and j+1..j+3
         // (copies).  gM/gD vanish outside x in [-1, W+1] by themselves; x = W+1 must not feed a deletion and
@@ -316,8 +318,8 @@ __device__ __forceinline__ void bwd_step(const PairCtx &pc, const Coef &a, BwdSt
             for (int e = 1; e <= NXM; e++) {
                 f2 Fe;
                 asm("ld.global.b64 %0, [%1];" : "=l"(Fe) : "l"(rp + (c - e * RS - e)));
-                if (CORR) st.Xm[c][e - 1] = fma2(mul2(Fe, g), bc2(ce[3 - e]), st.Xm[c][e - 1]);
-                else st.Xm[c][e - 1] = fma2(Fe, g, st.Xm[c][e - 1]);
+                if (CORR) acc2(st.Xm[c][e - 1], mul2(Fe, g), bc2(ce[3 - e]));
+                else acc2(st.Xm[c][e - 1], Fe, g);
             }
         }
         if (NXP > 0) {
@@ -327,8 +329,8 @@ __device__ __forceinline__ void bwd_step(const PairCtx &pc, const Coef &a, BwdSt
             for (int e = 1; e <= NXP; e++) {
                 f2 Fe;
                 asm("ld.global.b64 %0, [%1];" : "=l"(Fe) : "l"(rp + (c + e * RS + e)));
-                if (CORR) st.Xp[c][e - 1] = fma2(mul2(Fe, g), bc2(ce[3 + e]), st.Xp[c][e - 1]);
-                else st.Xp[c][e - 1] = fma2(Fe, g, st.Xp[c][e - 1]);
+                if (CORR) acc2(st.Xp[c][e - 1], mul2(Fe, g), bc2(ce[3 + e]));
+                else acc2(st.Xp[c][e - 1], Fe, g);
             }
         }
         bMD[c] = md;
