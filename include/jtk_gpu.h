@@ -155,6 +155,46 @@ int jtk_batch_colstats(jtk_batch *b, const float *min_req /* 3*H */, int H, floa
  * reads in batch order (filter_by, pseudo_mcmc.rs:70-75) */
 int jtk_batch_gather(jtk_batch *b, int tmpl, const float *min_req, int H, const uint32_t *cols, int D, double *out);
 
+/* ---- host side of local_clustering: everything in pseudo_mcmc.rs that is not the pair HMM ---------------- */
+/* likelihood_gains::Gains (likelihood_gains.rs:56-62): expected gain and null probability per (DiffType, homopolymer
+ * length 1..homop_len); rows in DiffType order Subst, Del, Ins (likelihood_gains.rs:195-199). */
+typedef struct {
+    int homop_len;
+    const double *gain; /* 3 * homop_len */
+    const double *prob; /* 3 * homop_len */
+} jtk_gains;
+/* pseudo_mcmc::ClusteringConfig (pseudo_mcmc.rs:18-43) */
+typedef struct {
+    int band_width;
+    int copy_num;
+    double coverage;       /* haploid coverage */
+    double local_coverage; /* per-cluster coverage */
+} jtk_clustering_config;
+
+/*
+ * pseudo_mcmc::clustering (pseudo_mcmc.rs:77-107) given the per-read profiles (table - lk) of one chunk:
+ * compress_small_gains, filter_profiles, pick_filtered_profiles, cluster_filtered_variants, re-assignment and
+ * posteriors.  profiles: n_reads x (Lt+1)*JTK_NUM_ROW, row-major.  The generator is
+ * Xoshiro256StarStar::seed_from_u64(seed) (local_clustering/mod.rs:97 uses chunk.id * 3490).
+ * out_asn[n_reads]; out_post[n_reads * post_stride] holds log-posteriors of the first *out_k clusters per read;
+ * out_probe_pos (may be NULL) receives the selected flat positions j*NUM_ROW+row.
+ */
+int jtk_lc_clustering_profiles(const double *profiles, int n_reads, const uint8_t *tmpl, int Lt, const uint8_t *strands,
+                               const jtk_gains *gains, const jtk_clustering_config *cfg, uint64_t seed, uint64_t *out_asn,
+                               double *out_post, int post_stride, double *out_score, int *out_k, uint32_t *out_probe_pos,
+                               int probe_cap, int *out_n_probes);
+/* The same with the chunk's profiles resident in a batch: stats = this template's slice of jtk_batch_colstats;
+ * candidate columns are fetched with jtk_batch_gather. */
+int jtk_lc_clustering_batch(jtk_batch *b, int tmpl_index, const uint8_t *tmpl, int Lt, int n_reads, const jtk_colstat *stats,
+                            const jtk_gains *gains, const jtk_clustering_config *cfg, uint64_t seed, uint64_t *out_asn,
+                            double *out_post, int post_stride, double *out_score, int *out_k, uint32_t *out_probe_pos,
+                            int probe_cap, int *out_n_probes);
+const char *jtk_lc_last_error(void);
+/* hooks for the reference's unit tests on these files (pseudo_mcmc.rs:876-904) and the generator */
+double jtk_lc_cosine_similarity(const double *profiles, int n, int ncol, int i, int j);
+int jtk_lc_homopolymer_length(const uint8_t *xs, int n, uint32_t *out);
+void jtk_lc_rng_words(uint64_t seed, int use_state, const uint64_t *state, int n, uint64_t *out);
+
 /* in-band cell count C = sum_d w(d) of one pair (SURVEY.md section 8d work unit); <0 if ops are invalid */
 int64_t jtk_band_cell_count(const uint8_t *ops, int n_ops, int Lt, int Lr, int radius);
 

@@ -1,0 +1,795 @@
+// local_clustering.cpp -- host side of haplotyper::local_clustering (everything in pseudo_mcmc.rs that is not the
+// pair-HMM): compress_small_gains, filter_profiles, pick_filtered_profiles, k-means++ / MCMC clustering, posteriors.
+//
+// Line-by-line restatement of /root/reference/haplotyper/src/local_clustering/pseudo_mcmc.rs, misc.rs:84-92,231-341 and
+// likelihood_gains.rs:56-158.  In the real drop-in these loops stay in Rust; this C++ twin exists so
+// that the CUDA tables can be checked end to end here: identical profiles must give identical probe columns and
+// assignments.  The random streams follow rand 0.8.5 / rand_xoshiro 0.6.0 (Cargo.lock:621-663) as published:
+// Xoshiro256** seeded through SplitMix64, widening-multiply range sampling, Bernoulli via 64-bit threshold,
+// reservoir `IteratorRandom::choose`, cumulative-weight `choose_weighted`.  Those crates are
+// not under /root/reference, so stream identity with the Rust build is unpinned; determinism and every reference
+// assertion are tested.
+#include "../../include/jtk_gpu.h"
+
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace jtk {
+namespace host {
+
+constexpr int NUM_ROW = JTK_NUM_ROW;
+constexpr int COPY_SIZE = JTK_COPY_SIZE;
+constexpr size_t MASK_LENGTH = 7;     // pseudo_mcmc.rs:3
+constexpr size_t MAX_HOMOP_LENGTH = 2; // :4
+constexpr double POS_THR = 0.00001;   // :5
+constexpr double MIN_REQ_FRACTION = 0.5; // :140
+constexpr double EXPT_GAIN_FACTOR = 0.8; // :286
+constexpr int ROUND = 3;              // :421
+constexpr double PVALUE = 0.05;       // :422
+
+struct Panic : std::runtime_error { using std::runtime_error::runtime_error; };
+#define JTK_ASSERT(c, msg) do { if (!(c)) throw Panic(std::string("assertion failed: ") + msg); } while (0)
+
+enum DiffType { Subst = 0, Del = 1, Ins = 2 }; // likelihood_gains.rs:195-199
+
+// ---------------------------------------------------------------------------------------------- rand 0.8.5
+struct Rng { // rand_xoshiro::Xoshiro256StarStar
+    uint64_t s[4];
+    static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+    explicit Rng(uint64_t seed) { // seed_from_u64: SplitMix64 fills the state
+        uint64_t x = seed;
+        for (int i = 0; i < 4; i++) {
+            x += 0x9e3779b97f4a7c15ULL;
+            uint64_t z = x;
+            z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+            z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+            s[i] = z ^ (z >> 31);
+        }
+    }
+    uint64_t next_u64() {
+        const uint64_t result = rotl(s[1] * 5, 7) * 9;
+        const uint64_t t = s[1] << 17;
+        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3];
+        s[2] ^= t;
+        s[3] = rotl(s[3], 45);
+        return result;
+    }
+    uint32_t next_u32() { return (uint32_t)(next_u64() >> 32); }
+    // UniformInt<usize>::sample_single_inclusive(0, n-1)
+    size_t gen_range(size_t n) {
+        JTK_ASSERT(n > 0, "gen_range: empty range");
+        const uint64_t range = n;
+        const uint64_t zone = (range << __builtin_clzll(range)) - 1;
+        for (;;) {
+            const uint64_t v = next_u64();
+            const unsigned __int128 m = (unsigned __int128)v * range;
+            if ((uint64_t)m <= zone) return (size_t)(m >> 64);
+        }
+    }
+    // rand::seq::gen_index
+    size_t gen_index(size_t ubound) {
+        if (ubound <= 0xffffffffULL) {
+            const uint32_t range = (uint32_t)ubound;
+            JTK_ASSERT(range > 0, "gen_index: empty range");
+            const uint32_t zone = (range << __builtin_clz(range)) - 1;
+            for (;;) {
+                const uint32_t v = next_u32();
+                const uint64_t m = (uint64_t)v * range;
+                if ((uint32_t)m <= zone) return (size_t)(m >> 32);
+            }
+        }
+        return gen_range(ubound);
+    }
+    // Bernoulli::new(p).sample
+    bool gen_bool(double p) {
+        if (!(p >= 0.0 && p < 1.0)) {
+            if (p == 1.0) return true; // ALWAYS_TRUE: no draw
+            throw Panic("gen_bool: p is outside range [0.0, 1.0]");
+        }
+        const uint64_t p_int = (uint64_t)(p * 18446744073709551616.0);
+        return next_u64() < p_int;
+    }
+    // Uniform<f64>::new(0, total).sample
+    double uniform0(double total) {
+        const uint64_t bits = (next_u64() >> 12) | (1023ULL << 52);
+        double v12;
+        std::memcpy(&v12, &bits, 8);
+        return (v12 - 1.0) * total + 0.0;
+    }
+    // SliceRandom::choose_weighted -> index; panics like unwrap() on invalid / all-zero weights
+    size_t choose_weighted(const std::vector<double> &w) {
+        JTK_ASSERT(!w.empty(), "choose_weighted: NoItem");
+        double total = w[0];
+        JTK_ASSERT(total >= 0.0, "choose_weighted: InvalidWeight");
+        std::vector<double> cum;
+        cum.reserve(w.size());
+        for (size_t i = 1; i < w.size(); i++) {
+            JTK_ASSERT(w[i] >= 0.0, "choose_weighted: InvalidWeight");
+            cum.push_back(total);
+            total += w[i];
+        }
+        JTK_ASSERT(total != 0.0, "choose_weighted: AllWeightsZero");
+        const double chosen = uniform0(total);
+        size_t lo = 0, hi = cum.size(); // first cumulative weight > chosen
+        while (lo < hi) {
+            const size_t mid = lo + (hi - lo) / 2;
+            if (cum[mid] <= chosen) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    }
+    // IteratorRandom::choose over (0..k).filter(|x| x != old): size_hint lower bound 0 -> one draw per element
+    size_t choose_other(size_t k, size_t old) {
+        size_t consumed = 0, result = (size_t)-1;
+        for (size_t x = 0; x < k; x++) {
+            if (x == old) continue;
+            consumed++;
+            if (gen_index(consumed) == 0) result = x;
+        }
+        JTK_ASSERT(result != (size_t)-1, "choose: empty iterator");
+        return result;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- Gains / Pvalues
+struct Gains { // likelihood_gains.rs:56-112
+    int H = 0;
+    std::vector<double> gain[3], prob[3]; // indexed by DiffType
+    double expected(size_t homop_len, DiffType t) const {
+        JTK_ASSERT(0 < homop_len, "0 < homop_len");
+        const size_t h = std::min<size_t>(homop_len, (size_t)H);
+        return gain[t][h - 1];
+    }
+};
+
+static double logsumexp2(double x, double y) { // likelihood_gains.rs:131-137
+    return (y < x) ? x + std::log(1.0 + std::exp(y - x)) : y + std::log(1.0 + std::exp(x - y));
+}
+// i -> Prob(i <= X | n, prob)   (likelihood_gains.rs:115-129)
+static std::vector<double> pvalues_of(double prob, size_t n) {
+    const double ln = std::log(prob), in_ln = std::log(1.0 - prob);
+    std::vector<double> lp{ in_ln * (double)n };
+    for (size_t k = 0; k < n; k++) {
+        const double prev = lp.back();
+        const double offset = ln + std::log((double)(n - k)) - in_ln - std::log((double)(k + 1));
+        lp.push_back(prev + offset);
+    }
+    for (size_t k = n; k-- > 0;) lp[k] = logsumexp2(lp[k + 1], lp[k]);
+    for (double &x : lp) x = std::exp(x);
+    return lp;
+}
+struct Pvalues {
+    int H; size_t total;
+    std::vector<std::vector<double>> tab[3];
+    double pvalue(size_t homop_len, DiffType t, size_t count) const { // likelihood_gains.rs:148-158
+        JTK_ASSERT(0 < homop_len, "0 < homop_len");
+        JTK_ASSERT(count <= total, "count <= total");
+        const size_t h = std::min<size_t>(homop_len, (size_t)H);
+        return tab[t][h - 1][count];
+    }
+};
+static Pvalues make_pvalues(const Gains &g, size_t total) {
+    Pvalues p; p.H = g.H; p.total = total;
+    for (int t = 0; t < 3; t++)
+        for (int h = 0; h < g.H; h++) p.tab[t].push_back(pvalues_of(g.prob[t][h], total));
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------- small helpers
+static double logsumexp(const std::vector<double> &xs) { // misc.rs:84-92
+    if (xs.empty()) return 0.;
+    const double mx = *std::max_element(xs.begin(), xs.end());
+    double sum = 0;
+    for (double x : xs) sum += std::exp(x - mx);
+    sum = std::log(sum);
+    JTK_ASSERT(sum >= 0., "logsumexp sum >= 0");
+    return mx + sum;
+}
+
+static void pos_to_bp_and_difftype(size_t pos, size_t &bp, DiffType &t) { // pseudo_mcmc.rs:168-178
+    bp = pos / NUM_ROW;
+    const size_t op = pos % NUM_ROW;
+    t = op < 4 ? Subst : (op < 8 + (size_t)COPY_SIZE ? Ins : Del);
+}
+
+std::vector<size_t> homopolymer_length(const uint8_t *xs, size_t n) { // pseudo_mcmc.rs:195-211
+    std::vector<size_t> homop;
+    if (n == 0) return homop;
+    uint8_t current = xs[0];
+    size_t length = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (xs[i] == current) length++;
+        else { homop.insert(homop.end(), length, length); current = xs[i]; length = 1; }
+    }
+    homop.insert(homop.end(), length, length);
+    JTK_ASSERT(homop.size() == n, "homop.len() == xs.len()");
+    return homop;
+}
+
+static double poisson_lk(size_t x, double lambda) { // :636-638
+    double s = 0;
+    for (size_t c = 1; c < x + 1; c++) s += std::log((double)c);
+    return (double)x * std::log(lambda) - lambda - s;
+}
+static double max_poisson_lk(size_t x, double lambda, size_t c_start, size_t c_end) { // :641-645
+    double best = -std::numeric_limits<double>::infinity();
+    for (size_t c = std::max<size_t>(c_start, 1); c <= c_end; c++) best = std::max(best, poisson_lk(x, lambda * (double)c));
+    return best;
+}
+
+struct ColStat { double sum; size_t count; size_t sc[4]; }; // sc[strand*2 + positive]
+
+// is_explainable_by_strandedness (:314-339) from the 2x2 counts
+static bool explainable_by_strandedness(const ColStat &c) {
+    size_t strand_count[2] = { c.sc[0] + c.sc[1], c.sc[2] + c.sc[3] };
+    size_t sign_count[2] = { c.sc[0] + c.sc[2], c.sc[1] + c.sc[3] };
+    const size_t sum = strand_count[0] + strand_count[1];
+    if (sum == 0) return false;
+    double chisq = 0;
+    for (int st = 0; st < 2; st++)
+        for (int sg = 0; sg < 2; sg++) {
+            const double expected = (double)(strand_count[st] * sign_count[sg]) / (double)sum;
+            const double obs = (double)c.sc[st * 2 + sg];
+            chisq += (obs - expected) * (obs - expected) / expected; // 0/0 -> NaN, NaN < 10 is false (as in Rust)
+        }
+    return chisq < 10.0;
+}
+
+static bool is_in_short_homopolymer(size_t pos, const std::vector<size_t> &homop, const uint8_t *tmpl, size_t Lt) { // :497-514
+    size_t x; DiffType t;
+    pos_to_bp_and_difftype(pos, x, t);
+    if (t == Ins) {
+        const size_t r = pos % NUM_ROW - 4;
+        const uint8_t base = r < 4 ? (uint8_t)"ACGT"[r] : 0;
+        JTK_ASSERT(x >= 1, "index out of bounds: template[x - 1]");
+        const size_t prev_len = (0 < x) ? homop[x - 1] + (tmpl[x - 1] == base) : (size_t)(tmpl[x - 1] == base);
+        JTK_ASSERT(x < Lt, "index out of bounds: template[x]");
+        const size_t next_len = (x < Lt) ? homop[x] + (tmpl[x] == base) : (size_t)(tmpl[x] == base);
+        return prev_len <= MAX_HOMOP_LENGTH && next_len <= MAX_HOMOP_LENGTH;
+    }
+    if (t == Del && x < Lt) return homop[x] <= MAX_HOMOP_LENGTH;
+    return true;
+}
+
+static bool has_small_pvalue(size_t pos, double gain, size_t count, const std::vector<size_t> &homop, const Pvalues &pv,
+                             const Gains &gains, size_t template_len) { // :476-495
+    size_t bp; DiffType t;
+    pos_to_bp_and_difftype(pos, bp, t);
+    const size_t homop_len = bp < homop.size() ? homop[bp] : 0;
+    double pvalue = pv.pvalue(homop_len, t, count);
+    const double expt = gains.expected(homop_len, t) * EXPT_GAIN_FACTOR;
+    pvalue = (double)template_len * pvalue;
+    return (double)count * expt < gain && pvalue < PVALUE / (double)template_len;
+}
+
+// candidate columns after the per-column filters of filter_profiles (:440-466), before the greedy pick
+struct Probe { size_t pos; double lk; };
+
+static std::vector<Probe> candidate_probes(const uint8_t *tmpl, size_t Lt, const std::vector<ColStat> &stats, size_t n_reads,
+                                           const Gains &gains, size_t cluster_num, double coverage) {
+    const Pvalues pv = make_pvalues(gains, n_reads);
+    const std::vector<size_t> homop = homopolymer_length(tmpl, Lt);
+    const size_t temp_len = stats.size() / NUM_ROW;
+    std::vector<Probe> probes;
+    for (size_t pos = 0; pos < stats.size(); pos++) {
+        const size_t bp = pos / NUM_ROW, row = pos % NUM_ROW;
+        if (!(MASK_LENGTH <= bp && bp <= temp_len - MASK_LENGTH)) continue;
+        if (!(row < 8 || row == 8 + (size_t)COPY_SIZE)) continue;
+        if (!is_in_short_homopolymer(pos, homop, tmpl, Lt)) continue;
+        if (!has_small_pvalue(pos, stats[pos].sum, stats[pos].count, homop, pv, gains, temp_len)) continue;
+        if (!explainable_by_strandedness(stats[pos])) continue;
+        double max_lk = -std::numeric_limits<double>::infinity();
+        bool any = false;
+        for (size_t k = 1; k < cluster_num + 1; k++) {
+            const double v = poisson_lk(stats[pos].count, coverage * (double)k);
+            if (!any || !(v < max_lk)) max_lk = v; // Iterator::max_by keeps the last of equal maxima
+            any = true;
+        }
+        JTK_ASSERT(any, "cluster_num");
+        const double total_lk = max_lk + stats[pos].sum;
+        if (0.0 < total_lk) probes.push_back({ pos, total_lk });
+    }
+    return probes;
+}
+
+// values of the candidate columns: cand[r * M + m] = compressed profile of read r at probes[m].pos
+static double cosine_similarity(const std::vector<double> &cand, size_t n, size_t M, size_t i, size_t j) { // :602-615
+    double ip = 0, isq = 0, jsq = 0;
+    for (size_t r = 0; r < n; r++) {
+        const double x = cand[r * M + i], y = cand[r * M + j];
+        if (POS_THR < std::fabs(x) && POS_THR < std::fabs(y)) { ip += x * y; isq += x * x; jsq += y * y; }
+    }
+    if (isq == 0.0) return 0.0;
+    return ip / std::sqrt(isq) / std::sqrt(jsq);
+}
+static double sokal_michener(const std::vector<double> &cand, size_t n, size_t M, size_t i, size_t j) { // :618-633
+    size_t mat = 0, mism = 0;
+    for (size_t r = 0; r < n; r++) {
+        const double x = cand[r * M + i], y = cand[r * M + j];
+        if (POS_THR < std::fabs(x) && POS_THR < std::fabs(y)) { if (0.0 < x * y) mat++; else mism++; }
+    }
+    const size_t total = mat + mism;
+    return total == 0 ? 0.0 : (double)std::max(mism, mat) / (double)total;
+}
+
+// pick_filtered_profiles (:516-575): returns indices into probes, in probe order
+static std::vector<size_t> pick_filtered_profiles(const std::vector<Probe> &probes, const std::vector<double> &cand, size_t n,
+                                                  size_t cluster_num) {
+    const size_t M = probes.size();
+    std::vector<uint8_t> sel(M, 0);
+    for (int round = 0; round < ROUND; round++) {
+        for (auto &b : sel) if (b == 3) b = 0;
+        for (size_t it = 0; it < std::max<size_t>(cluster_num, 2); it++) {
+            // find_next_variants (:590-600): max_by keeps the last maximum
+            bool found = false; size_t next = 0; double best = 0;
+            for (size_t m = 0; m < M; m++)
+                if (sel[m] == 0 && (!found || !(probes[m].lk < best))) { found = true; next = m; best = probes[m].lk; }
+            if (!found) break;
+            const size_t picked_bp = probes[next].pos / NUM_ROW;
+            sel[next] = 1;
+            for (size_t m = 0; m < M; m++) {
+                if (!(sel[m] == 0 || sel[m] == 3)) continue;
+                const size_t bp = probes[m].pos / NUM_ROW;
+                const size_t diff = std::max(bp, picked_bp) - std::min(bp, picked_bp);
+                if (diff < MASK_LENGTH) sel[m] = 2;
+                else {
+                    const double sok = sokal_michener(cand, n, M, next, m);
+                    const double cs = cosine_similarity(cand, n, M, next, m);
+                    if (0.8 < sok || 0.8 < std::fabs(cs)) sel[m] = 3;
+                }
+            }
+        }
+    }
+    std::vector<size_t> out;
+    for (size_t m = 0; m < M; m++) if (sel[m] == 1) out.push_back(m);
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------- clustering
+typedef std::vector<std::vector<double>> Mat;
+
+struct LKCount { // :797-845
+    double total_gain = 0; size_t num_pos = 0, num_neg = 0, num_zero = 0;
+    bool is_informative() const {
+        const double cov = (double)(num_pos + num_neg) + 0.0000001;
+        return 0.0 < total_gain && 0.70 < (double)num_pos / cov;
+    }
+    void add(double x) {
+        total_gain += x;
+        if (POS_THR < x) num_pos++; else if (x < -POS_THR) num_neg++; else { JTK_ASSERT(std::fabs(x) < POS_THR, "x.abs() < POS_THR"); num_zero++; }
+    }
+    void sub(double x) {
+        total_gain -= x;
+        if (POS_THR < x) num_pos--; else if (x < -POS_THR) num_neg--; else { JTK_ASSERT(std::fabs(x) < POS_THR, "x.abs() < POS_THR"); num_zero--; }
+    }
+};
+typedef std::vector<std::vector<LKCount>> LKs;
+
+static std::vector<bool> get_used_columns(const LKs &lks) { // :847-869
+    std::vector<bool> use(lks[0].size(), false);
+    for (const auto &row : lks) {
+        JTK_ASSERT(use.size() == row.size(), "to_uses.len() == lks.len()");
+        for (size_t d = 0; d < row.size(); d++) use[d] = use[d] | row[d].is_informative();
+    }
+    for (size_t d = 0; d < use.size(); d++) {
+        size_t in_use = 0, in_neg = 0;
+        for (const auto &row : lks) { if (0.0 < row[d].total_gain) in_use += row[d].num_pos; if (row[d].total_gain <= 0.0) in_neg += row[d].num_pos; }
+        use[d] = use[d] & ((double)in_neg * 2.0 < (double)in_use);
+    }
+    return use;
+}
+
+static double get_lk(const LKs &lks, const std::vector<size_t> &clusters, const std::vector<double> &size_to_lk) { // :785-795
+    const std::vector<bool> use = get_used_columns(lks);
+    double lk = 0;
+    for (size_t sz : clusters) lk += size_to_lk[sz];
+    for (const auto &row : lks)
+        for (size_t d = 0; d < row.size(); d++) if (use[d]) lk += std::max(row[d].total_gain, 0.0);
+    return lk;
+}
+
+static void build_lks(const Mat &data, const std::vector<size_t> &assign, size_t k, LKs &lks, std::vector<size_t> &clusters) {
+    clusters.assign(k, 0);
+    lks.assign(k, std::vector<LKCount>(data[0].size()));
+    for (size_t i = 0; i < data.size(); i++) {
+        clusters[assign[i]]++;
+        for (size_t d = 0; d < data[i].size(); d++) lks[assign[i]][d].add(data[i][d]);
+    }
+}
+
+static void flip(const Mat &data, std::vector<size_t> &assign, size_t idx, size_t to, LKs &lks, std::vector<size_t> &clusters) { // :764-783
+    const size_t from = assign[idx];
+    clusters[from]--;
+    for (size_t d = 0; d < data[idx].size(); d++) lks[from][d].sub(data[idx][d]);
+    assign[idx] = to;
+    clusters[to]++;
+    for (size_t d = 0; d < data[idx].size(); d++) lks[to][d].add(data[idx][d]);
+}
+
+static double mcmc_with_filter(const Mat &data, std::vector<size_t> &assign, size_t k, double cov, Rng &rng) { // :704-762
+    std::vector<double> size_to_lk;
+    for (size_t x = 0; x <= data.size(); x++) size_to_lk.push_back(max_poisson_lk(x, cov, 1, k));
+    for (double x : size_to_lk) JTK_ASSERT(!std::isnan(x), "is_valid_lk");
+    LKs lks; std::vector<size_t> clusters;
+    build_lks(data, assign, k, lks, clusters);
+    double lk = get_lk(lks, clusters, size_to_lk);
+    double mx = lk;
+    std::vector<size_t> argmax = assign;
+    const size_t total = 2000 * data.size();
+    for (size_t t = 0; t < total; t++) {
+        const size_t idx = rng.gen_range(data.size());
+        const size_t old = assign[idx];
+        const size_t nw = rng.choose_other(k, old);
+        flip(data, assign, idx, nw, lks, clusters);
+        const double proposed = get_lk(lks, clusters, size_to_lk);
+        const double diff = proposed - lk;
+        if (0.0 < diff || rng.gen_bool(std::exp(diff))) {
+            lk = proposed;
+            if (mx < lk) { mx = proposed; argmax = assign; }
+        } else flip(data, assign, idx, old, lks, clusters);
+    }
+    assign = argmax;
+    build_lks(data, assign, k, lks, clusters);
+    const double chk = get_lk(lks, clusters, size_to_lk);
+    JTK_ASSERT(std::fabs(mx - chk) < 0.0001, "(max - lk).abs() < 0.0001");
+    return mx;
+}
+
+// ---- misc::kmeans (misc.rs:231-341)
+static double dist2(const std::vector<double> &x, const std::vector<double> &y) {
+    JTK_ASSERT(x.size() == y.size(), "xs.len() == ys.len()");
+    double s = 0;
+    for (size_t i = 0; i < x.size(); i++) s += (x[i] - y[i]) * (x[i] - y[i]); // powi(2)
+    return s;
+}
+static void update_assignments(const Mat &data, const Mat &centers, std::vector<size_t> &asn) {
+    for (size_t i = 0; i < data.size(); i++) {
+        size_t best = 0; double bd = 0;
+        for (size_t c = 0; c < centers.size(); c++) {
+            const double d = dist2(data[i], centers[c]);
+            if (c == 0 || d < bd) { best = c; bd = d; } // min_by keeps the first minimum
+        }
+        asn[i] = best;
+    }
+}
+static std::vector<size_t> suggest_first(const Mat &data, size_t k, Rng &rng) {
+    JTK_ASSERT(k <= data.size(), "k <= data.len()");
+    Mat centers{ data[rng.gen_index(data.size())] };
+    for (size_t it = 0; it + 1 < k; it++) {
+        std::vector<double> dists(data.size());
+        for (size_t i = 0; i < data.size(); i++) {
+            double m = 0;
+            for (size_t c = 0; c < centers.size(); c++) { const double d = dist2(data[i], centers[c]); if (c == 0 || d < m) m = d; }
+            dists[i] = m;
+        }
+        centers.push_back(data[rng.choose_weighted(dists)]);
+    }
+    std::vector<size_t> asn(data.size(), 0);
+    update_assignments(data, centers, asn);
+    return asn;
+}
+static double get_dist(const Mat &data, const Mat &centers, const std::vector<size_t> &asn) {
+    double s = 0;
+    for (size_t i = 0; i < data.size(); i++) s += dist2(data[i], centers[asn[i]]);
+    return s;
+}
+static std::vector<size_t> kmeans(const Mat &data, size_t k, Rng &rng) {
+    JTK_ASSERT(1 <= k, "1 <= k");
+    const size_t dim = data[0].size();
+    JTK_ASSERT(0 < dim, "0 < dim");
+    std::vector<size_t> asn;
+    if (rng.gen_bool(0.5)) { asn.resize(data.size()); for (auto &a : asn) a = rng.gen_range(k); }
+    else asn = suggest_first(data, k, rng);
+    Mat centers(k, std::vector<double>(dim, 0.0));
+    std::vector<size_t> counts(k, 0);
+    double dist = get_dist(data, centers, asn);
+    for (;;) {
+        for (auto &c : centers) std::fill(c.begin(), c.end(), 0.0);
+        std::fill(counts.begin(), counts.end(), 0);
+        for (size_t i = 0; i < data.size(); i++) { for (size_t d = 0; d < dim; d++) centers[asn[i]][d] += data[i][d]; counts[asn[i]]++; }
+        for (size_t c = 0; c < k; c++) if (0 < counts[c]) for (double &x : centers[c]) x /= (double)counts[c];
+        update_assignments(data, centers, asn);
+        const double nd = get_dist(data, centers, asn);
+        JTK_ASSERT(nd < dist + 0.00000001, "new_dist < dist + UPDATE_THR");
+        if (dist - nd < 0.00000001) break;
+        dist = nd;
+    }
+    return asn;
+}
+
+struct ClusterOut { std::vector<size_t> asn; double score; std::vector<double> read_gains; std::vector<bool> used; };
+
+static void get_read_lk_gains(const Mat &variants, const std::vector<size_t> &asn, size_t k, std::vector<bool> &use, std::vector<double> &gain) { // :381-408
+    LKs lks; std::vector<size_t> clusters;
+    build_lks(variants, asn, k, lks, clusters);
+    use = get_used_columns(lks);
+    gain.assign(variants.size(), 0.0);
+    for (size_t i = 0; i < variants.size(); i++) {
+        double s = 0;
+        for (size_t d = 0; d < variants[i].size(); d++)
+            if (use[d] && POS_THR < lks[asn[i]][d].total_gain) s += variants[i][d];
+        gain[i] = s;
+    }
+}
+
+static ClusterOut mcmc_clustering(const Mat &data, size_t k, double cov, Rng &rng) { // :649-670
+    std::vector<size_t> best; double best_lk = 0; bool any = false;
+    for (int t = 0; t < 20; t++) {
+        std::vector<size_t> asn = kmeans(data, k, rng);
+        const double lk = mcmc_with_filter(data, asn, k, cov, rng);
+        if (!any || !(lk < best_lk)) { best = asn; best_lk = lk; any = true; } // max_by keeps the last maximum
+    }
+    ClusterOut o; o.asn = best;
+    get_read_lk_gains(data, o.asn, k, o.used, o.read_gains);
+    std::vector<size_t> counts(k, 0);
+    for (size_t a : o.asn) counts[a]++;
+    double cluster_lk = 0;
+    for (size_t c : counts) cluster_lk += max_poisson_lk(c, cov, 1, k);
+    o.score = best_lk - cluster_lk;
+    return o;
+}
+
+static ClusterOut use_highest_gain(const Mat &data) { // :673-693
+    const size_t dim = data[0].size();
+    std::vector<double> gains(dim, 0.0);
+    for (const auto &xs : data) for (size_t d = 0; d < dim; d++) gains[d] += std::max(xs[d], 0.0);
+    size_t mi = 0;
+    for (size_t d = 0; d < dim; d++) if (!(gains[d] < gains[mi])) mi = d; // last maximum
+    ClusterOut o;
+    for (const auto &xs : data) o.asn.push_back((size_t)(0.0 < xs[mi]));
+    get_read_lk_gains(data, o.asn, 2, o.used, o.read_gains);
+    o.score = 0;
+    for (double g : o.read_gains) o.score += g;
+    return o;
+}
+
+typedef std::vector<std::pair<size_t, DiffType>> VarTypes;
+
+static double min_gain(const Gains &g, const VarTypes &vt, const std::vector<bool> &used) { // :276-284
+    bool any = false; double m = 0;
+    for (size_t d = 0; d < vt.size() && d < used.size(); d++)
+        if (used[d]) { const double v = g.expected(vt[d].first, vt[d].second) / 3.0; if (!any || v < m) { m = v; any = true; } }
+    return any ? m : 1.0;
+}
+static double expected_gains(const Gains &g, const VarTypes &vt, const std::vector<bool> &prev, const std::vector<bool> &used) { // :287-306
+    JTK_ASSERT(vt.size() == used.size(), "variant_type.len() == used_columns.len()");
+    const bool no_new = prev == used;
+    bool any = false; double m = 0;
+    for (size_t d = 0; d < vt.size(); d++) {
+        const bool check = ((!prev[d]) & used[d]) | no_new;
+        const double v = check ? g.expected(vt[d].first, vt[d].second) : 0.0000001;
+        if (!any || !(v < m)) { m = v; any = true; }
+    }
+    if (!any) m = 0.0;
+    return std::max(EXPT_GAIN_FACTOR * m, 0.1);
+}
+
+static Mat get_likelihood_gain(const Mat &variants, const std::vector<size_t> &asn, size_t k) { // :353-379
+    LKs lks; std::vector<size_t> clusters;
+    build_lks(variants, asn, k, lks, clusters);
+    const std::vector<bool> use = get_used_columns(lks);
+    Mat out;
+    for (const auto &vars : variants) {
+        std::vector<double> row;
+        for (const auto &slots : lks) {
+            double s = 0;
+            for (size_t d = 0; d < vars.size(); d++) if (use[d] && POS_THR < slots[d].total_gain) s += vars[d];
+            row.push_back(s);
+        }
+        out.push_back(row);
+    }
+    return out;
+}
+
+struct DevResult { std::vector<size_t> asn; Mat gains; double score; size_t k; };
+
+static DevResult cluster_filtered_variants(const Mat &variants, const VarTypes &vt, size_t copy_num, double coverage,
+                                           double per_cluster_cov, const Gains &gains, Rng &rng) { // :213-274
+    bool all_empty = true;
+    for (const auto &xs : variants) if (!xs.empty()) all_empty = false;
+    if (copy_num <= 1 || all_empty || variants.size() <= copy_num)
+        return { std::vector<size_t>(variants.size(), 0), Mat(variants.size(), std::vector<double>(1, 0.0)), 0.0, 1 };
+    const size_t n = variants.size();
+    std::vector<size_t> assignments(n, 0);
+    double mx = 0; size_t max_k = 1;
+    std::vector<double> read_lk_gains(n, 0.0);
+    std::vector<bool> prev_used(variants[0].size(), false);
+    const size_t end = std::min(copy_num, 1 + 2 * vt.size());
+    const size_t start = std::max<size_t>(end, 5) - 3;
+    for (size_t k = start; k <= end; k++) {
+        ClusterOut c = mcmc_clustering(variants, k, coverage, rng);
+        if (k == 2) {
+            ClusterOut h = use_highest_gain(variants);
+            if (c.score < h.score) c = h;
+        }
+        (void)min_gain(gains, vt, c.used); // count_improved_reads only feeds a trace! line
+        const double expected_gain = expected_gains(gains, vt, prev_used, c.used) * per_cluster_cov + 0.1;
+        if (expected_gain < c.score - mx) {
+            assignments = c.asn; mx = c.score; max_k = k; read_lk_gains = c.read_gains; prev_used = c.used;
+        } else break;
+    }
+    return { assignments, get_likelihood_gain(variants, assignments, max_k), mx, max_k };
+}
+
+// pseudo_mcmc::clustering (:77-107) after search_variants produced (variants, variant types)
+static DevResult clustering_tail(const Mat &variants, const VarTypes &vt, size_t copy_num, double coverage,
+                                 double local_coverage, const Gains &gains, Rng &rng) {
+    DevResult r = cluster_filtered_variants(variants, vt, copy_num, coverage, local_coverage, gains, rng);
+    for (size_t i = 0; i < r.asn.size(); i++) {
+        const auto &lks = r.gains[i];
+        size_t bi = 0;
+        for (size_t c = 0; c < lks.size(); c++) if (!(lks[c] < lks[bi])) bi = c; // last maximum
+        if (lks[r.asn[i]] + 0.001 < lks[bi]) r.asn[i] = bi;
+    }
+    for (auto &xs : r.gains) { const double tot = logsumexp(xs); for (double &x : xs) x -= tot; }
+    return r;
+}
+
+static Gains to_gains(const jtk_gains *g) {
+    Gains out; out.H = g->homop_len;
+    for (int t = 0; t < 3; t++) { out.gain[t].assign(g->gain + t * g->homop_len, g->gain + (t + 1) * g->homop_len); out.prob[t].assign(g->prob + t * g->homop_len, g->prob + (t + 1) * g->homop_len); }
+    return out;
+}
+
+} // namespace host
+} // namespace jtk
+
+using namespace jtk::host;
+
+namespace {
+thread_local std::string g_lc_error;
+
+int write_result(const DevResult &r, const std::vector<Probe> &probes, const std::vector<size_t> &picked, uint64_t *out_asn,
+                 double *out_post, int post_stride, double *out_score, int *out_k, uint32_t *out_probe_pos, int probe_cap,
+                 int *out_n_probes) {
+    if ((int)r.k > post_stride) { g_lc_error = "post_stride smaller than the cluster number"; return JTK_EINVAL; }
+    for (size_t i = 0; i < r.asn.size(); i++) {
+        out_asn[i] = r.asn[i];
+        for (size_t c = 0; c < r.k; c++) out_post[i * (size_t)post_stride + c] = r.gains[i][c];
+    }
+    *out_score = r.score; *out_k = (int)r.k;
+    if (out_n_probes) *out_n_probes = (int)picked.size();
+    if (out_probe_pos)
+        for (size_t m = 0; m < picked.size() && (int)m < probe_cap; m++) out_probe_pos[m] = (uint32_t)probes[picked[m]].pos;
+    return JTK_OK;
+}
+} // namespace
+
+extern "C" {
+
+const char *jtk_lc_last_error(void) { return g_lc_error.c_str(); }
+
+// pseudo_mcmc::clustering on host-resident profiles (pseudo_mcmc.rs:77-138).
+int jtk_lc_clustering_profiles(const double *profiles, int n_reads, const uint8_t *tmpl, int Lt, const uint8_t *strands,
+                               const jtk_gains *gains_c, const jtk_clustering_config *cfg, uint64_t seed, uint64_t *out_asn,
+                               double *out_post, int post_stride, double *out_score, int *out_k, uint32_t *out_probe_pos,
+                               int probe_cap, int *out_n_probes) {
+    try {
+        if (!profiles || !tmpl || !strands || !gains_c || !cfg || !out_asn || !out_post || !out_score || !out_k || n_reads < 0 || Lt < 1) {
+            g_lc_error = "null / bad argument"; return JTK_EINVAL;
+        }
+        const size_t n = (size_t)n_reads, ncol = (size_t)(Lt + 1) * NUM_ROW;
+        const size_t copy_num = (size_t)cfg->copy_num;
+        if (copy_num < 2) { // :86-88
+            for (size_t i = 0; i < n; i++) { out_asn[i] = 0; out_post[i * (size_t)post_stride] = 0.0; }
+            *out_score = 0.0; *out_k = 1; if (out_n_probes) *out_n_probes = 0;
+            return JTK_OK;
+        }
+        const Gains gains = to_gains(gains_c);
+        Rng rng(seed);
+        // compress_small_gains (:141-165) + column_sum (:577-588) + strand/sign counts (:314-322)
+        const std::vector<size_t> homop = homopolymer_length(tmpl, (size_t)Lt);
+        std::vector<double> min_req(ncol);
+        for (size_t pos = 0; pos < ncol; pos++) {
+            size_t bp; DiffType t;
+            pos_to_bp_and_difftype(pos, bp, t);
+            const size_t hl = bp < homop.size() ? homop[bp] : 1;
+            min_req[pos] = gains.expected(hl, t) * MIN_REQ_FRACTION;
+        }
+        std::vector<ColStat> stats(ncol, ColStat{ 0.0, 0, { 0, 0, 0, 0 } });
+        auto value = [&](size_t r, size_t pos) { const double x = profiles[r * ncol + pos]; return std::fabs(x) < min_req[pos] ? 0.0 : x; };
+        for (size_t r = 0; r < n; r++)
+            for (size_t pos = 0; pos < ncol; pos++) {
+                const double x = value(r, pos);
+                if (POS_THR < x) { stats[pos].sum += x; stats[pos].count++; }
+                if (std::fabs(x) > 0.0001) stats[pos].sc[(strands[r] ? 2 : 0) + (std::signbit(x) ? 0 : 1)]++;
+            }
+        const std::vector<Probe> probes = candidate_probes(tmpl, (size_t)Lt, stats, n, gains, copy_num, cfg->coverage);
+        const size_t M = probes.size();
+        std::vector<double> cand(n * M);
+        for (size_t r = 0; r < n; r++) for (size_t m = 0; m < M; m++) cand[r * M + m] = value(r, probes[m].pos);
+        const std::vector<size_t> picked = pick_filtered_profiles(probes, cand, n, copy_num);
+        Mat variants(n);
+        VarTypes vt;
+        for (size_t m : picked) {
+            size_t bp; DiffType t;
+            pos_to_bp_and_difftype(probes[m].pos, bp, t);
+            vt.push_back({ bp < homop.size() ? homop[bp] : 0, t });
+        }
+        for (size_t r = 0; r < n; r++) for (size_t m : picked) variants[r].push_back(cand[r * M + m]);
+        const DevResult res = clustering_tail(variants, vt, copy_num, cfg->coverage, cfg->local_coverage, gains, rng);
+        return write_result(res, probes, picked, out_asn, out_post, post_stride, out_score, out_k, out_probe_pos, probe_cap, out_n_probes);
+    } catch (const std::exception &e) {
+        g_lc_error = e.what();
+        return JTK_EINVAL;
+    }
+}
+
+// The same call with the profiles resident on the device: per-column statistics and the candidate columns come from
+// jtk_batch_colstats / jtk_batch_gather; everything after that is the same host code.
+int jtk_lc_clustering_batch(jtk_batch *b, int tmpl_index, const uint8_t *tmpl, int Lt, int n_reads, const jtk_colstat *stats_c,
+                            const jtk_gains *gains_c, const jtk_clustering_config *cfg, uint64_t seed, uint64_t *out_asn,
+                            double *out_post, int post_stride, double *out_score, int *out_k, uint32_t *out_probe_pos,
+                            int probe_cap, int *out_n_probes) {
+    try {
+        if (!b || !tmpl || !stats_c || !gains_c || !cfg || !out_asn || !out_post || !out_score || !out_k || n_reads < 0 || Lt < 1) {
+            g_lc_error = "null / bad argument"; return JTK_EINVAL;
+        }
+        const size_t n = (size_t)n_reads, ncol = (size_t)(Lt + 1) * NUM_ROW;
+        const size_t copy_num = (size_t)cfg->copy_num;
+        if (copy_num < 2) {
+            for (size_t i = 0; i < n; i++) { out_asn[i] = 0; out_post[i * (size_t)post_stride] = 0.0; }
+            *out_score = 0.0; *out_k = 1; if (out_n_probes) *out_n_probes = 0;
+            return JTK_OK;
+        }
+        const Gains gains = to_gains(gains_c);
+        Rng rng(seed);
+        const std::vector<size_t> homop = homopolymer_length(tmpl, (size_t)Lt);
+        std::vector<ColStat> stats(ncol);
+        for (size_t pos = 0; pos < ncol; pos++)
+            stats[pos] = ColStat{ stats_c[pos].sum, (size_t)stats_c[pos].count,
+                                  { stats_c[pos].sc[0], stats_c[pos].sc[1], stats_c[pos].sc[2], stats_c[pos].sc[3] } };
+        const std::vector<Probe> probes = candidate_probes(tmpl, (size_t)Lt, stats, n, gains, copy_num, cfg->coverage);
+        const size_t M = probes.size();
+        std::vector<double> cand(n * M);
+        if (M > 0) {
+            std::vector<uint32_t> cols(M);
+            for (size_t m = 0; m < M; m++) cols[m] = (uint32_t)probes[m].pos;
+            std::vector<float> min_req((size_t)3 * gains.H);
+            for (int t = 0; t < 3; t++) for (int h = 0; h < gains.H; h++) min_req[(size_t)t * gains.H + h] = (float)(gains.gain[t][h] * MIN_REQ_FRACTION);
+            const int rc = jtk_batch_gather(b, tmpl_index, min_req.data(), gains.H, cols.data(), (int)M, cand.data());
+            if (rc) { g_lc_error = "jtk_batch_gather failed"; return rc; }
+        }
+        const std::vector<size_t> picked = pick_filtered_profiles(probes, cand, n, copy_num);
+        Mat variants(n);
+        VarTypes vt;
+        for (size_t m : picked) {
+            size_t bp; DiffType t;
+            pos_to_bp_and_difftype(probes[m].pos, bp, t);
+            vt.push_back({ bp < homop.size() ? homop[bp] : 0, t });
+        }
+        for (size_t r = 0; r < n; r++) for (size_t m : picked) variants[r].push_back(cand[r * M + m]);
+        const DevResult res = clustering_tail(variants, vt, copy_num, cfg->coverage, cfg->local_coverage, gains, rng);
+        return write_result(res, probes, picked, out_asn, out_post, post_stride, out_score, out_k, out_probe_pos, probe_cap, out_n_probes);
+    } catch (const std::exception &e) {
+        g_lc_error = e.what();
+        return JTK_EINVAL;
+    }
+}
+
+// test hooks for the reference's own unit tests on these files (pseudo_mcmc.rs:876-904)
+double jtk_lc_cosine_similarity(const double *profiles, int n, int ncol, int i, int j) {
+    std::vector<double> cand((size_t)n * 2);
+    for (int r = 0; r < n; r++) { cand[(size_t)r * 2] = profiles[(size_t)r * ncol + i]; cand[(size_t)r * 2 + 1] = profiles[(size_t)r * ncol + j]; }
+    return cosine_similarity(cand, (size_t)n, 2, 0, 1);
+}
+int jtk_lc_homopolymer_length(const uint8_t *xs, int n, uint32_t *out) {
+    const std::vector<size_t> h = homopolymer_length(xs, (size_t)n);
+    for (int i = 0; i < n; i++) out[i] = (uint32_t)h[(size_t)i];
+    return 0;
+}
+// raw generator words (test hook: Xoshiro256** reference vector, SplitMix64 seeding)
+void jtk_lc_rng_words(uint64_t seed, int use_state, const uint64_t *state, int n, uint64_t *out) {
+    Rng r(seed);
+    if (use_state) std::memcpy(r.s, state, 32);
+    for (int i = 0; i < n; i++) out[i] = r.next_u64();
+}
+
+} // extern "C"

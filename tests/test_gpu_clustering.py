@@ -1,0 +1,131 @@
+"""GPU parity for the haplotyper-shaped path: identical selected variant columns and per-read cluster assignments
+whether the profiles come from the f64 oracle or from the CUDA kernels (BASELINE.json north_star), and the
+device-side column statistics / gather agree with a numpy restatement of pseudo_mcmc.rs:141-165,577-588,314-339."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from jtk_b200 import local_clustering as LC
+from jtk_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+GAINS = LC.Gains(gain=np.array([[4.0, 4.0, 4.0], [3.0, 2.0, 1.5], [3.0, 2.0, 1.5]]),
+                 prob=np.array([[0.02, 0.02, 0.02], [0.05, 0.08, 0.1], [0.05, 0.08, 0.1]]))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from jtk_b200 import _lib
+    c = _lib.Context()
+    yield c
+    c.close()
+
+
+def to_c(h):
+    from jtk_b200 import _lib
+    return _lib.HmmParams.from_buffer_copy(bytes(h))
+
+
+def oracle_profiles(d, fwd, rev, radius):
+    n = len(d["reads"])
+    tabs, lks = O.modification_table_batch(fwd, rev, [d["template"]] * n, d["reads"], d["ops"], d["strands"], radius,
+                                           n_threads=4)
+    prof = np.stack(tabs) - lks[:, None]
+    prof[np.stack(tabs) < -1e9] = -1e10
+    return prof
+
+
+def gpu_profiles(ctx, d, fwd, rev, radius):
+    n = len(d["reads"])
+    lk, tabs = ctx.modtable_batch(to_c(fwd), to_c(rev), [d["template"]], d["reads"], d["ops"], d["strands"],
+                                  np.zeros(n, np.uint32), radius)
+    prof = np.stack(tabs) - lk[:, None]
+    prof[np.stack(tabs) < -1e9] = -1e10
+    return prof
+
+
+@pytest.mark.parametrize("seed,length,n_reads,n_snv,radius", [(21, 600, 40, 4, 18), (22, 1000, 60, 5, 30), (23, 800, 50, 2, 24)])
+def test_columns_and_assignments_identical_oracle_vs_gpu(ctx, seed, length, n_reads, n_snv, radius):
+    d = synth.diploid_chunk(seed, length=length, n_reads=n_reads, error_rate=0.08, n_snv=n_snv)
+    h = O.default_hmm()
+    cfg = LC.ClusteringConfig.new(radius, 2, n_reads / 2, n_reads / 2, GAINS)
+    ro = LC.clustering_on_profiles(oracle_profiles(d, h, h, radius), d["template"], d["strands"], cfg, seed * 3490)
+    rg = LC.clustering_on_profiles(gpu_profiles(ctx, d, h, h, radius), d["template"], d["strands"], cfg, seed * 3490)
+    assert ro.probes.tolist() == rg.probes.tolist()
+    assert ro.k == rg.k and (ro.assignments == rg.assignments).all()
+    assert abs(ro.score - rg.score) < 1e-3
+    assert np.allclose(ro.posterior, rg.posterior, atol=1e-3)
+    agree = (rg.assignments == d["hap"]).mean()
+    assert max(agree, 1 - agree) >= 0.95
+
+
+def numpy_colstats(prof, template, strands, gains):
+    """compress_small_gains + column_sum + strand/sign counts, restated with numpy."""
+    Lt = len(template)
+    homop = LC.homopolymer_length(template).astype(np.int64)
+    hl = np.concatenate([homop, [1]])
+    H = gains.gain.shape[1]
+    row = np.arange(14)
+    typ = np.where(row < 4, 0, np.where(row < 11, 2, 1))  # Subst, Ins (incl. copy), Del
+    thr = gains.gain[typ[None, :], np.minimum(hl, H)[:, None] - 1] * 0.5
+    x = prof.reshape(len(prof), Lt + 1, 14).copy()
+    x[np.abs(x) < thr[None]] = 0.0
+    pos = x > 1e-5
+    s = np.where(pos, x, 0).sum(axis=0)
+    cnt = pos.sum(axis=0)
+    big = np.abs(x) > 1e-4
+    st = np.asarray(strands).astype(bool)[:, None, None]
+    sc = np.stack([(big & ~st & (x < 0)).sum(0), (big & ~st & (x > 0)).sum(0), (big & st & (x < 0)).sum(0),
+                   (big & st & (x > 0)).sum(0)], axis=-1)
+    return x, s.reshape(-1), cnt.reshape(-1), sc.reshape(-1, 4)
+
+
+def test_batch_path_matches_profile_path(ctx):
+    """Level 2 (profiles stay in HBM, 9-row kernel, colstats + gather) gives the same result as level 1."""
+    chunks = [synth.diploid_chunk(31 + c, length=700, n_reads=44, error_rate=0.08, n_snv=3) for c in range(3)]
+    h = O.default_hmm()
+    templates = [c["template"] for c in chunks]
+    reads = [r for c in chunks for r in c["reads"]]
+    ops = [o for c in chunks for o in c["ops"]]
+    strands = np.concatenate([c["strands"] for c in chunks])
+    tidx = np.repeat(np.arange(3, dtype=np.uint32), 44)
+    b = ctx.batch(templates, reads, ops, strands, tidx, 21)
+    b.modtable(to_c(h), to_c(h), 9)
+    stats = b.colstats(GAINS.min_req, 1e-5)
+    lk = b.lk()
+    cfg = LC.ClusteringConfig.new(21, 2, 22.0, 22.0, GAINS)
+    for t, d in enumerate(chunks):
+        sl = slice(int(b.stat_off[t]), int(b.stat_off[t + 1]))
+        prof = gpu_profiles(ctx, d, h, h, 21)
+        # device statistics == numpy restatement on the 14-row profiles (the rows filter_profiles reads)
+        x, s, cnt, sc = numpy_colstats(prof, d["template"], d["strands"], GAINS)
+        rows = (np.arange(len(s)) % 14 < 8) | (np.arange(len(s)) % 14 == 11)
+        assert (stats["count"][sl][rows] == cnt[rows]).all()
+        assert np.allclose(stats["sum"][sl][rows], s[rows], atol=1e-3)
+        assert (stats["sc"][sl][rows] == sc[rows]).all()
+        # gather == compressed profile columns
+        cols = np.flatnonzero(rows & (cnt > 0))[:50].astype(np.uint32)
+        g = b.gather(t, GAINS.min_req, cols)
+        assert np.allclose(g, x.reshape(len(prof), -1)[:, cols], atol=1e-4)
+        rb = LC.clustering_on_batch(b, t, d["template"], stats[sl], cfg, (t + 1) * 3490)
+        rp = LC.clustering_on_profiles(prof, d["template"], d["strands"], cfg, (t + 1) * 3490)
+        assert rb.probes.tolist() == rp.probes.tolist()
+        assert rb.k == rp.k and (rb.assignments == rp.assignments).all()
+        # likelihoods of the two kernels (9-row and 14-row variants share the forward pass)
+        want = ctx.likelihood_batch(to_c(h), to_c(h), [d["template"]], d["reads"], d["ops"], d["strands"],
+                                    np.zeros(44, np.uint32), 21)
+        assert np.allclose(lk[t * 44:(t + 1) * 44], want, rtol=1e-6)
+    b.close()
+
+
+def test_kiley_shaped_clustering_call(ctx):
+    """local_clustering.clustering mirrors pseudo_mcmc::clustering's argument list."""
+    from jtk_b200 import hmm
+    d = synth.diploid_chunk(41, length=600, n_reads=40, error_rate=0.08, n_snv=4)
+    cfg = LC.ClusteringConfig.new(18, 2, 20.0, 20.0, GAINS)
+    r = LC.clustering(d["template"], d["reads"], d["ops"], d["strands"], 41 * 3490,
+                      hmm.PairHiddenMarkovModelOnStrands.default(), cfg, ctx=ctx)
+    assert r.k == 2
+    agree = (r.assignments == d["hap"]).mean()
+    assert max(agree, 1 - agree) >= 0.95

@@ -1,0 +1,101 @@
+"""Host side of local_clustering (csrc/local_clustering.cpp): the reference's own unit tests on these files restated,
+generator vectors, and behaviour on oracle-made profiles (no GPU needed)."""
+import math
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from jtk_b200 import local_clustering as LC
+from jtk_b200 import synth
+
+GAINS = LC.Gains(gain=np.array([[4.0, 4.0, 4.0], [3.0, 2.0, 1.5], [3.0, 2.0, 1.5]]),
+                 prob=np.array([[0.02, 0.02, 0.02], [0.05, 0.08, 0.1], [0.05, 0.08, 0.1]]))
+
+
+def test_cosine_similarity_test():
+    """pseudo_mcmc.rs:876-897"""
+    assert abs(1 - LC.cosine_similarity([[1, 1], [2, 2]], 0, 1)) < 1e-4
+    assert abs(-1 - LC.cosine_similarity([[1, -3], [1, -3]], 0, 1)) < 1e-5
+    assert abs(LC.cosine_similarity([[1, 3], [1, -3]], 0, 1)) < 1e-5
+    assert math.sqrt(0.5) - abs(LC.cosine_similarity([[0, 100], [1, 100]], 0, 1)) < 1e-5
+
+
+def test_homop_length_test():
+    """pseudo_mcmc.rs:899-904"""
+    assert LC.homopolymer_length(b"ACCCCGTTTGGTT").tolist() == [1, 4, 4, 4, 4, 1, 3, 3, 3, 2, 2, 2, 2]
+
+
+def test_xoshiro256starstar_reference_vector():
+    """First outputs of the published xoshiro256** reference implementation for state {1,2,3,4} (the vector
+    rand_xoshiro's own test uses)."""
+    w = LC.rng_words(0, 4, state=[1, 2, 3, 4])
+    assert w.tolist() == [11520, 0, 1509978240, 1215971899390074240]
+
+
+def test_seed_from_u64_is_splitmix64():
+    """seed_from_u64 fills the state with SplitMix64 outputs; check against an independent Python restatement."""
+    def splitmix(x, n):
+        out = []
+        for _ in range(n):
+            x = (x + 0x9e3779b97f4a7c15) & (2 ** 64 - 1)
+            z = x
+            z = ((z ^ (z >> 30)) * 0xbf58476d1ce4e5b9) & (2 ** 64 - 1)
+            z = ((z ^ (z >> 27)) * 0x94d049bb133111eb) & (2 ** 64 - 1)
+            out.append(z ^ (z >> 31))
+        return out
+    for seed in (0, 3490, 7 * 3490):
+        a = LC.rng_words(seed, 6)
+        b = LC.rng_words(0, 6, state=splitmix(seed, 4))
+        assert a.tolist() == b.tolist()
+
+
+def oracle_profiles(d, fwd, rev, radius):
+    n = len(d["reads"])
+    tabs, lks = O.modification_table_batch(fwd, rev, [d["template"]] * n, d["reads"], d["ops"], d["strands"], radius,
+                                           n_threads=4)
+    prof = np.stack(tabs) - lks[:, None]
+    prof[np.stack(tabs) < -1e9] = -1e10
+    return prof
+
+
+@pytest.fixture(scope="module")
+def chunk_profiles():
+    d = synth.diploid_chunk(11, length=600, n_reads=40, error_rate=0.08, n_snv=4)
+    h = O.default_hmm()
+    return d, oracle_profiles(d, h, h, 18)
+
+
+def test_diploid_chunk_is_phased(chunk_profiles):
+    """P8: on benchmark_clustering-style data the adjusted Rand index is ~1 and the selected columns are
+    the planted SNVs."""
+    d, prof = chunk_profiles
+    cfg = LC.ClusteringConfig.new(18, 2, 20.0, 20.0, GAINS)
+    r = LC.clustering_on_profiles(prof, d["template"], d["strands"], cfg, seed=5 * 3490)
+    assert r.k == 2
+    agree = (r.assignments == d["hap"]).mean()
+    assert max(agree, 1 - agree) >= 0.95
+    snv = set(d["snv_pos"][0])
+    assert len(r.probes) >= 2 and {int(p) // 14 for p in r.probes} <= snv
+    assert all(int(p) % 14 < 4 for p in r.probes)  # substitutions
+    # posteriors are normalised log-probabilities (the reference asserts this at mod.rs:185)
+    assert np.allclose(np.exp(r.posterior).sum(axis=1), 1.0, atol=1e-9)
+    # determinism: same seed, same stream
+    r2 = LC.clustering_on_profiles(prof, d["template"], d["strands"], cfg, seed=5 * 3490)
+    assert (r.assignments == r2.assignments).all() and r.score == r2.score
+
+
+def test_single_haplotype_is_not_split():
+    d = synth.diploid_chunk(12, length=500, n_reads=30, error_rate=0.08, n_snv=0, n_hap=1)
+    h = O.default_hmm()
+    prof = oracle_profiles(d, h, h, 15)
+    cfg = LC.ClusteringConfig.new(15, 2, 15.0, 15.0, GAINS)
+    r = LC.clustering_on_profiles(prof, d["template"], d["strands"], cfg, seed=1)
+    assert r.k == 1 and (r.assignments == 0).all() and len(r.probes) == 0
+
+
+def test_copy_num_one_is_trivial(chunk_profiles):
+    d, prof = chunk_profiles
+    cfg = LC.ClusteringConfig.new(18, 1, 20.0, 40.0, GAINS)
+    r = LC.clustering_on_profiles(prof, d["template"], d["strands"], cfg, seed=3)
+    assert r.k == 1 and r.score == 0.0 and (r.assignments == 0).all()
