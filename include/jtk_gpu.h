@@ -155,6 +155,37 @@ int jtk_batch_colstats(jtk_batch *b, const float *min_req /* 3*H */, int H, floa
  * reads in batch order (filter_by, pseudo_mcmc.rs:70-75) */
 int jtk_batch_gather(jtk_batch *b, int tmpl, const float *min_req, int H, const uint32_t *cols, int D, double *out);
 
+/* ---- consensus polishing (K3) ------------------------------------------------------------------------- */
+/* kiley::hmm::HMMPolishConfig::new(radius, take_num, ignore_edge)
+ *   (local_clustering/mod.rs:105,154; model_tune.rs:142; consensus/mod.rs:476) */
+typedef struct {
+    int radius;
+    int take_num;    /* only the first take_num reads vote (pile-ups are pre-sorted, mod.rs:47-50) */
+    int ignore_edge; /* bases at both ends of the template that are never edited */
+} jtk_polish_config;
+
+/*
+ * Batched PairHiddenMarkovModelOnStrands::polish_until_converge_antidiagonal(draft, seqs, &mut ops, strands, cfg)
+ *   reference call sites: local_clustering/mod.rs:106,155-156; model_tune.rs:143; consensus/mod.rs:477-483.
+ * Every chunk c has a draft (draft_concat[draft_off[c]..draft_off[c+1])) and the reads p with tmpl_idx[p] == c, in
+ * batch order.  Loop (the oracle's definition): modification tables of the first take_num
+ * reads on the GPU, per-column sums on the GPU, greedy pick of positive-gain edits on the host, local patch of every
+ * read's ops, until no chunk changes (<= 20 rounds).
+ * ops are in/out: pair p owns ops_buf[ops_pos[p] .. ops_pos[p] + ops_cap[p]) and n_ops[p] holds its length.
+ * out_cons: chunk c owns out_cons[cons_pos[c] .. cons_pos[c] + cons_cap[c]); out_len[c] is the polished length.
+ * out_iters (may be NULL): rounds in which chunk c changed.
+ */
+int jtk_polish_until_converge_batch(jtk_ctx *ctx, const jtk_hmm_params *fwd, const jtk_hmm_params *rev, int n_chunks,
+                                    const uint8_t *draft_concat, const uint32_t *draft_off, int n_pairs,
+                                    const uint8_t *read_concat, const uint32_t *read_off, uint8_t *ops_buf,
+                                    const uint64_t *ops_pos, const uint32_t *ops_cap, uint32_t *n_ops,
+                                    const uint8_t *strand, const uint32_t *tmpl_idx, const jtk_polish_config *cfg,
+                                    uint8_t *out_cons, const uint64_t *cons_pos, const uint32_t *cons_cap,
+                                    uint32_t *out_len, int32_t *out_iters);
+/* per-column sums over the first take_num reads of every template of a batch (device reduction used by the
+ * polish loop): out[stat_off[t] + e] = sum_r profile_r[e] */
+int jtk_batch_colsums(jtk_batch *b, int take_num, double *out, const uint64_t *stat_off);
+
 /* ---- host side of local_clustering: everything in pseudo_mcmc.rs that is not the pair HMM ---------------- */
 /* likelihood_gains::Gains (likelihood_gains.rs:56-62): expected gain and null probability per (DiffType, homopolymer
  * length 1..homop_len); rows in DiffType order Subst, Del, Ins (likelihood_gains.rs:195-199). */

@@ -573,6 +573,22 @@ __global__ void gather_kernel(const float *__restrict__ delta, const DevPair *__
     out[idx] = (double)x;
 }
 
+// plain per-column sums over the first `take` reads of each template (polish loop)
+__global__ void colsums_kernel(const float *__restrict__ delta, const DevPair *__restrict__ pairs,
+                               const uint32_t *__restrict__ tp_start, const uint32_t *__restrict__ tp_ids,
+                               const uint32_t *__restrict__ tmpl_len, const unsigned long long *__restrict__ stat_off,
+                               int take, double *__restrict__ out) {
+    const int t = blockIdx.y;
+    const uint32_t n_ent = (tmpl_len[t] + 1) * kNumRow;
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_ent) return;
+    const uint32_t first = tp_start[t];
+    const uint32_t last = min(tp_start[t + 1], first + (uint32_t)take);
+    double sum = 0.0;
+    for (uint32_t k = first; k < last; k++) sum += (double)delta[pairs[tp_ids[k]].tab_off + e];
+    out[stat_off[t] + e] = sum;
+}
+
 } // namespace
 
 extern "C" {
@@ -728,6 +744,28 @@ int jtk_ctx_measure_fp32_peak(jtk_ctx *ctx, double *tflops_ffma, double *tflops_
     *tflops_ffma = best[0];
     *tflops_ffma2 = best[1];
     return JTK_OK;
+}
+
+int jtk_batch_colsums(jtk_batch *b, int take_num, double *out, const uint64_t *stat_off) {
+    if (!b) return JTK_EINVAL;
+    jtk_ctx *ctx = b->ctx;
+    if (!out || !stat_off || take_num < 0) return ctx->fail(JTK_EINVAL, "bad argument");
+    if (!b->has_profiles) return ctx->fail(JTK_ESTATE, "jtk_batch_modtable has not run");
+    if (b->n_tmpl == 0) return JTK_OK;
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaStream_t st = ctx->stream;
+    uint64_t total = 0;
+    for (int t = 0; t < b->n_tmpl; t++) total = std::max<uint64_t>(total, stat_off[t] + (uint64_t)(b->tmpl_len[t] + 1) * kNumRow);
+    CU(b->d_stat_off.reserve((size_t)b->n_tmpl), "cudaMalloc stat_off");
+    CU(ctx->d_gather.reserve((size_t)total), "cudaMalloc sums");
+    CU(cudaMemcpyAsync(b->d_stat_off.p, stat_off, sizeof(uint64_t) * (size_t)b->n_tmpl, cudaMemcpyHostToDevice, st), "H2D stat_off");
+    dim3 grid((unsigned)(((size_t)(b->max_lt + 1) * kNumRow + 255) / 256), (unsigned)b->n_tmpl);
+    colsums_kernel<<<grid, 256, 0, st>>>(b->d_delta.p, b->d_pairs.p, b->d_tp_start.p, b->d_tp_ids.p, b->d_tmpl_len.p,
+                                        b->d_stat_off.p, take_num, ctx->d_gather.p);
+    CU(cudaGetLastError(), "colsums launch");
+    ctx->launches++;
+    CU(cudaMemcpyAsync(out, ctx->d_gather.p, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, st), "D2H sums");
+    return batch_sync(b);
 }
 
 // ---- level 1 on top of the batch ---------------------------------------------------------------------

@@ -1,0 +1,179 @@
+// polish.cpp -- K3: PairHiddenMarkovModelOnStrands::polish_until_converge_antidiagonal, batched over chunks.
+// Reference call sites: haplotyper/src/local_clustering/mod.rs:105-106,154-156, model_tune.rs:141-143,
+// consensus/mod.rs:476-483.  kiley's loop body is not observable from the reference (SURVEY A.5 [FREE]); the
+// definition implemented here is the one written down in DESIGN.md section 2 and restated in f64 by the oracle:
+// the tables and per-column sums come from the GPU, edit selection and the local patch of the guide ops run here.
+#include "../../include/jtk_gpu.h"
+
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+constexpr double kMinGain = 0.1;
+constexpr int kInactive = 5;
+constexpr int kMaxIter = 20;
+constexpr int NUM_ROW = JTK_NUM_ROW, COPY = JTK_COPY_SIZE;
+
+struct Edit { int j, row; };
+
+inline int code(uint8_t c) {
+    switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 0; }
+}
+
+// greedy left-to-right pick of positive-gain edits on the summed table
+void select_edits(const double *sum, const std::vector<uint8_t> &tmpl, int ignore_edge, std::vector<Edit> &ed) {
+    const int L = (int)tmpl.size();
+    ed.clear();
+    int j = ignore_edge;
+    while (j <= L - ignore_edge) {
+        int best = -1;
+        double bg = kMinGain;
+        const int own = j < L ? code(tmpl[(size_t)j]) : -1;
+        for (int row = 0; row < NUM_ROW; row++) {
+            if (row == own) continue;
+            if (row < 4 && j >= L - ignore_edge) continue;
+            if (row >= 8 && row < 8 + COPY && j + (row - 7) > L - ignore_edge) continue;
+            if (row >= 8 + COPY && j + (row - 7 - COPY) > L - ignore_edge) continue;
+            const double g = sum[(size_t)j * NUM_ROW + row];
+            if (g > bg) { bg = g; best = row; }
+        }
+        if (best >= 0) {
+            ed.push_back({ j, best });
+            const int consumed = best >= 8 + COPY ? best - 7 - COPY : (best < 4 ? 1 : 0);
+            j += consumed + kInactive;
+        } else j++;
+    }
+}
+
+void apply_edits(std::vector<uint8_t> &tmpl, const std::vector<Edit> &ed) {
+    std::vector<uint8_t> next;
+    next.reserve(tmpl.size() + 3 * ed.size());
+    size_t src = 0;
+    for (const Edit &e : ed) {
+        while (src < (size_t)e.j) next.push_back(tmpl[src++]);
+        if (e.row < 4) { next.push_back((uint8_t)"ACGT"[e.row]); src++; }
+        else if (e.row < 8) next.push_back((uint8_t)"ACGT"[e.row - 4]);
+        else if (e.row < 8 + COPY) { for (int x = 0; x < e.row - 7; x++) next.push_back(tmpl[(size_t)e.j + x]); }
+        else src += (size_t)(e.row - 7 - COPY);
+    }
+    while (src < tmpl.size()) next.push_back(tmpl[src++]);
+    tmpl.swap(next);
+}
+
+// rewrite one read's guide path after the template edits (sorted, old coordinates)
+bool update_ops(const uint8_t *ops, int n, const std::vector<Edit> &ed, std::vector<uint8_t> &out) {
+    out.clear();
+    int k = 0, tpos = 0, del_left = 0;
+    size_t e = 0;
+    for (;;) {
+        while (e < ed.size() && ed[e].j == tpos && del_left == 0) {
+            const int row = ed[e].row;
+            e++;
+            if (row < 4) continue;
+            if (row < 8 + COPY) {
+                const int nb = row < 8 ? 1 : row - 7;
+                for (int x = 0; x < nb; x++) {
+                    if (k < n && ops[k] == JTK_OP_INS) { out.push_back(JTK_OP_MATCH); k++; }
+                    else out.push_back(JTK_OP_DEL);
+                }
+            } else del_left = row - 7 - COPY;
+        }
+        if (k >= n) break;
+        const uint8_t op = ops[k++];
+        if (op == JTK_OP_INS) { out.push_back(JTK_OP_INS); continue; }
+        if (del_left > 0) { if (op != JTK_OP_DEL) out.push_back(JTK_OP_INS); del_left--; }
+        else out.push_back(op);
+        tpos++;
+    }
+    return true;
+}
+
+} // namespace
+
+extern "C" int jtk_polish_until_converge_batch(jtk_ctx *ctx, const jtk_hmm_params *fwd, const jtk_hmm_params *rev, int n_chunks,
+                                               const uint8_t *draft_concat, const uint32_t *draft_off, int n_pairs,
+                                               const uint8_t *read_concat, const uint32_t *read_off, uint8_t *ops_buf,
+                                               const uint64_t *ops_pos, const uint32_t *ops_cap, uint32_t *n_ops,
+                                               const uint8_t *strand, const uint32_t *tmpl_idx, const jtk_polish_config *cfg,
+                                               uint8_t *out_cons, const uint64_t *cons_pos, const uint32_t *cons_cap,
+                                               uint32_t *out_len, int32_t *out_iters) {
+    if (!ctx || !fwd || !rev || !cfg || n_chunks < 0 || n_pairs < 0) return JTK_EINVAL;
+    if (n_chunks == 0) return JTK_OK;
+    if (!draft_concat || !draft_off || !read_concat || !read_off || !ops_buf || !ops_pos || !ops_cap || !n_ops || !strand ||
+        !tmpl_idx || !out_cons || !cons_pos || !cons_cap || !out_len)
+        return JTK_EINVAL;
+    std::vector<std::vector<uint8_t>> tmpl((size_t)n_chunks);
+    std::vector<std::vector<uint32_t>> members((size_t)n_chunks);
+    for (int c = 0; c < n_chunks; c++) tmpl[(size_t)c].assign(draft_concat + draft_off[c], draft_concat + draft_off[c + 1]);
+    for (int p = 0; p < n_pairs; p++) {
+        if (tmpl_idx[p] >= (uint32_t)n_chunks) return JTK_EINVAL;
+        members[tmpl_idx[p]].push_back((uint32_t)p);
+    }
+    std::vector<int> iters((size_t)n_chunks, 0);
+    std::vector<uint8_t> active((size_t)n_chunks, 1);
+    std::vector<uint8_t> t_cat, r_cat, o_cat, s_vec, patched;
+    std::vector<uint32_t> t_off, r_off, o_off, t_idx, chunk_of;
+    std::vector<uint64_t> stat_off;
+    std::vector<double> sums;
+    std::vector<Edit> ed;
+    for (int round = 0; round < kMaxIter; round++) {
+        // batch of the voting reads of every chunk that is still changing
+        t_cat.clear(); r_cat.clear(); o_cat.clear(); s_vec.clear();
+        t_off.assign(1, 0); r_off.assign(1, 0); o_off.assign(1, 0); t_idx.clear(); chunk_of.clear(); stat_off.clear();
+        uint64_t so = 0;
+        for (int c = 0; c < n_chunks; c++) {
+            if (!active[(size_t)c]) continue;
+            const uint32_t bt = (uint32_t)chunk_of.size();
+            chunk_of.push_back((uint32_t)c);
+            t_cat.insert(t_cat.end(), tmpl[(size_t)c].begin(), tmpl[(size_t)c].end());
+            t_off.push_back((uint32_t)t_cat.size());
+            stat_off.push_back(so);
+            so += (uint64_t)(tmpl[(size_t)c].size() + 1) * NUM_ROW;
+            const size_t take = std::min<size_t>((size_t)std::max(cfg->take_num, 0), members[(size_t)c].size());
+            for (size_t m = 0; m < take; m++) {
+                const uint32_t p = members[(size_t)c][m];
+                r_cat.insert(r_cat.end(), read_concat + read_off[p], read_concat + read_off[p + 1]);
+                r_off.push_back((uint32_t)r_cat.size());
+                o_cat.insert(o_cat.end(), ops_buf + ops_pos[p], ops_buf + ops_pos[p] + n_ops[p]);
+                o_off.push_back((uint32_t)o_cat.size());
+                s_vec.push_back(strand[p]);
+                t_idx.push_back(bt);
+            }
+        }
+        if (chunk_of.empty()) break;
+        jtk_batch *b = nullptr;
+        int rc = jtk_batch_create(ctx, (int)t_idx.size(), (int)chunk_of.size(), t_cat.data(), t_off.data(), r_cat.data(),
+                                  r_off.data(), o_cat.data(), o_off.data(), s_vec.data(), t_idx.data(), cfg->radius, &b);
+        if (rc) return rc;
+        sums.assign((size_t)so, 0.0);
+        if (!t_idx.empty()) {
+            rc = jtk_batch_modtable(b, fwd, rev, 14);
+            if (!rc) rc = jtk_batch_colsums(b, cfg->take_num, sums.data(), stat_off.data());
+        }
+        jtk_batch_destroy(b);
+        if (rc) return rc;
+        for (size_t bt = 0; bt < chunk_of.size(); bt++) {
+            const int c = (int)chunk_of[bt];
+            select_edits(sums.data() + stat_off[bt], tmpl[(size_t)c], cfg->ignore_edge, ed);
+            if (ed.empty()) { active[(size_t)c] = 0; continue; }
+            iters[(size_t)c]++;
+            for (uint32_t p : members[(size_t)c]) {
+                update_ops(ops_buf + ops_pos[p], (int)n_ops[p], ed, patched);
+                if (patched.size() > ops_cap[p]) return JTK_EINVAL;
+                std::memcpy(ops_buf + ops_pos[p], patched.data(), patched.size());
+                n_ops[p] = (uint32_t)patched.size();
+            }
+            apply_edits(tmpl[(size_t)c], ed);
+        }
+    }
+    for (int c = 0; c < n_chunks; c++) {
+        if (tmpl[(size_t)c].size() > cons_cap[c]) return JTK_EINVAL;
+        std::memcpy(out_cons + cons_pos[c], tmpl[(size_t)c].data(), tmpl[(size_t)c].size());
+        out_len[c] = (uint32_t)tmpl[(size_t)c].size();
+        if (out_iters) out_iters[c] = iters[(size_t)c];
+    }
+    return JTK_OK;
+}

@@ -85,6 +85,18 @@ class PairHiddenMarkovModel:
 
 
 @dataclass
+class HMMPolishConfig:
+    """kiley::hmm::HMMPolishConfig::new(radius, take_num, ignore_edge) (local_clustering/mod.rs:105)."""
+    radius: int
+    take_num: int
+    ignore_edge: int
+
+    @classmethod
+    def new(cls, radius: int, take_num: int, ignore_edge: int) -> "HMMPolishConfig":
+        return cls(radius, take_num, ignore_edge)
+
+
+@dataclass
 class PairHiddenMarkovModelOnStrands:
     _forward: PairHiddenMarkovModel = field(default_factory=PairHiddenMarkovModel)
     _reverse: PairHiddenMarkovModel = field(default_factory=PairHiddenMarkovModel)
@@ -115,3 +127,58 @@ class PairHiddenMarkovModelOnStrands:
         prof = np.stack(tabs) - lk[:, None]
         prof[np.stack(tabs) <= _lib.TABLE_NEG * 0.1] = _lib.TABLE_NEG
         return prof, lk
+
+    def polish_until_converge_antidiagonal(self, draft, seqs: Sequence, ops: list, strands: Sequence[bool],
+                                           config: HMMPolishConfig, ctx: Optional[Context] = None) -> np.ndarray:
+        """Reference signature (local_clustering/mod.rs:106): returns the polished consensus; `ops` (a list of uint8
+        arrays) is rewritten in place like the reference's `&mut ops`."""
+        cons, new_ops, _ = polish_chunks(self, [draft], list(seqs), ops, strands, np.zeros(len(seqs), np.uint32), config,
+                                         ctx=ctx)
+        for k in range(len(ops)):
+            ops[k] = new_ops[k]
+        return cons[0]
+
+
+def polish_chunks(models: PairHiddenMarkovModelOnStrands, drafts: Sequence, reads: Sequence, ops: Sequence,
+                  strands: Sequence[bool], tmpl_idx, config: HMMPolishConfig, ctx: Optional[Context] = None):
+    """jtk_polish_until_converge_batch: many chunks per call.  Returns (consensus list, ops list, iterations)."""
+    import ctypes as C
+    ctx = ctx or default_context()
+    L = _lib.lib()
+    n_chunks, n_pairs = len(drafts), len(reads)
+    dcat, doff = _lib.concat(drafts)
+    rcat, roff = _lib.concat(reads)
+    tmpl_idx = np.ascontiguousarray(tmpl_idx, dtype=np.uint32)
+    st = _lib._u8(np.asarray(strands, dtype=np.uint8))
+    dlen = np.diff(doff.astype(np.int64))
+    rlen = np.diff(roff.astype(np.int64))
+    caps = (rlen + 2 * dlen[tmpl_idx] + 64).astype(np.uint32)
+    pos = np.zeros(n_pairs + 1, dtype=np.uint64)
+    np.cumsum(caps, out=pos[1:])
+    buf = np.zeros(int(pos[-1]), dtype=np.uint8)
+    n_ops = np.zeros(n_pairs, dtype=np.uint32)
+    for k, o in enumerate(ops):
+        o = _lib._u8(o)
+        buf[int(pos[k]):int(pos[k]) + len(o)] = o
+        n_ops[k] = len(o)
+    ccap = (2 * dlen + 64).astype(np.uint32)
+    cpos = np.zeros(n_chunks + 1, dtype=np.uint64)
+    np.cumsum(ccap, out=cpos[1:])
+    cons = np.zeros(int(cpos[-1]), dtype=np.uint8)
+    clen = np.zeros(n_chunks, dtype=np.uint32)
+    iters = np.zeros(n_chunks, dtype=np.int32)
+
+    class _Cfg(C.Structure):
+        _fields_ = [("radius", C.c_int), ("take_num", C.c_int), ("ignore_edge", C.c_int)]
+    cfg = _Cfg(config.radius, config.take_num, config.ignore_edge)
+    vp = C.c_void_p
+    L.jtk_polish_until_converge_batch.argtypes = [vp, C.POINTER(HmmParams), C.POINTER(HmmParams), C.c_int, vp, vp, C.c_int,
+                                                  vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(_Cfg), vp, vp, vp, vp, vp]
+    f, r = models.forward().to_c(), models.reverse().to_c()
+    p = _lib._ptr
+    ctx._check(L.jtk_polish_until_converge_batch(ctx._h, C.byref(f), C.byref(r), n_chunks, p(dcat), p(doff), n_pairs, p(rcat),
+                                                 p(roff), p(buf), p(pos), p(caps), p(n_ops), p(st), p(tmpl_idx),
+                                                 C.byref(cfg), p(cons), p(cpos), p(ccap), p(clen), p(iters)))
+    out_cons = [cons[int(cpos[c]):int(cpos[c]) + int(clen[c])].copy() for c in range(n_chunks)]
+    out_ops = [buf[int(pos[k]):int(pos[k]) + int(n_ops[k])].copy() for k in range(n_pairs)]
+    return out_cons, out_ops, iters

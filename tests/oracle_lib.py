@@ -163,3 +163,34 @@ def modification_table_batch(fwd, rev, templates, reads, ops, strands, radius, n
         raise ValueError(f"batch rc={rc}")
     lks = np.array([pairs[k].lk for k in range(n)])
     return (tables if want_tables else None), lks
+
+
+def polish_until_converge(fwd, rev, draft, reads, ops, strands, radius, take_num, ignore_edge):
+    """orc_polish_until_converge.  Returns (consensus uint8[], ops list, iterations)."""
+    L = lib()
+    draft = _u8(draft)
+    n = len(reads)
+    reads = [_u8(r) for r in reads]
+    cap = max(len(r) for r in reads) + 2 * len(draft) + 64
+    bufs = [np.zeros(cap, dtype=np.uint8) for _ in range(n)]
+    n_ops = (C.c_int * n)()
+    for k, o in enumerate(ops):
+        o = _u8(o)
+        bufs[k][:len(o)] = o
+        n_ops[k] = len(o)
+    rp = (C.c_void_p * n)(*[r.ctypes.data for r in reads])
+    rl = (C.c_int * n)(*[len(r) for r in reads])
+    op = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+    st = _u8(np.asarray(strands, dtype=np.uint8))
+    cfg = OrcPolishCfg(radius, take_num, ignore_edge)
+    cons_cap = 2 * len(draft) + 64
+    out = np.zeros(cons_cap + 16, dtype=np.uint8)
+    it = C.c_int()
+    L.orc_polish_until_converge.argtypes = [C.POINTER(OrcHmm), C.POINTER(OrcHmm), C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(OrcPolishCfg),
+                                            C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    rc = L.orc_polish_until_converge(C.byref(fwd), C.byref(rev), _p(draft), len(draft), n, rp, rl, op, n_ops, cap, _p(st),
+                                     C.byref(cfg), _p(out), cons_cap, C.byref(it))
+    if rc < 0:
+        raise ValueError(f"orc_polish_until_converge rc={rc}")
+    return out[:rc].copy(), [bufs[k][:n_ops[k]].copy() for k in range(n)], it.value
