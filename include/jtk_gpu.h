@@ -186,6 +186,22 @@ int jtk_polish_until_converge_batch(jtk_ctx *ctx, const jtk_hmm_params *fwd, con
  * polish loop): out[stat_off[t] + e] = sum_r profile_r[e] */
 int jtk_batch_colsums(jtk_batch *b, int take_num, double *out, const uint64_t *stat_off);
 
+/* ---- HMM fit (K4) --------------------------------------------------------------------------------------- */
+/* Expected transition / emission counts of every pair of a batch under (fwd, rev), summed per strand:
+ * acc90[0..45) forward-strand reads, acc90[45..90) reverse-strand reads; each block is 9 transitions, 16 mat_emit,
+ * 20 ins_emit in HMMParam order.  The E-step of one Baum-Welch round. */
+int jtk_batch_expected_counts(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev, double *acc90);
+/*
+ * PairHiddenMarkovModelOnStrands::fit_antidiagonal_par_multiple(&mut self, &[TrainingDataPack], radius)
+ *   reference call site: haplotyper/src/model_tune.rs:145-151 (TrainingDataPack::new(cons, strands, seqs, ops)).
+ * One EM update of both strand models in place: E-step on the GPU over all packs (= templates of the batch inputs),
+ * M-step (row normalisation; rows without counts keep their values) on the host.
+ */
+int jtk_hmm_fit_batch(jtk_ctx *ctx, jtk_hmm_params *fwd, jtk_hmm_params *rev, int n_pairs, int n_tmpl,
+                      const uint8_t *tmpl_concat, const uint32_t *tmpl_off, const uint8_t *read_concat,
+                      const uint32_t *read_off, const uint8_t *ops_concat, const uint32_t *ops_off,
+                      const uint8_t *strand, const uint32_t *tmpl_idx, int radius);
+
 /* ---- host side of local_clustering: everything in pseudo_mcmc.rs that is not the pair HMM ---------------- */
 /* likelihood_gains::Gains (likelihood_gains.rs:56-62): expected gain and null probability per (DiffType, homopolymer
  * length 1..homop_len); rows in DiffType order Subst, Del, Ins (likelihood_gains.rs:195-199). */

@@ -16,6 +16,7 @@ cudaError_t launch_modtable(const KParams &p, int C, int grid, cudaStream_t st);
 cudaError_t launch_likelihood(const KParams &p, int C, int grid, cudaStream_t st);
 int warps_per_cta();
 int frow_slots_per_row(int C);
+cudaError_t launch_fit(const KParams &p, int C, int grid, double *acc90, cudaStream_t st);
 cudaError_t launch_fp32_peak(int mode, int blocks, int threads, int iters, float *sink, cudaStream_t st);
 } // namespace jtk
 
@@ -766,6 +767,82 @@ int jtk_batch_colsums(jtk_batch *b, int take_num, double *out, const uint64_t *s
     ctx->launches++;
     CU(cudaMemcpyAsync(out, ctx->d_gather.p, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, st), "D2H sums");
     return batch_sync(b);
+}
+
+int jtk_batch_expected_counts(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev, double *acc90) {
+    if (!b) return JTK_EINVAL;
+    jtk_ctx *ctx = b->ctx;
+    if (!fwd || !rev || !acc90) return ctx->fail(JTK_EINVAL, "null argument");
+    std::memset(acc90, 0, sizeof(double) * 90);
+    if (b->n_pairs == 0) return JTK_OK;
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    float models[2 * kModelFloats];
+    pack_model(fwd, models);
+    pack_model(rev, models + kModelFloats);
+    const int wpc = warps_per_cta();
+    int grid = (b->n_pairs + wpc - 1) / wpc;
+    const int max_grid = ctx->sm_count * 4;
+    if (grid > max_grid) grid = max_grid;
+    cudaStream_t st = ctx->stream;
+    KParams kp{};
+    const size_t slots = (size_t)grid * wpc;
+    kp.frow_stride = (size_t)2 * (b->max_nd + 1) * 32 * b->C; // one float4 (F_M, F_I, F_D, -) per slot and row
+    kp.kf_stride = (size_t)b->max_nd + 6;
+    CU(ctx->d_models.reserve(2 * kModelFloats), "cudaMalloc models");
+    CU(ctx->d_counter.reserve(1), "cudaMalloc counter");
+    CU(ctx->d_frows.reserve(slots * kp.frow_stride), "cudaMalloc forward rows");
+    CU(ctx->d_kf.reserve(slots * kp.kf_stride), "cudaMalloc scale exponents");
+    CU(ctx->d_gather.reserve(90), "cudaMalloc counts");
+    CU(cudaMemcpyAsync(ctx->d_models.p, models, sizeof(models), cudaMemcpyHostToDevice, st), "H2D models");
+    CU(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(int), st), "memset counter");
+    CU(cudaMemsetAsync(ctx->d_gather.p, 0, sizeof(double) * 90, st), "memset counts");
+    kp.pairs = b->d_pairs.p; kp.n_pairs = b->n_pairs;
+    kp.codes = b->d_codes.p; kp.bits = b->d_bits.p; kp.models = ctx->d_models.p;
+    kp.radius = b->radius; kp.rows = 0;
+    kp.frows = ctx->d_frows.p; kp.kf = ctx->d_kf.p;
+    kp.out_delta = nullptr; kp.out_lk = b->d_lk.p; kp.counter = ctx->d_counter.p;
+    CU(launch_fit(kp, b->C, grid, ctx->d_gather.p, st), "fit kernel launch");
+    ctx->launches++;
+    CU(cudaMemcpyAsync(acc90, ctx->d_gather.p, sizeof(double) * 90, cudaMemcpyDeviceToHost, st), "D2H counts");
+    return batch_sync(b);
+}
+
+static void mstep(jtk_hmm_params *h, const double *acc) {
+    double *tr[9] = { &h->mat_mat, &h->mat_ins, &h->mat_del, &h->ins_mat, &h->ins_ins, &h->ins_del,
+                      &h->del_mat, &h->del_ins, &h->del_del };
+    for (int st = 0; st < 3; st++) {
+        const double tot = acc[3 * st] + acc[3 * st + 1] + acc[3 * st + 2];
+        if (tot > 0) for (int k = 0; k < 3; k++) *tr[3 * st + k] = acc[3 * st + k] / tot;
+    }
+    for (int r = 0; r < 4; r++) {
+        double tot = 0;
+        for (int x = 0; x < 4; x++) tot += acc[9 + 4 * r + x];
+        if (tot > 0) for (int x = 0; x < 4; x++) h->mat_emit[4 * r + x] = acc[9 + 4 * r + x] / tot;
+    }
+    for (int c = 0; c < 5; c++) {
+        double tot = 0;
+        for (int x = 0; x < 4; x++) tot += acc[25 + 4 * c + x];
+        if (tot > 0) for (int x = 0; x < 4; x++) h->ins_emit[4 * c + x] = acc[25 + 4 * c + x] / tot;
+    }
+}
+
+int jtk_hmm_fit_batch(jtk_ctx *ctx, jtk_hmm_params *fwd, jtk_hmm_params *rev, int n_pairs, int n_tmpl,
+                      const uint8_t *tmpl_concat, const uint32_t *tmpl_off, const uint8_t *read_concat,
+                      const uint32_t *read_off, const uint8_t *ops_concat, const uint32_t *ops_off,
+                      const uint8_t *strand, const uint32_t *tmpl_idx, int radius) {
+    if (!ctx) return JTK_EINVAL;
+    if (!fwd || !rev) return ctx->fail(JTK_EINVAL, "null model");
+    jtk_batch *b = nullptr;
+    int rc = batch_create(ctx, n_pairs, n_tmpl, tmpl_concat, tmpl_off, read_concat, read_off, ops_concat, ops_off, strand,
+                          tmpl_idx, radius, false, &b);
+    if (rc) return rc;
+    double acc[90];
+    rc = jtk_batch_expected_counts(b, fwd, rev, acc);
+    jtk_batch_destroy(b);
+    if (rc) return rc;
+    mstep(fwd, acc);      // strand 1 reads -> model 0 (forward)
+    mstep(rev, acc + 45); // strand 0 reads -> model 1 (reverse)
+    return JTK_OK;
 }
 
 // ---- level 1 on top of the batch ---------------------------------------------------------------------

@@ -127,7 +127,7 @@ template <int C> struct FwdState {
     float toI[C], inD[C], inMa[C], inMb[C];
 };
 
-template <int C, bool STORE, bool SPECIAL>
+template <int C, int STORE, bool SPECIAL>
 __device__ __forceinline__ void fwd_step(const PairCtx &pc, const Coef &a, FwdState<C> &st, const int s, const int cen,
                                          int &K, f2 *__restrict__ &wrow, const int halo, int32_t *__restrict__ kf,
                                          volatile float *s_ftot, unsigned short *ev_s, int &ev_n) {
@@ -137,6 +137,7 @@ __device__ __forceinline__ void fwd_step(const PairCtx &pc, const Coef &a, FwdSt
     const int lo = band_lo(cen, pc.r, s, pc.Lt), hi = band_hi(cen, pc.r, s, pc.Lr);
     const int W = hi - lo, A = s - lo;
     f2 tMD[C];
+    float Fm[C], Fi[C], Fd[C]; // forward states, kept only for the fit kernel (STORE == 2)
     unsigned dead = 0u;
 #pragma unroll
     for (int c = 0; c < C; c++) {
@@ -154,6 +155,7 @@ __device__ __forceinline__ void fwd_step(const PairCtx &pc, const Coef &a, FwdSt
         if (SPECIAL && s == 0 && st.j[c] == 0) M = 1.f;
         tMD[c] = fma2(a.fD, bc2(D), fma2(a.fI, bc2(I), mul2(a.fM, bc2(M))));
         st.toI[c] = fmaf(a.f_di, D, fmaf(a.f_ii, I, a.f_mi * M));
+        if (STORE == 2) { Fm[c] = M; Fi[c] = I; Fd[c] = D; }
         if (SPECIAL && s >= pc.nd - 4 && valid && x + lo == pc.Lr && st.j[c] >= pc.Lt - 3) s_ftot[pc.Lt - st.j[c]] = M + I + D;
         if (x > W) dead |= 1u << c;
     }
@@ -177,14 +179,25 @@ __device__ __forceinline__ void fwd_step(const PairCtx &pc, const Coef &a, FwdSt
             const float sc = pow2i(k);
 #pragma unroll
             for (int c = 0; c < C; c++) { tMD[c] = mul2(tMD[c], bc2(sc)); st.toI[c] *= sc; st.inMa[c] *= sc; }
+            if (STORE == 2) {
+#pragma unroll
+                for (int c = 0; c < C; c++) { Fm[c] *= sc; Fi[c] *= sc; Fd[c] *= sc; }
+            }
             K += k;
-            if (STORE) {
+            if (STORE == 1) {
                 if (ev_n < kMaxEvents && lane == 0) ev_s[ev_n] = (unsigned short)s;
                 ev_n++;
             }
         }
     }
-    if (STORE) {
+    if (STORE == 2) { // fit: the three forward states of every cell, one float4 per slot, no halo
+        if (lane == 0) kf[s] = K;
+        float4 *srow = reinterpret_cast<float4 *>(wrow);
+#pragma unroll
+        for (int c = 0; c < C; c++) srow[c] = make_float4(Fm[c], Fi[c], Fd[c], 0.f);
+        wrow = reinterpret_cast<f2 *>(srow + NSLOT);
+    }
+    if (STORE == 1) {
         if (lane == 0) kf[s] = K;
 #pragma unroll
         for (int c = 0; c < C; c += 2)
@@ -204,14 +217,15 @@ __device__ __forceinline__ void fwd_step(const PairCtx &pc, const Coef &a, FwdSt
     st.inMb[0] = st.inMa[0]; st.inMa[0] = rM; st.inD[0] = rD;
 }
 
-template <int C, bool STORE>
+template <int C, int STORE>
 __device__ __forceinline__ void forward_pass(const PairCtx &pc, const Coef &a, float2 *__restrict__ frow,
                                              int32_t *__restrict__ kf, volatile float *s_ftot, int &Ktot,
                                              unsigned short *ev_s, int &ev_n) {
     constexpr int NSLOT = 32 * C;
     const int lane = threadIdx.x & 31;
     const int nd = pc.nd;
-    f2 *wrow = reinterpret_cast<f2 *>(frow) + kHalo + lane * C; // this lane's slots in row 0
+    f2 *wrow = (STORE == 2) ? reinterpret_cast<f2 *>(reinterpret_cast<float4 *>(frow) + lane * C)
+                            : reinterpret_cast<f2 *>(frow) + kHalo + lane * C; // this lane's slots in row 0
     const int halo = (lane * C < 3) ? NSLOT : ((lane * C + C > NSLOT - 3) ? -NSLOT : 0);
     ev_n = 0;
     FwdState<C> st;
@@ -540,7 +554,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) modtable_kernel(KParams p) 
         const Coef a = load_coef(sh.trans[P.model]);
         int Ktot;
         int ev_n;
-        forward_pass<C, true>(pc, a, frow, kf, sh.ftot[warp], Ktot, sh.ev_s[warp], ev_n);
+        forward_pass<C, 1>(pc, a, frow, kf, sh.ftot[warp], Ktot, sh.ev_s[warp], ev_n);
         // rows / exponents just past the last anti-diagonal read as zero / Ktot
         for (int k = lane; k < 3 * RS; k += 32) frow[(size_t)pc.nd * RS + k] = make_float2(0.f, 0.f);
         if (lane < 3) kf[pc.nd + lane] = Ktot;
@@ -568,10 +582,170 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) likelihood_kernel(KParams p
         const Coef a = load_coef(sh.trans[P.model]);
         int Ktot;
         int ev_n;
-        forward_pass<C, false>(pc, a, nullptr, nullptr, sh.ftot[warp], Ktot, nullptr, ev_n);
+        forward_pass<C, 0>(pc, a, nullptr, nullptr, sh.ftot[warp], Ktot, nullptr, ev_n);
         const float fin = sh.ftot[warp][0];
         if (lane == 0)
             p.out_lk[pi] = fin > 0.f ? log((double)fin) - (double)Ktot * 0.6931471805599453 : -INFINITY;
+        __syncwarp();
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// K4: expected counts of one Baum-Welch step (kiley fit_antidiagonal_par_multiple, model_tune.rs:151).
+// Forward pass stores (F_M, F_I, F_D) of every cell; the backward pass recomputes the in-sums gM, gI, gD of the
+// same cell and accumulates, per lane,
+//   T[s][move]      = sum F_s(i,j) * g_move(i,j)              (9 sums; times a[s][move] / P on the way out)
+//   binM[t[j]][q[i]] += toM(i,j) * gM(i,j)      binI[ctx][q[i]] += toI(i,j) * gI(i,j)
+// bins live in a lane-private column of shared memory (bin*32 + lane: no conflicts, no atomics).
+// ------------------------------------------------------------------------------------------------
+constexpr int kFitBins = 40; // [tc or ctx 0..4][qc 0..7]
+
+template <int C>
+__device__ __forceinline__ void fit_backward(const PairCtx &pc, const Coef &a, const float *trans, const float4 *__restrict__ srow0,
+                                             const int32_t *__restrict__ kf, volatile float *s_ftot, float *binM, float *binI,
+                                             double *__restrict__ acc45) {
+    constexpr int NSLOT = 32 * C;
+    const int lane = threadIdx.x & 31;
+    const int Lt = pc.Lt, Lr = pc.Lr, nd = pc.nd;
+    const float fin_raw = s_ftot[0];
+    if (!(fin_raw > 0.f)) return;
+    const int e_fin = (int)(__float_as_uint(fin_raw) >> 23) - 127;
+    const float boff = pow2i(max(-120, min(120, kProductExp - e_fin)));
+    const float inv_p = 1.f / (fin_raw * boff);
+    const float mm = trans[0], mi = trans[1], md = trans[2], im = trans[3], ii = trans[4], id = trans[5], dm = trans[6],
+                di = trans[7], dd = trans[8];
+    for (int k = 0; k < kFitBins; k++) { binM[k * 32 + lane] = 0.f; binI[k * 32 + lane] = 0.f; }
+    int j[C];
+    unsigned tcB[C], win[C];
+    float BI[C], inD[C], inMa[C], inMb[C];
+    float T[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) T[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        const int sigma = lane * C + c;
+        j[c] = Lt - ((Lt - sigma) & (NSLOT - 1));
+        tcB[c] = pc.sEM + ((unsigned)pc.Tb[j[c] + 1] << 5);
+        win[c] = 0u;
+        BI[c] = inD[c] = inMa[c] = inMb[c] = 0.f;
+    }
+    int cen = Lr;
+    unsigned bword = pc.bw[(nd - 1) >> 5];
+    const float4 *rp = srow0 + (ptrdiff_t)(nd - 1) * NSLOT + lane * C;
+    int kcur = kf[nd - 1];
+    for (int s = nd - 1; s >= 0; --s, rp -= NSLOT) {
+        const int lo = band_lo(cen, pc.r, s, Lt), hi = band_hi(cen, pc.r, s, Lr);
+        const int W = hi - lo, A = s - lo;
+        if (s == nd - 1 || (s & 3) == 3) {
+#pragma unroll
+            for (int c = 0; c < C; c++) win[c] = win_down(pc.RbP, s - j[c] + 1);
+        }
+        float bM[C], bD[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const int x = A - j[c];
+            const bool valid = (unsigned)x <= (unsigned)W;
+            const unsigned w = win[c];
+            win[c] = w >> 8;
+            const float em = lds_f32(tcB[c] | (w & 0x1cu));
+            const float ei = lds_f32(pc.sEI | (w & 0xffu));
+            const float gM = em * inMb[c], gI = ei * BI[c], gD = inD[c];
+            float m_ = mm * gM + mi * gI + md * gD;
+            float i_ = im * gM + ii * gI + id * gD;
+            float d_ = dm * gM + di * gI + dd * gD;
+            if (s == nd - 1) { m_ = boff; i_ = boff; d_ = boff; }
+            if (!valid) { m_ = 0.f; i_ = 0.f; d_ = 0.f; }
+            const float4 F = rp[c]; // zero outside the band
+            T[0] = fmaf(F.x, gM, T[0]); T[1] = fmaf(F.x, gI, T[1]); T[2] = fmaf(F.x, gD, T[2]);
+            T[3] = fmaf(F.y, gM, T[3]); T[4] = fmaf(F.y, gI, T[4]); T[5] = fmaf(F.y, gD, T[5]);
+            T[6] = fmaf(F.z, gM, T[6]); T[7] = fmaf(F.z, gI, T[7]); T[8] = fmaf(F.z, gD, T[8]);
+            const float toM = mm * F.x + im * F.y + dm * F.z;
+            const float toI = mi * F.x + ii * F.y + di * F.z;
+            const unsigned bm = (((tcB[c] - pc.sEM) >> 2) | ((w >> 2) & 7u)) * 32u + lane;
+            const unsigned bi = ((w >> 2) & 63u) * 32u + lane;
+            binM[bm] += toM * gM;
+            binI[bi] += toI * gI;
+            bM[c] = m_; bD[c] = d_; BI[c] = i_;
+            if (x < 0) { // above the band for good
+                j[c] -= NSLOT;
+                tcB[c] = pc.sEM + ((unsigned)pc.Tb[j[c] + 1] << 5);
+                win[c] = win_down(pc.RbP, (s - 1) - j[c] + 1);
+            }
+        }
+        const float rM = __shfl_sync(kFull, bM[0], (lane + 1) & 31);
+        const float rD = __shfl_sync(kFull, bD[0], (lane + 1) & 31);
+#pragma unroll
+        for (int c = 0; c < C - 1; c++) { inMb[c] = inMa[c]; inMa[c] = bM[c + 1]; inD[c] = bD[c + 1]; }
+        inMb[C - 1] = inMa[C - 1]; inMa[C - 1] = rM; inD[C - 1] = rD;
+        if (s > 0) {
+            const int kprev = kf[s - 1];
+            if (kcur != kprev) {
+                const float sc = pow2i(kcur - kprev);
+#pragma unroll
+                for (int c = 0; c < C; c++) { BI[c] *= sc; inD[c] *= sc; inMa[c] *= sc; inMb[c] *= sc; }
+            }
+            kcur = kprev;
+            cen -= (bword >> ((s - 1) & 31)) & 1u;
+            if (((s - 1) & 31) == 0 && s > 1) bword = pc.bw[(s - 2) >> 5];
+        }
+    }
+    // reduce over lanes, scale by a[s][move] / P, add into the strand's accumulators
+    const float tr[9] = { mm, mi, md, im, ii, id, dm, di, dd };
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+        float v = T[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        if (lane == 0) atomicAdd(&acc45[k], (double)(v * tr[k]) * (double)inv_p);
+    }
+    __syncwarp();
+    for (int k = 0; k < kFitBins; k++) {
+        float vm = binM[k * 32 + lane], vi = binI[k * 32 + lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { vm += __shfl_xor_sync(kFull, vm, o); vi += __shfl_xor_sync(kFull, vi, o); }
+        const int hi8 = k >> 3, q = k & 7;
+        if (lane == 0 && q < 4) {
+            if (hi8 < 4) atomicAdd(&acc45[9 + 4 * hi8 + q], (double)vm * (double)inv_p);
+            atomicAdd(&acc45[25 + 4 * hi8 + q], (double)vi * (double)inv_p);
+        }
+    }
+    __syncwarp();
+}
+
+static_assert(kStageCols * kStageStride >= kFitBins * 32, "the staging ring doubles as the match-emission bins");
+struct FitSmem {
+    float binI[kWarpsPerCta][kFitBins * 32];
+};
+
+template <int C>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) fit_kernel(KParams p, double *acc90) {
+    __shared__ SmemLayout sh;
+    __shared__ FitSmem fs;
+    fill_tables(sh, p.models);
+    constexpr int NSLOT = 32 * C;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t wslot = (size_t)blockIdx.x * kWarpsPerCta + warp;
+    // the same scratch, viewed as one float4 per slot: stride (nd+6) * (NSLOT+8) float2 >= nd * NSLOT float4 / 2 is NOT
+    // guaranteed, so the host sizes frow_stride for this kernel as 2 * (max_nd + 1) * NSLOT float2
+    float2 *frow = p.frows + wslot * p.frow_stride;
+    int32_t *kf = p.kf + wslot * p.kf_stride + 3;
+    for (;;) {
+        int pi = 0;
+        if (lane == 0) pi = atomicAdd(p.counter, 1);
+        pi = __shfl_sync(kFull, pi, 0);
+        if (pi >= p.n_pairs) break;
+        const DevPair P = p.pairs[pi];
+        const PairCtx pc = make_pair_ctx(p, P, sh);
+        const Coef a = load_coef(sh.trans[P.model]);
+        int Ktot, ev_n;
+        forward_pass<C, 2>(pc, a, frow, kf, sh.ftot[warp], Ktot, nullptr, ev_n);
+        __syncwarp();
+        const float fin = sh.ftot[warp][0];
+        if (lane == 0)
+            p.out_lk[pi] = fin > 0.f ? log((double)fin) - (double)Ktot * 0.6931471805599453 : -INFINITY;
+        fit_backward<C>(pc, a, sh.trans[P.model], reinterpret_cast<const float4 *>(frow), kf, sh.ftot[warp],
+                        sh.stage[warp], fs.binI[warp], acc90 + 45 * P.model);
         __syncwarp();
     }
 }
@@ -603,6 +777,15 @@ cudaError_t launch_likelihood(const KParams &p, int C, int grid, cudaStream_t st
     switch (C) {
     case 2: likelihood_kernel<2><<<grid, kWarpsPerCta * 32, 0, st>>>(p); break;
     case 4: likelihood_kernel<4><<<grid, kWarpsPerCta * 32, 0, st>>>(p); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fit(const KParams &p, int C, int grid, double *acc90, cudaStream_t st) {
+    switch (C) {
+    case 2: fit_kernel<2><<<grid, kWarpsPerCta * 32, 0, st>>>(p, acc90); break;
+    case 4: fit_kernel<4><<<grid, kWarpsPerCta * 32, 0, st>>>(p, acc90); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

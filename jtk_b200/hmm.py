@@ -182,3 +182,44 @@ def polish_chunks(models: PairHiddenMarkovModelOnStrands, drafts: Sequence, read
     out_cons = [cons[int(cpos[c]):int(cpos[c]) + int(clen[c])].copy() for c in range(n_chunks)]
     out_ops = [buf[int(pos[k]):int(pos[k]) + int(n_ops[k])].copy() for k in range(n_pairs)]
     return out_cons, out_ops, iters
+
+
+def expected_counts(models: PairHiddenMarkovModelOnStrands, templates, reads, ops, strands, tmpl_idx, radius,
+                    ctx: Optional[Context] = None) -> np.ndarray:
+    """jtk_batch_expected_counts: float64[2, 45] (forward-strand reads, reverse-strand reads)."""
+    import ctypes as C
+    ctx = ctx or default_context()
+    L = _lib.lib()
+    b = ctx.batch(list(templates), list(reads), list(ops), np.asarray(strands, dtype=np.uint8), tmpl_idx, radius)
+    try:
+        acc = np.zeros(90, dtype=np.float64)
+        L.jtk_batch_expected_counts.argtypes = [C.c_void_p, C.POINTER(HmmParams), C.POINTER(HmmParams), C.c_void_p]
+        f, r = models.forward().to_c(), models.reverse().to_c()
+        ctx._check(L.jtk_batch_expected_counts(b._h, C.byref(f), C.byref(r), _lib._ptr(acc)))
+        return acc.reshape(2, 45)
+    finally:
+        b.close()
+
+
+def fit_antidiagonal_par_multiple(models: PairHiddenMarkovModelOnStrands, packs, radius: int,
+                                  ctx: Optional[Context] = None) -> None:
+    """Reference signature (model_tune.rs:151): packs = [(cons, strands, seqs, ops), ...] as TrainingDataPack::new;
+    both strand models are updated in place by one EM step."""
+    import ctypes as C
+    ctx = ctx or default_context()
+    L = _lib.lib()
+    templates = [p[0] for p in packs]
+    reads = [r for p in packs for r in p[2]]
+    ops = [o for p in packs for o in p[3]]
+    strands = np.concatenate([np.asarray(p[1], dtype=np.uint8) for p in packs])
+    tidx = np.repeat(np.arange(len(packs), dtype=np.uint32), [len(p[2]) for p in packs])
+    tcat, toff, rcat, roff, ocat, ooff, st, ti = _lib.pack_inputs(templates, reads, ops, strands, tidx)
+    f, r = models.forward().to_c(), models.reverse().to_c()
+    vp = C.c_void_p
+    L.jtk_hmm_fit_batch.argtypes = [vp, C.POINTER(HmmParams), C.POINTER(HmmParams), C.c_int, C.c_int, vp, vp, vp, vp, vp, vp,
+                                    vp, vp, C.c_int]
+    p = _lib._ptr
+    ctx._check(L.jtk_hmm_fit_batch(ctx._h, C.byref(f), C.byref(r), len(reads), len(templates), p(tcat), p(toff), p(rcat),
+                                   p(roff), p(ocat), p(ooff), p(st), p(ti), radius))
+    models._forward = PairHiddenMarkovModel.from_array(np.frombuffer(bytes(f), dtype=np.float64))
+    models._reverse = PairHiddenMarkovModel.from_array(np.frombuffer(bytes(r), dtype=np.float64))

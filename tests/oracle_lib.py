@@ -194,3 +194,34 @@ def polish_until_converge(fwd, rev, draft, reads, ops, strands, radius, take_num
     if rc < 0:
         raise ValueError(f"orc_polish_until_converge rc={rc}")
     return out[:rc].copy(), [bufs[k][:n_ops[k]].copy() for k in range(n)], it.value
+
+
+def fit(fwd, rev, packs, radius):
+    """orc_fit on packs [(template, strands, reads, ops), ...]; returns the two updated OrcHmm."""
+    f = OrcHmm.from_array(fwd.as_array())
+    r = OrcHmm.from_array(rev.as_array())
+    accf, accr = np.zeros(45), np.zeros(45)
+    for (t, strands, reads, ops) in packs:
+        for q, o, st in zip(reads, ops, strands):
+            acc = expected_counts(f if st else r, t, q, o, radius)
+            if st:
+                accf += acc
+            else:
+                accr += acc
+
+    def mstep(h, acc):
+        a = h.as_array()
+        for s in range(3):
+            tot = acc[3 * s:3 * s + 3].sum()
+            if tot > 0:
+                a[3 * s:3 * s + 3] = acc[3 * s:3 * s + 3] / tot
+        for k in range(4):
+            tot = acc[9 + 4 * k:13 + 4 * k].sum()
+            if tot > 0:
+                a[9 + 4 * k:13 + 4 * k] = acc[9 + 4 * k:13 + 4 * k] / tot
+        for c in range(5):
+            tot = acc[25 + 4 * c:29 + 4 * c].sum()
+            if tot > 0:
+                a[25 + 4 * c:29 + 4 * c] = acc[25 + 4 * c:29 + 4 * c] / tot
+        return OrcHmm.from_array(a)
+    return mstep(f, accf), mstep(r, accr), accf, accr
