@@ -16,6 +16,8 @@ cudaError_t launch_modtable(const KParams &p, int C, int grid, cudaStream_t st);
 cudaError_t launch_likelihood(const KParams &p, int C, int grid, cudaStream_t st);
 int warps_per_cta();
 int frow_slots_per_row(int C);
+int frow_extra_rows();
+int modtable_ctas_per_sm(int C);
 cudaError_t launch_fit(const KParams &p, int C, int grid, double *acc90, cudaStream_t st);
 cudaError_t launch_fp32_peak(int mode, int blocks, int threads, int iters, float *sink, cudaStream_t st);
 } // namespace jtk
@@ -477,7 +479,8 @@ int batch_run(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev
     pack_model(rev, models + kModelFloats);
     const int wpc = warps_per_cta();
     int grid = (b->n_pairs + wpc - 1) / wpc;
-    const int max_grid = ctx->sm_count * 4;
+    // persistent CTAs: one wave of resident CTAs pulls pairs from the queue
+    const int max_grid = ctx->sm_count * (table ? modtable_ctas_per_sm(b->C) : 4);
     if (grid > max_grid) grid = max_grid;
     cudaStream_t st = ctx->stream;
     KParams kp{};
@@ -485,7 +488,7 @@ int batch_run(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev
     CU(ctx->d_counter.reserve(1), "cudaMalloc counter");
     if (table) {
         const size_t slots = (size_t)grid * wpc;
-        kp.frow_stride = (size_t)(b->max_nd + 6) * frow_slots_per_row(b->C);
+        kp.frow_stride = (size_t)(b->max_nd + frow_extra_rows()) * frow_slots_per_row(b->C);
         kp.kf_stride = (size_t)b->max_nd + 6;
         CU(ctx->d_frows.reserve(slots * kp.frow_stride), "cudaMalloc forward rows");
         CU(ctx->d_kf.reserve(slots * kp.kf_stride), "cudaMalloc scale exponents");

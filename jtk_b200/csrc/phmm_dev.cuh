@@ -14,7 +14,7 @@ namespace jtk {
 constexpr int kNumRow = 14;
 constexpr int kCodePad = 1024;       // sentinel bytes on both sides of every code array
 constexpr int kStageCols = 64;       // per-warp staging ring (columns) for finished column sums
-constexpr int kStageStride = 20;     // floats per staged column (16 used)
+constexpr int kStageStride = 16;     // floats per staged column
 // per-model float block: [0..8] transitions (HMMParam order), [12..75] eM[tc*8+qc], [76..139] eI[ctx*8+qc],
 // [140..171] eMT[qc*4+b] = eM(ref b, query qc).  Codes 4..7 (no base / padding) hold zeros.
 constexpr int kOffEM = 12, kOffEI = 76, kOffEMT = 140;

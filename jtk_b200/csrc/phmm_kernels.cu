@@ -30,8 +30,13 @@ constexpr int kScaleLow = 88;
 constexpr int kScaleTarget = 100;
 constexpr int kScaleStep = 64;
 constexpr int kProductExp = 0;
-constexpr int kMaxEvents = 96;  // rescale events remembered per pair for the backward fast path
-constexpr int kPrefetchRows = 4; // backward pass: rows pulled into L1 this many steps before their first use
+constexpr int kEvBits = 4096;   // rescale-event map: one bit per block of four anti-diagonals (pairs up to ~16 k diagonals)
+constexpr int kEvWords = kEvBits / 32 + 2;
+// backward pass: per-warp shared-memory ring of forward rows, filled by bulk async copies
+constexpr int kRingRows = 16;   // row slots (four groups of four rows)
+constexpr int kRingMargin = 3;  // copies of the rows at the other end of the ring, on both sides
+constexpr int kRowShift = 4;    // ring / group index of anti-diagonal s is rho = s + kRowShift (four zero rows below s = 0)
+constexpr int kRowsAbove = 8;   // rows past the last anti-diagonal that exist in the scratch (the first three read as zero)
 constexpr int kHalo = 4;        // forward rows carry 4 replicated slots on both sides: neighbours need no wrap-around
 
 // ---- small helpers --------------------------------------------------------------------------------------
@@ -45,6 +50,8 @@ __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %
 __device__ __forceinline__ void acc2(f2 &acc, f2 a, f2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 bc2(float v) { return mk2(v, v); }
+// a packed pair the compiler must keep as one 64-bit value (loop-invariant coefficients: no re-packing per use)
+__device__ __forceinline__ f2 mk2_keep(float lo, float hi) { f2 r; asm volatile("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 
 __device__ __forceinline__ float lds_f32(unsigned a) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void lds_f32x4(unsigned a, f2 &x, f2 &y) {
@@ -54,8 +61,10 @@ __device__ __forceinline__ void lds_f32x4(unsigned a, f2 &x, f2 &y) {
 __device__ __forceinline__ float pow2i(int k) { // exact 2^k, k in [-126, 127]
     return __uint_as_float((unsigned)(127 + k) << 23);
 }
-__device__ __forceinline__ int band_lo(int cen, int r, int s, int Lt) { return max(max(cen - r, 0), s - Lt); }
-__device__ __forceinline__ int band_hi(int cen, int r, int s, int Lr) { return min(min(cen + r, Lr), s); }
+// band window of an anti-diagonal, NOT clamped to the matrix: cells outside the matrix evaluate to zero by themselves
+// (sentinel codes have zero emissions), see the note above the forward pass
+__device__ __forceinline__ int band_lo(int cen, int r, int s, int Lt) { (void)s; (void)Lt; return cen - r; }
+__device__ __forceinline__ int band_hi(int cen, int r, int s, int Lr) { (void)s; (void)Lr; return cen + r; }
 
 // four consecutive read-row codes Rb[i..i+3] as one register (byte 0 = row i); RbP = Rb - kCodePad is 4-aligned
 __device__ __forceinline__ unsigned win_up(const uint8_t *__restrict__ RbP, int i) {
@@ -75,12 +84,14 @@ struct Coef {
     f2 bM, bI, bD;        // backward: (B_M, B_D) = bM*gM + bI*gI + bD*gD   = ((mm,dm), (mi,di), (md,dd))
     float b_im, b_ii, b_id; //         B_I      = im*gM + ii*gI + id*gD
 };
-__device__ __forceinline__ Coef load_coef(const float *t) { // t: mat_mat, mat_ins, mat_del, ins_mat, ...
-    const float mm = t[0], mi = t[1], md = t[2], im = t[3], ii = t[4], id = t[5], dm = t[6], di = t[7], dd = t[8];
+__device__ __forceinline__ Coef load_coef(const float *t, const unsigned long long *cp) {
+    // t: mat_mat, mat_ins, mat_del, ins_mat, ...; cp: the six packed pairs, read as 64-bit values so that they stay
+    // in aligned register pairs (no re-packing at every use)
+    const float mi = t[1], im = t[3], ii = t[4], id = t[5], di = t[7];
     Coef c;
-    c.fM = mk2(mm, md); c.fI = mk2(im, id); c.fD = mk2(dm, dd);
+    c.fM = cp[0]; c.fI = cp[1]; c.fD = cp[2];
     c.f_mi = mi; c.f_ii = ii; c.f_di = di;
-    c.bM = mk2(mm, dm); c.bI = mk2(mi, di); c.bD = mk2(md, dd);
+    c.bM = cp[3]; c.bI = cp[4]; c.bD = cp[5];
     c.b_im = im; c.b_ii = ii; c.b_id = id;
     return c;
 }
@@ -91,10 +102,11 @@ struct __align__(256) SmemLayout {
     float ei[2][64];  // [ctx*8 + qc]  byte offset = the read-row code byte (ctx<<5 | qc<<2)
     float emt[2][32]; // [qc*4 + b]    eM(ref b, query qc)
     float trans[2][12];
+    unsigned long long cpair[2][6]; // (mm,md) (im,id) (dm,dd) | (mm,dm) (mi,di) (md,dd) as packed fp32 pairs
     float stage[kWarpsPerCta][kStageCols * kStageStride];
     float ftot[kWarpsPerCta][4];
-    unsigned short ev_s[kWarpsPerCta][kMaxEvents]; // steps at which the forward pass rescaled
-    int ev_n[kWarpsPerCta];
+    unsigned evw[kWarpsPerCta][kEvWords];          // blocks of four anti-diagonals in which the forward pass rescaled
+    unsigned long long bar[kWarpsPerCta][4];       // mbarriers of the four ring groups
 };
 
 __device__ __forceinline__ void fill_tables(SmemLayout &sh, const float *__restrict__ models) {
@@ -104,6 +116,10 @@ __device__ __forceinline__ void fill_tables(SmemLayout &sh, const float *__restr
         sh.ei[m][e] = models[m * kModelFloats + kOffEI + e];
         if (e < 32) sh.emt[m][e] = models[m * kModelFloats + kOffEMT + e];
         if (e < 12) sh.trans[m][e] = models[m * kModelFloats + e];
+        if (e < 6) {
+            const int lo_i[6] = { 0, 3, 6, 0, 1, 2 }, hi_i[6] = { 2, 5, 8, 6, 7, 8 };
+            sh.cpair[m][e] = mk2(models[m * kModelFloats + lo_i[e]], models[m * kModelFloats + hi_i[e]]);
+        }
     }
     __syncthreads();
 }
@@ -117,32 +133,36 @@ struct PairCtx { // warp-uniform view of one pair
 };
 
 // ------------------------------------------------------------------------------------------------
-// Forward pass.  STORE: write (toM, toD) of every cell to frow[s*NSLOT + slot] and the cumulative scale
-// exponent to kf[s].  s_ftot[d] (d = 0..3) receives (F_M+F_I+F_D)(Lr, Lt-d) * 2^Ktot; s_ftot[0] is the
-// final value the likelihood is read from.
+// Band bookkeeping.  A slot tracks x = i - (centre(s) - r), the offset of its cell inside the band window of
+// anti-diagonal s; the cell is in band iff 0 <= x <= W = 2r.  The matrix edges need no clamps: codes outside
+// [1, L] are sentinels whose emissions are zero, so every cell outside the matrix evaluates to zero by itself
+// (forward: nothing flows in from i < 0 / j < 0; the D-state garbage in columns > Lt never flows back and meets
+// g = 0 in every table sum; backward: the terminal value is injected at (Lr, Lt) only).
+// Moving to the next anti-diagonal changes x only when the centre stays (guide bit 0): all x move by one and
+// exactly one slot leaves the band -- a warp-uniform event, no vote needed.
+// ------------------------------------------------------------------------------------------------
+// Forward pass.  STORE = 1: write (toM, toD) of every cell to frow[s*RS + kHalo + slot] and the cumulative scale
+// exponent to kf[s], and mark rescale events in evw.  STORE = 2 (fit): write (F_M, F_I, F_D) per slot.
+// s_ftot[d] (d = 0..3) receives (F_M+F_I+F_D)(Lr, Lt-d) * 2^Ktot; s_ftot[0] is the value the likelihood is read from.
 // ------------------------------------------------------------------------------------------------
 template <int C> struct FwdState {
-    int j[C];
+    int x[C], j[C];
     unsigned tcB[C], win[C];
     float toI[C], inD[C], inMa[C], inMb[C];
 };
 
 template <int C, int STORE, bool SPECIAL>
-__device__ __forceinline__ void fwd_step(const PairCtx &pc, const Coef &a, FwdState<C> &st, const int s, const int cen,
+__device__ __forceinline__ void fwd_step(const PairCtx &pc, const Coef &a, FwdState<C> &st, const int s, const int W,
                                          int &K, f2 *__restrict__ &wrow, const int halo, int32_t *__restrict__ kf,
-                                         volatile float *s_ftot, unsigned short *ev_s, int &ev_n) {
+                                         volatile float *s_ftot, unsigned *evw) {
     constexpr int NSLOT = 32 * C;
     constexpr int RS = NSLOT + 2 * kHalo;
     const int lane = threadIdx.x & 31;
-    const int lo = band_lo(cen, pc.r, s, pc.Lt), hi = band_hi(cen, pc.r, s, pc.Lr);
-    const int W = hi - lo, A = s - lo;
     f2 tMD[C];
     float Fm[C], Fi[C], Fd[C]; // forward states, kept only for the fit kernel (STORE == 2)
-    unsigned dead = 0u;
 #pragma unroll
     for (int c = 0; c < C; c++) {
-        const int x = A - st.j[c];
-        const bool valid = (unsigned)x <= (unsigned)W;
+        const bool valid = (unsigned)st.x[c] <= (unsigned)W;
         const unsigned w = st.win[c];
         st.win[c] = w >> 8;
         float em = lds_f32(st.tcB[c] | (w & 0x1cu));
@@ -156,17 +176,8 @@ __device__ __forceinline__ void fwd_step(const PairCtx &pc, const Coef &a, FwdSt
         tMD[c] = fma2(a.fD, bc2(D), fma2(a.fI, bc2(I), mul2(a.fM, bc2(M))));
         st.toI[c] = fmaf(a.f_di, D, fmaf(a.f_ii, I, a.f_mi * M));
         if (STORE == 2) { Fm[c] = M; Fi[c] = I; Fd[c] = D; }
-        if (SPECIAL && s >= pc.nd - 4 && valid && x + lo == pc.Lr && st.j[c] >= pc.Lt - 3) s_ftot[pc.Lt - st.j[c]] = M + I + D;
-        if (x > W) dead |= 1u << c;
-    }
-    if (__any_sync(kFull, dead != 0u)) { // rare: keep it a real branch, not predicated code in the hot path
-#pragma unroll
-        for (int c = 0; c < C; c++)
-            if (dead & (1u << c)) { // below the band for good: the slot moves on to column j + NSLOT
-                st.j[c] += NSLOT;
-                st.tcB[c] = pc.sEM + ((unsigned)pc.Tb[st.j[c]] << 5);
-                st.win[c] = win_up(pc.RbP, s + 1 - st.j[c]);
-            }
+        if (SPECIAL && s >= pc.nd - 4 && valid && s - st.j[c] == pc.Lr && st.j[c] >= pc.Lt - 3)
+            s_ftot[pc.Lt - st.j[c]] = M + I + D;
     }
     if ((s & (kRescaleEvery - 1)) == kRescaleEvery - 1 && s < pc.nd - 8) {
         float v = lo2(tMD[0]);
@@ -184,9 +195,9 @@ __device__ __forceinline__ void fwd_step(const PairCtx &pc, const Coef &a, FwdSt
                 for (int c = 0; c < C; c++) { Fm[c] *= sc; Fi[c] *= sc; Fd[c] *= sc; }
             }
             K += k;
-            if (STORE == 1) {
-                if (ev_n < kMaxEvents && lane == 0) ev_s[ev_n] = (unsigned short)s;
-                ev_n++;
+            if (STORE == 1) { // the backward pass takes the exact-correction path around this row
+                const unsigned b = (unsigned)(s >> 2) + 2u;
+                if (lane == 0 && b < (unsigned)(kEvWords * 32)) evw[b >> 5] |= 1u << (b & 31u);
             }
         }
     }
@@ -219,29 +230,48 @@ __device__ __forceinline__ void fwd_step(const PairCtx &pc, const Coef &a, FwdSt
 
 template <int C, int STORE>
 __device__ __forceinline__ void forward_pass(const PairCtx &pc, const Coef &a, float2 *__restrict__ frow,
-                                             int32_t *__restrict__ kf, volatile float *s_ftot, int &Ktot,
-                                             unsigned short *ev_s, int &ev_n) {
+                                             int32_t *__restrict__ kf, volatile float *s_ftot, int &Ktot, unsigned *evw) {
     constexpr int NSLOT = 32 * C;
     const int lane = threadIdx.x & 31;
-    const int nd = pc.nd;
+    const int nd = pc.nd, W = 2 * pc.r;
     f2 *wrow = (STORE == 2) ? reinterpret_cast<f2 *>(reinterpret_cast<float4 *>(frow) + lane * C)
                             : reinterpret_cast<f2 *>(frow) + kHalo + lane * C; // this lane's slots in row 0
     const int halo = (lane * C < 3) ? NSLOT : ((lane * C + C > NSLOT - 3) ? -NSLOT : 0);
-    ev_n = 0;
     FwdState<C> st;
 #pragma unroll
     for (int c = 0; c < C; c++) {
         st.j[c] = lane * C + c;
+        st.x[c] = pc.r - st.j[c]; // row i = -j on anti-diagonal 0, window starts at row -r
         st.tcB[c] = pc.sEM + ((unsigned)pc.Tb[st.j[c]] << 5);
         st.win[c] = win_up(pc.RbP, -st.j[c]);
         st.toI[c] = st.inD[c] = st.inMa[c] = st.inMb[c] = 0.f;
     }
     if (lane < 4) s_ftot[lane] = 0.f;
-    int cen = 0, K = 0;
+    int K = 0;
+    int xtop = pc.r; // largest x over the slots (warp-uniform)
     unsigned bword = pc.bw[0];
-    auto advance = [&](int s) { // centre of anti-diagonal s+1
-        cen += (bword >> (s & 31)) & 1u;
+    auto transition = [&](int s) { // anti-diagonal s -> s+1
+        const unsigned b = (bword >> (s & 31)) & 1u;
         if (((s + 1) & 31) == 0) bword = pc.bw[(s + 1) >> 5];
+        if (b == 0u) { // centre stays: every cell moves one row up inside the window
+            if (xtop < W) {
+                xtop++;
+#pragma unroll
+                for (int c = 0; c < C; c++) st.x[c]++;
+            } else {
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    if (st.x[c] == W) { // the slot at the top of the band moves on to column j + NSLOT
+                        st.j[c] += NSLOT;
+                        st.tcB[c] = pc.sEM + ((unsigned)pc.Tb[st.j[c]] << 5);
+                        st.win[c] = win_up(pc.RbP, s + 1 - st.j[c]);
+                        st.x[c] = W + 1 - NSLOT;
+                    } else {
+                        st.x[c]++;
+                    }
+                }
+            }
+        }
     };
     auto reload = [&](int s) {
 #pragma unroll
@@ -250,22 +280,22 @@ __device__ __forceinline__ void forward_pass(const PairCtx &pc, const Coef &a, f
     int s = 0;
     // prologue: the first four anti-diagonals (the start cell is injected at s = 0)
     for (; s < 4 && s < nd; ++s) {
-        fwd_step<C, STORE, true>(pc, a, st, s, cen, K, wrow, halo, kf, s_ftot, ev_s, ev_n);
-        advance(s);
+        fwd_step<C, STORE, true>(pc, a, st, s, W, K, wrow, halo, kf, s_ftot, evw);
+        if (s < nd - 1) transition(s);
     }
     // main loop: four steps per read-row window
     for (; s + 3 < nd - 4; s += 4) {
         reload(s);
-        fwd_step<C, STORE, false>(pc, a, st, s, cen, K, wrow, halo, kf, s_ftot, ev_s, ev_n); advance(s);
-        fwd_step<C, STORE, false>(pc, a, st, s + 1, cen, K, wrow, halo, kf, s_ftot, ev_s, ev_n); advance(s + 1);
-        fwd_step<C, STORE, false>(pc, a, st, s + 2, cen, K, wrow, halo, kf, s_ftot, ev_s, ev_n); advance(s + 2);
-        fwd_step<C, STORE, false>(pc, a, st, s + 3, cen, K, wrow, halo, kf, s_ftot, ev_s, ev_n); advance(s + 3);
+        fwd_step<C, STORE, false>(pc, a, st, s, W, K, wrow, halo, kf, s_ftot, evw); transition(s);
+        fwd_step<C, STORE, false>(pc, a, st, s + 1, W, K, wrow, halo, kf, s_ftot, evw); transition(s + 1);
+        fwd_step<C, STORE, false>(pc, a, st, s + 2, W, K, wrow, halo, kf, s_ftot, evw); transition(s + 2);
+        fwd_step<C, STORE, false>(pc, a, st, s + 3, W, K, wrow, halo, kf, s_ftot, evw); transition(s + 3);
     }
     // epilogue: the last anti-diagonals also record the delete-to-end terms
     for (; s < nd; ++s) {
         if ((s & 3) == 0) reload(s);
-        fwd_step<C, STORE, true>(pc, a, st, s, cen, K, wrow, halo, kf, s_ftot, ev_s, ev_n);
-        if (s < nd - 1) advance(s);
+        fwd_step<C, STORE, true>(pc, a, st, s, W, K, wrow, halo, kf, s_ftot, evw);
+        if (s < nd - 1) transition(s);
     }
     Ktot = K;
     __syncwarp();
@@ -274,9 +304,33 @@ __device__ __forceinline__ void forward_pass(const PairCtx &pc, const Coef &a, f
 // ------------------------------------------------------------------------------------------------
 // Backward pass fused with the modification-table reduction.  ROWS = 14 (all rows) or 9 (rows 0-7 and
 // the one-base deletion, the only rows local_clustering reads: pseudo_mcmc.rs:447).
+//
+// The forward rows come back from HBM through a per-warp shared-memory ring filled by bulk async copies
+// (cp.async.bulk, completion on an mbarrier), one group of four rows per copy, issued one block of four
+// anti-diagonals ahead of their first use: the inner loop sees shared-memory loads with immediate offsets only.
+// Ring geometry: row index rho = s + kRowShift; 16 row slots + 3 margin slots on both sides that hold copies of the
+// rows at the other end, so that rows rho-3 .. rho+3 are always contiguous around slot (rho & 15) + 3.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok = 0;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 template <int C> struct BwdState {
-    int j[C];
+    int x[C], j[C];
     unsigned tcB[C], win[C];
     float BI[C], BMo[C], inD[C], inMa[C], inMb[C];
     f2 S01[C], S23[C], N01[C], N23[C]; // substitution / insertion sums over the four bases
@@ -284,34 +338,43 @@ template <int C> struct BwdState {
     f2 Xp[C][3], Xm[C][3];             // (sum toM*gM, sum toD*gD) of the copy / deletion cuts
 };
 
+// One anti-diagonal.  rp = this lane's first slot of forward row s inside the ring; row s+e, slot+e is rp[e*RS + e].
+// CORR: a rescale lies within rows s-2 .. s+3 (products that pair two rows get their exact power-of-two correction);
+// FIRST: s = nd-1, the terminal cell is injected.
 template <int C, int ROWS, bool CORR, bool FIRST>
-__device__ __forceinline__ void bwd_step(const PairCtx &pc, const Coef &a, BwdState<C> &st, const int s, const int lo,
-                                         const int W, const f2 *__restrict__ rp, const float *ce, const float boff,
-                                         f2 (&bMD)[C], unsigned &dead_mask) {
+__device__ __forceinline__ void bwd_step(const PairCtx &pc, const Coef &a, BwdState<C> &st, const f2 *rp, const int W,
+                                         const float *ce, const float boff, f2 (&bMD)[C]) {
     constexpr int NSLOT = 32 * C;
-    constexpr int RS = NSLOT + 2 * kHalo; // rp = this lane's first slot in row s; row s+e, slot+e is rp[e*RS + e]
+    constexpr int RS = NSLOT + 2 * kHalo;
     constexpr int NXM = (ROWS == 14) ? 3 : 1;
     constexpr int NXP = (ROWS == 14) ? 3 : 0;
-    const int A = s - lo;
     f2 F0[C];
 #pragma unroll
-    for (int c = 0; c < C; c += 2)
-        asm("ld.global.v2.b64 {%0, %1}, [%2];" : "=l"(F0[c]), "=l"(F0[c + 1]) : "l"(rp + c));
+    for (int c = 0; c < C; c += 2) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(rp + c);
+        F0[c] = v.x; F0[c + 1] = v.y;
+    }
 #pragma unroll
     for (int c = 0; c < C; c++) {
-        const int x = A - st.j[c];
-        const bool valid = (unsigned)x <= (unsigned)W;
+        const bool valid = (unsigned)st.x[c] <= (unsigned)W;
         const unsigned w = st.win[c];
         st.win[c] = w >> 8;
-        const float em = lds_f32(st.tcB[c] | (w & 0x1cu));
-        const float ei = lds_f32(pc.sEI | (w & 0xffu));
+        float em = lds_f32(st.tcB[c] | (w & 0x1cu));
+        float ei = lds_f32(pc.sEI | (w & 0xffu));
         f2 ec01, ec23;
         lds_f32x4(pc.sEMT | ((w & 0x1cu) << 2), ec01, ec23);
-        const float gM = em * st.inMb[c], gI = ei * st.BI[c], gD = st.inD[c];
+        // a cell outside the band contributes nothing: its in-sums are masked (its forward values are zero already)
+        em = valid ? em : 0.f;
+        ei = valid ? ei : 0.f;
+        const float gD = valid ? st.inD[c] : 0.f;
+        const float gM = em * st.inMb[c], gI = ei * st.BI[c];
         f2 md = fma2(a.bD, bc2(gD), fma2(a.bI, bc2(gI), mul2(a.bM, bc2(gM))));
         float i_ = fmaf(a.b_id, gD, fmaf(a.b_ii, gI, a.b_im * gM));
-        if (FIRST) { md = bc2(boff); i_ = boff; }
-        if (!valid) { md = 0ull; i_ = 0.f; }
+        if (FIRST) { // B(Lr, Lt) = boff, everything else on the last anti-diagonal is outside the matrix
+            const bool term = st.j[c] == pc.Lt;
+            md = term ? bc2(boff) : 0ull;
+            i_ = term ? boff : 0.f;
+        }
         // ---- table reduction for cell (i, j) ----
         const float f0m = lo2(F0[c]), f0d = hi2(F0[c]);
         const f2 U = bc2(f0m * st.inMb[c]);
@@ -322,65 +385,86 @@ __device__ __forceinline__ void bwd_step(const PairCtx &pc, const Coef &a, BwdSt
         acc2(st.N01[c], U2, ec01);
         acc2(st.N23[c], U2, ec23);
         st.Vn[c] = fmaf(f0d, hi2(md), st.Vn[c]);
-        // cuts pairing this column's backward terms with forward columns j-1..j-3 (deletions) and j+1..j+3
-        // (copies).  gM/gD vanish outside x in [-1, W+1] by themselves; x = W+1 must not feed a deletion and
-        // x = -1 must not feed a copy, or a slot would alias the column NSLOT away.
-        {
-            const bool okm = x <= W;
-            const f2 g = mk2(okm ? gM : 0.f, okm ? gD : 0.f);
+        // cuts pairing this column's backward in-sums with forward columns j-1..j-3 (deletions) and j+1..j+3
+        // (copies).  g is zero unless the cell is in band, and then slot+e of row s+e holds column j+e.
+        const f2 g = mk2(gM, gD);
 #pragma unroll
-            for (int e = 1; e <= NXM; e++) {
-                f2 Fe;
-                asm("ld.global.b64 %0, [%1];" : "=l"(Fe) : "l"(rp + (c - e * RS - e)));
-                if (CORR) acc2(st.Xm[c][e - 1], mul2(Fe, g), bc2(ce[3 - e]));
-                else acc2(st.Xm[c][e - 1], Fe, g);
-            }
+        for (int e = 1; e <= NXM; e++) {
+            const f2 Fe = rp[c - e * RS - e];
+            if (CORR) acc2(st.Xm[c][e - 1], mul2(Fe, g), bc2(ce[3 - e]));
+            else acc2(st.Xm[c][e - 1], Fe, g);
         }
-        if (NXP > 0) {
-            const bool okp = x >= 0;
-            const f2 g = mk2(okp ? gM : 0.f, okp ? gD : 0.f);
 #pragma unroll
-            for (int e = 1; e <= NXP; e++) {
-                f2 Fe;
-                asm("ld.global.b64 %0, [%1];" : "=l"(Fe) : "l"(rp + (c + e * RS + e)));
-                if (CORR) acc2(st.Xp[c][e - 1], mul2(Fe, g), bc2(ce[3 + e]));
-                else acc2(st.Xp[c][e - 1], Fe, g);
-            }
+        for (int e = 1; e <= NXP; e++) {
+            const f2 Fe = rp[c + e * RS + e];
+            if (CORR) acc2(st.Xp[c][e - 1], mul2(Fe, g), bc2(ce[3 + e]));
+            else acc2(st.Xp[c][e - 1], Fe, g);
         }
         bMD[c] = md;
         st.BI[c] = i_; st.BMo[c] = lo2(md);
-        if (x < 0) dead_mask |= 1u << c;
     }
 }
 
 template <int C, int ROWS>
 __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, const float2 *__restrict__ frow,
                                               const int32_t *__restrict__ kf, float *stage, volatile float *s_ftot,
-                                              float *__restrict__ out, const unsigned short *ev_s, const int ev_n) {
+                                              float *__restrict__ out, const unsigned *evw, f2 *ring, const unsigned bars,
+                                              unsigned &phase) {
     constexpr int NSLOT = 32 * C;
     constexpr int RS = NSLOT + 2 * kHalo;
+    constexpr unsigned RSB = RS * 8u; // bytes per forward row
     const int lane = threadIdx.x & 31;
-    const int Lt = pc.Lt, Lr = pc.Lr, nd = pc.nd;
+    const int Lt = pc.Lt, Lr = pc.Lr, nd = pc.nd, W = 2 * pc.r;
     // B(Lr,Lt) = boff puts sum_cells F*B = fin * boff at about 2^kProductExp
     const float fin_raw = s_ftot[0];
     const int e_fin = (int)(__float_as_uint(fin_raw) >> 23) - 127;
     const float boff = fin_raw > 0.f ? pow2i(max(-120, min(120, kProductExp - e_fin))) : 1.f;
     const float fin = fin_raw * boff;
 
+    // ---- ring of forward rows ------------------------------------------------------------------------
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+    const float2 *grow0 = frow - (ptrdiff_t)kRowShift * RS; // global row rho = 0
+    auto issue_group = [&](int q) { // rows rho = 4q .. 4q+3
+        if (lane == 0) {
+            const unsigned g = (unsigned)q & 3u;
+            const unsigned bar = bars + 8u * g;
+            const float2 *src = grow0 + (size_t)(4 * q) * RS;
+            mbar_expect_tx(bar, (g == 0u || g == 3u) ? 7u * RSB : 4u * RSB);
+            bulk_g2s(ring_s + (4u * g + kRingMargin) * RSB, src, 4u * RSB, bar);
+            if (g == 3u) bulk_g2s(ring_s, src + RS, 3u * RSB, bar);                                // rows 13..15 below slot 0
+            if (g == 0u) bulk_g2s(ring_s + (kRingRows + kRingMargin) * RSB, src, 3u * RSB, bar);  // rows 0..2 above slot 15
+        }
+    };
+    auto wait_group = [&](int q) {
+        const unsigned g = (unsigned)q & 3u;
+        mbar_wait(bars + 8u * g, (phase >> g) & 1u);
+        phase ^= 1u << g;
+    };
+    const int q_top = (nd + 3) >> 2; // block of the last anti-diagonal (rho = nd + 3)
+    // the forward rows were written through the generic proxy: order them before the async-proxy reads
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+    __syncwarp();
+    issue_group(q_top + 1);
+    issue_group(q_top);
+    issue_group(q_top - 1);
+
     BwdState<C> st;
 #pragma unroll
     for (int c = 0; c < C; c++) {
         const int sigma = lane * C + c;
-        st.j[c] = Lt - ((Lt - sigma) & (NSLOT - 1)); // largest column <= Lt owned by this slot
+        const int d = (Lt - sigma) & (NSLOT - 1);
+        st.j[c] = Lt - d;      // largest column <= Lt owned by this slot
+        st.x[c] = d + pc.r;    // row i = Lr + d on the last anti-diagonal, window starts at row Lr - r
         st.tcB[c] = pc.sEM + ((unsigned)pc.Tb[st.j[c] + 1] << 5); // code of t[j]
-        st.win[c] = win_down(pc.RbP, (nd - 1) - st.j[c] + 1);
+        st.win[c] = 0u;
         st.BI[c] = st.BMo[c] = st.inD[c] = st.inMa[c] = st.inMb[c] = 0.f;
         st.Vs[c] = st.Vn[c] = 0.f;
         st.S01[c] = st.S23[c] = st.N01[c] = st.N23[c] = 0ull;
 #pragma unroll
         for (int e = 0; e < 3; e++) { st.Xp[c][e] = 0ull; st.Xm[c][e] = 0ull; }
     }
-    int cen = Lr;
+    int xmin = pc.r;   // smallest x over the slots (warp-uniform)
+    int jd = Lt;       // the column that leaves the band next (warp-uniform)
     int blk_lo = (Lt >> 5) << 5;
 
     auto flush_col = [&](int c) {
@@ -426,93 +510,99 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
         }
         __syncwarp();
     };
-
-    unsigned bword = pc.bw[(nd - 1) >> 5];
-    const f2 *rp = reinterpret_cast<const f2 *>(frow) + (ptrdiff_t)(nd - 1) * RS + kHalo + lane * C;
-    // newest rescale event at or below s+3; the fast path needs none inside rows s-2 .. s+3
-    const bool ev_over = ev_n > kMaxEvents;
-    int ei = min(ev_n, kMaxEvents) - 1;
-    int es = ei >= 0 ? (int)ev_s[ei] : -100;
-    int s = nd - 1;
-    // One anti-diagonal.  CORR: a rescale lies within rows s-2 .. s+3 (exact corrections, mirrored scaling);
-    // FIRST: s = nd-1, the terminal cell is injected.  The common case (no rescale nearby) runs in its own loop
-    // so that its register allocation is not tied to the rare path's.
-    auto body = [&](auto corr_t, auto first_t) {
-        constexpr bool CORR = decltype(corr_t)::value;
-        constexpr bool FIRST = decltype(first_t)::value;
-        const int lo = band_lo(cen, pc.r, s, Lt), hi = band_hi(cen, pc.r, s, Lr);
-        const int W = hi - lo;
-        if (FIRST || (s & 3) == 3) {
+    // hand (B_M, B_D) to the left-hand neighbour column (slot-1, wrapping)
+    auto hand_off = [&](f2 (&bMD)[C]) {
+        const float rM = __shfl_sync(kFull, lo2(bMD[0]), (lane + 1) & 31);
+        const float rD = __shfl_sync(kFull, hi2(bMD[0]), (lane + 1) & 31);
 #pragma unroll
-            for (int c = 0; c < C; c++) st.win[c] = win_down(pc.RbP, s - st.j[c] + 1);
-        }
-        // the forward row that enters the 7-row window kPrefetchRows steps from now: pull it into L1 early
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(rp - (3 + kPrefetchRows) * RS));
-        f2 bMD[C];
-        unsigned dead = 0;
-        int kstep = 0; // exponent the forward pass added at step s (mirrored below)
-        if (CORR) {
-            const int kcur = kf[s];
-            kstep = kcur - kf[s - 1];
-            float ce[7];
+        for (int c = 0; c < C - 1; c++) { st.inMb[c] = st.inMa[c]; st.inMa[c] = lo2(bMD[c + 1]); st.inD[c] = hi2(bMD[c + 1]); }
+        st.inMb[C - 1] = st.inMa[C - 1]; st.inMa[C - 1] = rM; st.inD[C - 1] = rD;
+    };
+    // anti-diagonal s -> s-1 when the centre stays (guide bit 0): every cell moves one row down inside the window and
+    // the slot at the bottom of the band is done: its column sums are staged and the slot moves on to column j - NSLOT
+    auto shift_down = [&](int s) {
+        if (xmin > 0) {
+            xmin--;
 #pragma unroll
-            for (int e = -3; e <= 3; e++) ce[e + 3] = pow2i(max(-126, min(126, kcur - kf[s + e])));
-            bwd_step<C, ROWS, true, FIRST>(pc, a, st, s, lo, W, rp, ce, boff, bMD, dead);
+            for (int c = 0; c < C; c++) st.x[c]--;
         } else {
-            bwd_step<C, ROWS, false, FIRST>(pc, a, st, s, lo, W, rp, nullptr, boff, bMD, dead);
-        }
-        if (__any_sync(kFull, dead != 0)) {
 #pragma unroll
             for (int c = 0; c < C; c++) {
-                if (dead & (1u << c)) { // above the band for good: stage the finished sums, move to column j - NSLOT
-                    if (st.j[c] >= 0 && st.j[c] <= Lt) flush_col(c);
+                if (st.x[c] == 0) {
+                    if (st.j[c] >= 0) flush_col(c);
                     st.j[c] -= NSLOT;
+                    st.x[c] = NSLOT - 1;
                     st.tcB[c] = pc.sEM + ((unsigned)pc.Tb[st.j[c] + 1] << 5);
                     st.win[c] = win_down(pc.RbP, (s - 1) - st.j[c] + 1);
                     st.Vs[c] = st.Vn[c] = 0.f;
                     st.S01[c] = st.S23[c] = st.N01[c] = st.N23[c] = 0ull;
 #pragma unroll
                     for (int e = 0; e < 3; e++) { st.Xp[c][e] = 0ull; st.Xm[c][e] = 0ull; }
+                } else {
+                    st.x[c]--;
                 }
             }
-            const int jhi = s - lo;
-            while (blk_lo > jhi) { emit_block(blk_lo); blk_lo -= 32; }
+            if (jd == blk_lo) { emit_block(blk_lo); blk_lo -= 32; }
+            jd--;
         }
-        // hand (B_M, B_D) to the left-hand neighbour column (slot-1, wrapping)
-        const float rM = __shfl_sync(kFull, lo2(bMD[0]), (lane + 1) & 31);
-        const float rD = __shfl_sync(kFull, hi2(bMD[0]), (lane + 1) & 31);
+    };
+    auto reload = [&](int s) {
 #pragma unroll
-        for (int c = 0; c < C - 1; c++) { st.inMb[c] = st.inMa[c]; st.inMa[c] = lo2(bMD[c + 1]); st.inD[c] = hi2(bMD[c + 1]); }
-        st.inMb[C - 1] = st.inMa[C - 1]; st.inMa[C - 1] = rM; st.inD[C - 1] = rD;
+        for (int c = 0; c < C; c++) st.win[c] = win_down(pc.RbP, s - st.j[c] + 1);
+    };
+    // generic step: any s, exact corrections, ring slot computed from s
+    auto slow_step = [&](int s) {
+        const f2 *rp = ring + (size_t)(((s + kRowShift) & (kRingRows - 1)) + kRingMargin) * RS + kHalo + lane * C;
+        if (s == nd - 1 || (s & 3) == 3) reload(s);
+        const int kcur = kf[s];
+        const int kstep = kcur - kf[s - 1]; // exponent the forward pass added at step s (mirrored below)
+        float ce[7];
+#pragma unroll
+        for (int e = -3; e <= 3; e++) ce[e + 3] = pow2i(max(-126, min(126, kcur - kf[s + e])));
+        f2 bMD[C];
+        if (s == nd - 1) bwd_step<C, ROWS, true, true>(pc, a, st, rp, W, ce, boff, bMD);
+        else bwd_step<C, ROWS, true, false>(pc, a, st, rp, W, ce, boff, bMD);
+        hand_off(bMD);
         if (s > 0) {
-            if (CORR && kstep != 0) { // mirror of the forward rescale at step s
+            if (kstep != 0) { // mirror of the forward rescale at step s
                 const float sc = pow2i(kstep);
 #pragma unroll
                 for (int c = 0; c < C; c++) { st.BI[c] *= sc; st.BMo[c] *= sc; st.inD[c] *= sc; st.inMa[c] *= sc; st.inMb[c] *= sc; }
             }
-            cen -= (bword >> ((s - 1) & 31)) & 1u;
-            if (((s - 1) & 31) == 0 && s > 1) bword = pc.bw[(s - 2) >> 5];
+            const unsigned b = (pc.bw[(s - 1) >> 5] >> ((s - 1) & 31)) & 1u;
+            if (b == 0u) shift_down(s);
         }
-        --s;
-        rp -= RS;
     };
-    using T = std::true_type;
-    using F = std::false_type;
-    body(T{}, T{});
-    while (s >= 0) {
-        while (es > s + 3) { ei--; es = ei >= 0 ? (int)ev_s[ei] : -100; }
-        if (!ev_over && es < s - 2) {
-            const int s_end = max(es + 3, 0); // rows down to here see no rescale inside s-2 .. s+3
-            while (s >= s_end) body(F{}, F{});
+
+    const bool ev_over = ((nd >> 2) + 3) >= kEvWords * 32; // event map too short for this pair: every block is generic
+    wait_group(q_top + 1);
+    wait_group(q_top);
+    for (int q = q_top; q >= 1; --q) { // block q: anti-diagonals s = 4q-1 .. 4q-4 (rho = 4q+3 .. 4q)
+        wait_group(q - 1);
+        __syncwarp(); // every lane is done with the rows that the next copy overwrites
+        if (q >= 2) issue_group(q - 2);
+        const int s_hi = 4 * q - 1;
+        // rescale events in rows 4q-7 .. 4q+2 are bits q .. q+2 of the event map
+        const unsigned ew = __funnelshift_r(evw[q >> 5], evw[(q >> 5) + 1], q & 31) & 7u;
+        if (s_hi <= nd - 2 && q >= 2 && ew == 0u && !ev_over) {
+            const f2 *rp = ring + (size_t)(4 * (q & 3) + 3 + kRingMargin) * RS + kHalo + lane * C;
+            reload(s_hi);
+            // guide bits 4q-5 .. 4q-2: step k (s = s_hi - k) moves on with bit 4q-2-k
+            const int b0 = 4 * q - 5;
+            const unsigned nib = __funnelshift_r(pc.bw[b0 >> 5], pc.bw[(b0 >> 5) + 1], b0 & 31);
+#pragma unroll 1
+            for (int k = 0; k < 4; k++, rp -= RS) {
+                f2 bMD[C];
+                bwd_step<C, ROWS, false, false>(pc, a, st, rp, W, nullptr, boff, bMD);
+                hand_off(bMD);
+                if (((nib >> (3 - k)) & 1u) == 0u) shift_down(s_hi - k);
+            }
         } else {
-            body(T{}, F{});
+            for (int s = min(s_hi, nd - 1); s >= 4 * q - 4; --s) slow_step(s);
         }
     }
-    // columns still alive after s = 0 (column 0), then the remaining blocks
-#pragma unroll
-    for (int c = 0; c < C; c++)
-        if (st.j[c] >= 0 && st.j[c] <= Lt) flush_col(c);
-    while (blk_lo >= 0) { emit_block(blk_lo); blk_lo -= 32; }
+    // the columns still in the window after s = 0 (0 .. r) leave it in the same order, block by block
+    while (jd >= 0) shift_down(0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -530,19 +620,27 @@ __device__ __forceinline__ PairCtx make_pair_ctx(const KParams &p, const DevPair
     return pc;
 }
 
+template <int C> constexpr int ring_floats2() { return (kRingRows + 2 * kRingMargin) * (32 * C + 2 * kHalo); }
+
 template <int C, int ROWS>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) modtable_kernel(KParams p) {
     __shared__ SmemLayout sh;
+    extern __shared__ __align__(128) unsigned char dyn_smem[]; // kWarpsPerCta rings of forward rows
     fill_tables(sh, p.models);
     constexpr int NSLOT = 32 * C;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t wslot = (size_t)blockIdx.x * kWarpsPerCta + warp;
     constexpr int RS = NSLOT + 2 * kHalo;
-    float2 *frow = p.frows + wslot * p.frow_stride + 3 * RS; // row 0 (3 zero rows below)
+    float2 *frow = p.frows + wslot * p.frow_stride + kRowShift * RS; // row 0 (kRowShift zero rows below)
     int32_t *kf = p.kf + wslot * p.kf_stride + 3;
-    // rows -3..-1 (before the first anti-diagonal) read as zero, exponent 0
-    for (int k = lane; k < 3 * RS; k += 32) frow[k - 3 * RS] = make_float2(0.f, 0.f);
+    f2 *ring = reinterpret_cast<f2 *>(dyn_smem) + (size_t)warp * ring_floats2<C>();
+    const unsigned bars = (unsigned)__cvta_generic_to_shared(&sh.bar[warp][0]);
+    unsigned phase = 0u;
+    // rows -kRowShift..-1 (before the first anti-diagonal) read as zero, exponent 0
+    for (int k = lane; k < kRowShift * RS; k += 32) frow[k - kRowShift * RS] = make_float2(0.f, 0.f);
     if (lane < 3) kf[lane - 3] = 0;
+    if (lane < 4) mbar_init(bars + 8u * lane, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
     for (;;) {
         int pi = 0;
@@ -551,18 +649,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) modtable_kernel(KParams p) 
         if (pi >= p.n_pairs) break;
         const DevPair P = p.pairs[pi];
         const PairCtx pc = make_pair_ctx(p, P, sh);
-        const Coef a = load_coef(sh.trans[P.model]);
+        const Coef a = load_coef(sh.trans[P.model], sh.cpair[P.model]);
+        for (int k = lane; k < kEvWords; k += 32) sh.evw[warp][k] = 0u;
+        __syncwarp();
         int Ktot;
-        int ev_n;
-        forward_pass<C, 1>(pc, a, frow, kf, sh.ftot[warp], Ktot, sh.ev_s[warp], ev_n);
+        forward_pass<C, 1>(pc, a, frow, kf, sh.ftot[warp], Ktot, sh.evw[warp]);
         // rows / exponents just past the last anti-diagonal read as zero / Ktot
-        for (int k = lane; k < 3 * RS; k += 32) frow[(size_t)pc.nd * RS + k] = make_float2(0.f, 0.f);
+        for (int k = lane; k < kRowsAbove * RS; k += 32) frow[(size_t)pc.nd * RS + k] = make_float2(0.f, 0.f);
         if (lane < 3) kf[pc.nd + lane] = Ktot;
         __syncwarp();
         const float fin = sh.ftot[warp][0];
         if (lane == 0)
             p.out_lk[pi] = fin > 0.f ? log((double)fin) - (double)Ktot * 0.6931471805599453 : -INFINITY;
-        backward_pass<C, ROWS>(pc, a, frow, kf, sh.stage[warp], sh.ftot[warp], p.out_delta + P.tab_off, sh.ev_s[warp], ev_n);
+        backward_pass<C, ROWS>(pc, a, frow, kf, sh.stage[warp], sh.ftot[warp], p.out_delta + P.tab_off, sh.evw[warp], ring,
+                               bars, phase);
         __syncwarp();
     }
 }
@@ -579,10 +679,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) likelihood_kernel(KParams p
         if (pi >= p.n_pairs) break;
         const DevPair P = p.pairs[pi];
         const PairCtx pc = make_pair_ctx(p, P, sh);
-        const Coef a = load_coef(sh.trans[P.model]);
+        const Coef a = load_coef(sh.trans[P.model], sh.cpair[P.model]);
         int Ktot;
-        int ev_n;
-        forward_pass<C, 0>(pc, a, nullptr, nullptr, sh.ftot[warp], Ktot, nullptr, ev_n);
+        forward_pass<C, 0>(pc, a, nullptr, nullptr, sh.ftot[warp], Ktot, nullptr);
         const float fin = sh.ftot[warp][0];
         if (lane == 0)
             p.out_lk[pi] = fin > 0.f ? log((double)fin) - (double)Ktot * 0.6931471805599453 : -INFINITY;
@@ -654,7 +753,7 @@ __device__ __forceinline__ void fit_backward(const PairCtx &pc, const Coef &a, c
             float m_ = mm * gM + mi * gI + md * gD;
             float i_ = im * gM + ii * gI + id * gD;
             float d_ = dm * gM + di * gI + dd * gD;
-            if (s == nd - 1) { m_ = boff; i_ = boff; d_ = boff; }
+            if (s == nd - 1) { const float t = (j[c] == Lt) ? boff : 0.f; m_ = t; i_ = t; d_ = t; } // B(Lr, Lt) only
             if (!valid) { m_ = 0.f; i_ = 0.f; d_ = 0.f; }
             const float4 F = rp[c]; // zero outside the band
             T[0] = fmaf(F.x, gM, T[0]); T[1] = fmaf(F.x, gI, T[1]); T[2] = fmaf(F.x, gD, T[2]);
@@ -713,15 +812,16 @@ __device__ __forceinline__ void fit_backward(const PairCtx &pc, const Coef &a, c
     __syncwarp();
 }
 
-static_assert(kStageCols * kStageStride >= kFitBins * 32, "the staging ring doubles as the match-emission bins");
 struct FitSmem {
+    float binM[kWarpsPerCta][kFitBins * 32];
     float binI[kWarpsPerCta][kFitBins * 32];
 };
 
 template <int C>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) fit_kernel(KParams p, double *acc90) {
     __shared__ SmemLayout sh;
-    __shared__ FitSmem fs;
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    FitSmem &fs = *reinterpret_cast<FitSmem *>(dyn_smem);
     fill_tables(sh, p.models);
     constexpr int NSLOT = 32 * C;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -737,15 +837,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) fit_kernel(KParams p, doubl
         if (pi >= p.n_pairs) break;
         const DevPair P = p.pairs[pi];
         const PairCtx pc = make_pair_ctx(p, P, sh);
-        const Coef a = load_coef(sh.trans[P.model]);
-        int Ktot, ev_n;
-        forward_pass<C, 2>(pc, a, frow, kf, sh.ftot[warp], Ktot, nullptr, ev_n);
+        const Coef a = load_coef(sh.trans[P.model], sh.cpair[P.model]);
+        int Ktot;
+        forward_pass<C, 2>(pc, a, frow, kf, sh.ftot[warp], Ktot, nullptr);
         __syncwarp();
         const float fin = sh.ftot[warp][0];
         if (lane == 0)
             p.out_lk[pi] = fin > 0.f ? log((double)fin) - (double)Ktot * 0.6931471805599453 : -INFINITY;
         fit_backward<C>(pc, a, sh.trans[P.model], reinterpret_cast<const float4 *>(frow), kf, sh.ftot[warp],
-                        sh.stage[warp], fs.binI[warp], acc90 + 45 * P.model);
+                        fs.binM[warp], fs.binI[warp], acc90 + 45 * P.model);
         __syncwarp();
     }
 }
@@ -758,11 +858,17 @@ int cols_per_lane_for_radius(int radius) {
     return 0;
 }
 
+template <int C, int ROWS>
+static cudaError_t launch_modtable_cr(const KParams &p, int grid, cudaStream_t st) {
+    const int dyn = kWarpsPerCta * ring_floats2<C>() * (int)sizeof(f2);
+    cudaError_t e = cudaFuncSetAttribute(modtable_kernel<C, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    if (e != cudaSuccess) return e;
+    modtable_kernel<C, ROWS><<<grid, kWarpsPerCta * 32, dyn, st>>>(p);
+    return cudaGetLastError();
+}
 template <int C>
 static cudaError_t launch_modtable_c(const KParams &p, int rows, int grid, cudaStream_t st) {
-    if (rows == 14) modtable_kernel<C, 14><<<grid, kWarpsPerCta * 32, 0, st>>>(p);
-    else modtable_kernel<C, 9><<<grid, kWarpsPerCta * 32, 0, st>>>(p);
-    return cudaGetLastError();
+    return rows == 14 ? launch_modtable_cr<C, 14>(p, grid, st) : launch_modtable_cr<C, 9>(p, grid, st);
 }
 
 cudaError_t launch_modtable(const KParams &p, int C, int grid, cudaStream_t st) {
@@ -783,16 +889,27 @@ cudaError_t launch_likelihood(const KParams &p, int C, int grid, cudaStream_t st
 }
 
 cudaError_t launch_fit(const KParams &p, int C, int grid, double *acc90, cudaStream_t st) {
+    const int dyn = (int)sizeof(FitSmem);
+    cudaError_t e = cudaSuccess;
     switch (C) {
-    case 2: fit_kernel<2><<<grid, kWarpsPerCta * 32, 0, st>>>(p, acc90); break;
-    case 4: fit_kernel<4><<<grid, kWarpsPerCta * 32, 0, st>>>(p, acc90); break;
+    case 2:
+        e = cudaFuncSetAttribute(fit_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+        if (e == cudaSuccess) fit_kernel<2><<<grid, kWarpsPerCta * 32, dyn, st>>>(p, acc90);
+        break;
+    case 4:
+        e = cudaFuncSetAttribute(fit_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+        if (e == cudaSuccess) fit_kernel<4><<<grid, kWarpsPerCta * 32, dyn, st>>>(p, acc90);
+        break;
     default: return cudaErrorInvalidValue;
     }
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 
 int warps_per_cta() { return kWarpsPerCta; }
 int frow_slots_per_row(int C) { return 32 * C + 2 * kHalo; }
+int frow_extra_rows() { return kRowShift + kRowsAbove; }
+int modtable_ctas_per_sm(int C) { return C == 2 ? 3 : 1; }
 
 // ---- FP32 peak micro-benchmark (roofline denominator) ---------------------------------------------------
 // 16 independent accumulators per thread so the 4-cycle FMA latency is covered at 8 warps per scheduler.
