@@ -13,8 +13,10 @@ against its chunk consensus by the banded pair-HMM forward/backward, the 14-row 
 value   GCUPS with the batch already resident in HBM (kernels only).  One cell update = all three states of
         one in-band DP cell in one direction; a modification-table job is 2*C cell updates (SURVEY.md 8d);
         checkpoint / reduction work is not credited.
-e2e     the same metric through the C ABI with HOST buffers: encode + H2D of the step's inputs, kernels, D2H of
-        the likelihoods and the per-column statistics, all inside the timed region.
+e2e     the same metric through the C ABI with HOST buffers (the call sequence of INTEGRATION.md): jtk_batch_create
+        (encode on the host threads + H2D of the step's inputs), jtk_batch_modtable (14 rows),
+        jtk_batch_search_variants (filter_profiles on the device, gather of the candidate columns, greedy pick on the
+        host, D2H of candidates and values), jtk_batch_fetch_lk, jtk_batch_destroy -- all inside the timed region.
 Chunks are independent: rank r processes its own 80 chunks (weak scaling), no collective on the data path.
 """
 from __future__ import annotations
@@ -38,6 +40,7 @@ POS_THR = 1e-5
 # Gains fixture (expected log-lik gain per (DiffType, homopolymer length)): estimate_gain_default output is an
 # input fixture here; rows Subst, Del, Ins; MIN_REQ_FRACTION 0.5 (pseudo_mcmc.rs:140)
 GAINS_EXPECTED = np.array([[4.0, 4.0, 4.0], [3.0, 2.0, 1.5], [3.0, 2.0, 1.5]], dtype=np.float32)
+GAINS_PROB = np.array([[0.02, 0.02, 0.02], [0.05, 0.08, 0.1], [0.05, 0.08, 0.1]], dtype=np.float64)
 
 
 def make_workload(rank: int, n_chunks: int, n_reads: int, length: int):
@@ -242,14 +245,16 @@ def main():
     ctx.kernel_times()
 
     # ---- end-to-end leg (host buffers in, statistics out) ---------------------------------------
+    cov = args.reads / 2.0
+
     def step_e2e():
         b = _lib.Batch(ctx, templates, reads, ops, strands, tidx, RADIUS, packed=packed)
         b.modtable(fwd, rev, 14)
-        st = b.colstats(min_req, POS_THR, fetch=True)
+        n_probes, probe_pos, variants = b.search_variants(GAINS_EXPECTED.astype(np.float64), GAINS_PROB, 2, cov)
         lk = b.lk()
         h2d = b.h2d_bytes
         b.close()
-        return h2d, st.nbytes + lk.nbytes
+        return h2d, n_probes.nbytes + probe_pos.nbytes + variants.nbytes + lk.nbytes
 
     for _ in range(2):
         h2d_bytes, d2h_bytes = step_e2e()

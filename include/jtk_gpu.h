@@ -51,6 +51,22 @@ typedef struct {
 
 typedef struct jtk_ctx jtk_ctx;
 
+/* likelihood_gains::Gains (likelihood_gains.rs:56-62): expected gain and null probability per (DiffType, homopolymer
+ * length 1..homop_len); rows in DiffType order Subst, Del, Ins (likelihood_gains.rs:195-199). */
+typedef struct {
+    int homop_len;
+    const double *gain; /* 3 * homop_len */
+    const double *prob; /* 3 * homop_len */
+} jtk_gains;
+/* pseudo_mcmc::ClusteringConfig (pseudo_mcmc.rs:18-43) */
+typedef struct {
+    int band_width;
+    int copy_num;
+    double coverage;       /* haploid coverage */
+    double local_coverage; /* per-cluster coverage */
+} jtk_clustering_config;
+
+
 /* ---- context ----------------------------------------------------------------------------------- */
 /* device < 0: use the current CUDA device.  workspace_bytes = 0: size scratch on demand. */
 int jtk_ctx_create(int device, size_t workspace_bytes, jtk_ctx **out);
@@ -155,6 +171,34 @@ int jtk_batch_colstats(jtk_batch *b, const float *min_req /* 3*H */, int H, floa
  * reads in batch order (filter_by, pseudo_mcmc.rs:70-75) */
 int jtk_batch_gather(jtk_batch *b, int tmpl, const float *min_req, int H, const uint32_t *cols, int D, double *out);
 
+/*
+ * filter_profiles (pseudo_mcmc.rs:426-474) for every chunk of the batch on the device: compress_small_gains, column_sum,
+ * position mask, row filter, is_in_short_homopolymer, has_small_pvalue, is_explainable_by_strandedness and the Poisson
+ * prior; only the surviving candidate columns cross PCIe.  copy_num[t] is the chunk's copy number (cluster_num of
+ * filter_profiles), coverage the haploid coverage (ClusteringConfig, pseudo_mcmc.rs:18-43).  Candidates are returned
+ * sorted by (tmpl, pos); *out_n receives their number (if it exceeds cap the call fails and *out_n says how many).
+ */
+typedef struct {
+    uint32_t tmpl;  /* chunk index in the batch */
+    uint32_t pos;   /* flat position j*NUM_ROW + row */
+    uint32_t count; /* reads with a gain > POS_THR in this column */
+    uint32_t pad_;
+    double sum;     /* their summed gain (column_sum) */
+    double lk;      /* sum + max_k poisson_lk(count, coverage*k): the score pick_filtered_profiles ranks by */
+} jtk_candidate;
+int jtk_batch_candidates(jtk_batch *b, const jtk_gains *gains, const int32_t *copy_num /* n_tmpl */, double coverage,
+                         jtk_candidate *out, int cap, int *out_n);
+/*
+ * pseudo_mcmc::search_variants (pseudo_mcmc.rs:109-138) for every chunk of the batch: candidates on the device, their
+ * values gathered on the device, greedy pick_filtered_profiles (:516-575) on the host.
+ * out_n_probes[t] selected columns of chunk t, their flat positions at out_probe_pos[t*probe_cap ..], and for every pair p
+ * (batch order) the compressed profile values at out_variants[p*probe_cap ..] (filter_by, :70-75); probe_cap >=
+ * 3*max(copy_num, 2).  Chunks with copy_num < 2 are skipped (pseudo_mcmc.rs:86-88).
+ */
+int jtk_batch_search_variants(jtk_batch *b, const jtk_gains *gains, const int32_t *copy_num, double coverage, int probe_cap,
+                              uint32_t *out_n_probes /* n_tmpl */, uint32_t *out_probe_pos /* n_tmpl*probe_cap */,
+                              double *out_variants /* n_pairs*probe_cap */);
+
 /* ---- consensus polishing (K3) ------------------------------------------------------------------------- */
 /* kiley::hmm::HMMPolishConfig::new(radius, take_num, ignore_edge)
  *   (local_clustering/mod.rs:105,154; model_tune.rs:142; consensus/mod.rs:476) */
@@ -203,21 +247,6 @@ int jtk_hmm_fit_batch(jtk_ctx *ctx, jtk_hmm_params *fwd, jtk_hmm_params *rev, in
                       const uint8_t *strand, const uint32_t *tmpl_idx, int radius);
 
 /* ---- host side of local_clustering: everything in pseudo_mcmc.rs that is not the pair HMM ---------------- */
-/* likelihood_gains::Gains (likelihood_gains.rs:56-62): expected gain and null probability per (DiffType, homopolymer
- * length 1..homop_len); rows in DiffType order Subst, Del, Ins (likelihood_gains.rs:195-199). */
-typedef struct {
-    int homop_len;
-    const double *gain; /* 3 * homop_len */
-    const double *prob; /* 3 * homop_len */
-} jtk_gains;
-/* pseudo_mcmc::ClusteringConfig (pseudo_mcmc.rs:18-43) */
-typedef struct {
-    int band_width;
-    int copy_num;
-    double coverage;       /* haploid coverage */
-    double local_coverage; /* per-cluster coverage */
-} jtk_clustering_config;
-
 /*
  * pseudo_mcmc::clustering (pseudo_mcmc.rs:77-107) given the per-read profiles (table - lk) of one chunk:
  * compress_small_gains, filter_profiles, pick_filtered_profiles, cluster_filtered_variants, re-assignment and
@@ -236,6 +265,12 @@ int jtk_lc_clustering_batch(jtk_batch *b, int tmpl_index, const uint8_t *tmpl, i
                             const jtk_gains *gains, const jtk_clustering_config *cfg, uint64_t seed, uint64_t *out_asn,
                             double *out_post, int post_stride, double *out_score, int *out_k, uint32_t *out_probe_pos,
                             int probe_cap, int *out_n_probes);
+/* pseudo_mcmc::clustering (pseudo_mcmc.rs:77-107) from the output of search_variants: variants[r*stride + d] is the value
+ * of read r at the selected position probe_pos[d] (one chunk's rows of jtk_batch_search_variants). */
+int jtk_lc_clustering_variants(const double *variants, int n_reads, int n_probes, int stride, const uint32_t *probe_pos,
+                               const uint8_t *tmpl, int Lt, const jtk_gains *gains, const jtk_clustering_config *cfg,
+                               uint64_t seed, uint64_t *out_asn, double *out_post, int post_stride, double *out_score,
+                               int *out_k);
 const char *jtk_lc_last_error(void);
 /* hooks for the reference's unit tests on these files (pseudo_mcmc.rs:876-904) and the generator */
 double jtk_lc_cosine_similarity(const double *profiles, int n, int ncol, int i, int j);

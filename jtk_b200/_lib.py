@@ -24,11 +24,20 @@ EXPORTS = [
     "jtk_hmm_likelihood_batch", "jtk_band_cell_count", "jtk_batch_create", "jtk_batch_destroy",
     "jtk_batch_cell_updates", "jtk_batch_h2d_bytes", "jtk_batch_modtable", "jtk_batch_sync", "jtk_batch_fetch_lk",
     "jtk_batch_fetch_profile", "jtk_batch_colstats", "jtk_batch_gather", "jtk_ctx_timer_start", "jtk_ctx_timer_stop",
-    "jtk_ctx_kernel_times", "jtk_ctx_measure_fp32_peak",
+    "jtk_ctx_kernel_times", "jtk_ctx_measure_fp32_peak", "jtk_batch_candidates", "jtk_batch_search_variants",
+    "jtk_lc_clustering_variants", "jtk_batch_colsums", "jtk_batch_expected_counts", "jtk_hmm_fit_batch",
+    "jtk_polish_until_converge_batch", "jtk_lc_clustering_profiles", "jtk_lc_clustering_batch", "jtk_lc_last_error",
 ]
 
 COLSTAT_DTYPE = np.dtype([("sum", "<f8"), ("count", "<i4"), ("sc", "<u2", (4,)), ("pad", "<i4")])
 assert COLSTAT_DTYPE.itemsize == 24
+CANDIDATE_DTYPE = np.dtype([("tmpl", "<u4"), ("pos", "<u4"), ("count", "<u4"), ("pad", "<u4"), ("sum", "<f8"), ("lk", "<f8")])
+assert CANDIDATE_DTYPE.itemsize == 32
+
+
+class CGains(C.Structure):
+    """jtk_gains (likelihood_gains::Gains)."""
+    _fields_ = [("homop_len", C.c_int), ("gain", C.c_void_p), ("prob", C.c_void_p)]
 
 
 class JtkError(RuntimeError):
@@ -86,6 +95,8 @@ def lib() -> C.CDLL:
     L.jtk_batch_fetch_profile.argtypes = [C.c_void_p, C.c_int, vp]
     L.jtk_batch_colstats.argtypes = [C.c_void_p, vp, C.c_int, C.c_float, vp, u64p]
     L.jtk_batch_gather.argtypes = [C.c_void_p, C.c_int, vp, C.c_int, u32p, C.c_int, vp]
+    L.jtk_batch_candidates.argtypes = [C.c_void_p, C.POINTER(CGains), vp, C.c_double, vp, C.c_int, C.POINTER(C.c_int)]
+    L.jtk_batch_search_variants.argtypes = [C.c_void_p, C.POINTER(CGains), vp, C.c_double, C.c_int, vp, vp, vp]
     L.jtk_ctx_timer_start.argtypes = [C.c_void_p]
     L.jtk_ctx_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.jtk_ctx_kernel_times.argtypes = [C.c_void_p, vp, C.c_int]
@@ -276,6 +287,34 @@ class Batch:
         self.ctx._check(lib().jtk_batch_colstats(self._h, _ptr(mr), mr.shape[1], pos_thr, _ptr(out),
                                                  _ptr(self.stat_off)))
         return out
+
+    def _gains_c(self, gain, prob):
+        self._g_gain = np.ascontiguousarray(gain, dtype=np.float64)
+        self._g_prob = np.ascontiguousarray(prob, dtype=np.float64)
+        assert self._g_gain.shape == self._g_prob.shape and self._g_gain.shape[0] == 3
+        return CGains(self._g_gain.shape[1], self._g_gain.ctypes.data, self._g_prob.ctypes.data)
+
+    def candidates(self, gain, prob, copy_num, coverage: float, cap: int = 0) -> np.ndarray:
+        """jtk_batch_candidates: filter_profiles on the device; structured array (CANDIDATE_DTYPE) sorted by (tmpl, pos)."""
+        g = self._gains_c(gain, prob)
+        cn = np.ascontiguousarray(np.broadcast_to(copy_num, (self.n_tmpl,)), dtype=np.int32)
+        cap = cap or 256 * self.n_tmpl + 4096
+        out = np.zeros(cap, dtype=CANDIDATE_DTYPE)
+        n = C.c_int()
+        self.ctx._check(lib().jtk_batch_candidates(self._h, C.byref(g), _ptr(cn), coverage, _ptr(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def search_variants(self, gain, prob, copy_num, coverage: float, probe_cap: int = 0):
+        """jtk_batch_search_variants: (n_probes uint32[n_tmpl], probe_pos uint32[n_tmpl, cap], variants float64[n_pairs, cap])."""
+        g = self._gains_c(gain, prob)
+        cn = np.ascontiguousarray(np.broadcast_to(copy_num, (self.n_tmpl,)), dtype=np.int32)
+        cap = probe_cap or 3 * max(2, int(cn.max()) if len(cn) else 2)
+        n_probes = np.zeros(self.n_tmpl, dtype=np.uint32)
+        probe_pos = np.zeros((self.n_tmpl, cap), dtype=np.uint32)
+        variants = np.zeros((self.n_pairs, cap), dtype=np.float64)
+        self.ctx._check(lib().jtk_batch_search_variants(self._h, C.byref(g), _ptr(cn), coverage, cap, _ptr(n_probes),
+                                                        _ptr(probe_pos), _ptr(variants)))
+        return n_probes, probe_pos, variants
 
     def gather(self, tmpl: int, min_req: np.ndarray, cols) -> np.ndarray:
         mr = np.ascontiguousarray(min_req, dtype=np.float32)

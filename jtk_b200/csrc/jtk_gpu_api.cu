@@ -2,12 +2,17 @@
 // entry point needs a CUDA device and fails with JTK_ECUDA otherwise.
 #include "../../include/jtk_gpu.h"
 #include "phmm_dev.cuh"
+#include "lc_host.h"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
+#include <mutex>
+#include <cstdlib>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace jtk {
@@ -28,19 +33,63 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// Device blocks released by a batch are kept by the context and handed to the next batch: a chunk pipeline creates and
+// destroys batches of similar size all the time, and cudaMalloc / cudaFree (which synchronises) would dominate.
+// All work of a context runs on one stream, so reuse needs no extra ordering.
+struct DevPool {
+    struct Block { void *p; size_t bytes; };
+    std::vector<Block> free_blocks;
+    size_t cached = 0;
+    static constexpr size_t kMaxCached = (size_t)48 << 30;
+    void *take(size_t bytes, size_t &got) {
+        size_t best = free_blocks.size();
+        for (size_t k = 0; k < free_blocks.size(); k++)
+            if (free_blocks[k].bytes >= bytes && free_blocks[k].bytes <= 2 * bytes + (1 << 20) &&
+                (best == free_blocks.size() || free_blocks[k].bytes < free_blocks[best].bytes)) best = k;
+        if (best == free_blocks.size()) return nullptr;
+        Block blk = free_blocks[best];
+        free_blocks.erase(free_blocks.begin() + (ptrdiff_t)best);
+        cached -= blk.bytes;
+        got = blk.bytes;
+        return blk.p;
+    }
+    void give(void *p, size_t bytes) {
+        if (cached + bytes > kMaxCached) { cudaFree(p); return; }
+        free_blocks.push_back({ p, bytes });
+        cached += bytes;
+    }
+    void clear() {
+        for (auto &b : free_blocks) cudaFree(b.p);
+        free_blocks.clear();
+        cached = 0;
+    }
+};
+
 template <typename T> struct DevBuf {
     T *p = nullptr;
     size_t cap = 0; // elements
+    DevPool *pool = nullptr;
     cudaError_t reserve(size_t n) {
         if (n <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        size_t want = n + n / 8 + 64;
+        release();
+        const size_t want = n + n / 8 + 64;
+        if (pool) {
+            size_t got = 0;
+            if (void *q = pool->take(want * sizeof(T), got)) { p = (T *)q; cap = got / sizeof(T); return cudaSuccess; }
+        }
         cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
-        if (e == cudaSuccess) cap = want;
+        if (e != cudaSuccess && pool && !pool->free_blocks.empty()) { // give the cache back to the driver and retry
+            cudaGetLastError();
+            pool->clear();
+            e = cudaMalloc((void **)&p, want * sizeof(T));
+        }
+        if (e == cudaSuccess) cap = want; else p = nullptr;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() {
+        if (p) { if (pool) pool->give(p, cap * sizeof(T)); else cudaFree(p); }
+        p = nullptr; cap = 0;
+    }
 };
 
 template <typename T> struct PinBuf {
@@ -134,6 +183,8 @@ struct jtk_ctx {
     uint64_t launches = 0;
     float last_ms = 0.f;
     bool timing_pending = false;
+    DevPool pool;             // device blocks recycled between batches
+    int host_threads = 1;     // threads of the host-side encoders (JTK_HOST_THREADS, default: all cores, at most 32)
     // device buffers
     DevBuf<float> d_models;
     DevBuf<float2> d_frows;   // per-warp forward rows (scratch shared by all batches of this ctx)
@@ -142,6 +193,9 @@ struct jtk_ctx {
     DevBuf<float> d_minreq;
     DevBuf<uint32_t> d_cols;
     DevBuf<double> d_gather;
+    DevBuf<double> d_tabs;        // p-value / prior / expected-gain tables of the candidate kernel
+    DevBuf<uint32_t> d_tab_off;
+    DevBuf<jtk_candidate> d_cand;
     // pinned host staging
     PinBuf<DevPair> h_pairs;
     PinBuf<uint8_t> h_codes;
@@ -149,6 +203,8 @@ struct jtk_ctx {
     PinBuf<float> h_delta;
     PinBuf<double> h_lk;
     PinBuf<uint8_t> h_homop;
+    PinBuf<jtk_candidate> h_cand;
+    PinBuf<double> h_gather;
     // host scratch
     std::vector<uint32_t> tmpl_code_off;
     std::vector<uint8_t> tmp_ops;
@@ -189,6 +245,11 @@ int jtk_ctx_create(int device, size_t workspace_bytes, jtk_ctx **out) {
     jtk_ctx *ctx = new jtk_ctx();
     ctx->device = device;
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    {
+        int nt = (int)std::thread::hardware_concurrency();
+        if (const char *env = std::getenv("JTK_HOST_THREADS")) nt = std::atoi(env);
+        ctx->host_threads = std::max(1, std::min(nt, 32));
+    }
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->tm0)) != cudaSuccess || (e = cudaEventCreate(&ctx->tm1)) != cudaSuccess) {
@@ -205,8 +266,10 @@ void jtk_ctx_destroy(jtk_ctx *ctx) {
     cudaSetDevice(ctx->device);
     ctx->d_models.release(); ctx->d_frows.release(); ctx->d_kf.release(); ctx->d_counter.release();
     ctx->d_minreq.release(); ctx->d_cols.release(); ctx->d_gather.release();
+    ctx->d_tabs.release(); ctx->d_tab_off.release(); ctx->d_cand.release(); ctx->h_cand.release(); ctx->h_gather.release();
     ctx->h_pairs.release(); ctx->h_codes.release(); ctx->h_bits.release(); ctx->h_delta.release(); ctx->h_lk.release();
     ctx->h_homop.release();
+    ctx->pool.clear();
     for (int k = 0; k < jtk_ctx::kRing; k++) { if (ctx->ring0[k]) cudaEventDestroy(ctx->ring0[k]); if (ctx->ring1[k]) cudaEventDestroy(ctx->ring1[k]); }
     if (ctx->tm0) cudaEventDestroy(ctx->tm0);
     if (ctx->tm1) cudaEventDestroy(ctx->tm1);
@@ -263,9 +326,17 @@ struct jtk_batch {
     DevBuf<double> d_lk;
     DevBuf<uint32_t> d_tp_start, d_tp_ids, d_tmpl_len, d_homop_off;
     DevBuf<uint8_t> d_homop;
+    DevBuf<uint32_t> d_tmpl_code_off; // codes[tmpl_code_off[t] + j + 1] = code of t[j]
+    std::vector<uint32_t> tmpl_code_off;
     DevBuf<unsigned long long> d_stat_off;
     DevBuf<jtk_colstat> d_stats;
+    void attach(DevPool *pool) {
+        d_pairs.pool = pool; d_codes.pool = pool; d_bits.pool = pool; d_delta.pool = pool; d_lk.pool = pool;
+        d_tp_start.pool = pool; d_tp_ids.pool = pool; d_tmpl_len.pool = pool; d_homop_off.pool = pool; d_homop.pool = pool;
+        d_stat_off.pool = pool; d_stats.pool = pool; d_tmpl_code_off.pool = pool;
+    }
     void release() {
+        d_tmpl_code_off.release();
         d_pairs.release(); d_codes.release(); d_bits.release(); d_delta.release(); d_lk.release();
         d_tp_start.release(); d_tp_ids.release(); d_tmpl_len.release(); d_homop_off.release(); d_homop.release();
         d_stat_off.release(); d_stats.release();
@@ -274,7 +345,30 @@ struct jtk_batch {
 
 namespace {
 
+// Run fn(k) for k in [0, n) on the context's host threads (dynamic chunks of `grain` items).
+template <typename F> void parallel_for(int n_threads, int n, int grain, F fn) {
+    if (n <= 0) return;
+    const int nt = std::max(1, std::min(n_threads, (n + grain - 1) / grain));
+    if (nt == 1) { for (int k = 0; k < n; k++) fn(k); return; }
+    std::atomic<int> next(0);
+    auto worker = [&]() {
+        for (;;) {
+            const int k0 = next.fetch_add(grain);
+            if (k0 >= n) break;
+            const int k1 = std::min(n, k0 + grain);
+            for (int k = k0; k < k1; k++) fn(k);
+        }
+    };
+    std::vector<std::thread> th;
+    th.reserve((size_t)nt - 1);
+    for (int t = 1; t < nt; t++) th.emplace_back(worker);
+    worker();
+    for (auto &t : th) t.join();
+}
+
 // Encode templates / reads / guide paths into the device layout of phmm_dev.cuh (pinned staging of ctx).
+// Pass 1 lays out every array (sequential, O(pairs)); pass 2 encodes templates and pairs on the host threads: every
+// template / pair owns its own byte ranges.
 int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uint32_t *tmpl_off,
                const uint8_t *read_concat, const uint32_t *read_off, const uint8_t *ops_concat,
                const uint32_t *ops_off, const uint8_t *strand, const uint32_t *tmpl_idx, size_t &code_bytes,
@@ -283,26 +377,42 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
     size_t cb = 0, hb = 0;
     b->tmpl_len.resize((size_t)n_tmpl);
     b->homop_off.resize((size_t)n_tmpl + 1);
+    b->tmpl_code_off.resize((size_t)n_tmpl);
     for (int t = 0; t < n_tmpl; t++) {
         if (tmpl_off[t + 1] < tmpl_off[t]) return ctx->fail(JTK_EINVAL, "tmpl_off is not monotone");
         const size_t L = tmpl_off[t + 1] - tmpl_off[t];
         b->tmpl_len[t] = (uint32_t)L;
         b->homop_off[t] = (uint32_t)hb;
+        b->tmpl_code_off[t] = (uint32_t)(cb + kCodePad);
         cb += 2 * (size_t)kCodePad + ((L + 1 + 3) & ~(size_t)3);
         hb += L + 1;
         b->max_lt = std::max(b->max_lt, (int)L);
     }
     b->homop_off[n_tmpl] = (uint32_t)hb;
     size_t bwords = 0;
+    uint64_t tab = 0;
     std::vector<uint32_t> cnt((size_t)n_tmpl + 1, 0);
+    b->pairs.resize((size_t)n_pairs);
+    b->max_nd = 0;
     for (int p = 0; p < n_pairs; p++) {
         if (read_off[p + 1] < read_off[p]) return ctx->fail(JTK_EINVAL, "read_off is not monotone");
         if (tmpl_idx[p] >= (uint32_t)n_tmpl) return ctx->fail(JTK_EINVAL, "tmpl_idx out of range");
+        if (ops_concat && ops_off[p + 1] < ops_off[p]) return ctx->fail(JTK_EINVAL, "ops_off is not monotone");
         const size_t Lr = read_off[p + 1] - read_off[p];
         const size_t Lt = b->tmpl_len[tmpl_idx[p]];
+        DevPair &dp = b->pairs[p];
+        dp.tb_off = b->tmpl_code_off[tmpl_idx[p]];
+        dp.rb_off = (uint32_t)(cb + kCodePad);
+        dp.bits_off = (uint32_t)bwords;
+        dp.Lt = (int32_t)Lt; dp.Lr = (int32_t)Lr;
+        dp.model = strand[p] ? 0 : 1;
+        dp.pad_ = 0;
+        dp.tab_off = tab;
+        tab += (uint64_t)(Lt + 1) * kNumRow;
         cb += 2 * (size_t)kCodePad + ((Lr + 2 + 3) & ~(size_t)3);
         bwords += (Lt + Lr + 1 + 31) / 32 + 1;
         cnt[tmpl_idx[p] + 1]++;
+        b->max_nd = std::max(b->max_nd, (int)(Lt + Lr + 1));
     }
     if (cb >= (size_t)0xffffffffu) return ctx->fail(JTK_EINVAL, "batch too large: split it (code bytes exceed 4 GiB)");
     b->tp_start.assign((size_t)n_tmpl + 1, 0);
@@ -319,17 +429,14 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
     uint8_t *codes = ctx->h_codes.p;
     uint32_t *bits = ctx->h_bits.p;
     uint8_t *homop = ctx->h_homop.p;
-    std::memset(codes, 4, cb);
-    std::memset(bits, 0, bwords * sizeof(uint32_t));
-    ctx->tmpl_code_off.resize((size_t)n_tmpl);
-    size_t pos = 0;
-    for (int t = 0; t < n_tmpl; t++) {
+    const int nt = ctx->host_threads;
+
+    parallel_for(nt, n_tmpl, 4, [&](int t) {
         const uint8_t *s = tmpl_concat + tmpl_off[t];
         const size_t L = b->tmpl_len[t];
-        pos += kCodePad;
-        ctx->tmpl_code_off[t] = (uint32_t)pos;
-        for (size_t j = 1; j <= L; j++) codes[pos + j] = base_code(s[j - 1]);
-        pos += ((L + 1 + 3) & ~(size_t)3) + kCodePad;
+        uint8_t *c = codes + b->tmpl_code_off[t]; // c[j] = code of t[j-1]; 4 = none
+        std::memset(c - kCodePad, 4, 2 * (size_t)kCodePad + ((L + 1 + 3) & ~(size_t)3));
+        for (size_t j = 1; j <= L; j++) c[j] = base_code(s[j - 1]);
         // homopolymer run length of every base (pseudo_mcmc.rs:195-211), 1 past the end (:153)
         uint8_t *h = homop + b->homop_off[t];
         size_t k = 0;
@@ -340,44 +447,52 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
             k = e;
         }
         h[L] = 1;
-    }
-    size_t bpos = 0;
-    uint64_t tab = 0, cells = 0;
-    b->max_nd = 0;
-    b->pairs.resize((size_t)n_pairs);
-    for (int p = 0; p < n_pairs; p++) {
+    });
+
+    std::atomic<int> first_bad(n_pairs); // smallest failing pair so far (the error reported is the first in batch order)
+    std::atomic<unsigned long long> cells_total(0);
+    std::mutex bad_mu;
+    std::string bad_text;
+    int bad_code = 0;
+    parallel_for(nt, n_pairs, 16, [&](int p) {
+        if (first_bad.load(std::memory_order_relaxed) < p) return;
+        const DevPair &dp = b->pairs[p];
         const uint32_t ti = tmpl_idx[p];
-        const int Lt = (int)b->tmpl_len[ti];
-        const int Lr = (int)(read_off[p + 1] - read_off[p]);
+        const int Lt = dp.Lt, Lr = dp.Lr;
         const uint8_t *q = read_concat + read_off[p];
         // read rows: byte = ctx<<5 | qc<<2 (the byte offset into the eI table; bits 2-4 index eM rows); 16 = no base
         const size_t rlen = ((size_t)Lr + 2 + 3) & ~(size_t)3;
-        std::memset(codes + pos, 16, 2 * (size_t)kCodePad + rlen);
-        pos += kCodePad;
-        DevPair &dp = b->pairs[p];
-        dp.tb_off = ctx->tmpl_code_off[ti];
-        dp.rb_off = (uint32_t)pos;
+        uint8_t *rc = codes + dp.rb_off;
+        std::memset(rc - kCodePad, 16, 2 * (size_t)kCodePad + rlen);
         for (int i = 1; i <= Lr; i++) {
             const uint8_t qc = base_code(q[i - 1]);
             const uint8_t cx = i >= 2 ? base_code(q[i - 2]) : 4;
-            codes[pos + i] = (uint8_t)((cx << 5) | (qc << 2));
+            rc[i] = (uint8_t)((cx << 5) | (qc << 2));
         }
-        pos += rlen + kCodePad;
         const uint8_t *ops;
         int n_ops;
+        static thread_local std::vector<uint8_t> tl_ops;
+        static thread_local std::vector<int> tl_D;
+        auto fail = [&](int code, const std::string &msg) {
+            std::lock_guard<std::mutex> lk(bad_mu);
+            if (p < first_bad.load()) { first_bad.store(p); bad_text = msg; bad_code = code; }
+        };
         if (ops_concat) {
-            if (ops_off[p + 1] < ops_off[p]) return ctx->fail(JTK_EINVAL, "ops_off is not monotone");
             ops = ops_concat + ops_off[p];
             n_ops = (int)(ops_off[p + 1] - ops_off[p]);
         } else {
             const uint8_t *t = tmpl_concat + tmpl_off[ti];
-            if (!edit_ops(t, Lt, q, Lr, radius, ctx->tmp_ops, ctx->tmp_D))
-                return ctx->fail(JTK_EINVAL, "bootstrap alignment: band cannot connect the corners (pair " + std::to_string(p) + ")");
-            ops = ctx->tmp_ops.data();
-            n_ops = (int)ctx->tmp_ops.size();
+            if (!edit_ops(t, Lt, q, Lr, radius, tl_ops, tl_D)) {
+                fail(JTK_EINVAL, "bootstrap alignment: band cannot connect the corners (pair " + std::to_string(p) + ")");
+                return;
+            }
+            ops = tl_ops.data();
+            n_ops = (int)tl_ops.size();
         }
         // guide path -> centre increments, and the in-band cell count on the way
-        uint32_t *bw = bits + bpos;
+        const size_t nwords = (size_t)(Lt + Lr + 1 + 31) / 32 + 1;
+        uint32_t *bw = bits + dp.bits_off;
+        std::memset(bw, 0, nwords * sizeof(uint32_t));
         int i = 0, j = 0, s = 0;
         auto width = [&](int cen, int d) -> uint64_t {
             const int lo = std::max(std::max(cen - radius, 0), d - Lt), hi = std::min(std::min(cen + radius, Lr), d);
@@ -398,26 +513,21 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
             } else if (op == JTK_OP_DEL) {
                 if (j >= Lt) { bad = true; break; }
                 j++; s += 1; c += width(i, s);
-            } else return ctx->fail(JTK_EINVAL, "invalid op code in pair " + std::to_string(p));
+            } else { fail(JTK_EINVAL, "invalid op code in pair " + std::to_string(p)); return; }
         }
-        if (bad || i != Lr || j != Lt)
-            return ctx->fail(JTK_EINVAL, "ops of pair " + std::to_string(p) + " do not span (template, read): consumed (" +
-                                             std::to_string(j) + "," + std::to_string(i) + ") of (" + std::to_string(Lt) + "," +
-                                             std::to_string(Lr) + ")");
-        cells += 2 * c;
-        dp.bits_off = (uint32_t)bpos;
-        bpos += (size_t)(Lt + Lr + 1 + 31) / 32 + 1;
-        dp.Lt = Lt; dp.Lr = Lr;
-        dp.model = strand[p] ? 0 : 1;
-        dp.pad_ = 0;
-        dp.tab_off = tab;
-        tab += (uint64_t)(Lt + 1) * kNumRow;
-        b->max_nd = std::max(b->max_nd, Lt + Lr + 1);
-    }
+        if (bad || i != Lr || j != Lt) {
+            fail(JTK_EINVAL, "ops of pair " + std::to_string(p) + " do not span (template, read): consumed (" + std::to_string(j) +
+                                 "," + std::to_string(i) + ") of (" + std::to_string(Lt) + "," + std::to_string(Lr) + ")");
+            return;
+        }
+        cells_total.fetch_add(2 * c, std::memory_order_relaxed);
+    });
+    if (first_bad.load() < n_pairs) return ctx->fail(bad_code ? bad_code : JTK_EINVAL, bad_text);
     std::memcpy(ctx->h_pairs.p, b->pairs.data(), sizeof(DevPair) * (size_t)n_pairs);
+    ctx->tmpl_code_off = b->tmpl_code_off;
     b->table_floats = tab;
-    b->cell_updates = cells;
-    b->h2d_bytes = cb + bwords * sizeof(uint32_t) + hb + sizeof(DevPair) * (size_t)n_pairs + sizeof(uint32_t) * (3 * (size_t)n_tmpl + 3 + (size_t)n_pairs);
+    b->cell_updates = cells_total.load();
+    b->h2d_bytes = cb + bwords * sizeof(uint32_t) + hb + sizeof(DevPair) * (size_t)n_pairs + sizeof(uint32_t) * (4 * (size_t)n_tmpl + 3 + (size_t)n_pairs);
     code_bytes = cb; bit_words = bwords; homop_bytes = hb;
     return JTK_OK;
 }
@@ -437,6 +547,7 @@ int batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_conc
     CU(cudaSetDevice(ctx->device), "cudaSetDevice");
     jtk_batch *b = new jtk_batch();
     b->ctx = ctx; b->n_pairs = n_pairs; b->n_tmpl = n_tmpl; b->radius = radius; b->C = C;
+    b->attach(&ctx->pool);
     if (n_pairs == 0) { *out = b; return JTK_OK; }
     size_t code_bytes = 0, bit_words = 0, homop_bytes = 0;
     int rc = pack_batch(ctx, b, tmpl_concat, tmpl_off, read_concat, read_off, ops_concat, ops_off, strand, tmpl_idx,
@@ -454,6 +565,7 @@ int batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_conc
     CB(b->d_tmpl_len.reserve(b->tmpl_len.size()), "cudaMalloc tmpl_len");
     CB(b->d_homop_off.reserve(b->homop_off.size()), "cudaMalloc homop_off");
     CB(b->d_homop.reserve(homop_bytes), "cudaMalloc homop");
+    CB(b->d_tmpl_code_off.reserve(b->tmpl_code_off.size()), "cudaMalloc tmpl_code_off");
     CB(cudaMemcpyAsync(b->d_pairs.p, ctx->h_pairs.p, sizeof(DevPair) * (size_t)n_pairs, cudaMemcpyHostToDevice, st), "H2D pairs");
     CB(cudaMemcpyAsync(b->d_codes.p, ctx->h_codes.p, code_bytes, cudaMemcpyHostToDevice, st), "H2D codes");
     CB(cudaMemcpyAsync(b->d_bits.p, ctx->h_bits.p, bit_words * sizeof(uint32_t), cudaMemcpyHostToDevice, st), "H2D bits");
@@ -462,6 +574,7 @@ int batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_conc
     CB(cudaMemcpyAsync(b->d_tp_ids.p, b->tp_ids.data(), sizeof(uint32_t) * b->tp_ids.size(), cudaMemcpyHostToDevice, st), "H2D csr");
     CB(cudaMemcpyAsync(b->d_tmpl_len.p, b->tmpl_len.data(), sizeof(uint32_t) * b->tmpl_len.size(), cudaMemcpyHostToDevice, st), "H2D tmpl_len");
     CB(cudaMemcpyAsync(b->d_homop_off.p, b->homop_off.data(), sizeof(uint32_t) * b->homop_off.size(), cudaMemcpyHostToDevice, st), "H2D homop_off");
+    CB(cudaMemcpyAsync(b->d_tmpl_code_off.p, b->tmpl_code_off.data(), sizeof(uint32_t) * b->tmpl_code_off.size(), cudaMemcpyHostToDevice, st), "H2D tmpl_code_off");
     CB(cudaStreamSynchronize(st), "upload");
 #undef CB
     *out = b;
@@ -575,6 +688,113 @@ __global__ void gather_kernel(const float *__restrict__ delta, const DevPair *__
     const float thr = min_req_of(min_req, H, e % kNumRow, homop[e / kNumRow]);
     if (fabsf(x) < thr) x = 0.f;
     out[idx] = (double)x;
+}
+
+
+// --- filter_profiles on the device (pseudo_mcmc.rs:426-474): per-column statistics + every per-column test -----------
+// One thread per table entry: compress_small_gains + column_sum + strand/sign counts over the reads of the chunk (the
+// loop of colstats_kernel), then mask / row filter (:443-447), is_in_short_homopolymer (:497-514), has_small_pvalue
+// (:476-495), is_explainable_by_strandedness (:314-339) and the Poisson prior (:457-465).  Survivors are appended to one
+// global list.  The p-value and prior tables are computed by the host restatement and only looked up here, and the f64
+// arithmetic uses explicit round-to-nearest operations in the host's order, so both sides take the same decisions.
+struct CandArgs {
+    const float *delta; const DevPair *pairs;
+    const uint32_t *tp_start, *tp_ids, *tmpl_len;
+    const uint8_t *homop; const uint32_t *homop_off;
+    const uint8_t *codes; const uint32_t *tmpl_code_off;
+    const float *min_req;      // 3*H: Gains::expected * MIN_REQ_FRACTION (fp32, as colstats_kernel)
+    const double *expected;    // 3*H: Gains::expected
+    int H;
+    const double *pv; const uint32_t *pv_off;       // per template: 3*H*(n+1) p-values
+    const double *prior; const uint32_t *prior_off; // per template: n+1 Poisson priors
+    float pos_thr;
+    jtk_candidate *out; int cap; int *counter;
+};
+
+__global__ void candidates_kernel(CandArgs a) {
+    const int t = blockIdx.y;
+    const uint32_t Lt = a.tmpl_len[t];
+    const uint32_t n_ent = (Lt + 1) * kNumRow;
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_ent) return;
+    const uint32_t j = e / kNumRow, row = e % kNumRow;
+    const uint32_t temp_len = Lt + 1; // profile length in positions (pseudo_mcmc.rs:439)
+    if (!(7u <= j && j + 7u <= temp_len)) return;   // MASK_LENGTH (:443-446)
+    if (!(row < 8u || row == 8u + JTK_COPY_SIZE)) return; // (:447)
+    const uint8_t *hp = a.homop + a.homop_off[t];
+    const uint8_t *tc = a.codes + a.tmpl_code_off[t] + 1; // tc[x] = code of t[x]
+    const int type = row < 4 ? 0 : (row < 8 + JTK_COPY_SIZE ? 2 : 1); // Subst, Ins (incl. copy), Del
+    // is_in_short_homopolymer (:497-514); j < Lt holds for every unmasked position
+    if (type == 2) {
+        const uint32_t r = row - 4;
+        const uint32_t prev_len = hp[j - 1] + (r < 4u && tc[j - 1] == r ? 1u : 0u);
+        const uint32_t next_len = hp[j] + (r < 4u && tc[j] == r ? 1u : 0u);
+        if (!(prev_len <= 2u && next_len <= 2u)) return;
+    } else if (type == 1) {
+        if (!(hp[j] <= 2u)) return;
+    }
+    const int hl = min(max((int)hp[j], 1), a.H);
+    const float thr = a.min_req[type * a.H + hl - 1];
+    double sum = 0.0;
+    unsigned cnt = 0;
+    unsigned sc[4] = { 0, 0, 0, 0 };
+    const uint32_t k0 = a.tp_start[t], k1 = a.tp_start[t + 1];
+    for (uint32_t k = k0; k < k1; k++) {
+        const DevPair &p = a.pairs[a.tp_ids[k]];
+        float x = a.delta[p.tab_off + e];
+        if (fabsf(x) < thr) x = 0.f;
+        if (x > a.pos_thr) { sum = __dadd_rn(sum, (double)x); cnt++; }
+        if (fabsf(x) > 1e-4f) sc[(p.model == 0 ? 2 : 0) + (x > 0.f ? 1 : 0)]++;
+    }
+    const uint32_t n = k1 - k0;
+    // has_small_pvalue (:476-495)
+    const double pvalue = a.pv[a.pv_off[t] + (size_t)(type * a.H + hl - 1) * (n + 1) + cnt];
+    const double expt = __dmul_rn(a.expected[type * a.H + hl - 1], 0.8);
+    if (!(__dmul_rn((double)cnt, expt) < sum && __dmul_rn((double)temp_len, pvalue) < __ddiv_rn(0.05, (double)temp_len))) return;
+    // is_explainable_by_strandedness (:314-339): chi-square of the 2x2 (strand, sign) table
+    {
+        const unsigned strand_count[2] = { sc[0] + sc[1], sc[2] + sc[3] };
+        const unsigned sign_count[2] = { sc[0] + sc[2], sc[1] + sc[3] };
+        const unsigned tot = strand_count[0] + strand_count[1];
+        if (tot == 0) return;
+        double chisq = 0.0;
+#pragma unroll
+        for (int st = 0; st < 2; st++)
+#pragma unroll
+            for (int sg = 0; sg < 2; sg++) {
+                const double expected = __ddiv_rn((double)((unsigned long long)strand_count[st] * sign_count[sg]), (double)tot);
+                const double d = __dadd_rn((double)sc[st * 2 + sg], -expected);
+                chisq = __dadd_rn(chisq, __ddiv_rn(__dmul_rn(d, d), expected)); // 0/0 -> NaN, NaN < 10 is false (as in Rust)
+            }
+        if (!(chisq < 10.0)) return;
+    }
+    const double total_lk = __dadd_rn(a.prior[a.prior_off[t] + cnt], sum);
+    if (!(0.0 < total_lk)) return;
+    const int idx = atomicAdd(a.counter, 1);
+    if (idx < a.cap) {
+        jtk_candidate c;
+        c.tmpl = (uint32_t)t; c.pos = e; c.count = cnt; c.pad_ = 0; c.sum = sum; c.lk = total_lk;
+        a.out[idx] = c;
+    }
+}
+
+// compressed profile values of every candidate column: candidate m of template t, read k of t ->
+// out[c_base[m] + k * c_stride[m]]  (filter_by, pseudo_mcmc.rs:70-75, for all chunks at once)
+__global__ void gather_all_kernel(const float *__restrict__ delta, const DevPair *__restrict__ pairs,
+                                  const uint32_t *__restrict__ tp_start, const uint32_t *__restrict__ tp_ids,
+                                  const uint8_t *__restrict__ homop, const uint32_t *__restrict__ homop_off,
+                                  const float *__restrict__ min_req, int H, const uint32_t *__restrict__ c_tmpl,
+                                  const uint32_t *__restrict__ c_pos, const uint32_t *__restrict__ c_base,
+                                  const uint32_t *__restrict__ c_stride, double *__restrict__ out) {
+    const uint32_t m = blockIdx.x;
+    const uint32_t t = c_tmpl[m], e = c_pos[m];
+    const uint32_t first = tp_start[t], n = tp_start[t + 1] - first;
+    const float thr = min_req_of(min_req, H, e % kNumRow, homop[homop_off[t] + e / kNumRow]);
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+        float x = delta[pairs[tp_ids[first + k]].tab_off + e];
+        if (fabsf(x) < thr) x = 0.f;
+        out[c_base[m] + (size_t)k * c_stride[m]] = (double)x;
+    }
 }
 
 // plain per-column sums over the first `take` reads of each template (polish loop)
@@ -698,6 +918,209 @@ int jtk_batch_gather(jtk_batch *b, int tmpl, const float *min_req, int H, const 
     CU(cudaMemcpyAsync(out, ctx->d_gather.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st), "D2H gather");
     return batch_sync(b);
 }
+
+} // extern "C"
+
+// ---- filter_profiles / search_variants for every chunk of a batch ---------------------------------------------------
+namespace {
+struct CandScratch {
+    std::vector<double> pv, prior, expected;
+    std::vector<uint32_t> pv_off, prior_off;
+    std::vector<float> min_req;
+};
+
+int run_candidates(jtk_batch *b, const jtk_gains *gains, const int32_t *copy_num, double coverage, int cap, int *out_n) {
+    jtk_ctx *ctx = b->ctx;
+    const int H = gains->homop_len, n_tmpl = b->n_tmpl;
+    cudaStream_t st = ctx->stream;
+    CandScratch sc;
+    sc.min_req.resize((size_t)3 * H);
+    sc.expected.assign(gains->gain, gains->gain + (size_t)3 * H);
+    for (int k = 0; k < 3 * H; k++) sc.min_req[k] = (float)(gains->gain[k] * 0.5); // MIN_REQ_FRACTION (:140)
+    // tables per distinct read count / (copy number, read count)
+    sc.pv_off.resize((size_t)n_tmpl); sc.prior_off.resize((size_t)n_tmpl);
+    std::vector<std::pair<uint32_t, uint32_t>> pv_seen;                 // (n, offset)
+    std::vector<std::pair<std::pair<uint32_t, int32_t>, uint32_t>> pr_seen; // ((n, copy_num), offset)
+    std::vector<double> tmp;
+    for (int t = 0; t < n_tmpl; t++) {
+        const uint32_t n = b->tp_start[(size_t)t + 1] - b->tp_start[(size_t)t];
+        if (copy_num[t] < 1) return ctx->fail(JTK_EINVAL, "copy_num must be >= 1");
+        uint32_t off = UINT32_MAX;
+        for (auto &kv : pv_seen) if (kv.first == n) off = kv.second;
+        if (off == UINT32_MAX) {
+            off = (uint32_t)sc.pv.size();
+            jtk::host::pvalue_tables(gains, n, tmp);
+            sc.pv.insert(sc.pv.end(), tmp.begin(), tmp.end());
+            pv_seen.push_back({ n, off });
+        }
+        sc.pv_off[t] = off;
+        off = UINT32_MAX;
+        for (auto &kv : pr_seen) if (kv.first.first == n && kv.first.second == copy_num[t]) off = kv.second;
+        if (off == UINT32_MAX) {
+            off = (uint32_t)sc.prior.size();
+            jtk::host::poisson_prior_table(coverage, (size_t)copy_num[t], n, tmp);
+            sc.prior.insert(sc.prior.end(), tmp.begin(), tmp.end());
+            pr_seen.push_back({ { n, copy_num[t] }, off });
+        }
+        sc.prior_off[t] = off;
+    }
+    CU(ctx->d_minreq.reserve((size_t)3 * H), "cudaMalloc min_req");
+    CU(ctx->d_tabs.reserve(sc.pv.size() + sc.prior.size() + sc.expected.size()), "cudaMalloc tables");
+    CU(ctx->d_tab_off.reserve((size_t)2 * n_tmpl), "cudaMalloc table offsets");
+    CU(ctx->d_cand.reserve((size_t)cap), "cudaMalloc candidates");
+    CU(ctx->d_counter.reserve(1), "cudaMalloc counter");
+    double *d_pv = ctx->d_tabs.p, *d_prior = d_pv + sc.pv.size(), *d_exp = d_prior + sc.prior.size();
+    CU(cudaMemcpyAsync(ctx->d_minreq.p, sc.min_req.data(), sizeof(float) * 3 * (size_t)H, cudaMemcpyHostToDevice, st), "H2D min_req");
+    CU(cudaMemcpyAsync(d_pv, sc.pv.data(), sizeof(double) * sc.pv.size(), cudaMemcpyHostToDevice, st), "H2D pvalues");
+    CU(cudaMemcpyAsync(d_prior, sc.prior.data(), sizeof(double) * sc.prior.size(), cudaMemcpyHostToDevice, st), "H2D prior");
+    CU(cudaMemcpyAsync(d_exp, sc.expected.data(), sizeof(double) * sc.expected.size(), cudaMemcpyHostToDevice, st), "H2D expected");
+    CU(cudaMemcpyAsync(ctx->d_tab_off.p, sc.pv_off.data(), sizeof(uint32_t) * (size_t)n_tmpl, cudaMemcpyHostToDevice, st), "H2D pv_off");
+    CU(cudaMemcpyAsync(ctx->d_tab_off.p + n_tmpl, sc.prior_off.data(), sizeof(uint32_t) * (size_t)n_tmpl, cudaMemcpyHostToDevice, st), "H2D prior_off");
+    CU(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(int), st), "memset counter");
+    CandArgs a{};
+    a.delta = b->d_delta.p; a.pairs = b->d_pairs.p; a.tp_start = b->d_tp_start.p; a.tp_ids = b->d_tp_ids.p;
+    a.tmpl_len = b->d_tmpl_len.p; a.homop = b->d_homop.p; a.homop_off = b->d_homop_off.p; a.codes = b->d_codes.p;
+    a.tmpl_code_off = b->d_tmpl_code_off.p; a.min_req = ctx->d_minreq.p; a.expected = d_exp; a.H = H;
+    a.pv = d_pv; a.pv_off = ctx->d_tab_off.p; a.prior = d_prior; a.prior_off = ctx->d_tab_off.p + n_tmpl;
+    a.pos_thr = 1e-5f; a.out = ctx->d_cand.p; a.cap = cap; a.counter = ctx->d_counter.p;
+    dim3 grid((unsigned)(((size_t)(b->max_lt + 1) * kNumRow + 255) / 256), (unsigned)n_tmpl);
+    candidates_kernel<<<grid, 256, 0, st>>>(a);
+    CU(cudaGetLastError(), "candidates launch");
+    ctx->launches++;
+    // the scratch vectors must outlive the asynchronous copies: wait for the count right here
+    int n = 0;
+    CU(cudaMemcpyAsync(&n, ctx->d_counter.p, sizeof(int), cudaMemcpyDeviceToHost, st), "D2H candidate count");
+    int rc = batch_sync(b);
+    if (rc) return rc;
+    *out_n = n;
+    return JTK_OK;
+}
+} // namespace
+
+extern "C" {
+
+int jtk_batch_candidates(jtk_batch *b, const jtk_gains *gains, const int32_t *copy_num, double coverage,
+                         jtk_candidate *out, int cap, int *out_n) {
+    if (!b) return JTK_EINVAL;
+    jtk_ctx *ctx = b->ctx;
+    if (!gains || !gains->gain || !gains->prob || gains->homop_len < 1 || !copy_num || !out_n || cap < 0 || (cap > 0 && !out))
+        return ctx->fail(JTK_EINVAL, "null / bad argument");
+    if (!b->has_profiles) return ctx->fail(JTK_ESTATE, "jtk_batch_modtable has not run");
+    *out_n = 0;
+    if (b->n_tmpl == 0 || b->n_pairs == 0) return JTK_OK;
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const int dev_cap = std::max(cap, 1);
+    int n = 0;
+    int rc = run_candidates(b, gains, copy_num, coverage, dev_cap, &n);
+    if (rc) return rc;
+    *out_n = n;
+    if (n > cap) return ctx->fail(JTK_EINVAL, "candidate buffer too small: " + std::to_string(n) + " candidates");
+    if (n == 0) return JTK_OK;
+    CU(ctx->h_cand.reserve((size_t)n), "cudaMallocHost candidates");
+    CU(cudaMemcpyAsync(ctx->h_cand.p, ctx->d_cand.p, sizeof(jtk_candidate) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream), "D2H candidates");
+    rc = batch_sync(b);
+    if (rc) return rc;
+    std::sort(ctx->h_cand.p, ctx->h_cand.p + n, [](const jtk_candidate &x, const jtk_candidate &y) {
+        return x.tmpl != y.tmpl ? x.tmpl < y.tmpl : x.pos < y.pos;
+    });
+    std::memcpy(out, ctx->h_cand.p, sizeof(jtk_candidate) * (size_t)n);
+    return JTK_OK;
+}
+
+int jtk_batch_search_variants(jtk_batch *b, const jtk_gains *gains, const int32_t *copy_num, double coverage, int probe_cap,
+                              uint32_t *out_n_probes, uint32_t *out_probe_pos, double *out_variants) {
+    if (!b) return JTK_EINVAL;
+    jtk_ctx *ctx = b->ctx;
+    if (!gains || !gains->gain || !gains->prob || gains->homop_len < 1 || !copy_num || probe_cap < 1 || !out_n_probes ||
+        !out_probe_pos || !out_variants)
+        return ctx->fail(JTK_EINVAL, "null / bad argument");
+    if (!b->has_profiles) return ctx->fail(JTK_ESTATE, "jtk_batch_modtable has not run");
+    const int n_tmpl = b->n_tmpl;
+    for (int t = 0; t < n_tmpl; t++) {
+        out_n_probes[t] = 0;
+        if (copy_num[t] >= 1 && 3 * std::max(copy_num[t], 2) > probe_cap)
+            return ctx->fail(JTK_EINVAL, "probe_cap must be at least 3 * max(copy_num, 2)");
+    }
+    if (n_tmpl == 0 || b->n_pairs == 0) return JTK_OK;
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaStream_t st = ctx->stream;
+    // 1. candidate columns of every chunk (device)
+    int cap = 256 * n_tmpl + 4096, n = 0;
+    int rc = run_candidates(b, gains, copy_num, coverage, cap, &n);
+    if (rc) return rc;
+    if (n > cap) { // rare: rerun with the exact size
+        cap = n;
+        rc = run_candidates(b, gains, copy_num, coverage, cap, &n);
+        if (rc) return rc;
+    }
+    std::fill(out_variants, out_variants + (size_t)b->n_pairs * probe_cap, 0.0);
+    if (n == 0) return JTK_OK;
+    CU(ctx->h_cand.reserve((size_t)n), "cudaMallocHost candidates");
+    CU(cudaMemcpyAsync(ctx->h_cand.p, ctx->d_cand.p, sizeof(jtk_candidate) * (size_t)n, cudaMemcpyDeviceToHost, st), "D2H candidates");
+    rc = batch_sync(b);
+    if (rc) return rc;
+    jtk_candidate *cand = ctx->h_cand.p;
+    std::sort(cand, cand + n, [](const jtk_candidate &x, const jtk_candidate &y) {
+        return x.tmpl != y.tmpl ? x.tmpl < y.tmpl : x.pos < y.pos;
+    });
+    // 2. their values for every read of the chunk (device gather), laid out as cand[r * M_t + m] per chunk
+    std::vector<uint32_t> meta((size_t)4 * n); // c_tmpl | c_pos | c_base | c_stride
+    std::vector<uint32_t> first_m((size_t)n_tmpl + 1, 0), val_off((size_t)n_tmpl + 1, 0);
+    for (int m = 0; m < n; m++) first_m[cand[m].tmpl + 1]++;
+    for (int t = 0; t < n_tmpl; t++) {
+        first_m[t + 1] += first_m[t];
+        const uint32_t Mt = first_m[t + 1] - first_m[t];
+        val_off[t + 1] = val_off[t] + Mt * (b->tp_start[(size_t)t + 1] - b->tp_start[(size_t)t]);
+    }
+    for (int m = 0; m < n; m++) {
+        const uint32_t t = cand[m].tmpl;
+        meta[m] = t; meta[(size_t)n + m] = cand[m].pos;
+        meta[(size_t)2 * n + m] = val_off[t] + ((uint32_t)m - first_m[t]);
+        meta[(size_t)3 * n + m] = first_m[t + 1] - first_m[t];
+    }
+    const size_t n_val = val_off[n_tmpl];
+    CU(ctx->d_cols.reserve(meta.size()), "cudaMalloc candidate meta");
+    CU(ctx->d_gather.reserve(n_val), "cudaMalloc candidate values");
+    CU(ctx->h_gather.reserve(n_val), "cudaMallocHost candidate values");
+    CU(cudaMemcpyAsync(ctx->d_cols.p, meta.data(), sizeof(uint32_t) * meta.size(), cudaMemcpyHostToDevice, st), "H2D candidate meta");
+    gather_all_kernel<<<(unsigned)n, 64, 0, st>>>(b->d_delta.p, b->d_pairs.p, b->d_tp_start.p, b->d_tp_ids.p, b->d_homop.p,
+                                                 b->d_homop_off.p, ctx->d_minreq.p, gains->homop_len, ctx->d_cols.p,
+                                                 ctx->d_cols.p + n, ctx->d_cols.p + 2 * (size_t)n, ctx->d_cols.p + 3 * (size_t)n,
+                                                 ctx->d_gather.p);
+    CU(cudaGetLastError(), "gather launch");
+    ctx->launches++;
+    CU(cudaMemcpyAsync(ctx->h_gather.p, ctx->d_gather.p, sizeof(double) * n_val, cudaMemcpyDeviceToHost, st), "D2H candidate values");
+    rc = batch_sync(b);
+    if (rc) return rc;
+    // 3. greedy pick per chunk (host, pseudo_mcmc.rs:516-575) and filter_by (:70-75)
+    std::vector<uint32_t> pos;
+    std::vector<double> lk;
+    try {
+        for (int t = 0; t < n_tmpl; t++) {
+            const uint32_t m0 = first_m[t], Mt = first_m[t + 1] - m0;
+            if (Mt == 0 || copy_num[t] < 2) continue; // pseudo_mcmc.rs:86-88: single-copy chunks are not searched
+            const uint32_t r0 = b->tp_start[(size_t)t], nr = b->tp_start[(size_t)t + 1] - r0;
+            pos.resize(Mt); lk.resize(Mt);
+            for (uint32_t m = 0; m < Mt; m++) { pos[m] = cand[m0 + m].pos; lk[m] = cand[m0 + m].lk; }
+            const double *vals = ctx->h_gather.p + val_off[t];
+            const std::vector<size_t> picked = jtk::host::pick_probes(pos.data(), lk.data(), Mt, vals, nr, (size_t)copy_num[t]);
+            if ((int)picked.size() > probe_cap) return ctx->fail(JTK_EINVAL, "probe_cap too small");
+            out_n_probes[t] = (uint32_t)picked.size();
+            for (size_t d = 0; d < picked.size(); d++) {
+                out_probe_pos[(size_t)t * probe_cap + d] = pos[picked[d]];
+                for (uint32_t r = 0; r < nr; r++)
+                    out_variants[(size_t)b->tp_ids[r0 + r] * probe_cap + d] = vals[(size_t)r * Mt + picked[d]];
+            }
+        }
+    } catch (const std::exception &e) {
+        return ctx->fail(JTK_EINVAL, std::string("pick_filtered_profiles: ") + e.what());
+    }
+    return JTK_OK;
+}
+
+} // extern "C"
+
+extern "C" {
 
 int jtk_ctx_timer_start(jtk_ctx *ctx) {
     if (!ctx) return JTK_EINVAL;

@@ -10,6 +10,7 @@
 // not under /root/reference, so stream identity with the Rust build is unpinned; determinism and every reference
 // assertion are tested.
 #include "../../include/jtk_gpu.h"
+#include "lc_host.h"
 
 #include <algorithm>
 #include <cassert>
@@ -638,6 +639,39 @@ static Gains to_gains(const jtk_gains *g) {
     return out;
 }
 
+
+// ---------------------------------------------------------------------------------------------- device-path helpers
+void pvalue_tables(const jtk_gains *g, size_t total, std::vector<double> &out) {
+    const Gains gains = to_gains(g);
+    const Pvalues pv = make_pvalues(gains, total);
+    out.assign((size_t)3 * gains.H * (total + 1), 0.0);
+    for (int t = 0; t < 3; t++)
+        for (int h = 0; h < gains.H; h++)
+            for (size_t c = 0; c <= total; c++) out[((size_t)t * gains.H + h) * (total + 1) + c] = pv.tab[t][h][c];
+}
+
+void poisson_prior_table(double coverage, size_t cluster_num, size_t total, std::vector<double> &out) {
+    out.assign(total + 1, 0.0);
+    for (size_t count = 0; count <= total; count++) {
+        double max_lk = -std::numeric_limits<double>::infinity();
+        bool any = false;
+        for (size_t k = 1; k < cluster_num + 1; k++) {
+            const double v = poisson_lk(count, coverage * (double)k);
+            if (!any || !(v < max_lk)) max_lk = v;
+            any = true;
+        }
+        out[count] = max_lk;
+    }
+}
+
+std::vector<size_t> pick_probes(const uint32_t *pos, const double *lk, size_t M, const double *cand, size_t n,
+                                size_t cluster_num) {
+    std::vector<Probe> probes(M);
+    for (size_t m = 0; m < M; m++) probes[m] = Probe{ (size_t)pos[m], lk[m] };
+    const std::vector<double> c(cand, cand + n * M);
+    return pick_filtered_profiles(probes, c, n, cluster_num);
+}
+
 } // namespace host
 } // namespace jtk
 
@@ -768,6 +802,47 @@ int jtk_lc_clustering_batch(jtk_batch *b, int tmpl_index, const uint8_t *tmpl, i
         for (size_t r = 0; r < n; r++) for (size_t m : picked) variants[r].push_back(cand[r * M + m]);
         const DevResult res = clustering_tail(variants, vt, copy_num, cfg->coverage, cfg->local_coverage, gains, rng);
         return write_result(res, probes, picked, out_asn, out_post, post_stride, out_score, out_k, out_probe_pos, probe_cap, out_n_probes);
+    } catch (const std::exception &e) {
+        g_lc_error = e.what();
+        return JTK_EINVAL;
+    }
+}
+
+// pseudo_mcmc::clustering (:77-107) from the output of search_variants: variants[r * stride + d] is the compressed
+// profile value of read r at the selected flat position probe_pos[d] (jtk_batch_search_variants).
+int jtk_lc_clustering_variants(const double *variants, int n_reads, int n_probes, int stride, const uint32_t *probe_pos,
+                               const uint8_t *tmpl, int Lt, const jtk_gains *gains_c, const jtk_clustering_config *cfg,
+                               uint64_t seed, uint64_t *out_asn, double *out_post, int post_stride, double *out_score, int *out_k) {
+    try {
+        if (!tmpl || !gains_c || !cfg || !out_asn || !out_post || !out_score || !out_k || n_reads < 0 || Lt < 1 || n_probes < 0 ||
+            (n_probes > 0 && (!variants || !probe_pos || stride < n_probes))) {
+            g_lc_error = "null / bad argument"; return JTK_EINVAL;
+        }
+        const size_t n = (size_t)n_reads, copy_num = (size_t)cfg->copy_num;
+        if (copy_num < 2) { // :86-88
+            for (size_t i = 0; i < n; i++) { out_asn[i] = 0; out_post[i * (size_t)post_stride] = 0.0; }
+            *out_score = 0.0; *out_k = 1;
+            return JTK_OK;
+        }
+        const Gains gains = to_gains(gains_c);
+        Rng rng(seed);
+        const std::vector<size_t> homop = homopolymer_length(tmpl, (size_t)Lt);
+        Mat vars(n);
+        VarTypes vt;
+        for (int d = 0; d < n_probes; d++) {
+            size_t bp; DiffType t;
+            pos_to_bp_and_difftype(probe_pos[d], bp, t);
+            vt.push_back({ bp < homop.size() ? homop[bp] : 0, t });
+        }
+        for (size_t r = 0; r < n; r++) vars[r].assign(variants + r * (size_t)stride, variants + r * (size_t)stride + n_probes);
+        const DevResult res = clustering_tail(vars, vt, copy_num, cfg->coverage, cfg->local_coverage, gains, rng);
+        if ((int)res.k > post_stride) { g_lc_error = "post_stride smaller than the cluster number"; return JTK_EINVAL; }
+        for (size_t i = 0; i < n; i++) {
+            out_asn[i] = res.asn[i];
+            for (size_t c = 0; c < res.k; c++) out_post[i * (size_t)post_stride + c] = res.gains[i][c];
+        }
+        *out_score = res.score; *out_k = (int)res.k;
+        return JTK_OK;
     } catch (const std::exception &e) {
         g_lc_error = e.what();
         return JTK_EINVAL;

@@ -85,6 +85,9 @@ def _bind():
         L.jtk_lc_clustering_batch.argtypes = [C.c_void_p, C.c_int, vp, C.c_int, C.c_int, vp, C.POINTER(_CGains),
                                               C.POINTER(_CConfig), C.c_uint64, vp, vp, C.c_int, C.POINTER(C.c_double),
                                               C.POINTER(C.c_int), vp, C.c_int, C.POINTER(C.c_int)]
+        L.jtk_lc_clustering_variants.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.POINTER(_CGains),
+                                                 C.POINTER(_CConfig), C.c_uint64, vp, vp, C.c_int, C.POINTER(C.c_double),
+                                                 C.POINTER(C.c_int)]
         L.jtk_lc_last_error.restype = C.c_char_p
         L.jtk_lc_cosine_similarity.restype = C.c_double
         L.jtk_lc_cosine_similarity.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -138,6 +141,44 @@ def clustering_on_batch(batch: Batch, tmpl: int, template, stats, config: Cluste
                                    _ptr(asn), _ptr(post), stride, C.byref(score), C.byref(k), _ptr(probes), len(probes),
                                    C.byref(nprobe))
     return _finish(rc, n, stride, asn, post, score, k, probes, nprobe)
+
+
+def clustering_on_variants(variants, probe_pos, template, config: ClusteringConfig, seed: int) -> ClusteringResult:
+    """pseudo_mcmc::clustering after `search_variants`: variants float64[n, >=D] (one chunk's rows of
+    Batch.search_variants), probe_pos uint32[D]."""
+    L = _bind()
+    v = np.ascontiguousarray(variants, dtype=np.float64)
+    pp = np.ascontiguousarray(probe_pos, dtype=np.uint32)
+    t = _lib._u8(template)
+    n, stride = v.shape
+    pstride = max(config.copy_num, 1)
+    asn = np.zeros(n, dtype=np.uint64)
+    post = np.zeros(n * pstride, dtype=np.float64)
+    score, k = C.c_double(), C.c_int()
+    g, c = config.gains.to_c(), config.to_c()
+    rc = L.jtk_lc_clustering_variants(_ptr(v), n, len(pp), stride, _ptr(pp), _ptr(t), len(t), C.byref(g), C.byref(c), seed,
+                                      _ptr(asn), _ptr(post), pstride, C.byref(score), C.byref(k))
+    if rc != 0:
+        raise _lib.JtkError(rc, L.jtk_lc_last_error().decode())
+    kk = int(k.value)
+    return ClusteringResult(asn, post.reshape(n, pstride)[:, :kk].copy(), float(score.value), kk, pp.copy())
+
+
+def local_clustering_batch(batch: Batch, templates, config_of, seeds, hmm_fwd, hmm_rev, gains: Gains, coverage: float):
+    """The per-chunk loop of local_clustering_selected (local_clustering/mod.rs:64-72) after polishing, for a whole
+    batch: 9-row modification tables, device-side filter_profiles, gathered candidate columns, host pick + MCMC.
+    config_of(t) -> ClusteringConfig of chunk t; seeds[t] the chunk's RNG seed (chunk.id * 3490, mod.rs:97)."""
+    batch.modtable(hmm_fwd, hmm_rev, 9)
+    cfgs = [config_of(t) for t in range(batch.n_tmpl)]
+    copy_num = np.array([max(c.copy_num, 1) for c in cfgs], dtype=np.int32)
+    n_probes, probe_pos, variants = batch.search_variants(gains.gain, gains.prob, copy_num, coverage)
+    out = []
+    for t in range(batch.n_tmpl):
+        rows = np.flatnonzero(batch.tmpl_idx == t)
+        d = int(n_probes[t])
+        out.append(clustering_on_variants(variants[rows][:, :max(d, 1)] if d else np.zeros((len(rows), 1)), probe_pos[t, :d],
+                                          templates[t], cfgs[t], int(seeds[t])))
+    return out
 
 
 def clustering(template, reads: Sequence, ops: Sequence, strands: Sequence[bool], seed: int, hmm, config: ClusteringConfig,

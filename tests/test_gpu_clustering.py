@@ -119,6 +119,46 @@ def test_batch_path_matches_profile_path(ctx):
     b.close()
 
 
+def test_device_filter_profiles_matches_host(ctx):
+    """jtk_batch_candidates / jtk_batch_search_variants (filter_profiles on the device, only candidates cross PCIe) select
+    exactly the columns the host restatement selects from the full per-column statistics, and the clustering that
+    follows is identical (pseudo_mcmc.rs:109-138,426-575)."""
+    chunks = [synth.diploid_chunk(51 + c, length=600 + 50 * c, n_reads=40 + 2 * c, error_rate=0.08, n_snv=2 + c) for c in range(4)]
+    h = O.default_hmm()
+    templates = [c["template"] for c in chunks]
+    reads = [r for c in chunks for r in c["reads"]]
+    ops = [o for c in chunks for o in c["ops"]]
+    strands = np.concatenate([c["strands"] for c in chunks])
+    tidx = np.repeat(np.arange(4, dtype=np.uint32), [len(c["reads"]) for c in chunks])
+    b = ctx.batch(templates, reads, ops, strands, tidx, 20)
+    b.modtable(to_c(h), to_c(h), 9)
+    stats = b.colstats(GAINS.min_req, 1e-5)
+    copy_num = np.array([2, 2, 3, 2], dtype=np.int32)
+    cov = 21.0
+    cand = b.candidates(GAINS.gain, GAINS.prob, copy_num, cov)
+    n_probes, probe_pos, variants = b.search_variants(GAINS.gain, GAINS.prob, copy_num, cov)
+    assert len(cand) > 0 and (np.diff(cand["tmpl"].astype(np.int64)) >= 0).all()
+    for t, d in enumerate(chunks):
+        sl = slice(int(b.stat_off[t]), int(b.stat_off[t + 1]))
+        cfg = LC.ClusteringConfig.new(20, int(copy_num[t]), cov, cov, GAINS)
+        ref = LC.clustering_on_batch(b, t, d["template"], stats[sl], cfg, (t + 7) * 3490)
+        ct = cand[cand["tmpl"] == t]
+        # every candidate carries the statistics of its column, and the selected probes come out of the candidates
+        assert (stats["count"][sl][ct["pos"]] == ct["count"]).all()
+        assert (stats["sum"][sl][ct["pos"]] == ct["sum"]).all()
+        k = int(n_probes[t])
+        assert probe_pos[t, :k].tolist() == ref.probes.tolist()
+        assert set(probe_pos[t, :k].tolist()) <= set(ct["pos"].tolist())
+        rows = np.flatnonzero(tidx == t)
+        got = LC.clustering_on_variants(variants[rows], probe_pos[t, :k], d["template"], cfg, (t + 7) * 3490)
+        assert got.k == ref.k and (got.assignments == ref.assignments).all()
+        assert got.score == ref.score and np.array_equal(got.posterior, ref.posterior)
+        if k:
+            g = b.gather(t, GAINS.min_req, probe_pos[t, :k])
+            assert np.array_equal(g, variants[rows][:, :k])
+    b.close()
+
+
 def test_kiley_shaped_clustering_call(ctx):
     """local_clustering.clustering mirrors pseudo_mcmc::clustering's argument list."""
     from jtk_b200 import hmm
