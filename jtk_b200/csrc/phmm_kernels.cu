@@ -26,7 +26,7 @@ constexpr int kRescaleEvery = 4;
 //    backward product of one cell is (posterior mass) x 2^kProductExp: B = 2^kProductExp / F on the cells that
 //    matter, inside the fp32 range on both sides as long as the dead-end advantage stays below ~2^180.
 //  * a product that pairs rows on the two sides of a rescale gets its exact power-of-two correction.
-constexpr int kScaleLow = 88;
+constexpr int kScaleLow = 64;
 constexpr int kScaleTarget = 100;
 constexpr int kScaleStep = 64;
 constexpr int kProductExp = 0;
@@ -50,8 +50,6 @@ __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %
 __device__ __forceinline__ void acc2(f2 &acc, f2 a, f2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 bc2(float v) { return mk2(v, v); }
-// a packed pair the compiler must keep as one 64-bit value (loop-invariant coefficients: no re-packing per use)
-__device__ __forceinline__ f2 mk2_keep(float lo, float hi) { f2 r; asm volatile("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 
 __device__ __forceinline__ float lds_f32(unsigned a) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void lds_f32x4(unsigned a, f2 &x, f2 &y) {
@@ -248,28 +246,24 @@ __device__ __forceinline__ void forward_pass(const PairCtx &pc, const Coef &a, f
     }
     if (lane < 4) s_ftot[lane] = 0.f;
     int K = 0;
-    int xtop = pc.r; // largest x over the slots (warp-uniform)
     unsigned bword = pc.bw[0];
-    auto transition = [&](int s) { // anti-diagonal s -> s+1
-        const unsigned b = (bword >> (s & 31)) & 1u;
+    // anti-diagonal s -> s+1: when the centre stays (guide bit 0) every cell moves one row up inside the window
+    auto transition = [&](int s) {
+        const int up = (int)(((bword >> (s & 31)) & 1u) ^ 1u);
         if (((s + 1) & 31) == 0) bword = pc.bw[(s + 1) >> 5];
-        if (b == 0u) { // centre stays: every cell moves one row up inside the window
-            if (xtop < W) {
-                xtop++;
 #pragma unroll
-                for (int c = 0; c < C; c++) st.x[c]++;
-            } else {
+        for (int c = 0; c < C; c++) st.x[c] += up;
+    };
+    // A slot whose cell has left the band at the top (x > W) moves on to column j + NSLOT.  It may be done up to two
+    // steps late: the ring has NSLOT - (W+1) >= 3 spare slots, and a cell outside the band is masked anyway.
+    auto retarget = [&](int s_next) {
 #pragma unroll
-                for (int c = 0; c < C; c++) {
-                    if (st.x[c] == W) { // the slot at the top of the band moves on to column j + NSLOT
-                        st.j[c] += NSLOT;
-                        st.tcB[c] = pc.sEM + ((unsigned)pc.Tb[st.j[c]] << 5);
-                        st.win[c] = win_up(pc.RbP, s + 1 - st.j[c]);
-                        st.x[c] = W + 1 - NSLOT;
-                    } else {
-                        st.x[c]++;
-                    }
-                }
+        for (int c = 0; c < C; c++) {
+            if (st.x[c] > W) {
+                st.j[c] += NSLOT;
+                st.x[c] -= NSLOT;
+                st.tcB[c] = pc.sEM + ((unsigned)pc.Tb[st.j[c]] << 5);
+                st.win[c] = win_up(pc.RbP, s_next - st.j[c]);
             }
         }
     };
@@ -281,21 +275,23 @@ __device__ __forceinline__ void forward_pass(const PairCtx &pc, const Coef &a, f
     // prologue: the first four anti-diagonals (the start cell is injected at s = 0)
     for (; s < 4 && s < nd; ++s) {
         fwd_step<C, STORE, true>(pc, a, st, s, W, K, wrow, halo, kf, s_ftot, evw);
-        if (s < nd - 1) transition(s);
+        if (s < nd - 1) { transition(s); retarget(s + 1); }
     }
     // main loop: four steps per read-row window
     for (; s + 3 < nd - 4; s += 4) {
         reload(s);
         fwd_step<C, STORE, false>(pc, a, st, s, W, K, wrow, halo, kf, s_ftot, evw); transition(s);
         fwd_step<C, STORE, false>(pc, a, st, s + 1, W, K, wrow, halo, kf, s_ftot, evw); transition(s + 1);
+        retarget(s + 2);
         fwd_step<C, STORE, false>(pc, a, st, s + 2, W, K, wrow, halo, kf, s_ftot, evw); transition(s + 2);
         fwd_step<C, STORE, false>(pc, a, st, s + 3, W, K, wrow, halo, kf, s_ftot, evw); transition(s + 3);
+        retarget(s + 4);
     }
     // epilogue: the last anti-diagonals also record the delete-to-end terms
     for (; s < nd; ++s) {
         if ((s & 3) == 0) reload(s);
         fwd_step<C, STORE, true>(pc, a, st, s, W, K, wrow, halo, kf, s_ftot, evw);
-        if (s < nd - 1) transition(s);
+        if (s < nd - 1) { transition(s); retarget(s + 1); }
     }
     Ktot = K;
     __syncwarp();
@@ -623,7 +619,7 @@ __device__ __forceinline__ PairCtx make_pair_ctx(const KParams &p, const DevPair
 template <int C> constexpr int ring_floats2() { return (kRingRows + 2 * kRingMargin) * (32 * C + 2 * kHalo); }
 
 template <int C, int ROWS>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) modtable_kernel(KParams p) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, C == 2 ? 3 : 1) modtable_kernel(KParams p) {
     __shared__ SmemLayout sh;
     extern __shared__ __align__(128) unsigned char dyn_smem[]; // kWarpsPerCta rings of forward rows
     fill_tables(sh, p.models);
