@@ -146,6 +146,7 @@ struct PairCtx { // warp-uniform view of one pair
 template <int C> struct FwdState {
     int x[C], j[C];
     unsigned tcB[C], win[C];
+    unsigned tcn[C]; // template code of the column this slot takes next (j + NSLOT), loaded one column-life ahead
     float toI[C], inD[C], inMa[C], inMb[C];
 };
 
@@ -241,6 +242,7 @@ __device__ __forceinline__ void forward_pass(const PairCtx &pc, const Coef &a, f
         st.j[c] = lane * C + c;
         st.x[c] = pc.r - st.j[c]; // row i = -j on anti-diagonal 0, window starts at row -r
         st.tcB[c] = pc.sEM + ((unsigned)pc.Tb[st.j[c]] << 5);
+        st.tcn[c] = pc.Tb[st.j[c] + NSLOT];
         st.win[c] = win_up(pc.RbP, -st.j[c]);
         st.toI[c] = st.inD[c] = st.inMa[c] = st.inMb[c] = 0.f;
     }
@@ -262,8 +264,12 @@ __device__ __forceinline__ void forward_pass(const PairCtx &pc, const Coef &a, f
             if (st.x[c] > W) {
                 st.j[c] += NSLOT;
                 st.x[c] -= NSLOT;
-                st.tcB[c] = pc.sEM + ((unsigned)pc.Tb[st.j[c]] << 5);
-                st.win[c] = win_up(pc.RbP, s_next - st.j[c]);
+                // no load on this path: the template code was fetched when the slot took its previous column, and the
+                // read-row window of a retargeted slot is not needed before the next regular reload (the slot stays
+                // outside the band for at least as many steps as that is away)
+                st.tcB[c] = pc.sEM + (st.tcn[c] << 5);
+                st.tcn[c] = pc.Tb[st.j[c] + NSLOT];
+                (void)s_next;
             }
         }
     };
@@ -328,6 +334,7 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
 template <int C> struct BwdState {
     int x[C], j[C];
     unsigned tcB[C], win[C];
+    unsigned tcn[C]; // template code of the column this slot takes next (j - NSLOT), loaded one column-life ahead
     float BI[C], BMo[C], inD[C], inMa[C], inMb[C];
     f2 S01[C], S23[C], N01[C], N23[C]; // substitution / insertion sums over the four bases
     float Vs[C], Vn[C];
@@ -452,6 +459,7 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
         st.j[c] = Lt - d;      // largest column <= Lt owned by this slot
         st.x[c] = d + pc.r;    // row i = Lr + d on the last anti-diagonal, window starts at row Lr - r
         st.tcB[c] = pc.sEM + ((unsigned)pc.Tb[st.j[c] + 1] << 5); // code of t[j]
+        st.tcn[c] = pc.Tb[st.j[c] + 1 - NSLOT];
         st.win[c] = 0u;
         st.BI[c] = st.BMo[c] = st.inD[c] = st.inMa[c] = st.inMb[c] = 0.f;
         st.Vs[c] = st.Vn[c] = 0.f;
@@ -528,8 +536,9 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
                     if (st.j[c] >= 0) flush_col(c);
                     st.j[c] -= NSLOT;
                     st.x[c] = NSLOT - 1;
-                    st.tcB[c] = pc.sEM + ((unsigned)pc.Tb[st.j[c] + 1] << 5);
-                    st.win[c] = win_down(pc.RbP, (s - 1) - st.j[c] + 1);
+                    st.tcB[c] = pc.sEM + (st.tcn[c] << 5); // fetched one column-life ago; the window comes with the next reload
+                    st.tcn[c] = pc.Tb[st.j[c] + 1 - NSLOT];
+                    (void)s;
                     st.Vs[c] = st.Vn[c] = 0.f;
                     st.S01[c] = st.S23[c] = st.N01[c] = st.N23[c] = 0ull;
 #pragma unroll
@@ -573,7 +582,14 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
     const bool ev_over = ((nd >> 2) + 3) >= kEvWords * 32; // event map too short for this pair: every block is generic
     wait_group(q_top + 1);
     wait_group(q_top);
+    auto load_nib = [&](int q) -> unsigned { // guide bits 4q-5 .. 4q-2 of block q >= 2
+        const int b0 = 4 * q - 5;
+        return __funnelshift_r(pc.bw[b0 >> 5], pc.bw[(b0 >> 5) + 1], b0 & 31);
+    };
+    unsigned nib_cur = 0u, nib_nxt = q_top >= 2 ? load_nib(q_top) : 0u;
     for (int q = q_top; q >= 1; --q) { // block q: anti-diagonals s = 4q-1 .. 4q-4 (rho = 4q+3 .. 4q)
+        nib_cur = nib_nxt;
+        if (q >= 3) nib_nxt = load_nib(q - 1);
         wait_group(q - 1);
         __syncwarp(); // every lane is done with the rows that the next copy overwrites
         if (q >= 2) issue_group(q - 2);
@@ -583,9 +599,8 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
         if (s_hi <= nd - 2 && q >= 2 && ew == 0u && !ev_over) {
             const f2 *rp = ring + (size_t)(4 * (q & 3) + 3 + kRingMargin) * RS + kHalo + lane * C;
             reload(s_hi);
-            // guide bits 4q-5 .. 4q-2: step k (s = s_hi - k) moves on with bit 4q-2-k
-            const int b0 = 4 * q - 5;
-            const unsigned nib = __funnelshift_r(pc.bw[b0 >> 5], pc.bw[(b0 >> 5) + 1], b0 & 31);
+            // guide bits 4q-5 .. 4q-2 (fetched one block ahead): step k (s = s_hi - k) moves on with bit 4q-2-k
+            const unsigned nib = nib_cur;
 #pragma unroll 1
             for (int k = 0; k < 4; k++, rp -= RS) {
                 f2 bMD[C];
