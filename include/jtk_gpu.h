@@ -271,6 +271,13 @@ int jtk_lc_clustering_variants(const double *variants, int n_reads, int n_probes
                                const uint8_t *tmpl, int Lt, const jtk_gains *gains, const jtk_clustering_config *cfg,
                                uint64_t seed, uint64_t *out_asn, double *out_post, int post_stride, double *out_score,
                                int *out_k);
+/* the same with the caller's generator (four Xoshiro256** state words, in/out): clustering_recursive threads one rng
+ * through every level of the recursion (local_clustering/mod.rs:97,114,143,159) */
+void jtk_lc_rng_seed(uint64_t seed, uint64_t *state4);
+int jtk_lc_clustering_variants_rng(const double *variants, int n_reads, int n_probes, int stride, const uint32_t *probe_pos,
+                                   const uint8_t *tmpl, int Lt, const jtk_gains *gains, const jtk_clustering_config *cfg,
+                                   uint64_t *state4, uint64_t *out_asn, double *out_post, int post_stride, double *out_score,
+                                   int *out_k);
 const char *jtk_lc_last_error(void);
 /* hooks for the reference's unit tests on these files (pseudo_mcmc.rs:876-904) and the generator */
 double jtk_lc_cosine_similarity(const double *profiles, int n, int ncol, int i, int j);

@@ -810,9 +810,9 @@ int jtk_lc_clustering_batch(jtk_batch *b, int tmpl_index, const uint8_t *tmpl, i
 
 // pseudo_mcmc::clustering (:77-107) from the output of search_variants: variants[r * stride + d] is the compressed
 // profile value of read r at the selected flat position probe_pos[d] (jtk_batch_search_variants).
-int jtk_lc_clustering_variants(const double *variants, int n_reads, int n_probes, int stride, const uint32_t *probe_pos,
-                               const uint8_t *tmpl, int Lt, const jtk_gains *gains_c, const jtk_clustering_config *cfg,
-                               uint64_t seed, uint64_t *out_asn, double *out_post, int post_stride, double *out_score, int *out_k) {
+static int clustering_variants_impl(const double *variants, int n_reads, int n_probes, int stride, const uint32_t *probe_pos,
+                                    const uint8_t *tmpl, int Lt, const jtk_gains *gains_c, const jtk_clustering_config *cfg,
+                                    Rng &rng, uint64_t *out_asn, double *out_post, int post_stride, double *out_score, int *out_k) {
     try {
         if (!tmpl || !gains_c || !cfg || !out_asn || !out_post || !out_score || !out_k || n_reads < 0 || Lt < 1 || n_probes < 0 ||
             (n_probes > 0 && (!variants || !probe_pos || stride < n_probes))) {
@@ -825,7 +825,6 @@ int jtk_lc_clustering_variants(const double *variants, int n_reads, int n_probes
             return JTK_OK;
         }
         const Gains gains = to_gains(gains_c);
-        Rng rng(seed);
         const std::vector<size_t> homop = homopolymer_length(tmpl, (size_t)Lt);
         Mat vars(n);
         VarTypes vt;
@@ -847,6 +846,33 @@ int jtk_lc_clustering_variants(const double *variants, int n_reads, int n_probes
         g_lc_error = e.what();
         return JTK_EINVAL;
     }
+}
+
+int jtk_lc_clustering_variants(const double *variants, int n_reads, int n_probes, int stride, const uint32_t *probe_pos,
+                               const uint8_t *tmpl, int Lt, const jtk_gains *gains_c, const jtk_clustering_config *cfg,
+                               uint64_t seed, uint64_t *out_asn, double *out_post, int post_stride, double *out_score, int *out_k) {
+    Rng rng(seed);
+    return clustering_variants_impl(variants, n_reads, n_probes, stride, probe_pos, tmpl, Lt, gains_c, cfg, rng, out_asn, out_post,
+                                    post_stride, out_score, out_k);
+}
+
+// The same with the caller's generator state (four Xoshiro256** words, in/out): clustering_recursive threads ONE rng
+// through every level of the recursion (local_clustering/mod.rs:97,114,143,159).
+void jtk_lc_rng_seed(uint64_t seed, uint64_t *state4) {
+    Rng rng(seed);
+    std::memcpy(state4, rng.s, 32);
+}
+int jtk_lc_clustering_variants_rng(const double *variants, int n_reads, int n_probes, int stride, const uint32_t *probe_pos,
+                                   const uint8_t *tmpl, int Lt, const jtk_gains *gains_c, const jtk_clustering_config *cfg,
+                                   uint64_t *state4, uint64_t *out_asn, double *out_post, int post_stride, double *out_score,
+                                   int *out_k) {
+    if (!state4) { g_lc_error = "null rng state"; return JTK_EINVAL; }
+    Rng rng(0);
+    std::memcpy(rng.s, state4, 32);
+    const int rc = clustering_variants_impl(variants, n_reads, n_probes, stride, probe_pos, tmpl, Lt, gains_c, cfg, rng, out_asn,
+                                            out_post, post_stride, out_score, out_k);
+    std::memcpy(state4, rng.s, 32);
+    return rc;
 }
 
 // test hooks for the reference's own unit tests on these files (pseudo_mcmc.rs:876-904)

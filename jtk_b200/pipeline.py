@@ -1,0 +1,385 @@
+"""Mirror of the per-chunk driver of haplotyper::local_clustering and of the HMM fit loop.
+
+Reference (all under /root/reference/haplotyper/src):
+  local_clustering/mod.rs:23-83    LocalClustering::{local_clustering, local_clustering_selected}, pileup_nodes
+  local_clustering/mod.rs:86-123   clustering_on_pileup
+  local_clustering/mod.rs:126-260  clustering_recursive, estim_copy_num, filter_sub_clusters, update_by_clusterings
+  local_clustering/normalize.rs    normalize_local_clustering, reorder
+  model_tune.rs:94-156             estimate_model_parameters_on_both_strands (5 chunks x 10 rounds of polish + EM)
+  misc.rs:394-407                  update_coverage
+  definitions/src/lib.rs:173-210   ReadType::band_width
+
+Same names and argument meaning; the difference is the execution shape: where the reference runs one chunk per rayon
+task and one kiley call per read, this driver hands ALL selected pile-ups to the GPU at once (one polish batch, one
+9-row modification-table batch, one device-side filter_profiles), keeps the host loops (greedy pick, k-means, MCMC)
+per chunk, and can shard the chunks over ranks (scheduler.py).  Data model: `Chunk`, `Node`, `DataSet` carry exactly the
+fields the hot path reads and writes (definitions/src/lib.rs); `Node.ops` is the per-column op vector
+(misc::ops_to_kiley of `Node.cigar`).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, Iterable, List, Optional, Sequence, Set, Tuple
+
+import numpy as np
+
+from . import _lib, scheduler
+from .hmm import HMMPolishConfig, PairHiddenMarkovModelOnStrands, default_context, fit_antidiagonal_par_multiple, polish_chunks
+from .local_clustering import ClusteringConfig, ClusteringResult, Gains, _bind, _CConfig
+import ctypes as C
+
+UPPER_COPY_NUM = 8   # local_clustering/mod.rs:85
+BRANCH_NUM = 4       # local_clustering/mod.rs:139
+TRAIN_UNIT_SIZE = 5  # model_tune.rs:94
+TRAIN_ROUND = 10     # model_tune.rs:95
+BAND_FRAC = {"CCS": 0.01, "CLR": 0.05, "ONT": 0.03, "None": 0.05}  # definitions/src/lib.rs:173-175,201-210
+
+
+def band_width(read_type: str, length: int) -> int:
+    """ReadType::band_width (definitions/src/lib.rs:201-210)."""
+    return int(math.ceil(length * BAND_FRAC[read_type]))
+
+
+@dataclass
+class Chunk:
+    id: int
+    seq: np.ndarray          # uint8 ASCII
+    copy_num: int
+    cluster_num: int = 1
+    score: float = 0.0
+
+
+@dataclass
+class Node:
+    chunk: int
+    seq: np.ndarray          # uint8 ASCII, already in chunk orientation (definitions/src/lib.rs:678)
+    ops: np.ndarray          # uint8 per alignment column: 0 Match, 1 Mismatch, 2 Ins, 3 Del (global over the chunk)
+    is_forward: bool
+    cluster: int = 0
+    posterior: np.ndarray = field(default_factory=lambda: np.zeros(1))
+
+
+@dataclass
+class DataSet:
+    selected_chunks: List[Chunk]
+    nodes: List[Node]        # encoded_reads.iter().flat_map(|r| r.nodes) in read order
+    read_type: str = "ONT"
+    coverage: Optional[float] = None
+    coverage_protected: bool = False
+    model: Optional[PairHiddenMarkovModelOnStrands] = None
+
+
+def update_coverage(ds: DataSet) -> None:
+    """misc::update_coverage (misc.rs:394-407): haploid coverage = median node count per chunk / 2."""
+    if ds.coverage_protected and ds.coverage is not None:
+        return
+    counts: Dict[int, int] = {}
+    for n in ds.nodes:
+        counts[n.chunk] = counts.get(n.chunk, 0) + 1
+    cs = sorted(counts.values())
+    ds.coverage = cs[len(cs) // 2] / 2.0
+
+
+def nonmatch_columns(node: Node, chunk: Chunk) -> int:
+    """Sort key of pileup_nodes (mod.rs:47-50): alignment columns of Node::recover that are not '|'."""
+    ops = np.asarray(node.ops)
+    indel = int(np.count_nonzero(ops >= 2))
+    diag = ops < 2
+    qi = np.cumsum(ops != 3) - 1   # read index consumed at each column
+    tj = np.cumsum(ops != 2) - 1   # template index consumed at each column
+    mism = int(np.count_nonzero(np.asarray(node.seq)[qi[diag]] != np.asarray(chunk.seq)[tj[diag]]))
+    return indel + mism
+
+
+def pileup_nodes(ds: DataSet, selection: Set[int]) -> Dict[int, Tuple[List[Node], Chunk]]:
+    """mod.rs:33-53: nodes per selected chunk, cleanest alignments first (stable sort, as sort_by_cached_key)."""
+    pile: Dict[int, Tuple[List[Node], Chunk]] = {c.id: ([], c) for c in ds.selected_chunks if c.id in selection}
+    for n in ds.nodes:
+        if n.chunk in pile:
+            pile[n.chunk][0].append(n)
+    for nodes, chunk in pile.values():
+        nodes.sort(key=lambda n: nonmatch_columns(n, chunk))
+    return pile
+
+
+def estim_copy_num(asn: Sequence[int], k: int, copy_num: int, coverage: float) -> List[int]:
+    """mod.rs:223-242 (max_by keeps the last of equal maxima)."""
+    assert k <= copy_num, (k, copy_num)
+    counts = [0.0] * k
+    for x in asn:
+        counts[int(x)] += 1.0
+    cps = [1] * k
+    for _ in range(k, copy_num):
+        best, arg = None, 0
+        for i in range(k):
+            v = (counts[i] - coverage * cps[i]) ** 2
+            if best is None or not (v < best):
+                best, arg = v, i
+        cps[arg] += 1
+    assert sum(cps) == copy_num
+    return cps
+
+
+def reorder(xs, indices) -> None:
+    """normalize.rs:54-63 (in place)."""
+    for i in range(len(xs)):
+        while int(indices[i]) != i:
+            to = int(indices[i])
+            xs[i], xs[to] = xs[to], xs[i]
+            indices[i], indices[to] = indices[to], indices[i]
+
+
+def normalize_local_clustering(ds: DataSet) -> None:
+    """normalize.rs:6-51: relabel the clusters of every chunk by descending size, permute the posteriors."""
+    cluster_num = {c.id: c.cluster_num for c in ds.selected_chunks}
+    pile: Dict[int, List[Node]] = {}
+    for n in ds.nodes:
+        pile.setdefault(n.chunk, []).append(n)
+    for cid, nodes in pile.items():
+        if cid not in cluster_num:
+            continue
+        mx = cluster_num[cid]
+        for n in nodes:
+            assert len(n.posterior) == mx, (cid, len(n.posterior), mx)
+        counts = [[c, 0] for c in range(mx)]
+        for n in nodes:
+            counts[int(n.cluster)][1] += 1
+        counts.sort(key=lambda x: x[1])   # stable, then reversed: as sort_by_key + reverse
+        counts.reverse()
+        mapsto = [0] * mx
+        for to, (frm, _) in enumerate(counts):
+            mapsto[frm] = to
+        for n in nodes:
+            idx = list(mapsto)
+            n.cluster = mapsto[int(n.cluster)]
+            post = list(n.posterior)
+            reorder(post, idx)
+            n.posterior = np.array(post)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def _rng_seed(seed: int) -> np.ndarray:
+    st = np.zeros(4, dtype=np.uint64)
+    L = _bind()
+    L.jtk_lc_rng_seed.argtypes = [C.c_uint64, C.c_void_p]
+    L.jtk_lc_rng_seed.restype = None
+    L.jtk_lc_rng_seed(seed, _lib._ptr(st))
+    return st
+
+
+def _clustering_variants_rng(variants, probe_pos, template, config: ClusteringConfig, state: np.ndarray) -> ClusteringResult:
+    """jtk_lc_clustering_variants_rng: pseudo_mcmc::clustering after search_variants, advancing the caller's generator."""
+    L = _bind()
+    vp = C.c_void_p
+    L.jtk_lc_clustering_variants_rng.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_void_p, C.POINTER(_CConfig),
+                                                 vp, vp, vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    v = np.ascontiguousarray(variants, dtype=np.float64)
+    pp = np.ascontiguousarray(probe_pos, dtype=np.uint32)
+    t = _lib._u8(template)
+    n, stride = v.shape
+    pstride = max(config.copy_num, 1)
+    asn = np.zeros(n, dtype=np.uint64)
+    post = np.zeros(n * pstride, dtype=np.float64)
+    score, k = C.c_double(), C.c_int()
+    g, c = config.gains.to_c(), config.to_c()
+    rc = L.jtk_lc_clustering_variants_rng(_lib._ptr(v), n, len(pp), stride, _lib._ptr(pp), _lib._ptr(t), len(t), C.byref(g),
+                                          C.byref(c), _lib._ptr(state), _lib._ptr(asn), _lib._ptr(post), pstride,
+                                          C.byref(score), C.byref(k))
+    if rc != 0:
+        raise _lib.JtkError(rc, L.jtk_lc_last_error().decode())
+    kk = int(k.value)
+    return ClusteringResult(asn, post.reshape(n, pstride)[:, :kk].copy(), float(score.value), kk, pp.copy())
+
+
+def _search_and_cluster(ctx, hmm, cons, seqs, ops, strands, config: ClusteringConfig, state: np.ndarray) -> ClusteringResult:
+    """pseudo_mcmc::clustering (pseudo_mcmc.rs:77-107) for one pile-up with the caller's generator."""
+    n = len(seqs)
+    if config.copy_num < 2:
+        return ClusteringResult(np.zeros(n, np.uint64), np.zeros((n, 1)), 0.0, 1, np.zeros(0, np.uint32))
+    b = ctx.batch([cons], list(seqs), list(ops), np.asarray(strands, dtype=np.uint8), np.zeros(n, np.uint32), config.band_width)
+    try:
+        b.modtable(hmm.forward().to_c(), hmm.reverse().to_c(), 9)
+        n_probes, probe_pos, variants = b.search_variants(config.gains.gain, config.gains.prob, config.copy_num, config.coverage)
+    finally:
+        b.close()
+    d = int(n_probes[0])
+    return _clustering_variants_rng(variants[:, :max(d, 1)], probe_pos[0, :d], cons, config, state)
+
+
+def clustering_recursive(ctx, cons, seqs, ops, strands, state: np.ndarray, hmm, config: ClusteringConfig,
+                         first: Optional[ClusteringResult] = None):
+    """mod.rs:126-190.  Returns (assignments list, posterior rows list, score, k).  `first`: the top-level clustering when it
+    was already computed in a batch (only valid for copy_num < UPPER_COPY_NUM)."""
+    if config.copy_num < UPPER_COPY_NUM:
+        r = first if first is not None else _search_and_cluster(ctx, hmm, cons, seqs, ops, strands, config, state)
+        return [int(a) for a in r.assignments], [list(p) for p in r.posterior], r.score, r.k
+    rec = ClusteringConfig(config.band_width, BRANCH_NUM, config.coverage, config.local_coverage, config.gains)
+    r = _search_and_cluster(ctx, hmm, cons, seqs, ops, strands, rec, state)
+    asn, pss, score, k = [int(a) for a in r.assignments], [list(p) for p in r.posterior], r.score, r.k
+    copy_numbers = estim_copy_num(asn, k, config.copy_num, config.coverage)
+    if k <= 1:
+        return asn, pss, score, k
+    rec_results = []
+    for cl, cp in enumerate(copy_numbers):
+        idx = [i for i, a in enumerate(asn) if a == cl]          # filter_sub_clusters (mod.rs:200-221)
+        sub_seqs = [seqs[i] for i in idx]
+        sub_ops = [np.array(ops[i], copy=True) for i in idx]
+        sub_str = [strands[i] for i in idx]
+        pcfg = HMMPolishConfig.new(config.band_width, len(sub_seqs), 0)   # mod.rs:154
+        sub_cons = hmm.polish_until_converge_antidiagonal(cons, sub_seqs, sub_ops, sub_str, pcfg, ctx=ctx)
+        sub_cfg = ClusteringConfig(config.band_width, cp, config.coverage, config.local_coverage, config.gains)
+        rec_results.append(clustering_recursive(ctx, sub_cons, sub_seqs, sub_ops, sub_str, state, hmm, sub_cfg))
+    total_score = sum(x[2] for x in rec_results) + score
+    cluster_nums = [x[3] for x in rec_results]
+    total_k = sum(cluster_nums)
+    offsets = list(np.cumsum([0] + cluster_nums[:-1]))
+    pointers = [0] * BRANCH_NUM
+    merged_asn, merged_post = [], []
+    for a, ps in zip(asn, pss):
+        in_asn = rec_results[a][0][pointers[a]]
+        in_ps = rec_results[a][1][pointers[a]]
+        pointers[a] += 1
+        merged_asn.append(int(offsets[a]) + in_asn)
+        posterior: List[float] = []
+        for p, num in zip(ps, cluster_nums):
+            posterior.extend([p - math.log(num)] * num)
+        for t, p in enumerate(in_ps):
+            posterior[t + int(offsets[a])] += p + math.log(cluster_nums[a])
+        assert abs(1.0 - sum(math.exp(x) for x in posterior)) < 1e-4   # mod.rs:185
+        merged_post.append(posterior)
+    return merged_asn, merged_post, total_score, total_k
+
+
+def estimate_model_parameters_on_both_strands(ds: DataSet, ctx=None, rounds: int = TRAIN_ROUND) -> PairHiddenMarkovModelOnStrands:
+    """model_tune.rs:96-156: chunks with coverage within median +-2, first five by id; per round polish every pile-up
+    with the current models (HMMPolishConfig(bw/2, n, 0)), then one Baum-Welch step over all of them (radius max bw / 2)."""
+    ctx = ctx or default_context()
+    chunks = {c.id: c for c in ds.selected_chunks}
+    models = ds.model or PairHiddenMarkovModelOnStrands.default()
+    models = PairHiddenMarkovModelOnStrands.new(models.forward(), models.reverse())
+    pile: Dict[int, List[Node]] = {k: [] for k in chunks}
+    for n in ds.nodes:
+        pile.setdefault(n.chunk, []).append(n)
+    covs = sorted(len(v) for v in pile.values())
+    cov = covs[len(pile) // 2]
+    filtered = sorted((k, v) for k, v in pile.items() if max(cov, 2) - 2 <= len(v) < cov + 2)[:TRAIN_UNIT_SIZE]
+    pairs = []
+    for uid, nodes in filtered:
+        if uid not in chunks:
+            continue
+        bw = band_width(ds.read_type, len(chunks[uid].seq))
+        pairs.append([np.array(chunks[uid].seq, copy=True), [n.seq for n in nodes], [np.array(n.ops, copy=True) for n in nodes],
+                      [n.is_forward for n in nodes], bw])
+    assert pairs, "no pile-up to train on"
+    bw = max(p[4] for p in pairs)
+    for _ in range(rounds):
+        # the five polishes of a round are independent: one batch per distinct radius
+        for radius in sorted({p[4] // 2 for p in pairs}):
+            grp = [p for p in pairs if p[4] // 2 == radius]
+            drafts = [p[0] for p in grp]
+            reads = [r for p in grp for r in p[1]]
+            ops = [o for p in grp for o in p[2]]
+            strands = [s for p in grp for s in p[3]]
+            tidx = np.repeat(np.arange(len(grp), dtype=np.uint32), [len(p[1]) for p in grp])
+            cons, new_ops, _ = polish_chunks(models, drafts, reads, ops, strands, tidx,
+                                             HMMPolishConfig.new(radius, max(len(p[1]) for p in grp), 0), ctx=ctx)
+            k = 0
+            for g, p in enumerate(grp):
+                p[0] = cons[g]
+                p[2] = new_ops[k:k + len(p[1])]
+                k += len(p[1])
+        packs = [(p[0], p[3], p[1], p[2]) for p in pairs]   # TrainingDataPack::new(cons, strands, seqs, ops)
+        fit_antidiagonal_par_multiple(models, packs, bw // 2, ctx=ctx)
+    return models
+
+
+def local_clustering_selected(ds: DataSet, selection: Iterable[int], gains: Optional[Gains] = None, ctx=None,
+                              fit_models: bool = True, rank: int = 0, world: int = 1, group=None) -> Optional[Dict[int, tuple]]:
+    """local_clustering/mod.rs:56-83.  Mutates `ds` on rank 0 (chunk.seq / score / cluster_num, node.cluster / posterior /
+    ops) and returns {chunk id: (consensus, score, cluster_num)} there; other ranks return None.
+    gains=None runs likelihood_gains::estimate_gain_default on the GPU (mod.rs:60)."""
+    ctx = ctx or default_context()
+    selection = set(selection)
+    update_coverage(ds)
+    if fit_models:
+        ds.model = estimate_model_parameters_on_both_strands(ds, ctx=ctx)           # mod.rs:58
+    hmm = ds.model or PairHiddenMarkovModelOnStrands.default()
+    if gains is None:
+        from .likelihood_gains import estimate_gain_default
+        gains = estimate_gain_default(hmm, ctx=ctx)
+    coverage = float(ds.coverage)
+    pile = {cid: pc for cid, pc in pileup_nodes(ds, selection).items() if pc[0]}
+    ids = sorted(pile)
+    weights = [scheduler.chunk_weight(len(pile[c][0]), len(pile[c][1].seq), float(np.mean([len(n.seq) for n in pile[c][0]])),
+                                      band_width(ds.read_type, len(pile[c][1].seq)) // 2) for c in ids]
+
+    def process(my_ids: List[int]) -> Dict[int, tuple]:
+        return _cluster_pileups(ctx, hmm, gains, coverage, ds.read_type, {c: pile[c] for c in my_ids})
+
+    merged = scheduler.run_sharded(ids, weights, process, rank, world, group=group)
+    if merged is None:
+        return None
+    out = {}
+    for cid, (cons, score, k, asn, post, ops) in merged.items():
+        nodes, chunk = pile[cid]
+        for n, a, p, o in zip(nodes, asn, post, ops):                              # update_by_clusterings (mod.rs:244-260)
+            n.posterior = np.array(p)
+            n.cluster = int(a)
+            n.ops = o
+        chunk.seq, chunk.score, chunk.cluster_num = cons, score, k                 # mod.rs:74-81
+        out[cid] = (cons, score, k)
+    normalize_local_clustering(ds)
+    return out
+
+
+def _cluster_pileups(ctx, hmm, gains: Gains, coverage: float, read_type: str, pile: Dict[int, Tuple[List[Node], Chunk]]):
+    """clustering_on_pileup (mod.rs:86-123) for a set of pile-ups: one polish batch and one table batch per radius."""
+    res: Dict[int, tuple] = {}
+    by_radius: Dict[int, List[int]] = {}
+    for cid, (nodes, chunk) in pile.items():
+        by_radius.setdefault(band_width(read_type, len(chunk.seq)) // 2, []).append(cid)
+    for radius, cids in by_radius.items():
+        cids.sort()
+        drafts = [pile[c][1].seq for c in cids]
+        reads = [n.seq for c in cids for n in pile[c][0]]
+        ops = [n.ops for c in cids for n in pile[c][0]]
+        strands = [n.is_forward for c in cids for n in pile[c][0]]
+        counts = [len(pile[c][0]) for c in cids]
+        tidx = np.repeat(np.arange(len(cids), dtype=np.uint32), counts)
+        # HMMPolishConfig::new(band_width / 2, seqs.len(), 3): every read of a chunk votes (mod.rs:105)
+        cons, new_ops, _ = polish_chunks(hmm, drafts, reads, ops, strands, tidx, HMMPolishConfig.new(radius, max(counts), 3), ctx=ctx)
+        first = np.concatenate([[0], np.cumsum(counts)])
+        cfgs = []
+        for g, c in enumerate(cids):
+            cp, n = pile[c][1].copy_num, counts[g]
+            per_cluster = n / cp if cp <= 2 else max(n / cp, coverage)   # mod.rs:108-111 (copy_num 0 divides by zero there too)
+            cfgs.append(ClusteringConfig.new(radius, cp, coverage, per_cluster, gains))
+        # chunks below UPPER_COPY_NUM: one 9-row table batch + device-side filter_profiles for all of them
+        small = [g for g, c in enumerate(cids) if 2 <= cfgs[g].copy_num < UPPER_COPY_NUM]
+        firsts: Dict[int, ClusteringResult] = {}
+        if small:
+            sub_reads = [reads[k] for g in small for k in range(first[g], first[g + 1])]
+            sub_ops = [new_ops[k] for g in small for k in range(first[g], first[g + 1])]
+            sub_str = [strands[k] for g in small for k in range(first[g], first[g + 1])]
+            sub_idx = np.repeat(np.arange(len(small), dtype=np.uint32), [counts[g] for g in small])
+            b = ctx.batch([cons[g] for g in small], sub_reads, sub_ops, np.asarray(sub_str, dtype=np.uint8), sub_idx, radius)
+            try:
+                b.modtable(hmm.forward().to_c(), hmm.reverse().to_c(), 9)
+                n_probes, probe_pos, variants = b.search_variants(gains.gain, gains.prob,
+                                                                  np.array([cfgs[g].copy_num for g in small], dtype=np.int32), coverage)
+            finally:
+                b.close()
+            off = np.concatenate([[0], np.cumsum([counts[g] for g in small])])
+            for s, g in enumerate(small):
+                d = int(n_probes[s])
+                state = _rng_seed(pile[cids[g]][1].id * 3490)                       # mod.rs:97
+                firsts[g] = _clustering_variants_rng(variants[off[s]:off[s + 1], :max(d, 1)], probe_pos[s, :d], cons[g],
+                                                     cfgs[g], state)
+        for g, c in enumerate(cids):
+            sl = slice(first[g], first[g + 1])
+            state = _rng_seed(pile[c][1].id * 3490)
+            asn, post, score, k = clustering_recursive(ctx, cons[g], reads[sl], new_ops[sl], strands[sl], state, hmm, cfgs[g],
+                                                       first=firsts.get(g))
+            res[c] = (cons[g], score, k, asn, post, new_ops[sl])
+    return res
