@@ -172,6 +172,33 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def phase_leg(ctx, templates, reads, ops, strands, tidx, n_chunks, cov):
+    """'chunks phased per second' (BASELINE.json metric, second half): the whole per-chunk path of
+    local_clustering_selected (local_clustering/mod.rs:56-83 without the model fit) on the first n_chunks chunks --
+    batched polish, 9-row tables, device-side filter_profiles, host greedy pick + k-means + MCMC, posteriors,
+    normalisation -- through jtk_b200/pipeline.py.  Wall clock; rank 0 only."""
+    from jtk_b200 import pipeline as P
+    from jtk_b200 import local_clustering as LC
+    gains = LC.Gains(gain=GAINS_EXPECTED.astype(np.float64), prob=GAINS_PROB)
+
+    def dataset(chunk_ids):
+        chunks = [P.Chunk(id=int(c) + 1, seq=templates[c].copy(), copy_num=2) for c in chunk_ids]
+        nodes = [P.Node(chunk=int(tidx[k]) + 1, seq=reads[k], ops=ops[k], is_forward=bool(strands[k]))
+                 for k in range(len(reads)) if int(tidx[k]) in set(chunk_ids)]
+        return P.DataSet(selected_chunks=chunks, nodes=nodes, read_type="ONT")
+
+    warm = dataset(list(range(min(2, n_chunks))))
+    P.local_clustering_selected(warm, {c.id for c in warm.selected_chunks}, gains=gains, ctx=ctx, fit_models=False)
+    ds = dataset(list(range(n_chunks)))
+    t0 = time.perf_counter()
+    out = P.local_clustering_selected(ds, {c.id for c in ds.selected_chunks}, gains=gains, ctx=ctx, fit_models=False)
+    dt = time.perf_counter() - t0
+    ks = [out[c][2] for c in sorted(out)]
+    return {"phases_s": {k: round(v, 4) for k, v in P.LAST_TIMING.items()}, "chunks_per_s": n_chunks / dt, "chunks": n_chunks, "seconds": dt, "host_threads": P.host_threads(),
+            "two_cluster_chunks": int(sum(1 for k in ks if k == 2)),
+            "what": "polish + 9-row tables + device filter_profiles + host pick/k-means/MCMC + normalise, 1 GPU"}
+
+
 def workload_config(args):
     return {"workload": f"BASELINE.json configs[1]: mock diploid {args.chunks * 2.5:.0f} kbp region, {args.chunks} chunks x "
                         f"{args.reads} ONT-like reads ({args.length} bp, 8% error), radius {RADIUS}, 14-row table + column stats, per GPU",
@@ -191,6 +218,7 @@ def main():
     ap.add_argument("--reads", type=int, default=60)
     ap.add_argument("--length", type=int, default=2000)
     ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="pairs in the cpu_baseline sample (0: auto)")
+    ap.add_argument("--phase-chunks", type=int, default=80, help="chunks of the 'chunks phased per second' extra (0: skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -286,6 +314,11 @@ def main():
     barrier()
     e2e_ms = (time.perf_counter() - t1) * 1e3 / e2e_steps
 
+    # ---- chunks phased per second through the driver (extra; rank 0's GPU, host clustering on all cores) -----------
+    phased = None
+    if args.phase_chunks > 0 and rank == 0:
+        phased = phase_leg(ctx, templates, reads, ops, strands, tidx, min(args.phase_chunks, args.chunks), cov)
+
     # ---- reduce over ranks ------------------------------------------------------------------------
     step_ms = dev_ms / args.steps
     tot_cells = float(cells)
@@ -341,7 +374,8 @@ def main():
                       "pairs_per_s": world * len(reads) / (step_ms * 1e-3),
                       "wall_ms_per_step": wall_step,
                       "rows9": {"ms_per_step": ms9, "gcups": cells / (ms9 * 1e-3) / 1e9,
-                                "chunks_per_s": args.chunks / (ms9 * 1e-3), "note": "rank 0 only"}},
+                                "chunks_per_s": args.chunks / (ms9 * 1e-3), "note": "rank 0 only"},
+                      "chunks_phased": phased},
         }
         print(json.dumps(line), flush=True)
     batch.close()

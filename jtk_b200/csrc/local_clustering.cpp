@@ -414,31 +414,75 @@ static void flip(const Mat &data, std::vector<size_t> &assign, size_t idx, size_
     for (size_t d = 0; d < data[idx].size(); d++) lks[to][d].add(data[idx][d]);
 }
 
-static double mcmc_with_filter(const Mat &data, std::vector<size_t> &assign, size_t k, double cov, Rng &rng) { // :704-762
+// mcmc_with_filter (:704-762).  Same proposals, same arithmetic in the same order as the reference; the state lives in
+// flat arrays that are allocated once per call (the per-proposal get_lk of the restatement above allocates nothing here).
+static double mcmc_with_filter(const Mat &data, std::vector<size_t> &assign, size_t k, double cov, Rng &rng) {
+    const size_t n = data.size(), D = n ? data[0].size() : 0;
     std::vector<double> size_to_lk;
-    for (size_t x = 0; x <= data.size(); x++) size_to_lk.push_back(max_poisson_lk(x, cov, 1, k));
+    for (size_t x = 0; x <= n; x++) size_to_lk.push_back(max_poisson_lk(x, cov, 1, k));
     for (double x : size_to_lk) JTK_ASSERT(!std::isnan(x), "is_valid_lk");
-    LKs lks; std::vector<size_t> clusters;
-    build_lks(data, assign, k, lks, clusters);
-    double lk = get_lk(lks, clusters, size_to_lk);
+    std::vector<double> flat(n * D);
+    for (size_t i = 0; i < n; i++) { JTK_ASSERT(data[i].size() == D, "ragged variants"); for (size_t d = 0; d < D; d++) flat[i * D + d] = data[i][d]; }
+    std::vector<LKCount> lks(k * D);
+    std::vector<size_t> clusters(k, 0);
+    std::vector<uint8_t> use(D);
+    for (size_t i = 0; i < n; i++) {
+        clusters[assign[i]]++;
+        for (size_t d = 0; d < D; d++) lks[assign[i] * D + d].add(flat[i * D + d]);
+    }
+    // LKCount::is_informative's ratio test (0.70 < num_pos / (num_pos + num_neg + 1e-7)) for every pair of counts,
+    // evaluated once with the reference's own expression: the proposal loop looks it up instead of dividing
+    std::vector<uint8_t> ratio_ok((n + 1) * (n + 1));
+    for (size_t p = 0; p <= n; p++)
+        for (size_t q = 0; q + p <= n; q++) ratio_ok[p * (n + 1) + q] = 0.70 < (double)p / ((double)(p + q) + 0.0000001);
+    auto informative = [&](const LKCount &x) { return 0.0 < x.total_gain && ratio_ok[x.num_pos * (n + 1) + x.num_neg] != 0; };
+    auto current_lk = [&]() -> double { // get_lk (:785-795) with get_used_columns (:847-869)
+        for (size_t d = 0; d < D; d++) {
+            bool u = false;
+            for (size_t c = 0; c < k; c++) u = u | informative(lks[c * D + d]);
+            size_t in_use = 0, in_neg = 0;
+            for (size_t c = 0; c < k; c++) {
+                const LKCount &x = lks[c * D + d];
+                if (0.0 < x.total_gain) in_use += x.num_pos;
+                if (x.total_gain <= 0.0) in_neg += x.num_pos;
+            }
+            use[d] = u & ((double)in_neg * 2.0 < (double)in_use);
+        }
+        double lk = 0;
+        for (size_t c = 0; c < k; c++) lk += size_to_lk[clusters[c]];
+        for (size_t c = 0; c < k; c++)
+            for (size_t d = 0; d < D; d++) if (use[d]) lk += std::max(lks[c * D + d].total_gain, 0.0);
+        return lk;
+    };
+    auto do_flip = [&](size_t idx, size_t to) { // flip (:764-783)
+        const size_t from = assign[idx];
+        const double *row = &flat[idx * D];
+        clusters[from]--;
+        for (size_t d = 0; d < D; d++) lks[from * D + d].sub(row[d]);
+        assign[idx] = to;
+        clusters[to]++;
+        for (size_t d = 0; d < D; d++) lks[to * D + d].add(row[d]);
+    };
+    double lk = current_lk();
     double mx = lk;
     std::vector<size_t> argmax = assign;
-    const size_t total = 2000 * data.size();
+    const size_t total = 2000 * n;
     for (size_t t = 0; t < total; t++) {
-        const size_t idx = rng.gen_range(data.size());
+        const size_t idx = rng.gen_range(n);
         const size_t old = assign[idx];
         const size_t nw = rng.choose_other(k, old);
-        flip(data, assign, idx, nw, lks, clusters);
-        const double proposed = get_lk(lks, clusters, size_to_lk);
+        do_flip(idx, nw);
+        const double proposed = current_lk();
         const double diff = proposed - lk;
         if (0.0 < diff || rng.gen_bool(std::exp(diff))) {
             lk = proposed;
-            if (mx < lk) { mx = proposed; argmax = assign; }
-        } else flip(data, assign, idx, old, lks, clusters);
+            if (mx < lk) { mx = proposed; std::copy(assign.begin(), assign.end(), argmax.begin()); }
+        } else do_flip(idx, old);
     }
     assign = argmax;
-    build_lks(data, assign, k, lks, clusters);
-    const double chk = get_lk(lks, clusters, size_to_lk);
+    LKs chk_lks; std::vector<size_t> chk_clusters;
+    build_lks(data, assign, k, chk_lks, chk_clusters);
+    const double chk = get_lk(chk_lks, chk_clusters, size_to_lk);
     JTK_ASSERT(std::fabs(mx - chk) < 0.0001, "(max - lk).abs() < 0.0001");
     return mx;
 }

@@ -333,9 +333,22 @@ def local_clustering_selected(ds: DataSet, selection: Iterable[int], gains: Opti
     return out
 
 
+LAST_TIMING: Dict[str, float] = {}  # seconds spent in the phases of the last _cluster_pileups call (diagnostics)
+
+
+def host_threads() -> int:
+    """Threads of the per-chunk host loops (k-means / MCMC): the reference's rayon pool (`-t`, cli/src/bin/jtk.rs:396-408)."""
+    import os
+    return max(1, min(int(os.environ.get("JTK_HOST_THREADS", os.cpu_count() or 1)), 64))
+
+
 def _cluster_pileups(ctx, hmm, gains: Gains, coverage: float, read_type: str, pile: Dict[int, Tuple[List[Node], Chunk]]):
-    """clustering_on_pileup (mod.rs:86-123) for a set of pile-ups: one polish batch and one table batch per radius."""
+    """clustering_on_pileup (mod.rs:86-123) for a set of pile-ups: one polish batch and one table batch per radius; the
+    host clustering of the chunks runs on a thread pool (the C call releases the GIL), one task per chunk as rayon does."""
+    from concurrent.futures import ThreadPoolExecutor
+    import time
     res: Dict[int, tuple] = {}
+    tm = {"polish": 0.0, "tables_filter": 0.0, "host_clustering": 0.0, "recursive": 0.0}
     by_radius: Dict[int, List[int]] = {}
     for cid, (nodes, chunk) in pile.items():
         by_radius.setdefault(band_width(read_type, len(chunk.seq)) // 2, []).append(cid)
@@ -348,7 +361,9 @@ def _cluster_pileups(ctx, hmm, gains: Gains, coverage: float, read_type: str, pi
         counts = [len(pile[c][0]) for c in cids]
         tidx = np.repeat(np.arange(len(cids), dtype=np.uint32), counts)
         # HMMPolishConfig::new(band_width / 2, seqs.len(), 3): every read of a chunk votes (mod.rs:105)
+        t0 = time.perf_counter()
         cons, new_ops, _ = polish_chunks(hmm, drafts, reads, ops, strands, tidx, HMMPolishConfig.new(radius, max(counts), 3), ctx=ctx)
+        tm["polish"] += time.perf_counter() - t0
         first = np.concatenate([[0], np.cumsum(counts)])
         cfgs = []
         for g, c in enumerate(cids):
@@ -359,6 +374,7 @@ def _cluster_pileups(ctx, hmm, gains: Gains, coverage: float, read_type: str, pi
         small = [g for g, c in enumerate(cids) if 2 <= cfgs[g].copy_num < UPPER_COPY_NUM]
         firsts: Dict[int, ClusteringResult] = {}
         if small:
+            t0 = time.perf_counter()
             sub_reads = [reads[k] for g in small for k in range(first[g], first[g + 1])]
             sub_ops = [new_ops[k] for g in small for k in range(first[g], first[g + 1])]
             sub_str = [strands[k] for g in small for k in range(first[g], first[g + 1])]
@@ -371,15 +387,27 @@ def _cluster_pileups(ctx, hmm, gains: Gains, coverage: float, read_type: str, pi
             finally:
                 b.close()
             off = np.concatenate([[0], np.cumsum([counts[g] for g in small])])
-            for s, g in enumerate(small):
+            tm["tables_filter"] += time.perf_counter() - t0
+            t0 = time.perf_counter()
+
+            def one(sg):
+                s, g = sg
                 d = int(n_probes[s])
                 state = _rng_seed(pile[cids[g]][1].id * 3490)                       # mod.rs:97
-                firsts[g] = _clustering_variants_rng(variants[off[s]:off[s + 1], :max(d, 1)], probe_pos[s, :d], cons[g],
-                                                     cfgs[g], state)
+                return g, _clustering_variants_rng(variants[off[s]:off[s + 1], :max(d, 1)], probe_pos[s, :d], cons[g],
+                                                   cfgs[g], state)
+            with ThreadPoolExecutor(max_workers=host_threads()) as pool:
+                for g, r in pool.map(one, list(enumerate(small))):
+                    firsts[g] = r
+            tm["host_clustering"] += time.perf_counter() - t0
+        t0 = time.perf_counter()
         for g, c in enumerate(cids):
             sl = slice(first[g], first[g + 1])
             state = _rng_seed(pile[c][1].id * 3490)
             asn, post, score, k = clustering_recursive(ctx, cons[g], reads[sl], new_ops[sl], strands[sl], state, hmm, cfgs[g],
                                                        first=firsts.get(g))
             res[c] = (cons[g], score, k, asn, post, new_ops[sl])
+        tm["recursive"] += time.perf_counter() - t0
+    LAST_TIMING.clear()
+    LAST_TIMING.update(tm)
     return res
