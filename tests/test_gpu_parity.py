@@ -172,3 +172,53 @@ def test_kiley_shaped_single_call(ctx):
     assert np.max(np.abs((table - lk) - (otab - olk))[ok]) < 2e-3
     lkb = m.likelihood_antidiagonal_bootstrap(t, q, 20, ctx=ctx)
     assert abs(lkb - O.likelihood_bootstrap(O.default_hmm(), t, q, 20)) < 2e-5 * abs(olk)
+
+
+def test_very_long_pair_takes_the_generic_backward_path(ctx):
+    """Maximum sizes: a 8.4 kbp chunk (4x the pipeline's chunk length) has more anti-diagonals than the rescale-event
+    map covers, so every backward block takes the generic (exact-correction) step; results still match the oracle."""
+    rng = np.random.default_rng(99)
+    t = synth.random_template(rng, 8400)
+    fwd, rev = O.default_hmm(), random_hmm(3)
+    reads, ops = [], []
+    for _ in range(3):
+        q, o = synth.mutate_read(rng, t, 0.08)
+        reads.append(q); ops.append(o)
+    assert len(t) + min(len(q) for q in reads) + 1 > 4 * 4096
+    strands = np.array([1, 0, 1], np.uint8)
+    lk, tabs = ctx.modtable_batch(to_c(fwd), to_c(rev), [t], reads, ops, strands, np.zeros(3, np.uint32), 30)
+    otabs, olk = O.modification_table_batch(fwd, rev, [t] * 3, reads, ops, strands, 30, n_threads=3)
+    check_tables(tabs, lk, otabs, olk, [t], np.zeros(3, np.uint32))
+
+
+def test_full_size_properties_without_the_oracle(ctx):
+    """BASELINE.json full size (2 kbp x 60 reads x several chunks) through size-independent properties: the identity
+    substitution is exactly 0 in every profile, the 9-row kernel equals the 14-row kernel on the rows it computes, both
+    agree on the likelihood, and rows that are impossible by construction are flagged as such."""
+    chunks = synth.diploid_region(5, 6, length=2000, n_reads=60, error_rate=0.08)
+    templates = [c["template"] for c in chunks]
+    reads = [r for c in chunks for r in c["reads"]]
+    ops = [o for c in chunks for o in c["ops"]]
+    strands = np.concatenate([c["strands"] for c in chunks])
+    tidx = np.repeat(np.arange(6, dtype=np.uint32), 60)
+    h = to_c(O.default_hmm())
+    b = ctx.batch(templates, reads, ops, strands, tidx, 30)
+    b.modtable(h, h, 14)
+    lk14 = b.lk()
+    prof14 = {p: b.profile(p).reshape(-1, 14) for p in (0, 59, 60, 201, 359)}
+    b.modtable(h, h, 9)
+    lk9 = b.lk()
+    assert np.array_equal(lk14, lk9)
+    assert (lk14 < -200).all() and (lk14 > -3000).all()
+    for p, a in prof14.items():
+        c = b.profile(p).reshape(-1, 14)
+        rows = [0, 1, 2, 3, 4, 5, 6, 7, 11]
+        assert np.array_equal(a[:, rows], c[:, rows])
+        assert (c[:, [8, 9, 10, 12, 13]] < -1e9).all()
+        t = templates[int(tidx[p])]
+        code = np.searchsorted(synth.ACGT, t)
+        assert (a[np.arange(len(t)), code] == 0.0).all()
+        assert (a[len(t), :4] < -1e9).all() and (a[len(t) - 1, 12:] < -1e9).all()  # no base to substitute / too few to delete
+        # a read of its own haplotype rarely gains more than a few nats from any single edit, and never loses nothing
+        assert a[a > -1e9].max() < 40 and a[a > -1e9].min() < -5
+    b.close()

@@ -66,3 +66,29 @@ def test_gpu_polish_many_chunks():
         assert bytes(cons[c]) == bytes(want_cons) and iters[c] == want_it
         for k in range(16):
             assert new_ops[c * 16 + k].tolist() == want_ops[k].tolist()
+
+
+@pytest.mark.gpu
+def test_consensus_window_polish_repairs_drafts():
+    """consensus::polish_seg's HMM step for several windows in one batch (consensus/mod.rs:445-496): drafts with planted
+    errors converge to the truth, ops keep spanning (draft, read)."""
+    from jtk_b200 import consensus, hmm
+    rng = np.random.default_rng(12)
+    models = hmm.PairHiddenMarkovModelOnStrands.default()
+    drafts, windows, truths = [], [], []
+    for w in range(4):
+        truth = synth.random_template(rng, 500 + 20 * w)
+        d = truth.copy()
+        for p in (60, 200, 333):
+            d[p] = synth.ACGT[(np.searchsorted(synth.ACGT, d[p]) + 1 + w % 3) % 4]
+        d = np.delete(d, 410)
+        seqs, ops, strands = [], [], []
+        for _ in range(14):
+            q, _o = synth.mutate_read(rng, truth, 0.07)
+            seqs.append(q); ops.append(O.edit_ops(d, q, 40)); strands.append(bool(rng.random() < 0.5))
+        drafts.append(d); windows.append((seqs, ops, strands)); truths.append(truth)
+    radius = consensus.polish_radius(60)
+    assert radius == 50
+    cons, new_ops = consensus.polish_windows(models, drafts, windows, radius, 50)
+    for c, t in zip(cons, truths):
+        assert np.array_equal(c, t)
