@@ -17,7 +17,9 @@
 
 namespace jtk {
 int cols_per_lane_for_radius(int radius);
-cudaError_t launch_modtable(const KParams &p, int C, int grid, cudaStream_t st);
+cudaError_t launch_modtable(const KParams &p, int C, int grid_fwd, int grid_bwd, cudaStream_t st);
+int fwdrows_ctas_per_sm(int C);
+int fwdinfo_words();
 cudaError_t launch_likelihood(const KParams &p, int C, int grid, cudaStream_t st);
 int warps_per_cta();
 int frow_slots_per_row(int C);
@@ -189,6 +191,8 @@ struct jtk_ctx {
     DevBuf<float> d_models;
     DevBuf<float2> d_frows;   // per-warp forward rows (scratch shared by all batches of this ctx)
     DevBuf<int32_t> d_kf;
+    DevBuf<unsigned> d_fwdinfo;   // per pair slot: end sums, total exponent, rescale-event map (forward -> backward kernel)
+    size_t scratch_bytes = (size_t)16 << 30; // forward-row scratch budget of one wave (JTK_SCRATCH_MB)
     DevBuf<int> d_counter;
     DevBuf<float> d_minreq;
     DevBuf<uint32_t> d_cols;
@@ -249,6 +253,7 @@ int jtk_ctx_create(int device, size_t workspace_bytes, jtk_ctx **out) {
         int nt = (int)std::thread::hardware_concurrency();
         if (const char *env = std::getenv("JTK_HOST_THREADS")) nt = std::atoi(env);
         ctx->host_threads = std::max(1, std::min(nt, 32));
+        if (const char *env = std::getenv("JTK_SCRATCH_MB")) ctx->scratch_bytes = (size_t)std::max(64, std::atoi(env)) << 20;
     }
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
@@ -264,7 +269,7 @@ int jtk_ctx_create(int device, size_t workspace_bytes, jtk_ctx **out) {
 void jtk_ctx_destroy(jtk_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    ctx->d_models.release(); ctx->d_frows.release(); ctx->d_kf.release(); ctx->d_counter.release();
+    ctx->d_models.release(); ctx->d_frows.release(); ctx->d_kf.release(); ctx->d_fwdinfo.release(); ctx->d_counter.release();
     ctx->d_minreq.release(); ctx->d_cols.release(); ctx->d_gather.release();
     ctx->d_tabs.release(); ctx->d_tab_off.release(); ctx->d_cand.release(); ctx->h_cand.release(); ctx->h_gather.release();
     ctx->h_pairs.release(); ctx->h_codes.release(); ctx->h_bits.release(); ctx->h_delta.release(); ctx->h_lk.release();
@@ -591,29 +596,34 @@ int batch_run(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev
     pack_model(fwd, models);
     pack_model(rev, models + kModelFloats);
     const int wpc = warps_per_cta();
-    int grid = (b->n_pairs + wpc - 1) / wpc;
-    // persistent CTAs: one wave of resident CTAs pulls pairs from the queue
-    const int max_grid = ctx->sm_count * (table ? modtable_ctas_per_sm(b->C) : 4);
-    if (grid > max_grid) grid = max_grid;
     cudaStream_t st = ctx->stream;
     KParams kp{};
     CU(ctx->d_models.reserve(2 * kModelFloats), "cudaMalloc models");
-    CU(ctx->d_counter.reserve(1), "cudaMalloc counter");
+    CU(ctx->d_counter.reserve(2), "cudaMalloc counter");
+    // The modification table runs as waves of (forward kernel, backward kernel); the forward rows of every pair of a wave
+    // live in HBM between the two kernels (2.3 MB per 2 kbp pair), so a wave holds as many pairs as the scratch budget allows.
+    int per_wave = b->n_pairs;
     if (table) {
-        const size_t slots = (size_t)grid * wpc;
         kp.frow_stride = (size_t)(b->max_nd + frow_extra_rows()) * frow_slots_per_row(b->C);
         kp.kf_stride = (size_t)b->max_nd + 6;
-        CU(ctx->d_frows.reserve(slots * kp.frow_stride), "cudaMalloc forward rows");
-        CU(ctx->d_kf.reserve(slots * kp.kf_stride), "cudaMalloc scale exponents");
+        kp.fwdinfo_stride = (size_t)fwdinfo_words();
+        const size_t per_pair = kp.frow_stride * sizeof(float2) + kp.kf_stride * sizeof(int32_t) + kp.fwdinfo_stride * 4;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const size_t have = ctx->d_frows.cap * sizeof(float2);
+        size_t budget = std::min(ctx->scratch_bytes, (free_b + have) / 2);
+        per_wave = (int)std::max<size_t>(1, std::min<size_t>((size_t)b->n_pairs, budget / per_pair));
+        CU(ctx->d_frows.reserve((size_t)per_wave * kp.frow_stride), "cudaMalloc forward rows");
+        CU(ctx->d_kf.reserve((size_t)per_wave * kp.kf_stride), "cudaMalloc scale exponents");
+        CU(ctx->d_fwdinfo.reserve((size_t)per_wave * kp.fwdinfo_stride), "cudaMalloc forward info");
         CU(b->d_delta.reserve((size_t)b->table_floats), "cudaMalloc profiles");
     }
     CU(cudaMemcpyAsync(ctx->d_models.p, models, sizeof(models), cudaMemcpyHostToDevice, st), "H2D models");
-    CU(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(int), st), "memset counter");
     kp.pairs = b->d_pairs.p; kp.n_pairs = b->n_pairs;
     kp.codes = b->d_codes.p; kp.bits = b->d_bits.p; kp.models = ctx->d_models.p;
     kp.radius = b->radius; kp.rows = rows;
-    kp.frows = ctx->d_frows.p; kp.kf = ctx->d_kf.p;
-    kp.out_delta = b->d_delta.p; kp.out_lk = b->d_lk.p; kp.counter = ctx->d_counter.p;
+    kp.frows = ctx->d_frows.p; kp.kf = ctx->d_kf.p; kp.fwdinfo = ctx->d_fwdinfo.p;
+    kp.out_delta = b->d_delta.p; kp.out_lk = b->d_lk.p; kp.counter = ctx->d_counter.p; kp.counter2 = ctx->d_counter.p + 1;
     cudaEvent_t r0 = nullptr, r1 = nullptr;
     if (ctx->ring_n < jtk_ctx::kRing) {
         const int k = ctx->ring_n;
@@ -623,8 +633,23 @@ int batch_run(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev
     }
     CU(cudaEventRecord(ctx->ev0, st), "event");
     if (r0) CU(cudaEventRecord(r0, st), "event");
-    CU(table ? launch_modtable(kp, b->C, grid, st) : launch_likelihood(kp, b->C, grid, st), "kernel launch");
-    ctx->launches++;
+    for (int lo = 0; lo < b->n_pairs; lo += per_wave) {
+        const int hi = std::min(b->n_pairs, lo + per_wave);
+        const int ctas = (hi - lo + wpc - 1) / wpc;
+        CU(cudaMemsetAsync(ctx->d_counter.p, 0, 2 * sizeof(int), st), "memset counter");
+        kp.pair_lo = lo; kp.pair_hi = hi;
+        if (table) {
+            // persistent CTAs: one wave of resident CTAs pulls pairs from the queue
+            const int gf = std::min(ctas, ctx->sm_count * fwdrows_ctas_per_sm(b->C));
+            const int gb = std::min(ctas, ctx->sm_count * modtable_ctas_per_sm(b->C));
+            CU(launch_modtable(kp, b->C, gf, gb, st), "kernel launch");
+            ctx->launches += 2;
+        } else {
+            kp.n_pairs = b->n_pairs;
+            CU(launch_likelihood(kp, b->C, std::min(ctas, ctx->sm_count * 4), st), "kernel launch");
+            ctx->launches++;
+        }
+    }
     if (r1) CU(cudaEventRecord(r1, st), "event");
     CU(cudaEventRecord(ctx->ev1, st), "event");
     ctx->timing_pending = true;

@@ -47,7 +47,12 @@ struct KParams {
     size_t kf_stride;       // max_nd + 6
     float *out_delta;       // table - lk, fp32, kDeltaNeg for impossible edits
     double *out_lk;
-    int *counter;           // work queue head
+    int *counter;           // work queue head (forward kernel / single-kernel paths)
+    // modification table = two kernels (forward rows, then backward + table): the scratch is per PAIR of a wave
+    int pair_lo, pair_hi;   // pairs [pair_lo, pair_hi) of this wave; scratch slot = pair index - pair_lo
+    unsigned *fwdinfo;      // per pair slot: [0..3] ftot (float bits), [4] Ktot, [8..] rescale-event map
+    size_t fwdinfo_stride;  // words per pair slot
+    int *counter2;          // work queue head of the backward kernel
 };
 
 } // namespace jtk

@@ -633,45 +633,81 @@ __device__ __forceinline__ PairCtx make_pair_ctx(const KParams &p, const DevPair
 
 template <int C> constexpr int ring_floats2() { return (kRingRows + 2 * kRingMargin) * (32 * C + 2 * kHalo); }
 
+constexpr int kInfoEv = 8; // word offset of the rescale-event map inside a pair's fwdinfo block
+
+// Kernel 1 of the modification table: forward pass of every pair of the wave.  Writes the forward rows (toM, toD of every
+// cell), the cumulative scale exponent of every row, the rescale-event map, the four end sums and the likelihood.
+// Light on registers (no table accumulators), so it runs at a much higher occupancy than the backward kernel.
+template <int C>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 5) fwdrows_kernel(KParams p) {
+    __shared__ SmemLayout sh;
+    fill_tables(sh, p.models);
+    constexpr int NSLOT = 32 * C;
+    constexpr int RS = NSLOT + 2 * kHalo;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (;;) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(p.counter, 1);
+        k = __shfl_sync(kFull, k, 0);
+        const int pi = p.pair_lo + k;
+        if (pi >= p.pair_hi) break;
+        const DevPair P = p.pairs[pi];
+        const PairCtx pc = make_pair_ctx(p, P, sh);
+        const Coef a = load_coef(sh.trans[P.model], sh.cpair[P.model]);
+        float2 *frow = p.frows + (size_t)k * p.frow_stride + kRowShift * RS; // row 0 (kRowShift zero rows below)
+        int32_t *kf = p.kf + (size_t)k * p.kf_stride + 3;
+        unsigned *info = p.fwdinfo + (size_t)k * p.fwdinfo_stride;
+        for (int w = lane; w < kEvWords; w += 32) sh.evw[warp][w] = 0u;
+        // rows -kRowShift..-1 (before the first anti-diagonal) read as zero, exponent 0
+        for (int w = lane; w < kRowShift * RS; w += 32) frow[w - kRowShift * RS] = make_float2(0.f, 0.f);
+        if (lane < 3) kf[lane - 3] = 0;
+        __syncwarp();
+        int Ktot;
+        forward_pass<C, 1>(pc, a, frow, kf, sh.ftot[warp], Ktot, sh.evw[warp]);
+        // rows / exponents just past the last anti-diagonal read as zero / Ktot
+        for (int w = lane; w < kRowsAbove * RS; w += 32) frow[(size_t)pc.nd * RS + w] = make_float2(0.f, 0.f);
+        if (lane < 3) kf[pc.nd + lane] = Ktot;
+        __syncwarp();
+        const float fin = sh.ftot[warp][0];
+        if (lane < 4) info[lane] = __float_as_uint(sh.ftot[warp][lane]);
+        if (lane == 4) info[4] = (unsigned)Ktot;
+        for (int w = lane; w < kEvWords; w += 32) info[kInfoEv + w] = sh.evw[warp][w];
+        if (lane == 0)
+            p.out_lk[pi] = fin > 0.f ? log((double)fin) - (double)Ktot * 0.6931471805599453 : -INFINITY;
+        __syncwarp();
+    }
+}
+
+// Kernel 2: backward pass fused with the table reduction, reading the forward rows of kernel 1.
 template <int C, int ROWS>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, C == 2 ? 3 : 1) modtable_kernel(KParams p) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, C == 2 ? 3 : 1) bwdtable_kernel(KParams p) {
     __shared__ SmemLayout sh;
     extern __shared__ __align__(128) unsigned char dyn_smem[]; // kWarpsPerCta rings of forward rows
     fill_tables(sh, p.models);
     constexpr int NSLOT = 32 * C;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t wslot = (size_t)blockIdx.x * kWarpsPerCta + warp;
     constexpr int RS = NSLOT + 2 * kHalo;
-    float2 *frow = p.frows + wslot * p.frow_stride + kRowShift * RS; // row 0 (kRowShift zero rows below)
-    int32_t *kf = p.kf + wslot * p.kf_stride + 3;
     f2 *ring = reinterpret_cast<f2 *>(dyn_smem) + (size_t)warp * ring_floats2<C>();
     const unsigned bars = (unsigned)__cvta_generic_to_shared(&sh.bar[warp][0]);
     unsigned phase = 0u;
-    // rows -kRowShift..-1 (before the first anti-diagonal) read as zero, exponent 0
-    for (int k = lane; k < kRowShift * RS; k += 32) frow[k - kRowShift * RS] = make_float2(0.f, 0.f);
-    if (lane < 3) kf[lane - 3] = 0;
     if (lane < 4) mbar_init(bars + 8u * lane, 1u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
     for (;;) {
-        int pi = 0;
-        if (lane == 0) pi = atomicAdd(p.counter, 1);
-        pi = __shfl_sync(kFull, pi, 0);
-        if (pi >= p.n_pairs) break;
+        int k = 0;
+        if (lane == 0) k = atomicAdd(p.counter2, 1);
+        k = __shfl_sync(kFull, k, 0);
+        const int pi = p.pair_lo + k;
+        if (pi >= p.pair_hi) break;
         const DevPair P = p.pairs[pi];
         const PairCtx pc = make_pair_ctx(p, P, sh);
         const Coef a = load_coef(sh.trans[P.model], sh.cpair[P.model]);
-        for (int k = lane; k < kEvWords; k += 32) sh.evw[warp][k] = 0u;
+        const float2 *frow = p.frows + (size_t)k * p.frow_stride + kRowShift * RS;
+        const int32_t *kf = p.kf + (size_t)k * p.kf_stride + 3;
+        const unsigned *info = p.fwdinfo + (size_t)k * p.fwdinfo_stride;
+        for (int w = lane; w < kEvWords; w += 32) sh.evw[warp][w] = info[kInfoEv + w];
+        if (lane < 4) sh.ftot[warp][lane] = __uint_as_float(info[lane]);
         __syncwarp();
-        int Ktot;
-        forward_pass<C, 1>(pc, a, frow, kf, sh.ftot[warp], Ktot, sh.evw[warp]);
-        // rows / exponents just past the last anti-diagonal read as zero / Ktot
-        for (int k = lane; k < kRowsAbove * RS; k += 32) frow[(size_t)pc.nd * RS + k] = make_float2(0.f, 0.f);
-        if (lane < 3) kf[pc.nd + lane] = Ktot;
-        __syncwarp();
-        const float fin = sh.ftot[warp][0];
-        if (lane == 0)
-            p.out_lk[pi] = fin > 0.f ? log((double)fin) - (double)Ktot * 0.6931471805599453 : -INFINITY;
         backward_pass<C, ROWS>(pc, a, frow, kf, sh.stage[warp], sh.ftot[warp], p.out_delta + P.tab_off, sh.evw[warp], ring,
                                bars, phase);
         __syncwarp();
@@ -870,22 +906,26 @@ int cols_per_lane_for_radius(int radius) {
 }
 
 template <int C, int ROWS>
-static cudaError_t launch_modtable_cr(const KParams &p, int grid, cudaStream_t st) {
+static cudaError_t launch_modtable_cr(const KParams &p, int grid_fwd, int grid_bwd, cudaStream_t st) {
     const int dyn = kWarpsPerCta * ring_floats2<C>() * (int)sizeof(f2);
-    cudaError_t e = cudaFuncSetAttribute(modtable_kernel<C, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    cudaError_t e = cudaFuncSetAttribute(bwdtable_kernel<C, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     if (e != cudaSuccess) return e;
-    modtable_kernel<C, ROWS><<<grid, kWarpsPerCta * 32, dyn, st>>>(p);
+    fwdrows_kernel<C><<<grid_fwd, kWarpsPerCta * 32, 0, st>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    bwdtable_kernel<C, ROWS><<<grid_bwd, kWarpsPerCta * 32, dyn, st>>>(p);
     return cudaGetLastError();
 }
 template <int C>
-static cudaError_t launch_modtable_c(const KParams &p, int rows, int grid, cudaStream_t st) {
-    return rows == 14 ? launch_modtable_cr<C, 14>(p, grid, st) : launch_modtable_cr<C, 9>(p, grid, st);
+static cudaError_t launch_modtable_c(const KParams &p, int rows, int grid_fwd, int grid_bwd, cudaStream_t st) {
+    return rows == 14 ? launch_modtable_cr<C, 14>(p, grid_fwd, grid_bwd, st) : launch_modtable_cr<C, 9>(p, grid_fwd, grid_bwd, st);
 }
 
-cudaError_t launch_modtable(const KParams &p, int C, int grid, cudaStream_t st) {
+// one wave of the modification table: forward kernel, then backward kernel, pairs [p.pair_lo, p.pair_hi)
+cudaError_t launch_modtable(const KParams &p, int C, int grid_fwd, int grid_bwd, cudaStream_t st) {
     switch (C) {
-    case 2: return launch_modtable_c<2>(p, p.rows, grid, st);
-    case 4: return launch_modtable_c<4>(p, p.rows, grid, st);
+    case 2: return launch_modtable_c<2>(p, p.rows, grid_fwd, grid_bwd, st);
+    case 4: return launch_modtable_c<4>(p, p.rows, grid_fwd, grid_bwd, st);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -921,6 +961,8 @@ int warps_per_cta() { return kWarpsPerCta; }
 int frow_slots_per_row(int C) { return 32 * C + 2 * kHalo; }
 int frow_extra_rows() { return kRowShift + kRowsAbove; }
 int modtable_ctas_per_sm(int C) { return C == 2 ? 3 : 1; }
+int fwdrows_ctas_per_sm(int C) { return C == 2 ? 5 : 2; }
+int fwdinfo_words() { return ((kInfoEv + kEvWords + 15) / 16) * 16; }
 
 // ---- FP32 peak micro-benchmark (roofline denominator) ---------------------------------------------------
 // 16 independent accumulators per thread so the 4-cycle FMA latency is covered at 8 warps per scheduler.
