@@ -20,6 +20,7 @@ int cols_per_lane_for_radius(int radius);
 cudaError_t launch_modtable(const KParams &p, int C, int grid_fwd, int grid_bwd, cudaStream_t st);
 int fwdrows_ctas_per_sm(int C);
 int fwdinfo_words();
+int fwd_pad_rows(int C);
 cudaError_t launch_likelihood(const KParams &p, int C, int grid, cudaStream_t st);
 int warps_per_cta();
 int frow_slots_per_row(int C);
@@ -191,6 +192,7 @@ struct jtk_ctx {
     DevBuf<float> d_models;
     DevBuf<float2> d_frows;   // per-warp forward rows (scratch shared by all batches of this ctx)
     DevBuf<int32_t> d_kf;
+    DevBuf<float4> d_raw;         // per pair slot: raw column sums (backward -> finalize kernel)
     DevBuf<unsigned> d_fwdinfo;   // per pair slot: end sums, total exponent, rescale-event map (forward -> backward kernel)
     size_t scratch_bytes = (size_t)16 << 30; // forward-row scratch budget of one wave (JTK_SCRATCH_MB)
     DevBuf<int> d_counter;
@@ -269,7 +271,7 @@ int jtk_ctx_create(int device, size_t workspace_bytes, jtk_ctx **out) {
 void jtk_ctx_destroy(jtk_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    ctx->d_models.release(); ctx->d_frows.release(); ctx->d_kf.release(); ctx->d_fwdinfo.release(); ctx->d_counter.release();
+    ctx->d_models.release(); ctx->d_frows.release(); ctx->d_kf.release(); ctx->d_fwdinfo.release(); ctx->d_raw.release(); ctx->d_counter.release();
     ctx->d_minreq.release(); ctx->d_cols.release(); ctx->d_gather.release();
     ctx->d_tabs.release(); ctx->d_tab_off.release(); ctx->d_cand.release(); ctx->h_cand.release(); ctx->h_gather.release();
     ctx->h_pairs.release(); ctx->h_codes.release(); ctx->h_bits.release(); ctx->h_delta.release(); ctx->h_lk.release();
@@ -317,7 +319,7 @@ int64_t jtk_band_cell_count(const uint8_t *ops, int n_ops, int Lt, int Lr, int r
 // ---------------------------------------------------------------------------------------------------
 struct jtk_batch {
     jtk_ctx *ctx = nullptr;
-    int n_pairs = 0, n_tmpl = 0, radius = 0, C = 0, max_nd = 0, max_lt = 0;
+    int n_pairs = 0, n_tmpl = 0, radius = 0, C = 0, max_nd = 0, max_lt = 0, max_lr = 0;
     uint64_t table_floats = 0, cell_updates = 0, h2d_bytes = 0;
     bool has_profiles = false;
     std::vector<DevPair> pairs;           // host copy
@@ -418,6 +420,7 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
         bwords += (Lt + Lr + 1 + 31) / 32 + 1;
         cnt[tmpl_idx[p] + 1]++;
         b->max_nd = std::max(b->max_nd, (int)(Lt + Lr + 1));
+        b->max_lr = std::max(b->max_lr, (int)Lr);
     }
     if (cb >= (size_t)0xffffffffu) return ctx->fail(JTK_EINVAL, "batch too large: split it (code bytes exceed 4 GiB)");
     b->tp_start.assign((size_t)n_tmpl + 1, 0);
@@ -607,7 +610,12 @@ int batch_run(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev
         kp.frow_stride = (size_t)(b->max_nd + frow_extra_rows()) * frow_slots_per_row(b->C);
         kp.kf_stride = (size_t)b->max_nd + 6;
         kp.fwdinfo_stride = (size_t)fwdinfo_words();
-        const size_t per_pair = kp.frow_stride * sizeof(float2) + kp.kf_stride * sizeof(int32_t) + kp.fwdinfo_stride * 4;
+        kp.smem_rb = ((b->max_lr + 2 * fwd_pad_rows(b->C)) + 15) & ~15;
+        kp.smem_tb = ((b->max_lt + 32 * b->C + 16) + 15) & ~15;
+        kp.raw_stride = (size_t)4 * (b->max_lt + 1);
+        kp.max_lt = b->max_lt;
+        const size_t per_pair = kp.frow_stride * sizeof(float2) + kp.kf_stride * sizeof(int32_t) + kp.fwdinfo_stride * 4 +
+                                kp.raw_stride * sizeof(float4);
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
         const size_t have = ctx->d_frows.cap * sizeof(float2);
@@ -616,13 +624,14 @@ int batch_run(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev
         CU(ctx->d_frows.reserve((size_t)per_wave * kp.frow_stride), "cudaMalloc forward rows");
         CU(ctx->d_kf.reserve((size_t)per_wave * kp.kf_stride), "cudaMalloc scale exponents");
         CU(ctx->d_fwdinfo.reserve((size_t)per_wave * kp.fwdinfo_stride), "cudaMalloc forward info");
+        CU(ctx->d_raw.reserve((size_t)per_wave * kp.raw_stride), "cudaMalloc raw column sums");
         CU(b->d_delta.reserve((size_t)b->table_floats), "cudaMalloc profiles");
     }
     CU(cudaMemcpyAsync(ctx->d_models.p, models, sizeof(models), cudaMemcpyHostToDevice, st), "H2D models");
     kp.pairs = b->d_pairs.p; kp.n_pairs = b->n_pairs;
     kp.codes = b->d_codes.p; kp.bits = b->d_bits.p; kp.models = ctx->d_models.p;
     kp.radius = b->radius; kp.rows = rows;
-    kp.frows = ctx->d_frows.p; kp.kf = ctx->d_kf.p; kp.fwdinfo = ctx->d_fwdinfo.p;
+    kp.frows = ctx->d_frows.p; kp.kf = ctx->d_kf.p; kp.fwdinfo = ctx->d_fwdinfo.p; kp.raw = ctx->d_raw.p;
     kp.out_delta = b->d_delta.p; kp.out_lk = b->d_lk.p; kp.counter = ctx->d_counter.p; kp.counter2 = ctx->d_counter.p + 1;
     cudaEvent_t r0 = nullptr, r1 = nullptr;
     if (ctx->ring_n < jtk_ctx::kRing) {
@@ -643,7 +652,7 @@ int batch_run(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev
             const int gf = std::min(ctas, ctx->sm_count * fwdrows_ctas_per_sm(b->C));
             const int gb = std::min(ctas, ctx->sm_count * modtable_ctas_per_sm(b->C));
             CU(launch_modtable(kp, b->C, gf, gb, st), "kernel launch");
-            ctx->launches += 2;
+            ctx->launches += 3;
         } else {
             kp.n_pairs = b->n_pairs;
             CU(launch_likelihood(kp, b->C, std::min(ctas, ctx->sm_count * 4), st), "kernel launch");

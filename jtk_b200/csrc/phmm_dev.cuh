@@ -53,6 +53,10 @@ struct KParams {
     unsigned *fwdinfo;      // per pair slot: [0..3] ftot (float bits), [4] Ktot, [8..] rescale-event map
     size_t fwdinfo_stride;  // words per pair slot
     int *counter2;          // work queue head of the backward kernel
+    float4 *raw;            // per pair slot: 16 raw column sums per template column (backward -> finalize kernel)
+    size_t raw_stride;      // float4 per pair slot = 4 * (max_lt + 1)
+    int max_lt;
+    int smem_rb, smem_tb;   // bytes of staged read / template codes per warp in the forward kernel (multiples of 16)
 };
 
 } // namespace jtk

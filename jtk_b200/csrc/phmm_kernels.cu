@@ -410,9 +410,8 @@ __device__ __forceinline__ void bwd_step(const PairCtx &pc, const Coef &a, BwdSt
 
 template <int C, int ROWS>
 __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, const float2 *__restrict__ frow,
-                                              const int32_t *__restrict__ kf, float *stage, volatile float *s_ftot,
-                                              float *__restrict__ out, const unsigned *evw, f2 *ring, const unsigned bars,
-                                              unsigned &phase) {
+                                              const int32_t *__restrict__ kb, float4 *__restrict__ raw,
+                                              volatile float *s_ftot, f2 *ring, const unsigned bars, unsigned &phase) {
     constexpr int NSLOT = 32 * C;
     constexpr int RS = NSLOT + 2 * kHalo;
     constexpr unsigned RSB = RS * 8u; // bytes per forward row
@@ -469,50 +468,16 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
     }
     int xmin = pc.r;   // smallest x over the slots (warp-uniform)
     int jd = Lt;       // the column that leaves the band next (warp-uniform)
-    int blk_lo = (Lt >> 5) << 5;
 
+    // a finished column leaves its 16 raw sums in the pair's scratch (64 B, one lane); finalize_kernel turns them into the
+    // 14 log-ratios of the table
     auto flush_col = [&](int c) {
-        float4 *sg = reinterpret_cast<float4 *>(stage + (st.j[c] & (kStageCols - 1)) * kStageStride);
-        sg[0] = make_float4(lo2(st.S01[c]), hi2(st.S01[c]), lo2(st.S23[c]), hi2(st.S23[c]));
-        sg[1] = make_float4(st.Vs[c], lo2(st.N01[c]), hi2(st.N01[c]), lo2(st.N23[c]));
-        sg[2] = make_float4(hi2(st.N23[c]), st.Vn[c], lo2(st.Xp[c][0]) + hi2(st.Xp[c][0]), lo2(st.Xp[c][1]) + hi2(st.Xp[c][1]));
-        sg[3] = make_float4(lo2(st.Xp[c][2]) + hi2(st.Xp[c][2]), lo2(st.Xm[c][0]) + hi2(st.Xm[c][0]),
-                            lo2(st.Xm[c][1]) + hi2(st.Xm[c][1]), lo2(st.Xm[c][2]) + hi2(st.Xm[c][2]));
-    };
-    auto dlog = [](float num, float ref) -> float {
-        return (num > 0.f && ref > 0.f) ? logf(num / ref) : kDeltaNeg;
-    };
-    auto emit_block = [&](int lo_col) {
-        __syncwarp();
-        const int jj = lo_col + lane;
-        if (jj >= 0 && jj <= Lt) {
-            const float4 *sg = reinterpret_cast<const float4 *>(stage + (jj & (kStageCols - 1)) * kStageStride);
-            const float4 q0 = sg[0], q1 = sg[1], q2 = sg[2], q3 = sg[3];
-            const float s4[4] = { q0.x, q0.y, q0.z, q0.w };
-            const float n4[4] = { q1.y, q1.z, q1.w, q2.x };
-            const float vs = q1.x, vn = q2.y;
-            const float xp[3] = { q2.z, q2.w, q3.x };
-            const int tcode = pc.Tb[jj + 1];
-            float ref = fin;
-            if (jj < Lt) ref = s4[tcode & 3] + vs;
-            float *o = out + (size_t)jj * kNumRow;
-#pragma unroll
-            for (int b = 0; b < 4; b++) o[b] = (jj < Lt) ? dlog(s4[b] + vs, ref) : kDeltaNeg;
-#pragma unroll
-            for (int b = 0; b < 4; b++) o[4 + b] = dlog(n4[b] + vn, ref);
-#pragma unroll
-            for (int e = 1; e <= 3; e++) {
-                o[7 + e] = (ROWS == 14 && jj + e <= Lt) ? dlog(xp[e - 1], ref) : kDeltaNeg;
-                float v = kDeltaNeg;
-                if ((ROWS == 14 || e == 1) && jj + e <= Lt) {
-                    float acc = stage[((jj + e) & (kStageCols - 1)) * kStageStride + 13 + (e - 1)];
-                    if (jj + e == Lt) acc += s_ftot[e] * boff;
-                    v = dlog(acc, ref);
-                }
-                o[10 + e] = v;
-            }
-        }
-        __syncwarp();
+        float4 *sg = raw + (size_t)st.j[c] * 4;
+        __stcg(sg + 0, make_float4(lo2(st.S01[c]), hi2(st.S01[c]), lo2(st.S23[c]), hi2(st.S23[c])));
+        __stcg(sg + 1, make_float4(st.Vs[c], lo2(st.N01[c]), hi2(st.N01[c]), lo2(st.N23[c])));
+        __stcg(sg + 2, make_float4(hi2(st.N23[c]), st.Vn[c], lo2(st.Xp[c][0]) + hi2(st.Xp[c][0]), lo2(st.Xp[c][1]) + hi2(st.Xp[c][1])));
+        __stcg(sg + 3, make_float4(lo2(st.Xp[c][2]) + hi2(st.Xp[c][2]), lo2(st.Xm[c][0]) + hi2(st.Xm[c][0]),
+                                   lo2(st.Xm[c][1]) + hi2(st.Xm[c][1]), lo2(st.Xm[c][2]) + hi2(st.Xm[c][2])));
     };
     // hand (B_M, B_D) to the left-hand neighbour column (slot-1, wrapping)
     auto hand_off = [&](f2 (&bMD)[C]) {
@@ -547,7 +512,6 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
                     st.x[c]--;
                 }
             }
-            if (jd == blk_lo) { emit_block(blk_lo); blk_lo -= 32; }
             jd--;
         }
     };
@@ -559,11 +523,14 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
     auto slow_step = [&](int s) {
         const f2 *rp = ring + (size_t)(((s + kRowShift) & (kRingRows - 1)) + kRingMargin) * RS + kHalo + lane * C;
         if (s == nd - 1 || (s & 3) == 3) reload(s);
-        const int kcur = kf[s];
-        const int kstep = kcur - kf[s - 1]; // exponent the forward pass added at step s (mirrored below)
+        // cumulative scale exponent of forward row t: rescales happen on the last row of a block of four, kb[q] = exponent
+        // after block q
+        auto kfat = [&](int t) -> int { return kb[(t - 3) >> 2]; };
+        const int kcur = kfat(s);
+        const int kstep = kcur - kfat(s - 1); // exponent the forward pass added at step s (mirrored below)
         float ce[7];
 #pragma unroll
-        for (int e = -3; e <= 3; e++) ce[e + 3] = pow2i(max(-126, min(126, kcur - kf[s + e])));
+        for (int e = -3; e <= 3; e++) ce[e + 3] = pow2i(max(-126, min(126, kcur - kfat(s + e))));
         f2 bMD[C];
         if (s == nd - 1) bwd_step<C, ROWS, true, true>(pc, a, st, rp, W, ce, boff, bMD);
         else bwd_step<C, ROWS, true, false>(pc, a, st, rp, W, ce, boff, bMD);
@@ -579,7 +546,9 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
         }
     };
 
-    const bool ev_over = ((nd >> 2) + 3) >= kEvWords * 32; // event map too short for this pair: every block is generic
+    // block q (rows 4q-4 .. 4q-1 = forward block q-1) touches forward rows 4q-7 .. 4q+2: it needs exact corrections iff the
+    // forward pass rescaled at the end of forward block q-1 or q-2, i.e. unless kb[q-1] == kb[q-2] == kb[q-3]
+    int kb1 = kb[q_top - 1], kb2 = kb[q_top - 2], kb3 = kb[q_top - 3];
     wait_group(q_top + 1);
     wait_group(q_top);
     auto load_nib = [&](int q) -> unsigned { // guide bits 4q-5 .. 4q-2 of block q >= 2
@@ -594,9 +563,9 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
         __syncwarp(); // every lane is done with the rows that the next copy overwrites
         if (q >= 2) issue_group(q - 2);
         const int s_hi = 4 * q - 1;
-        // rescale events in rows 4q-7 .. 4q+2 are bits q .. q+2 of the event map
-        const unsigned ew = __funnelshift_r(evw[q >> 5], evw[(q >> 5) + 1], q & 31) & 7u;
-        if (s_hi <= nd - 2 && q >= 2 && ew == 0u && !ev_over) {
+        const bool clean = kb1 == kb2 && kb2 == kb3;
+        kb1 = kb2; kb2 = kb3; kb3 = kb[q - 4];
+        if (s_hi <= nd - 2 && q >= 2 && clean) {
             const f2 *rp = ring + (size_t)(4 * (q & 3) + 3 + kRingMargin) * RS + kHalo + lane * C;
             reload(s_hi);
             // guide bits 4q-5 .. 4q-2 (fetched one block ahead): step k (s = s_hi - k) moves on with bit 4q-2-k
@@ -619,7 +588,8 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ PairCtx make_pair_ctx(const KParams &p, const DevPair &P, SmemLayout &sh) {
+template <typename SM>
+__device__ __forceinline__ PairCtx make_pair_ctx(const KParams &p, const DevPair &P, SM &sh) {
     PairCtx pc;
     pc.Tb = p.codes + P.tb_off;
     pc.RbP = p.codes + P.rb_off - kCodePad;
@@ -633,18 +603,68 @@ __device__ __forceinline__ PairCtx make_pair_ctx(const KParams &p, const DevPair
 
 template <int C> constexpr int ring_floats2() { return (kRingRows + 2 * kRingMargin) * (32 * C + 2 * kHalo); }
 
-constexpr int kInfoEv = 8; // word offset of the rescale-event map inside a pair's fwdinfo block
+// ------------------------------------------------------------------------------------------------
+// Kernel 1 of the modification table: the forward pass of every pair of the wave (v7).
+//   * read codes and template codes of the pair are staged in shared memory once (compact one-byte table offsets), so
+//     the step body has no window registers, no reloads and one integer instruction per emission lookup;
+//   * a cell outside the band is handled by multiplying its three out-sums with a per-slot 0/1 float that is
+//     recomputed only when the band moves (FMA pipe instead of per-cell compares and selects);
+//   * the guide bits are consumed four at a time, slots are retargeted once per block of four anti-diagonals;
+//   * the scale exponent is kept per BLOCK (rescales only happen on the last step of a block): kb[q].
+// Writes the forward rows (toM, toD of every cell), kb, the four end sums and the likelihood.
+// ------------------------------------------------------------------------------------------------
+constexpr int kIdxModel = 25;   // compact read-code index = model*25 + ctx*5 + q  (q, ctx in 0..4, 4 = none)
+constexpr int kEm2Stride = 52;  // floats per template-code row of em2
+struct __align__(16) FwdSmem {
+    float em2[5][kEm2Stride];      // [tc][idx] = eM(model(idx); tc, q(idx)), zero for tc = 4 or q = 4
+    float ei2[kEm2Stride];         // [idx]     = eI(model(idx); ctx(idx), q(idx))
+    unsigned char lut[2][256];     // global read-code byte (ctx<<5 | q<<2) -> byte offset 4*idx
+    float trans[2][12];
+    unsigned long long cpair[2][6];
+    float ftot[kWarpsPerCta][4];
+};
 
-// Kernel 1 of the modification table: forward pass of every pair of the wave.  Writes the forward rows (toM, toD of every
-// cell), the cumulative scale exponent of every row, the rescale-event map, the four end sums and the likelihood.
-// Light on registers (no table accumulators), so it runs at a much higher occupancy than the backward kernel.
+__device__ __forceinline__ void fill_fwd_tables(FwdSmem &sh, const float *__restrict__ models) {
+    for (int k = threadIdx.x; k < 5 * kEm2Stride; k += blockDim.x) {
+        const int tc = k / kEm2Stride, idx = k % kEm2Stride;
+        float v = 0.f, w = 0.f;
+        if (idx < 2 * kIdxModel) {
+            const int m = idx / kIdxModel, ctx = (idx % kIdxModel) / 5, q = idx % 5;
+            if (tc < 4 && q < 4) v = models[m * kModelFloats + kOffEM + tc * 8 + q];
+            if (q < 4) w = models[m * kModelFloats + kOffEI + ctx * 8 + q];
+        }
+        sh.em2[tc][idx] = v;
+        if (tc == 0) sh.ei2[idx] = w;
+    }
+    for (int k = threadIdx.x; k < 512; k += blockDim.x) {
+        const int m = k >> 8, b = k & 255;
+        const int ctx = min(b >> 5, 4), q = min((b >> 2) & 7, 4);
+        sh.lut[m][b] = (unsigned char)(4 * (m * kIdxModel + ctx * 5 + q));
+    }
+    for (int k = threadIdx.x; k < 24; k += blockDim.x) {
+        const int m = k / 12, e = k % 12;
+        sh.trans[m][e] = models[m * kModelFloats + e];
+        if (e < 6) {
+            const int lo_i[6] = { 0, 3, 6, 0, 1, 2 }, hi_i[6] = { 2, 5, 8, 6, 7, 8 };
+            sh.cpair[m][e] = mk2(models[m * kModelFloats + lo_i[e]], models[m * kModelFloats + hi_i[e]]);
+        }
+    }
+    __syncthreads();
+}
+
 template <int C>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 5) fwdrows_kernel(KParams p) {
-    __shared__ SmemLayout sh;
-    fill_tables(sh, p.models);
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 6) fwdrows_kernel(KParams p) {
+    __shared__ FwdSmem sh;
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    fill_fwd_tables(sh, p.models);
     constexpr int NSLOT = 32 * C;
     constexpr int RS = NSLOT + 2 * kHalo;
+    constexpr int PADR = NSLOT + 16; // staged read rows: -PADR .. Lr + PADR
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *rb_s = dyn_smem + (size_t)warp * (p.smem_rb + p.smem_tb); // rb_s[i + PADR] = 4*idx of read row i
+    unsigned char *tb_s = rb_s + p.smem_rb;                                  // tb_s[j] = template code of column j (t[j-1])
+    volatile float *s_ftot = sh.ftot[warp];
+    const int W = 2 * p.radius;
     for (;;) {
         int k = 0;
         if (lane == 0) k = atomicAdd(p.counter, 1);
@@ -652,38 +672,193 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 5) fwdrows_kernel(KParams p
         const int pi = p.pair_lo + k;
         if (pi >= p.pair_hi) break;
         const DevPair P = p.pairs[pi];
-        const PairCtx pc = make_pair_ctx(p, P, sh);
+        const int Lt = P.Lt, Lr = P.Lr, nd = Lt + Lr + 1;
         const Coef a = load_coef(sh.trans[P.model], sh.cpair[P.model]);
         float2 *frow = p.frows + (size_t)k * p.frow_stride + kRowShift * RS; // row 0 (kRowShift zero rows below)
-        int32_t *kf = p.kf + (size_t)k * p.kf_stride + 3;
+        int32_t *kb = p.kf + (size_t)k * p.kf_stride + 4;                    // kb[q], q >= -4
         unsigned *info = p.fwdinfo + (size_t)k * p.fwdinfo_stride;
-        for (int w = lane; w < kEvWords; w += 32) sh.evw[warp][w] = 0u;
-        // rows -kRowShift..-1 (before the first anti-diagonal) read as zero, exponent 0
-        for (int w = lane; w < kRowShift * RS; w += 32) frow[w - kRowShift * RS] = make_float2(0.f, 0.f);
-        if (lane < 3) kf[lane - 3] = 0;
+        // ---- stage the codes of this pair ----
+        {
+            const uint8_t *Rb = p.codes + P.rb_off;
+            const uint8_t *Tb = p.codes + P.tb_off;
+            const unsigned char *lut = sh.lut[P.model];
+            const int nr = Lr + 2 * PADR, nt = Lt + NSLOT + 16;
+            for (int w = lane; w < nr; w += 32) rb_s[w] = lut[Rb[w - PADR]];
+            for (int w = lane; w < nt; w += 32) tb_s[w] = Tb[w];
+            // rows -kRowShift..-1 (before the first anti-diagonal) read as zero, exponent 0
+            for (int w = lane; w < kRowShift * RS; w += 32) frow[w - kRowShift * RS] = make_float2(0.f, 0.f);
+            if (lane < 4) { kb[lane - 4] = 0; s_ftot[lane] = 0.f; }
+        }
         __syncwarp();
-        int Ktot;
-        forward_pass<C, 1>(pc, a, frow, kf, sh.ftot[warp], Ktot, sh.evw[warp]);
-        // rows / exponents just past the last anti-diagonal read as zero / Ktot
-        for (int w = lane; w < kRowsAbove * RS; w += 32) frow[(size_t)pc.nd * RS + w] = make_float2(0.f, 0.f);
-        if (lane < 3) kf[pc.nd + lane] = Ktot;
+        // ---- per-slot state ----
+        int x[C];                 // offset of the slot's cell inside the band window of the current anti-diagonal
+        const unsigned char *rbp[C]; // staged read code of the slot's cell (row s - j)
+        const unsigned char *tbp[C]; // staged template code of the slot's column
+        const char *emrow[C];     // em2 row of the slot's column
+        float msk[C], toI[C], inD[C], inMa[C], inMb[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const int j = lane * C + c;
+            x[c] = p.radius - j;
+            rbp[c] = rb_s + PADR - j;
+            tbp[c] = tb_s + j;
+            emrow[c] = reinterpret_cast<const char *>(sh.em2[min((int)tbp[c][0], 4)]);
+            msk[c] = (unsigned)x[c] <= (unsigned)W ? 1.f : 0.f;
+            toI[c] = inD[c] = inMa[c] = inMb[c] = 0.f;
+        }
+        f2 *wrow = reinterpret_cast<f2 *>(frow) + kHalo + lane * C; // this lane's slots in row 0
+        const int halo = (lane * C < 3) ? NSLOT : ((lane * C + C > NSLOT - 3) ? -NSLOT : 0);
+        int K = 0;
+        const uint32_t *bw = p.bits + P.bits_off;
+
+        // one anti-diagonal; kk = row offset inside the current block (immediate in the unrolled loop)
+        auto step = [&](const int s, const int kk, const bool special, const bool rescale) {
+            f2 tMD[C];
+            float nI[C];
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const unsigned w = rbp[c][kk];
+                const float em = *reinterpret_cast<const float *>(emrow[c] + w);
+                const float ei = *reinterpret_cast<const float *>(reinterpret_cast<const char *>(sh.ei2) + w);
+                float M = em * inMb[c];
+                const float I = ei * toI[c];
+                const float D = inD[c];
+                if (special && s == 0 && lane * C + c == 0) M = 1.f;
+                tMD[c] = mul2(fma2(a.fD, bc2(D), fma2(a.fI, bc2(I), mul2(a.fM, bc2(M)))), bc2(msk[c]));
+                nI[c] = fmaf(a.f_di, D, fmaf(a.f_ii, I, a.f_mi * M)) * msk[c];
+                if (special && s >= nd - 4 && msk[c] != 0.f) {
+                    const int j = (int)(tbp[c] - tb_s);
+                    if (s - j == Lr && j >= Lt - 3) s_ftot[Lt - j] = M + I + D;
+                }
+            }
+            if (rescale) {
+                float v = lo2(tMD[0]);
+#pragma unroll
+                for (int c = 1; c < C; c++) v = fmaxf(v, lo2(tMD[c]));
+                const unsigned mx = __reduce_max_sync(kFull, __float_as_uint(v));
+                const int e = (int)(mx >> 23) - 127;
+                if (mx != 0u && e < kScaleLow) {
+                    const int kx = min(kScaleTarget - e, kScaleStep);
+                    const float sc = pow2i(kx);
+#pragma unroll
+                    for (int c = 0; c < C; c++) { tMD[c] = mul2(tMD[c], bc2(sc)); nI[c] *= sc; inMa[c] *= sc; }
+                    K += kx;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < C; c += 2)
+                asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(wrow + kk * RS + c), "l"(tMD[c]), "l"(tMD[c + 1]) : "memory");
+            if (halo != 0) { // the first / last slots are replicated past the other end of the row
+#pragma unroll
+                for (int c = 0; c < C; c += 2)
+                    asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(wrow + kk * RS + halo + c), "l"(tMD[c]), "l"(tMD[c + 1]) : "memory");
+            }
+            // hand (toM, toD) to the right-hand neighbour column (slot+1, wrapping)
+            const float rM = __shfl_sync(kFull, lo2(tMD[C - 1]), (lane + 31) & 31);
+            const float rD = __shfl_sync(kFull, hi2(tMD[C - 1]), (lane + 31) & 31);
+#pragma unroll
+            for (int c = C - 1; c >= 1; c--) { inMb[c] = inMa[c]; inMa[c] = lo2(tMD[c - 1]); inD[c] = hi2(tMD[c - 1]); }
+            inMb[0] = inMa[0]; inMa[0] = rM; inD[0] = rD;
+#pragma unroll
+            for (int c = 0; c < C; c++) toI[c] = nI[c];
+        };
+        // anti-diagonal s -> s+1 when the centre stays (guide bit 0): every cell moves one row up inside the window
+        auto band_up = [&]() {
+#pragma unroll
+            for (int c = 0; c < C; c++) { x[c]++; msk[c] = (unsigned)x[c] <= (unsigned)W ? 1.f : 0.f; }
+        };
+        // a slot whose cell left the band at the top (x > W) moves on to column j + NSLOT; it has NSLOT - (W+1) >= 3 band
+        // moves of slack, and until then its mask is zero
+        auto retarget = [&]() {
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                if (x[c] > W) {
+                    x[c] -= NSLOT; rbp[c] -= NSLOT; tbp[c] += NSLOT;
+                    emrow[c] = reinterpret_cast<const char *>(sh.em2[min((int)tbp[c][0], 4)]);
+                    msk[c] = (unsigned)x[c] <= (unsigned)W ? 1.f : 0.f;
+                }
+            }
+        };
+        auto advance = [&](int n) {
+#pragma unroll
+            for (int c = 0; c < C; c++) rbp[c] += n;
+            wrow += n * RS;
+        };
+        int s = 0;
+        // prologue: the first four anti-diagonals (the start cell is injected at s = 0)
+        for (; s < 4 && s < nd; ++s) {
+            step(s, 0, true, false);
+            advance(1);
+            if (s < nd - 1) { if (((bw[s >> 5] >> (s & 31)) & 1u) == 0u) band_up(); retarget(); }
+        }
+        if (lane == 0) kb[0] = 0;
+        // main loop: blocks of four anti-diagonals, guide bits four at a time
+        unsigned bword = bw[0];
+        for (; s + 3 < nd - 4; s += 4) {
+            if ((s & 31) == 0) bword = bw[s >> 5];
+            const unsigned nib = bword >> (s & 31);
+            step(s, 0, false, false);     if ((nib & 1u) == 0u) band_up();
+            step(s + 1, 1, false, false); if ((nib & 2u) == 0u) band_up();
+            step(s + 2, 2, false, false); if ((nib & 4u) == 0u) band_up();
+            step(s + 3, 3, false, s + 3 < nd - 8); if ((nib & 8u) == 0u) band_up();
+            retarget();
+            advance(4);
+            if (lane == 0) kb[s >> 2] = K;
+        }
+        // epilogue: the last anti-diagonals also record the delete-to-end terms
+        for (; s < nd; ++s) {
+            step(s, 0, true, false);
+            advance(1);
+            if (s < nd - 1) { if (((bw[s >> 5] >> (s & 31)) & 1u) == 0u) band_up(); retarget(); }
+        }
+        // rows just past the last anti-diagonal read as zero; the exponent stays at K
+        for (int w = lane; w < kRowsAbove * RS; w += 32) frow[(size_t)nd * RS + w] = make_float2(0.f, 0.f);
+        {
+            const int q0 = (nd - 8) >> 2; // blocks from here on cannot rescale
+            for (int q = max(q0, 0) + lane; q <= ((nd + 3) >> 2) + 2; q += 32) kb[q] = K;
+        }
         __syncwarp();
-        const float fin = sh.ftot[warp][0];
-        if (lane < 4) info[lane] = __float_as_uint(sh.ftot[warp][lane]);
-        if (lane == 4) info[4] = (unsigned)Ktot;
-        for (int w = lane; w < kEvWords; w += 32) info[kInfoEv + w] = sh.evw[warp][w];
+        const float fin = s_ftot[0];
+        if (lane < 4) info[lane] = __float_as_uint(s_ftot[lane]);
+        if (lane == 4) info[4] = (unsigned)K;
         if (lane == 0)
-            p.out_lk[pi] = fin > 0.f ? log((double)fin) - (double)Ktot * 0.6931471805599453 : -INFINITY;
+            p.out_lk[pi] = fin > 0.f ? log((double)fin) - (double)K * 0.6931471805599453 : -INFINITY;
         __syncwarp();
     }
 }
 
-// Kernel 2: backward pass fused with the table reduction, reading the forward rows of kernel 1.
+// Kernel 2: backward pass fused with the table reduction, reading the forward rows of kernel 1.  Finished columns leave
+// their 16 raw sums in the pair's scratch; kernel 3 (finalize) turns them into the table.  No staging buffer and a ring
+// without spare rows: 128 registers and 13 KB of shared memory per warp => 16 warps per SM.
+struct __align__(256) BwdSmem {
+    float em[2][64];  // [tc*8 + qc]   byte offset tc*32 + qc*4
+    float ei[2][64];  // [ctx*8 + qc]  byte offset = the read-row code byte (ctx<<5 | qc<<2)
+    float emt[2][32]; // [qc*4 + b]    eM(ref b, query qc)
+    float trans[2][12];
+    unsigned long long cpair[2][6];
+    float ftot[kWarpsPerCta][4];
+    unsigned long long bar[kWarpsPerCta][4];       // mbarriers of the four ring groups
+};
+__device__ __forceinline__ void fill_bwd_tables(BwdSmem &sh, const float *__restrict__ models) {
+    for (int k = threadIdx.x; k < 2 * 64; k += blockDim.x) {
+        const int m = k >> 6, e = k & 63;
+        sh.em[m][e] = models[m * kModelFloats + kOffEM + e];
+        sh.ei[m][e] = models[m * kModelFloats + kOffEI + e];
+        if (e < 32) sh.emt[m][e] = models[m * kModelFloats + kOffEMT + e];
+        if (e < 12) sh.trans[m][e] = models[m * kModelFloats + e];
+        if (e < 6) {
+            const int lo_i[6] = { 0, 3, 6, 0, 1, 2 }, hi_i[6] = { 2, 5, 8, 6, 7, 8 };
+            sh.cpair[m][e] = mk2(models[m * kModelFloats + lo_i[e]], models[m * kModelFloats + hi_i[e]]);
+        }
+    }
+    __syncthreads();
+}
+
 template <int C, int ROWS>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, C == 2 ? 3 : 1) bwdtable_kernel(KParams p) {
-    __shared__ SmemLayout sh;
+__global__ void __launch_bounds__(kWarpsPerCta * 32, C == 2 ? 4 : 1) bwdtable_kernel(KParams p) {
+    __shared__ BwdSmem sh;
     extern __shared__ __align__(128) unsigned char dyn_smem[]; // kWarpsPerCta rings of forward rows
-    fill_tables(sh, p.models);
+    fill_bwd_tables(sh, p.models);
     constexpr int NSLOT = 32 * C;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int RS = NSLOT + 2 * kHalo;
@@ -703,14 +878,58 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, C == 2 ? 3 : 1) bwdtable_ke
         const PairCtx pc = make_pair_ctx(p, P, sh);
         const Coef a = load_coef(sh.trans[P.model], sh.cpair[P.model]);
         const float2 *frow = p.frows + (size_t)k * p.frow_stride + kRowShift * RS;
-        const int32_t *kf = p.kf + (size_t)k * p.kf_stride + 3;
+        const int32_t *kb = p.kf + (size_t)k * p.kf_stride + 4;
         const unsigned *info = p.fwdinfo + (size_t)k * p.fwdinfo_stride;
-        for (int w = lane; w < kEvWords; w += 32) sh.evw[warp][w] = info[kInfoEv + w];
         if (lane < 4) sh.ftot[warp][lane] = __uint_as_float(info[lane]);
         __syncwarp();
-        backward_pass<C, ROWS>(pc, a, frow, kf, sh.stage[warp], sh.ftot[warp], p.out_delta + P.tab_off, sh.evw[warp], ring,
-                               bars, phase);
+        backward_pass<C, ROWS>(pc, a, frow, kb, p.raw + (size_t)k * p.raw_stride, sh.ftot[warp], ring, bars, phase);
         __syncwarp();
+    }
+}
+
+// Kernel 3: raw column sums -> the 14 log-ratios of the table (table - lk), one thread per column.
+// raw[j] = { S[0..3] | Vs, N[0..2] | N[3], Vn, Xp[0..1] | Xp[2], Xm[0..2] } (DESIGN.md 3.2, table identities).
+__global__ void __launch_bounds__(128) finalize_kernel(KParams p) {
+    const int k = blockIdx.y;
+    const int pi = p.pair_lo + k;
+    const DevPair P = p.pairs[pi];
+    const int Lt = P.Lt;
+    const int jj = blockIdx.x * blockDim.x + threadIdx.x;
+    if (jj > Lt) return;
+    const unsigned *info = p.fwdinfo + (size_t)k * p.fwdinfo_stride;
+    const float fin_raw = __uint_as_float(info[0]);
+    const int e_fin = (int)(__float_as_uint(fin_raw) >> 23) - 127;
+    const float boff = fin_raw > 0.f ? pow2i(max(-120, min(120, kProductExp - e_fin))) : 1.f;
+    const float fin = fin_raw * boff;
+    const float4 *sg = p.raw + (size_t)k * p.raw_stride + (size_t)jj * 4;
+    const float4 q0 = __ldcg(sg), q1 = __ldcg(sg + 1), q2 = __ldcg(sg + 2), q3 = __ldcg(sg + 3);
+    const float s4[4] = { q0.x, q0.y, q0.z, q0.w };
+    const float n4[4] = { q1.y, q1.z, q1.w, q2.x };
+    const float vs = q1.x, vn = q2.y;
+    const float xp[3] = { q2.z, q2.w, q3.x };
+    const int tcode = p.codes[P.tb_off + jj + 1];
+    float ref = fin;
+    if (jj < Lt) ref = s4[tcode & 3] + vs;
+    auto dlog = [](float num, float den) -> float {
+        return (num > 0.f && den > 0.f) ? logf(num / den) : kDeltaNeg;
+    };
+    float *o = p.out_delta + P.tab_off + (size_t)jj * kNumRow;
+    const bool all_rows = p.rows == 14;
+#pragma unroll
+    for (int b = 0; b < 4; b++) o[b] = (jj < Lt) ? dlog(s4[b] + vs, ref) : kDeltaNeg;
+#pragma unroll
+    for (int b = 0; b < 4; b++) o[4 + b] = dlog(n4[b] + vn, ref);
+#pragma unroll
+    for (int e = 1; e <= 3; e++) {
+        o[7 + e] = (all_rows && jj + e <= Lt) ? dlog(xp[e - 1], ref) : kDeltaNeg;
+        float v = kDeltaNeg;
+        if ((all_rows || e == 1) && jj + e <= Lt) {
+            const float4 qe = __ldcg(sg + 4 * e + 3);
+            float acc = e == 1 ? qe.y : (e == 2 ? qe.z : qe.w);
+            if (jj + e == Lt) acc += __uint_as_float(info[e]) * boff;
+            v = dlog(acc, ref);
+        }
+        o[10 + e] = v;
     }
 }
 
@@ -910,10 +1129,16 @@ static cudaError_t launch_modtable_cr(const KParams &p, int grid_fwd, int grid_b
     const int dyn = kWarpsPerCta * ring_floats2<C>() * (int)sizeof(f2);
     cudaError_t e = cudaFuncSetAttribute(bwdtable_kernel<C, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     if (e != cudaSuccess) return e;
-    fwdrows_kernel<C><<<grid_fwd, kWarpsPerCta * 32, 0, st>>>(p);
+    const int dyn_f = kWarpsPerCta * (p.smem_rb + p.smem_tb);
+    e = cudaFuncSetAttribute(fwdrows_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_f);
+    if (e != cudaSuccess) return e;
+    fwdrows_kernel<C><<<grid_fwd, kWarpsPerCta * 32, dyn_f, st>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     bwdtable_kernel<C, ROWS><<<grid_bwd, kWarpsPerCta * 32, dyn, st>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    finalize_kernel<<<dim3((unsigned)((p.max_lt + 1 + 127) / 128), (unsigned)(p.pair_hi - p.pair_lo)), 128, 0, st>>>(p);
     return cudaGetLastError();
 }
 template <int C>
@@ -960,9 +1185,10 @@ cudaError_t launch_fit(const KParams &p, int C, int grid, double *acc90, cudaStr
 int warps_per_cta() { return kWarpsPerCta; }
 int frow_slots_per_row(int C) { return 32 * C + 2 * kHalo; }
 int frow_extra_rows() { return kRowShift + kRowsAbove; }
-int modtable_ctas_per_sm(int C) { return C == 2 ? 3 : 1; }
-int fwdrows_ctas_per_sm(int C) { return C == 2 ? 5 : 2; }
-int fwdinfo_words() { return ((kInfoEv + kEvWords + 15) / 16) * 16; }
+int modtable_ctas_per_sm(int C) { return C == 2 ? 4 : 1; }
+int fwdrows_ctas_per_sm(int C) { return C == 2 ? 6 : 3; }
+int fwdinfo_words() { return 16; }
+int fwd_pad_rows(int C) { return 32 * C + 16; }
 
 // ---- FP32 peak micro-benchmark (roofline denominator) ---------------------------------------------------
 // 16 independent accumulators per thread so the 4-cycle FMA latency is covered at 8 warps per scheduler.
