@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libjtkgpu.so")
+# JTK_LIB_PATH: kernel-tuning experiments load an alternative build of the SAME library (tools/prof.py); never a fallback
+LIB_PATH = os.environ.get("JTK_LIB_PATH") or os.path.join(HERE, "libjtkgpu.so")
 
 NUM_ROW = 14
 COPY_SIZE = 3

@@ -37,6 +37,10 @@ constexpr int kRingRows = 16;   // row slots (four groups of four rows)
 constexpr int kRingMargin = 3;  // copies of the rows at the other end of the ring, on both sides
 constexpr int kRowShift = 4;    // ring / group index of anti-diagonal s is rho = s + kRowShift (four zero rows below s = 0)
 constexpr int kRowsAbove = 8;   // rows past the last anti-diagonal that exist in the scratch (the first three read as zero)
+#ifndef JTK_BWD_UNROLL
+#define JTK_BWD_UNROLL 4
+#endif
+constexpr int kBwdUnroll = JTK_BWD_UNROLL; // steps of the fast backward block unrolled by the compiler
 constexpr int kHalo = 4;        // forward rows carry 4 replicated slots on both sides: neighbours need no wrap-around
 
 // ---- small helpers --------------------------------------------------------------------------------------
@@ -341,7 +345,10 @@ template <int C> struct BwdState {
     f2 Xp[C][3], Xm[C][3];             // (sum toM*gM, sum toD*gD) of the copy / deletion cuts
 };
 
-// One anti-diagonal.  rp = this lane's first slot of forward row s inside the ring; row s+e, slot+e is rp[e*RS + e].
+// One anti-diagonal.  Backward slot mapping (v8): lane l owns slots sigma = l + 32*c, so every forward-row load of a warp
+// is one contiguous run of 8-byte words (no shared-memory bank conflicts) and the slots that leave the band one after the
+// other sit in neighbouring lanes with the same c.  rp = slot `lane` of forward row s inside the ring; row s+e, slot
+// sigma+e is rp[32*c + e*RS + e].
 // CORR: a rescale lies within rows s-2 .. s+3 (products that pair two rows get their exact power-of-two correction);
 // FIRST: s = nd-1, the terminal cell is injected.
 template <int C, int ROWS, bool CORR, bool FIRST>
@@ -353,10 +360,7 @@ __device__ __forceinline__ void bwd_step(const PairCtx &pc, const Coef &a, BwdSt
     constexpr int NXP = (ROWS == 14) ? 3 : 0;
     f2 F0[C];
 #pragma unroll
-    for (int c = 0; c < C; c += 2) {
-        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(rp + c);
-        F0[c] = v.x; F0[c + 1] = v.y;
-    }
+    for (int c = 0; c < C; c++) F0[c] = rp[32 * c];
 #pragma unroll
     for (int c = 0; c < C; c++) {
         const bool valid = (unsigned)st.x[c] <= (unsigned)W;
@@ -393,13 +397,13 @@ __device__ __forceinline__ void bwd_step(const PairCtx &pc, const Coef &a, BwdSt
         const f2 g = mk2(gM, gD);
 #pragma unroll
         for (int e = 1; e <= NXM; e++) {
-            const f2 Fe = rp[c - e * RS - e];
+            const f2 Fe = rp[32 * c - e * RS - e];
             if (CORR) acc2(st.Xm[c][e - 1], mul2(Fe, g), bc2(ce[3 - e]));
             else acc2(st.Xm[c][e - 1], Fe, g);
         }
 #pragma unroll
         for (int e = 1; e <= NXP; e++) {
-            const f2 Fe = rp[c + e * RS + e];
+            const f2 Fe = rp[32 * c + e * RS + e];
             if (CORR) acc2(st.Xp[c][e - 1], mul2(Fe, g), bc2(ce[3 + e]));
             else acc2(st.Xp[c][e - 1], Fe, g);
         }
@@ -453,7 +457,7 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
     BwdState<C> st;
 #pragma unroll
     for (int c = 0; c < C; c++) {
-        const int sigma = lane * C + c;
+        const int sigma = lane + 32 * c;
         const int d = (Lt - sigma) & (NSLOT - 1);
         st.j[c] = Lt - d;      // largest column <= Lt owned by this slot
         st.x[c] = d + pc.r;    // row i = Lr + d on the last anti-diagonal, window starts at row Lr - r
@@ -466,8 +470,6 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
 #pragma unroll
         for (int e = 0; e < 3; e++) { st.Xp[c][e] = 0ull; st.Xm[c][e] = 0ull; }
     }
-    int xmin = pc.r;   // smallest x over the slots (warp-uniform)
-    int jd = Lt;       // the column that leaves the band next (warp-uniform)
 
     // a finished column leaves its 16 raw sums in the pair's scratch (64 B, one lane); finalize_kernel turns them into the
     // 14 log-ratios of the table
@@ -479,40 +481,40 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
         __stcg(sg + 3, make_float4(lo2(st.Xp[c][2]) + hi2(st.Xp[c][2]), lo2(st.Xm[c][0]) + hi2(st.Xm[c][0]),
                                    lo2(st.Xm[c][1]) + hi2(st.Xm[c][1]), lo2(st.Xm[c][2]) + hi2(st.Xm[c][2])));
     };
-    // hand (B_M, B_D) to the left-hand neighbour column (slot-1, wrapping)
+    // hand (B_M, B_D) to the left-hand neighbour column: slot sigma receives from slot sigma+1 = lane+1 with the same c;
+    // past lane 31 that is lane 0 with c+1 (wrapping), so lane 0 sends its values rotated by one
+    const bool lane0 = lane == 0;
     auto hand_off = [&](f2 (&bMD)[C]) {
-        const float rM = __shfl_sync(kFull, lo2(bMD[0]), (lane + 1) & 31);
-        const float rD = __shfl_sync(kFull, hi2(bMD[0]), (lane + 1) & 31);
 #pragma unroll
-        for (int c = 0; c < C - 1; c++) { st.inMb[c] = st.inMa[c]; st.inMa[c] = lo2(bMD[c + 1]); st.inD[c] = hi2(bMD[c + 1]); }
-        st.inMb[C - 1] = st.inMa[C - 1]; st.inMa[C - 1] = rM; st.inD[C - 1] = rD;
+        for (int c = 0; c < C; c++) {
+            const f2 own = bMD[c], nxt = bMD[(c + 1) % C];
+            const float sM = lane0 ? lo2(nxt) : lo2(own);
+            const float sD = lane0 ? hi2(nxt) : hi2(own);
+            const float rM = __shfl_sync(kFull, sM, (lane + 1) & 31);
+            const float rD = __shfl_sync(kFull, sD, (lane + 1) & 31);
+            st.inMb[c] = st.inMa[c]; st.inMa[c] = rM; st.inD[c] = rD;
+        }
     };
-    // anti-diagonal s -> s-1 when the centre stays (guide bit 0): every cell moves one row down inside the window and
-    // the slot at the bottom of the band is done: its column sums are staged and the slot moves on to column j - NSLOT
-    auto shift_down = [&](int s) {
-        if (xmin > 0) {
-            xmin--;
+    // Anti-diagonal s -> s-1 when the centre stays (guide bit 0): every cell moves one row down inside the window
+    // (x--), and the slot at the bottom of the band has seen its last in-band cell.  Retirement is DEFERRED to the end of
+    // the block of four anti-diagonals: a slot with x < 0 is masked like any cell outside the band, the ring has
+    // NSLOT - (W+1) >= 3 spare slots, and the column j - NSLOT that the slot takes over cannot enter the band before the
+    // first step of the next block.  The (on average two) slots that retire in one block are neighbouring lanes with the
+    // same c, so one pass through the flush code serves them all.
+    auto retire = [&]() {
 #pragma unroll
-            for (int c = 0; c < C; c++) st.x[c]--;
-        } else {
+        for (int c = 0; c < C; c++) {
+            if (st.x[c] < 0) {
+                if (st.j[c] >= 0) flush_col(c);
+                st.j[c] -= NSLOT;
+                st.x[c] += NSLOT;
+                st.tcB[c] = pc.sEM + (st.tcn[c] << 5); // fetched one column-life ago; the window comes with the next reload
+                st.tcn[c] = pc.Tb[st.j[c] + 1 - NSLOT];
+                st.Vs[c] = st.Vn[c] = 0.f;
+                st.S01[c] = st.S23[c] = st.N01[c] = st.N23[c] = 0ull;
 #pragma unroll
-            for (int c = 0; c < C; c++) {
-                if (st.x[c] == 0) {
-                    if (st.j[c] >= 0) flush_col(c);
-                    st.j[c] -= NSLOT;
-                    st.x[c] = NSLOT - 1;
-                    st.tcB[c] = pc.sEM + (st.tcn[c] << 5); // fetched one column-life ago; the window comes with the next reload
-                    st.tcn[c] = pc.Tb[st.j[c] + 1 - NSLOT];
-                    (void)s;
-                    st.Vs[c] = st.Vn[c] = 0.f;
-                    st.S01[c] = st.S23[c] = st.N01[c] = st.N23[c] = 0ull;
-#pragma unroll
-                    for (int e = 0; e < 3; e++) { st.Xp[c][e] = 0ull; st.Xm[c][e] = 0ull; }
-                } else {
-                    st.x[c]--;
-                }
+                for (int e = 0; e < 3; e++) { st.Xp[c][e] = 0ull; st.Xm[c][e] = 0ull; }
             }
-            jd--;
         }
     };
     auto reload = [&](int s) {
@@ -521,7 +523,7 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
     };
     // generic step: any s, exact corrections, ring slot computed from s
     auto slow_step = [&](int s) {
-        const f2 *rp = ring + (size_t)(((s + kRowShift) & (kRingRows - 1)) + kRingMargin) * RS + kHalo + lane * C;
+        const f2 *rp = ring + (size_t)(((s + kRowShift) & (kRingRows - 1)) + kRingMargin) * RS + kHalo + lane;
         if (s == nd - 1 || (s & 3) == 3) reload(s);
         // cumulative scale exponent of forward row t: rescales happen on the last row of a block of four, kb[q] = exponent
         // after block q
@@ -541,8 +543,9 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
 #pragma unroll
                 for (int c = 0; c < C; c++) { st.BI[c] *= sc; st.BMo[c] *= sc; st.inD[c] *= sc; st.inMa[c] *= sc; st.inMb[c] *= sc; }
             }
-            const unsigned b = (pc.bw[(s - 1) >> 5] >> ((s - 1) & 31)) & 1u;
-            if (b == 0u) shift_down(s);
+            const int dec = (int)(((pc.bw[(s - 1) >> 5] >> ((s - 1) & 31)) & 1u) ^ 1u);
+#pragma unroll
+            for (int c = 0; c < C; c++) st.x[c] -= dec;
         }
     };
 
@@ -566,23 +569,28 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
         const bool clean = kb1 == kb2 && kb2 == kb3;
         kb1 = kb2; kb2 = kb3; kb3 = kb[q - 4];
         if (s_hi <= nd - 2 && q >= 2 && clean) {
-            const f2 *rp = ring + (size_t)(4 * (q & 3) + 3 + kRingMargin) * RS + kHalo + lane * C;
+            const f2 *rp = ring + (size_t)(4 * (q & 3) + 3 + kRingMargin) * RS + kHalo + lane;
             reload(s_hi);
             // guide bits 4q-5 .. 4q-2 (fetched one block ahead): step k (s = s_hi - k) moves on with bit 4q-2-k
             const unsigned nib = nib_cur;
-#pragma unroll 1
-            for (int k = 0; k < 4; k++, rp -= RS) {
+#pragma unroll kBwdUnroll
+            for (int k = 0; k < 4; k++) {
                 f2 bMD[C];
-                bwd_step<C, ROWS, false, false>(pc, a, st, rp, W, nullptr, boff, bMD);
+                bwd_step<C, ROWS, false, false>(pc, a, st, rp - k * RS, W, nullptr, boff, bMD);
                 hand_off(bMD);
-                if (((nib >> (3 - k)) & 1u) == 0u) shift_down(s_hi - k);
+                const int dec = (int)(((nib >> (3 - k)) & 1u) ^ 1u);
+#pragma unroll
+                for (int c = 0; c < C; c++) st.x[c] -= dec;
             }
         } else {
             for (int s = min(s_hi, nd - 1); s >= 4 * q - 4; --s) slow_step(s);
         }
+        retire();
     }
-    // the columns still in the window after s = 0 (0 .. r) leave it in the same order, block by block
-    while (jd >= 0) shift_down(0);
+    // the columns still in the window after s = 0 (0 .. r) are complete
+#pragma unroll
+    for (int c = 0; c < C; c++)
+        if (st.j[c] >= 0) flush_col(c);
 }
 
 // ------------------------------------------------------------------------------------------------
