@@ -55,36 +55,92 @@ def make_workload(rank: int, n_chunks: int, n_reads: int, length: int):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """Samples SM clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).
+
+    The samples are taken in-process through NVML (the library behind nvidia-smi: same counters, same reason bits).  A
+    polling `nvidia-smi --query-gpu ... -lms 100` child was measured to stall the GPU for milliseconds per sample (a 150 ms
+    timed region read 40 % slow with it, profiles/README.md); JTK_BENCH_SAMPLER=smi selects it anyway, =none disables."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, period_s: float = 0.05):
         self.index = index
+        self.period = period_s
         self.lines = []
+        self.samples = []          # (sm_mhz, reason bitmask)
         self.proc = None
+        self.thread = None
+        self.stop_flag = threading.Event()
+        self.mode = os.environ.get("JTK_BENCH_SAMPLER", "nvml")
+        self.mx = None
+        self.nv = None
 
     def start(self):
+        if self.mode == "none":
+            return
+        if self.mode == "nvml":
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = self.index
+                if vis:
+                    try:
+                        idx = int(vis.split(",")[self.index])
+                    except (ValueError, IndexError):
+                        idx = self.index
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+                self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+                self.nv = pynvml
+                self.thread = threading.Thread(target=self._poll, daemon=True)
+                self.thread.start()
+                return
+            except Exception:
+                self.nv = None
+                self.mode = "smi"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((sm, rs))
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
 
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nv is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=1.0)
+            nv = self.nv
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            reasons = sorted(n for n, b in bits.items() if any(rs & b for _, rs in self.samples))
+            sm = [x for x, _ in self.samples]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.mx, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml in-process, %d ms period" % int(self.period * 1e3)}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler unavailable"], "source": self.mode}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
@@ -93,11 +149,11 @@ class ClockSampler:
                 sm.append(float(f[0])); mx = float(f[1])
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
+            for n, v in zip(self.NAMES, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 200"}
 
 
 def ncu_traffic(n_pairs):

@@ -680,27 +680,51 @@ __device__ __forceinline__ float min_req_of(const float *min_req, int H, int row
     return min_req[type * H + h - 1];
 }
 
+// The reads of one chunk as (table offset, strand model), staged in shared memory by the whole CTA: the per-entry loops
+// below then issue independent, coalesced loads instead of a tp_ids -> pairs -> delta chain per read.
+constexpr int kReadTile = 256;
+struct ReadRef { unsigned long long tab_off; int model; int pad_; };
+__device__ __forceinline__ int stage_reads(ReadRef *sh, const DevPair *__restrict__ pairs, const uint32_t *__restrict__ tp_ids,
+                                           uint32_t k0, uint32_t k1) {
+    const int n = (int)min(k1 - k0, (uint32_t)kReadTile);
+    __syncthreads(); // the previous tile is no longer read
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const DevPair &p = pairs[tp_ids[k0 + k]];
+        sh[k].tab_off = p.tab_off; sh[k].model = p.model;
+    }
+    __syncthreads();
+    return n;
+}
+
 __global__ void colstats_kernel(const float *__restrict__ delta, const DevPair *__restrict__ pairs,
                                 const uint32_t *__restrict__ tp_start, const uint32_t *__restrict__ tp_ids,
                                 const uint32_t *__restrict__ tmpl_len, const uint8_t *__restrict__ homop,
                                 const uint32_t *__restrict__ homop_off, const unsigned long long *__restrict__ stat_off,
                                 const float *__restrict__ min_req, int H, float pos_thr, jtk_colstat *__restrict__ out) {
+    __shared__ ReadRef rr[kReadTile];
     const int t = blockIdx.y;
     const uint32_t n_ent = (tmpl_len[t] + 1) * kNumRow;
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_ent) return;
-    const uint32_t j = e / kNumRow, row = e % kNumRow;
+    if (blockIdx.x * blockDim.x >= n_ent) return;
+    const bool live = e < n_ent;
+    const uint32_t j = live ? e / kNumRow : 0u, row = e % kNumRow;
     const float thr = min_req_of(min_req, H, row, homop[homop_off[t] + j]);
     double sum = 0.0;
     int cnt = 0;
     unsigned sc[4] = { 0, 0, 0, 0 };
-    for (uint32_t k = tp_start[t]; k < tp_start[t + 1]; k++) {
-        const DevPair &p = pairs[tp_ids[k]];
-        float x = delta[p.tab_off + e];
-        if (fabsf(x) < thr) x = 0.f;
-        if (x > pos_thr) { sum += (double)x; cnt++; }
-        if (fabsf(x) > 1e-4f) sc[(p.model == 0 ? 2 : 0) + (x > 0.f ? 1 : 0)]++;
+    const uint32_t k_end = tp_start[t + 1];
+    for (uint32_t k0 = tp_start[t]; k0 < k_end; k0 += kReadTile) {
+        const int n = stage_reads(rr, pairs, tp_ids, k0, k_end);
+        if (!live) continue;
+#pragma unroll 4
+        for (int k = 0; k < n; k++) {
+            float x = delta[rr[k].tab_off + e];
+            if (fabsf(x) < thr) x = 0.f;
+            if (x > pos_thr) { sum += (double)x; cnt++; }
+            if (fabsf(x) > 1e-4f) sc[(rr[k].model == 0 ? 2 : 0) + (x > 0.f ? 1 : 0)]++;
+        }
     }
+    if (!live) return;
     jtk_colstat o;
     o.sum = sum; o.count = cnt;
     o.sc[0] = (uint16_t)min(sc[0], 65535u); o.sc[1] = (uint16_t)min(sc[1], 65535u);
@@ -746,26 +770,30 @@ struct CandArgs {
 };
 
 __global__ void candidates_kernel(CandArgs a) {
+    __shared__ ReadRef rr[kReadTile];
     const int t = blockIdx.y;
     const uint32_t Lt = a.tmpl_len[t];
     const uint32_t n_ent = (Lt + 1) * kNumRow;
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_ent) return;
-    const uint32_t j = e / kNumRow, row = e % kNumRow;
+    if (blockIdx.x * blockDim.x >= n_ent) return;
+    const uint32_t j = min(e, n_ent - 1) / kNumRow, row = e % kNumRow;
     const uint32_t temp_len = Lt + 1; // profile length in positions (pseudo_mcmc.rs:439)
-    if (!(7u <= j && j + 7u <= temp_len)) return;   // MASK_LENGTH (:443-446)
-    if (!(row < 8u || row == 8u + JTK_COPY_SIZE)) return; // (:447)
+    bool live = e < n_ent;
+    if (!(7u <= j && j + 7u <= temp_len)) live = false;   // MASK_LENGTH (:443-446)
+    if (!(row < 8u || row == 8u + JTK_COPY_SIZE)) live = false; // (:447)
     const uint8_t *hp = a.homop + a.homop_off[t];
     const uint8_t *tc = a.codes + a.tmpl_code_off[t] + 1; // tc[x] = code of t[x]
     const int type = row < 4 ? 0 : (row < 8 + JTK_COPY_SIZE ? 2 : 1); // Subst, Ins (incl. copy), Del
     // is_in_short_homopolymer (:497-514); j < Lt holds for every unmasked position
-    if (type == 2) {
-        const uint32_t r = row - 4;
-        const uint32_t prev_len = hp[j - 1] + (r < 4u && tc[j - 1] == r ? 1u : 0u);
-        const uint32_t next_len = hp[j] + (r < 4u && tc[j] == r ? 1u : 0u);
-        if (!(prev_len <= 2u && next_len <= 2u)) return;
-    } else if (type == 1) {
-        if (!(hp[j] <= 2u)) return;
+    if (live) {
+        if (type == 2) {
+            const uint32_t r = row - 4;
+            const uint32_t prev_len = hp[j - 1] + (r < 4u && tc[j - 1] == r ? 1u : 0u);
+            const uint32_t next_len = hp[j] + (r < 4u && tc[j] == r ? 1u : 0u);
+            if (!(prev_len <= 2u && next_len <= 2u)) live = false;
+        } else if (type == 1) {
+            if (!(hp[j] <= 2u)) live = false;
+        }
     }
     const int hl = min(max((int)hp[j], 1), a.H);
     const float thr = a.min_req[type * a.H + hl - 1];
@@ -773,13 +801,18 @@ __global__ void candidates_kernel(CandArgs a) {
     unsigned cnt = 0;
     unsigned sc[4] = { 0, 0, 0, 0 };
     const uint32_t k0 = a.tp_start[t], k1 = a.tp_start[t + 1];
-    for (uint32_t k = k0; k < k1; k++) {
-        const DevPair &p = a.pairs[a.tp_ids[k]];
-        float x = a.delta[p.tab_off + e];
-        if (fabsf(x) < thr) x = 0.f;
-        if (x > a.pos_thr) { sum = __dadd_rn(sum, (double)x); cnt++; }
-        if (fabsf(x) > 1e-4f) sc[(p.model == 0 ? 2 : 0) + (x > 0.f ? 1 : 0)]++;
+    for (uint32_t kt = k0; kt < k1; kt += kReadTile) {
+        const int nr = stage_reads(rr, a.pairs, a.tp_ids, kt, k1);
+        if (!live) continue;
+#pragma unroll 4
+        for (int k = 0; k < nr; k++) {
+            float x = a.delta[rr[k].tab_off + e];
+            if (fabsf(x) < thr) x = 0.f;
+            if (x > a.pos_thr) { sum = __dadd_rn(sum, (double)x); cnt++; }
+            if (fabsf(x) > 1e-4f) sc[(rr[k].model == 0 ? 2 : 0) + (x > 0.f ? 1 : 0)]++;
+        }
     }
+    if (!live) return;
     const uint32_t n = k1 - k0;
     // has_small_pvalue (:476-495)
     const double pvalue = a.pv[a.pv_off[t] + (size_t)(type * a.H + hl - 1) * (n + 1) + cnt];
