@@ -9,6 +9,10 @@
 #include <cstdio>
 #include <cstring>
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <memory>
 #include <mutex>
 #include <cstdlib>
 #include <string>
@@ -25,7 +29,7 @@ cudaError_t launch_likelihood(const KParams &p, int C, int grid, cudaStream_t st
 int warps_per_cta();
 int frow_slots_per_row(int C);
 int frow_extra_rows();
-int modtable_ctas_per_sm(int C);
+int modtable_ctas_per_sm(int C, int rows);
 cudaError_t launch_fit(const KParams &p, int C, int grid, double *acc90, cudaStream_t st);
 cudaError_t launch_fp32_peak(int mode, int blocks, int threads, int iters, float *sink, cudaStream_t st);
 } // namespace jtk
@@ -110,15 +114,17 @@ template <typename T> struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-inline uint8_t base_code(uint8_t c) {
-    switch (c) {
-    case 'A': case 'a': return 0;
-    case 'C': case 'c': return 1;
-    case 'G': case 'g': return 2;
-    case 'T': case 't': return 3;
-    default: return 0;
+// A/a -> 0, C/c -> 1, G/g -> 2, T/t -> 3, anything else -> 0.  A table, not a switch: on random bases the switch
+// mispredicted on most calls and the read encoder spent 8 of its 9 ms per 4 800 pairs there.
+struct BaseCodeLut {
+    uint8_t v[256];
+    constexpr BaseCodeLut() : v() {
+        for (int k = 0; k < 256; k++) v[k] = 0;
+        v['C'] = v['c'] = 1; v['G'] = v['g'] = 2; v['T'] = v['t'] = 3;
     }
-}
+};
+static constexpr BaseCodeLut kBaseCode{};
+inline uint8_t base_code(uint8_t c) { return kBaseCode.v[c]; }
 
 void pack_model(const jtk_hmm_params *h, float *m) {
     std::memset(m, 0, sizeof(float) * kModelFloats);
@@ -174,6 +180,85 @@ bool edit_ops(const uint8_t *t, int Lt, const uint8_t *q, int Lr, int radius, st
 
 } // namespace
 
+// Host worker threads of one context, parked between calls (jtk_batch_create encodes every batch on them; spawning 2 x 15
+// threads per batch cost ~1 ms of a 10 ms create).  run(n, grain, fn) executes fn(k) for k in [0, n) in dynamic chunks of
+// `grain` items on the workers and the calling thread, and returns when all are done.
+class HostPool {
+  public:
+    explicit HostPool(int n_threads) {
+        for (int t = 1; t < n_threads; t++) workers_.emplace_back([this]() { loop(); });
+    }
+    ~HostPool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    int size() const { return (int)workers_.size() + 1; }
+    template <typename F> void run(int n, int grain, F fn) {
+        if (n <= 0) return;
+        if (workers_.empty() || n <= grain) { for (int k = 0; k < n; k++) fn(k); return; }
+        std::function<void(int)> f = fn;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &f; n_ = n; grain_ = grain; next_.store(0); active_ = (int)workers_.size(); gen_++;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [this]() { return active_ == 0; });
+        fn_ = nullptr;
+    }
+
+  private:
+    void work() {
+        for (;;) {
+            const int k0 = next_.fetch_add(grain_);
+            if (k0 >= n_) break;
+            const int k1 = std::min(n_, k0 + grain_);
+            for (int k = k0; k < k1; k++) (*fn_)(k);
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&]() { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+            }
+            work();
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--active_ == 0) done_.notify_one();
+            }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int)> *fn_ = nullptr;
+    int n_ = 0, grain_ = 1, active_ = 0;
+    std::atomic<int> next_{0};
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
+// Small host -> device parameter blocks (models, thresholds, offsets) are uploaded only when their bytes change: a
+// cudaMemcpyAsync from pageable memory synchronises the stream first, so repeating it every call stops the host from
+// queueing launches ahead of the GPU (each step then pays a host wake-up; 7.3 -> 11.3 ms per step on a busy host).
+struct SmallUpload {
+    std::vector<uint8_t> last;
+    const void *dst = nullptr;
+    cudaError_t put(void *d, const void *src, size_t bytes, cudaStream_t st) {
+        if (d == dst && last.size() == bytes && std::memcmp(last.data(), src, bytes) == 0) return cudaSuccess;
+        cudaError_t e = cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) { last.assign((const uint8_t *)src, (const uint8_t *)src + bytes); dst = d; }
+        else { last.clear(); dst = nullptr; }
+        return e;
+    }
+};
+
 struct jtk_ctx {
     int device = 0;
     int sm_count = 0;
@@ -188,6 +273,8 @@ struct jtk_ctx {
     bool timing_pending = false;
     DevPool pool;             // device blocks recycled between batches
     int host_threads = 1;     // threads of the host-side encoders (JTK_HOST_THREADS, default: all cores, at most 32)
+    std::unique_ptr<HostPool> hpool;
+    SmallUpload up_models, up_minreq;
     // device buffers
     DevBuf<float> d_models;
     DevBuf<float2> d_frows;   // per-warp forward rows (scratch shared by all batches of this ctx)
@@ -255,6 +342,7 @@ int jtk_ctx_create(int device, size_t workspace_bytes, jtk_ctx **out) {
         int nt = (int)std::thread::hardware_concurrency();
         if (const char *env = std::getenv("JTK_HOST_THREADS")) nt = std::atoi(env);
         ctx->host_threads = std::max(1, std::min(nt, 32));
+        ctx->hpool.reset(new HostPool(ctx->host_threads));
         if (const char *env = std::getenv("JTK_SCRATCH_MB")) ctx->scratch_bytes = (size_t)std::max(64, std::atoi(env)) << 20;
     }
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -336,6 +424,7 @@ struct jtk_batch {
     DevBuf<uint32_t> d_tmpl_code_off; // codes[tmpl_code_off[t] + j + 1] = code of t[j]
     std::vector<uint32_t> tmpl_code_off;
     DevBuf<unsigned long long> d_stat_off;
+    SmallUpload up_stat_off;
     DevBuf<jtk_colstat> d_stats;
     void attach(DevPool *pool) {
         d_pairs.pool = pool; d_codes.pool = pool; d_bits.pool = pool; d_delta.pool = pool; d_lk.pool = pool;
@@ -351,6 +440,20 @@ struct jtk_batch {
 };
 
 namespace {
+
+// JTK_TIMING=1: wall-clock phases of jtk_batch_create on stderr (tools/e2e_phases.py)
+struct PhaseTimer {
+    bool on; std::chrono::steady_clock::time_point t0; std::string out;
+    PhaseTimer() : on(std::getenv("JTK_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        char buf[96];
+        std::snprintf(buf, sizeof buf, " %s=%.3fms", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        out += buf; t0 = t1;
+    }
+    ~PhaseTimer() { if (on && !out.empty()) std::fprintf(stderr, "[jtk timing]%s\n", out.c_str()); }
+};
 
 // Run fn(k) for k in [0, n) on the context's host threads (dynamic chunks of `grain` items).
 template <typename F> void parallel_for(int n_threads, int n, int grain, F fn) {
@@ -381,6 +484,7 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
                const uint32_t *ops_off, const uint8_t *strand, const uint32_t *tmpl_idx, size_t &code_bytes,
                size_t &bit_words, size_t &homop_bytes) {
     const int n_pairs = b->n_pairs, n_tmpl = b->n_tmpl, radius = b->radius;
+    PhaseTimer pt;
     size_t cb = 0, hb = 0;
     b->tmpl_len.resize((size_t)n_tmpl);
     b->homop_off.resize((size_t)n_tmpl + 1);
@@ -437,9 +541,9 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
     uint8_t *codes = ctx->h_codes.p;
     uint32_t *bits = ctx->h_bits.p;
     uint8_t *homop = ctx->h_homop.p;
-    const int nt = ctx->host_threads;
+    pt.mark("layout");
 
-    parallel_for(nt, n_tmpl, 4, [&](int t) {
+    ctx->hpool->run(n_tmpl, 4, [&](int t) {
         const uint8_t *s = tmpl_concat + tmpl_off[t];
         const size_t L = b->tmpl_len[t];
         uint8_t *c = codes + b->tmpl_code_off[t]; // c[j] = code of t[j-1]; 4 = none
@@ -457,12 +561,13 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
         h[L] = 1;
     });
 
+    pt.mark("templates");
     std::atomic<int> first_bad(n_pairs); // smallest failing pair so far (the error reported is the first in batch order)
     std::atomic<unsigned long long> cells_total(0);
     std::mutex bad_mu;
     std::string bad_text;
     int bad_code = 0;
-    parallel_for(nt, n_pairs, 16, [&](int p) {
+    ctx->hpool->run(n_pairs, 8, [&](int p) {
         if (first_bad.load(std::memory_order_relaxed) < p) return;
         const DevPair &dp = b->pairs[p];
         const uint32_t ti = tmpl_idx[p];
@@ -472,10 +577,11 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
         const size_t rlen = ((size_t)Lr + 2 + 3) & ~(size_t)3;
         uint8_t *rc = codes + dp.rb_off;
         std::memset(rc - kCodePad, 16, 2 * (size_t)kCodePad + rlen);
+        uint8_t cx = 4; // context = previous read base, 4 = none
         for (int i = 1; i <= Lr; i++) {
             const uint8_t qc = base_code(q[i - 1]);
-            const uint8_t cx = i >= 2 ? base_code(q[i - 2]) : 4;
             rc[i] = (uint8_t)((cx << 5) | (qc << 2));
+            cx = qc;
         }
         const uint8_t *ops;
         int n_ops;
@@ -497,32 +603,44 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
             ops = tl_ops.data();
             n_ops = (int)tl_ops.size();
         }
-        // guide path -> centre increments, and the in-band cell count on the way
+        // guide path -> centre increments, and the in-band cell count on the way.  The window of a diagonal is the full
+        // 2r+1 cells unless the path cell is within r of a matrix edge; the guide bits are assembled in a register.
         const size_t nwords = (size_t)(Lt + Lr + 1 + 31) / 32 + 1;
         uint32_t *bw = bits + dp.bits_off;
-        std::memset(bw, 0, nwords * sizeof(uint32_t));
         int i = 0, j = 0, s = 0;
+        const uint64_t full = (uint64_t)(2 * radius + 1);
         auto width = [&](int cen, int d) -> uint64_t {
+            const int jc = d - cen; // template coordinate of the centre cell
+            if (cen > radius && cen + radius < Lr && jc > radius && jc + radius < Lt) return full;
             const int lo = std::max(std::max(cen - radius, 0), d - Lt), hi = std::min(std::min(cen + radius, Lr), d);
             return hi >= lo ? (uint64_t)(hi - lo + 1) : 0;
         };
         uint64_t c = width(0, 0);
         bool bad = false;
+        uint32_t acc = 0;     // bits of word wi collected so far
+        size_t wi = 0;
+        auto put = [&](int pos) { // set bit `pos` (positions arrive in increasing order)
+            const size_t w = (size_t)pos >> 5;
+            if (w != wi) { bw[wi] = acc; for (size_t k = wi + 1; k < w; k++) bw[k] = 0; wi = w; acc = 0; }
+            acc |= 1u << (pos & 31);
+        };
         for (int k = 0; k < n_ops; k++) {
             const uint8_t op = ops[k];
             if (op <= JTK_OP_MISMATCH) {
                 if (i >= Lr || j >= Lt) { bad = true; break; }
                 c += width(i, s + 1);
-                i++; j++; bw[(s + 1) >> 5] |= 1u << ((s + 1) & 31); s += 2;
+                i++; j++; put(s + 1); s += 2;
                 c += width(i, s);
             } else if (op == JTK_OP_INS) {
                 if (i >= Lr) { bad = true; break; }
-                i++; bw[s >> 5] |= 1u << (s & 31); s += 1; c += width(i, s);
+                i++; put(s); s += 1; c += width(i, s);
             } else if (op == JTK_OP_DEL) {
                 if (j >= Lt) { bad = true; break; }
                 j++; s += 1; c += width(i, s);
             } else { fail(JTK_EINVAL, "invalid op code in pair " + std::to_string(p)); return; }
         }
+        bw[wi] = acc;
+        for (size_t k = wi + 1; k < nwords; k++) bw[k] = 0;
         if (bad || i != Lr || j != Lt) {
             fail(JTK_EINVAL, "ops of pair " + std::to_string(p) + " do not span (template, read): consumed (" + std::to_string(j) +
                                  "," + std::to_string(i) + ") of (" + std::to_string(Lt) + "," + std::to_string(Lr) + ")");
@@ -530,6 +648,7 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
         }
         cells_total.fetch_add(2 * c, std::memory_order_relaxed);
     });
+    pt.mark("pairs");
     if (first_bad.load() < n_pairs) return ctx->fail(bad_code ? bad_code : JTK_EINVAL, bad_text);
     std::memcpy(ctx->h_pairs.p, b->pairs.data(), sizeof(DevPair) * (size_t)n_pairs);
     ctx->tmpl_code_off = b->tmpl_code_off;
@@ -561,6 +680,7 @@ int batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_conc
     int rc = pack_batch(ctx, b, tmpl_concat, tmpl_off, read_concat, read_off, ops_concat, ops_off, strand, tmpl_idx,
                         code_bytes, bit_words, homop_bytes);
     if (rc) { b->release(); delete b; return rc; }
+    PhaseTimer pt;
     cudaStream_t st = ctx->stream;
     cudaError_t e;
 #define CB(call, what) do { if ((e = (call)) != cudaSuccess) { b->release(); delete b; return ctx->cuda_fail(e, what); } } while (0)
@@ -574,6 +694,7 @@ int batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_conc
     CB(b->d_homop_off.reserve(b->homop_off.size()), "cudaMalloc homop_off");
     CB(b->d_homop.reserve(homop_bytes), "cudaMalloc homop");
     CB(b->d_tmpl_code_off.reserve(b->tmpl_code_off.size()), "cudaMalloc tmpl_code_off");
+    pt.mark("reserve");
     CB(cudaMemcpyAsync(b->d_pairs.p, ctx->h_pairs.p, sizeof(DevPair) * (size_t)n_pairs, cudaMemcpyHostToDevice, st), "H2D pairs");
     CB(cudaMemcpyAsync(b->d_codes.p, ctx->h_codes.p, code_bytes, cudaMemcpyHostToDevice, st), "H2D codes");
     CB(cudaMemcpyAsync(b->d_bits.p, ctx->h_bits.p, bit_words * sizeof(uint32_t), cudaMemcpyHostToDevice, st), "H2D bits");
@@ -583,7 +704,9 @@ int batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_conc
     CB(cudaMemcpyAsync(b->d_tmpl_len.p, b->tmpl_len.data(), sizeof(uint32_t) * b->tmpl_len.size(), cudaMemcpyHostToDevice, st), "H2D tmpl_len");
     CB(cudaMemcpyAsync(b->d_homop_off.p, b->homop_off.data(), sizeof(uint32_t) * b->homop_off.size(), cudaMemcpyHostToDevice, st), "H2D homop_off");
     CB(cudaMemcpyAsync(b->d_tmpl_code_off.p, b->tmpl_code_off.data(), sizeof(uint32_t) * b->tmpl_code_off.size(), cudaMemcpyHostToDevice, st), "H2D tmpl_code_off");
+    pt.mark("h2d_issue");
     CB(cudaStreamSynchronize(st), "upload");
+    pt.mark("h2d_sync");
 #undef CB
     *out = b;
     return JTK_OK;
@@ -616,10 +739,13 @@ int batch_run(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev
         kp.max_lt = b->max_lt;
         const size_t per_pair = kp.frow_stride * sizeof(float2) + kp.kf_stride * sizeof(int32_t) + kp.fwdinfo_stride * 4 +
                                 kp.raw_stride * sizeof(float4);
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
         const size_t have = ctx->d_frows.cap * sizeof(float2);
-        size_t budget = std::min(ctx->scratch_bytes, (free_b + have) / 2);
+        size_t budget = ctx->scratch_bytes;
+        if ((size_t)b->n_pairs * per_pair > have) { // the scratch has to grow: see what the device can give
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            budget = std::min(budget, (free_b + have) / 2);
+        }
         per_wave = (int)std::max<size_t>(1, std::min<size_t>((size_t)b->n_pairs, budget / per_pair));
         CU(ctx->d_frows.reserve((size_t)per_wave * kp.frow_stride), "cudaMalloc forward rows");
         CU(ctx->d_kf.reserve((size_t)per_wave * kp.kf_stride), "cudaMalloc scale exponents");
@@ -627,7 +753,7 @@ int batch_run(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev
         CU(ctx->d_raw.reserve((size_t)per_wave * kp.raw_stride), "cudaMalloc raw column sums");
         CU(b->d_delta.reserve((size_t)b->table_floats), "cudaMalloc profiles");
     }
-    CU(cudaMemcpyAsync(ctx->d_models.p, models, sizeof(models), cudaMemcpyHostToDevice, st), "H2D models");
+    CU(ctx->up_models.put(ctx->d_models.p, models, sizeof(models), st), "H2D models");
     kp.pairs = b->d_pairs.p; kp.n_pairs = b->n_pairs;
     kp.codes = b->d_codes.p; kp.bits = b->d_bits.p; kp.models = ctx->d_models.p;
     kp.radius = b->radius; kp.rows = rows;
@@ -650,7 +776,7 @@ int batch_run(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev
         if (table) {
             // persistent CTAs: one wave of resident CTAs pulls pairs from the queue
             const int gf = std::min(ctas, ctx->sm_count * fwdrows_ctas_per_sm(b->C));
-            const int gb = std::min(ctas, ctx->sm_count * modtable_ctas_per_sm(b->C));
+            const int gb = std::min(ctas, ctx->sm_count * modtable_ctas_per_sm(b->C, rows));
             CU(launch_modtable(kp, b->C, gf, gb, st), "kernel launch");
             ctx->launches += 3;
         } else {
@@ -945,8 +1071,8 @@ int jtk_batch_colstats(jtk_batch *b, const float *min_req, int H, float pos_thr,
     CU(ctx->d_minreq.reserve((size_t)3 * H), "cudaMalloc min_req");
     CU(b->d_stat_off.reserve((size_t)b->n_tmpl), "cudaMalloc stat_off");
     CU(b->d_stats.reserve((size_t)total), "cudaMalloc stats");
-    CU(cudaMemcpyAsync(ctx->d_minreq.p, min_req, sizeof(float) * 3 * (size_t)H, cudaMemcpyHostToDevice, st), "H2D min_req");
-    CU(cudaMemcpyAsync(b->d_stat_off.p, stat_off, sizeof(uint64_t) * (size_t)b->n_tmpl, cudaMemcpyHostToDevice, st), "H2D stat_off");
+    CU(ctx->up_minreq.put(ctx->d_minreq.p, min_req, sizeof(float) * 3 * (size_t)H, st), "H2D min_req");
+    CU(b->up_stat_off.put(b->d_stat_off.p, stat_off, sizeof(uint64_t) * (size_t)b->n_tmpl, st), "H2D stat_off");
     dim3 grid((unsigned)(((size_t)(b->max_lt + 1) * kNumRow + 255) / 256), (unsigned)b->n_tmpl);
     colstats_kernel<<<grid, 256, 0, st>>>(b->d_delta.p, b->d_pairs.p, b->d_tp_start.p, b->d_tp_ids.p, b->d_tmpl_len.p,
                                          b->d_homop.p, b->d_homop_off.p, b->d_stat_off.p, ctx->d_minreq.p, H, pos_thr,
@@ -974,7 +1100,7 @@ int jtk_batch_gather(jtk_batch *b, int tmpl, const float *min_req, int H, const 
     CU(ctx->d_minreq.reserve((size_t)3 * H), "cudaMalloc min_req");
     CU(ctx->d_cols.reserve((size_t)D), "cudaMalloc cols");
     CU(ctx->d_gather.reserve((size_t)D * n_reads), "cudaMalloc gather");
-    CU(cudaMemcpyAsync(ctx->d_minreq.p, min_req, sizeof(float) * 3 * (size_t)H, cudaMemcpyHostToDevice, st), "H2D min_req");
+    CU(ctx->up_minreq.put(ctx->d_minreq.p, min_req, sizeof(float) * 3 * (size_t)H, st), "H2D min_req");
     CU(cudaMemcpyAsync(ctx->d_cols.p, cols, sizeof(uint32_t) * (size_t)D, cudaMemcpyHostToDevice, st), "H2D cols");
     const uint32_t n = n_reads * (uint32_t)D;
     gather_kernel<<<(n + 127) / 128, 128, 0, st>>>(b->d_delta.p, b->d_pairs.p, b->d_tp_ids.p, first, n_reads,
@@ -1037,7 +1163,7 @@ int run_candidates(jtk_batch *b, const jtk_gains *gains, const int32_t *copy_num
     CU(ctx->d_cand.reserve((size_t)cap), "cudaMalloc candidates");
     CU(ctx->d_counter.reserve(1), "cudaMalloc counter");
     double *d_pv = ctx->d_tabs.p, *d_prior = d_pv + sc.pv.size(), *d_exp = d_prior + sc.prior.size();
-    CU(cudaMemcpyAsync(ctx->d_minreq.p, sc.min_req.data(), sizeof(float) * 3 * (size_t)H, cudaMemcpyHostToDevice, st), "H2D min_req");
+    CU(ctx->up_minreq.put(ctx->d_minreq.p, sc.min_req.data(), sizeof(float) * 3 * (size_t)H, st), "H2D min_req");
     CU(cudaMemcpyAsync(d_pv, sc.pv.data(), sizeof(double) * sc.pv.size(), cudaMemcpyHostToDevice, st), "H2D pvalues");
     CU(cudaMemcpyAsync(d_prior, sc.prior.data(), sizeof(double) * sc.prior.size(), cudaMemcpyHostToDevice, st), "H2D prior");
     CU(cudaMemcpyAsync(d_exp, sc.expected.data(), sizeof(double) * sc.expected.size(), cudaMemcpyHostToDevice, st), "H2D expected");
@@ -1252,7 +1378,7 @@ int jtk_batch_colsums(jtk_batch *b, int take_num, double *out, const uint64_t *s
     for (int t = 0; t < b->n_tmpl; t++) total = std::max<uint64_t>(total, stat_off[t] + (uint64_t)(b->tmpl_len[t] + 1) * kNumRow);
     CU(b->d_stat_off.reserve((size_t)b->n_tmpl), "cudaMalloc stat_off");
     CU(ctx->d_gather.reserve((size_t)total), "cudaMalloc sums");
-    CU(cudaMemcpyAsync(b->d_stat_off.p, stat_off, sizeof(uint64_t) * (size_t)b->n_tmpl, cudaMemcpyHostToDevice, st), "H2D stat_off");
+    CU(b->up_stat_off.put(b->d_stat_off.p, stat_off, sizeof(uint64_t) * (size_t)b->n_tmpl, st), "H2D stat_off");
     dim3 grid((unsigned)(((size_t)(b->max_lt + 1) * kNumRow + 255) / 256), (unsigned)b->n_tmpl);
     colsums_kernel<<<grid, 256, 0, st>>>(b->d_delta.p, b->d_pairs.p, b->d_tp_start.p, b->d_tp_ids.p, b->d_tmpl_len.p,
                                         b->d_stat_off.p, take_num, ctx->d_gather.p);
@@ -1286,7 +1412,7 @@ int jtk_batch_expected_counts(jtk_batch *b, const jtk_hmm_params *fwd, const jtk
     CU(ctx->d_frows.reserve(slots * kp.frow_stride), "cudaMalloc forward rows");
     CU(ctx->d_kf.reserve(slots * kp.kf_stride), "cudaMalloc scale exponents");
     CU(ctx->d_gather.reserve(90), "cudaMalloc counts");
-    CU(cudaMemcpyAsync(ctx->d_models.p, models, sizeof(models), cudaMemcpyHostToDevice, st), "H2D models");
+    CU(ctx->up_models.put(ctx->d_models.p, models, sizeof(models), st), "H2D models");
     CU(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(int), st), "memset counter");
     CU(cudaMemsetAsync(ctx->d_gather.p, 0, sizeof(double) * 90, st), "memset counts");
     kp.pairs = b->d_pairs.p; kp.n_pairs = b->n_pairs;

@@ -41,7 +41,23 @@ constexpr int kRowsAbove = 8;   // rows past the last anti-diagonal that exist i
 #define JTK_BWD_UNROLL 4
 #endif
 constexpr int kBwdUnroll = JTK_BWD_UNROLL; // steps of the fast backward block unrolled by the compiler
-constexpr int kHalo = 4;        // forward rows carry 4 replicated slots on both sides: neighbours need no wrap-around
+// resident CTAs per SM of bwdtable_kernel<2, ROWS> (register cap 65536 / (128 * this)): the 14-row kernel carries 44
+// accumulators + 12 reused forward-row entries per lane and spills at 128 registers (152 without a cap -> 3 CTAs);
+// the 9-row kernel fits 128 registers (4 CTAs).  Measured: profiles/README.md, v9.
+#ifndef JTK_BWD_CTAS14
+#define JTK_BWD_CTAS14 3
+#endif
+#ifndef JTK_BWD_CTAS9
+#define JTK_BWD_CTAS9 4
+#endif
+constexpr int bwd_ctas_per_sm(int C, int rows) { return C == 2 ? (rows == 14 ? JTK_BWD_CTAS14 : JTK_BWD_CTAS9) : 1; }
+constexpr int kHalo = 4;        // (single-kernel forward_pass, STORE == 1) replicated slots on both sides of a row
+// Forward rows of the two-kernel modification table (v9): a row is C planes, plane c holds the slots sigma == c (mod C)
+// in slot order (plane c, index k = slot C*k + c), 32 entries + 2 replicated entries on both sides.  A backward lane
+// owns the C adjacent slots C*lane + c: its own entries and every neighbour sigma +- 1..3 sit at lane stride 8 bytes
+// (no shared-memory bank conflicts) at compile-time offsets from one per-lane pointer.
+constexpr int kPlaneHalo = 2;
+constexpr int kPlane = 32 + 2 * kPlaneHalo;
 
 // ---- small helpers --------------------------------------------------------------------------------------
 typedef unsigned long long f2; // two packed fp32 (lo, hi) in one 64-bit register pair
@@ -343,24 +359,36 @@ template <int C> struct BwdState {
     f2 S01[C], S23[C], N01[C], N23[C]; // substitution / insertion sums over the four bases
     float Vs[C], Vn[C];
     f2 Xp[C][3], Xm[C][3];             // (sum toM*gM, sum toD*gD) of the copy / deletion cuts
+    f2 cF[C][7];                       // forward-row entries slot c loaded on the previous step (c >= 1): slot c-1 reuses them
 };
 
-// One anti-diagonal.  Backward slot mapping (v8): lane l owns slots sigma = l + 32*c, so every forward-row load of a warp
-// is one contiguous run of 8-byte words (no shared-memory bank conflicts) and the slots that leave the band one after the
-// other sit in neighbouring lanes with the same c.  rp = slot `lane` of forward row s inside the ring; row s+e, slot
-// sigma+e is rp[32*c + e*RS + e].
+// One anti-diagonal.  Backward slot mapping (v9): lane l owns the C adjacent slots sigma = C*l + c.  rp = entry `lane` of
+// plane 0 of forward row s inside the ring; row s+e, slot sigma+e is plane (c+e) mod C, index l + floor((c+e)/C).
+// Cells (i, j) [slot c, this step] and (i, j+1) [slot c+1, previous step] lie on the same read row, so the entries
+// slot c needs -- forward row s+e, slot sigma+e, e = -3..3 -- are the SAME ADDRESSES slot c+1 read one step earlier with
+// e-1: only slot C-1 loads its seven entries, every other slot loads one (e = -3) and takes six from the registers of
+// its right-hand neighbour (st.cF).  This is an address identity: it holds whatever columns the slots currently carry.
 // CORR: a rescale lies within rows s-2 .. s+3 (products that pair two rows get their exact power-of-two correction);
-// FIRST: s = nd-1, the terminal cell is injected.
+// FIRST: s = nd-1, the terminal cell is injected (and nothing is carried yet).
+template <int C> __device__ __forceinline__ constexpr int frow_pos(int c, int e) {
+    // offset (in entries) of row s+e, slot sigma+e from rp, for slot c of the lane
+    return (((c + e) % C + C) % C) * kPlane + ((c + e) - (((c + e) % C + C) % C)) / C + e * (C * kPlane);
+}
+
 template <int C, int ROWS, bool CORR, bool FIRST>
 __device__ __forceinline__ void bwd_step(const PairCtx &pc, const Coef &a, BwdState<C> &st, const f2 *rp, const int W,
                                          const float *ce, const float boff, f2 (&bMD)[C]) {
-    constexpr int NSLOT = 32 * C;
-    constexpr int RS = NSLOT + 2 * kHalo;
     constexpr int NXM = (ROWS == 14) ? 3 : 1;
     constexpr int NXP = (ROWS == 14) ? 3 : 0;
-    f2 F0[C];
+    f2 F[C][7]; // F[c][e + 3] = forward row s+e, slot sigma+e
 #pragma unroll
-    for (int c = 0; c < C; c++) F0[c] = rp[32 * c];
+    for (int c = C - 1; c >= 0; c--) {
+#pragma unroll
+        for (int e = -NXM; e <= NXP; e++) {
+            const bool reuse = !FIRST && c < C - 1 && e - 1 >= -NXM;
+            F[c][e + 3] = reuse ? st.cF[c + 1][e + 2] : rp[frow_pos<C>(c, e)];
+        }
+    }
 #pragma unroll
     for (int c = 0; c < C; c++) {
         const bool valid = (unsigned)st.x[c] <= (unsigned)W;
@@ -383,7 +411,8 @@ __device__ __forceinline__ void bwd_step(const PairCtx &pc, const Coef &a, BwdSt
             i_ = term ? boff : 0.f;
         }
         // ---- table reduction for cell (i, j) ----
-        const float f0m = lo2(F0[c]), f0d = hi2(F0[c]);
+        const f2 F0 = F[c][3];
+        const float f0m = lo2(F0), f0d = hi2(F0);
         const f2 U = bc2(f0m * st.inMb[c]);
         acc2(st.S01[c], U, ec01);
         acc2(st.S23[c], U, ec23);
@@ -397,18 +426,24 @@ __device__ __forceinline__ void bwd_step(const PairCtx &pc, const Coef &a, BwdSt
         const f2 g = mk2(gM, gD);
 #pragma unroll
         for (int e = 1; e <= NXM; e++) {
-            const f2 Fe = rp[32 * c - e * RS - e];
+            const f2 Fe = F[c][3 - e];
             if (CORR) acc2(st.Xm[c][e - 1], mul2(Fe, g), bc2(ce[3 - e]));
             else acc2(st.Xm[c][e - 1], Fe, g);
         }
 #pragma unroll
         for (int e = 1; e <= NXP; e++) {
-            const f2 Fe = rp[32 * c + e * RS + e];
+            const f2 Fe = F[c][3 + e];
             if (CORR) acc2(st.Xp[c][e - 1], mul2(Fe, g), bc2(ce[3 + e]));
             else acc2(st.Xp[c][e - 1], Fe, g);
         }
         bMD[c] = md;
         st.BI[c] = i_; st.BMo[c] = lo2(md);
+    }
+    // what the left-hand neighbour slot reuses on the next step
+#pragma unroll
+    for (int c = 1; c < C; c++) {
+#pragma unroll
+        for (int e = -NXM; e <= NXP - 1; e++) st.cF[c][e + 3] = F[c][e + 3];
     }
 }
 
@@ -417,7 +452,7 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
                                               const int32_t *__restrict__ kb, float4 *__restrict__ raw,
                                               volatile float *s_ftot, f2 *ring, const unsigned bars, unsigned &phase) {
     constexpr int NSLOT = 32 * C;
-    constexpr int RS = NSLOT + 2 * kHalo;
+    constexpr int RS = C * kPlane;
     constexpr unsigned RSB = RS * 8u; // bytes per forward row
     const int lane = threadIdx.x & 31;
     const int Lt = pc.Lt, Lr = pc.Lr, nd = pc.nd, W = 2 * pc.r;
@@ -457,7 +492,7 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
     BwdState<C> st;
 #pragma unroll
     for (int c = 0; c < C; c++) {
-        const int sigma = lane + 32 * c;
+        const int sigma = lane * C + c;
         const int d = (Lt - sigma) & (NSLOT - 1);
         st.j[c] = Lt - d;      // largest column <= Lt owned by this slot
         st.x[c] = d + pc.r;    // row i = Lr + d on the last anti-diagonal, window starts at row Lr - r
@@ -481,19 +516,14 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
         __stcg(sg + 3, make_float4(lo2(st.Xp[c][2]) + hi2(st.Xp[c][2]), lo2(st.Xm[c][0]) + hi2(st.Xm[c][0]),
                                    lo2(st.Xm[c][1]) + hi2(st.Xm[c][1]), lo2(st.Xm[c][2]) + hi2(st.Xm[c][2])));
     };
-    // hand (B_M, B_D) to the left-hand neighbour column: slot sigma receives from slot sigma+1 = lane+1 with the same c;
-    // past lane 31 that is lane 0 with c+1 (wrapping), so lane 0 sends its values rotated by one
-    const bool lane0 = lane == 0;
+    // hand (B_M, B_D) to the left-hand neighbour column: slot sigma receives from slot sigma+1 -- the next slot of the same
+    // lane, or slot 0 of lane+1 (wrapping) for the last one: one pair of shuffles per lane and step
     auto hand_off = [&](f2 (&bMD)[C]) {
+        const float rM = __shfl_sync(kFull, lo2(bMD[0]), (lane + 1) & 31);
+        const float rD = __shfl_sync(kFull, hi2(bMD[0]), (lane + 1) & 31);
 #pragma unroll
-        for (int c = 0; c < C; c++) {
-            const f2 own = bMD[c], nxt = bMD[(c + 1) % C];
-            const float sM = lane0 ? lo2(nxt) : lo2(own);
-            const float sD = lane0 ? hi2(nxt) : hi2(own);
-            const float rM = __shfl_sync(kFull, sM, (lane + 1) & 31);
-            const float rD = __shfl_sync(kFull, sD, (lane + 1) & 31);
-            st.inMb[c] = st.inMa[c]; st.inMa[c] = rM; st.inD[c] = rD;
-        }
+        for (int c = 0; c < C - 1; c++) { st.inMb[c] = st.inMa[c]; st.inMa[c] = lo2(bMD[c + 1]); st.inD[c] = hi2(bMD[c + 1]); }
+        st.inMb[C - 1] = st.inMa[C - 1]; st.inMa[C - 1] = rM; st.inD[C - 1] = rD;
     };
     // Anti-diagonal s -> s-1 when the centre stays (guide bit 0): every cell moves one row down inside the window
     // (x--), and the slot at the bottom of the band has seen its last in-band cell.  Retirement is DEFERRED to the end of
@@ -523,7 +553,7 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
     };
     // generic step: any s, exact corrections, ring slot computed from s
     auto slow_step = [&](int s) {
-        const f2 *rp = ring + (size_t)(((s + kRowShift) & (kRingRows - 1)) + kRingMargin) * RS + kHalo + lane;
+        const f2 *rp = ring + (size_t)(((s + kRowShift) & (kRingRows - 1)) + kRingMargin) * RS + kPlaneHalo + lane;
         if (s == nd - 1 || (s & 3) == 3) reload(s);
         // cumulative scale exponent of forward row t: rescales happen on the last row of a block of four, kb[q] = exponent
         // after block q
@@ -569,7 +599,7 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
         const bool clean = kb1 == kb2 && kb2 == kb3;
         kb1 = kb2; kb2 = kb3; kb3 = kb[q - 4];
         if (s_hi <= nd - 2 && q >= 2 && clean) {
-            const f2 *rp = ring + (size_t)(4 * (q & 3) + 3 + kRingMargin) * RS + kHalo + lane;
+            const f2 *rp = ring + (size_t)(4 * (q & 3) + 3 + kRingMargin) * RS + kPlaneHalo + lane;
             reload(s_hi);
             // guide bits 4q-5 .. 4q-2 (fetched one block ahead): step k (s = s_hi - k) moves on with bit 4q-2-k
             const unsigned nib = nib_cur;
@@ -609,7 +639,7 @@ __device__ __forceinline__ PairCtx make_pair_ctx(const KParams &p, const DevPair
     return pc;
 }
 
-template <int C> constexpr int ring_floats2() { return (kRingRows + 2 * kRingMargin) * (32 * C + 2 * kHalo); }
+template <int C> constexpr int ring_floats2() { return (kRingRows + 2 * kRingMargin) * (C * kPlane); }
 
 // ------------------------------------------------------------------------------------------------
 // Kernel 1 of the modification table: the forward pass of every pair of the wave (v7).
@@ -666,7 +696,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 6) fwdrows_kernel(KParams p
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     fill_fwd_tables(sh, p.models);
     constexpr int NSLOT = 32 * C;
-    constexpr int RS = NSLOT + 2 * kHalo;
+    constexpr int RS = C * kPlane;   // a row is C planes of 32 + 2*2 entries (see kPlane)
     constexpr int PADR = NSLOT + 16; // staged read rows: -PADR .. Lr + PADR
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *rb_s = dyn_smem + (size_t)warp * (p.smem_rb + p.smem_tb); // rb_s[i + PADR] = 4*idx of read row i
@@ -714,8 +744,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 6) fwdrows_kernel(KParams p
             msk[c] = (unsigned)x[c] <= (unsigned)W ? 1.f : 0.f;
             toI[c] = inD[c] = inMa[c] = inMb[c] = 0.f;
         }
-        f2 *wrow = reinterpret_cast<f2 *>(frow) + kHalo + lane * C; // this lane's slots in row 0
-        const int halo = (lane * C < 3) ? NSLOT : ((lane * C + C > NSLOT - 3) ? -NSLOT : 0);
+        f2 *wrow = reinterpret_cast<f2 *>(frow) + kPlaneHalo + lane; // entry `lane` of plane 0 in row 0; slot c is in plane c
+        const int halo = (lane < kPlaneHalo) ? 32 : ((lane >= 32 - kPlaneHalo) ? -32 : 0);
         int K = 0;
         const uint32_t *bw = p.bits + P.bits_off;
 
@@ -754,12 +784,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 6) fwdrows_kernel(KParams p
                 }
             }
 #pragma unroll
-            for (int c = 0; c < C; c += 2)
-                asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(wrow + kk * RS + c), "l"(tMD[c]), "l"(tMD[c + 1]) : "memory");
-            if (halo != 0) { // the first / last slots are replicated past the other end of the row
+            for (int c = 0; c < C; c++)
+                asm volatile("st.global.b64 [%0], %1;" ::"l"(wrow + kk * RS + c * kPlane), "l"(tMD[c]) : "memory");
+            if (halo != 0) { // the first / last entries of every plane are replicated past its other end
 #pragma unroll
-                for (int c = 0; c < C; c += 2)
-                    asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(wrow + kk * RS + halo + c), "l"(tMD[c]), "l"(tMD[c + 1]) : "memory");
+                for (int c = 0; c < C; c++)
+                    asm volatile("st.global.b64 [%0], %1;" ::"l"(wrow + kk * RS + c * kPlane + halo), "l"(tMD[c]) : "memory");
             }
             // hand (toM, toD) to the right-hand neighbour column (slot+1, wrapping)
             const float rM = __shfl_sync(kFull, lo2(tMD[C - 1]), (lane + 31) & 31);
@@ -863,13 +893,12 @@ __device__ __forceinline__ void fill_bwd_tables(BwdSmem &sh, const float *__rest
 }
 
 template <int C, int ROWS>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, C == 2 ? 4 : 1) bwdtable_kernel(KParams p) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, bwd_ctas_per_sm(C, ROWS)) bwdtable_kernel(KParams p) {
     __shared__ BwdSmem sh;
     extern __shared__ __align__(128) unsigned char dyn_smem[]; // kWarpsPerCta rings of forward rows
     fill_bwd_tables(sh, p.models);
-    constexpr int NSLOT = 32 * C;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int RS = NSLOT + 2 * kHalo;
+    constexpr int RS = C * kPlane;
     f2 *ring = reinterpret_cast<f2 *>(dyn_smem) + (size_t)warp * ring_floats2<C>();
     const unsigned bars = (unsigned)__cvta_generic_to_shared(&sh.bar[warp][0]);
     unsigned phase = 0u;
@@ -895,50 +924,68 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, C == 2 ? 4 : 1) bwdtable_ke
     }
 }
 
-// Kernel 3: raw column sums -> the 14 log-ratios of the table (table - lk), one thread per column.
+// Kernel 3: raw column sums -> the 14 log-ratios of the table (table - lk).  One CTA per 128 columns of one pair: the raw
+// sums (64 B per column) come in and the table rows (56 B per column) go out as contiguous runs through shared memory,
+// one thread computes one column in between.
 // raw[j] = { S[0..3] | Vs, N[0..2] | N[3], Vn, Xp[0..1] | Xp[2], Xm[0..2] } (DESIGN.md 3.2, table identities).
-__global__ void __launch_bounds__(128) finalize_kernel(KParams p) {
+constexpr int kFinCols = 128;
+constexpr int kFinRawStride = 5;  // float4 per staged column (4 used): 80-byte stride, conflict-free 16-byte reads
+constexpr int kFinOutStride = 15; // floats per staged output column (14 used)
+__global__ void __launch_bounds__(kFinCols) finalize_kernel(KParams p) {
+    __shared__ float4 sraw[(kFinCols + 3) * kFinRawStride];
+    __shared__ float sout[kFinCols * kFinOutStride];
     const int k = blockIdx.y;
     const int pi = p.pair_lo + k;
     const DevPair P = p.pairs[pi];
     const int Lt = P.Lt;
-    const int jj = blockIdx.x * blockDim.x + threadIdx.x;
-    if (jj > Lt) return;
+    const int j0 = blockIdx.x * kFinCols;
+    if (j0 > Lt) return;
+    const int ncol = min(kFinCols, Lt + 1 - j0);       // columns of this CTA
+    const int nraw = min(kFinCols + 3, Lt + 1 - j0);   // + the three columns to the right (multi-base deletions)
+    const float4 *sg = p.raw + (size_t)k * p.raw_stride + (size_t)j0 * 4;
+    for (int t = threadIdx.x; t < nraw * 4; t += kFinCols) sraw[(t >> 2) * kFinRawStride + (t & 3)] = __ldcg(sg + t);
     const unsigned *info = p.fwdinfo + (size_t)k * p.fwdinfo_stride;
     const float fin_raw = __uint_as_float(info[0]);
     const int e_fin = (int)(__float_as_uint(fin_raw) >> 23) - 127;
     const float boff = fin_raw > 0.f ? pow2i(max(-120, min(120, kProductExp - e_fin))) : 1.f;
     const float fin = fin_raw * boff;
-    const float4 *sg = p.raw + (size_t)k * p.raw_stride + (size_t)jj * 4;
-    const float4 q0 = __ldcg(sg), q1 = __ldcg(sg + 1), q2 = __ldcg(sg + 2), q3 = __ldcg(sg + 3);
-    const float s4[4] = { q0.x, q0.y, q0.z, q0.w };
-    const float n4[4] = { q1.y, q1.z, q1.w, q2.x };
-    const float vs = q1.x, vn = q2.y;
-    const float xp[3] = { q2.z, q2.w, q3.x };
-    const int tcode = p.codes[P.tb_off + jj + 1];
-    float ref = fin;
-    if (jj < Lt) ref = s4[tcode & 3] + vs;
-    auto dlog = [](float num, float den) -> float {
-        return (num > 0.f && den > 0.f) ? logf(num / den) : kDeltaNeg;
-    };
-    float *o = p.out_delta + P.tab_off + (size_t)jj * kNumRow;
-    const bool all_rows = p.rows == 14;
+    __syncthreads();
+    const int c = threadIdx.x, jj = j0 + c;
+    if (c < ncol) {
+        const float4 q0 = sraw[c * kFinRawStride], q1 = sraw[c * kFinRawStride + 1], q2 = sraw[c * kFinRawStride + 2],
+                     q3 = sraw[c * kFinRawStride + 3];
+        const float s4[4] = { q0.x, q0.y, q0.z, q0.w };
+        const float n4[4] = { q1.y, q1.z, q1.w, q2.x };
+        const float vs = q1.x, vn = q2.y;
+        const float xp[3] = { q2.z, q2.w, q3.x };
+        const int tcode = p.codes[P.tb_off + jj + 1];
+        float ref = fin;
+        if (jj < Lt) ref = s4[tcode & 3] + vs;
+        auto dlog = [](float num, float den) -> float {
+            return (num > 0.f && den > 0.f) ? logf(num / den) : kDeltaNeg;
+        };
+        float *o = sout + c * kFinOutStride;
+        const bool all_rows = p.rows == 14;
 #pragma unroll
-    for (int b = 0; b < 4; b++) o[b] = (jj < Lt) ? dlog(s4[b] + vs, ref) : kDeltaNeg;
+        for (int b = 0; b < 4; b++) o[b] = (jj < Lt) ? dlog(s4[b] + vs, ref) : kDeltaNeg;
 #pragma unroll
-    for (int b = 0; b < 4; b++) o[4 + b] = dlog(n4[b] + vn, ref);
+        for (int b = 0; b < 4; b++) o[4 + b] = dlog(n4[b] + vn, ref);
 #pragma unroll
-    for (int e = 1; e <= 3; e++) {
-        o[7 + e] = (all_rows && jj + e <= Lt) ? dlog(xp[e - 1], ref) : kDeltaNeg;
-        float v = kDeltaNeg;
-        if ((all_rows || e == 1) && jj + e <= Lt) {
-            const float4 qe = __ldcg(sg + 4 * e + 3);
-            float acc = e == 1 ? qe.y : (e == 2 ? qe.z : qe.w);
-            if (jj + e == Lt) acc += __uint_as_float(info[e]) * boff;
-            v = dlog(acc, ref);
+        for (int e = 1; e <= 3; e++) {
+            o[7 + e] = (all_rows && jj + e <= Lt) ? dlog(xp[e - 1], ref) : kDeltaNeg;
+            float v = kDeltaNeg;
+            if ((all_rows || e == 1) && jj + e <= Lt) {
+                const float4 qe = sraw[(c + e) * kFinRawStride + 3];
+                float acc = e == 1 ? qe.y : (e == 2 ? qe.z : qe.w);
+                if (jj + e == Lt) acc += __uint_as_float(info[e]) * boff;
+                v = dlog(acc, ref);
+            }
+            o[10 + e] = v;
         }
-        o[10 + e] = v;
     }
+    __syncthreads();
+    float *og = p.out_delta + P.tab_off + (size_t)j0 * kNumRow;
+    for (int n = threadIdx.x; n < ncol * kNumRow; n += kFinCols) og[n] = sout[(n / kNumRow) * kFinOutStride + (n % kNumRow)];
 }
 
 template <int C>
@@ -1146,7 +1193,7 @@ static cudaError_t launch_modtable_cr(const KParams &p, int grid_fwd, int grid_b
     bwdtable_kernel<C, ROWS><<<grid_bwd, kWarpsPerCta * 32, dyn, st>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    finalize_kernel<<<dim3((unsigned)((p.max_lt + 1 + 127) / 128), (unsigned)(p.pair_hi - p.pair_lo)), 128, 0, st>>>(p);
+    finalize_kernel<<<dim3((unsigned)((p.max_lt + kFinCols) / kFinCols), (unsigned)(p.pair_hi - p.pair_lo)), kFinCols, 0, st>>>(p);
     return cudaGetLastError();
 }
 template <int C>
@@ -1191,9 +1238,9 @@ cudaError_t launch_fit(const KParams &p, int C, int grid, double *acc90, cudaStr
 }
 
 int warps_per_cta() { return kWarpsPerCta; }
-int frow_slots_per_row(int C) { return 32 * C + 2 * kHalo; }
+int frow_slots_per_row(int C) { return C * kPlane; }
 int frow_extra_rows() { return kRowShift + kRowsAbove; }
-int modtable_ctas_per_sm(int C) { return C == 2 ? 4 : 1; }
+int modtable_ctas_per_sm(int C, int rows) { return bwd_ctas_per_sm(C, rows); }
 int fwdrows_ctas_per_sm(int C) { return C == 2 ? 6 : 3; }
 int fwdinfo_words() { return 16; }
 int fwd_pad_rows(int C) { return 32 * C + 16; }
