@@ -70,6 +70,9 @@ __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %
 __device__ __forceinline__ void acc2(f2 &acc, f2 a, f2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 bc2(float v) { return mk2(v, v); }
+// x = +0 for a finite x >= 0, as ONE instruction on the FMA pipe (FMUL2 / FMUL with RZ)
+__device__ __forceinline__ void clear2(f2 &x) { asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(0ull)); }
+__device__ __forceinline__ void clear1(float &x) { asm volatile("mul.rn.f32 %0, %0, 0f00000000;" : "+f"(x)); }
 
 __device__ __forceinline__ float lds_f32(unsigned a) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void lds_f32x4(unsigned a, f2 &x, f2 &y) {
@@ -351,6 +354,14 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// one lane of the (converged) warp, chosen by the hardware: tells ptxas that what follows runs in ONE thread, so the bulk
+// copy's uniform-register operands need no "for every distinct value among the active lanes" loop
+__device__ __forceinline__ bool elect_one() {
+    unsigned p;
+    asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(p));
+    return p != 0u;
+}
+
 template <int C> struct BwdState {
     int x[C], j[C];
     unsigned tcB[C], win[C];
@@ -466,7 +477,7 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
     const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
     const float2 *grow0 = frow - (ptrdiff_t)kRowShift * RS; // global row rho = 0
     auto issue_group = [&](int q) { // rows rho = 4q .. 4q+3
-        if (lane == 0) {
+        if (elect_one()) {
             const unsigned g = (unsigned)q & 3u;
             const unsigned bar = bars + 8u * g;
             const float2 *src = grow0 + (size_t)(4 * q) * RS;
@@ -508,13 +519,18 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
 
     // a finished column leaves its 16 raw sums in the pair's scratch (64 B, one lane); finalize_kernel turns them into the
     // 14 log-ratios of the table
+    // raw[j] = { S0 S1 | S2 S3 | N0 N1 | N2 N3 | Vs Vn Xp0 Xp1 | Xp2 Xm0 Xm1 Xm2 }: the packed accumulators go out as they
+    // sit in their register pairs (8-byte stores), only the cut sums are assembled
     auto flush_col = [&](int c) {
-        float4 *sg = raw + (size_t)st.j[c] * 4;
-        __stcg(sg + 0, make_float4(lo2(st.S01[c]), hi2(st.S01[c]), lo2(st.S23[c]), hi2(st.S23[c])));
-        __stcg(sg + 1, make_float4(st.Vs[c], lo2(st.N01[c]), hi2(st.N01[c]), lo2(st.N23[c])));
-        __stcg(sg + 2, make_float4(hi2(st.N23[c]), st.Vn[c], lo2(st.Xp[c][0]) + hi2(st.Xp[c][0]), lo2(st.Xp[c][1]) + hi2(st.Xp[c][1])));
-        __stcg(sg + 3, make_float4(lo2(st.Xp[c][2]) + hi2(st.Xp[c][2]), lo2(st.Xm[c][0]) + hi2(st.Xm[c][0]),
-                                   lo2(st.Xm[c][1]) + hi2(st.Xm[c][1]), lo2(st.Xm[c][2]) + hi2(st.Xm[c][2])));
+        f2 *sg = reinterpret_cast<f2 *>(raw + (size_t)st.j[c] * 4);
+        asm volatile("st.global.cg.b64 [%0], %1;" ::"l"(sg + 0), "l"(st.S01[c]) : "memory");
+        asm volatile("st.global.cg.b64 [%0], %1;" ::"l"(sg + 1), "l"(st.S23[c]) : "memory");
+        asm volatile("st.global.cg.b64 [%0], %1;" ::"l"(sg + 2), "l"(st.N01[c]) : "memory");
+        asm volatile("st.global.cg.b64 [%0], %1;" ::"l"(sg + 3), "l"(st.N23[c]) : "memory");
+        __stcg(raw + (size_t)st.j[c] * 4 + 2, make_float4(st.Vs[c], st.Vn[c], lo2(st.Xp[c][0]) + hi2(st.Xp[c][0]),
+                                                          lo2(st.Xp[c][1]) + hi2(st.Xp[c][1])));
+        __stcg(raw + (size_t)st.j[c] * 4 + 3, make_float4(lo2(st.Xp[c][2]) + hi2(st.Xp[c][2]), lo2(st.Xm[c][0]) + hi2(st.Xm[c][0]),
+                                                          lo2(st.Xm[c][1]) + hi2(st.Xm[c][1]), lo2(st.Xm[c][2]) + hi2(st.Xm[c][2])));
     };
     // hand (B_M, B_D) to the left-hand neighbour column: slot sigma receives from slot sigma+1 -- the next slot of the same
     // lane, or slot 0 of lane+1 (wrapping) for the last one: one pair of shuffles per lane and step
@@ -540,10 +556,15 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
                 st.x[c] += NSLOT;
                 st.tcB[c] = pc.sEM + (st.tcn[c] << 5); // fetched one column-life ago; the window comes with the next reload
                 st.tcn[c] = pc.Tb[st.j[c] + 1 - NSLOT];
-                st.Vs[c] = st.Vn[c] = 0.f;
-                st.S01[c] = st.S23[c] = st.N01[c] = st.N23[c] = 0ull;
+                // reset = multiply by zero, one instruction per register pair (the sums are finite and >= 0); a plain
+                // "= 0" went through 22 uniform-register moves + 22 copies in SASS
+                clear2(st.S01[c]); clear2(st.S23[c]); clear2(st.N01[c]); clear2(st.N23[c]);
+                clear1(st.Vs[c]); clear1(st.Vn[c]);
 #pragma unroll
-                for (int e = 0; e < 3; e++) { st.Xp[c][e] = 0ull; st.Xm[c][e] = 0ull; }
+                for (int e = 0; e < 3; e++) { // the 9-row kernel only accumulates Xm[0]: leave the others to the compiler
+                    if (ROWS == 14) clear2(st.Xp[c][e]); else st.Xp[c][e] = 0ull;
+                    if (ROWS == 14 || e == 0) clear2(st.Xm[c][e]); else st.Xm[c][e] = 0ull;
+                }
             }
         }
     };
@@ -589,19 +610,23 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
         return __funnelshift_r(pc.bw[b0 >> 5], pc.bw[(b0 >> 5) + 1], b0 & 31);
     };
     unsigned nib_cur = 0u, nib_nxt = q_top >= 2 ? load_nib(q_top) : 0u;
-    for (int q = q_top; q >= 1; --q) { // block q: anti-diagonals s = 4q-1 .. 4q-4 (rho = 4q+3 .. 4q)
+    // per-block preamble: guide bits one block ahead, the ring group this block reads below itself has landed, the next
+    // copy is issued; returns whether block q takes the fast path
+    auto preamble = [&](int q) -> bool {
         nib_cur = nib_nxt;
         if (q >= 3) nib_nxt = load_nib(q - 1);
         wait_group(q - 1);
         __syncwarp(); // every lane is done with the rows that the next copy overwrites
         if (q >= 2) issue_group(q - 2);
-        const int s_hi = 4 * q - 1;
         const bool clean = kb1 == kb2 && kb2 == kb3;
         kb1 = kb2; kb2 = kb3; kb3 = kb[q - 4];
-        if (s_hi <= nd - 2 && q >= 2 && clean) {
+        return 4 * q - 1 <= nd - 2 && q >= 2 && clean;
+    };
+    for (int q = q_top; q >= 1; --q) {
+        if (preamble(q)) {
             const f2 *rp = ring + (size_t)(4 * (q & 3) + 3 + kRingMargin) * RS + kPlaneHalo + lane;
-            reload(s_hi);
-            // guide bits 4q-5 .. 4q-2 (fetched one block ahead): step k (s = s_hi - k) moves on with bit 4q-2-k
+            reload(4 * q - 1);
+            // guide bits 4q-5 .. 4q-2 (fetched one block ahead): step k (s = 4q-1-k) moves on with bit 4q-2-k
             const unsigned nib = nib_cur;
 #pragma unroll kBwdUnroll
             for (int k = 0; k < 4; k++) {
@@ -613,7 +638,7 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
                 for (int c = 0; c < C; c++) st.x[c] -= dec;
             }
         } else {
-            for (int s = min(s_hi, nd - 1); s >= 4 * q - 4; --s) slow_step(s);
+            for (int s = min(4 * q - 1, nd - 1); s >= 4 * q - 4; --s) slow_step(s);
         }
         retire();
     }
@@ -927,7 +952,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, bwd_ctas_per_sm(C, ROWS)) b
 // Kernel 3: raw column sums -> the 14 log-ratios of the table (table - lk).  One CTA per 128 columns of one pair: the raw
 // sums (64 B per column) come in and the table rows (56 B per column) go out as contiguous runs through shared memory,
 // one thread computes one column in between.
-// raw[j] = { S[0..3] | Vs, N[0..2] | N[3], Vn, Xp[0..1] | Xp[2], Xm[0..2] } (DESIGN.md 3.2, table identities).
+// raw[j] = { S[0..3] | N[0..3] | Vs, Vn, Xp[0..1] | Xp[2], Xm[0..2] } (DESIGN.md 3.2, table identities).
 constexpr int kFinCols = 128;
 constexpr int kFinRawStride = 5;  // float4 per staged column (4 used): 80-byte stride, conflict-free 16-byte reads
 constexpr int kFinOutStride = 15; // floats per staged output column (14 used)
@@ -955,8 +980,8 @@ __global__ void __launch_bounds__(kFinCols) finalize_kernel(KParams p) {
         const float4 q0 = sraw[c * kFinRawStride], q1 = sraw[c * kFinRawStride + 1], q2 = sraw[c * kFinRawStride + 2],
                      q3 = sraw[c * kFinRawStride + 3];
         const float s4[4] = { q0.x, q0.y, q0.z, q0.w };
-        const float n4[4] = { q1.y, q1.z, q1.w, q2.x };
-        const float vs = q1.x, vn = q2.y;
+        const float n4[4] = { q1.x, q1.y, q1.z, q1.w };
+        const float vs = q2.x, vn = q2.y;
         const float xp[3] = { q2.z, q2.w, q3.x };
         const int tcode = p.codes[P.tb_off + jj + 1];
         float ref = fin;
