@@ -414,16 +414,17 @@ def main():
         ach_tflops = cells * FLOPS_PER_CELL / (k_ms * 1e-3) / 1e12
         prof_bytes = float(sum((len(templates[int(t)]) + 1) * 14 * 4 for t in tidx))
         in_bytes = float(batch.h2d_bytes)
-        roof = {"bound": "fp32", "kernel": "modtable_kernel<2,14>", "achieved": ach_tflops, "peak": ffma,
+        roof = {"bound": "fp32", "kernel": "fwdrows_kernel<2> + bwdtable_kernel<2,14> + finalize_kernel (one modification-table "
+                                          "launch sequence; bwdtable is ~65 % of it)", "achieved": ach_tflops, "peak": ffma,
                 "unit": "TFLOP/s", "frac": ach_tflops / ffma if ffma else None,
                 "peak_source": "measured in this run: register-resident fma.rn.f32 loop on all SMs "
                                "(MEASURED_PEAKS.json holds only HBM and bf16 figures)",
                 "peak_ffma2": ffma2, "flops_per_cell_update": FLOPS_PER_CELL,
                 "cell_updates_per_launch": cells, "kernel_ms": k_ms, "gcups_kernel": cells / (k_ms * 1e-3) / 1e9,
                 "traffic": ncu_traffic(len(reads)),
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full, profiles/); it is the "
-                                "forward-row scratch (2 x 2.3 MB per pair), not the algorithmic bytes: the kernel is FP32/issue "
-                                "bound, see roofline.hbm",
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the three kernels of one launch sequence (ncu --set "
+                                "full, profiles/r1_traffic.json); it is the forward-row scratch (2 x 2.3 MB per pair: written by "
+                                "fwdrows at 6.0 TB/s, read back by bwdtable), not the algorithmic bytes, see roofline.hbm",
                 "hbm": {"algorithmic_bytes_per_launch": prof_bytes + in_bytes,
                         "achieved_gbs": (prof_bytes + in_bytes) / (k_ms * 1e-3) / 1e9,
                         "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src}}
