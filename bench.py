@@ -228,11 +228,13 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def phase_leg(ctx, templates, reads, ops, strands, tidx, n_chunks, cov):
+def phase_leg(ctx, templates, reads, ops, strands, tidx, n_chunks, cov, rank=0, world=1):
     """'chunks phased per second' (BASELINE.json metric, second half): the whole per-chunk path of
     local_clustering_selected (local_clustering/mod.rs:56-83 without the model fit) on the first n_chunks chunks --
     batched polish, 9-row tables, device-side filter_profiles, host greedy pick + k-means + MCMC, posteriors,
-    normalisation -- through jtk_b200/pipeline.py.  Wall clock; rank 0 only."""
+    normalisation -- through jtk_b200/pipeline.py.  Wall clock.  Under torchrun every rank calls this with the SAME chunks
+    (rank 0's workload): the scheduler shards them over the ranks and gathers the per-chunk results on rank 0 (strong
+    scaling; the host clustering of all ranks shares the box's cores)."""
     from jtk_b200 import pipeline as P
     from jtk_b200 import local_clustering as LC
     gains = LC.Gains(gain=GAINS_EXPECTED.astype(np.float64), prob=GAINS_PROB)
@@ -243,16 +245,24 @@ def phase_leg(ctx, templates, reads, ops, strands, tidx, n_chunks, cov):
                  for k in range(len(reads)) if int(tidx[k]) in set(chunk_ids)]
         return P.DataSet(selected_chunks=chunks, nodes=nodes, read_type="ONT")
 
-    warm = dataset(list(range(min(2, n_chunks))))
-    P.local_clustering_selected(warm, {c.id for c in warm.selected_chunks}, gains=gains, ctx=ctx, fit_models=False)
+    warm = dataset(list(range(min(max(2, world), n_chunks))))
+    P.local_clustering_selected(warm, {c.id for c in warm.selected_chunks}, gains=gains, ctx=ctx, fit_models=False,
+                                rank=rank, world=world)
     ds = dataset(list(range(n_chunks)))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
     t0 = time.perf_counter()
-    out = P.local_clustering_selected(ds, {c.id for c in ds.selected_chunks}, gains=gains, ctx=ctx, fit_models=False)
+    out = P.local_clustering_selected(ds, {c.id for c in ds.selected_chunks}, gains=gains, ctx=ctx, fit_models=False,
+                                      rank=rank, world=world)
     dt = time.perf_counter() - t0
+    if out is None:
+        return None
     ks = [out[c][2] for c in sorted(out)]
     return {"phases_s": {k: round(v, 4) for k, v in P.LAST_TIMING.items()}, "chunks_per_s": n_chunks / dt, "chunks": n_chunks, "seconds": dt, "host_threads": P.host_threads(),
             "two_cluster_chunks": int(sum(1 for k in ks if k == 2)),
-            "what": "polish + 9-row tables + device filter_profiles + host pick/k-means/MCMC + normalise, 1 GPU"}
+            "what": "polish + 9-row tables + device filter_profiles + host pick/k-means/MCMC + normalise; "
+                    f"{n_chunks} chunks sharded over {world} GPU(s), host gather on rank 0 (strong scaling)"}
 
 
 def workload_config(args):
@@ -389,8 +399,9 @@ def main():
 
     # ---- chunks phased per second through the driver (extra; rank 0's GPU, host clustering on all cores) -----------
     phased = None
-    if args.phase_chunks > 0 and rank == 0:
-        phased = phase_leg(ctx, templates, reads, ops, strands, tidx, min(args.phase_chunks, args.chunks), cov)
+    if args.phase_chunks > 0:
+        w0 = (templates, reads, ops, strands, tidx) if rank == 0 else make_workload(0, args.chunks, args.reads, args.length)
+        phased = phase_leg(ctx, *w0, min(args.phase_chunks, args.chunks), cov, rank=rank, world=world)
 
     # ---- reduce over ranks ------------------------------------------------------------------------
     step_ms = dev_ms / args.steps

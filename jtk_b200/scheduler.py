@@ -68,7 +68,8 @@ def run_sharded(chunk_ids: Sequence[int], weights: Sequence[float], process: Cal
     missing = set(mine) - set(local)
     if missing:
         raise RuntimeError(f"rank {rank}: no result for chunks {sorted(missing)[:5]}")
-    merged = gather_to_rank0(local, group=group)
+    # world == 1: nothing to gather, even inside a process that has a torch.distributed group for other work
+    merged = dict(local) if world <= 1 else gather_to_rank0(local, group=group)
     if merged is not None and set(merged) != set(chunk_ids):
         raise RuntimeError("gather lost or duplicated chunks")
     return merged

@@ -222,3 +222,31 @@ def test_full_size_properties_without_the_oracle(ctx):
         # a read of its own haplotype rarely gains more than a few nats from any single edit, and never loses nothing
         assert a[a > -1e9].max() < 40 and a[a > -1e9].min() < -5
     b.close()
+
+
+def test_parameter_uploads_follow_their_contents(ctx):
+    """Models, min_req and stat_off are uploaded only when their bytes change (csrc/jtk_gpu_api.cu, SmallUpload): a call
+    with NEW parameters on a context that has seen others must use the new ones, and going back must reproduce the first
+    answer bit for bit."""
+    from jtk_b200 import _lib
+    d = synth.diploid_chunk(21, length=400, n_reads=10)
+    tidx = np.zeros(len(d["reads"]), np.uint32)
+    ha, hb = to_c(O.default_hmm()), to_c(random_hmm(5))
+    b = ctx.batch([d["template"]], d["reads"], d["ops"], d["strands"], tidx, 30)
+    b.modtable(ha, ha, 14); lk_a = b.lk(); pa = b.profile(3)
+    b.modtable(hb, hb, 14); lk_b = b.lk(); pb = b.profile(3)
+    b.modtable(ha, ha, 14); lk_a2 = b.lk(); pa2 = b.profile(3)
+    assert np.array_equal(lk_a, lk_a2) and np.array_equal(pa, pa2)
+    assert not np.array_equal(lk_a, lk_b) and not np.array_equal(pa, pb)
+    fresh = _lib.Context()
+    fb = fresh.batch([d["template"]], d["reads"], d["ops"], d["strands"], tidx, 30)
+    fb.modtable(hb, hb, 14)
+    assert np.array_equal(fb.lk(), lk_b) and np.array_equal(fb.profile(3), pb)
+    # thresholds: two different min_req blocks on the same batch / context, then the first one again
+    m1 = np.full((3, 4), 0.5, np.float32); m2 = np.full((3, 4), 3.0, np.float32)
+    s1 = b.colstats(m1); s2 = b.colstats(m2); s1b = b.colstats(m1)
+    assert np.array_equal(s1, s1b)
+    assert s2["count"].sum() < s1["count"].sum()
+    fb.modtable(ha, ha, 14)                      # same profiles as b holds now, on a context that never saw m1
+    assert np.array_equal(fb.colstats(m2), s2)
+    fb.close(); fresh.close(); b.close()

@@ -112,6 +112,11 @@ def _gloo_worker(rank, world, port, ret):
             return {c: (c * 3490, np.arange(c % 7, dtype=np.uint64), f"rank{rank}") for c in my}
 
         merged = S.run_sharded(ids, weights, process, rank, world)
+        # a caller that asks for ONE rank inside a process that has a group (bench.py's rank-0-only legs) must not enter a
+        # collective the other ranks never join
+        if rank == 0:
+            solo = S.run_sharded(ids[:5], weights[:5], process, 0, 1)
+            ret["solo"] = sorted(solo)
         if rank == 0:
             ret["ids"] = sorted(merged)
             ret["seeds"] = [merged[c][0] for c in sorted(merged)]
@@ -132,6 +137,7 @@ def test_sharded_run_gathers_every_chunk_once_gloo_world2():
         ret = m.dict()
         mp.spawn(_gloo_worker, args=(2, port, ret), nprocs=2, join=True)
         assert ret["ids"] == list(range(100, 123))
+        assert ret["solo"] == list(range(100, 105))
         assert ret["seeds"] == [c * 3490 for c in range(100, 123)]
         assert ret["ranks"] == ["rank0", "rank1"]
         assert ret["lens"] == [c % 7 for c in range(100, 123)]
