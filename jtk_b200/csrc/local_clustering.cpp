@@ -423,58 +423,93 @@ static double mcmc_with_filter(const Mat &data, std::vector<size_t> &assign, siz
     for (double x : size_to_lk) JTK_ASSERT(!std::isnan(x), "is_valid_lk");
     std::vector<double> flat(n * D);
     for (size_t i = 0; i < n; i++) { JTK_ASSERT(data[i].size() == D, "ragged variants"); for (size_t d = 0; d < D; d++) flat[i * D + d] = data[i][d]; }
-    std::vector<LKCount> lks(k * D);
+    // LKCount (:797-845) as flat arrays: total gain and the counts of positive / negative entries per (cluster, column).
+    // The sign class of every entry is fixed, so it is tabulated once and a flip updates the counters without a branch
+    // (the per-entry `if POS_THR < x ... else if x < -POS_THR` of add / sub mispredicted on most proposals).
+    std::vector<double> total(k * D, 0.0);
+    std::vector<uint32_t> npos(k * D, 0), nneg(k * D, 0);
+    std::vector<uint32_t> pinc(n * D), ninc(n * D);
     std::vector<size_t> clusters(k, 0);
     std::vector<uint8_t> use(D);
+    for (size_t i = 0; i < n * D; i++) {
+        const double x = flat[i];
+        pinc[i] = POS_THR < x ? 1u : 0u;
+        ninc[i] = (!(POS_THR < x) && x < -POS_THR) ? 1u : 0u;
+        JTK_ASSERT(pinc[i] || ninc[i] || std::fabs(x) < POS_THR, "x.abs() < POS_THR");
+    }
     for (size_t i = 0; i < n; i++) {
         clusters[assign[i]]++;
-        for (size_t d = 0; d < D; d++) lks[assign[i] * D + d].add(flat[i * D + d]);
+        for (size_t d = 0; d < D; d++) {
+            total[assign[i] * D + d] += flat[i * D + d];
+            npos[assign[i] * D + d] += pinc[i * D + d];
+            nneg[assign[i] * D + d] += ninc[i * D + d];
+        }
     }
     // LKCount::is_informative's ratio test (0.70 < num_pos / (num_pos + num_neg + 1e-7)) for every pair of counts,
     // evaluated once with the reference's own expression: the proposal loop looks it up instead of dividing
     std::vector<uint8_t> ratio_ok((n + 1) * (n + 1));
     for (size_t p = 0; p <= n; p++)
         for (size_t q = 0; q + p <= n; q++) ratio_ok[p * (n + 1) + q] = 0.70 < (double)p / ((double)(p + q) + 0.0000001);
-    auto informative = [&](const LKCount &x) { return 0.0 < x.total_gain && ratio_ok[x.num_pos * (n + 1) + x.num_neg] != 0; };
+    // raw views for the proposal loop (no reloads of the vectors' data pointers after every store)
+    double *__restrict__ const tot_p = total.data();
+    uint32_t *__restrict__ const npos_p = npos.data();
+    uint32_t *__restrict__ const nneg_p = nneg.data();
+    const uint32_t *__restrict__ const pinc_p = pinc.data();
+    const uint32_t *__restrict__ const ninc_p = ninc.data();
+    const double *__restrict__ const flat_p = flat.data();
+    const uint8_t *__restrict__ const ratio_p = ratio_ok.data();
+    const double *__restrict__ const s2l_p = size_to_lk.data();
+    size_t *__restrict__ const clus_p = clusters.data();
+    uint8_t *__restrict__ const use_p = use.data();
+    size_t *__restrict__ const asn_p = assign.data();
     auto current_lk = [&]() -> double { // get_lk (:785-795) with get_used_columns (:847-869)
         for (size_t d = 0; d < D; d++) {
-            bool u = false;
-            for (size_t c = 0; c < k; c++) u = u | informative(lks[c * D + d]);
-            size_t in_use = 0, in_neg = 0;
+            unsigned u = 0;
+            uint32_t in_use = 0, in_neg = 0;
             for (size_t c = 0; c < k; c++) {
-                const LKCount &x = lks[c * D + d];
-                if (0.0 < x.total_gain) in_use += x.num_pos;
-                if (x.total_gain <= 0.0) in_neg += x.num_pos;
+                const double g = tot_p[c * D + d];
+                const uint32_t p = npos_p[c * D + d];
+                const bool pos = 0.0 < g;
+                u |= (unsigned)pos & ratio_p[(size_t)p * (n + 1) + nneg_p[c * D + d]];
+                in_use += pos ? p : 0u;
+                in_neg += (g <= 0.0) ? p : 0u;
             }
-            use[d] = u & ((double)in_neg * 2.0 < (double)in_use);
+            use_p[d] = (uint8_t)(u & (unsigned)((double)in_neg * 2.0 < (double)in_use));
         }
         double lk = 0;
-        for (size_t c = 0; c < k; c++) lk += size_to_lk[clusters[c]];
+        for (size_t c = 0; c < k; c++) lk += s2l_p[clus_p[c]];
         for (size_t c = 0; c < k; c++)
-            for (size_t d = 0; d < D; d++) if (use[d]) lk += std::max(lks[c * D + d].total_gain, 0.0);
+            for (size_t d = 0; d < D; d++) if (use_p[d]) lk += std::max(tot_p[c * D + d], 0.0);
         return lk;
     };
     auto do_flip = [&](size_t idx, size_t to) { // flip (:764-783)
-        const size_t from = assign[idx];
-        const double *row = &flat[idx * D];
-        clusters[from]--;
-        for (size_t d = 0; d < D; d++) lks[from * D + d].sub(row[d]);
-        assign[idx] = to;
-        clusters[to]++;
-        for (size_t d = 0; d < D; d++) lks[to * D + d].add(row[d]);
+        const size_t from = asn_p[idx];
+        const double *row = &flat_p[idx * D];
+        const uint32_t *pi = &pinc_p[idx * D], *ni = &ninc_p[idx * D];
+        clus_p[from]--;
+        for (size_t d = 0; d < D; d++) { tot_p[from * D + d] -= row[d]; npos_p[from * D + d] -= pi[d]; nneg_p[from * D + d] -= ni[d]; }
+        asn_p[idx] = to;
+        clus_p[to]++;
+        for (size_t d = 0; d < D; d++) { tot_p[to * D + d] += row[d]; npos_p[to * D + d] += pi[d]; nneg_p[to * D + d] += ni[d]; }
     };
     double lk = current_lk();
     double mx = lk;
     std::vector<size_t> argmax = assign;
-    const size_t total = 2000 * n;
-    for (size_t t = 0; t < total; t++) {
+    const size_t n_proposals = 2000 * n;
+    for (size_t t = 0; t < n_proposals; t++) {
         const size_t idx = rng.gen_range(n);
         const size_t old = assign[idx];
         const size_t nw = rng.choose_other(k, old);
         do_flip(idx, nw);
         const double proposed = current_lk();
         const double diff = proposed - lk;
-        if (0.0 < diff || rng.gen_bool(std::exp(diff))) {
+        // exp(diff) * 2^64 < 1 for diff < -45 (e^-45 = 2^-64.9): Bernoulli's integer threshold is 0, the draw is consumed and
+        // the proposal rejected -- the same stream and the same decision as gen_bool(exp(diff)), without the exp
+        bool accept;
+        if (0.0 < diff) accept = true;
+        else if (diff < -45.0) { (void)rng.next_u64(); accept = false; }
+        else accept = rng.gen_bool(std::exp(diff));
+        if (accept) {
             lk = proposed;
             if (mx < lk) { mx = proposed; std::copy(assign.begin(), assign.end(), argmax.begin()); }
         } else do_flip(idx, old);
