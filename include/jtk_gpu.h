@@ -283,6 +283,9 @@ const char *jtk_lc_last_error(void);
 double jtk_lc_cosine_similarity(const double *profiles, int n, int ncol, int i, int j);
 int jtk_lc_homopolymer_length(const uint8_t *xs, int n, uint32_t *out);
 void jtk_lc_rng_words(uint64_t seed, int use_state, const uint64_t *state, int n, uint64_t *out);
+/* sort key of pileup_nodes (haplotyper/src/local_clustering/mod.rs:47-50): alignment columns of Node::recover that are not
+ * '|' = indel columns + diagonal columns whose bases differ; <0 if the ops do not span (read, template) */
+int jtk_lc_nonmatch_columns(const uint8_t *ops, int n_ops, const uint8_t *read, int Lr, const uint8_t *tmpl, int Lt);
 
 /* in-band cell count C = sum_d w(d) of one pair (SURVEY.md section 8d work unit); <0 if ops are invalid */
 int64_t jtk_band_cell_count(const uint8_t *ops, int n_ops, int Lt, int Lr, int radius);

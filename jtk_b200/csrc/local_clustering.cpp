@@ -960,6 +960,22 @@ double jtk_lc_cosine_similarity(const double *profiles, int n, int ncol, int i, 
     for (int r = 0; r < n; r++) { cand[(size_t)r * 2] = profiles[(size_t)r * ncol + i]; cand[(size_t)r * 2 + 1] = profiles[(size_t)r * ncol + j]; }
     return cosine_similarity(cand, (size_t)n, 2, 0, 1);
 }
+int jtk_lc_nonmatch_columns(const uint8_t *ops, int n_ops, const uint8_t *read, int Lr, const uint8_t *tmpl, int Lt) {
+    if (!ops || n_ops < 0 || Lr < 0 || Lt < 0 || (Lr > 0 && !read) || (Lt > 0 && !tmpl)) return -1;
+    int i = 0, j = 0, bad = 0;
+    for (int k = 0; k < n_ops; k++) {
+        const uint8_t op = ops[k];
+        if (op <= JTK_OP_MISMATCH) {
+            if (i >= Lr || j >= Lt) return -1;
+            bad += read[i] != tmpl[j];
+            i++; j++;
+        } else if (op == JTK_OP_INS) { if (i >= Lr) return -1; i++; bad++; }
+        else if (op == JTK_OP_DEL) { if (j >= Lt) return -1; j++; bad++; }
+        else return -1;
+    }
+    return bad;
+}
+
 int jtk_lc_homopolymer_length(const uint8_t *xs, int n, uint32_t *out) {
     const std::vector<size_t> h = homopolymer_length(xs, (size_t)n);
     for (int i = 0; i < n; i++) out[i] = (uint32_t)h[(size_t)i];

@@ -82,14 +82,16 @@ def update_coverage(ds: DataSet) -> None:
 
 
 def nonmatch_columns(node: Node, chunk: Chunk) -> int:
-    """Sort key of pileup_nodes (mod.rs:47-50): alignment columns of Node::recover that are not '|'."""
-    ops = np.asarray(node.ops)
-    indel = int(np.count_nonzero(ops >= 2))
-    diag = ops < 2
-    qi = np.cumsum(ops != 3) - 1   # read index consumed at each column
-    tj = np.cumsum(ops != 2) - 1   # template index consumed at each column
-    mism = int(np.count_nonzero(np.asarray(node.seq)[qi[diag]] != np.asarray(chunk.seq)[tj[diag]]))
-    return indel + mism
+    """Sort key of pileup_nodes (mod.rs:47-50): alignment columns of Node::recover that are not '|'
+    (jtk_lc_nonmatch_columns; the numpy version of this loop was 17 % of a 80-chunk local_clustering_selected call)."""
+    L = _bind()
+    ops, q, t = _lib._u8(node.ops), _lib._u8(node.seq), _lib._u8(chunk.seq)
+    f = L.jtk_lc_nonmatch_columns
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    r = f(_lib._ptr(ops), len(ops), _lib._ptr(q), len(q), _lib._ptr(t), len(t))
+    if r < 0:
+        raise ValueError("node ops do not span (read, chunk)")
+    return int(r)
 
 
 def pileup_nodes(ds: DataSet, selection: Set[int]) -> Dict[int, Tuple[List[Node], Chunk]]:
