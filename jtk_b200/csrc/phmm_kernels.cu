@@ -50,7 +50,8 @@ constexpr int kBwdUnroll = JTK_BWD_UNROLL; // steps of the fast backward block u
 #ifndef JTK_BWD_CTAS9
 #define JTK_BWD_CTAS9 4
 #endif
-constexpr int bwd_ctas_per_sm(int C, int rows) { return C == 2 ? (rows == 14 ? JTK_BWD_CTAS14 : JTK_BWD_CTAS9) : 1; }
+// C = 4 (radius 31..62): 255 registers and a 101 KB ring per CTA either way, two CTAs fit an SM
+constexpr int bwd_ctas_per_sm(int C, int rows) { return C == 2 ? (rows == 14 ? JTK_BWD_CTAS14 : JTK_BWD_CTAS9) : 2; }
 constexpr int kHalo = 4;        // (single-kernel forward_pass, STORE == 1) replicated slots on both sides of a row
 // Forward rows of the two-kernel modification table (v9): a row is C planes, plane c holds the slots sigma == c (mod C)
 // in slot order (plane c, index k = slot C*k + c), 32 entries + 2 replicated entries on both sides.  A backward lane
