@@ -847,7 +847,10 @@ __global__ void colstats_kernel(const float *__restrict__ delta, const DevPair *
             float x = delta[rr[k].tab_off + e];
             if (fabsf(x) < thr) x = 0.f;
             if (x > pos_thr) { sum += (double)x; cnt++; }
-            if (fabsf(x) > 1e-4f) sc[(rr[k].model == 0 ? 2 : 0) + (x > 0.f ? 1 : 0)]++;
+            // (strand, sign) counters as four predicated adds: a computed index put sc[] into local memory
+            const bool big = fabsf(x) > 1e-4f, pos = x > 0.f, m0 = rr[k].model == 0;
+            sc[0] += (unsigned)(big & !m0 & !pos); sc[1] += (unsigned)(big & !m0 & pos);
+            sc[2] += (unsigned)(big & m0 & !pos);  sc[3] += (unsigned)(big & m0 & pos);
         }
     }
     if (!live) return;
@@ -935,7 +938,9 @@ __global__ void candidates_kernel(CandArgs a) {
             float x = a.delta[rr[k].tab_off + e];
             if (fabsf(x) < thr) x = 0.f;
             if (x > a.pos_thr) { sum = __dadd_rn(sum, (double)x); cnt++; }
-            if (fabsf(x) > 1e-4f) sc[(rr[k].model == 0 ? 2 : 0) + (x > 0.f ? 1 : 0)]++;
+            const bool big = fabsf(x) > 1e-4f, pos = x > 0.f, m0 = rr[k].model == 0;
+            sc[0] += (unsigned)(big & !m0 & !pos); sc[1] += (unsigned)(big & !m0 & pos);
+            sc[2] += (unsigned)(big & m0 & !pos);  sc[3] += (unsigned)(big & m0 & pos);
         }
     }
     if (!live) return;
