@@ -287,6 +287,34 @@ void jtk_lc_rng_words(uint64_t seed, int use_state, const uint64_t *state, int n
  * '|' = indel columns + diagonal columns whose bases differ; <0 if the ops do not span (read, template) */
 int jtk_lc_nonmatch_columns(const uint8_t *ops, int n_ops, const uint8_t *read, int Lr, const uint8_t *tmpl, int Lt);
 
+/* The k-means + MCMC restarts of pseudo_mcmc::mcmc_clustering (haplotyper/src/local_clustering/pseudo_mcmc.rs:649-670:
+ * `restarts` = 20 x (misc::kmeans + mcmc_with_filter) on one generator, keeping the last maximum) for n_chains independent
+ * problems at once, one warp per chain.  Chain c: variants data_concat[data_off[c] ..] as n_rows[c] x
+ * n_cols[c] doubles (row-major), n_clusters[c] clusters, size_to_lk (max_poisson_lk(x, cov, 1, k), x = 0..n_rows[c]:
+ * n_rows[c]+1 doubles, concatenated), generator state rng_state[4c..4c+3] (Xoshiro256**, in/out).  Out: best assignment
+ * (one byte per read, chains concatenated), its likelihood, and a status per chain (0 ok; non-zero = an assertion of the
+ * reference failed: 1 k-means diverged, 2 invalid acceptance probability, 3 likelihood bookkeeping, 4 weights, 5 k < 2). */
+int jtk_mcmc_restarts_batch(jtk_ctx *ctx, int n_chains, const double *data_concat, const uint64_t *data_off,
+                            const uint32_t *n_rows, const uint32_t *n_cols, const uint32_t *n_clusters,
+                            const double *size_to_lk_concat, int restarts, uint64_t *rng_state, uint8_t *out_asn,
+                            double *out_lk, int *out_err);
+
+/* Host twin of one chain of jtk_mcmc_restarts_batch (parity tests) and the size_to_lk table both use. */
+int jtk_lc_mcmc_restarts_host(const double *data, int n, int D, int k, double cov, int restarts, uint64_t *state4,
+                              uint8_t *out_asn, double *out_lk);
+void jtk_lc_size_to_lk(int n, double cov, int k, double *out);
+/* jtk_lc_clustering_variants_rng for many chunks with the restarts of every chunk on the GPU: chunk g has n_reads[g] x
+ * n_probes[g] variants (dense, row-major, at var_off[g]), probe positions at ppos_off[g], template bytes
+ * tmpl_off[g]..tmpl_off[g+1], its own config and generator state (states[4g..], in/out).  Out per chunk: assignments at
+ * asn_off[g], log-posteriors at post_off[g] (n_reads[g] x post_stride), score, cluster number.  Results and generator
+ * streams are those of the per-chunk call (pseudo_mcmc.rs:77-107,213-274). */
+int jtk_lc_clustering_variants_batch(jtk_ctx *ctx, int n_chunks, const double *variants_concat, const uint64_t *var_off,
+                                     const int32_t *n_reads, const int32_t *n_probes, const uint32_t *probe_pos_concat,
+                                     const uint64_t *ppos_off, const uint8_t *tmpl_concat, const uint64_t *tmpl_off,
+                                     const jtk_gains *gains, const jtk_clustering_config *cfgs, uint64_t *states,
+                                     uint64_t *out_asn_concat, const uint64_t *asn_off, double *out_post_concat,
+                                     const uint64_t *post_off, int post_stride, double *out_score, int32_t *out_k);
+
 /* in-band cell count C = sum_d w(d) of one pair (SURVEY.md section 8d work unit); <0 if ops are invalid */
 int64_t jtk_band_cell_count(const uint8_t *ops, int n_ops, int Lt, int Lr, int radius);
 

@@ -224,6 +224,39 @@ class Context:
         return lk
 
 
+    def mcmc_restarts(self, datas, ks, covs, states, restarts: int = 20):
+        """jtk_mcmc_restarts_batch: the k-means + MCMC restarts of pseudo_mcmc::mcmc_clustering for many chains at once.
+        datas: list of float64[n, D]; ks, covs per chain; states: uint64[n_chains, 4] (updated in place).
+        Returns (list of uint8[n] assignments, float64[n_chains] likelihoods, int32[n_chains] status)."""
+        L = lib()
+        nch = len(datas)
+        ds = [np.ascontiguousarray(d, dtype=np.float64) for d in datas]
+        n_rows = np.array([d.shape[0] for d in ds], dtype=np.uint32)
+        n_cols = np.array([d.shape[1] for d in ds], dtype=np.uint32)
+        kk = np.ascontiguousarray(ks, dtype=np.uint32)
+        off = np.zeros(nch, dtype=np.uint64)
+        if nch > 1:
+            off[1:] = np.cumsum([d.size for d in ds[:-1]])
+        data = np.concatenate([d.ravel() for d in ds]) if nch else np.zeros(0)
+        s2l = []
+        L.jtk_lc_size_to_lk.argtypes = [C.c_int, C.c_double, C.c_int, C.c_void_p]
+        L.jtk_lc_size_to_lk.restype = None
+        for d, k, cov in zip(ds, kk, covs):
+            t = np.empty(d.shape[0] + 1, dtype=np.float64)
+            L.jtk_lc_size_to_lk(int(d.shape[0]), float(cov), int(k), _ptr(t))
+            s2l.append(t)
+        s2l = np.concatenate(s2l) if nch else np.zeros(0)
+        states = np.ascontiguousarray(states, dtype=np.uint64).reshape(nch, 4)
+        asn = np.zeros(int(n_rows.sum()), dtype=np.uint8)
+        lk = np.zeros(nch, dtype=np.float64)
+        err = np.zeros(nch, dtype=np.int32)
+        vp = C.c_void_p
+        L.jtk_mcmc_restarts_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp]
+        self._check(L.jtk_mcmc_restarts_batch(self._h, nch, _ptr(data), _ptr(off), _ptr(n_rows), _ptr(n_cols), _ptr(kk), _ptr(s2l),
+                                              restarts, _ptr(states), _ptr(asn), _ptr(lk), _ptr(err)))
+        pos = np.concatenate([[0], np.cumsum(n_rows)]).astype(np.int64)
+        return [asn[pos[c]:pos[c + 1]].copy() for c in range(nch)], lk, err, states
+
 class Batch:
     """jtk_batch: chunks + reads resident in HBM (level 2 of include/jtk_gpu.h)."""
 

@@ -3,6 +3,7 @@
 #include "../../include/jtk_gpu.h"
 #include "phmm_dev.cuh"
 #include "lc_host.h"
+#include "mcmc_dev.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -289,6 +290,13 @@ struct jtk_ctx {
     DevBuf<double> d_tabs;        // p-value / prior / expected-gain tables of the candidate kernel
     DevBuf<uint32_t> d_tab_off;
     DevBuf<jtk_candidate> d_cand;
+    // k-means / MCMC restarts on the device (jtk_mcmc_restarts_batch)
+    DevBuf<McmcChain> d_mc_chains;
+    DevBuf<double> d_mc_f64, d_mc_lk;
+    DevBuf<uint32_t> d_mc_u32;
+    DevBuf<uint8_t> d_mc_u8, d_mc_asn;
+    DevBuf<uint64_t> d_mc_rng, d_mc_asn_off;
+    DevBuf<int> d_mc_err;
     // pinned host staging
     PinBuf<DevPair> h_pairs;
     PinBuf<uint8_t> h_codes;
@@ -361,6 +369,8 @@ void jtk_ctx_destroy(jtk_ctx *ctx) {
     cudaSetDevice(ctx->device);
     ctx->d_models.release(); ctx->d_frows.release(); ctx->d_kf.release(); ctx->d_fwdinfo.release(); ctx->d_raw.release(); ctx->d_counter.release();
     ctx->d_minreq.release(); ctx->d_cols.release(); ctx->d_gather.release();
+    ctx->d_mc_chains.release(); ctx->d_mc_f64.release(); ctx->d_mc_lk.release(); ctx->d_mc_u32.release(); ctx->d_mc_u8.release();
+    ctx->d_mc_asn.release(); ctx->d_mc_rng.release(); ctx->d_mc_asn_off.release(); ctx->d_mc_err.release();
     ctx->d_tabs.release(); ctx->d_tab_off.release(); ctx->d_cand.release(); ctx->h_cand.release(); ctx->h_gather.release();
     ctx->h_pairs.release(); ctx->h_codes.release(); ctx->h_bits.release(); ctx->h_delta.release(); ctx->h_lk.release();
     ctx->h_homop.release();
@@ -1087,6 +1097,64 @@ int jtk_batch_colstats(jtk_batch *b, const float *min_req, int H, float pos_thr,
     if (!out) return JTK_OK;
     CU(cudaMemcpyAsync(out, b->d_stats.p, sizeof(jtk_colstat) * (size_t)total, cudaMemcpyDeviceToHost, st), "D2H stats");
     return batch_sync(b);
+}
+
+int jtk_mcmc_restarts_batch(jtk_ctx *ctx, int n_chains, const double *data_concat, const uint64_t *data_off,
+                            const uint32_t *n_rows, const uint32_t *n_cols, const uint32_t *n_clusters,
+                            const double *size_to_lk_concat, int restarts, uint64_t *rng_state, uint8_t *out_asn,
+                            double *out_lk, int *out_err) {
+    if (!ctx) return JTK_EINVAL;
+    if (n_chains < 0 || restarts < 0) return ctx->fail(JTK_EINVAL, "negative count");
+    if (n_chains == 0) return JTK_OK;
+    if (!data_concat || !data_off || !n_rows || !n_cols || !n_clusters || !size_to_lk_concat || !rng_state || !out_asn || !out_lk || !out_err)
+        return ctx->fail(JTK_EINVAL, "null argument");
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaStream_t st = ctx->stream;
+    std::vector<McmcChain> chains((size_t)n_chains);
+    std::vector<uint64_t> asn_off((size_t)n_chains);
+    size_t f64 = 0, u8 = 0, asn = 0, s2l = 0, smem = 0;
+    for (int c = 0; c < n_chains; c++) {
+        const uint32_t n = n_rows[c], D = n_cols[c], k = n_clusters[c];
+        if (n == 0 || D == 0 || D > (uint32_t)kMcmcMaxD || k == 0 || k > (uint32_t)kMcmcMaxK || k > n)
+            return ctx->fail(JTK_EINVAL, "chain needs 1 <= k <= min(n, 8) and 1 <= D <= 32");
+        McmcChain &m = chains[(size_t)c];
+        m.n = n; m.D = D; m.k = k; m.pad_ = 0; m.cov = 0.0;
+        m.off_f64 = f64; m.off_u32 = 0; m.off_u8 = u8;
+        asn_off[(size_t)c] = asn;
+        f64 += mcmc_f64_words(n, D); u8 += (mcmc_u8_bytes(n, D) + 127) & ~(size_t)127;
+        smem = std::max(smem, mcmc_smem_bytes(n, D, k));
+        asn += n;
+    }
+    if (smem > 200 * 1024) return ctx->fail(JTK_EINVAL, "chain too large for the shared memory of one SM");
+    // workspace: flat data and size_to_lk go in, everything else is scratch the kernel initialises itself
+    std::vector<double> wf(f64, 0.0);
+    for (int c = 0; c < n_chains; c++) {
+        const McmcChain &m = chains[(size_t)c];
+        std::memcpy(wf.data() + m.off_f64, data_concat + data_off[c], sizeof(double) * (size_t)m.n * m.D);
+        std::memcpy(wf.data() + m.off_f64 + (size_t)m.n * m.D, size_to_lk_concat + s2l, sizeof(double) * (m.n + 1));
+        s2l += m.n + 1;
+    }
+    CU(ctx->d_mc_chains.reserve((size_t)n_chains), "cudaMalloc mcmc chains");
+    CU(ctx->d_mc_f64.reserve(f64), "cudaMalloc mcmc workspace");
+    CU(ctx->d_mc_u8.reserve(u8), "cudaMalloc mcmc workspace");
+    CU(ctx->d_mc_asn.reserve(asn), "cudaMalloc mcmc assignments");
+    CU(ctx->d_mc_asn_off.reserve((size_t)n_chains), "cudaMalloc mcmc offsets");
+    CU(ctx->d_mc_rng.reserve((size_t)4 * n_chains), "cudaMalloc mcmc rng");
+    CU(ctx->d_mc_lk.reserve((size_t)n_chains), "cudaMalloc mcmc lk");
+    CU(ctx->d_mc_err.reserve((size_t)n_chains), "cudaMalloc mcmc status");
+    CU(cudaMemcpyAsync(ctx->d_mc_chains.p, chains.data(), sizeof(McmcChain) * (size_t)n_chains, cudaMemcpyHostToDevice, st), "H2D mcmc chains");
+    CU(cudaMemcpyAsync(ctx->d_mc_f64.p, wf.data(), sizeof(double) * f64, cudaMemcpyHostToDevice, st), "H2D mcmc data");
+    CU(cudaMemcpyAsync(ctx->d_mc_asn_off.p, asn_off.data(), sizeof(uint64_t) * (size_t)n_chains, cudaMemcpyHostToDevice, st), "H2D mcmc offsets");
+    CU(cudaMemcpyAsync(ctx->d_mc_rng.p, rng_state, sizeof(uint64_t) * 4 * (size_t)n_chains, cudaMemcpyHostToDevice, st), "H2D mcmc rng");
+    CU(launch_mcmc_restarts(ctx->d_mc_chains.p, n_chains, ctx->d_mc_f64.p, ctx->d_mc_u8.p, ctx->d_mc_rng.p, ctx->d_mc_asn.p,
+                            ctx->d_mc_asn_off.p, ctx->d_mc_lk.p, ctx->d_mc_err.p, restarts, smem, st), "mcmc launch");
+    ctx->launches++;
+    CU(cudaMemcpyAsync(rng_state, ctx->d_mc_rng.p, sizeof(uint64_t) * 4 * (size_t)n_chains, cudaMemcpyDeviceToHost, st), "D2H mcmc rng");
+    CU(cudaMemcpyAsync(out_asn, ctx->d_mc_asn.p, asn, cudaMemcpyDeviceToHost, st), "D2H mcmc assignments");
+    CU(cudaMemcpyAsync(out_lk, ctx->d_mc_lk.p, sizeof(double) * (size_t)n_chains, cudaMemcpyDeviceToHost, st), "D2H mcmc lk");
+    CU(cudaMemcpyAsync(out_err, ctx->d_mc_err.p, sizeof(int) * (size_t)n_chains, cudaMemcpyDeviceToHost, st), "D2H mcmc status");
+    CU(cudaStreamSynchronize(st), "mcmc execution");
+    return JTK_OK;
 }
 
 int jtk_batch_gather(jtk_batch *b, int tmpl, const float *min_req, int H, const uint32_t *cols, int D, double *out) {

@@ -599,13 +599,18 @@ static void get_read_lk_gains(const Mat &variants, const std::vector<size_t> &as
     }
 }
 
-static ClusterOut mcmc_clustering(const Mat &data, size_t k, double cov, Rng &rng) { // :649-670
-    std::vector<size_t> best; double best_lk = 0; bool any = false;
-    for (int t = 0; t < 20; t++) {
+// mcmc_clustering (:649-670) in two halves: the 20 restarts on one generator (the part jtk_mcmc_restarts_batch runs on the
+// GPU for many chunks at once) and the bookkeeping on the best assignment.
+static void mcmc_restarts(const Mat &data, size_t k, double cov, Rng &rng, int restarts, std::vector<size_t> &best, double &best_lk) {
+    bool any = false;
+    best.clear(); best_lk = 0;
+    for (int t = 0; t < restarts; t++) {
         std::vector<size_t> asn = kmeans(data, k, rng);
         const double lk = mcmc_with_filter(data, asn, k, cov, rng);
         if (!any || !(lk < best_lk)) { best = asn; best_lk = lk; any = true; } // max_by keeps the last maximum
     }
+}
+static ClusterOut mcmc_finish(const Mat &data, size_t k, double cov, const std::vector<size_t> &best, double best_lk) {
     ClusterOut o; o.asn = best;
     get_read_lk_gains(data, o.asn, k, o.used, o.read_gains);
     std::vector<size_t> counts(k, 0);
@@ -614,6 +619,11 @@ static ClusterOut mcmc_clustering(const Mat &data, size_t k, double cov, Rng &rn
     for (size_t c : counts) cluster_lk += max_poisson_lk(c, cov, 1, k);
     o.score = best_lk - cluster_lk;
     return o;
+}
+static ClusterOut mcmc_clustering(const Mat &data, size_t k, double cov, Rng &rng) { // :649-670
+    std::vector<size_t> best; double best_lk = 0;
+    mcmc_restarts(data, k, cov, rng, 20, best, best_lk);
+    return mcmc_finish(data, k, cov, best, best_lk);
 }
 
 static ClusterOut use_highest_gain(const Mat &data) { // :673-693
@@ -952,6 +962,151 @@ int jtk_lc_clustering_variants_rng(const double *variants, int n_reads, int n_pr
                                             out_post, post_stride, out_score, out_k);
     std::memcpy(state4, rng.s, 32);
     return rc;
+}
+
+// Host twin of one chain of jtk_mcmc_restarts_batch (tests: device == host, bit for bit)
+int jtk_lc_mcmc_restarts_host(const double *data, int n, int D, int k, double cov, int restarts, uint64_t *state4,
+                              uint8_t *out_asn, double *out_lk) {
+    try {
+        if (!data || !state4 || !out_asn || !out_lk || n < 1 || D < 1 || k < 1) { g_lc_error = "bad argument"; return JTK_EINVAL; }
+        Mat m((size_t)n);
+        for (int i = 0; i < n; i++) m[(size_t)i].assign(data + (size_t)i * D, data + (size_t)(i + 1) * D);
+        Rng rng(0);
+        std::memcpy(rng.s, state4, 32);
+        std::vector<size_t> best; double best_lk = 0;
+        mcmc_restarts(m, (size_t)k, cov, rng, restarts, best, best_lk);
+        std::memcpy(state4, rng.s, 32);
+        for (int i = 0; i < n; i++) out_asn[i] = (uint8_t)best[(size_t)i];
+        *out_lk = best_lk;
+        return JTK_OK;
+    } catch (const std::exception &e) { g_lc_error = e.what(); return JTK_EINVAL; }
+}
+void jtk_lc_size_to_lk(int n, double cov, int k, double *out) { // max_poisson_lk(x, cov, 1, k), x = 0..n
+    for (int x = 0; x <= n; x++) out[x] = max_poisson_lk((size_t)x, cov, 1, (size_t)k);
+}
+
+// pseudo_mcmc::clustering after search_variants (clustering_variants_impl) for MANY chunks, with the k-means / MCMC
+// restarts of every chunk on the GPU (jtk_mcmc_restarts_batch): cluster_filtered_variants (:213-274) is walked level by
+// level -- all chunks that still try cluster number k run their 20 restarts side by side, then each decides on the host
+// whether to go on -- so every chunk sees exactly the generator stream and the decisions of the per-chunk call.
+int jtk_lc_clustering_variants_batch(jtk_ctx *ctx, int n_chunks, const double *variants_concat, const uint64_t *var_off,
+                                     const int32_t *n_reads, const int32_t *n_probes, const uint32_t *probe_pos_concat,
+                                     const uint64_t *ppos_off, const uint8_t *tmpl_concat, const uint64_t *tmpl_off,
+                                     const jtk_gains *gains_c, const jtk_clustering_config *cfgs, uint64_t *states,
+                                     uint64_t *out_asn_concat, const uint64_t *asn_off, double *out_post_concat,
+                                     const uint64_t *post_off, int post_stride, double *out_score, int32_t *out_k) {
+    try {
+        if (!ctx || n_chunks < 0 || !var_off || !n_reads || !n_probes || !ppos_off || !tmpl_concat || !tmpl_off || !gains_c || !cfgs ||
+            !states || !out_asn_concat || !asn_off || !out_post_concat || !post_off || !out_score || !out_k || post_stride < 1) {
+            g_lc_error = "null / bad argument"; return JTK_EINVAL;
+        }
+        const Gains gains = to_gains(gains_c);
+        struct Job {
+            Mat vars; VarTypes vt; size_t copy_num = 0; double coverage = 0, per_cluster = 0;
+            size_t k = 0, end = 0, max_k = 1; double mx = 0; bool active = false;
+            std::vector<size_t> assignments; std::vector<bool> prev_used;
+            DevResult res;
+        };
+        std::vector<Job> jobs((size_t)n_chunks);
+        for (int g = 0; g < n_chunks; g++) {
+            Job &j = jobs[(size_t)g];
+            const size_t n = (size_t)n_reads[g], D = (size_t)n_probes[g];
+            j.copy_num = (size_t)cfgs[g].copy_num; j.coverage = cfgs[g].coverage; j.per_cluster = cfgs[g].local_coverage;
+            if (j.copy_num < 2) { // clustering (:86-88)
+                j.res = { std::vector<size_t>(n, 0), Mat(n, std::vector<double>(1, 0.0)), 0.0, 1 };
+                continue;
+            }
+            const uint8_t *tmpl = tmpl_concat + tmpl_off[g];
+            const size_t Lt = (size_t)(tmpl_off[g + 1] - tmpl_off[g]);
+            const std::vector<size_t> homop = homopolymer_length(tmpl, Lt);
+            for (size_t d = 0; d < D; d++) {
+                size_t bp; DiffType t;
+                pos_to_bp_and_difftype(probe_pos_concat[ppos_off[g] + d], bp, t);
+                j.vt.push_back({ bp < homop.size() ? homop[bp] : 0, t });
+            }
+            j.vars.assign(n, std::vector<double>());
+            for (size_t r = 0; r < n; r++) j.vars[r].assign(variants_concat + var_off[g] + r * D, variants_concat + var_off[g] + (r + 1) * D);
+            // cluster_filtered_variants (:213-274), the part before the loop
+            if (D == 0 || n <= j.copy_num) {
+                j.res = { std::vector<size_t>(n, 0), Mat(n, std::vector<double>(1, 0.0)), 0.0, 1 };
+                continue;
+            }
+            j.assignments.assign(n, 0);
+            j.prev_used.assign(D, false);
+            j.end = std::min(j.copy_num, 1 + 2 * j.vt.size());
+            j.k = std::max<size_t>(j.end, 5) - 3;
+            j.active = j.k <= j.end;
+        }
+        for (;;) { // one level: every active chunk runs the restarts for its current k
+            std::vector<int> act;
+            for (int g = 0; g < n_chunks; g++) if (jobs[(size_t)g].active) act.push_back(g);
+            if (act.empty()) break;
+            std::vector<double> data, s2l, lk(act.size());
+            std::vector<uint64_t> doff, rng(4 * act.size());
+            std::vector<uint32_t> nr, nc, kk;
+            std::vector<int> err(act.size());
+            size_t n_asn = 0;
+            for (size_t a = 0; a < act.size(); a++) {
+                const Job &j = jobs[(size_t)act[a]];
+                doff.push_back(data.size());
+                for (const auto &row : j.vars) data.insert(data.end(), row.begin(), row.end());
+                nr.push_back((uint32_t)j.vars.size()); nc.push_back((uint32_t)j.vars[0].size()); kk.push_back((uint32_t)j.k);
+                for (size_t x = 0; x <= j.vars.size(); x++) s2l.push_back(max_poisson_lk(x, j.coverage, 1, j.k));
+                std::memcpy(&rng[4 * a], states + 4 * (size_t)act[a], 32);
+                n_asn += j.vars.size();
+            }
+            std::vector<uint8_t> asn(n_asn);
+            const int rc = jtk_mcmc_restarts_batch(ctx, (int)act.size(), data.data(), doff.data(), nr.data(), nc.data(), kk.data(),
+                                                   s2l.data(), 20, rng.data(), asn.data(), lk.data(), err.data());
+            if (rc) { g_lc_error = std::string("jtk_mcmc_restarts_batch: ") + jtk_last_error(ctx); return rc; }
+            size_t apos = 0;
+            for (size_t a = 0; a < act.size(); a++) {
+                Job &j = jobs[(size_t)act[a]];
+                const size_t n = j.vars.size();
+                if (err[a] != 0) throw Panic("assertion failed on the device (mcmc status " + std::to_string(err[a]) + ")");
+                std::memcpy(states + 4 * (size_t)act[a], &rng[4 * a], 32);
+                std::vector<size_t> best(n);
+                for (size_t i = 0; i < n; i++) best[i] = asn[apos + i];
+                apos += n;
+                ClusterOut c = mcmc_finish(j.vars, j.k, j.coverage, best, lk[a]);
+                if (j.k == 2) {
+                    ClusterOut h = use_highest_gain(j.vars);
+                    if (c.score < h.score) c = h;
+                }
+                (void)min_gain(gains, j.vt, c.used); // as the reference (its result only feeds a trace! line)
+                const double expected_gain = expected_gains(gains, j.vt, j.prev_used, c.used) * j.per_cluster + 0.1;
+                if (expected_gain < c.score - j.mx) {
+                    j.assignments = c.asn; j.mx = c.score; j.max_k = j.k; j.prev_used = c.used;
+                    j.k++;
+                    j.active = j.k <= j.end;
+                } else j.active = false;
+                if (!j.active) j.res = { j.assignments, get_likelihood_gain(j.vars, j.assignments, j.max_k), j.mx, j.max_k };
+            }
+        }
+        for (int g = 0; g < n_chunks; g++) { // clustering (:77-107): re-assignment to the best cluster, log-posteriors
+            Job &j = jobs[(size_t)g];
+            DevResult &r = j.res;
+            if (j.copy_num >= 2) {
+                for (size_t i = 0; i < r.asn.size(); i++) {
+                    const auto &lks = r.gains[i];
+                    size_t bi = 0;
+                    for (size_t c = 0; c < lks.size(); c++) if (!(lks[c] < lks[bi])) bi = c; // last maximum
+                    if (lks[r.asn[i]] + 0.001 < lks[bi]) r.asn[i] = bi;
+                }
+                for (auto &xs : r.gains) { const double tot = logsumexp(xs); for (double &x : xs) x -= tot; }
+            }
+            if ((int)r.k > post_stride) { g_lc_error = "post_stride smaller than the cluster number"; return JTK_EINVAL; }
+            for (size_t i = 0; i < r.asn.size(); i++) {
+                out_asn_concat[asn_off[g] + i] = r.asn[i];
+                for (size_t c = 0; c < r.k; c++) out_post_concat[post_off[g] + i * (size_t)post_stride + c] = r.gains[i][c];
+            }
+            out_score[g] = r.score; out_k[g] = (int32_t)r.k;
+        }
+        return JTK_OK;
+    } catch (const std::exception &e) {
+        g_lc_error = e.what();
+        return JTK_EINVAL;
+    }
 }
 
 // test hooks for the reference's own unit tests on these files (pseudo_mcmc.rs:876-904)

@@ -194,6 +194,59 @@ def _clustering_variants_rng(variants, probe_pos, template, config: ClusteringCo
     return ClusteringResult(asn, post.reshape(n, pstride)[:, :kk].copy(), float(score.value), kk, pp.copy())
 
 
+def _clustering_variants_batch_gpu(ctx, jobs) -> List[ClusteringResult]:
+    """jtk_lc_clustering_variants_batch: the per-chunk `_clustering_variants_rng` for many chunks, with the 20 k-means +
+    MCMC restarts of every chunk as one warp each on the GPU.  jobs: list of (variants[n, D], probe_pos[D],
+    template, config, state[4]); the states are advanced in place exactly as by the per-chunk call."""
+    L = _bind()
+    vp = C.c_void_p
+    L.jtk_lc_clustering_variants_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp]
+    m = len(jobs)
+    if m == 0:
+        return []
+    vs = [np.ascontiguousarray(j[0], dtype=np.float64).reshape(len(j[0]), -1) for j in jobs]
+    pps = [np.ascontiguousarray(j[1], dtype=np.uint32) for j in jobs]
+    for v, pp in zip(vs, pps):
+        if v.shape[1] != len(pp):
+            raise ValueError("variants must have one column per probe")
+    ts = [_lib._u8(j[2]) for j in jobs]
+    n_reads = np.array([v.shape[0] for v in vs], dtype=np.int32)
+    n_probes = np.array([len(pp) for pp in pps], dtype=np.int32)
+
+    def offs(sizes):
+        o = np.zeros(len(sizes) + 1, dtype=np.uint64)
+        np.cumsum(sizes, out=o[1:])
+        return o
+    var_off, ppos_off, tmpl_off = offs([v.size for v in vs]), offs(n_probes), offs([len(t) for t in ts])
+    vcat = np.concatenate([v.ravel() for v in vs]) if var_off[-1] else np.zeros(1)
+    pcat = np.concatenate(pps) if ppos_off[-1] else np.zeros(1, dtype=np.uint32)
+    tcat = np.concatenate(ts)
+    cfgs = (_CConfig * m)(*[j[3].to_c() for j in jobs])
+    g = jobs[0][3].gains.to_c()
+    states = np.ascontiguousarray(np.stack([j[4] for j in jobs]), dtype=np.uint64)
+    pstride = max(max(j[3].copy_num, 1) for j in jobs)
+    asn_off = offs(n_reads)
+    post_off = offs(n_reads.astype(np.int64) * pstride)
+    asn = np.zeros(int(asn_off[-1]), dtype=np.uint64)
+    post = np.zeros(int(post_off[-1]), dtype=np.float64)
+    score = np.zeros(m, dtype=np.float64)
+    kk = np.zeros(m, dtype=np.int32)
+    p = _lib._ptr
+    rc = L.jtk_lc_clustering_variants_batch(ctx._h, m, p(vcat), p(var_off), p(n_reads), p(n_probes), p(pcat), p(ppos_off), p(tcat),
+                                            p(tmpl_off), C.byref(g), C.cast(cfgs, vp), p(states), p(asn), p(asn_off), p(post),
+                                            p(post_off), pstride, p(score), p(kk))
+    if rc != 0:
+        raise _lib.JtkError(rc, L.jtk_lc_last_error().decode())
+    out = []
+    for i, j in enumerate(jobs):
+        j[4][:] = states[i]
+        n, k = int(n_reads[i]), int(kk[i])
+        a = asn[int(asn_off[i]):int(asn_off[i]) + n].copy()
+        po = post[int(post_off[i]):int(post_off[i]) + n * pstride].reshape(n, pstride)[:, :k].copy()
+        out.append(ClusteringResult(a, po, float(score[i]), k, pps[i].copy()))
+    return out
+
+
 def _search_and_cluster(ctx, hmm, cons, seqs, ops, strands, config: ClusteringConfig, state: np.ndarray) -> ClusteringResult:
     """pseudo_mcmc::clustering (pseudo_mcmc.rs:77-107) for one pile-up with the caller's generator."""
     n = len(seqs)
@@ -344,6 +397,26 @@ def host_threads() -> int:
     return max(1, min(int(os.environ.get("JTK_HOST_THREADS", os.cpu_count() or 1)), 64))
 
 
+GPU_MCMC_CAPACITY = 1776   # chains one B200 runs side by side (148 SMs x 12 warps at 153 registers)
+GPU_MCMC_HOST_EQUIV = 25   # chunks one host thread clusters in the time the GPU takes for its (concurrent) chains
+
+
+def gpu_mcmc_share(n_chunks: int) -> int:
+    """How many of n_chunks go to jtk_mcmc_restarts_batch: none for small calls (a chain takes 25x longer on a warp than
+    on a core), otherwise as many as the GPU runs concurrently, leaving the host threads an equal-time share.
+    JTK_GPU_MCMC=0 / 1 forces none / all."""
+    import os
+    mode = os.environ.get("JTK_GPU_MCMC", "auto")
+    if mode == "0":
+        return 0
+    if mode == "1":
+        return n_chunks
+    host_share = GPU_MCMC_HOST_EQUIV * host_threads()
+    if n_chunks <= host_share:
+        return 0
+    return min(n_chunks - host_share, GPU_MCMC_CAPACITY)
+
+
 def _cluster_pileups(ctx, hmm, gains: Gains, coverage: float, read_type: str, pile: Dict[int, Tuple[List[Node], Chunk]]):
     """clustering_on_pileup (mod.rs:86-123) for a set of pile-ups: one polish batch and one table batch per radius; the
     host clustering of the chunks runs on a thread pool (the C call releases the GIL), one task per chunk as rayon does."""
@@ -398,10 +471,31 @@ def _cluster_pileups(ctx, hmm, gains: Gains, coverage: float, read_type: str, pi
                 state = _rng_seed(pile[cids[g]][1].id * 3490)                       # mod.rs:97
                 return g, _clustering_variants_rng(variants[off[s]:off[s + 1], :max(d, 1)], probe_pos[s, :d], cons[g],
                                                    cfgs[g], state)
-            with ThreadPoolExecutor(max_workers=host_threads()) as pool:
-                for g, r in pool.map(one, list(enumerate(small))):
+            # The 2.4 M sequential MCMC proposals of a chunk take ~0.1 s of one host core and ~2.5 s of one GPU warp, but
+            # the GPU runs ~1 800 chunks side by side (csrc/mcmc_kernels.cu): with many chunks in the call the restarts of
+            # most of them go to the GPU while the host threads work through the rest.  Same streams, same results.
+            todo = list(enumerate(small))
+            n_gpu = gpu_mcmc_share(len(todo))
+            gpu_part = [sg for sg in todo[:n_gpu] if int(n_probes[sg[0]]) >= 1]
+            gpu_set = {sg[0] for sg in gpu_part}
+            host_part = [sg for sg in todo if sg[0] not in gpu_set]
+
+            def gpu_side():
+                jobs = []
+                for s, g in gpu_part:
+                    d = int(n_probes[s])
+                    jobs.append((variants[off[s]:off[s + 1], :d], probe_pos[s, :d], cons[g], cfgs[g],
+                                 _rng_seed(pile[cids[g]][1].id * 3490)))
+                return _clustering_variants_batch_gpu(ctx, jobs)
+            with ThreadPoolExecutor(max_workers=host_threads() + 1) as pool:
+                fut = pool.submit(gpu_side) if gpu_part else None
+                for g, r in pool.map(one, host_part):
                     firsts[g] = r
+                if fut is not None:
+                    for (s, g), r in zip(gpu_part, fut.result()):
+                        firsts[g] = r
             tm["host_clustering"] += time.perf_counter() - t0
+            tm["gpu_mcmc_chunks"] = tm.get("gpu_mcmc_chunks", 0) + len(gpu_part)
         t0 = time.perf_counter()
         for g, c in enumerate(cids):
             sl = slice(first[g], first[g + 1])

@@ -169,3 +169,44 @@ def test_kiley_shaped_clustering_call(ctx):
     assert r.k == 2
     agree = (r.assignments == d["hap"]).mean()
     assert max(agree, 1 - agree) >= 0.95
+
+
+def _host_restarts(data, k, cov, state, restarts):
+    import ctypes as C
+    from jtk_b200 import _lib
+    L = _lib.lib()
+    d = np.ascontiguousarray(data, dtype=np.float64)
+    st = np.array(state, dtype=np.uint64)
+    asn = np.zeros(d.shape[0], dtype=np.uint8)
+    lk = C.c_double()
+    L.jtk_lc_mcmc_restarts_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
+                                            C.POINTER(C.c_double)]
+    rc = L.jtk_lc_mcmc_restarts_host(_lib._ptr(d), d.shape[0], d.shape[1], int(k), float(cov), restarts, _lib._ptr(st), _lib._ptr(asn),
+                                     C.byref(lk))
+    assert rc == 0
+    return asn, lk.value, st
+
+
+def test_device_mcmc_restarts_equal_the_host_twin(ctx):
+    """jtk_mcmc_restarts_batch (one warp per chain) against the host restatement of mcmc_clustering's
+    restart loop on the same variants and generator states: assignments, likelihood and the generator state after the
+    restarts must be identical, bit for bit (the generator state proves that every accept / reject went the same way)."""
+    from jtk_b200 import pipeline as P
+    rng = np.random.default_rng(17)
+    datas, ks, covs, states = [], [], [], []
+    for c, (n, D, k) in enumerate([(60, 6, 2), (24, 1, 2), (40, 3, 3), (12, 5, 2), (60, 4, 4), (33, 2, 2), (60, 6, 2), (18, 8, 3)]):
+        hap = rng.integers(0, k, n)
+        sign = np.where(rng.random((k, D)) < 0.5, 1.0, -1.0)
+        v = sign[hap] * rng.normal(6, 2, (n, D))
+        v[rng.random((n, D)) < 0.15] = 0.0
+        if c == 6:
+            v = rng.normal(0, 1.5, (n, D))  # no structure: the chain wanders, many acceptances through exp()
+        datas.append(v); ks.append(k); covs.append(n / k); states.append(P._rng_seed(1000 + 7 * c))
+    restarts = 3
+    asn, lk, err, st = ctx.mcmc_restarts(datas, ks, covs, np.array(states), restarts)
+    assert (err == 0).all(), err
+    for c in range(len(datas)):
+        ha, hlk, hst = _host_restarts(datas[c], ks[c], covs[c], states[c], restarts)
+        assert np.array_equal(asn[c], ha), c
+        assert lk[c] == hlk, (c, lk[c], hlk)
+        assert np.array_equal(st[c], hst), c

@@ -82,6 +82,28 @@ def test_sharded_driver_equals_single_rank(ctx):
         assert np.array_equal(np.array(a[4]), np.array(b[4]))
 
 
+def test_gpu_mcmc_path_equals_host_path(ctx, monkeypatch):
+    """with the k-means / MCMC restarts of every chunk on the GPU (jtk_lc_clustering_variants_batch) the
+    driver returns exactly what it returns with the per-chunk host calls: consensus, score, cluster number, assignments
+    and log-posteriors of every read."""
+    ds, _ = make_dataset(4, 500, 30, seed0=900)
+    ds.selected_chunks[3].copy_num = 3  # two levels of cluster_filtered_variants for one chunk
+    P.update_coverage(ds)
+    hmm = PairHiddenMarkovModelOnStrands.default()
+    pile = P.pileup_nodes(copy.deepcopy(ds), {1, 2, 3, 4})
+    monkeypatch.setenv("JTK_GPU_MCMC", "0")
+    host = P._cluster_pileups(ctx, hmm, GAINS, ds.coverage, "ONT", pile)
+    assert P.LAST_TIMING.get("gpu_mcmc_chunks", 0) == 0
+    monkeypatch.setenv("JTK_GPU_MCMC", "1")
+    dev = P._cluster_pileups(ctx, hmm, GAINS, ds.coverage, "ONT", pile)
+    assert P.LAST_TIMING["gpu_mcmc_chunks"] >= 3
+    for cid in host:
+        a, b = host[cid], dev[cid]
+        assert np.array_equal(a[0], b[0]) and a[1] == b[1] and a[2] == b[2], cid
+        assert np.array_equal(np.array(a[3]), np.array(b[3])), cid
+        assert np.array_equal(np.array(a[4]), np.array(b[4])), cid
+
+
 def test_fit_loop_and_default_gain_calibration(ctx):
     ds, _ = make_dataset(6, 300, 24, seed0=900)
     models = P.estimate_model_parameters_on_both_strands(ds, ctx=ctx, rounds=2)
