@@ -312,7 +312,7 @@ __device__ __forceinline__ int mcmc_with_filter(const ChainView &c, DevRng &rng,
 
 // One warp per chain.  rng_state: 4 words per chain, in/out.  out_asn: best assignment (bytes, n per chain at asn_off),
 // out_lk: its likelihood, out_err: 0 or the first failure.  Dynamic shared memory: smem_per_chain bytes per warp.
-__global__ void __launch_bounds__(128) mcmc_restarts_kernel(const McmcChain *__restrict__ chains, int n_chains, double *wf64,
+__global__ void __launch_bounds__(128, 4) mcmc_restarts_kernel(const McmcChain *__restrict__ chains, int n_chains, double *wf64,
                                                             uint8_t *wu8, uint64_t *rng_state, uint8_t *out_asn,
                                                             const uint64_t *__restrict__ asn_off, double *out_lk, int *out_err,
                                                             int restarts, int smem_per_chain) {

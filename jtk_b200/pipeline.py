@@ -397,7 +397,7 @@ def host_threads() -> int:
     return max(1, min(int(os.environ.get("JTK_HOST_THREADS", os.cpu_count() or 1)), 64))
 
 
-GPU_MCMC_CAPACITY = 1776   # chains one B200 runs side by side (148 SMs x 12 warps at 153 registers)
+GPU_MCMC_CAPACITY = 2368   # chains one B200 runs side by side (148 SMs x 16 warps at 127 registers)
 GPU_MCMC_HOST_EQUIV = 25   # chunks one host thread clusters in the time the GPU takes for its (concurrent) chains
 
 
