@@ -229,6 +229,11 @@ int jtk_polish_until_converge_batch(jtk_ctx *ctx, const jtk_hmm_params *fwd, con
 /* per-column sums over the first take_num reads of every template of a batch (device reduction used by the
  * polish loop): out[stat_off[t] + e] = sum_r profile_r[e] */
 int jtk_batch_colsums(jtk_batch *b, int take_num, double *out, const uint64_t *stat_off);
+/* The per-column choice of the polish loop on the device: out[col_off[t] + j] = the row (0..13) with the largest gain summed
+ * over the first take_num reads of template t, among the rows valid at column j (not the template's own base, within
+ * ignore_edge of neither end) and above min_gain, or -1.  Same sums and tie-break (first maximum) as a host scan of
+ * jtk_batch_colsums; tmpl_len[t] + 1 bytes per template. */
+int jtk_batch_best_edits(jtk_batch *b, int take_num, int ignore_edge, double min_gain, int8_t *out, const uint64_t *col_off);
 
 /* ---- HMM fit (K4) --------------------------------------------------------------------------------------- */
 /* Expected transition / emission counts of every pair of a batch under (fwd, rev), summed per strand:

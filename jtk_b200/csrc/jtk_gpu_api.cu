@@ -1021,6 +1021,53 @@ __global__ void colsums_kernel(const float *__restrict__ delta, const DevPair *_
     out[stat_off[t] + e] = sum;
 }
 
+
+// The inner loop of the polish edit selection (csrc/polish.cpp select_edits): for column j of template t, the row with the
+// largest summed gain over the first `take` reads (> min_gain, first maximum wins) among the rows that are valid at j, or
+// -1.  One thread per column; the sums are formed per (column, row) in the order colsums_kernel uses, so the choice is the
+// one the host makes on the full table -- but one byte per column crosses PCIe instead of 112.
+__global__ void best_edit_kernel(const float *__restrict__ delta, const DevPair *__restrict__ pairs,
+                                 const uint32_t *__restrict__ tp_start, const uint32_t *__restrict__ tp_ids,
+                                 const uint32_t *__restrict__ tmpl_len, const uint8_t *__restrict__ codes,
+                                 const uint32_t *__restrict__ tmpl_code_off, const unsigned long long *__restrict__ col_off,
+                                 int take, int ignore_edge, double min_gain, int8_t *__restrict__ out) {
+    __shared__ ReadRef rr[kReadTile];
+    const int t = blockIdx.y;
+    const int L = (int)tmpl_len[t];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((int)(blockIdx.x * blockDim.x) > L) return;
+    const bool live = j <= L;
+    double sum[kNumRow];
+#pragma unroll
+    for (int r = 0; r < kNumRow; r++) sum[r] = 0.0;
+    const uint32_t first = tp_start[t];
+    const uint32_t last = min(tp_start[t + 1], first + (uint32_t)max(take, 0));
+    for (uint32_t k0 = first; k0 < last; k0 += kReadTile) {
+        const int n = stage_reads(rr, pairs, tp_ids, k0, last);
+        if (!live) continue;
+        for (int k = 0; k < n; k++) {
+            const float *row = delta + rr[k].tab_off + (size_t)j * kNumRow;
+#pragma unroll
+            for (int r = 0; r < kNumRow; r++) sum[r] += (double)row[r];
+        }
+    }
+    if (!live) return;
+    int best = -1;
+    double bg = min_gain;
+    const int own = j < L ? (int)(codes[tmpl_code_off[t] + 1 + j] & 3) : -1; // template code of t[j]
+    if (j >= ignore_edge && j <= L - ignore_edge) {
+#pragma unroll
+        for (int r = 0; r < kNumRow; r++) {
+            if (r == own) continue;
+            if (r < 4 && j >= L - ignore_edge) continue;
+            if (r >= 8 && r < 8 + JTK_COPY_SIZE && j + (r - 7) > L - ignore_edge) continue;
+            if (r >= 8 + JTK_COPY_SIZE && j + (r - 7 - JTK_COPY_SIZE) > L - ignore_edge) continue;
+            if (sum[r] > bg) { bg = sum[r]; best = r; }
+        }
+    }
+    out[col_off[t] + j] = (int8_t)best;
+}
+
 } // namespace
 
 extern "C" {
@@ -1458,6 +1505,29 @@ int jtk_batch_colsums(jtk_batch *b, int take_num, double *out, const uint64_t *s
     CU(cudaGetLastError(), "colsums launch");
     ctx->launches++;
     CU(cudaMemcpyAsync(out, ctx->d_gather.p, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, st), "D2H sums");
+    return batch_sync(b);
+}
+
+int jtk_batch_best_edits(jtk_batch *b, int take_num, int ignore_edge, double min_gain, int8_t *out, const uint64_t *col_off) {
+    if (!b) return JTK_EINVAL;
+    jtk_ctx *ctx = b->ctx;
+    if (!out || !col_off || take_num < 0 || ignore_edge < 0) return ctx->fail(JTK_EINVAL, "bad argument");
+    if (!b->has_profiles) return ctx->fail(JTK_ESTATE, "jtk_batch_modtable has not run");
+    if (b->n_tmpl == 0) return JTK_OK;
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaStream_t st = ctx->stream;
+    uint64_t total = 0;
+    for (int t = 0; t < b->n_tmpl; t++) total = std::max<uint64_t>(total, col_off[t] + (uint64_t)b->tmpl_len[t] + 1);
+    CU(b->d_stat_off.reserve((size_t)b->n_tmpl), "cudaMalloc col_off");
+    CU(ctx->d_mc_asn.reserve((size_t)total), "cudaMalloc best edits");
+    CU(b->up_stat_off.put(b->d_stat_off.p, col_off, sizeof(uint64_t) * (size_t)b->n_tmpl, st), "H2D col_off");
+    dim3 grid((unsigned)((b->max_lt + 1 + 127) / 128), (unsigned)b->n_tmpl);
+    best_edit_kernel<<<grid, 128, 0, st>>>(b->d_delta.p, b->d_pairs.p, b->d_tp_start.p, b->d_tp_ids.p, b->d_tmpl_len.p, b->d_codes.p,
+                                           b->d_tmpl_code_off.p, b->d_stat_off.p, take_num, ignore_edge, min_gain,
+                                           reinterpret_cast<int8_t *>(ctx->d_mc_asn.p));
+    CU(cudaGetLastError(), "best_edit launch");
+    ctx->launches++;
+    CU(cudaMemcpyAsync(out, ctx->d_mc_asn.p, (size_t)total, cudaMemcpyDeviceToHost, st), "D2H best edits");
     return batch_sync(b);
 }
 

@@ -19,27 +19,15 @@ constexpr int NUM_ROW = JTK_NUM_ROW, COPY = JTK_COPY_SIZE;
 
 struct Edit { int j, row; };
 
-inline int code(uint8_t c) {
-    switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 0; }
-}
-
 // greedy left-to-right pick of positive-gain edits on the summed table
-void select_edits(const double *sum, const std::vector<uint8_t> &tmpl, int ignore_edge, std::vector<Edit> &ed) {
+// Greedy left-to-right pick over the per-column best rows (jtk_batch_best_edits: the row with the largest summed gain
+// > kMinGain among the rows valid at j, first maximum, or -1): an edit switches the next kInactive positions off.
+void select_edits(const int8_t *best_row, const std::vector<uint8_t> &tmpl, int ignore_edge, std::vector<Edit> &ed) {
     const int L = (int)tmpl.size();
     ed.clear();
     int j = ignore_edge;
     while (j <= L - ignore_edge) {
-        int best = -1;
-        double bg = kMinGain;
-        const int own = j < L ? code(tmpl[(size_t)j]) : -1;
-        for (int row = 0; row < NUM_ROW; row++) {
-            if (row == own) continue;
-            if (row < 4 && j >= L - ignore_edge) continue;
-            if (row >= 8 && row < 8 + COPY && j + (row - 7) > L - ignore_edge) continue;
-            if (row >= 8 + COPY && j + (row - 7 - COPY) > L - ignore_edge) continue;
-            const double g = sum[(size_t)j * NUM_ROW + row];
-            if (g > bg) { bg = g; best = row; }
-        }
+        const int best = best_row[j];
         if (best >= 0) {
             ed.push_back({ j, best });
             const int consumed = best >= 8 + COPY ? best - 7 - COPY : (best < 4 ? 1 : 0);
@@ -117,7 +105,7 @@ extern "C" int jtk_polish_until_converge_batch(jtk_ctx *ctx, const jtk_hmm_param
     std::vector<uint8_t> t_cat, r_cat, o_cat, s_vec, patched;
     std::vector<uint32_t> t_off, r_off, o_off, t_idx, chunk_of;
     std::vector<uint64_t> stat_off;
-    std::vector<double> sums;
+    std::vector<int8_t> best_rows;
     std::vector<Edit> ed;
     for (int round = 0; round < kMaxIter; round++) {
         // batch of the voting reads of every chunk that is still changing
@@ -131,7 +119,7 @@ extern "C" int jtk_polish_until_converge_batch(jtk_ctx *ctx, const jtk_hmm_param
             t_cat.insert(t_cat.end(), tmpl[(size_t)c].begin(), tmpl[(size_t)c].end());
             t_off.push_back((uint32_t)t_cat.size());
             stat_off.push_back(so);
-            so += (uint64_t)(tmpl[(size_t)c].size() + 1) * NUM_ROW;
+            so += (uint64_t)tmpl[(size_t)c].size() + 1;
             const size_t take = std::min<size_t>((size_t)std::max(cfg->take_num, 0), members[(size_t)c].size());
             for (size_t m = 0; m < take; m++) {
                 const uint32_t p = members[(size_t)c][m];
@@ -148,16 +136,16 @@ extern "C" int jtk_polish_until_converge_batch(jtk_ctx *ctx, const jtk_hmm_param
         int rc = jtk_batch_create(ctx, (int)t_idx.size(), (int)chunk_of.size(), t_cat.data(), t_off.data(), r_cat.data(),
                                   r_off.data(), o_cat.data(), o_off.data(), s_vec.data(), t_idx.data(), cfg->radius, &b);
         if (rc) return rc;
-        sums.assign((size_t)so, 0.0);
+        best_rows.assign((size_t)so, (int8_t)-1);
         if (!t_idx.empty()) {
             rc = jtk_batch_modtable(b, fwd, rev, 14);
-            if (!rc) rc = jtk_batch_colsums(b, cfg->take_num, sums.data(), stat_off.data());
+            if (!rc) rc = jtk_batch_best_edits(b, cfg->take_num, cfg->ignore_edge, kMinGain, best_rows.data(), stat_off.data());
         }
         jtk_batch_destroy(b);
         if (rc) return rc;
         for (size_t bt = 0; bt < chunk_of.size(); bt++) {
             const int c = (int)chunk_of[bt];
-            select_edits(sums.data() + stat_off[bt], tmpl[(size_t)c], cfg->ignore_edge, ed);
+            select_edits(best_rows.data() + stat_off[bt], tmpl[(size_t)c], cfg->ignore_edge, ed);
             if (ed.empty()) { active[(size_t)c] = 0; continue; }
             iters[(size_t)c]++;
             for (uint32_t p : members[(size_t)c]) {

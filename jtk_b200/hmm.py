@@ -155,12 +155,17 @@ def polish_chunks(models: PairHiddenMarkovModelOnStrands, drafts: Sequence, read
     caps = (rlen + 2 * dlen[tmpl_idx] + 64).astype(np.uint32)
     pos = np.zeros(n_pairs + 1, dtype=np.uint64)
     np.cumsum(caps, out=pos[1:])
-    buf = np.zeros(int(pos[-1]), dtype=np.uint8)
-    n_ops = np.zeros(n_pairs, dtype=np.uint32)
-    for k, o in enumerate(ops):
-        o = _lib._u8(o)
-        buf[int(pos[k]):int(pos[k]) + len(o)] = o
-        n_ops[k] = len(o)
+    # every read's ops at pos[k] with room to grow (caps[k]): one concatenate of (ops, zero padding) pieces instead of a
+    # Python-level copy per read (120 000 reads per call at 2 000 chunks)
+    ops8 = [_lib._u8(o) for o in ops]
+    n_ops = np.fromiter((len(o) for o in ops8), dtype=np.uint32, count=n_pairs)
+    if (n_ops > caps).any():
+        raise ValueError("ops longer than read + 2 * draft + 64")
+    zeros = np.zeros(int((caps - n_ops).max()) if n_pairs else 0, dtype=np.uint8)
+    pieces = [None] * (2 * n_pairs)
+    pieces[0::2] = ops8
+    pieces[1::2] = [zeros[:int(c)] for c in (caps - n_ops)]
+    buf = np.concatenate(pieces) if n_pairs else np.zeros(0, dtype=np.uint8)
     ccap = (2 * dlen + 64).astype(np.uint32)
     cpos = np.zeros(n_chunks + 1, dtype=np.uint64)
     np.cumsum(ccap, out=cpos[1:])
