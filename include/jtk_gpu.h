@@ -291,6 +291,11 @@ void jtk_lc_rng_words(uint64_t seed, int use_state, const uint64_t *state, int n
 /* sort key of pileup_nodes (haplotyper/src/local_clustering/mod.rs:47-50): alignment columns of Node::recover that are not
  * '|' = indel columns + diagonal columns whose bases differ; <0 if the ops do not span (read, template) */
 int jtk_lc_nonmatch_columns(const uint8_t *ops, int n_ops, const uint8_t *read, int Lr, const uint8_t *tmpl, int Lt);
+/* the same for n nodes in one call (concatenated ops / reads / templates with n+1 offsets each, node k on template
+ * tmpl_idx[k]); out[k] = the key or -1 */
+int jtk_lc_nonmatch_columns_batch(int n, const uint8_t *ops_concat, const uint64_t *ops_off, const uint8_t *read_concat,
+                                  const uint64_t *read_off, const uint8_t *tmpl_concat, const uint64_t *tmpl_off,
+                                  const uint32_t *tmpl_idx, int32_t *out);
 
 /* The k-means + MCMC restarts of pseudo_mcmc::mcmc_clustering (haplotyper/src/local_clustering/pseudo_mcmc.rs:649-670:
  * `restarts` = 20 x (misc::kmeans + mcmc_with_filter) on one generator, keeping the last maximum) for n_chains independent

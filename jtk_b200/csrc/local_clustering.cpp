@@ -1131,6 +1131,19 @@ int jtk_lc_nonmatch_columns(const uint8_t *ops, int n_ops, const uint8_t *read, 
     return bad;
 }
 
+int jtk_lc_nonmatch_columns_batch(int n, const uint8_t *ops_concat, const uint64_t *ops_off, const uint8_t *read_concat,
+                                  const uint64_t *read_off, const uint8_t *tmpl_concat, const uint64_t *tmpl_off,
+                                  const uint32_t *tmpl_idx, int32_t *out) {
+    if (n < 0 || (n > 0 && (!ops_concat || !ops_off || !read_concat || !read_off || !tmpl_concat || !tmpl_off || !tmpl_idx || !out))) return JTK_EINVAL;
+    for (int k = 0; k < n; k++) {
+        const uint32_t t = tmpl_idx[k];
+        out[k] = jtk_lc_nonmatch_columns(ops_concat + ops_off[k], (int)(ops_off[k + 1] - ops_off[k]), read_concat + read_off[k],
+                                         (int)(read_off[k + 1] - read_off[k]), tmpl_concat + tmpl_off[t],
+                                         (int)(tmpl_off[t + 1] - tmpl_off[t]));
+    }
+    return JTK_OK;
+}
+
 int jtk_lc_homopolymer_length(const uint8_t *xs, int n, uint32_t *out) {
     const std::vector<size_t> h = homopolymer_length(xs, (size_t)n);
     for (int i = 0; i < n; i++) out[i] = (uint32_t)h[(size_t)i];

@@ -6,6 +6,9 @@
 #include "../../include/jtk_gpu.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -107,9 +110,24 @@ extern "C" int jtk_polish_until_converge_batch(jtk_ctx *ctx, const jtk_hmm_param
     std::vector<uint64_t> stat_off;
     std::vector<int8_t> best_rows;
     std::vector<Edit> ed;
+    const bool timing = std::getenv("JTK_TIMING") != nullptr; // wall-clock phases of the loop on stderr
+    double t_pack = 0, t_create = 0, t_table = 0, t_pick = 0, t_patch = 0;
+    auto now = []() { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    int rounds_run = 0;
     for (int round = 0; round < kMaxIter; round++) {
+        const auto p0 = now();
         // batch of the voting reads of every chunk that is still changing
         t_cat.clear(); r_cat.clear(); o_cat.clear(); s_vec.clear();
+        if (round == 0) { // the first round carries every chunk: size the staging vectors once (growth by doubling copied ~3x the bytes)
+            size_t tb = 0, ob = 0;
+            for (int c = 0; c < n_chunks; c++) tb += tmpl[(size_t)c].size();
+            for (int p = 0; p < n_pairs; p++) ob += n_ops[p];
+            t_cat.reserve(tb + 64 * (size_t)n_chunks); r_cat.reserve(read_off[n_pairs]); o_cat.reserve(ob + 64 * (size_t)n_pairs);
+            s_vec.reserve((size_t)n_pairs); t_idx.reserve((size_t)n_pairs); r_off.reserve((size_t)n_pairs + 1); o_off.reserve((size_t)n_pairs + 1);
+        }
         t_off.assign(1, 0); r_off.assign(1, 0); o_off.assign(1, 0); t_idx.clear(); chunk_of.clear(); stat_off.clear();
         uint64_t so = 0;
         for (int c = 0; c < n_chunks; c++) {
@@ -132,10 +150,15 @@ extern "C" int jtk_polish_until_converge_batch(jtk_ctx *ctx, const jtk_hmm_param
             }
         }
         if (chunk_of.empty()) break;
+        rounds_run++;
+        const auto p1 = now();
+        t_pack += ms(p0, p1);
         jtk_batch *b = nullptr;
         int rc = jtk_batch_create(ctx, (int)t_idx.size(), (int)chunk_of.size(), t_cat.data(), t_off.data(), r_cat.data(),
                                   r_off.data(), o_cat.data(), o_off.data(), s_vec.data(), t_idx.data(), cfg->radius, &b);
         if (rc) return rc;
+        const auto p2 = now();
+        t_create += ms(p1, p2);
         best_rows.assign((size_t)so, (int8_t)-1);
         if (!t_idx.empty()) {
             rc = jtk_batch_modtable(b, fwd, rev, 14);
@@ -143,6 +166,8 @@ extern "C" int jtk_polish_until_converge_batch(jtk_ctx *ctx, const jtk_hmm_param
         }
         jtk_batch_destroy(b);
         if (rc) return rc;
+        const auto p3 = now();
+        t_table += ms(p2, p3);
         for (size_t bt = 0; bt < chunk_of.size(); bt++) {
             const int c = (int)chunk_of[bt];
             select_edits(best_rows.data() + stat_off[bt], tmpl[(size_t)c], cfg->ignore_edge, ed);
@@ -156,7 +181,12 @@ extern "C" int jtk_polish_until_converge_batch(jtk_ctx *ctx, const jtk_hmm_param
             }
             apply_edits(tmpl[(size_t)c], ed);
         }
+        t_patch += ms(p3, now());
     }
+    (void)t_pick;
+    if (timing)
+        std::fprintf(stderr, "[jtk timing] polish: %d rounds, pack=%.1fms create=%.1fms tables+pick=%.1fms patch=%.1fms\n", rounds_run,
+                     t_pack, t_create, t_table, t_patch);
     for (int c = 0; c < n_chunks; c++) {
         if (tmpl[(size_t)c].size() > cons_cap[c]) return JTK_EINVAL;
         std::memcpy(out_cons + cons_pos[c], tmpl[(size_t)c].data(), tmpl[(size_t)c].size());

@@ -95,13 +95,39 @@ def nonmatch_columns(node: Node, chunk: Chunk) -> int:
 
 
 def pileup_nodes(ds: DataSet, selection: Set[int]) -> Dict[int, Tuple[List[Node], Chunk]]:
-    """mod.rs:33-53: nodes per selected chunk, cleanest alignments first (stable sort, as sort_by_cached_key)."""
+    """mod.rs:33-53: nodes per selected chunk, cleanest alignments first (stable sort, as sort_by_cached_key).  The sort
+    keys of all nodes come from ONE call (jtk_lc_nonmatch_columns_batch)."""
     pile: Dict[int, Tuple[List[Node], Chunk]] = {c.id: ([], c) for c in ds.selected_chunks if c.id in selection}
     for n in ds.nodes:
         if n.chunk in pile:
             pile[n.chunk][0].append(n)
-    for nodes, chunk in pile.values():
-        nodes.sort(key=lambda n: nonmatch_columns(n, chunk))
+    cids = [cid for cid, (nodes, _) in pile.items() if nodes]
+    if not cids:
+        return pile
+    flat = [n for cid in cids for n in pile[cid][0]]
+    tidx = np.repeat(np.arange(len(cids), dtype=np.uint32), [len(pile[cid][0]) for cid in cids])
+
+    def cat64(seqs):
+        c, off = _lib.concat(seqs)
+        return c, off.astype(np.uint64)
+    ocat, ooff = cat64([n.ops for n in flat])
+    rcat, roff = cat64([n.seq for n in flat])
+    tcat, toff = cat64([pile[cid][1].seq for cid in cids])
+    keys = np.zeros(len(flat), dtype=np.int32)
+    L = _bind()
+    vp = C.c_void_p
+    L.jtk_lc_nonmatch_columns_batch.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+    p = _lib._ptr
+    rc = L.jtk_lc_nonmatch_columns_batch(len(flat), p(ocat), p(ooff), p(rcat), p(roff), p(tcat), p(toff), p(tidx), p(keys))
+    if rc != 0 or (keys < 0).any():
+        raise ValueError("node ops do not span (read, chunk)")
+    pos = 0
+    for cid in cids:
+        nodes = pile[cid][0]
+        k = keys[pos:pos + len(nodes)]
+        pos += len(nodes)
+        order = np.argsort(k, kind="stable")
+        nodes[:] = [nodes[i] for i in order]
     return pile
 
 
