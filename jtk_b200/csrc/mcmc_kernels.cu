@@ -44,9 +44,15 @@ struct DevRng { // rand_xoshiro::Xoshiro256StarStar + the rand 0.8.5 samplers us
     __device__ __forceinline__ uint32_t next_u32() { return (uint32_t)(next_u64() >> 32); }
     __device__ __forceinline__ uint64_t gen_range(uint64_t range) { // UniformInt<usize>::sample_single_inclusive(0, n-1)
         const uint64_t zone = (range << __clzll((long long)range)) - 1;
+        const uint32_t r32 = (uint32_t)range; // every range here (reads, clusters) fits 32 bits: two 32 x 32 -> 64 products
         for (;;) {
             const uint64_t v = next_u64();
-            const uint64_t lo = v * range, hi = __umul64hi(v, range);
+            uint64_t lo, hi;
+            if (range <= 0xffffffffULL) {
+                const uint64_t t = (uint64_t)(uint32_t)v * r32;
+                const uint64_t u = (uint64_t)(uint32_t)(v >> 32) * r32 + (t >> 32);
+                lo = (u << 32) | (uint32_t)t; hi = u >> 32;
+            } else { lo = v * range; hi = __umul64hi(v, range); }
             if (lo <= zone) return hi;
         }
     }
