@@ -99,3 +99,27 @@ def test_copy_num_one_is_trivial(chunk_profiles):
     cfg = LC.ClusteringConfig.new(18, 1, 20.0, 40.0, GAINS)
     r = LC.clustering_on_profiles(prof, d["template"], d["strands"], cfg, seed=3)
     assert r.k == 1 and r.score == 0.0 and (r.assignments == 0).all()
+
+
+def test_host_restarts_twin_is_deterministic_and_splits_two_haplotypes():
+    """jtk_lc_mcmc_restarts_host (the host twin the GPU restarts are compared with, tests/test_gpu_clustering.py): same
+    generator state in -> same assignment, likelihood and state out; a clean two-haplotype matrix is split exactly."""
+    import ctypes as C
+    from jtk_b200 import _lib, pipeline as P
+    L = _lib.lib()
+    rng = np.random.default_rng(5)
+    hap = rng.integers(0, 2, 40)
+    v = np.ascontiguousarray(np.where(hap[:, None] == 1, 7.0, -7.0) + rng.normal(0, 1, (40, 4)))
+    L.jtk_lc_mcmc_restarts_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
+                                            C.POINTER(C.c_double)]
+    outs = []
+    for _ in range(2):
+        st = P._rng_seed(99)
+        asn = np.zeros(40, dtype=np.uint8)
+        lk = C.c_double()
+        assert L.jtk_lc_mcmc_restarts_host(_lib._ptr(v), 40, 4, 2, 20.0, 2, _lib._ptr(st), _lib._ptr(asn), C.byref(lk)) == 0
+        outs.append((asn.copy(), lk.value, st.copy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1] and np.array_equal(outs[0][2], outs[1][2])
+    assert not np.array_equal(outs[0][2], P._rng_seed(99))
+    a = outs[0][0]
+    assert (a == hap).all() or (a == 1 - hap).all()
