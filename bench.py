@@ -65,7 +65,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index: int, period_s: float = 0.05):
+    def __init__(self, index: int, period_s: float = 0.01):
         self.index = index
         self.period = period_s
         self.lines = []
@@ -332,8 +332,8 @@ def main():
     batch.sync()
     ctx.kernel_times()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    if rank == 0 and sampler.mode == "smi":
+        sampler.start()          # the nvidia-smi child needs a head start
         time.sleep(0.3)
     barrier()
     l0 = ctx.launch_count
@@ -341,12 +341,16 @@ def main():
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_resident()
+    # the steps are queued, the GPU is working through them: sample its clocks now, i.e. DURING the timed region
+    if rank == 0 and sampler.mode != "smi":
+        sampler.start()
+        time.sleep(min(0.25, 0.5 * args.steps * 6e-3))
     dev_ms = ctx.timer_stop()
+    clocks = sampler.stop() if rank == 0 else None
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     launches = ctx.launch_count - l0
     ktimes = ctx.kernel_times()
-    clocks = sampler.stop() if rank == 0 else None
 
     # 9-row (clustering rows only) variant, reported as an extra
     for _ in range(2):

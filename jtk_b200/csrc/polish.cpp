@@ -6,6 +6,8 @@
 #include "../../include/jtk_gpu.h"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -105,11 +107,10 @@ extern "C" int jtk_polish_until_converge_batch(jtk_ctx *ctx, const jtk_hmm_param
     }
     std::vector<int> iters((size_t)n_chunks, 0);
     std::vector<uint8_t> active((size_t)n_chunks, 1);
-    std::vector<uint8_t> t_cat, r_cat, o_cat, s_vec, patched;
+    std::vector<uint8_t> t_cat, r_cat, o_cat, s_vec;
     std::vector<uint32_t> t_off, r_off, o_off, t_idx, chunk_of;
     std::vector<uint64_t> stat_off;
     std::vector<int8_t> best_rows;
-    std::vector<Edit> ed;
     const bool timing = std::getenv("JTK_TIMING") != nullptr; // wall-clock phases of the loop on stderr
     double t_pack = 0, t_create = 0, t_table = 0, t_pick = 0, t_patch = 0;
     auto now = []() { return std::chrono::steady_clock::now(); };
@@ -168,18 +169,36 @@ extern "C" int jtk_polish_until_converge_batch(jtk_ctx *ctx, const jtk_hmm_param
         if (rc) return rc;
         const auto p3 = now();
         t_table += ms(p2, p3);
-        for (size_t bt = 0; bt < chunk_of.size(); bt++) {
-            const int c = (int)chunk_of[bt];
-            select_edits(best_rows.data() + stat_off[bt], tmpl[(size_t)c], cfg->ignore_edge, ed);
-            if (ed.empty()) { active[(size_t)c] = 0; continue; }
-            iters[(size_t)c]++;
-            for (uint32_t p : members[(size_t)c]) {
-                update_ops(ops_buf + ops_pos[p], (int)n_ops[p], ed, patched);
-                if (patched.size() > ops_cap[p]) return JTK_EINVAL;
-                std::memcpy(ops_buf + ops_pos[p], patched.data(), patched.size());
-                n_ops[p] = (uint32_t)patched.size();
-            }
-            apply_edits(tmpl[(size_t)c], ed);
+        // chunks are independent (their reads' ops live in disjoint buffers): patch them on a few threads
+        {
+            std::atomic<size_t> next(0);
+            std::atomic<int> failed(0);
+            auto worker = [&]() {
+                std::vector<Edit> my_ed;
+                std::vector<uint8_t> my_patched;
+                for (;;) {
+                    const size_t bt = next.fetch_add(1);
+                    if (bt >= chunk_of.size()) break;
+                    const int c = (int)chunk_of[bt];
+                    select_edits(best_rows.data() + stat_off[bt], tmpl[(size_t)c], cfg->ignore_edge, my_ed);
+                    if (my_ed.empty()) { active[(size_t)c] = 0; continue; }
+                    iters[(size_t)c]++;
+                    for (uint32_t p : members[(size_t)c]) {
+                        update_ops(ops_buf + ops_pos[p], (int)n_ops[p], my_ed, my_patched);
+                        if (my_patched.size() > ops_cap[p]) { failed.store(1); return; }
+                        std::memcpy(ops_buf + ops_pos[p], my_patched.data(), my_patched.size());
+                        n_ops[p] = (uint32_t)my_patched.size();
+                    }
+                    apply_edits(tmpl[(size_t)c], my_ed);
+                }
+            };
+            const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+            const size_t nt = std::min<size_t>(hw, (chunk_of.size() + 15) / 16);
+            std::vector<std::thread> th;
+            for (size_t t = 1; t < nt; t++) th.emplace_back(worker);
+            worker();
+            for (auto &t : th) t.join();
+            if (failed.load()) return JTK_EINVAL;
         }
         t_patch += ms(p3, now());
     }
