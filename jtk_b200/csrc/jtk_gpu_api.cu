@@ -627,30 +627,27 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
         };
         uint64_t c = width(0, 0);
         bool bad = false;
-        uint32_t acc = 0;     // bits of word wi collected so far
+        // guide bits collect in a 64-bit window [base, base + 64) that is flushed a word at a time; away from the matrix
+        // edges (the usual case) every diagonal holds the full window and an op costs a handful of branch-free operations
+        uint64_t acc = 0;
+        int base = 0;
         size_t wi = 0;
-        auto put = [&](int pos) { // set bit `pos` (positions arrive in increasing order)
-            const size_t w = (size_t)pos >> 5;
-            if (w != wi) { bw[wi] = acc; for (size_t k = wi + 1; k < w; k++) bw[k] = 0; wi = w; acc = 0; }
-            acc |= 1u << (pos & 31);
-        };
+        const int i_lo = radius + 1, i_hi = Lr - radius - 2, j_lo = radius + 1, j_hi = Lt - radius - 2;
         for (int k = 0; k < n_ops; k++) {
             const uint8_t op = ops[k];
-            if (op <= JTK_OP_MISMATCH) {
-                if (i >= Lr || j >= Lt) { bad = true; break; }
-                c += width(i, s + 1);
-                i++; j++; put(s + 1); s += 2;
-                c += width(i, s);
-            } else if (op == JTK_OP_INS) {
-                if (i >= Lr) { bad = true; break; }
-                i++; put(s); s += 1; c += width(i, s);
-            } else if (op == JTK_OP_DEL) {
-                if (j >= Lt) { bad = true; break; }
-                j++; s += 1; c += width(i, s);
-            } else { fail(JTK_EINVAL, "invalid op code in pair " + std::to_string(p)); return; }
+            if (op > JTK_OP_DEL) { fail(JTK_EINVAL, "invalid op code in pair " + std::to_string(p)); return; }
+            const int diag = op <= JTK_OP_MISMATCH, ni = op != JTK_OP_DEL, nj = op != JTK_OP_INS;
+            if (i + ni > Lr || j + nj > Lt) { bad = true; break; }
+            if ((i >= i_lo) & (i <= i_hi) & (j >= j_lo) & (j <= j_hi)) c += full * (uint64_t)(1 + diag);
+            else if (diag) c += width(i, s + 1) + width(i + 1, s + 2);
+            else c += width(i + ni, s + 1);
+            acc |= (uint64_t)ni << (s + diag - base); // Match: bit s+1, Ins: bit s, Del: none
+            i += ni; j += nj; s += 1 + diag;
+            if (s - base >= 32) { bw[wi++] = (uint32_t)acc; acc >>= 32; base += 32; }
         }
-        bw[wi] = acc;
-        for (size_t k = wi + 1; k < nwords; k++) bw[k] = 0;
+        if (wi < nwords) bw[wi++] = (uint32_t)acc;
+        if (wi < nwords) bw[wi++] = (uint32_t)(acc >> 32);
+        for (size_t k = wi; k < nwords; k++) bw[k] = 0;
         if (bad || i != Lr || j != Lt) {
             fail(JTK_EINVAL, "ops of pair " + std::to_string(p) + " do not span (template, read): consumed (" + std::to_string(j) +
                                  "," + std::to_string(i) + ") of (" + std::to_string(Lt) + "," + std::to_string(Lr) + ")");
