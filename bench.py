@@ -306,6 +306,9 @@ def main():
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world > 1:
+        # every rank runs two encoder contexts (e2e leg): share the box's cores instead of 2 x world x all-cores threads
+        os.environ.setdefault("JTK_HOST_THREADS", str(max(2, (os.cpu_count() or 2) // (2 * world))))
     ctx = _lib.Context(local_rank)
     fwd = _lib.HmmParams.from_buffer_copy(_default_params())
     rev = fwd
