@@ -304,6 +304,11 @@ struct jtk_ctx {
     PinBuf<float> h_delta;
     PinBuf<double> h_lk;
     PinBuf<uint8_t> h_homop;
+    PinBuf<uint8_t> h_raw;                 // raw reads | raw ops of the batch being created (device encoder)
+    DevBuf<uint8_t> d_rawin;
+    DevBuf<uint32_t> d_raw_off;            // read_off | ops_off
+    DevBuf<int32_t> d_enc_status;          // EncStatus per pair | the cell count (8 bytes)
+    std::vector<int32_t> enc_status_host;
     PinBuf<jtk_candidate> h_cand;
     PinBuf<double> h_gather;
     // host scratch
@@ -369,6 +374,7 @@ void jtk_ctx_destroy(jtk_ctx *ctx) {
     cudaSetDevice(ctx->device);
     ctx->d_models.release(); ctx->d_frows.release(); ctx->d_kf.release(); ctx->d_fwdinfo.release(); ctx->d_raw.release(); ctx->d_counter.release();
     ctx->d_minreq.release(); ctx->d_cols.release(); ctx->d_gather.release();
+    ctx->h_raw.release(); ctx->d_rawin.release(); ctx->d_raw_off.release(); ctx->d_enc_status.release();
     ctx->d_mc_chains.release(); ctx->d_mc_f64.release(); ctx->d_mc_lk.release(); ctx->d_mc_u32.release(); ctx->d_mc_u8.release();
     ctx->d_mc_asn.release(); ctx->d_mc_rng.release(); ctx->d_mc_asn_off.release(); ctx->d_mc_err.release();
     ctx->d_tabs.release(); ctx->d_tab_off.release(); ctx->d_cand.release(); ctx->h_cand.release(); ctx->h_gather.release();
@@ -486,13 +492,115 @@ template <typename F> void parallel_for(int n_threads, int n, int grain, F fn) {
     for (auto &t : th) t.join();
 }
 
+// ---- the pair encoder on the device ------------------------------------------------------------------------------
+// What pack_batch's per-pair loop does on the host threads (read codes, guide bits, in-band cell count, validation of the
+// ops), one warp per pair, from the caller's raw reads and ops: the host then only lays the arrays out.  Same bytes, same
+// count, same first error as the host encoder.  It costs ~1.5 ms of GPU time per 4 800 pairs, so it is used only where the
+// host is the short resource (a context with fewer than 8 encoder threads, e.g. 8 ranks on one box: bench.py --gpus 8), or
+// under JTK_DEVICE_ENCODE=1; JTK_DEVICE_ENCODE=0 forces the host encoder, which the bootstrap path always uses.
+struct EncStatus { int32_t bad, i, j, pad_; }; // bad: 0 ok, 1 the ops do not span (template, read), 2 invalid op code
+
+__device__ __forceinline__ unsigned enc_base_code(unsigned c) { // A/a 0, C/c 1, G/g 2, T/t 3, anything else 0
+    c &= 0xdfu; // upper case
+    return c == 'C' ? 1u : (c == 'G' ? 2u : (c == 'T' ? 3u : 0u));
+}
+
+__global__ void __launch_bounds__(128) encode_pairs_kernel(const DevPair *__restrict__ pairs, int n_pairs,
+                                                           const uint8_t *__restrict__ raw_reads, const uint32_t *__restrict__ read_off,
+                                                           const uint8_t *__restrict__ raw_ops, const uint32_t *__restrict__ ops_off,
+                                                           uint8_t *__restrict__ codes, uint32_t *__restrict__ bits, int radius,
+                                                           int words_per_warp, EncStatus *__restrict__ status,
+                                                           unsigned long long *__restrict__ cells) {
+    extern __shared__ uint32_t enc_sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (p >= n_pairs) return;
+    const DevPair dp = pairs[p];
+    const int Lt = dp.Lt, Lr = dp.Lr;
+    uint32_t *w = enc_sm + (size_t)warp * words_per_warp;
+    const int nwords = (Lt + Lr + 1 + 31) / 32 + 1;
+    for (int k = lane; k < nwords; k += 32) w[k] = 0u;
+    // read rows: byte = ctx<<5 | qc<<2, 16 = no base; pads on both sides (four bytes per lane and store)
+    {
+        const uint8_t *q = raw_reads + read_off[p];
+        const int rlen = (Lr + 2 + 3) & ~3;
+        uint32_t *out = reinterpret_cast<uint32_t *>(codes + dp.rb_off - kCodePad);
+        const int n4 = (2 * kCodePad + rlen) >> 2;
+        for (int t = lane; t < n4; t += 32) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int idx = 4 * t + b - kCodePad;
+                unsigned byte = 16u;
+                if (idx >= 1 && idx <= Lr) {
+                    const unsigned qc = enc_base_code(q[idx - 1]);
+                    const unsigned cx = idx >= 2 ? enc_base_code(q[idx - 2]) : 4u;
+                    byte = (cx << 5) | (qc << 2);
+                }
+                v |= byte << (8 * b);
+            }
+            out[t] = v;
+        }
+    }
+    __syncwarp();
+    const uint8_t *ops = raw_ops + ops_off[p];
+    const int n_ops = (int)(ops_off[p + 1] - ops_off[p]);
+    const unsigned long long full = (unsigned long long)(2 * radius + 1);
+    auto width = [&](int cen, int d) -> unsigned long long {
+        const int lo = max(max(cen - radius, 0), d - Lt), hi = min(min(cen + radius, Lr), d);
+        return hi >= lo ? (unsigned long long)(hi - lo + 1) : 0ull;
+    };
+    unsigned long long c = lane == 0 ? width(0, 0) : 0ull;
+    int i = 0, j = 0, s = 0; // warp-uniform running coordinates
+    int bad = 0, bi = 0, bj = 0;
+    for (int base = 0; base < n_ops && !bad; base += 32) {
+        const int k = base + lane;
+        const bool act = k < n_ops;
+        const unsigned op = act ? ops[k] : 0u;
+        const bool invalid = act && op > JTK_OP_DEL;
+        const int diag = (act && !invalid && op <= JTK_OP_MISMATCH) ? 1 : 0;
+        const int ni = (act && !invalid && op != JTK_OP_DEL) ? 1 : 0, nj = (act && !invalid && op != JTK_OP_INS) ? 1 : 0;
+        const int adv = (act && !invalid) ? 1 + diag : 0;
+        int sa = adv, si = ni, sj = nj; // inclusive warp scans
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int ta = __shfl_up_sync(0xffffffffu, sa, o), ti = __shfl_up_sync(0xffffffffu, si, o), tj = __shfl_up_sync(0xffffffffu, sj, o);
+            if (lane >= o) { sa += ta; si += ti; sj += tj; }
+        }
+        const int s_b = s + sa - adv, i_b = i + si - ni, j_b = j + sj - nj; // coordinates before this op
+        const bool span = act && !invalid && (i_b + ni > Lr || j_b + nj > Lt);
+        const unsigned fm = __ballot_sync(0xffffffffu, invalid || span);
+        if (fm) { // the host encoder stops at the first offending op and reports what was consumed up to it
+            const int first = __ffs((int)fm) - 1;
+            bad = __shfl_sync(0xffffffffu, invalid ? 2 : 1, first);
+            bi = __shfl_sync(0xffffffffu, i_b, first); bj = __shfl_sync(0xffffffffu, j_b, first);
+            break;
+        }
+        if (act) {
+            if (i_b > radius && i_b + 1 + radius < Lr && j_b > radius && j_b + 1 + radius < Lt) c += full * (unsigned long long)(1 + diag);
+            else if (diag) c += width(i_b, s_b + 1) + width(i_b + 1, s_b + 2);
+            else c += width(i_b + ni, s_b + 1);
+            if (ni) { const int pos = s_b + diag; atomicOr(&w[pos >> 5], 1u << (pos & 31)); } // Match: bit s+1, Ins: bit s
+        }
+        s += __shfl_sync(0xffffffffu, sa, 31); i += __shfl_sync(0xffffffffu, si, 31); j += __shfl_sync(0xffffffffu, sj, 31);
+    }
+    if (!bad && (i != Lr || j != Lt)) { bad = 1; bi = i; bj = j; }
+    __syncwarp();
+    if (lane == 0) status[p] = EncStatus{ bad, bi, bj, 0 };
+    if (bad) return;
+    for (int k = lane; k < nwords; k += 32) bits[dp.bits_off + k] = w[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) atomicAdd(cells, 2ull * c);
+}
+
 // Encode templates / reads / guide paths into the device layout of phmm_dev.cuh (pinned staging of ctx).
 // Pass 1 lays out every array (sequential, O(pairs)); pass 2 encodes templates and pairs on the host threads: every
 // template / pair owns its own byte ranges.
 int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uint32_t *tmpl_off,
                const uint8_t *read_concat, const uint32_t *read_off, const uint8_t *ops_concat,
                const uint32_t *ops_off, const uint8_t *strand, const uint32_t *tmpl_idx, size_t &code_bytes,
-               size_t &bit_words, size_t &homop_bytes) {
+               size_t &bit_words, size_t &homop_bytes, bool device_encode, size_t &tmpl_code_bytes) {
     const int n_pairs = b->n_pairs, n_tmpl = b->n_tmpl, radius = b->radius;
     PhaseTimer pt;
     size_t cb = 0, hb = 0;
@@ -510,6 +618,7 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
         b->max_lt = std::max(b->max_lt, (int)L);
     }
     b->homop_off[n_tmpl] = (uint32_t)hb;
+    tmpl_code_bytes = cb; // the template codes come first; the read rows follow
     size_t bwords = 0;
     uint64_t tab = 0;
     std::vector<uint32_t> cnt((size_t)n_tmpl + 1, 0);
@@ -577,7 +686,7 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
     std::mutex bad_mu;
     std::string bad_text;
     int bad_code = 0;
-    ctx->hpool->run(n_pairs, 8, [&](int p) {
+    if (!device_encode) ctx->hpool->run(n_pairs, 8, [&](int p) {
         if (first_bad.load(std::memory_order_relaxed) < p) return;
         const DevPair &dp = b->pairs[p];
         const uint32_t ti = tmpl_idx[p];
@@ -671,7 +780,9 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
     ctx->tmpl_code_off = b->tmpl_code_off;
     b->table_floats = tab;
     b->cell_updates = cells_total.load();
-    b->h2d_bytes = cb + bwords * sizeof(uint32_t) + hb + sizeof(DevPair) * (size_t)n_pairs + sizeof(uint32_t) * (4 * (size_t)n_tmpl + 3 + (size_t)n_pairs);
+    b->h2d_bytes = (device_encode ? tmpl_code_bytes + (size_t)read_off[n_pairs] + (size_t)ops_off[n_pairs] + 8 * ((size_t)n_pairs + 1)
+                                  : cb + bwords * sizeof(uint32_t)) +
+                   hb + sizeof(DevPair) * (size_t)n_pairs + sizeof(uint32_t) * (4 * (size_t)n_tmpl + 3 + (size_t)n_pairs);
     code_bytes = cb; bit_words = bwords; homop_bytes = hb;
     return JTK_OK;
 }
@@ -693,9 +804,13 @@ int batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_conc
     b->ctx = ctx; b->n_pairs = n_pairs; b->n_tmpl = n_tmpl; b->radius = radius; b->C = C;
     b->attach(&ctx->pool);
     if (n_pairs == 0) { *out = b; return JTK_OK; }
-    size_t code_bytes = 0, bit_words = 0, homop_bytes = 0;
+    size_t code_bytes = 0, bit_words = 0, homop_bytes = 0, tmpl_code_bytes = 0;
+    // Guide ops given and few encoder threads in this context (or JTK_DEVICE_ENCODE=1): the pairs are encoded on the device
+    // from the raw reads and ops; otherwise on the host threads (see encode_pairs_kernel)
+    bool device_encode = ops_concat != nullptr && ctx->host_threads < 8;
+    if (const char *env = std::getenv("JTK_DEVICE_ENCODE")) device_encode = ops_concat != nullptr && std::atoi(env) != 0;
     int rc = pack_batch(ctx, b, tmpl_concat, tmpl_off, read_concat, read_off, ops_concat, ops_off, strand, tmpl_idx,
-                        code_bytes, bit_words, homop_bytes);
+                        code_bytes, bit_words, homop_bytes, device_encode, tmpl_code_bytes);
     if (rc) { b->release(); delete b; return rc; }
     PhaseTimer pt;
     cudaStream_t st = ctx->stream;
@@ -713,8 +828,39 @@ int batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_conc
     CB(b->d_tmpl_code_off.reserve(b->tmpl_code_off.size()), "cudaMalloc tmpl_code_off");
     pt.mark("reserve");
     CB(cudaMemcpyAsync(b->d_pairs.p, ctx->h_pairs.p, sizeof(DevPair) * (size_t)n_pairs, cudaMemcpyHostToDevice, st), "H2D pairs");
-    CB(cudaMemcpyAsync(b->d_codes.p, ctx->h_codes.p, code_bytes, cudaMemcpyHostToDevice, st), "H2D codes");
-    CB(cudaMemcpyAsync(b->d_bits.p, ctx->h_bits.p, bit_words * sizeof(uint32_t), cudaMemcpyHostToDevice, st), "H2D bits");
+    if (!device_encode) {
+        CB(cudaMemcpyAsync(b->d_codes.p, ctx->h_codes.p, code_bytes, cudaMemcpyHostToDevice, st), "H2D codes");
+        CB(cudaMemcpyAsync(b->d_bits.p, ctx->h_bits.p, bit_words * sizeof(uint32_t), cudaMemcpyHostToDevice, st), "H2D bits");
+    } else {
+        const size_t rb = read_off[n_pairs], ob = ops_off[n_pairs];
+        const size_t rb_pad = (rb + 255) & ~(size_t)255;
+        CB(ctx->h_raw.reserve(rb_pad + ob + 64), "cudaMallocHost raw reads / ops");
+        CB(ctx->d_rawin.reserve(rb_pad + ob + 64), "cudaMalloc raw reads / ops");
+        CB(ctx->d_raw_off.reserve(2 * ((size_t)n_pairs + 1)), "cudaMalloc raw offsets");
+        CB(ctx->d_enc_status.reserve((size_t)4 * n_pairs + 4), "cudaMalloc encoder status");
+        { // the caller's buffers -> pinned staging, on the host threads (1 MiB pieces)
+            const size_t piece = (size_t)1 << 20, nr = (rb + piece - 1) / piece, no = (ob + piece - 1) / piece;
+            uint8_t *hr = ctx->h_raw.p;
+            ctx->hpool->run((int)(nr + no), 1, [&](int k) {
+                if ((size_t)k < nr) { const size_t o = (size_t)k * piece; std::memcpy(hr + o, read_concat + o, std::min(piece, rb - o)); }
+                else { const size_t o = ((size_t)k - nr) * piece; std::memcpy(hr + rb_pad + o, ops_concat + o, std::min(piece, ob - o)); }
+            });
+        }
+        unsigned long long *d_cells = reinterpret_cast<unsigned long long *>(ctx->d_enc_status.p + (size_t)4 * n_pairs);
+        CB(cudaMemcpyAsync(b->d_codes.p, ctx->h_codes.p, tmpl_code_bytes, cudaMemcpyHostToDevice, st), "H2D template codes");
+        CB(cudaMemcpyAsync(ctx->d_rawin.p, ctx->h_raw.p, rb_pad + ob, cudaMemcpyHostToDevice, st), "H2D raw reads / ops");
+        CB(cudaMemcpyAsync(ctx->d_raw_off.p, read_off, sizeof(uint32_t) * ((size_t)n_pairs + 1), cudaMemcpyHostToDevice, st), "H2D read_off");
+        CB(cudaMemcpyAsync(ctx->d_raw_off.p + n_pairs + 1, ops_off, sizeof(uint32_t) * ((size_t)n_pairs + 1), cudaMemcpyHostToDevice, st), "H2D ops_off");
+        CB(cudaMemsetAsync(d_cells, 0, sizeof(unsigned long long), st), "memset cell count");
+        const int words = ((b->max_nd + 31) / 32 + 2 + 3) & ~3, warps = 4;
+        const size_t dyn = (size_t)warps * words * sizeof(uint32_t);
+        if (dyn > 48 * 1024) CB(cudaFuncSetAttribute(encode_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn), "encoder shared memory");
+        encode_pairs_kernel<<<(n_pairs + warps - 1) / warps, warps * 32, dyn, st>>>(
+            b->d_pairs.p, n_pairs, ctx->d_rawin.p, ctx->d_raw_off.p, ctx->d_rawin.p + rb_pad, ctx->d_raw_off.p + n_pairs + 1, b->d_codes.p,
+            b->d_bits.p, b->radius, words, reinterpret_cast<EncStatus *>(ctx->d_enc_status.p), d_cells);
+        CB(cudaGetLastError(), "encoder launch");
+        ctx->launches++;
+    }
     CB(cudaMemcpyAsync(b->d_homop.p, ctx->h_homop.p, homop_bytes, cudaMemcpyHostToDevice, st), "H2D homop");
     CB(cudaMemcpyAsync(b->d_tp_start.p, b->tp_start.data(), sizeof(uint32_t) * b->tp_start.size(), cudaMemcpyHostToDevice, st), "H2D csr");
     CB(cudaMemcpyAsync(b->d_tp_ids.p, b->tp_ids.data(), sizeof(uint32_t) * b->tp_ids.size(), cudaMemcpyHostToDevice, st), "H2D csr");
@@ -722,9 +868,29 @@ int batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_conc
     CB(cudaMemcpyAsync(b->d_homop_off.p, b->homop_off.data(), sizeof(uint32_t) * b->homop_off.size(), cudaMemcpyHostToDevice, st), "H2D homop_off");
     CB(cudaMemcpyAsync(b->d_tmpl_code_off.p, b->tmpl_code_off.data(), sizeof(uint32_t) * b->tmpl_code_off.size(), cudaMemcpyHostToDevice, st), "H2D tmpl_code_off");
     pt.mark("h2d_issue");
+    if (device_encode) {
+        ctx->enc_status_host.resize((size_t)4 * n_pairs + 4);
+        CB(cudaMemcpyAsync(ctx->enc_status_host.data(), ctx->d_enc_status.p, sizeof(int32_t) * ((size_t)4 * n_pairs + 4), cudaMemcpyDeviceToHost, st), "D2H encoder status");
+    }
     CB(cudaStreamSynchronize(st), "upload");
     pt.mark("h2d_sync");
 #undef CB
+    if (device_encode) {
+        const EncStatus *es = reinterpret_cast<const EncStatus *>(ctx->enc_status_host.data());
+        for (int p = 0; p < n_pairs; p++) {
+            if (es[p].bad == 0) continue;
+            const DevPair &dp = b->pairs[(size_t)p];
+            std::string msg = es[p].bad == 2 ? "invalid op code in pair " + std::to_string(p)
+                                             : "ops of pair " + std::to_string(p) + " do not span (template, read): consumed (" +
+                                                   std::to_string(es[p].j) + "," + std::to_string(es[p].i) + ") of (" + std::to_string(dp.Lt) +
+                                                   "," + std::to_string(dp.Lr) + ")";
+            b->release(); delete b;
+            return ctx->fail(JTK_EINVAL, msg);
+        }
+        unsigned long long cells = 0;
+        std::memcpy(&cells, ctx->enc_status_host.data() + (size_t)4 * n_pairs, sizeof cells);
+        b->cell_updates = cells;
+    }
     *out = b;
     return JTK_OK;
 }

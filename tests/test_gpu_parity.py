@@ -250,3 +250,38 @@ def test_parameter_uploads_follow_their_contents(ctx):
     fb.modtable(ha, ha, 14)                      # same profiles as b holds now, on a context that never saw m1
     assert np.array_equal(fb.colstats(m2), s2)
     fb.close(); fresh.close(); b.close()
+
+
+def test_device_encoder_equals_host_encoder(monkeypatch):
+    """encode_pairs_kernel (used when a context has few encoder threads, or under JTK_DEVICE_ENCODE=1) against the host
+    encoder: same cell count, same likelihoods and tables bit for bit (identical codes and guide bits), same rejection
+    of ops that do not span the pair."""
+    from jtk_b200 import _lib
+    d = synth.diploid_chunk(33, length=700, n_reads=12)
+    rng = np.random.default_rng(2)
+    t2 = synth.random_template(rng, 90)
+    q2, o2 = synth.mutate_read(rng, t2, 0.2)
+    templates = [d["template"], t2]
+    reads, ops = d["reads"] + [q2], d["ops"] + [o2]
+    strands = np.concatenate([d["strands"], [1]]).astype(np.uint8)
+    tidx = np.concatenate([np.zeros(len(d["reads"]), np.uint32), [1]]).astype(np.uint32)
+    h = to_c(random_hmm(3))
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("JTK_DEVICE_ENCODE", mode)
+        c = _lib.Context()
+        b = c.batch(templates, reads, ops, strands, tidx, 30)
+        b.modtable(h, h, 14)
+        out[mode] = (b.cell_updates, b.lk(), b.profile(0), b.profile(len(reads) - 1))
+        b.close()
+        with pytest.raises(_lib.JtkError) as e:
+            c.batch(templates, reads, [o[:-2] for o in ops], strands, tidx, 30)
+        assert e.value.code == -1
+        bad = [o.copy() for o in ops]
+        bad[3][5] = 7
+        with pytest.raises(_lib.JtkError):
+            c.batch(templates, reads, bad, strands, tidx, 30)
+        c.close()
+    assert out["0"][0] == out["1"][0] > 0
+    for k in (1, 2, 3):
+        assert np.array_equal(out["0"][k], out["1"][k])
