@@ -308,7 +308,8 @@ struct jtk_ctx {
     DevBuf<uint8_t> d_rawin;
     DevBuf<uint32_t> d_raw_off;            // read_off | ops_off
     DevBuf<int32_t> d_enc_status;          // EncStatus per pair | the cell count (8 bytes)
-    std::vector<int32_t> enc_status_host;
+    PinBuf<uint32_t> h_raw_off;
+    PinBuf<int32_t> h_enc_status;
     PinBuf<jtk_candidate> h_cand;
     PinBuf<double> h_gather;
     // host scratch
@@ -374,7 +375,7 @@ void jtk_ctx_destroy(jtk_ctx *ctx) {
     cudaSetDevice(ctx->device);
     ctx->d_models.release(); ctx->d_frows.release(); ctx->d_kf.release(); ctx->d_fwdinfo.release(); ctx->d_raw.release(); ctx->d_counter.release();
     ctx->d_minreq.release(); ctx->d_cols.release(); ctx->d_gather.release();
-    ctx->h_raw.release(); ctx->d_rawin.release(); ctx->d_raw_off.release(); ctx->d_enc_status.release();
+    ctx->h_raw.release(); ctx->h_raw_off.release(); ctx->h_enc_status.release(); ctx->d_rawin.release(); ctx->d_raw_off.release(); ctx->d_enc_status.release();
     ctx->d_mc_chains.release(); ctx->d_mc_f64.release(); ctx->d_mc_lk.release(); ctx->d_mc_u32.release(); ctx->d_mc_u8.release();
     ctx->d_mc_asn.release(); ctx->d_mc_rng.release(); ctx->d_mc_asn_off.release(); ctx->d_mc_err.release();
     ctx->d_tabs.release(); ctx->d_tab_off.release(); ctx->d_cand.release(); ctx->h_cand.release(); ctx->h_gather.release();
@@ -495,9 +496,10 @@ template <typename F> void parallel_for(int n_threads, int n, int grain, F fn) {
 // ---- the pair encoder on the device ------------------------------------------------------------------------------
 // What pack_batch's per-pair loop does on the host threads (read codes, guide bits, in-band cell count, validation of the
 // ops), one warp per pair, from the caller's raw reads and ops: the host then only lays the arrays out.  Same bytes, same
-// count, same first error as the host encoder.  It costs ~1.5 ms of GPU time per 4 800 pairs, so it is used only where the
-// host is the short resource (a context with fewer than 8 encoder threads, e.g. 8 ranks on one box: bench.py --gpus 8), or
-// under JTK_DEVICE_ENCODE=1; JTK_DEVICE_ENCODE=0 forces the host encoder, which the bootstrap path always uses.
+// count, same first error as the host encoder.  The kernel takes 0.1 ms per 4 800 pairs, but behind another context's
+// persistent table kernels it waits for milliseconds, so it is used only where the host is the short resource (a context
+// with fewer than 8 encoder threads, e.g. 8 ranks on one box: bench.py --gpus 8), or under JTK_DEVICE_ENCODE=1;
+// JTK_DEVICE_ENCODE=0 forces the host encoder, which the bootstrap path always uses.
 struct EncStatus { int32_t bad, i, j, pad_; }; // bad: 0 ok, 1 the ops do not span (template, read), 2 invalid op code
 
 __device__ __forceinline__ unsigned enc_base_code(unsigned c) { // A/a 0, C/c 1, G/g 2, T/t 3, anything else 0
@@ -849,8 +851,11 @@ int batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_conc
         unsigned long long *d_cells = reinterpret_cast<unsigned long long *>(ctx->d_enc_status.p + (size_t)4 * n_pairs);
         CB(cudaMemcpyAsync(b->d_codes.p, ctx->h_codes.p, tmpl_code_bytes, cudaMemcpyHostToDevice, st), "H2D template codes");
         CB(cudaMemcpyAsync(ctx->d_rawin.p, ctx->h_raw.p, rb_pad + ob, cudaMemcpyHostToDevice, st), "H2D raw reads / ops");
-        CB(cudaMemcpyAsync(ctx->d_raw_off.p, read_off, sizeof(uint32_t) * ((size_t)n_pairs + 1), cudaMemcpyHostToDevice, st), "H2D read_off");
-        CB(cudaMemcpyAsync(ctx->d_raw_off.p + n_pairs + 1, ops_off, sizeof(uint32_t) * ((size_t)n_pairs + 1), cudaMemcpyHostToDevice, st), "H2D ops_off");
+        // offsets through pinned staging too: a copy from pageable memory synchronises the stream before it starts
+        CB(ctx->h_raw_off.reserve(2 * ((size_t)n_pairs + 1)), "cudaMallocHost raw offsets");
+        std::memcpy(ctx->h_raw_off.p, read_off, sizeof(uint32_t) * ((size_t)n_pairs + 1));
+        std::memcpy(ctx->h_raw_off.p + n_pairs + 1, ops_off, sizeof(uint32_t) * ((size_t)n_pairs + 1));
+        CB(cudaMemcpyAsync(ctx->d_raw_off.p, ctx->h_raw_off.p, sizeof(uint32_t) * 2 * ((size_t)n_pairs + 1), cudaMemcpyHostToDevice, st), "H2D raw offsets");
         CB(cudaMemsetAsync(d_cells, 0, sizeof(unsigned long long), st), "memset cell count");
         const int words = ((b->max_nd + 31) / 32 + 2 + 3) & ~3, warps = 4;
         const size_t dyn = (size_t)warps * words * sizeof(uint32_t);
@@ -869,14 +874,14 @@ int batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_conc
     CB(cudaMemcpyAsync(b->d_tmpl_code_off.p, b->tmpl_code_off.data(), sizeof(uint32_t) * b->tmpl_code_off.size(), cudaMemcpyHostToDevice, st), "H2D tmpl_code_off");
     pt.mark("h2d_issue");
     if (device_encode) {
-        ctx->enc_status_host.resize((size_t)4 * n_pairs + 4);
-        CB(cudaMemcpyAsync(ctx->enc_status_host.data(), ctx->d_enc_status.p, sizeof(int32_t) * ((size_t)4 * n_pairs + 4), cudaMemcpyDeviceToHost, st), "D2H encoder status");
+        CB(ctx->h_enc_status.reserve((size_t)4 * n_pairs + 4), "cudaMallocHost encoder status");
+        CB(cudaMemcpyAsync(ctx->h_enc_status.p, ctx->d_enc_status.p, sizeof(int32_t) * ((size_t)4 * n_pairs + 4), cudaMemcpyDeviceToHost, st), "D2H encoder status");
     }
     CB(cudaStreamSynchronize(st), "upload");
     pt.mark("h2d_sync");
 #undef CB
     if (device_encode) {
-        const EncStatus *es = reinterpret_cast<const EncStatus *>(ctx->enc_status_host.data());
+        const EncStatus *es = reinterpret_cast<const EncStatus *>(ctx->h_enc_status.p);
         for (int p = 0; p < n_pairs; p++) {
             if (es[p].bad == 0) continue;
             const DevPair &dp = b->pairs[(size_t)p];
@@ -888,7 +893,7 @@ int batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_conc
             return ctx->fail(JTK_EINVAL, msg);
         }
         unsigned long long cells = 0;
-        std::memcpy(&cells, ctx->enc_status_host.data() + (size_t)4 * n_pairs, sizeof cells);
+        std::memcpy(&cells, ctx->h_enc_status.p + (size_t)4 * n_pairs, sizeof cells);
         b->cell_updates = cells;
     }
     *out = b;
