@@ -498,7 +498,7 @@ template <typename F> void parallel_for(int n_threads, int n, int grain, F fn) {
 // ops), one warp per pair, from the caller's raw reads and ops: the host then only lays the arrays out.  Same bytes, same
 // count, same first error as the host encoder.  The kernel takes 0.1 ms per 4 800 pairs, but behind another context's
 // persistent table kernels it waits for milliseconds, so it is used only where the host is the short resource (a context
-// with fewer than 8 encoder threads, e.g. 8 ranks on one box: bench.py --gpus 8), or under JTK_DEVICE_ENCODE=1;
+// with fewer than 6 encoder threads, e.g. 4 or 8 ranks on a 32-core box: bench.py --gpus 4 / 8), or under JTK_DEVICE_ENCODE=1;
 // JTK_DEVICE_ENCODE=0 forces the host encoder, which the bootstrap path always uses.
 struct EncStatus { int32_t bad, i, j, pad_; }; // bad: 0 ok, 1 the ops do not span (template, read), 2 invalid op code
 
@@ -809,7 +809,7 @@ int batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_conc
     size_t code_bytes = 0, bit_words = 0, homop_bytes = 0, tmpl_code_bytes = 0;
     // Guide ops given and few encoder threads in this context (or JTK_DEVICE_ENCODE=1): the pairs are encoded on the device
     // from the raw reads and ops; otherwise on the host threads (see encode_pairs_kernel)
-    bool device_encode = ops_concat != nullptr && ctx->host_threads < 8;
+    bool device_encode = ops_concat != nullptr && ctx->host_threads < 6;
     if (const char *env = std::getenv("JTK_DEVICE_ENCODE")) device_encode = ops_concat != nullptr && std::atoi(env) != 0;
     int rc = pack_batch(ctx, b, tmpl_concat, tmpl_off, read_concat, read_off, ops_concat, ops_off, strand, tmpl_idx,
                         code_bytes, bit_words, homop_bytes, device_encode, tmpl_code_bytes);
