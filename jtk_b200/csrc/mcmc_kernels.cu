@@ -25,9 +25,6 @@
 
 namespace jtk {
 
-#ifndef JTK_MCMC_MAX_K
-#define JTK_MCMC_MAX_K 8
-#endif
 constexpr double kPosThr = 0.00001; // pseudo_mcmc.rs:5
 
 struct DevRng { // rand_xoshiro::Xoshiro256StarStar + the rand 0.8.5 samplers used by the reference
@@ -92,7 +89,6 @@ struct DevRng { // rand_xoshiro::Xoshiro256StarStar + the rand 0.8.5 samplers us
 // error codes left in out_err (0 = ok); the host turns them into the reference's panics
 enum { kMcmcOk = 0, kMcmcKmeansDiverged = 1, kMcmcBadProb = 2, kMcmcLkMismatch = 3, kMcmcBadWeights = 4, kMcmcNoOther = 5 };
 
-constexpr int kMaxK = JTK_MCMC_MAX_K;   // clusters per chain (column statistics live in registers, indexed by unrolled selects)
 constexpr unsigned kFullMask = 0xffffffffu;
 
 struct ChainView {
