@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjtkgpu.so")
 SOURCES = ["phmm_kernels.cu", "jtk_gpu_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-shared", "--expt-relaxed-constexpr"]
 
 
 def sources():

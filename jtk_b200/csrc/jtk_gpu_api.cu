@@ -675,7 +675,7 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
         size_t k = 0;
         while (k < L) {
             size_t e = k;
-            while (e < L && base_code(s[e]) == base_code(s[k])) e++;
+            while (e < L && s[e] == s[k]) e++; // raw bytes, as the reference compares them
             for (size_t x = k; x < e; x++) h[x] = (uint8_t)std::min<size_t>(e - k, 255);
             k = e;
         }
@@ -800,7 +800,7 @@ int batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_conc
         return ctx->fail(JTK_EINVAL, "null argument");
     if (n_pairs > 0 && !allow_bootstrap && (!ops_concat || !ops_off)) return ctx->fail(JTK_EINVAL, "guide ops are required");
     const int C = cols_per_lane_for_radius(radius);
-    if (radius < 0 || C == 0 || C > 4) return ctx->fail(JTK_EINVAL, "radius out of range (0..62)");
+    if (radius < 0 || C == 0 || C > 8) return ctx->fail(JTK_EINVAL, "radius out of range (0..126)");
     CU(cudaSetDevice(ctx->device), "cudaSetDevice");
     jtk_batch *b = new jtk_batch();
     b->ctx = ctx; b->n_pairs = n_pairs; b->n_tmpl = n_tmpl; b->radius = radius; b->C = C;
@@ -1143,15 +1143,18 @@ __global__ void candidates_kernel(CandArgs a) {
         const unsigned sign_count[2] = { sc[0] + sc[2], sc[1] + sc[3] };
         const unsigned tot = strand_count[0] + strand_count[1];
         if (tot == 0) return;
-        double chisq = 0.0;
+        double chisq = 0.0; // summed per strand row, then over the rows, like the reference's nested .sum()
 #pragma unroll
-        for (int st = 0; st < 2; st++)
+        for (int st = 0; st < 2; st++) {
+            double row = 0.0;
 #pragma unroll
             for (int sg = 0; sg < 2; sg++) {
                 const double expected = __ddiv_rn((double)((unsigned long long)strand_count[st] * sign_count[sg]), (double)tot);
                 const double d = __dadd_rn((double)sc[st * 2 + sg], -expected);
-                chisq = __dadd_rn(chisq, __ddiv_rn(__dmul_rn(d, d), expected)); // 0/0 -> NaN, NaN < 10 is false (as in Rust)
+                row = __dadd_rn(row, __ddiv_rn(__dmul_rn(d, d), expected)); // 0/0 -> NaN, NaN < 10 is false (as in Rust)
             }
+            chisq = __dadd_rn(chisq, row);
+        }
         if (!(chisq < 10.0)) return;
     }
     const double total_lk = __dadd_rn(a.prior[a.prior_off[t] + cnt], sum);

@@ -16,6 +16,7 @@
 #include <cassert>
 #include <cmath>
 #include <cstdint>
+#include <cctype>
 #include <cstring>
 #include <functional>
 #include <limits>
@@ -233,13 +234,16 @@ static bool explainable_by_strandedness(const ColStat &c) {
     size_t sign_count[2] = { c.sc[0] + c.sc[2], c.sc[1] + c.sc[3] };
     const size_t sum = strand_count[0] + strand_count[1];
     if (sum == 0) return false;
-    double chisq = 0;
-    for (int st = 0; st < 2; st++)
+    double chisq = 0; // per strand row first, then over the rows: the reference's nested .sum() (:328-337)
+    for (int st = 0; st < 2; st++) {
+        double row = 0;
         for (int sg = 0; sg < 2; sg++) {
             const double expected = (double)(strand_count[st] * sign_count[sg]) / (double)sum;
             const double obs = (double)c.sc[st * 2 + sg];
-            chisq += (obs - expected) * (obs - expected) / expected; // 0/0 -> NaN, NaN < 10 is false (as in Rust)
+            row += (obs - expected) * (obs - expected) / expected; // 0/0 -> NaN, NaN < 10 is false (as in Rust)
         }
+        chisq += row;
+    }
     return chisq < 10.0;
 }
 
@@ -1122,7 +1126,7 @@ int jtk_lc_nonmatch_columns(const uint8_t *ops, int n_ops, const uint8_t *read, 
         const uint8_t op = ops[k];
         if (op <= JTK_OP_MISMATCH) {
             if (i >= Lr || j >= Lt) return -1;
-            bad += read[i] != tmpl[j];
+            bad += std::toupper(read[i]) != std::toupper(tmpl[j]); // Node::recover compares to_ascii_uppercase (definitions/src/lib.rs:777-783)
             i++; j++;
         } else if (op == JTK_OP_INS) { if (i >= Lr) return -1; i++; bad++; }
         else if (op == JTK_OP_DEL) { if (j >= Lt) return -1; j++; bad++; }

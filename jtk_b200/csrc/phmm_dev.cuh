@@ -12,7 +12,7 @@
 namespace jtk {
 
 constexpr int kNumRow = 14;
-constexpr int kCodePad = 512;        // sentinel bytes on both sides of every code array (kernels reach at most 2*NSLOT+16 = 272 past an end)
+constexpr int kCodePad = 544;        // sentinel bytes on both sides of every code array (kernels reach at most 2*NSLOT+16 = 528 past an end, NSLOT <= 256)
 constexpr int kStageCols = 64;       // per-warp staging ring (columns) for finished column sums
 constexpr int kStageStride = 16;     // floats per staged column
 // per-model float block: [0..8] transitions (HMMParam order), [12..75] eM[tc*8+qc], [76..139] eI[ctx*8+qc],

@@ -51,7 +51,8 @@ constexpr int kBwdUnroll = JTK_BWD_UNROLL; // steps of the fast backward block u
 #define JTK_BWD_CTAS9 4
 #endif
 // C = 4 (radius 31..62): 255 registers and a 101 KB ring per CTA either way, two CTAs fit an SM
-constexpr int bwd_ctas_per_sm(int C, int rows) { return C == 2 ? (rows == 14 ? JTK_BWD_CTAS14 : JTK_BWD_CTAS9) : 2; }
+// C = 8 (radius 63..126): the ring alone is 203 KB per CTA, one CTA per SM
+constexpr int bwd_ctas_per_sm(int C, int rows) { return C == 2 ? (rows == 14 ? JTK_BWD_CTAS14 : JTK_BWD_CTAS9) : (C == 4 ? 2 : 1); }
 constexpr int kHalo = 4;        // (single-kernel forward_pass, STORE == 1) replicated slots on both sides of a row
 // Forward rows of the two-kernel modification table (v9): a row is C planes, plane c holds the slots sigma == c (mod C)
 // in slot order (plane c, index k = slot C*k + c), 32 entries + 2 replicated entries on both sides.  A backward lane
@@ -715,8 +716,9 @@ __device__ __forceinline__ void fill_fwd_tables(FwdSmem &sh, const float *__rest
     __syncthreads();
 }
 
+constexpr int fwd_ctas_per_sm(int C) { return C == 2 ? 6 : (C == 4 ? 3 : 2); }
 template <int C>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 6) fwdrows_kernel(KParams p) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, fwd_ctas_per_sm(C)) fwdrows_kernel(KParams p) {
     __shared__ FwdSmem sh;
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     fill_fwd_tables(sh, p.models);
@@ -1230,6 +1232,7 @@ cudaError_t launch_modtable(const KParams &p, int C, int grid_fwd, int grid_bwd,
     switch (C) {
     case 2: return launch_modtable_c<2>(p, p.rows, grid_fwd, grid_bwd, st);
     case 4: return launch_modtable_c<4>(p, p.rows, grid_fwd, grid_bwd, st);
+    case 8: return launch_modtable_c<8>(p, p.rows, grid_fwd, grid_bwd, st);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -1238,6 +1241,7 @@ cudaError_t launch_likelihood(const KParams &p, int C, int grid, cudaStream_t st
     switch (C) {
     case 2: likelihood_kernel<2><<<grid, kWarpsPerCta * 32, 0, st>>>(p); break;
     case 4: likelihood_kernel<4><<<grid, kWarpsPerCta * 32, 0, st>>>(p); break;
+    case 8: likelihood_kernel<8><<<grid, kWarpsPerCta * 32, 0, st>>>(p); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -1255,6 +1259,10 @@ cudaError_t launch_fit(const KParams &p, int C, int grid, double *acc90, cudaStr
         e = cudaFuncSetAttribute(fit_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
         if (e == cudaSuccess) fit_kernel<4><<<grid, kWarpsPerCta * 32, dyn, st>>>(p, acc90);
         break;
+    case 8:
+        e = cudaFuncSetAttribute(fit_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+        if (e == cudaSuccess) fit_kernel<8><<<grid, kWarpsPerCta * 32, dyn, st>>>(p, acc90);
+        break;
     default: return cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return e;
@@ -1265,7 +1273,7 @@ int warps_per_cta() { return kWarpsPerCta; }
 int frow_slots_per_row(int C) { return C * kPlane; }
 int frow_extra_rows() { return kRowShift + kRowsAbove; }
 int modtable_ctas_per_sm(int C, int rows) { return bwd_ctas_per_sm(C, rows); }
-int fwdrows_ctas_per_sm(int C) { return C == 2 ? 6 : 3; }
+int fwdrows_ctas_per_sm(int C) { return fwd_ctas_per_sm(C); }
 int fwdinfo_words() { return 16; }
 int fwd_pad_rows(int C) { return 32 * C + 16; }
 

@@ -469,7 +469,10 @@ def _cluster_pileups(ctx, hmm, gains: Gains, coverage: float, read_type: str, pi
         cfgs = []
         for g, c in enumerate(cids):
             cp, n = pile[c][1].copy_num, counts[g]
-            per_cluster = n / cp if cp <= 2 else max(n / cp, coverage)   # mod.rs:108-111 (copy_num 0 divides by zero there too)
+            # mod.rs:108-111: f64 division, copy_num 0 gives inf and `clustering` then returns the trivial one-cluster
+            # result because copy_num < 2 (pseudo_mcmc.rs:86-88)
+            ratio = n / cp if cp > 0 else float("inf")
+            per_cluster = ratio if cp <= 2 else max(ratio, coverage)
             cfgs.append(ClusteringConfig.new(radius, cp, coverage, per_cluster, gains))
         # chunks below UPPER_COPY_NUM: one 9-row table batch + device-side filter_profiles for all of them
         small = [g for g, c in enumerate(cids) if 2 <= cfgs[g].copy_num < UPPER_COPY_NUM]

@@ -99,6 +99,52 @@ def test_modtable_chunk_config0_vs_oracle(ctx):
     assert worst < 2e-3
 
 
+@pytest.mark.parametrize("L,err,R,n", [
+    (300, 0.15, 63, 6), (700, 0.12, 80, 6), (1500, 0.15, 100, 4), (4000, 0.12, 100, 2), (8000, 0.08, 120, 2),
+])
+def test_modtable_wide_band_vs_oracle(ctx, L, err, R, n):
+    """Radius 63..126 (8 column slots per lane): the reference band is ceil(frac * L) / 2 (definitions/src/lib.rs:173-175,
+    201-210; local_clustering/mod.rs:105,112) -- ONT at 8 kbp gives radius 120, CLR at 4 kbp radius 100, and BASELINE.json
+    configs[3] sweeps the band to 100."""
+    rng = np.random.default_rng(L + R)
+    fwd, rev = random_hmm(21), random_hmm(22)
+    t = synth.random_template(rng, L)
+    reads, ops = [], []
+    for _ in range(n):
+        q, o = synth.mutate_read(rng, t, err)
+        reads.append(q); ops.append(o)
+    strands = (np.arange(n) % 2).astype(np.uint8)
+    tidx = np.zeros(n, np.uint32)
+    lk, tabs = ctx.modtable_batch(to_c(fwd), to_c(rev), [t], reads, ops, strands, tidx, R)
+    otabs, olk = O.modification_table_batch(fwd, rev, [t] * n, reads, ops, strands, R, n_threads=4)
+    check_tables(tabs, lk, otabs, olk, [t], tidx)
+    # likelihood-only kernel on the same pairs (guided)
+    lk2 = ctx.likelihood_batch(to_c(fwd), to_c(rev), [t], reads, ops, strands, tidx, R)
+    assert np.allclose(lk2, olk, rtol=2e-5, atol=1e-6)
+
+
+def test_band_sweep_config3_vs_oracle(ctx):
+    """BASELINE.json configs[3] sweeps the band width: radius 10, 20, 30, 50 and 100 on the same pile-up; a wider band can
+    only add paths, so the likelihood is non-decreasing in the radius, and every radius matches the oracle."""
+    rng = np.random.default_rng(404)
+    fwd, rev = random_hmm(31), random_hmm(32)
+    t = synth.random_template(rng, 1000)
+    reads, ops = [], []
+    for _ in range(4):
+        q, o = synth.mutate_read(rng, t, 0.15)
+        reads.append(q); ops.append(o)
+    strands = np.array([1, 0, 1, 0], np.uint8)
+    tidx = np.zeros(4, np.uint32)
+    prev = None
+    for R in (10, 20, 30, 50, 100):
+        lk, tabs = ctx.modtable_batch(to_c(fwd), to_c(rev), [t], reads, ops, strands, tidx, R)
+        otabs, olk = O.modification_table_batch(fwd, rev, [t] * 4, reads, ops, strands, R, n_threads=4)
+        check_tables(tabs, lk, otabs, olk, [t], tidx)
+        if prev is not None:
+            assert (lk >= prev - 1e-4 * np.abs(prev)).all()
+        prev = lk
+
+
 def test_likelihood_guided_and_bootstrap(ctx):
     rng = np.random.default_rng(77)
     fwd, rev = random_hmm(5), random_hmm(6)
@@ -153,7 +199,7 @@ def test_bad_ops_and_radius_are_rejected(ctx):
         ctx.modtable_batch(h, h, [t], [t], [np.zeros(3, np.uint8)], [1], [0], 5)
     assert e.value.code == -1
     with pytest.raises(_lib.JtkError):
-        ctx.modtable_batch(h, h, [t], [t], [np.zeros(4, np.uint8)], [1], [0], 500)
+        ctx.modtable_batch(h, h, [t], [t], [np.zeros(4, np.uint8)], [1], [0], 127)
     assert ctx.modtable_batch(h, h, [t], [], [], [], [], 5)[0].size == 0
 
 

@@ -61,6 +61,21 @@ def test_local_clustering_selected_phases_diploid_chunks(ctx):
             assert np.count_nonzero(n.ops != 2) == len(c.seq) and np.count_nonzero(n.ops != 3) == len(n.seq)
 
 
+def test_copy_number_zero_and_one_take_the_trivial_path(ctx):
+    """Chunks with copy_num 0 or 1 occur after multiplicity estimation: the reference divides in f64 (n / 0 = inf,
+    local_clustering/mod.rs:108-111) and `clustering` returns one cluster because copy_num < 2 (pseudo_mcmc.rs:86-88)."""
+    ds, _ = make_dataset(3, 400, 20, seed0=1300)
+    ds.selected_chunks[0].copy_num = 0
+    ds.selected_chunks[1].copy_num = 1
+    out = P.local_clustering_selected(ds, {1, 2, 3}, gains=GAINS, ctx=ctx, fit_models=False)
+    assert set(out) == {1, 2, 3}
+    for c in ds.selected_chunks[:2]:
+        assert c.cluster_num == 1 and c.score == 0.0
+        for n in (n for n in ds.nodes if n.chunk == c.id):
+            assert n.cluster == 0 and list(n.posterior) == [0.0]
+    assert ds.selected_chunks[2].cluster_num == 2
+
+
 def test_sharded_driver_equals_single_rank(ctx):
     """Chunks are independent: clustering the two halves of a partition separately (what two ranks do) gives exactly the
     single-rank result."""
