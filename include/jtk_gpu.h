@@ -215,7 +215,9 @@ typedef struct {
  * batch order.  Loop (the oracle's definition): modification tables of the first take_num
  * reads on the GPU, per-column sums on the GPU, greedy pick of positive-gain edits on the host, local patch of every
  * read's ops, until no chunk changes (<= 20 rounds).
- * ops are in/out: pair p owns ops_buf[ops_pos[p] .. ops_pos[p] + ops_cap[p]) and n_ops[p] holds its length.
+ * ops are in/out: pair p owns ops_buf[ops_pos[p] .. ops_pos[p] + ops_cap[p]) and n_ops[p] holds its length.  On a non-zero
+ * return ops_buf / n_ops / out_cons are UNDEFINED (some chunks may already be patched): the caller keeps its own copy if it
+ * wants to continue after a failure; jtk_last_error(ctx) names the cause.
  * out_cons: chunk c owns out_cons[cons_pos[c] .. cons_pos[c] + cons_cap[c]); out_len[c] is the polished length.
  * out_iters (may be NULL): rounds in which chunk c changed.
  */
@@ -283,6 +285,12 @@ int jtk_lc_clustering_variants_rng(const double *variants, int n_reads, int n_pr
                                    const uint8_t *tmpl, int Lt, const jtk_gains *gains, const jtk_clustering_config *cfg,
                                    uint64_t *state4, uint64_t *out_asn, double *out_post, int post_stride, double *out_score,
                                    int *out_k);
+/* exact_clustering::cluster_filtered_variants_exact (haplotyper/src/local_clustering/exact_clustering.rs:7-77): exhaustive
+ * search over one column subset per cluster (2^n_probes masks, non-increasing tuples of copy_num masks); the score the MCMC
+ * is compared with in sandbox/src/bin/benchmark_mcmc.rs:112-118.  out_gains[r * copy_num + c] = read r's summed values over
+ * cluster c's subset; out_asn[r] its best cluster (last maximum); *out_score = sum over reads of the best value. */
+int jtk_lc_cluster_filtered_variants_exact(const double *variants, int n_reads, int n_probes, int stride, int copy_num,
+                                           uint64_t *out_asn, double *out_gains, double *out_score);
 const char *jtk_lc_last_error(void);
 /* hooks for the reference's unit tests on these files (pseudo_mcmc.rs:876-904) and the generator */
 double jtk_lc_cosine_similarity(const double *profiles, int n, int ncol, int i, int j);
@@ -324,6 +332,25 @@ int jtk_lc_clustering_variants_batch(jtk_ctx *ctx, int n_chunks, const double *v
                                      const jtk_gains *gains, const jtk_clustering_config *cfgs, uint64_t *states,
                                      uint64_t *out_asn_concat, const uint64_t *asn_off, double *out_post_concat,
                                      const uint64_t *post_off, int post_stride, double *out_score, int32_t *out_k);
+
+/* ---- layout pins of every struct that crosses the ABI (LP64): the Rust `#[repr(C)]` mirrors in jtk-gpu-sys/src/lib.rs
+ * and the ctypes / numpy mirrors in jtk_b200/ carry the same numbers (tests/test_abi_exports.py) ---------------------- */
+#ifdef __cplusplus
+#define JTK_STATIC_ASSERT(c, m) static_assert(c, m)
+#else
+#define JTK_STATIC_ASSERT(c, m) _Static_assert(c, m)
+#endif
+JTK_STATIC_ASSERT(sizeof(jtk_hmm_params) == 45 * 8 && offsetof(jtk_hmm_params, mat_emit) == 72 &&
+                  offsetof(jtk_hmm_params, ins_emit) == 200, "jtk_hmm_params: 9 + 16 + 20 doubles, HMMParam order");
+JTK_STATIC_ASSERT(sizeof(jtk_colstat) == 24 && offsetof(jtk_colstat, count) == 8 && offsetof(jtk_colstat, sc) == 12,
+                  "jtk_colstat layout");
+JTK_STATIC_ASSERT(sizeof(jtk_candidate) == 32 && offsetof(jtk_candidate, sum) == 16 && offsetof(jtk_candidate, lk) == 24,
+                  "jtk_candidate layout");
+JTK_STATIC_ASSERT(sizeof(jtk_gains) == 24 && offsetof(jtk_gains, gain) == 8 && offsetof(jtk_gains, prob) == 16, "jtk_gains layout");
+JTK_STATIC_ASSERT(sizeof(jtk_clustering_config) == 24 && offsetof(jtk_clustering_config, coverage) == 8, "jtk_clustering_config layout");
+JTK_STATIC_ASSERT(sizeof(jtk_polish_config) == 12, "jtk_polish_config layout");
+/* sizeof() of the struct called `name` ("jtk_hmm_params", "jtk_colstat", ...) as this library was compiled; 0 = unknown name */
+size_t jtk_abi_sizeof(const char *name);
 
 /* in-band cell count C = sum_d w(d) of one pair (SURVEY.md section 8d work unit); <0 if ops are invalid */
 int64_t jtk_band_cell_count(const uint8_t *ops, int n_ops, int Lt, int Lr, int radius);

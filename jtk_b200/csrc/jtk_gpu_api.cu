@@ -48,8 +48,20 @@ struct DevPool {
     struct Block { void *p; size_t bytes; };
     std::vector<Block> free_blocks;
     size_t cached = 0;
-    static constexpr size_t kMaxCached = (size_t)48 << 30;
+    std::mutex mu; // take / give run on the owning context's thread, trim_all() on whichever thread ran out of memory
+    static constexpr size_t kMaxCached = (size_t)24 << 30;
+    static std::mutex &reg_mu() { static std::mutex m; return m; }
+    static std::vector<DevPool *> &registry() { static std::vector<DevPool *> r; return r; }
+    DevPool() { std::lock_guard<std::mutex> g(reg_mu()); registry().push_back(this); }
+    ~DevPool() {
+        std::lock_guard<std::mutex> g(reg_mu());
+        auto &r = registry();
+        r.erase(std::remove(r.begin(), r.end(), this), r.end());
+    }
+    DevPool(const DevPool &) = delete;
+    DevPool &operator=(const DevPool &) = delete;
     void *take(size_t bytes, size_t &got) {
+        std::lock_guard<std::mutex> g(mu);
         size_t best = free_blocks.size();
         for (size_t k = 0; k < free_blocks.size(); k++)
             if (free_blocks[k].bytes >= bytes && free_blocks[k].bytes <= 2 * bytes + (1 << 20) &&
@@ -62,14 +74,23 @@ struct DevPool {
         return blk.p;
     }
     void give(void *p, size_t bytes) {
+        std::lock_guard<std::mutex> g(mu);
         if (cached + bytes > kMaxCached) { cudaFree(p); return; }
         free_blocks.push_back({ p, bytes });
         cached += bytes;
     }
     void clear() {
+        std::lock_guard<std::mutex> g(mu);
         for (auto &b : free_blocks) cudaFree(b.p);
         free_blocks.clear();
         cached = 0;
+    }
+    // an allocation failed somewhere: every context of the process gives its cached blocks back to the driver
+    static bool trim_all() {
+        std::lock_guard<std::mutex> g(reg_mu());
+        bool any = false;
+        for (DevPool *p : registry()) { any = any || p->cached > 0; p->clear(); }
+        return any;
     }
 };
 
@@ -86,10 +107,9 @@ template <typename T> struct DevBuf {
             if (void *q = pool->take(want * sizeof(T), got)) { p = (T *)q; cap = got / sizeof(T); return cudaSuccess; }
         }
         cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
-        if (e != cudaSuccess && pool && !pool->free_blocks.empty()) { // give the cache back to the driver and retry
+        if (e != cudaSuccess) { // give the caches of all contexts back to the driver and retry
             cudaGetLastError();
-            pool->clear();
-            e = cudaMalloc((void **)&p, want * sizeof(T));
+            if (DevPool::trim_all()) e = cudaMalloc((void **)&p, want * sizeof(T));
         }
         if (e == cudaSuccess) cap = want; else p = nullptr;
         return e;
@@ -324,6 +344,7 @@ struct jtk_ctx {
     }
 };
 
+namespace jtk { int ctx_fail(jtk_ctx *ctx, int code, const char *msg) { return ctx ? ctx->fail(code, msg) : code; } }
 #define CU(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return ctx->cuda_fail(e_, what); } while (0)
 
 extern "C" {
@@ -800,6 +821,7 @@ int batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_conc
         return ctx->fail(JTK_EINVAL, "null argument");
     if (n_pairs > 0 && !allow_bootstrap && (!ops_concat || !ops_off)) return ctx->fail(JTK_EINVAL, "guide ops are required");
     const int C = cols_per_lane_for_radius(radius);
+    if (n_tmpl > 65535) return ctx->fail(JTK_EINVAL, "more than 65535 templates in one batch (the per-chunk kernels put the template on grid.y): split the call");
     if (radius < 0 || C == 0 || C > 8) return ctx->fail(JTK_EINVAL, "radius out of range (0..126)");
     CU(cudaSetDevice(ctx->device), "cudaSetDevice");
     jtk_batch *b = new jtk_batch();
@@ -935,6 +957,10 @@ int batch_run(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev
             budget = std::min(budget, (free_b + have) / 2);
         }
         per_wave = (int)std::max<size_t>(1, std::min<size_t>((size_t)b->n_pairs, budget / per_pair));
+        per_wave = std::min(per_wave, 65535); // finalize_kernel puts the pair of a wave on grid.y
+        // the forward kernel stages the codes of one pair per warp in shared memory
+        if ((size_t)wpc * (size_t)(kp.smem_rb + kp.smem_tb) > (size_t)227 * 1024 - 4096)
+            return ctx->fail(JTK_EINVAL, "pair too long for the modification-table kernels: read + template length must stay below ~56 000 bases");
         CU(ctx->d_frows.reserve((size_t)per_wave * kp.frow_stride), "cudaMalloc forward rows");
         CU(ctx->d_kf.reserve((size_t)per_wave * kp.kf_stride), "cudaMalloc scale exponents");
         CU(ctx->d_fwdinfo.reserve((size_t)per_wave * kp.fwdinfo_stride), "cudaMalloc forward info");

@@ -9,6 +9,8 @@
 #include <vector>
 
 namespace jtk {
+// records `msg` as the context's last error (jtk_last_error) and returns `code`: error paths outside jtk_gpu_api.cu
+int ctx_fail(jtk_ctx *ctx, int code, const char *msg);
 namespace host {
 
 // Pvalues::pvalue tables (likelihood_gains.rs:115-129,148-158) for `total` reads: out[(type * H + h) * (total + 1) + count]

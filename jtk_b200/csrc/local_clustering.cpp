@@ -712,6 +712,57 @@ static DevResult cluster_filtered_variants(const Mat &variants, const VarTypes &
     return { assignments, get_likelihood_gain(variants, assignments, max_k), mx, max_k };
 }
 
+// exact_clustering::cluster_filtered_variants_exact (haplotyper/src/local_clustering/exact_clustering.rs:7-77): every cluster
+// picks a subset of the D columns (a bit mask), a read scores the sum of its values over the subset of its best cluster;
+// all non-increasing tuples of copy_num masks are enumerated (increment_one, :66-77) and the first strict maximum is kept.
+// Used by sandbox/src/bin/benchmark_mcmc.rs:112-118 as the score the MCMC is compared with (SURVEY 8c pin P7).
+static double exact_selection_score(size_t selection, const std::vector<double> &xs) { // get_exact_score :49-54
+    double s = 0;
+    for (size_t i = 0; i < xs.size(); i++) if ((selection >> i) & 1u) s += xs[i];
+    return s;
+}
+static double exact_calc_score(const std::vector<size_t> &vars, const Mat &variants) { // calc_score :56-64
+    double total = 0;
+    for (const auto &xs : variants) {
+        double best = exact_selection_score(vars[0], xs);
+        for (size_t c = 1; c < vars.size(); c++) { const double v = exact_selection_score(vars[c], xs); if (!(v < best)) best = v; }
+        total += best;
+    }
+    return total;
+}
+static DevResult exact_get_result(const std::vector<size_t> &vars, const Mat &variants) { // get_result :28-47
+    DevResult r;
+    r.score = exact_calc_score(vars, variants);
+    r.k = vars.size();
+    for (const auto &xs : variants) {
+        std::vector<double> lk_gain;
+        for (size_t sel : vars) lk_gain.push_back(exact_selection_score(sel, xs));
+        size_t bi = 0;
+        for (size_t c = 0; c < lk_gain.size(); c++) if (!(lk_gain[c] < lk_gain[bi])) bi = c; // max_by: last maximum
+        r.asn.push_back(bi);
+        r.gains.push_back(lk_gain);
+    }
+    return r;
+}
+static DevResult cluster_filtered_variants_exact(const Mat &variants, size_t feature_dim, size_t copy_num) {
+    JTK_ASSERT(copy_num >= 1 && feature_dim < 24, "exact clustering: copy_num >= 1 and fewer than 24 columns");
+    std::vector<size_t> selected(copy_num, 0);
+    const size_t choices = (size_t)1 << feature_dim;
+    const std::vector<size_t> last_loop(copy_num, choices - 1);
+    double mx = 0;
+    DevResult argmax = exact_get_result(selected, variants);
+    while (selected != last_loop) { // the last tuple itself is never scored, as in the reference (:17-24)
+        const double score = exact_calc_score(selected, variants);
+        if (mx < score) { argmax = exact_get_result(selected, variants); mx = score; }
+        size_t idx = 0; // increment_one
+        while (choices == selected[idx] + 1) idx++;
+        selected[idx]++;
+        for (size_t j = 0; j < idx; j++) selected[j] = selected[idx];
+        for (size_t w = 0; w + 1 < selected.size(); w++) JTK_ASSERT(selected[w + 1] <= selected[w], "increment_one: tuple not sorted");
+    }
+    return argmax;
+}
+
 // pseudo_mcmc::clustering (:77-107) after search_variants produced (variants, variant types)
 static DevResult clustering_tail(const Mat &variants, const VarTypes &vt, size_t copy_num, double coverage,
                                  double local_coverage, const Gains &gains, Rng &rng) {
@@ -968,6 +1019,25 @@ int jtk_lc_clustering_variants_rng(const double *variants, int n_reads, int n_pr
     return rc;
 }
 
+// exact_clustering::cluster_filtered_variants_exact (exact_clustering.rs:7-77) on a dense n_reads x n_probes matrix
+int jtk_lc_cluster_filtered_variants_exact(const double *variants, int n_reads, int n_probes, int stride, int copy_num,
+                                           uint64_t *out_asn, double *out_gains, double *out_score) {
+    try {
+        if (n_reads < 0 || n_probes < 0 || copy_num < 1 || !out_asn || !out_gains || !out_score ||
+            (n_reads > 0 && n_probes > 0 && (!variants || stride < n_probes))) { g_lc_error = "null / bad argument"; return JTK_EINVAL; }
+        Mat vars((size_t)n_reads);
+        for (int r = 0; r < n_reads; r++)
+            if (n_probes > 0) vars[(size_t)r].assign(variants + (size_t)r * stride, variants + (size_t)r * stride + n_probes);
+        const DevResult res = cluster_filtered_variants_exact(vars, (size_t)n_probes, (size_t)copy_num);
+        for (int r = 0; r < n_reads; r++) {
+            out_asn[r] = res.asn[(size_t)r];
+            for (int c = 0; c < copy_num; c++) out_gains[(size_t)r * copy_num + c] = res.gains[(size_t)r][(size_t)c];
+        }
+        *out_score = res.score;
+        return JTK_OK;
+    } catch (const std::exception &e) { g_lc_error = e.what(); return JTK_EINVAL; }
+}
+
 // Host twin of one chain of jtk_mcmc_restarts_batch (tests: device == host, bit for bit)
 int jtk_lc_mcmc_restarts_host(const double *data, int n, int D, int k, double cov, int restarts, uint64_t *state4,
                               uint8_t *out_asn, double *out_lk) {
@@ -1111,6 +1181,18 @@ int jtk_lc_clustering_variants_batch(jtk_ctx *ctx, int n_chunks, const double *v
         g_lc_error = e.what();
         return JTK_EINVAL;
     }
+}
+
+size_t jtk_abi_sizeof(const char *name) {
+    if (!name) return 0;
+    const std::string n(name);
+    if (n == "jtk_hmm_params") return sizeof(jtk_hmm_params);
+    if (n == "jtk_colstat") return sizeof(jtk_colstat);
+    if (n == "jtk_candidate") return sizeof(jtk_candidate);
+    if (n == "jtk_gains") return sizeof(jtk_gains);
+    if (n == "jtk_clustering_config") return sizeof(jtk_clustering_config);
+    if (n == "jtk_polish_config") return sizeof(jtk_polish_config);
+    return 0;
 }
 
 // test hooks for the reference's own unit tests on these files (pseudo_mcmc.rs:876-904)

@@ -4,6 +4,7 @@
 // definition implemented here is the one written down in DESIGN.md section 2 and restated in f64 by the oracle:
 // the tables and per-column sums come from the GPU, edit selection and the local patch of the guide ops run here.
 #include "../../include/jtk_gpu.h"
+#include "lc_host.h"
 
 #include <algorithm>
 #include <atomic>
@@ -93,16 +94,16 @@ extern "C" int jtk_polish_until_converge_batch(jtk_ctx *ctx, const jtk_hmm_param
                                                const uint8_t *strand, const uint32_t *tmpl_idx, const jtk_polish_config *cfg,
                                                uint8_t *out_cons, const uint64_t *cons_pos, const uint32_t *cons_cap,
                                                uint32_t *out_len, int32_t *out_iters) {
-    if (!ctx || !fwd || !rev || !cfg || n_chunks < 0 || n_pairs < 0) return JTK_EINVAL;
+    if (!ctx || !fwd || !rev || !cfg || n_chunks < 0 || n_pairs < 0) return jtk::ctx_fail(ctx, JTK_EINVAL, "polish: null argument or negative count");
     if (n_chunks == 0) return JTK_OK;
     if (!draft_concat || !draft_off || !read_concat || !read_off || !ops_buf || !ops_pos || !ops_cap || !n_ops || !strand ||
         !tmpl_idx || !out_cons || !cons_pos || !cons_cap || !out_len)
-        return JTK_EINVAL;
+        return jtk::ctx_fail(ctx, JTK_EINVAL, "polish: null argument");
     std::vector<std::vector<uint8_t>> tmpl((size_t)n_chunks);
     std::vector<std::vector<uint32_t>> members((size_t)n_chunks);
     for (int c = 0; c < n_chunks; c++) tmpl[(size_t)c].assign(draft_concat + draft_off[c], draft_concat + draft_off[c + 1]);
     for (int p = 0; p < n_pairs; p++) {
-        if (tmpl_idx[p] >= (uint32_t)n_chunks) return JTK_EINVAL;
+        if (tmpl_idx[p] >= (uint32_t)n_chunks) return jtk::ctx_fail(ctx, JTK_EINVAL, "polish: tmpl_idx out of range");
         members[tmpl_idx[p]].push_back((uint32_t)p);
     }
     std::vector<int> iters((size_t)n_chunks, 0);
@@ -198,7 +199,7 @@ extern "C" int jtk_polish_until_converge_batch(jtk_ctx *ctx, const jtk_hmm_param
             for (size_t t = 1; t < nt; t++) th.emplace_back(worker);
             worker();
             for (auto &t : th) t.join();
-            if (failed.load()) return JTK_EINVAL;
+            if (failed.load()) return jtk::ctx_fail(ctx, JTK_EINVAL, "polish: a read's patched ops exceed ops_cap (ops_buf / n_ops are undefined after a failed call)");
         }
         t_patch += ms(p3, now());
     }
@@ -207,7 +208,7 @@ extern "C" int jtk_polish_until_converge_batch(jtk_ctx *ctx, const jtk_hmm_param
         std::fprintf(stderr, "[jtk timing] polish: %d rounds, pack=%.1fms create=%.1fms tables+pick=%.1fms patch=%.1fms\n", rounds_run,
                      t_pack, t_create, t_table, t_patch);
     for (int c = 0; c < n_chunks; c++) {
-        if (tmpl[(size_t)c].size() > cons_cap[c]) return JTK_EINVAL;
+        if (tmpl[(size_t)c].size() > cons_cap[c]) return jtk::ctx_fail(ctx, JTK_EINVAL, "polish: polished consensus exceeds cons_cap (ops_buf / n_ops are undefined after a failed call)");
         std::memcpy(out_cons + cons_pos[c], tmpl[(size_t)c].data(), tmpl[(size_t)c].size());
         out_len[c] = (uint32_t)tmpl[(size_t)c].size();
         if (out_iters) out_iters[c] = iters[(size_t)c];

@@ -24,6 +24,11 @@ from ._lib import COPY_SIZE, DEL_SIZE, NUM_ROW, Context, HmmParams, JtkError  # 
 _default_ctx: Optional[Context] = None
 
 
+class PolishCfg(_lib.C.Structure):
+    """jtk_polish_config == kiley::hmm::HMMPolishConfig::new(radius, take_num, ignore_edge)."""
+    _fields_ = [("radius", _lib.C.c_int), ("take_num", _lib.C.c_int), ("ignore_edge", _lib.C.c_int)]
+
+
 def default_context() -> Context:
     global _default_ctx
     if _default_ctx is None:
@@ -173,12 +178,10 @@ def polish_chunks(models: PairHiddenMarkovModelOnStrands, drafts: Sequence, read
     clen = np.zeros(n_chunks, dtype=np.uint32)
     iters = np.zeros(n_chunks, dtype=np.int32)
 
-    class _Cfg(C.Structure):
-        _fields_ = [("radius", C.c_int), ("take_num", C.c_int), ("ignore_edge", C.c_int)]
-    cfg = _Cfg(config.radius, config.take_num, config.ignore_edge)
+    cfg = PolishCfg(config.radius, config.take_num, config.ignore_edge)
     vp = C.c_void_p
     L.jtk_polish_until_converge_batch.argtypes = [vp, C.POINTER(HmmParams), C.POINTER(HmmParams), C.c_int, vp, vp, C.c_int,
-                                                  vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(_Cfg), vp, vp, vp, vp, vp]
+                                                  vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(PolishCfg), vp, vp, vp, vp, vp]
     f, r = models.forward().to_c(), models.reverse().to_c()
     p = _lib._ptr
     ctx._check(L.jtk_polish_until_converge_batch(ctx._h, C.byref(f), C.byref(r), n_chunks, p(dcat), p(doff), n_pairs, p(rcat),

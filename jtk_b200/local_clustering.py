@@ -88,6 +88,8 @@ def _bind():
         L.jtk_lc_clustering_variants.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.POINTER(_CGains),
                                                  C.POINTER(_CConfig), C.c_uint64, vp, vp, C.c_int, C.POINTER(C.c_double),
                                                  C.POINTER(C.c_int)]
+        L.jtk_lc_cluster_filtered_variants_exact.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
+                                                             C.POINTER(C.c_double)]
         L.jtk_lc_last_error.restype = C.c_char_p
         L.jtk_lc_cosine_similarity.restype = C.c_double
         L.jtk_lc_cosine_similarity.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -162,6 +164,21 @@ def clustering_on_variants(variants, probe_pos, template, config: ClusteringConf
         raise _lib.JtkError(rc, L.jtk_lc_last_error().decode())
     kk = int(k.value)
     return ClusteringResult(asn, post.reshape(n, pstride)[:, :kk].copy(), float(score.value), kk, pp.copy())
+
+
+def cluster_filtered_variants_exact(variants, copy_num: int):
+    """exact_clustering::cluster_filtered_variants_exact (exact_clustering.rs:7-77): exhaustive search over one column subset
+    per cluster.  Returns (assignments, per-read per-cluster gains, score, copy_num) like the reference's tuple."""
+    L = _bind()
+    v = np.ascontiguousarray(variants, dtype=np.float64)
+    n, d = v.shape
+    asn = np.zeros(n, dtype=np.uint64)
+    gains = np.zeros((n, copy_num), dtype=np.float64)
+    score = C.c_double()
+    rc = L.jtk_lc_cluster_filtered_variants_exact(_ptr(v), n, d, d, copy_num, _ptr(asn), _ptr(gains), C.byref(score))
+    if rc != 0:
+        raise _lib.JtkError(rc, L.jtk_lc_last_error().decode())
+    return asn, gains, float(score.value), copy_num
 
 
 def local_clustering_batch(batch: Batch, templates, config_of, seeds, hmm_fwd, hmm_rev, gains: Gains, coverage: float):

@@ -123,3 +123,62 @@ def test_host_restarts_twin_is_deterministic_and_splits_two_haplotypes():
     assert not np.array_equal(outs[0][2], P._rng_seed(99))
     a = outs[0][0]
     assert (a == hap).all() or (a == 1 - hap).all()
+
+
+def _brute_exact(v, k):
+    """Independent restatement of exact_clustering.rs:7-77 in plain Python (tiny sizes only)."""
+    n, d = v.shape
+    sel = [0] * k
+    choices = 1 << d
+    score_of = lambda sel: sum(max(sum(x for i, x in enumerate(row) if (s >> i) & 1) for s in sel) for row in v)
+    best, best_sel = 0.0, list(sel)
+    while sel != [choices - 1] * k:
+        sc = score_of(sel)
+        if best < sc:
+            best, best_sel = sc, list(sel)
+        idx = 0
+        while choices == sel[idx] + 1:
+            idx += 1
+        sel[idx] += 1
+        for j in range(idx):
+            sel[j] = sel[idx]
+    return best, best_sel
+
+
+def test_exact_clustering_matches_a_python_restatement():
+    """exact_clustering::cluster_filtered_variants_exact (exact_clustering.rs:7-77) against a plain-Python loop."""
+    rng = np.random.default_rng(4)
+    for n, d, k in ((7, 3, 2), (9, 4, 2), (6, 3, 3), (5, 1, 2)):
+        v = rng.normal(0, 3, (n, d))
+        asn, gains, score, kk = LC.cluster_filtered_variants_exact(v, k)
+        want, sel = _brute_exact(v, k)
+        assert kk == k and abs(score - want) < 1e-12
+        for r in range(n):
+            g = [sum(x for i, x in enumerate(v[r]) if (s >> i) & 1) for s in sel]
+            assert np.allclose(gains[r], g)
+            assert gains[r, int(asn[r])] == max(g)
+
+
+def test_exact_score_bounds_the_mcmc_score():
+    """SURVEY 8c pin P7 (sandbox/src/bin/benchmark_mcmc.rs:112-118 prints both): the exhaustive search maximises the data
+    term of the MCMC objective with free column subsets per cluster and no size prior (max_poisson_lk <= 0), so on the
+    same variants its score can never be below what cluster_filtered_variants returns; on a clean two-haplotype matrix
+    both find the planted split."""
+    rng = np.random.default_rng(17)
+    t = synth.random_template(rng, 300)
+    for trial in range(6):
+        n, d = 30 + 4 * trial, 2 + trial % 4
+        hap = rng.integers(0, 2, n)
+        signal = np.where(hap[:, None] == 1, 6.0, -6.0) * rng.choice([1.0, -1.0], d)[None, :]
+        v = signal + rng.normal(0, 1.5, (n, d))
+        v[np.abs(v) < 1.0] = 0.0  # compress_small_gains leaves exact zeros
+        pos = (np.arange(d) * 23 + 40) * 14 + rng.integers(0, 4, d)
+        cfg = LC.ClusteringConfig.new(15, 2, n / 2, n / 2, GAINS)
+        r = LC.clustering_on_variants(v, pos.astype(np.uint32), t, cfg, seed=3490 * (trial + 1))
+        asn, gains, score, _ = LC.cluster_filtered_variants_exact(v, 2)
+        assert score >= r.score - 1e-9, (trial, score, r.score)
+        assert r.k == 2
+        a = r.assignments.astype(int)
+        assert max((a == hap).mean(), (a != hap).mean()) >= 0.95
+        e = asn.astype(int)
+        assert max((e == hap).mean(), (e != hap).mean()) >= 0.95
