@@ -174,26 +174,34 @@ def measured_peaks():
 
 
 def cpu_baseline_run(templates, reads, ops, strands, tidx, n_pairs, threads, min_seconds=0.0):
-    """Oracle (f64 restatement, kind 'port') over the first n_pairs pairs, `threads` OS threads over pairs
-    (the reference's rayon decomposition), repeated until min_seconds of wall time have passed.  Pairs are scored in
-    slices of 480 so that the f64 tables of a slice (108 MB) are the only large allocation.
-    Returns (seconds, cell updates)."""
+    """Oracle (f64 restatement, kind 'port') over the chunks that hold the first n_pairs pairs.  Decomposition as in the
+    reference: one task per CHUNK on `threads` OS threads (`pileups.into_par_iter()`, local_clustering/mod.rs:64-72), each
+    task scoring the reads of its chunk one after the other (pseudo_mcmc.rs:53-67).  Repeated until min_seconds of wall time
+    have passed.  Returns (seconds, cell updates)."""
+    from concurrent.futures import ThreadPoolExecutor
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     from jtk_b200 import _lib
     h = O.default_hmm()
-    tl = [templates[int(tidx[k])] for k in range(n_pairs)]
-    per_pass = sum(2 * _lib.band_cell_count(ops[k], len(tl[k]), len(reads[k]), RADIUS) for k in range(n_pairs))
+    n_pairs = min(n_pairs, len(reads))
+    chunk_ids = sorted({int(tidx[k]) for k in range(n_pairs)})
+    members = {c: [] for c in chunk_ids}
+    for k in range(n_pairs):
+        members[int(tidx[k])].append(k)
+    per_pass = sum(2 * _lib.band_cell_count(ops[k], len(templates[int(tidx[k])]), len(reads[k]), RADIUS) for k in range(n_pairs))
+
+    def one_chunk(c):
+        ks = members[c]
+        O.modification_table_batch(h, h, [templates[c]] * len(ks), [reads[k] for k in ks], [ops[k] for k in ks],
+                                   [strands[k] for k in ks], RADIUS, n_threads=1, want_tables=True)
     t0 = time.perf_counter()
     cells = 0
-    while True:
-        for a in range(0, n_pairs, 480):
-            b = min(n_pairs, a + 480)
-            O.modification_table_batch(h, h, tl[a:b], reads[a:b], ops[a:b], strands[a:b], RADIUS,
-                                       n_threads=threads, want_tables=True)
-        cells += per_pass
-        if time.perf_counter() - t0 >= min_seconds:
-            break
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        while True:
+            list(pool.map(one_chunk, chunk_ids))
+            cells += per_pass
+            if time.perf_counter() - t0 >= min_seconds:
+                break
     return time.perf_counter() - t0, cells
 
 
@@ -203,7 +211,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_chunks_sample = 8
+    n_chunks_sample = max(8, threads)  # at least one chunk per thread
     templates, reads, ops, strands, tidx = make_workload(0, n_chunks_sample, args.reads, args.length)
     n_pairs = len(reads)
     for _ in range(args.warmup):
@@ -215,7 +223,8 @@ def run_reference(args, rank, world):
         t += dt
         cells += c
     gcups = cells / t / 1e9
-    sample = f"{n_chunks_sample} chunks x {args.reads} reads ({n_pairs} pairs) of the same workload per step"
+    sample = (f"{n_chunks_sample} chunks x {args.reads} reads ({n_pairs} pairs) of the same workload per step, one task per chunk on "
+              f"{threads} threads (rayon's decomposition)")
     line = {
         "impl": "reference", "metric": "pair-HMM modification-table GCUPS", "value": gcups, "unit": "GCUPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
@@ -228,41 +237,147 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def phase_leg(ctx, templates, reads, ops, strands, tidx, n_chunks, cov, rank=0, world=1):
+def phase_leg(ctx, templates, reads, ops, strands, tidx, n_chunks, cov, rank=0, world=1, group=None):
     """'chunks phased per second' (BASELINE.json metric, second half): the whole per-chunk path of
-    local_clustering_selected (local_clustering/mod.rs:56-83 without the model fit) on the first n_chunks chunks --
-    batched polish, 9-row tables, device-side filter_profiles, host greedy pick + k-means + MCMC, posteriors,
-    normalisation -- through jtk_b200/pipeline.py.  Wall clock.  Under torchrun every rank calls this with the SAME chunks
-    (rank 0's workload): the scheduler shards them over the ranks and gathers the per-chunk results on rank 0 (strong
-    scaling; the host clustering of all ranks shares the box's cores)."""
+    local_clustering_selected (local_clustering/mod.rs:56-83 without the model fit) on n_chunks chunks -- batched polish,
+    9-row tables, device-side filter_profiles, greedy pick, k-means + MCMC (GPU restarts kernel + host threads), posteriors,
+    normalisation -- through jtk_b200/pipeline.py.  Wall clock.  Under torchrun every rank calls this with the SAME chunks:
+    the scheduler shards them over the ranks and gathers the per-chunk results on rank 0 over the host group (strong
+    scaling; the host threads of all ranks share the box's cores)."""
     from jtk_b200 import pipeline as P
     from jtk_b200 import local_clustering as LC
     gains = LC.Gains(gain=GAINS_EXPECTED.astype(np.float64), prob=GAINS_PROB)
 
-    def dataset(chunk_ids):
-        chunks = [P.Chunk(id=int(c) + 1, seq=templates[c].copy(), copy_num=2) for c in chunk_ids]
+    def dataset(lo, hi):
+        chunks = [P.Chunk(id=c + 1, seq=templates[c].copy(), copy_num=2) for c in range(lo, hi)]
         nodes = [P.Node(chunk=int(tidx[k]) + 1, seq=reads[k], ops=ops[k], is_forward=bool(strands[k]))
-                 for k in range(len(reads)) if int(tidx[k]) in set(chunk_ids)]
+                 for k in range(len(reads)) if lo <= int(tidx[k]) < hi]
         return P.DataSet(selected_chunks=chunks, nodes=nodes, read_type="ONT")
 
-    warm = dataset(list(range(min(max(2, world), n_chunks))))
+    warm = dataset(0, min(max(2, world), n_chunks))
     P.local_clustering_selected(warm, {c.id for c in warm.selected_chunks}, gains=gains, ctx=ctx, fit_models=False,
-                                rank=rank, world=world)
-    ds = dataset(list(range(n_chunks)))
+                                rank=rank, world=world, group=group)
+    ds = dataset(0, n_chunks)
     if world > 1:
         import torch.distributed as dist
-        dist.barrier()
+        dist.barrier(group=group)
     t0 = time.perf_counter()
     out = P.local_clustering_selected(ds, {c.id for c in ds.selected_chunks}, gains=gains, ctx=ctx, fit_models=False,
-                                      rank=rank, world=world)
+                                      rank=rank, world=world, group=group)
     dt = time.perf_counter() - t0
     if out is None:
         return None
     ks = [out[c][2] for c in sorted(out)]
-    return {"phases_s": {k: round(v, 4) for k, v in P.LAST_TIMING.items()}, "chunks_per_s": n_chunks / dt, "chunks": n_chunks, "seconds": dt, "host_threads": P.host_threads(),
-            "two_cluster_chunks": int(sum(1 for k in ks if k == 2)),
-            "what": "polish + 9-row tables + device filter_profiles + host pick/k-means/MCMC + normalise; "
-                    f"{n_chunks} chunks sharded over {world} GPU(s), host gather on rank 0 (strong scaling)"}
+    return {"phases_s": {k: round(v, 4) for k, v in P.LAST_TIMING.items()}, "chunks_per_s": n_chunks / dt, "chunks": n_chunks, "seconds": dt,
+            "host_threads": P.host_threads(), "two_cluster_chunks": int(sum(1 for k in ks if k == 2)),
+            "what": "polish + 9-row tables + device filter_profiles + pick + k-means/MCMC (GPU restarts + host threads) + normalise; "
+                    f"{n_chunks} chunks sharded over {world} GPU(s), host gather on rank 0 (strong scaling); phases_s are rank 0's"}
+
+
+def band_sweep_leg(ctx, fwd, n_chunks=4, n_reads=240, length=2000):
+    """BASELINE.json configs[3]: repeat-heavy chunks (240 reads per chunk) with the band swept over the reference's range
+    (radius = ceil(frac * L) / 2: 10 .. 100, definitions/src/lib.rs:173-175,201-210): 14-row modification-table GCUPS per
+    radius on rank 0's GPU (kernels only), and the copy_num = 8 recursive clustering path of local_clustering/mod.rs:126-190."""
+    from jtk_b200 import synth
+    chunks = [synth.paralog_chunk(4242 + c, length=length, n_reads=n_reads) for c in range(n_chunks)]
+    templates = [c["template"] for c in chunks]
+    reads = [r for c in chunks for r in c["reads"]]
+    ops = [o for c in chunks for o in c["ops"]]
+    strands = np.concatenate([c["strands"] for c in chunks])
+    tidx = np.repeat(np.arange(n_chunks, dtype=np.uint32), [len(c["reads"]) for c in chunks])
+    out = {"what": f"{n_chunks} chunks x {n_reads} reads (4 paralogs x 2 haplotypes), 14 rows, kernels only", "radius": {}}
+    for radius in (10, 20, 30, 50, 100):
+        b = ctx.batch(templates, reads, ops, strands, tidx, radius)
+        for _ in range(2):
+            b.modtable(fwd, fwd, 14)
+        b.sync()
+        ctx.kernel_times()
+        for _ in range(3):
+            b.modtable(fwd, fwd, 14)
+        b.sync()
+        ms = float(np.median(ctx.kernel_times()))
+        out["radius"][str(radius)] = {"ms": ms, "gcups": b.cell_updates / (ms * 1e-3) / 1e9}
+        b.close()
+    return out, (chunks, templates, reads, ops, strands, tidx)
+
+
+def recursive_leg(ctx, chunks):
+    """copy_num = 8 chunks through the driver: clustering_recursive splits into <= 4, re-polishes every sub-cluster and
+    recurses (local_clustering/mod.rs:136-189).  Returns chunks/s and the pairwise agreement with the planted paralogs."""
+    from jtk_b200 import pipeline as P
+    from jtk_b200 import local_clustering as LC
+    gains = LC.Gains(gain=GAINS_EXPECTED.astype(np.float64), prob=GAINS_PROB)
+    cs = [P.Chunk(id=c + 1, seq=ch["template"].copy(), copy_num=8) for c, ch in enumerate(chunks)]
+    nodes = [P.Node(chunk=c + 1, seq=r, ops=o, is_forward=bool(s)) for c, ch in enumerate(chunks)
+             for r, o, s in zip(ch["reads"], ch["ops"], ch["strands"])]
+    ds = P.DataSet(selected_chunks=cs, nodes=nodes, read_type="ONT")
+    t0 = time.perf_counter()
+    P.local_clustering_selected(ds, {c.id for c in cs}, gains=gains, ctx=ctx, fit_models=False)
+    dt = time.perf_counter() - t0
+    rand = []
+    for c, ch in enumerate(chunks):
+        lab = np.array([n.cluster for n in ds.nodes if n.chunk == c + 1])
+        par = np.asarray(ch["paralog"])
+        same_l = lab[:, None] == lab[None, :]
+        same_p = par[:, None] == par[None, :]
+        iu = np.triu_indices(len(lab), 1)
+        rand.append(float((same_l[iu] == same_p[iu]).mean()))
+    return {"chunks": len(chunks), "seconds": dt, "chunks_per_s": len(chunks) / dt, "cluster_num": [int(c.cluster_num) for c in cs],
+            "rand_index_vs_paralogs": rand, "what": "copy_num 8, 240 reads per chunk: clustering_recursive (mod.rs:126-190) on one GPU"}
+
+
+def polish_fit_leg(ctx, templates, reads, ops, strands, tidx, n_chunks):
+    """BASELINE.json configs[4]: consensus polishing over the chunks of the region (drafts with 20 planted substitution errors
+    each, HMMPolishConfig(30, n, 0)) and the 10-round fit on 5 chunks (model_tune.rs:94-156); plus the window polish of a
+    contig stitched from the first chunks (consensus::polish, consensus/mod.rs:300-371)."""
+    from jtk_b200 import consensus as CS
+    from jtk_b200 import pipeline as P
+    from jtk_b200 import synth
+    from jtk_b200.hmm import HMMPolishConfig, PairHiddenMarkovModelOnStrands, polish_chunks
+    rng = np.random.default_rng(5)
+    models = PairHiddenMarkovModelOnStrands.default()
+    n_chunks = min(n_chunks, len(templates))
+    sel = [k for k in range(len(reads)) if int(tidx[k]) < n_chunks]
+    drafts = []
+    for c in range(n_chunks):
+        d = templates[c].copy()
+        pos = rng.choice(np.arange(5, len(d) - 5), size=20, replace=False)
+        d[pos] = synth.ACGT[(np.searchsorted(synth.ACGT, d[pos]) + rng.integers(1, 4, size=20)) % 4]
+        drafts.append(d)
+    t0 = time.perf_counter()
+    cons, _, iters = polish_chunks(models, drafts, [reads[k] for k in sel], [ops[k] for k in sel], [bool(strands[k]) for k in sel],
+                                   np.asarray([tidx[k] for k in sel], dtype=np.uint32), HMMPolishConfig.new(RADIUS, 60, 0), ctx=ctx)
+    dt = time.perf_counter() - t0
+    ident = [float((c == t).mean()) if len(c) == len(t) else 0.0 for c, t in zip(cons, templates[:n_chunks])]
+    out = {"polish": {"chunks": n_chunks, "seconds": dt, "chunks_per_s": n_chunks / dt, "iterations_mean": float(np.mean(iters)),
+                      "iterations_max": int(np.max(iters)), "identity_mean": float(np.mean(ident)), "identity_min": float(np.min(ident)),
+                      "what": "polish_until_converge_antidiagonal over all chunks in one batch, drafts with 20 substitution errors"}}
+    # fit: TRAIN_UNIT_SIZE = 5 chunks x TRAIN_ROUND = 10 rounds of (polish + Baum-Welch)
+    cs = [P.Chunk(id=c + 1, seq=templates[c].copy(), copy_num=2) for c in range(min(8, n_chunks))]
+    nodes = [P.Node(chunk=int(tidx[k]) + 1, seq=reads[k], ops=ops[k], is_forward=bool(strands[k])) for k in sel if int(tidx[k]) < len(cs)]
+    ds = P.DataSet(selected_chunks=cs, nodes=nodes, read_type="ONT")
+    t0 = time.perf_counter()
+    m = P.estimate_model_parameters_on_both_strands(ds, ctx=ctx)
+    out["fit"] = {"seconds": time.perf_counter() - t0, "rounds": 10, "chunks": 5, "mat_mat_forward": float(m.forward().as_array()[0]),
+                  "what": "estimate_model_parameters_on_both_strands (model_tune.rs:96-156)"}
+    # window polish of a contig (3 rounds, 2 000 bp windows, radius 50, coverage cap 50: assemble/mod.rs:186-195)
+    n_w = min(16, n_chunks)
+    truth = np.concatenate(templates[:n_w])
+    draft = np.concatenate(drafts[:n_w])
+    alns, off = [], np.concatenate([[0], np.cumsum([len(t) for t in templates[:n_w]])])
+    for k in sel:
+        c = int(tidx[k])
+        if c < n_w:
+            alns.append(CS.Alignment(query=reads[k], ops=ops[k], contig_start=int(off[c]), contig_end=int(off[c + 1]), is_forward=bool(strands[k])))
+    stats = {}
+    t0 = time.perf_counter()
+    pol = CS.polish(draft, alns, models, CS.PolishConfig(min_coverage=3, max_coverage=50, window_size=2000, radius=50, round_num=3),
+                    ctx=ctx, stats=stats)
+    dt = time.perf_counter() - t0
+    out["consensus_windows"] = {"windows": n_w, "rounds": stats.get("rounds"), "seconds": dt, "windows_per_s": 3 * n_w / dt,
+                                "identity": float((pol == truth).mean()) if len(pol) == len(truth) else 0.0,
+                                "what": "consensus::polish (consensus/mod.rs:300-371), all windows of a round in one batch"}
+    return out
 
 
 def workload_config(args):
@@ -284,7 +399,9 @@ def main():
     ap.add_argument("--reads", type=int, default=60)
     ap.add_argument("--length", type=int, default=2000)
     ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="pairs in the cpu_baseline sample (0: auto)")
-    ap.add_argument("--phase-chunks", type=int, default=80, help="chunks of the 'chunks phased per second' extra (0: skip)")
+    ap.add_argument("--phase-chunks", type=int, default=2000,
+                    help="chunks of the 'chunks phased per second' leg: BASELINE.json configs[2] scale, strong-scaled over the ranks (0: skip)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[3] / configs[4] legs (band sweep, recursive clustering, polish + fit)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -306,9 +423,15 @@ def main():
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    host_group = None
     if world > 1:
-        # every rank runs two encoder contexts (e2e leg): share the box's cores instead of 2 x world x all-cores threads
+        # the only exchange of the path is a HOST gather of per-chunk results: it runs over a gloo group, NCCL
+        # carries nothing but the timing reductions of this script
+        host_group = dist.new_group(backend="gloo")
+        # every rank runs two encoder contexts (e2e leg): share the box's cores instead of 2 x world x all-cores threads;
+        # the clustering threads of the phase leg get the rank's full share
         os.environ.setdefault("JTK_HOST_THREADS", str(max(2, (os.cpu_count() or 2) // (2 * world))))
+        os.environ.setdefault("JTK_CLUSTER_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
     ctx = _lib.Context(local_rank)
     fwd = _lib.HmmParams.from_buffer_copy(_default_params())
     rev = fwd
@@ -404,11 +527,20 @@ def main():
         e2e_ms = (time.perf_counter() - t1) * 1e3 / (2 * e2e_steps)
     ctx2.close()
 
-    # ---- chunks phased per second through the driver (extra; rank 0's GPU, host clustering on all cores) -----------
+    # ---- chunks phased per second through the driver: configs[2] scale, the SAME chunks on every rank, sharded ----------
     phased = None
     if args.phase_chunks > 0:
-        w0 = (templates, reads, ops, strands, tidx) if rank == 0 else make_workload(0, args.chunks, args.reads, args.length)
-        phased = phase_leg(ctx, *w0, min(args.phase_chunks, args.chunks), cov, rank=rank, world=world)
+        w0 = make_workload(0, args.phase_chunks, args.reads, args.length)   # rank-independent seed: every rank holds the region
+        phased = phase_leg(ctx, *w0, args.phase_chunks, cov, rank=rank, world=world, group=host_group)
+    # ---- configs[3] / configs[4] legs (rank 0's GPU; bounded samples) ------------------------------------------------------
+    extras = {}
+    if rank == 0 and not args.no_extras:
+        sweep, par = band_sweep_leg(ctx, fwd)
+        extras["band_sweep"] = sweep
+        extras["recursive_clustering"] = recursive_leg(ctx, par[0][:2])
+        extras["polish_fit"] = polish_fit_leg(ctx, templates, reads, ops, strands, tidx, args.chunks)
+    if world > 1:
+        dist.barrier(group=host_group)
 
     # ---- reduce over ranks ------------------------------------------------------------------------
     step_ms = dev_ms / args.steps
@@ -446,13 +578,17 @@ def main():
                 "hbm": {"algorithmic_bytes_per_launch": prof_bytes + in_bytes,
                         "achieved_gbs": (prof_bytes + in_bytes) / (k_ms * 1e-3) / 1e9,
                         "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src}}
-        # cpu baseline: bounded sample on this box's host cores
+        # cpu baseline: bounded sample on this box's host cores, one task per chunk like the reference's rayon fan-out, plus
+        # the single-thread figure (the reference's own benches pin num_threads(1), sandbox/src/bin/benchmark_clustering.rs:45-48)
         threads = os.cpu_count() or 1
-        n_sample = args.cpu_sample_pairs or len(reads)
-        cpu_s, cpu_cells = cpu_baseline_run(templates, reads, ops, strands, tidx, n_sample, threads, min_seconds=10.0)
+        n_sample = args.cpu_sample_pairs or min(len(reads), max(threads, 16) * args.reads)
+        cpu_s, cpu_cells = cpu_baseline_run(templates, reads, ops, strands, tidx, n_sample, threads, min_seconds=8.0)
+        one_s, one_cells = cpu_baseline_run(templates, reads, ops, strands, tidx, args.reads, 1, min_seconds=3.0)
         cpu = {"value": cpu_cells / cpu_s / 1e9, "unit": "GCUPS", "cores": threads, "kind": "port",
-               "sample": f"first {n_sample} pairs of rank 0's workload, repeated for {cpu_s:.1f} s, f64 oracle, "
-                         f"{threads} threads over pairs"}
+               "sample": f"the chunks of the first {n_sample} pairs of rank 0's workload, repeated for {cpu_s:.1f} s, f64 oracle "
+                         f"(scalar restatement, not kiley), one task per chunk on {threads} threads",
+               "mcups_per_thread": 1e3 * cpu_cells / cpu_s / 1e9 / threads,
+               "single_thread": {"value": one_cells / one_s / 1e9, "unit": "GCUPS", "sample": f"one chunk ({args.reads} pairs), {one_s:.1f} s"}}
         line = {
             "metric": "pair-HMM modification-table GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
@@ -464,13 +600,16 @@ def main():
                     "serial": {"value": tot_cells / (e2e_serial_ms * 1e-3) / 1e9, "ms_per_step": e2e_serial_ms,
                                "mode": "one host thread, one context"}},
             "gpu_launches": int(launches),
+            "chunks_per_s": phased["chunks_per_s"] if phased else None,
+            "chunks_per_s_note": (f"chunks phased per second: {phased['chunks']} chunks (configs[2] scale) through the whole per-chunk "
+                                  f"path, strong-scaled over {world} GPU(s), wall clock") if phased else None,
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
             "extra": {"chunks_per_s": world * args.chunks / (step_ms * 1e-3),
                       "pairs_per_s": world * len(reads) / (step_ms * 1e-3),
                       "wall_ms_per_step": wall_step,
                       "rows9": {"ms_per_step": ms9, "gcups": cells / (ms9 * 1e-3) / 1e9,
                                 "chunks_per_s": args.chunks / (ms9 * 1e-3), "note": "rank 0 only"},
-                      "chunks_phased": phased},
+                      "chunks_phased": phased, **extras},
         }
         print(json.dumps(line), flush=True)
     batch.close()

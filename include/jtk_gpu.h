@@ -213,8 +213,9 @@ typedef struct {
  *   reference call sites: local_clustering/mod.rs:106,155-156; model_tune.rs:143; consensus/mod.rs:477-483.
  * Every chunk c has a draft (draft_concat[draft_off[c]..draft_off[c+1])) and the reads p with tmpl_idx[p] == c, in
  * batch order.  Loop (the oracle's definition): modification tables of the first take_num
- * reads on the GPU, per-column sums on the GPU, greedy pick of positive-gain edits on the host, local patch of every
- * read's ops, until no chunk changes (<= 20 rounds).
+ * reads on the GPU, per-column sums and best rows on the GPU, left-to-right pick of the locally best positive-gain edits on
+ * the host (an edit is taken unless one of the next five columns gains more), local patch of every read's ops, until no
+ * chunk changes (<= 20 rounds).
  * ops are in/out: pair p owns ops_buf[ops_pos[p] .. ops_pos[p] + ops_cap[p]) and n_ops[p] holds its length.  On a non-zero
  * return ops_buf / n_ops / out_cons are UNDEFINED (some chunks may already be patched): the caller keeps its own copy if it
  * wants to continue after a failure; jtk_last_error(ctx) names the cause.
@@ -233,9 +234,10 @@ int jtk_polish_until_converge_batch(jtk_ctx *ctx, const jtk_hmm_params *fwd, con
 int jtk_batch_colsums(jtk_batch *b, int take_num, double *out, const uint64_t *stat_off);
 /* The per-column choice of the polish loop on the device: out[col_off[t] + j] = the row (0..13) with the largest gain summed
  * over the first take_num reads of template t, among the rows valid at column j (not the template's own base, within
- * ignore_edge of neither end) and above min_gain, or -1.  Same sums and tie-break (first maximum) as a host scan of
- * jtk_batch_colsums; tmpl_len[t] + 1 bytes per template. */
-int jtk_batch_best_edits(jtk_batch *b, int take_num, int ignore_edge, double min_gain, int8_t *out, const uint64_t *col_off);
+ * ignore_edge of neither end) and above min_gain, or -1; out_gain (may be NULL) receives that summed gain (0 where the row
+ * is -1).  Same sums and tie-break (first maximum) as a host scan of jtk_batch_colsums; tmpl_len[t] + 1 entries per template. */
+int jtk_batch_best_edits(jtk_batch *b, int take_num, int ignore_edge, double min_gain, int8_t *out, double *out_gain,
+                         const uint64_t *col_off);
 
 /* ---- HMM fit (K4) --------------------------------------------------------------------------------------- */
 /* Expected transition / emission counts of every pair of a batch under (fwd, rev), summed per strand:
@@ -351,6 +353,12 @@ JTK_STATIC_ASSERT(sizeof(jtk_clustering_config) == 24 && offsetof(jtk_clustering
 JTK_STATIC_ASSERT(sizeof(jtk_polish_config) == 12, "jtk_polish_config layout");
 /* sizeof() of the struct called `name` ("jtk_hmm_params", "jtk_colstat", ...) as this library was compiled; 0 = unknown name */
 size_t jtk_abi_sizeof(const char *name);
+
+/* Global alignment of `read` to `tmpl` (banded edit distance, band |i-j| <= radius + |Lr-Lt|; traceback prefers diagonal,
+ * Del, Ins): the host aligner behind consensus::global_align (haplotyper/src/consensus/mod.rs:424-436, edlib global mode in
+ * the reference) and the bootstrap guide of the likelihood call.  Writes one op per alignment column (<= Lt + Lr <= cap);
+ * returns the number of columns or a negative JTK_E* code (band cannot connect the corners). */
+int jtk_align_global(const uint8_t *tmpl, int Lt, const uint8_t *read, int Lr, int radius, uint8_t *out_ops, int cap);
 
 /* in-band cell count C = sum_d w(d) of one pair (SURVEY.md section 8d work unit); <0 if ops are invalid */
 int64_t jtk_band_cell_count(const uint8_t *ops, int n_ops, int Lt, int Lr, int radius);

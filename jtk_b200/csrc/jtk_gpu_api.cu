@@ -412,6 +412,21 @@ void jtk_ctx_destroy(jtk_ctx *ctx) {
     delete ctx;
 }
 
+// global alignment of a read to a (window of a) consensus: the library's banded edit-distance aligner (the guide of the
+// bootstrap likelihood) behind the call sites where the reference uses edlib in global mode
+// (haplotyper/src/consensus/mod.rs:424-436 `global_align`; edge cases as there: empty query -> all Del, empty target -> all Ins)
+int jtk_align_global(const uint8_t *tmpl, int Lt, const uint8_t *read, int Lr, int radius, uint8_t *out_ops, int cap) {
+    if (Lt < 0 || Lr < 0 || radius < 0 || !out_ops || (Lt > 0 && !tmpl) || (Lr > 0 && !read)) return JTK_EINVAL;
+    if (Lt + Lr > cap) return JTK_EINVAL;
+    if (Lr == 0) { std::memset(out_ops, JTK_OP_DEL, (size_t)Lt); return Lt; }
+    if (Lt == 0) { std::memset(out_ops, JTK_OP_INS, (size_t)Lr); return Lr; }
+    std::vector<uint8_t> ops;
+    std::vector<int> D;
+    if (!edit_ops(tmpl, Lt, read, Lr, radius, ops, D)) return JTK_EINVAL;
+    std::memcpy(out_ops, ops.data(), ops.size());
+    return (int)ops.size();
+}
+
 int64_t jtk_band_cell_count(const uint8_t *ops, int n_ops, int Lt, int Lr, int radius) {
     if (!ops || n_ops < 0 || Lt < 0 || Lr < 0 || radius < 0) return -1;
     int i = 0, j = 0;
@@ -1237,7 +1252,8 @@ __global__ void best_edit_kernel(const float *__restrict__ delta, const DevPair 
                                  const uint32_t *__restrict__ tp_start, const uint32_t *__restrict__ tp_ids,
                                  const uint32_t *__restrict__ tmpl_len, const uint8_t *__restrict__ codes,
                                  const uint32_t *__restrict__ tmpl_code_off, const unsigned long long *__restrict__ col_off,
-                                 int take, int ignore_edge, double min_gain, int8_t *__restrict__ out) {
+                                 int take, int ignore_edge, double min_gain, int8_t *__restrict__ out,
+                                 double *__restrict__ out_gain) {
     __shared__ ReadRef rr[kReadTile];
     const int t = blockIdx.y;
     const int L = (int)tmpl_len[t];
@@ -1273,6 +1289,7 @@ __global__ void best_edit_kernel(const float *__restrict__ delta, const DevPair 
         }
     }
     out[col_off[t] + j] = (int8_t)best;
+    if (out_gain) out_gain[col_off[t] + j] = best >= 0 ? bg : 0.0;
 }
 
 } // namespace
@@ -1400,9 +1417,24 @@ int jtk_mcmc_restarts_batch(jtk_ctx *ctx, int n_chains, const double *data_conca
     CU(cudaMemcpyAsync(ctx->d_mc_f64.p, wf.data(), sizeof(double) * f64, cudaMemcpyHostToDevice, st), "H2D mcmc data");
     CU(cudaMemcpyAsync(ctx->d_mc_asn_off.p, asn_off.data(), sizeof(uint64_t) * (size_t)n_chains, cudaMemcpyHostToDevice, st), "H2D mcmc offsets");
     CU(cudaMemcpyAsync(ctx->d_mc_rng.p, rng_state, sizeof(uint64_t) * 4 * (size_t)n_chains, cudaMemcpyHostToDevice, st), "H2D mcmc rng");
-    CU(launch_mcmc_restarts(ctx->d_mc_chains.p, n_chains, ctx->d_mc_f64.p, ctx->d_mc_u8.p, ctx->d_mc_rng.p, ctx->d_mc_asn.p,
-                            ctx->d_mc_asn_off.p, ctx->d_mc_lk.p, ctx->d_mc_err.p, restarts, smem, st), "mcmc launch");
-    ctx->launches++;
+    // chain indices grouped by kernel class, each group sorted by read count (the groups of a warp then run the same trip counts)
+    std::vector<int> ids((size_t)n_chains);
+    int class_count[5] = { 0, 0, 0, 0, 0 };
+    {
+        std::vector<int> cls((size_t)n_chains);
+        for (int c = 0; c < n_chains; c++) { cls[(size_t)c] = mcmc_class_of(n_rows[c], n_cols[c], n_clusters[c]); class_count[cls[(size_t)c]]++; }
+        for (int c = 0; c < n_chains; c++) ids[(size_t)c] = c;
+        std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) {
+            if (cls[(size_t)a] != cls[(size_t)b]) return cls[(size_t)a] < cls[(size_t)b];
+            return n_rows[a] < n_rows[b];
+        });
+    }
+    CU(ctx->d_mc_u32.reserve((size_t)n_chains), "cudaMalloc mcmc ids");
+    CU(cudaMemcpyAsync(ctx->d_mc_u32.p, ids.data(), sizeof(int) * (size_t)n_chains, cudaMemcpyHostToDevice, st), "H2D mcmc ids");
+    CU(launch_mcmc_restarts(ctx->d_mc_chains.p, chains.data(), reinterpret_cast<const int *>(ctx->d_mc_u32.p), ids.data(), class_count, n_chains,
+                            ctx->d_mc_f64.p, ctx->d_mc_u8.p, ctx->d_mc_rng.p, ctx->d_mc_asn.p, ctx->d_mc_asn_off.p, ctx->d_mc_lk.p,
+                            ctx->d_mc_err.p, restarts, smem, st), "mcmc launch");
+    for (int c = 0; c < 5; c++) ctx->launches += class_count[c] > 0 ? 1 : 0;
     CU(cudaMemcpyAsync(rng_state, ctx->d_mc_rng.p, sizeof(uint64_t) * 4 * (size_t)n_chains, cudaMemcpyDeviceToHost, st), "D2H mcmc rng");
     CU(cudaMemcpyAsync(out_asn, ctx->d_mc_asn.p, asn, cudaMemcpyDeviceToHost, st), "D2H mcmc assignments");
     CU(cudaMemcpyAsync(out_lk, ctx->d_mc_lk.p, sizeof(double) * (size_t)n_chains, cudaMemcpyDeviceToHost, st), "D2H mcmc lk");
@@ -1715,7 +1747,8 @@ int jtk_batch_colsums(jtk_batch *b, int take_num, double *out, const uint64_t *s
     return batch_sync(b);
 }
 
-int jtk_batch_best_edits(jtk_batch *b, int take_num, int ignore_edge, double min_gain, int8_t *out, const uint64_t *col_off) {
+int jtk_batch_best_edits(jtk_batch *b, int take_num, int ignore_edge, double min_gain, int8_t *out, double *out_gain,
+                         const uint64_t *col_off) {
     if (!b) return JTK_EINVAL;
     jtk_ctx *ctx = b->ctx;
     if (!out || !col_off || take_num < 0 || ignore_edge < 0) return ctx->fail(JTK_EINVAL, "bad argument");
@@ -1727,14 +1760,16 @@ int jtk_batch_best_edits(jtk_batch *b, int take_num, int ignore_edge, double min
     for (int t = 0; t < b->n_tmpl; t++) total = std::max<uint64_t>(total, col_off[t] + (uint64_t)b->tmpl_len[t] + 1);
     CU(b->d_stat_off.reserve((size_t)b->n_tmpl), "cudaMalloc col_off");
     CU(ctx->d_mc_asn.reserve((size_t)total), "cudaMalloc best edits");
+    if (out_gain) CU(ctx->d_gather.reserve((size_t)total), "cudaMalloc best gains");
     CU(b->up_stat_off.put(b->d_stat_off.p, col_off, sizeof(uint64_t) * (size_t)b->n_tmpl, st), "H2D col_off");
     dim3 grid((unsigned)((b->max_lt + 1 + 127) / 128), (unsigned)b->n_tmpl);
     best_edit_kernel<<<grid, 128, 0, st>>>(b->d_delta.p, b->d_pairs.p, b->d_tp_start.p, b->d_tp_ids.p, b->d_tmpl_len.p, b->d_codes.p,
                                            b->d_tmpl_code_off.p, b->d_stat_off.p, take_num, ignore_edge, min_gain,
-                                           reinterpret_cast<int8_t *>(ctx->d_mc_asn.p));
+                                           reinterpret_cast<int8_t *>(ctx->d_mc_asn.p), out_gain ? ctx->d_gather.p : nullptr);
     CU(cudaGetLastError(), "best_edit launch");
     ctx->launches++;
     CU(cudaMemcpyAsync(out, ctx->d_mc_asn.p, (size_t)total, cudaMemcpyDeviceToHost, st), "D2H best edits");
+    if (out_gain) CU(cudaMemcpyAsync(out_gain, ctx->d_gather.p, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, st), "D2H best gains");
     return batch_sync(b);
 }
 

@@ -93,6 +93,7 @@ constexpr unsigned kFullMask = 0xffffffffu;
 
 struct ChainView {
     uint32_t n, D, k;
+    uint32_t ld;                                             // row stride of flat (doubles): D, or the padded width of the sub-warp kernel
     const double *flat; const double *size_to_lk;          // global, read-only
     const uint8_t *pinc, *ninc, *ratio_ok;                   // global, written once at start
     double *centers, *dists, *cum; uint32_t *counts;         // shared: k-means scratch (lane 0)
@@ -109,7 +110,7 @@ __device__ void update_assignments(const ChainView &c, uint32_t n_centers) { // 
     for (uint32_t i = 0; i < c.n; i++) {
         uint32_t best = 0; double bd = 0.0;
         for (uint32_t m = 0; m < n_centers; m++) {
-            const double d = dist2(c.flat + (size_t)i * c.D, c.centers + (size_t)m * c.D, c.D);
+            const double d = dist2(c.flat + (size_t)i * c.ld, c.centers + (size_t)m * c.D, c.D);
             if (m == 0 || d < bd) { best = m; bd = d; }
         }
         c.assign[i] = (uint8_t)best;
@@ -118,7 +119,7 @@ __device__ void update_assignments(const ChainView &c, uint32_t n_centers) { // 
 
 __device__ double get_dist(const ChainView &c) {
     double s = 0.0;
-    for (uint32_t i = 0; i < c.n; i++) s = __dadd_rn(s, dist2(c.flat + (size_t)i * c.D, c.centers + (size_t)c.assign[i] * c.D, c.D));
+    for (uint32_t i = 0; i < c.n; i++) s = __dadd_rn(s, dist2(c.flat + (size_t)i * c.ld, c.centers + (size_t)c.assign[i] * c.D, c.D));
     return s;
 }
 
@@ -129,13 +130,13 @@ __device__ int kmeans(const ChainView &c, DevRng &rng) {
         for (uint32_t i = 0; i < n; i++) c.assign[i] = (uint8_t)rng.gen_range(k);
     } else { // suggest_first: k-means++ seeding, centres are data rows
         const uint32_t first = (uint32_t)rng.gen_index(n);
-        for (uint32_t d = 0; d < D; d++) c.centers[d] = c.flat[(size_t)first * D + d];
+        for (uint32_t d = 0; d < D; d++) c.centers[d] = c.flat[(size_t)first * c.ld + d];
         for (uint32_t it = 0; it + 1 < k; it++) {
             const uint32_t nc = it + 1;
             for (uint32_t i = 0; i < n; i++) {
                 double m = 0.0;
                 for (uint32_t q = 0; q < nc; q++) {
-                    const double d = dist2(c.flat + (size_t)i * D, c.centers + (size_t)q * D, D);
+                    const double d = dist2(c.flat + (size_t)i * c.ld, c.centers + (size_t)q * D, D);
                     if (q == 0 || d < m) m = d;
                 }
                 c.dists[i] = m;
@@ -155,7 +156,7 @@ __device__ int kmeans(const ChainView &c, DevRng &rng) {
                 const uint32_t mid = lo + (hi - lo) / 2;
                 if (c.cum[mid] <= chosen) lo = mid + 1; else hi = mid;
             }
-            for (uint32_t d = 0; d < D; d++) c.centers[(size_t)nc * D + d] = c.flat[(size_t)lo * D + d];
+            for (uint32_t d = 0; d < D; d++) c.centers[(size_t)nc * D + d] = c.flat[(size_t)lo * c.ld + d];
         }
         update_assignments(c, k);
     }
@@ -167,7 +168,7 @@ __device__ int kmeans(const ChainView &c, DevRng &rng) {
         for (uint32_t m = 0; m < k; m++) c.counts[m] = 0;
         for (uint32_t i = 0; i < n; i++) {
             const uint32_t a = c.assign[i];
-            for (uint32_t d = 0; d < D; d++) c.centers[(size_t)a * D + d] = __dadd_rn(c.centers[(size_t)a * D + d], c.flat[(size_t)i * D + d]);
+            for (uint32_t d = 0; d < D; d++) c.centers[(size_t)a * D + d] = __dadd_rn(c.centers[(size_t)a * D + d], c.flat[(size_t)i * c.ld + d]);
             c.counts[a]++;
         }
         for (uint32_t m = 0; m < k; m++)
@@ -314,17 +315,18 @@ __device__ __forceinline__ int mcmc_with_filter(const ChainView &c, DevRng &rng,
 
 // One warp per chain.  rng_state: 4 words per chain, in/out.  out_asn: best assignment (bytes, n per chain at asn_off),
 // out_lk: its likelihood, out_err: 0 or the first failure.  Dynamic shared memory: smem_per_chain bytes per warp.
-__global__ void __launch_bounds__(128, 4) mcmc_restarts_kernel(const McmcChain *__restrict__ chains, int n_chains, double *wf64,
+__global__ void __launch_bounds__(128, 4) mcmc_restarts_kernel(const McmcChain *__restrict__ chains, const int *__restrict__ ids, int n_chains, double *wf64,
                                                             uint8_t *wu8, uint64_t *rng_state, uint8_t *out_asn,
                                                             const uint64_t *__restrict__ asn_off, double *out_lk, int *out_err,
                                                             int restarts, int smem_per_chain) {
     extern __shared__ __align__(16) unsigned char mcmc_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int chain = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (chain >= n_chains) return;
+    const int slot = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (slot >= n_chains) return;
+    const int chain = ids[slot];
     const McmcChain ch = chains[chain];
     ChainView c;
-    c.n = ch.n; c.D = ch.D; c.k = ch.k;
+    c.n = ch.n; c.D = ch.D; c.k = ch.k; c.ld = ch.D;
     const double *f = wf64 + ch.off_f64;
     c.flat = f; c.size_to_lk = f + (size_t)c.n * c.D;
     uint8_t *b = wu8 + ch.off_u8;
@@ -385,22 +387,279 @@ __global__ void __launch_bounds__(128, 4) mcmc_restarts_kernel(const McmcChain *
     for (uint32_t i = lane; i < c.n; i += 32) oa[i] = c.best[i];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Two clusters, at most eight variant columns (every diploid chunk: D <= 3 * max(copy_num, 2) = 6): FOUR chains per warp,
+// eight lanes each, everything a proposal touches in shared memory, and a proposal latency of a few hundred cycles instead
+// of ~2 000.  Same stream, same decisions, same f64 sums in the same order as mcmc_with_filter<2> above / the host twin:
+//   * lane g of a group owns column g (columns >= D hold +0.0 and are never in use: adding +0.0 is exact, so the sums run
+//     over the padded width DP without a branch);
+//   * flip = `tot0 += s; tot1 -= s` with s = -x or x by the old cluster (a - b == a + (-b) exactly); the reject path
+//     replays the reference's flip back (the round trip (a - x) + x is not the identity in floating point);
+//   * the per-column terms of get_lk go through a double-buffered shared-memory exchange: one group barrier per proposal,
+//     then every lane adds the 2 + 2*DP terms in the reference's order;
+//   * the acceptance draw `next_u64() < trunc(exp(diff) * 2^64)` is decided from a cheap bracket of exp(diff) (ex2.approx,
+//     relative error < 1e-5, bracket +-1e-4) whenever the draw falls outside the bracket -- which is all but ~1e-4 of the
+//     time; only then is the correctly rounded exp evaluated.  The decision is the reference's in every case.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSubLanes = 8;
+struct SubLayout { // byte offsets inside one chain's shared-memory block
+    uint32_t x, cl, s2l, ratio, assign, argmax, best, xch, centers, dists, cum, counts, total, rwords;
+};
+__host__ __device__ inline SubLayout sub_layout(uint32_t n, uint32_t DP) {
+    SubLayout L;
+    uint32_t o = 0;
+    auto take = [&](uint32_t bytes) { const uint32_t at = o; o += (bytes + 15u) & ~15u; return at; };
+    L.rwords = (n + 1 + 31) / 32;
+    L.x = take(8u * n * DP);
+    L.s2l = take(8u * (n + 1));
+    L.xch = take(8u * 2 * 2 * DP);
+    L.centers = take(8u * 2 * DP);
+    L.dists = take(8u * n);
+    L.cum = take(8u * n);
+    L.ratio = take(4u * (n + 1) * L.rwords);
+    L.counts = take(16);
+    L.cl = take(n * DP);
+    L.assign = take(n);
+    L.argmax = take(n);
+    L.best = take(n);
+    L.total = o;
+    return L;
+}
+
+template <int DP>
+__global__ void __launch_bounds__(128, 2) mcmc_diploid_kernel(const McmcChain *__restrict__ chains, const int *__restrict__ ids,
+                                                              int n_ids, const double *__restrict__ wf64, uint64_t *rng_state,
+                                                              uint8_t *out_asn, const uint64_t *__restrict__ asn_off,
+                                                              double *out_lk, int *out_err, int restarts, int smem_per_chain) {
+    extern __shared__ __align__(16) unsigned char mcmc_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane & (kSubLanes - 1), grp = lane / kSubLanes, lead = grp * kSubLanes;
+    const unsigned gmask = 0xffu << lead;
+    const int slot = (blockIdx.x * (blockDim.x >> 5) + warp) * (32 / kSubLanes) + grp;
+    if (slot >= n_ids) return; // the eight lanes of a group leave together
+    const int chain = ids[slot];
+    const McmcChain ch = chains[chain];
+    const uint32_t n = ch.n, D = ch.D;
+    unsigned char *sm = mcmc_smem + (size_t)(warp * (32 / kSubLanes) + grp) * smem_per_chain;
+    const SubLayout L = sub_layout(n, DP);
+    double *X = reinterpret_cast<double *>(sm + L.x);
+    double *S2L = reinterpret_cast<double *>(sm + L.s2l);
+    double *XCH = reinterpret_cast<double *>(sm + L.xch);
+    uint32_t *RAT = reinterpret_cast<uint32_t *>(sm + L.ratio);
+    uint8_t *CL = sm + L.cl;
+    const uint32_t RW = L.rwords;
+    ChainView c;
+    c.n = n; c.D = D; c.k = 2; c.ld = DP;
+    c.flat = X; c.size_to_lk = S2L; c.pinc = nullptr; c.ninc = nullptr; c.ratio_ok = nullptr;
+    c.centers = reinterpret_cast<double *>(sm + L.centers);
+    c.dists = reinterpret_cast<double *>(sm + L.dists);
+    c.cum = reinterpret_cast<double *>(sm + L.cum);
+    c.counts = reinterpret_cast<uint32_t *>(sm + L.counts);
+    c.assign = sm + L.assign; c.argmax = sm + L.argmax; c.best = sm + L.best;
+    { // stage the chain: data (padded to DP columns), sign classes, size prior, the is_informative ratio table as bits
+        const double *f = wf64 + ch.off_f64;
+        for (uint32_t e = g; e < n * DP; e += kSubLanes) {
+            const uint32_t i = e / DP, d = e % DP;
+            const double x = d < D ? f[(size_t)i * D + d] : 0.0;
+            X[e] = x;
+            CL[e] = (uint8_t)((kPosThr < x ? 1 : 0) | ((!(kPosThr < x) && x < -kPosThr) ? 2 : 0));
+        }
+        for (uint32_t i = g; i <= n; i += kSubLanes) S2L[i] = f[(size_t)n * D + i];
+        for (uint32_t e = g; e < (n + 1) * RW; e += kSubLanes) {
+            const uint32_t p = e / RW, w = e % RW;
+            uint32_t bits = 0;
+            for (uint32_t b = 0; b < 32; b++) {
+                const uint32_t q = w * 32 + b;
+                if (q + p <= n && 0.70 < __ddiv_rn((double)p, __dadd_rn((double)(p + q), 0.0000001))) bits |= 1u << b;
+            }
+            RAT[e] = bits;
+        }
+    }
+    __syncwarp(gmask);
+    DevRng rng{ rng_state[4 * chain], rng_state[4 * chain + 1], rng_state[4 * chain + 2], rng_state[4 * chain + 3] };
+    const bool col = (uint32_t)g < D;
+    auto ratio_ok = [&](uint32_t p, uint32_t q) -> unsigned { return (RAT[p * RW + (q >> 5)] >> (q & 31u)) & 1u; };
+    // column statistics of the two clusters (lane g: column g) and the cluster sizes (every lane)
+    double tot0, tot1; uint32_t np0, np1, nn0, nn1, c0, c1;
+    auto build = [&]() {
+        tot0 = tot1 = 0.0; np0 = np1 = nn0 = nn1 = c0 = c1 = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t a = c.assign[i];
+            const double x = X[i * DP + g];
+            const uint32_t cl = CL[i * DP + g];
+            if (a == 0) { c0++; tot0 = __dadd_rn(tot0, x); np0 += cl & 1u; nn0 += cl >> 1; }
+            else { c1++; tot1 = __dadd_rn(tot1, x); np1 += cl & 1u; nn1 += cl >> 1; }
+        }
+    };
+    unsigned buf = 0;
+    auto current_lk = [&]() -> double { // get_lk (:785-795) with get_used_columns (:847-869)
+        const bool pos0 = 0.0 < tot0, pos1 = 0.0 < tot1;
+        const unsigned u = ((unsigned)pos0 & ratio_ok(np0, nn0)) | ((unsigned)pos1 & ratio_ok(np1, nn1));
+        const uint32_t in_use = (pos0 ? np0 : 0u) + (pos1 ? np1 : 0u);
+        const uint32_t in_neg = ((tot0 <= 0.0) ? np0 : 0u) + ((tot1 <= 0.0) ? np1 : 0u);
+        const bool use = col && u != 0u && 2u * in_neg < in_use; // the reference compares the same integers as f64
+        double *T = XCH + buf * (2 * DP);
+        buf ^= 1u;
+        T[g] = use ? (tot0 < 0.0 ? 0.0 : tot0) : 0.0;
+        T[DP + g] = use ? (tot1 < 0.0 ? 0.0 : tot1) : 0.0;
+        __syncwarp(gmask);
+        double lk = __dadd_rn(S2L[c0], S2L[c1]);
+#pragma unroll
+        for (int d = 0; d < 2 * DP; d++) lk = __dadd_rn(lk, T[d]);
+        return lk;
+    };
+    double best_lk = 0.0;
+    bool any = false;
+    int err = kMcmcOk;
+    for (int t = 0; t < restarts && err == kMcmcOk; t++) { // mcmc_clustering (:649-670): max_by keeps the last maximum
+        if (g == 0) err = kmeans(c, rng);
+        __syncwarp(gmask);
+        err = __shfl_sync(gmask, err, lead);
+        rng.s0 = __shfl_sync(gmask, rng.s0, lead); rng.s1 = __shfl_sync(gmask, rng.s1, lead);
+        rng.s2 = __shfl_sync(gmask, rng.s2, lead); rng.s3 = __shfl_sync(gmask, rng.s3, lead);
+        if (err != kMcmcOk) break;
+        // ---- mcmc_with_filter (:704-762), k = 2 ----
+        build();
+        double lk = current_lk();
+        double mx = lk;
+        for (uint32_t i = g; i < n; i += kSubLanes) c.argmax[i] = c.assign[i];
+        const uint64_t total = 2000ull * n;
+        for (uint64_t it = 0; it < total; it++) {
+            const uint32_t idx = (uint32_t)rng.gen_range(n);
+            const uint32_t old = c.assign[idx];
+            // choose_other(2, old): one candidate, gen_index(1) draws 32-bit words until one is <= 0x7fffffff
+            while (rng.next_u32() > 0x7fffffffu) { }
+            const double x = X[idx * DP + g];
+            const uint32_t cl = CL[idx * DP + g];
+            const double s = old == 0u ? -x : x;
+            const int dp = old == 0u ? -(int)(cl & 1u) : (int)(cl & 1u);
+            const int dn = old == 0u ? -(int)(cl >> 1) : (int)(cl >> 1);
+            const int dc = old == 0u ? -1 : 1;
+            tot0 = __dadd_rn(tot0, s); tot1 = __dadd_rn(tot1, -s);      // flip (:764-783)
+            np0 += dp; np1 -= dp; nn0 += dn; nn1 -= dn; c0 += dc; c1 -= dc;
+            const double proposed = current_lk();
+            const double diff = __dsub_rn(proposed, lk);
+            bool accept;
+            if (0.0 < diff) accept = true;
+            else if (diff < -45.0) { (void)rng.next_u64(); accept = false; } // threshold 0: the draw is consumed, never accepted
+            else {
+                bool decided = false;
+                accept = false;
+                uint64_t r = 0;
+                if (diff < -0.001) { // exp(diff) < 1: exactly one draw, compared with trunc(exp(diff) * 2^64)
+                    r = rng.next_u64();
+                    float pf;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pf) : "f"((float)diff * 1.4426950408889634f));
+                    const double rh = (double)(uint32_t)(r >> 32);
+                    const double ub = __dadd_rn(__dmul_rn((double)(pf * 1.0001f), 4294967296.0), 2.0);
+                    const double lb = __dadd_rn(__dmul_rn((double)(pf * 0.9999f), 4294967296.0), -2.0);
+                    if (rh >= ub) { decided = true; accept = false; }
+                    else if (__dadd_rn(rh, 1.0) <= lb) { decided = true; accept = true; }
+                }
+                if (!decided) {
+                    const double p = exp(diff);
+                    if (p == 1.0) accept = true;                            // Bernoulli ALWAYS_TRUE: no draw
+                    else if (!(p >= 0.0 && p < 1.0)) { err = kMcmcBadProb; break; } // NaN: the reference panics
+                    else {
+                        if (!(diff < -0.001)) r = rng.next_u64();
+                        accept = r < __double2ull_rz(__dmul_rn(p, 18446744073709551616.0));
+                    }
+                }
+            }
+            if (accept) {
+                c.assign[idx] = (uint8_t)(1u - old); // every lane of the group stores the same byte: no barrier needed to read it back
+                lk = proposed;
+                if (mx < lk) {
+                    mx = proposed;
+                    for (uint32_t i = g; i < n; i += kSubLanes) c.argmax[i] = c.assign[i];
+                }
+            } else { // flip back: the same subtraction / addition the reference performs
+                tot0 = __dadd_rn(tot0, -s); tot1 = __dadd_rn(tot1, s);
+                np0 -= dp; np1 += dp; nn0 -= dn; nn1 += dn; c0 -= dc; c1 += dc;
+            }
+        }
+        if (err != kMcmcOk) break;
+        __syncwarp(gmask);
+        for (uint32_t i = g; i < n; i += kSubLanes) c.assign[i] = c.argmax[i];
+        __syncwarp(gmask);
+        build();
+        const double chk = current_lk();
+        if (!(fabs(__dsub_rn(mx, chk)) < 0.0001)) { err = kMcmcLkMismatch; break; }
+        if (!any || !(mx < best_lk)) { for (uint32_t i = g; i < n; i += kSubLanes) c.best[i] = c.assign[i]; best_lk = mx; any = true; }
+        __syncwarp(gmask);
+    }
+    __syncwarp(gmask);
+    if (g == 0) {
+        rng_state[4 * chain] = rng.s0; rng_state[4 * chain + 1] = rng.s1; rng_state[4 * chain + 2] = rng.s2; rng_state[4 * chain + 3] = rng.s3;
+        out_lk[chain] = best_lk;
+        out_err[chain] = err;
+    }
+    uint8_t *oa = out_asn + asn_off[chain];
+    for (uint32_t i = g; i < n; i += kSubLanes) oa[i] = c.best[i];
+}
+
 size_t mcmc_smem_bytes(uint32_t n, uint32_t D, uint32_t k) {
     return (sizeof(double) * ((size_t)k * D + 2 * (size_t)n) + sizeof(uint32_t) * ((k + 1) & ~1u) + 3 * (size_t)n + 15) & ~(size_t)15;
 }
 
-cudaError_t launch_mcmc_restarts(const McmcChain *chains, int n_chains, double *wf64, uint8_t *wu8, uint64_t *rng_state,
+template <int DP>
+static cudaError_t launch_diploid(const McmcChain *chains, const int *ids, int n_ids, uint32_t n_max, const double *wf64, uint64_t *rng_state,
+                                  uint8_t *out_asn, const uint64_t *asn_off, double *out_lk, int *out_err, int restarts, cudaStream_t st) {
+    const size_t per_chain = sub_layout(n_max, DP).total;
+    int warps = 4;
+    while (warps > 1 && (size_t)warps * (32 / kSubLanes) * per_chain > 110 * 1024) warps >>= 1; // two CTAs per SM when they fit
+    const size_t dyn = (size_t)warps * (32 / kSubLanes) * per_chain;
+    if (dyn > 220 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(mcmc_diploid_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+    const int per_cta = warps * (32 / kSubLanes);
+    mcmc_diploid_kernel<DP><<<(n_ids + per_cta - 1) / per_cta, warps * 32, dyn, st>>>(chains, ids, n_ids, wf64, rng_state, out_asn, asn_off,
+                                                                                       out_lk, out_err, restarts, (int)per_chain);
+    return cudaGetLastError();
+}
+
+// Chains with two clusters and at most eight columns (class_of >= 0) go to the sub-warp kernel of their padded width;
+// everything else runs one warp per chain.  ids: device array of n_chains ints, the chain indices grouped by class
+// (class_count[c] of them for class c = 0..4: widths 2, 4, 6, 8, then the general kernel), each group sorted by read count.
+int mcmc_class_of(uint32_t n, uint32_t D, uint32_t k) {
+    if (k != 2 || D > 8 || n > 255) return 4;
+    return (int)((D + 1) / 2) - 1;
+}
+
+cudaError_t launch_mcmc_restarts(const McmcChain *chains, const McmcChain *host_chains, const int *ids, const int *host_ids,
+                                 const int class_count[5], int n_chains, double *wf64, uint8_t *wu8, uint64_t *rng_state,
                                  uint8_t *out_asn, const uint64_t *asn_off, double *out_lk, int *out_err, int restarts,
                                  size_t smem_per_chain, cudaStream_t st) {
     if (n_chains <= 0) return cudaSuccess;
-    int warps = 4;
-    while (warps > 1 && warps * smem_per_chain > 200 * 1024) warps >>= 1;
-    const size_t dyn = warps * smem_per_chain;
-    cudaError_t e = cudaFuncSetAttribute(mcmc_restarts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    if (e != cudaSuccess) return e;
-    mcmc_restarts_kernel<<<(n_chains + warps - 1) / warps, warps * 32, dyn, st>>>(chains, n_chains, wf64, wu8, rng_state, out_asn, asn_off,
+    int at = 0;
+    for (int cls = 0; cls < 4; cls++) {
+        const int cnt = class_count[cls];
+        if (cnt > 0) {
+            uint32_t n_max = 0;
+            for (int q = 0; q < cnt; q++) n_max = n_max > host_chains[host_ids[at + q]].n ? n_max : host_chains[host_ids[at + q]].n;
+            cudaError_t e = cudaSuccess;
+            switch (cls) {
+            case 0: e = launch_diploid<2>(chains, ids + at, cnt, n_max, wf64, rng_state, out_asn, asn_off, out_lk, out_err, restarts, st); break;
+            case 1: e = launch_diploid<4>(chains, ids + at, cnt, n_max, wf64, rng_state, out_asn, asn_off, out_lk, out_err, restarts, st); break;
+            case 2: e = launch_diploid<6>(chains, ids + at, cnt, n_max, wf64, rng_state, out_asn, asn_off, out_lk, out_err, restarts, st); break;
+            default: e = launch_diploid<8>(chains, ids + at, cnt, n_max, wf64, rng_state, out_asn, asn_off, out_lk, out_err, restarts, st); break;
+            }
+            if (e != cudaSuccess) return e;
+        }
+        at += cnt;
+    }
+    const int rest = class_count[4];
+    if (rest > 0) {
+        int warps = 4;
+        while (warps > 1 && warps * smem_per_chain > 200 * 1024) warps >>= 1;
+        const size_t dyn = warps * smem_per_chain;
+        cudaError_t e = cudaFuncSetAttribute(mcmc_restarts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return e;
+        mcmc_restarts_kernel<<<(rest + warps - 1) / warps, warps * 32, dyn, st>>>(chains, ids + at, rest, wf64, wu8, rng_state, out_asn, asn_off,
                                                                                    out_lk, out_err, restarts, (int)smem_per_chain);
-    return cudaGetLastError();
+        return cudaGetLastError();
+    }
+    return cudaSuccess;
 }
 
 } // namespace jtk

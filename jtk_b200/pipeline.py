@@ -94,14 +94,24 @@ def nonmatch_columns(node: Node, chunk: Chunk) -> int:
     return int(r)
 
 
-def pileup_nodes(ds: DataSet, selection: Set[int]) -> Dict[int, Tuple[List[Node], Chunk]]:
-    """mod.rs:33-53: nodes per selected chunk, cleanest alignments first (stable sort, as sort_by_cached_key).  The sort
-    keys of all nodes come from ONE call (jtk_lc_nonmatch_columns_batch)."""
+def group_nodes(ds: DataSet, selection: Set[int]) -> Dict[int, Tuple[List[Node], Chunk]]:
+    """The grouping half of pileup_nodes (mod.rs:33-46): nodes per selected chunk in read order, not yet sorted."""
     pile: Dict[int, Tuple[List[Node], Chunk]] = {c.id: ([], c) for c in ds.selected_chunks if c.id in selection}
     for n in ds.nodes:
         if n.chunk in pile:
             pile[n.chunk][0].append(n)
-    cids = [cid for cid, (nodes, _) in pile.items() if nodes]
+    return pile
+
+
+def pileup_nodes(ds: DataSet, selection: Set[int], pile: Optional[Dict[int, Tuple[List[Node], Chunk]]] = None,
+                 only: Optional[Iterable[int]] = None) -> Dict[int, Tuple[List[Node], Chunk]]:
+    """mod.rs:33-53: nodes per selected chunk, cleanest alignments first (stable sort, as sort_by_cached_key).  The sort
+    keys of all nodes come from ONE call (jtk_lc_nonmatch_columns_batch).  `pile` / `only`: sort just these chunks of an
+    existing grouping (a rank sorts the pile-ups it will process, not everybody's)."""
+    if pile is None:
+        pile = group_nodes(ds, selection)
+    wanted = set(only) if only is not None else None
+    cids = [cid for cid, (nodes, _) in pile.items() if nodes and (wanted is None or cid in wanted)]
     if not cids:
         return pile
     flat = [n for cid in cids for n in pile[cid][0]]
@@ -390,12 +400,14 @@ def local_clustering_selected(ds: DataSet, selection: Iterable[int], gains: Opti
         from .likelihood_gains import estimate_gain_default
         gains = estimate_gain_default(hmm, ctx=ctx)
     coverage = float(ds.coverage)
-    pile = {cid: pc for cid, pc in pileup_nodes(ds, selection).items() if pc[0]}
+    pile = {cid: pc for cid, pc in group_nodes(ds, selection).items() if pc[0]}
     ids = sorted(pile)
-    weights = [scheduler.chunk_weight(len(pile[c][0]), len(pile[c][1].seq), float(np.mean([len(n.seq) for n in pile[c][0]])),
+    weights = [scheduler.chunk_weight(len(pile[c][0]), len(pile[c][1].seq),
+                                      sum(len(n.seq) for n in pile[c][0]) / len(pile[c][0]),
                                       band_width(ds.read_type, len(pile[c][1].seq)) // 2) for c in ids]
 
     def process(my_ids: List[int]) -> Dict[int, tuple]:
+        pileup_nodes(ds, selection, pile=pile, only=my_ids)   # the sort of mod.rs:47-50, for this rank's chunks only
         return _cluster_pileups(ctx, hmm, gains, coverage, ds.read_type, {c: pile[c] for c in my_ids})
 
     merged = scheduler.run_sharded(ids, weights, process, rank, world, group=group)
@@ -420,11 +432,12 @@ LAST_TIMING: Dict[str, float] = {}  # seconds spent in the phases of the last _c
 def host_threads() -> int:
     """Threads of the per-chunk host loops (k-means / MCMC): the reference's rayon pool (`-t`, cli/src/bin/jtk.rs:396-408)."""
     import os
-    return max(1, min(int(os.environ.get("JTK_HOST_THREADS", os.cpu_count() or 1)), 64))
+    v = os.environ.get("JTK_CLUSTER_THREADS") or os.environ.get("JTK_HOST_THREADS") or (os.cpu_count() or 1)
+    return max(1, min(int(v), 64))
 
 
-GPU_MCMC_CAPACITY = 2368   # chains one B200 runs side by side (148 SMs x 16 warps at 127 registers)
-GPU_MCMC_HOST_EQUIV = 25   # chunks one host thread clusters in the time the GPU takes for its (concurrent) chains
+GPU_MCMC_CAPACITY = 4736   # diploid chains one B200 runs side by side (148 SMs x 8 warps x 4 chains, mcmc_diploid_kernel)
+GPU_MCMC_HOST_EQUIV = 8    # chunks one host thread clusters in the time the GPU takes for its (concurrent) chains (~1.3 s)
 
 
 def gpu_mcmc_share(n_chunks: int) -> int:

@@ -96,6 +96,39 @@ def diploid_chunk(seed: int, length: int = 2000, n_reads: int = 60, error_rate: 
                 hap=np.array(hap_of, dtype=np.int32), snv_pos=snvs, haps=haps)
 
 
+def paralog_chunk(seed: int, length: int = 2000, n_reads: int = 240, error_rate: float = 0.08,
+                  n_paralog: int = 4, paralog_div: float = 0.05, hap_div: float = 0.001):
+    """BASELINE.json configs[3]: a repeat-heavy chunk -- n_paralog copies that differ from the first by `paralog_div`
+    substitutions per base (`sandbox/src/bin/gen_sim_genome_segdup.rs:30-35` style), each with two haplotypes at `hap_div`;
+    n_reads reads split evenly over the 2 * n_paralog sequences.  Substitutions only, so the generating alignment of a read
+    is a valid global path against `template` (copy 0, haplotype 0).
+    Returns dict(template, reads, ops, strands, paralog int[n], hap int[n])."""
+    rng = np.random.default_rng(seed)
+    tmpl = random_template(rng, length)
+
+    def substitute(seq, rate, lo=10):
+        out = seq.copy()
+        n = max(1, int(round(rate * length)))
+        pos = rng.choice(np.arange(lo, length - lo), size=n, replace=False)
+        out[pos] = ACGT[(np.searchsorted(ACGT, out[pos]) + rng.integers(1, 4, size=n)) % 4]
+        return out
+    seqs = []
+    for p in range(n_paralog):
+        a = tmpl if p == 0 else substitute(tmpl, paralog_div)
+        seqs.append((p, a))
+        seqs.append((p, substitute(a, hap_div)))
+    reads, ops, par, hap = [], [], [], []
+    per = n_reads // len(seqs)
+    for h, (p, sq) in enumerate(seqs):
+        cnt = per if h < len(seqs) - 1 else n_reads - per * (len(seqs) - 1)
+        for _ in range(cnt):
+            r, o = mutate_read(rng, sq, error_rate)
+            reads.append(r); ops.append(o); par.append(p); hap.append(h)
+    strands = (rng.random(len(reads)) < 0.5).astype(np.uint8)
+    return dict(template=tmpl, reads=reads, ops=ops, strands=strands, paralog=np.array(par, dtype=np.int32),
+                hap=np.array(hap, dtype=np.int32))
+
+
 def diploid_region(seed: int, n_chunks: int, length: int = 2000, n_reads: int = 60,
                    error_rate: float = 0.08, div: float = 0.0005):
     """BASELINE.json configs[1]/[2]: chunks of a mock diploid region (hap B = hap A + `div` SNV rate,

@@ -26,6 +26,7 @@
 #include "phmm_oracle.h"
 #include <math.h>
 #include <pthread.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -478,8 +479,11 @@ int orc_modification_table_batch(const orc_hmm *fwd, const orc_hmm *rev, orc_pai
 
 /* ---------------------------------------------------------------- K3 polish */
 #define POLISH_MIN_GAIN 0.1
-#define POLISH_INACTIVE 5
+#define POLISH_SUPPRESS 10
+#define POLISH_DUP_SPAN 40
+#define POLISH_TWIN_TOL 0.1
 #define POLISH_MAX_ITER 20
+#define POLISH_TIE_MARGIN 0.01
 
 typedef struct { int j, row; } edit_t;
 
@@ -539,27 +543,51 @@ int orc_polish_until_converge(const orc_hmm *fwd, const orc_hmm *rev, const uint
         }
         free(tab);
         if (rc) { free(sum); break; }
-        /* greedy left-to-right pick */
+        /* per-column best row and gain */
         edit_t *ed = (edit_t *)malloc(sizeof(edit_t) * (size_t)(L + 1));
-        int n_ed = 0;
-        int j = cfg->ignore_edge;
-        while (j <= L - cfg->ignore_edge) {
+        int *brow = (int *)malloc(sizeof(int) * (size_t)(L + 1));
+        double *bgain = (double *)malloc(sizeof(double) * (size_t)(L + 1));
+        for (int j = 0; j <= L; j++) {
             int best = -1; double bg = POLISH_MIN_GAIN;
             int own = j < L ? base2(tmpl[j]) : -1;
-            for (int row = 0; row < ORC_NUM_ROW; row++) {
-                if (row == own) continue;
-                if (row < 4 && j >= L - cfg->ignore_edge) continue;
-                if (row >= 8 && row < 8 + ORC_COPY_SIZE && j + (row - 7) > L - cfg->ignore_edge) continue;
-                if (row >= 8 + ORC_COPY_SIZE && j + (row - 7 - ORC_COPY_SIZE) > L - cfg->ignore_edge) continue;
-                double g = sum[(size_t)j * ORC_NUM_ROW + row];
-                if (g > bg) { bg = g; best = row; }
+            if (j >= cfg->ignore_edge && j <= L - cfg->ignore_edge) {
+                for (int row = 0; row < ORC_NUM_ROW; row++) {
+                    if (row == own) continue;
+                    if (row < 4 && j >= L - cfg->ignore_edge) continue;
+                    if (row >= 8 && row < 8 + ORC_COPY_SIZE && j + (row - 7) > L - cfg->ignore_edge) continue;
+                    if (row >= 8 + ORC_COPY_SIZE && j + (row - 7 - ORC_COPY_SIZE) > L - cfg->ignore_edge) continue;
+                    double g = sum[(size_t)j * ORC_NUM_ROW + row];
+                    if (g > bg) { bg = g; best = row; }
+                }
             }
-            if (best >= 0) {
-                ed[n_ed].j = j; ed[n_ed].row = best; n_ed++;
-                int consumed = best >= 8 + ORC_COPY_SIZE ? best - 7 - ORC_COPY_SIZE : (best < 4 ? 1 : 0);
-                j += consumed + POLISH_INACTIVE;
-            } else j++;
+            brow[j] = best; bgain[j] = best >= 0 ? bg : 0.0;
         }
+        /* an edit is taken iff (1) no candidate within POLISH_SUPPRESS columns gains more (ties within the margin: the
+         * leftmost wins) and (2) it is not the tandem-repeat twin of an edit already taken (an indel of the same row with
+         * a gain within POLISH_TWIN_TOL, at most POLISH_DUP_SPAN columns to the right) */
+        int n_ed = 0;
+        double *tgain = (double *)malloc(sizeof(double) * (size_t)(L + 1));
+        for (int j = cfg->ignore_edge; j <= L - cfg->ignore_edge; j++) {
+            int best = brow[j];
+            if (best < 0) continue;
+            double g = bgain[j];
+            int take = 1;
+            int lo = j - POLISH_SUPPRESS < cfg->ignore_edge ? cfg->ignore_edge : j - POLISH_SUPPRESS;
+            for (int a = lo; a <= j + POLISH_SUPPRESS && a <= L - cfg->ignore_edge && take; a++) {
+                if (a == j || brow[a] < 0) continue;
+                if (a < j ? bgain[a] >= g - POLISH_TIE_MARGIN : bgain[a] > g + POLISH_TIE_MARGIN) take = 0;
+            }
+            for (int e = n_ed - 1; take && e >= 0 && j - ed[e].j <= POLISH_DUP_SPAN; e--)
+                if (best >= 4 && ed[e].row == best && fabs(tgain[e] - g) <= POLISH_TWIN_TOL * (tgain[e] > g ? tgain[e] : g)) take = 0;
+            if (take) { ed[n_ed].j = j; ed[n_ed].row = best; tgain[n_ed] = g; n_ed++; }
+        }
+        free(tgain);
+        if (getenv("ORC_POLISH_DEBUG")) {
+            fprintf(stderr, "iter %d L %d:", iters, L);
+            for (int e = 0; e < n_ed; e++) fprintf(stderr, " (%d,%d,%.2f)", ed[e].j, ed[e].row, bgain[ed[e].j]);
+            fprintf(stderr, "\n");
+        }
+        free(brow); free(bgain);
         free(sum);
         if (n_ed == 0) { free(ed); break; }
         /* apply to the template */

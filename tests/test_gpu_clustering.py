@@ -188,18 +188,20 @@ def _host_restarts(data, k, cov, state, restarts):
 
 
 def test_device_mcmc_restarts_equal_the_host_twin(ctx):
-    """jtk_mcmc_restarts_batch (one warp per chain) against the host restatement of mcmc_clustering's
+    """jtk_mcmc_restarts_batch (two clusters and <= 8 columns: four chains per warp, mcmc_diploid_kernel; otherwise
+    one warp per chain) against the host restatement of mcmc_clustering's
     restart loop on the same variants and generator states: assignments, likelihood and the generator state after the
     restarts must be identical, bit for bit (the generator state proves that every accept / reject went the same way)."""
     from jtk_b200 import pipeline as P
     rng = np.random.default_rng(17)
     datas, ks, covs, states = [], [], [], []
-    for c, (n, D, k) in enumerate([(60, 6, 2), (24, 1, 2), (40, 3, 3), (12, 5, 2), (60, 4, 4), (33, 2, 2), (60, 6, 2), (18, 8, 3)]):
+    for c, (n, D, k) in enumerate([(60, 6, 2), (24, 1, 2), (40, 3, 3), (12, 5, 2), (60, 4, 4), (33, 2, 2), (60, 6, 2), (18, 8, 3),
+                                   (64, 7, 2), (100, 8, 2), (31, 2, 2), (63, 4, 2), (60, 9, 2)]):
         hap = rng.integers(0, k, n)
         sign = np.where(rng.random((k, D)) < 0.5, 1.0, -1.0)
         v = sign[hap] * rng.normal(6, 2, (n, D))
         v[rng.random((n, D)) < 0.15] = 0.0
-        if c == 6:
+        if c in (6, 11):
             v = rng.normal(0, 1.5, (n, D))  # no structure: the chain wanders, many acceptances through exp()
         datas.append(v); ks.append(k); covs.append(n / k); states.append(P._rng_seed(1000 + 7 * c))
     restarts = 3

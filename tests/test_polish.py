@@ -92,3 +92,53 @@ def test_consensus_window_polish_repairs_drafts():
     cons, new_ops = consensus.polish_windows(models, drafts, windows, radius, 50)
     for c, t in zip(cons, truths):
         assert np.array_equal(c, t)
+
+
+def clustered_error_case(seed, L=700, n=20, n_err=12):
+    """A draft whose errors come in clusters (pairs 2-6 columns apart) and that contains a tandem repeat with one unit missing:
+    the shapes on which a pick of the FIRST positive-gain column oscillates (spurious indels next to a substitution, two
+    equivalent unit deletions applied at once)."""
+    rng = np.random.default_rng(seed)
+    truth = synth.random_template(rng, L)
+    unit = synth.random_template(rng, 6)
+    truth[300:336] = np.tile(unit, 6)
+    draft = truth.copy()
+    pos = []
+    for k in range(n_err // 2):
+        a = 30 + k * 100 + int(rng.integers(0, 20))
+        pos += [a, a + int(rng.integers(2, 7))]
+    pos = np.array(pos)
+    draft[pos] = synth.ACGT[(np.searchsorted(synth.ACGT, draft[pos]) + rng.integers(1, 4, size=len(pos))) % 4]
+    draft = np.delete(draft, np.arange(312, 318))   # one repeat unit missing
+    reads, ops = [], []
+    for _ in range(n):
+        q, _o = synth.mutate_read(rng, truth, 0.08)
+        reads.append(q); ops.append(O.edit_ops(draft, q, 30))
+    strands = (rng.random(n) < 0.5).astype(np.uint8)
+    return truth, draft, reads, ops, strands
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_oracle_polish_converges_on_clustered_errors_and_repeats(seed):
+    truth, draft, reads, ops, strands = clustered_error_case(seed)
+    h = O.default_hmm()
+    cons, new_ops, iters = O.polish_until_converge(h, h, draft, reads, ops, strands, 30, len(reads), 0)
+    assert iters <= 10, iters
+    assert bytes(cons) == bytes(truth)
+    for o, r in zip(new_ops, reads):
+        check_ops_span(o, len(cons), len(r))
+
+
+@pytest.mark.gpu
+def test_gpu_polish_converges_on_clustered_errors_like_the_oracle():
+    from jtk_b200 import hmm
+    h = O.default_hmm()
+    m = hmm.PairHiddenMarkovModelOnStrands.default()
+    for seed in (1, 2):
+        truth, draft, reads, ops, strands = clustered_error_case(seed)
+        want_cons, want_ops, want_it = O.polish_until_converge(h, h, draft, reads, ops, strands, 30, len(reads), 0)
+        gops = [o.copy() for o in ops]
+        cons = m.polish_until_converge_antidiagonal(draft, reads, gops, strands, hmm.HMMPolishConfig.new(30, len(reads), 0))
+        assert bytes(cons) == bytes(want_cons) == bytes(truth)
+        for a, b in zip(gops, want_ops):
+            assert a.tolist() == b.tolist()
