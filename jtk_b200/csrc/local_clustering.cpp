@@ -17,9 +17,11 @@
 #include <cmath>
 #include <cstdint>
 #include <cctype>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <limits>
+#include <thread>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -1221,12 +1223,25 @@ int jtk_lc_nonmatch_columns_batch(int n, const uint8_t *ops_concat, const uint64
                                   const uint64_t *read_off, const uint8_t *tmpl_concat, const uint64_t *tmpl_off,
                                   const uint32_t *tmpl_idx, int32_t *out) {
     if (n < 0 || (n > 0 && (!ops_concat || !ops_off || !read_concat || !read_off || !tmpl_concat || !tmpl_off || !tmpl_idx || !out))) return JTK_EINVAL;
-    for (int k = 0; k < n; k++) {
-        const uint32_t t = tmpl_idx[k];
-        out[k] = jtk_lc_nonmatch_columns(ops_concat + ops_off[k], (int)(ops_off[k + 1] - ops_off[k]), read_concat + read_off[k],
-                                         (int)(read_off[k + 1] - read_off[k]), tmpl_concat + tmpl_off[t],
-                                         (int)(tmpl_off[t + 1] - tmpl_off[t]));
-    }
+    // nodes are independent: the reference computes these keys inside sort_by_cached_key on its rayon workers
+    auto range = [&](int lo, int hi) {
+        for (int k = lo; k < hi; k++) {
+            const uint32_t t = tmpl_idx[k];
+            out[k] = jtk_lc_nonmatch_columns(ops_concat + ops_off[k], (int)(ops_off[k + 1] - ops_off[k]), read_concat + read_off[k],
+                                             (int)(read_off[k + 1] - read_off[k]), tmpl_concat + tmpl_off[t],
+                                             (int)(tmpl_off[t + 1] - tmpl_off[t]));
+        }
+    };
+    int nt = (int)std::thread::hardware_concurrency();
+    if (const char *env = std::getenv("JTK_CLUSTER_THREADS")) nt = std::atoi(env);
+    else if (const char *env2 = std::getenv("JTK_HOST_THREADS")) nt = std::atoi(env2);
+    nt = std::max(1, std::min(std::min(nt, 32), n / 256));
+    if (nt <= 1) { range(0, n); return JTK_OK; }
+    std::vector<std::thread> th;
+    const int per = (n + nt - 1) / nt;
+    for (int t = 1; t < nt; t++) th.emplace_back(range, std::min(n, t * per), std::min(n, (t + 1) * per));
+    range(0, std::min(n, per));
+    for (auto &x : th) x.join();
     return JTK_OK;
 }
 

@@ -188,12 +188,16 @@ def normalize_local_clustering(ds: DataSet) -> None:
         mapsto = [0] * mx
         for to, (frm, _) in enumerate(counts):
             mapsto[frm] = to
-        for n in nodes:
-            idx = list(mapsto)
+        if mapsto == list(range(mx)):
+            continue   # already in descending size order: `reorder` with the identity changes nothing
+        # `reorder(&mut posterior, &mut mapsto.clone())` (normalize.rs:47-49,54-63) moves entry c to position mapsto[c]: one
+        # scatter for the whole pile-up instead of a swap loop per node
+        post = np.stack([n.posterior for n in nodes])
+        moved = np.empty_like(post)
+        moved[:, mapsto] = post
+        for i, n in enumerate(nodes):
             n.cluster = mapsto[int(n.cluster)]
-            post = list(n.posterior)
-            reorder(post, idx)
-            n.posterior = np.array(post)
+            n.posterior = moved[i]
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -400,30 +404,82 @@ def local_clustering_selected(ds: DataSet, selection: Iterable[int], gains: Opti
         from .likelihood_gains import estimate_gain_default
         gains = estimate_gain_default(hmm, ctx=ctx)
     coverage = float(ds.coverage)
+    import time
+    t0 = time.perf_counter()
     pile = {cid: pc for cid, pc in group_nodes(ds, selection).items() if pc[0]}
     ids = sorted(pile)
     weights = [scheduler.chunk_weight(len(pile[c][0]), len(pile[c][1].seq),
                                       sum(len(n.seq) for n in pile[c][0]) / len(pile[c][0]),
                                       band_width(ds.read_type, len(pile[c][1].seq)) // 2) for c in ids]
+    t_group = time.perf_counter() - t0
+    inner: Dict[str, float] = {}
 
     def process(my_ids: List[int]) -> Dict[int, tuple]:
+        t1 = time.perf_counter()
         pileup_nodes(ds, selection, pile=pile, only=my_ids)   # the sort of mod.rs:47-50, for this rank's chunks only
-        return _cluster_pileups(ctx, hmm, gains, coverage, ds.read_type, {c: pile[c] for c in my_ids})
+        inner["pileup_sort"] = time.perf_counter() - t1
+        out = _cluster_pileups(ctx, hmm, gains, coverage, ds.read_type, {c: pile[c] for c in my_ids})
+        inner.update(LAST_TIMING)
+        if world > 1:
+            # what travels to rank 0 per chunk: assignments as one int array, log-posteriors as one n x k array, guide ops at
+            # 2 bits per column (the reference's Node.cigar is run-length coded for the same reason)
+            t1 = time.perf_counter()
+            out = {c: (r[0], r[1], r[2], np.asarray(r[3], dtype=np.int64), np.asarray(r[4], dtype=np.float64), _pack_ops_chunk(r[5]))
+                   for c, r in out.items()}
+            inner["pack_ops"] = time.perf_counter() - t1
+        return out
 
+    t0 = time.perf_counter()
     merged = scheduler.run_sharded(ids, weights, process, rank, world, group=group)
+    t_run = time.perf_counter() - t0
     if merged is None:
         return None
+    t0 = time.perf_counter()
     out = {}
     for cid, (cons, score, k, asn, post, ops) in merged.items():
         nodes, chunk = pile[cid]
-        for n, a, p, o in zip(nodes, asn, post, ops):                              # update_by_clusterings (mod.rs:244-260)
-            n.posterior = np.array(p)
-            n.cluster = int(a)
-            n.ops = o
+        if isinstance(ops, tuple):
+            ops = _unpack_ops_chunk(ops)
+        post = np.asarray(post, dtype=np.float64)
+        asn = np.asarray(asn).tolist()
+        for i, n in enumerate(nodes):                                               # update_by_clusterings (mod.rs:244-260)
+            n.posterior = post[i]
+            n.cluster = asn[i]
+            n.ops = ops[i]
         chunk.seq, chunk.score, chunk.cluster_num = cons, score, k                 # mod.rs:74-81
         out[cid] = (cons, score, k)
     normalize_local_clustering(ds)
+    LAST_TIMING.clear()
+    LAST_TIMING.update(inner)
+    LAST_TIMING.update({"group_nodes": t_group, "gather_wait": max(0.0, t_run - sum(v for k, v in inner.items() if k != "gpu_mcmc_chunks")),
+                        "write_back": time.perf_counter() - t0})
     return out
+
+
+def _pack_ops(ops: np.ndarray):
+    """Guide ops (values 0..3) as 2 bits per column for the host gather: (column count, packed bytes)."""
+    o = np.asarray(ops, dtype=np.uint8)
+    pad = (-len(o)) % 4
+    q = np.concatenate([o, np.zeros(pad, dtype=np.uint8)]).reshape(-1, 4)
+    return len(o), (q[:, 0] | (q[:, 1] << 2) | (q[:, 2] << 4) | (q[:, 3] << 6)).astype(np.uint8)
+
+
+def _unpack_ops(packed) -> np.ndarray:
+    n, b = packed
+    return np.stack([b & 3, (b >> 2) & 3, (b >> 4) & 3, (b >> 6) & 3], axis=1).reshape(-1)[:n].astype(np.uint8)
+
+
+def _pack_ops_chunk(ops_list):
+    """All guide ops of one chunk in one packed array: (lengths int32[n], packed bytes) -- one numpy pass per chunk."""
+    lens = np.fromiter((len(o) for o in ops_list), dtype=np.int32, count=len(ops_list))
+    cat = np.concatenate(ops_list) if len(ops_list) else np.zeros(0, dtype=np.uint8)
+    return lens, _pack_ops(cat)[1]
+
+
+def _unpack_ops_chunk(packed):
+    lens, b = packed
+    flat = _unpack_ops((int(lens.sum()), b))
+    return np.split(flat, np.cumsum(lens)[:-1]) if len(lens) else []
 
 
 LAST_TIMING: Dict[str, float] = {}  # seconds spent in the phases of the last _cluster_pileups call (diagnostics)

@@ -159,6 +159,51 @@ def test_device_filter_profiles_matches_host(ctx):
     b.close()
 
 
+def test_full_size_chunk_oracle_vs_gpu(ctx):
+    """BASELINE.json configs[0] / one chunk of configs[1] at FULL size: 2 kbp, all 60 reads, radius 30, fitted-looking
+    (non-default) strand models.  Every table entry against the oracle, then pseudo_mcmc::clustering on oracle tables and on
+    GPU tables: identical probe columns, cluster number and assignments."""
+    from test_gpu_parity import check_tables, random_hmm
+    d = synth.diploid_chunk(7, length=2000, n_reads=60, error_rate=0.08, n_snv=5)
+    fwd, rev = random_hmm(41), random_hmm(42)
+    n = 60
+    tidx = np.zeros(n, np.uint32)
+    lk, tabs = ctx.modtable_batch(to_c(fwd), to_c(rev), [d["template"]], d["reads"], d["ops"], d["strands"], tidx, 30)
+    otabs, olk = O.modification_table_batch(fwd, rev, [d["template"]] * n, d["reads"], d["ops"], d["strands"], 30, n_threads=8)
+    worst = check_tables(tabs, lk, otabs, olk, [d["template"]], tidx)
+    assert worst < 2e-3
+    cfg = LC.ClusteringConfig.new(30, 2, 30.0, 30.0, GAINS)
+
+    def prof(t, l):
+        p = np.stack(t) - np.asarray(l)[:, None]
+        p[np.stack(t) < -1e9] = -1e10
+        return p
+    ro = LC.clustering_on_profiles(prof(otabs, olk), d["template"], d["strands"], cfg, 7 * 3490)
+    rg = LC.clustering_on_profiles(prof(tabs, lk), d["template"], d["strands"], cfg, 7 * 3490)
+    assert ro.probes.tolist() == rg.probes.tolist() and len(rg.probes) >= 3
+    assert ro.k == rg.k == 2 and (ro.assignments == rg.assignments).all()
+    agree = (rg.assignments == d["hap"]).mean()
+    assert max(agree, 1 - agree) >= 0.95
+
+
+def test_repeat_heavy_chunk_first_level_oracle_vs_gpu(ctx):
+    """BASELINE.json configs[3] shape: 4 paralogs x 2 haplotypes, 240 reads.  clustering_recursive's first level clusters into
+    BRANCH_NUM = 4 (local_clustering/mod.rs:139-143): the same columns and assignments from oracle tables and from GPU tables,
+    and the four clusters are the four paralogs."""
+    d = synth.paralog_chunk(11, length=1000, n_reads=240)
+    h = O.default_hmm()
+    cfg = LC.ClusteringConfig.new(30, 4, 30.0, 60.0, GAINS)
+    ro = LC.clustering_on_profiles(oracle_profiles(d, h, h, 30), d["template"], d["strands"], cfg, 11 * 3490)
+    rg = LC.clustering_on_profiles(gpu_profiles(ctx, d, h, h, 30), d["template"], d["strands"], cfg, 11 * 3490)
+    assert ro.probes.tolist() == rg.probes.tolist()
+    assert ro.k == rg.k and (ro.assignments == rg.assignments).all()
+    assert rg.k == 4
+    lab, par = rg.assignments.astype(int), d["paralog"]
+    iu = np.triu_indices(len(lab), 1)
+    rand = ((lab[:, None] == lab[None, :])[iu] == (par[:, None] == par[None, :])[iu]).mean()
+    assert rand >= 0.97, rand
+
+
 def test_kiley_shaped_clustering_call(ctx):
     """local_clustering.clustering mirrors pseudo_mcmc::clustering's argument list."""
     from jtk_b200 import hmm

@@ -141,3 +141,14 @@ def test_sharded_run_gathers_every_chunk_once_gloo_world2():
         assert ret["seeds"] == [c * 3490 for c in range(100, 123)]
         assert ret["ranks"] == ["rank0", "rank1"]
         assert ret["lens"] == [c % 7 for c in range(100, 123)]
+
+
+def test_ops_travel_packed_two_bits_per_column():
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 3, 4, 5, 2047):
+        o = rng.integers(0, 4, n).astype(np.uint8)
+        assert np.array_equal(P._unpack_ops(P._pack_ops(o)), o)
+        assert len(P._pack_ops(o)[1]) == (n + 3) // 4
+    ops = [rng.integers(0, 4, n).astype(np.uint8) for n in (5, 0, 2047, 3)]
+    back = P._unpack_ops_chunk(P._pack_ops_chunk(ops))
+    assert len(back) == 4 and all(np.array_equal(a, b) for a, b in zip(ops, back))

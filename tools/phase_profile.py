@@ -9,11 +9,12 @@ import bench  # noqa: E402
 def main():
     from jtk_b200 import _lib
     ctx = _lib.Context(0)
-    w = bench.make_workload(0, 80, 60, 2000)
-    bench.phase_leg(ctx, *w, 80, 30.0)
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 80
+    w = bench.make_workload(0, n, 60, 2000)
+    bench.phase_leg(ctx, *w, n, 30.0)
     pr = cProfile.Profile()
     pr.enable()
-    out = bench.phase_leg(ctx, *w, 80, 30.0)
+    out = bench.phase_leg(ctx, *w, n, 30.0)
     pr.disable()
     print({k: v for k, v in out.items() if k != "what"})
     pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
