@@ -23,6 +23,11 @@
 namespace jtk {
 int cols_per_lane_for_radius(int radius);
 cudaError_t launch_modtable(const KParams &p, int C, int grid_fwd, int grid_bwd, cudaStream_t st);
+cudaError_t launch_modtable_fused(const KParams &p, int C, int grid, cudaStream_t st);
+int fused_dyn_smem(int C, int smem_rb);
+int fused_grid(int C, int rows, int dyn, int sm_count);
+size_t fused_ckpt_bytes(int C, int max_nd);
+size_t fused_kb_ints(int max_nd);
 int fwdrows_ctas_per_sm(int C);
 int fwdinfo_words();
 int fwd_pad_rows(int C);
@@ -463,6 +468,7 @@ struct jtk_batch {
     int n_pairs = 0, n_tmpl = 0, radius = 0, C = 0, max_nd = 0, max_lt = 0, max_lr = 0;
     uint64_t table_floats = 0, cell_updates = 0, h2d_bytes = 0;
     bool has_profiles = false;
+    bool has_order = false;               // ragged batch: the kernels take the pairs longest first (order follows d_pairs)
     std::vector<DevPair> pairs;           // host copy
     std::vector<uint32_t> tmpl_len;
     std::vector<uint32_t> tp_start, tp_ids; // CSR template -> pairs
@@ -493,6 +499,9 @@ struct jtk_batch {
 };
 
 namespace {
+
+// DevPair elements that hold n uint32 queue-order entries behind the pairs
+inline size_t order_pairs(size_t n) { return (n * sizeof(uint32_t) + sizeof(DevPair) - 1) / sizeof(DevPair); }
 
 // JTK_TIMING=1: wall-clock phases of jtk_batch_create on stderr (tools/e2e_phases.py)
 struct PhaseTimer {
@@ -662,6 +671,7 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
     std::vector<uint32_t> cnt((size_t)n_tmpl + 1, 0);
     b->pairs.resize((size_t)n_pairs);
     b->max_nd = 0;
+    int min_nd = INT32_MAX;
     for (int p = 0; p < n_pairs; p++) {
         if (read_off[p + 1] < read_off[p]) return ctx->fail(JTK_EINVAL, "read_off is not monotone");
         if (tmpl_idx[p] >= (uint32_t)n_tmpl) return ctx->fail(JTK_EINVAL, "tmpl_idx out of range");
@@ -681,8 +691,12 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
         bwords += (Lt + Lr + 1 + 31) / 32 + 1;
         cnt[tmpl_idx[p] + 1]++;
         b->max_nd = std::max(b->max_nd, (int)(Lt + Lr + 1));
+        min_nd = std::min(min_nd, (int)(Lt + Lr + 1));
         b->max_lr = std::max(b->max_lr, (int)Lr);
     }
+    // length-sorted work queue: when the pairs of a batch differ in length by more than an eighth, the persistent warps pull
+    // them longest first (no long pair starts when the others are finishing); uniform batches keep the batch order
+    b->has_order = n_pairs > 1 && (size_t)(b->max_nd - min_nd) * 8 > (size_t)b->max_nd;
     if (cb >= (size_t)0xffffffffu) return ctx->fail(JTK_EINVAL, "batch too large: split it (code bytes exceed 4 GiB)");
     b->tp_start.assign((size_t)n_tmpl + 1, 0);
     for (int t = 0; t < n_tmpl; t++) b->tp_start[t + 1] = b->tp_start[t] + cnt[t + 1];
@@ -693,7 +707,7 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
     }
     CU(ctx->h_codes.reserve(cb), "cudaMallocHost codes");
     CU(ctx->h_bits.reserve(bwords), "cudaMallocHost bits");
-    CU(ctx->h_pairs.reserve((size_t)n_pairs), "cudaMallocHost pairs");
+    CU(ctx->h_pairs.reserve((size_t)n_pairs + order_pairs((size_t)n_pairs)), "cudaMallocHost pairs");
     CU(ctx->h_homop.reserve(hb), "cudaMallocHost homop");
     uint8_t *codes = ctx->h_codes.p;
     uint32_t *bits = ctx->h_bits.p;
@@ -815,6 +829,12 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
     pt.mark("pairs");
     if (first_bad.load() < n_pairs) return ctx->fail(bad_code ? bad_code : JTK_EINVAL, bad_text);
     std::memcpy(ctx->h_pairs.p, b->pairs.data(), sizeof(DevPair) * (size_t)n_pairs);
+    if (b->has_order) {
+        uint32_t *ord = reinterpret_cast<uint32_t *>(ctx->h_pairs.p + n_pairs);
+        for (int p = 0; p < n_pairs; p++) ord[p] = (uint32_t)p;
+        const DevPair *pp = b->pairs.data();
+        std::stable_sort(ord, ord + n_pairs, [pp](uint32_t x, uint32_t y) { return pp[x].Lt + pp[x].Lr > pp[y].Lt + pp[y].Lr; });
+    }
     ctx->tmpl_code_off = b->tmpl_code_off;
     b->table_floats = tab;
     b->cell_updates = cells_total.load();
@@ -855,7 +875,8 @@ int batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_conc
     cudaStream_t st = ctx->stream;
     cudaError_t e;
 #define CB(call, what) do { if ((e = (call)) != cudaSuccess) { b->release(); delete b; return ctx->cuda_fail(e, what); } } while (0)
-    CB(b->d_pairs.reserve((size_t)n_pairs), "cudaMalloc pairs");
+    const size_t pair_elems = (size_t)n_pairs + (b->has_order ? order_pairs((size_t)n_pairs) : 0);
+    CB(b->d_pairs.reserve(pair_elems), "cudaMalloc pairs");
     CB(b->d_codes.reserve(code_bytes), "cudaMalloc codes");
     CB(b->d_bits.reserve(bit_words), "cudaMalloc bits");
     CB(b->d_lk.reserve((size_t)n_pairs), "cudaMalloc lk");
@@ -866,7 +887,7 @@ int batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_conc
     CB(b->d_homop.reserve(homop_bytes), "cudaMalloc homop");
     CB(b->d_tmpl_code_off.reserve(b->tmpl_code_off.size()), "cudaMalloc tmpl_code_off");
     pt.mark("reserve");
-    CB(cudaMemcpyAsync(b->d_pairs.p, ctx->h_pairs.p, sizeof(DevPair) * (size_t)n_pairs, cudaMemcpyHostToDevice, st), "H2D pairs");
+    CB(cudaMemcpyAsync(b->d_pairs.p, ctx->h_pairs.p, sizeof(DevPair) * pair_elems, cudaMemcpyHostToDevice, st), "H2D pairs");
     if (!device_encode) {
         CB(cudaMemcpyAsync(b->d_codes.p, ctx->h_codes.p, code_bytes, cudaMemcpyHostToDevice, st), "H2D codes");
         CB(cudaMemcpyAsync(b->d_bits.p, ctx->h_bits.p, bit_words * sizeof(uint32_t), cudaMemcpyHostToDevice, st), "H2D bits");
@@ -954,7 +975,35 @@ int batch_run(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev
     // The modification table runs as waves of (forward kernel, backward kernel); the forward rows of every pair of a wave
     // live in HBM between the two kernels (2.3 MB per 2 kbp pair), so a wave holds as many pairs as the scratch budget allows.
     int per_wave = b->n_pairs;
-    if (table) {
+    const bool legacy = std::getenv("JTK_MODTABLE_LEGACY") != nullptr; // v9 three-kernel path with forward rows in HBM (A/B runs)
+    int fused_blocks = 0;
+    if (table && !legacy) {
+        // v10: one fused kernel, forward rows recomputed in shared memory.  Per WARP SLOT: checkpoints + block exponents; per
+        // pair of a wave: raw column sums (64 B per template column) + forward info for finalize_kernel.
+        kp.smem_rb = ((b->max_lr + 2 * fwd_pad_rows(b->C)) + 15) & ~15;
+        kp.smem_tb = 0;
+        kp.fwdinfo_stride = (size_t)fwdinfo_words();
+        kp.raw_stride = (size_t)4 * (b->max_lt + 1);
+        kp.max_lt = b->max_lt;
+        const int dyn = fused_dyn_smem(b->C, kp.smem_rb);
+        if ((size_t)dyn > (size_t)227 * 1024 - 4096)
+            return ctx->fail(JTK_EINVAL, "pair too long for the modification-table kernel: the read must stay below ~50 000 bases");
+        const int per_sm = fused_grid(b->C, rows, dyn, 1);
+        if (per_sm <= 0) return ctx->fail(JTK_ECUDA, "modification-table kernel does not fit an SM");
+        const size_t per_pair = kp.fwdinfo_stride * 4 + kp.raw_stride * sizeof(float4);
+        per_wave = (int)std::max<size_t>(1, std::min<size_t>((size_t)b->n_pairs, ctx->scratch_bytes / per_pair));
+        per_wave = std::min(per_wave, 65535); // finalize_kernel puts the pair of a wave on grid.y
+        per_wave = (int)std::max<size_t>(1, std::min<size_t>((size_t)per_wave, (size_t)0xffffffffu / kp.raw_stride - 1)); // 32-bit raw offsets
+        fused_blocks = std::min((per_wave + wpc - 1) / wpc, ctx->sm_count * per_sm);
+        kp.frow_stride = (fused_ckpt_bytes(b->C, b->max_nd) + 15) & ~(size_t)15;                  // BYTES per warp slot
+        kp.kf_stride = (fused_kb_ints(b->max_nd) + 3) & ~(size_t)3;
+        const size_t slots = (size_t)fused_blocks * wpc;
+        CU(ctx->d_frows.reserve(slots * kp.frow_stride / sizeof(float2)), "cudaMalloc checkpoints");
+        CU(ctx->d_kf.reserve(slots * kp.kf_stride), "cudaMalloc scale exponents");
+        CU(ctx->d_fwdinfo.reserve((size_t)per_wave * kp.fwdinfo_stride), "cudaMalloc forward info");
+        CU(ctx->d_raw.reserve((size_t)per_wave * kp.raw_stride), "cudaMalloc raw column sums");
+        CU(b->d_delta.reserve((size_t)b->table_floats), "cudaMalloc profiles");
+    } else if (table) {
         kp.frow_stride = (size_t)(b->max_nd + frow_extra_rows()) * frow_slots_per_row(b->C);
         kp.kf_stride = (size_t)b->max_nd + 6;
         kp.fwdinfo_stride = (size_t)fwdinfo_words();
@@ -988,6 +1037,7 @@ int batch_run(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev
     kp.radius = b->radius; kp.rows = rows;
     kp.frows = ctx->d_frows.p; kp.kf = ctx->d_kf.p; kp.fwdinfo = ctx->d_fwdinfo.p; kp.raw = ctx->d_raw.p;
     kp.out_delta = b->d_delta.p; kp.out_lk = b->d_lk.p; kp.counter = ctx->d_counter.p; kp.counter2 = ctx->d_counter.p + 1;
+    kp.order = b->has_order ? reinterpret_cast<const uint32_t *>(b->d_pairs.p + b->n_pairs) : nullptr;
     cudaEvent_t r0 = nullptr, r1 = nullptr;
     if (ctx->ring_n < jtk_ctx::kRing) {
         const int k = ctx->ring_n;
@@ -1002,7 +1052,10 @@ int batch_run(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev
         const int ctas = (hi - lo + wpc - 1) / wpc;
         CU(cudaMemsetAsync(ctx->d_counter.p, 0, 2 * sizeof(int), st), "memset counter");
         kp.pair_lo = lo; kp.pair_hi = hi;
-        if (table) {
+        if (table && !legacy) {
+            CU(launch_modtable_fused(kp, b->C, std::min(ctas, fused_blocks), st), "kernel launch");
+            ctx->launches += 2;
+        } else if (table) {
             // persistent CTAs: one wave of resident CTAs pulls pairs from the queue
             const int gf = std::min(ctas, ctx->sm_count * fwdrows_ctas_per_sm(b->C));
             const int gb = std::min(ctas, ctx->sm_count * modtable_ctas_per_sm(b->C, rows));

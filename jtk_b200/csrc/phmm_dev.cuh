@@ -57,6 +57,7 @@ struct KParams {
     size_t raw_stride;      // float4 per pair slot = 4 * (max_lt + 1)
     int max_lt;
     int smem_rb, smem_tb;   // bytes of staged read / template codes per warp in the forward kernel (multiples of 16)
+    const uint32_t *order;  // queue position -> pair index (longest pairs first), or null: pairs in batch order
 };
 
 } // namespace jtk

@@ -11,6 +11,7 @@
 // forward x backward product carries the same exponent and the table is a plain ratio of sums.
 #include "phmm_dev.cuh"
 #include <type_traits>
+#include <algorithm>
 
 namespace jtk {
 
@@ -145,6 +146,11 @@ __device__ __forceinline__ void fill_tables(SmemLayout &sh, const float *__restr
         }
     }
     __syncthreads();
+}
+
+// pair behind queue position k of the current wave (longest pairs first when the host gives an order)
+__device__ __forceinline__ int pair_index(const KParams &p, int k) {
+    return p.order ? (int)p.order[p.pair_lo + k] : p.pair_lo + k;
 }
 
 struct PairCtx { // warp-uniform view of one pair
@@ -367,6 +373,7 @@ __device__ __forceinline__ bool elect_one() {
 template <int C> struct BwdState {
     int x[C], j[C];
     unsigned tcB[C], win[C];
+    const unsigned char *rbp[C]; // (fused kernel) staged code byte of read row s - j + 1 for the first step of the current block
     unsigned tcn[C]; // template code of the column this slot takes next (j - NSLOT), loaded one column-life ahead
     float BI[C], BMo[C], inD[C], inMa[C], inMb[C];
     f2 S01[C], S23[C], N01[C], N23[C]; // substitution / insertion sums over the four bases
@@ -388,9 +395,11 @@ template <int C> __device__ __forceinline__ constexpr int frow_pos(int c, int e)
     return (((c + e) % C + C) % C) * kPlane + ((c + e) - (((c + e) % C + C) % C)) / C + e * (C * kPlane);
 }
 
-template <int C, int ROWS, bool CORR, bool FIRST>
+// STAGED: the read-row codes come from the pair's staged copy in shared memory (st.rbp, step kk of the block) instead of the
+// byte windows st.win refilled from global memory.
+template <int C, int ROWS, bool CORR, bool FIRST, bool STAGED = false>
 __device__ __forceinline__ void bwd_step(const PairCtx &pc, const Coef &a, BwdState<C> &st, const f2 *rp, const int W,
-                                         const float *ce, const float boff, f2 (&bMD)[C]) {
+                                         const float *ce, const float boff, f2 (&bMD)[C], const int kk = 0) {
     constexpr int NXM = (ROWS == 14) ? 3 : 1;
     constexpr int NXP = (ROWS == 14) ? 3 : 0;
     f2 F[C][7]; // F[c][e + 3] = forward row s+e, slot sigma+e
@@ -405,10 +414,11 @@ __device__ __forceinline__ void bwd_step(const PairCtx &pc, const Coef &a, BwdSt
 #pragma unroll
     for (int c = 0; c < C; c++) {
         const bool valid = (unsigned)st.x[c] <= (unsigned)W;
-        const unsigned w = st.win[c];
-        st.win[c] = w >> 8;
+        unsigned w;
+        if (STAGED) w = st.rbp[c][-kk];
+        else { w = st.win[c]; st.win[c] = w >> 8; }
         float em = lds_f32(st.tcB[c] | (w & 0x1cu));
-        float ei = lds_f32(pc.sEI | (w & 0xffu));
+        float ei = lds_f32(STAGED ? pc.sEI + w : pc.sEI | (w & 0xffu));
         f2 ec01, ec23;
         lds_f32x4(pc.sEMT | ((w & 0x1cu) << 2), ec01, ec23);
         // a cell outside the band contributes nothing: its in-sums are masked (its forward values are zero already)
@@ -734,8 +744,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, fwd_ctas_per_sm(C)) fwdrows
         int k = 0;
         if (lane == 0) k = atomicAdd(p.counter, 1);
         k = __shfl_sync(kFull, k, 0);
-        const int pi = p.pair_lo + k;
-        if (pi >= p.pair_hi) break;
+        if (p.pair_lo + k >= p.pair_hi) break;
+        const int pi = pair_index(p, k);
         const DevPair P = p.pairs[pi];
         const int Lt = P.Lt, Lr = P.Lr, nd = Lt + Lr + 1;
         const Coef a = load_coef(sh.trans[P.model], sh.cpair[P.model]);
@@ -936,8 +946,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, bwd_ctas_per_sm(C, ROWS)) b
         int k = 0;
         if (lane == 0) k = atomicAdd(p.counter2, 1);
         k = __shfl_sync(kFull, k, 0);
-        const int pi = p.pair_lo + k;
-        if (pi >= p.pair_hi) break;
+        if (p.pair_lo + k >= p.pair_hi) break;
+        const int pi = pair_index(p, k);
         const DevPair P = p.pairs[pi];
         const PairCtx pc = make_pair_ctx(p, P, sh);
         const Coef a = load_coef(sh.trans[P.model], sh.cpair[P.model]);
@@ -962,7 +972,7 @@ __global__ void __launch_bounds__(kFinCols) finalize_kernel(KParams p) {
     __shared__ float4 sraw[(kFinCols + 3) * kFinRawStride];
     __shared__ float sout[kFinCols * kFinOutStride];
     const int k = blockIdx.y;
-    const int pi = p.pair_lo + k;
+    const int pi = pair_index(p, k);
     const DevPair P = p.pairs[pi];
     const int Lt = P.Lt;
     const int j0 = blockIdx.x * kFinCols;
@@ -1197,6 +1207,541 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) fit_kernel(KParams p, doubl
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// v10: the modification table as ONE kernel whose DP matrices never touch HBM (north star: "the backward pass is fused with
+// the modification-table reduction so the full DP matrix never touches HBM").
+//
+//   pass 1   lean forward pass (the v7 step body, no row stores): likelihood, one scale exponent per block of four
+//            anti-diagonals (kb, 1 int / 4 rows) and a CHECKPOINT of the forward state every SEG anti-diagonals
+//            (inMb, inMa, inD, toI of every slot + the band offset: C*512 + 16 bytes, i.e. 65 B per row instead of 576 B);
+//   pass 2   top-down over segments of SEG anti-diagonals: the forward rows of the segment are RECOMPUTED from its
+//            checkpoint into a per-warp shared-memory buffer (same plane layout as the v9 ring), then the v9 backward /
+//            table step runs over them.  The cuts reach three rows up and down, so the buffer keeps the eight lowest rows of
+//            the segment above (moved up by one shared-memory copy per segment) and a segment's rows start four rows below
+//            its first backward row.  Checkpoint k+1... are fetched one segment ahead by a bulk async copy (mbarrier).
+// The recomputation replays pass 1 instruction for instruction (explicit fma / mul intrinsics) and takes its rescale decisions
+// from kb, so the rows are the ones pass 1 saw.  FP32 work per cell: 11 (pass 1) + 11 (recompute) + 11 + 24 (backward, table).
+// ------------------------------------------------------------------------------------------------
+template <int C> __host__ __device__ constexpr int seg_rows() { return C == 2 ? 16 : 8; }
+constexpr int kSegKeep = 8;   // rows of the segment above that stay in the buffer
+constexpr int kSegBelow = 4;  // a segment's rows start this far below its first backward row
+template <int C> __host__ __device__ constexpr int seg_buf_rows() { return seg_rows<C>() + kSegKeep; }
+template <int C> __host__ __device__ constexpr int ckpt_bytes() { return C * 512 + 16; }
+template <int C> __host__ __device__ constexpr int ckpt_stage_bytes() { return (ckpt_bytes<C>() + 127) & ~127; }
+constexpr int fused_ctas_per_sm(int C) { return C == 2 ? 3 : (C == 4 ? 2 : 1); }
+
+// shared tables of the fused kernel (as BwdSmem): both passes look emissions up with the raw read-row code byte w = ctx<<5 | q<<2,
+// eM at (row of the column's base) | (w & 0x1c), eI at base + w: every distinct address of a warp sits in its own bank
+struct __align__(256) LeanSmem {
+    float em[2][64];  // [tc*8 + qc]
+    float ei[2][64];  // [ctx*8 + qc], byte offset = the read-row code byte
+    float emt[2][32]; // backward: [qc*4 + b]
+    float trans[2][12];
+    unsigned long long cpair[2][6];
+    unsigned long long cdup[2][9]; // (t[k], t[k]): the nine transitions as broadcast pairs (slot-paired forward step)
+    float ftot[kWarpsPerCta][4];
+    unsigned long long bar[kWarpsPerCta];
+};
+__device__ __forceinline__ void fill_lean_tables(LeanSmem &sh, const float *__restrict__ models) {
+    for (int k = threadIdx.x; k < 2 * 64; k += blockDim.x) {
+        const int m = k >> 6, e = k & 63;
+        sh.em[m][e] = models[m * kModelFloats + kOffEM + e];
+        sh.ei[m][e] = models[m * kModelFloats + kOffEI + e];
+        if (e < 32) sh.emt[m][e] = models[m * kModelFloats + kOffEMT + e];
+        if (e < 12) sh.trans[m][e] = models[m * kModelFloats + e];
+        if (e < 9) sh.cdup[m][e] = mk2(models[m * kModelFloats + e], models[m * kModelFloats + e]);
+        if (e < 6) {
+            const int lo_i[6] = { 0, 3, 6, 0, 1, 2 }, hi_i[6] = { 2, 5, 8, 6, 7, 8 };
+            sh.cpair[m][e] = mk2(models[m * kModelFloats + lo_i[e]], models[m * kModelFloats + hi_i[e]]);
+        }
+    }
+    __syncthreads();
+}
+
+struct LeanPair { // warp-uniform view of one pair for the lean forward pass
+    const uint8_t *Tb;        // Tb[j] = code of t[j-1]
+    const uint32_t *bw;       // guide bits
+    const unsigned char *rb0; // staged read codes in shared memory: rb0[i] = code byte of read row i
+    unsigned sEM, sEI;        // shared-space addresses of the pair's eM / eI tables (256-byte aligned)
+    int Lt, Lr, nd, r;
+};
+
+// Forward state with the two adjacent slots 2p, 2p+1 of a lane packed into one fp32 pair (lo = slot 2p): every arithmetic
+// instruction of the step is a packed one, the coefficients are (v, v) pairs and nothing has to be broadcast.
+template <int C> struct LeanFwd {
+    static constexpr int P = C / 2;
+    int x[C];
+    const unsigned char *rbp[C]; // staged code of the slot's cell in the first row of the current block
+    unsigned emrow[C];           // shared address of the eM row of the slot's column
+    const uint8_t *tnext[C];     // &Tb[j + 2*NSLOT]: code of the column after the next one (the slot's column is tnext - Tb - 2*NSLOT)
+    unsigned tcn[C];             // template code of the column the slot takes next, fetched one column-life ahead
+    f2 msk[P], toI[P], inD[P], inMa[P], inMb[P];
+};
+struct LeanCoef { f2 mm, im, dm, md, id, dd, mi, ii, di; }; // (v, v) pairs
+__device__ __forceinline__ LeanCoef load_lean_coef(const unsigned long long *d) {
+    LeanCoef c; // d[k] = (t[k], t[k]), t = mat_mat, mat_ins, mat_del, ins_mat, ins_ins, ins_del, del_mat, del_ins, del_del
+    c.mm = d[0]; c.mi = d[1]; c.md = d[2]; c.im = d[3]; c.ii = d[4]; c.id = d[5]; c.dm = d[6]; c.di = d[7]; c.dd = d[8];
+    return c;
+}
+__device__ __forceinline__ void set_lo(f2 &v, float x) { v = mk2(x, hi2(v)); }
+__device__ __forceinline__ void set_hi(f2 &v, float x) { v = mk2(lo2(v), x); }
+
+// slot state of anti-diagonal s0 (a multiple of four) from the number of band moves so far: the slot holds the one column
+// j == sigma (mod NSLOT) with x <= W, which is what the per-block retargeting of the forward pass leaves at block boundaries
+template <int C>
+__device__ __forceinline__ void lean_seed(const LeanSmem &sh, LeanFwd<C> &st, const LeanPair &lp, const int s0, const int ups) {
+    constexpr int NSLOT = 32 * C;
+    const int lane = threadIdx.x & 31, W = 2 * lp.r;
+    float m[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        const int sigma = lane * C + c;
+        const int t = lp.r - sigma + ups;
+        const int w = t > W ? (t - W + NSLOT - 1) / NSLOT : 0;
+        const int j = sigma + w * NSLOT;
+        st.x[c] = t - w * NSLOT;
+        st.rbp[c] = lp.rb0 + (s0 - j);
+        st.emrow[c] = lp.sEM + ((unsigned)lp.Tb[j] << 5);
+        st.tcn[c] = lp.Tb[j + NSLOT];
+        st.tnext[c] = lp.Tb + j + 2 * NSLOT;
+        m[c] = (unsigned)st.x[c] <= (unsigned)W ? 1.f : 0.f;
+    }
+#pragma unroll
+    for (int p = 0; p < C / 2; p++) st.msk[p] = mk2(m[2 * p], m[2 * p + 1]);
+}
+
+// Rows [s_begin, s_end) of the forward pass, s_begin a multiple of four, s_end a multiple of four or nd.
+// MODE 0 (pass 1): rescale decisions by warp maximum, kb[q] and checkpoints written, end sums recorded.
+// MODE 1 (recompute): rescales replayed from kb, (toM, toD) of every cell written to the shared-memory rows at `wrow`
+// (entry `lane` of plane 0 of row s_begin).
+template <int C, int MODE>
+__device__ __forceinline__ void lean_forward(const LeanSmem &sh, const LeanCoef &a, LeanFwd<C> &st, const LeanPair &lp, const int s_begin,
+                                             const int s_end, int &K, int &ups, int32_t *__restrict__ kb,
+                                             unsigned char *__restrict__ ckpt_g, f2 *wrow, volatile float *s_ftot) {
+    constexpr int NSLOT = 32 * C, RS = C * kPlane, SEG = seg_rows<C>(), CKB = ckpt_bytes<C>(), P = C / 2;
+    const int lane = threadIdx.x & 31, W = 2 * lp.r, nd = lp.nd;
+    // the cells of one anti-diagonal: out-sums (toM, toD, toI) of the slot pairs
+    auto cells = [&](const int s, const int kk, const bool special, f2 (&tM)[P], f2 (&tD)[P], f2 (&nI)[P]) {
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            const unsigned w0 = st.rbp[2 * p][kk], w1 = st.rbp[2 * p + 1][kk];
+            const f2 em = mk2(lds_f32(st.emrow[2 * p] | (w0 & 0x1cu)), lds_f32(st.emrow[2 * p + 1] | (w1 & 0x1cu)));
+            const f2 ei = mk2(lds_f32(lp.sEI + w0), lds_f32(lp.sEI + w1));
+            f2 M = mul2(em, st.inMb[p]);
+            const f2 I = mul2(ei, st.toI[p]);
+            const f2 D = st.inD[p];
+            if (special && s == 0 && p == 0 && lane == 0) set_lo(M, 1.f); // F_M(0, 0) = 1
+            tM[p] = mul2(fma2(a.dm, D, fma2(a.im, I, mul2(a.mm, M))), st.msk[p]);
+            tD[p] = mul2(fma2(a.dd, D, fma2(a.id, I, mul2(a.md, M))), st.msk[p]);
+            nI[p] = mul2(fma2(a.di, D, fma2(a.ii, I, mul2(a.mi, M))), st.msk[p]);
+            if (MODE == 0 && special && s >= nd - 4) { // the end sums F(Lr, Lt - d), d = 0..3
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int j = (int)(st.tnext[2 * p + h] - lp.Tb) - 2 * NSLOT;
+                    const float mk = h ? hi2(st.msk[p]) : lo2(st.msk[p]);
+                    if (mk != 0.f && s - j == lp.Lr && j >= lp.Lt - 3)
+                        s_ftot[lp.Lt - j] = h ? hi2(M) + hi2(I) + hi2(D) : lo2(M) + lo2(I) + lo2(D);
+                }
+            }
+        }
+    };
+    auto rescale_by = [&](const int kx, f2 (&tM)[P], f2 (&tD)[P], f2 (&nI)[P]) {
+        const f2 sc = bc2(pow2i(kx));
+#pragma unroll
+        for (int p = 0; p < P; p++) { tM[p] = mul2(tM[p], sc); tD[p] = mul2(tD[p], sc); nI[p] = mul2(nI[p], sc); st.inMa[p] = mul2(st.inMa[p], sc); }
+    };
+    auto finish = [&](const int kk, f2 (&tM)[P], f2 (&tD)[P], f2 (&nI)[P]) {
+        if (MODE == 1) { // plane c, entry lane = (toM, toD) of slot C*lane + c (the replicated plane ends are filled per segment)
+            f2 *w = wrow + kk * RS;
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                w[(2 * p) * kPlane] = mk2(lo2(tM[p]), lo2(tD[p]));
+                w[(2 * p + 1) * kPlane] = mk2(hi2(tM[p]), hi2(tD[p]));
+            }
+        }
+        // hand (toM, toD) to the right-hand neighbour column (slot+1, wrapping): the new in-pair is (left neighbour, own lo)
+        const float rM = __shfl_sync(kFull, hi2(tM[P - 1]), (lane + 31) & 31);
+        const float rD = __shfl_sync(kFull, hi2(tD[P - 1]), (lane + 31) & 31);
+#pragma unroll
+        for (int p = P - 1; p >= 1; p--) {
+            st.inMb[p] = st.inMa[p];
+            st.inMa[p] = mk2(hi2(tM[p - 1]), lo2(tM[p]));
+            st.inD[p] = mk2(hi2(tD[p - 1]), lo2(tD[p]));
+        }
+        st.inMb[0] = st.inMa[0];
+        st.inMa[0] = mk2(rM, lo2(tM[0]));
+        st.inD[0] = mk2(rD, lo2(tD[0]));
+#pragma unroll
+        for (int p = 0; p < P; p++) st.toI[p] = nI[p];
+    };
+    // anti-diagonal s -> s+1: when the centre stays (guide bit 0, up = 1) every cell moves one row up inside the window.
+    // Unconditional: a predicated version issues its dozen instructions whether or not the band moves.
+    auto masks = [&]() {
+        float m[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) m[c] = (unsigned)st.x[c] <= (unsigned)W ? 1.f : 0.f;
+#pragma unroll
+        for (int p = 0; p < P; p++) st.msk[p] = mk2(m[2 * p], m[2 * p + 1]);
+    };
+    // a slot whose cell left the band at the top (x > W) moves on to column j + NSLOT (at the end of a block of four: the
+    // slot ring has NSLOT - (W+1) >= 3 spare slots, and until then its mask is zero)
+    auto band_up = [&](const int up, const bool retarget) {
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            st.x[c] += up;
+            if (retarget && st.x[c] > W) {
+                st.x[c] -= NSLOT; st.rbp[c] -= NSLOT;
+                st.emrow[c] = lp.sEM + (st.tcn[c] << 5);
+                st.tcn[c] = *st.tnext[c];
+                st.tnext[c] += NSLOT;
+            }
+        }
+        masks();
+    };
+    unsigned bword = lp.bw[s_begin >> 5];
+    for (int s = s_begin; s < s_end; s += 4) {
+        if ((s & 31) == 0) bword = lp.bw[s >> 5];
+        const unsigned nib = bword >> (s & 31);
+        if (MODE == 0 && ((s + kSegBelow) & (SEG - 1)) == 0 && s > 0) { // checkpoint: the state before row s
+            unsigned char *ck = ckpt_g + (size_t)((s + kSegBelow) / SEG) * CKB;
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                reinterpret_cast<float4 *>(ck)[(2 * p) * 32 + lane] = make_float4(lo2(st.inMb[p]), hi2(st.inMb[p]), lo2(st.inMa[p]), hi2(st.inMa[p]));
+                reinterpret_cast<float4 *>(ck)[(2 * p + 1) * 32 + lane] = make_float4(lo2(st.inD[p]), hi2(st.inD[p]), lo2(st.toI[p]), hi2(st.toI[p]));
+            }
+            if (lane == 0) *reinterpret_cast<int4 *>(ck + C * 512) = make_int4(ups, K, 0, 0);
+        }
+        if (s >= 4 && s + 3 < nd - 4) {
+            const int Knew = (MODE == 1) ? kb[s >> 2] : 0;
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                f2 tM[P], tD[P], nI[P];
+                cells(s + kk, kk, false, tM, tD, nI);
+                if (kk == 3) {
+                    if (MODE == 0) {
+                        if (s + 3 < nd - 8) {
+                            float v = fmaxf(lo2(tM[0]), hi2(tM[0]));
+#pragma unroll
+                            for (int p = 1; p < P; p++) v = fmaxf(v, fmaxf(lo2(tM[p]), hi2(tM[p])));
+                            const unsigned mx = __reduce_max_sync(kFull, __float_as_uint(v));
+                            const int e = (int)(mx >> 23) - 127;
+                            if (mx != 0u && e < kScaleLow) {
+                                const int kx = min(kScaleTarget - e, kScaleStep);
+                                rescale_by(kx, tM, tD, nI);
+                                K += kx;
+                            }
+                        }
+                    } else if (Knew != K) {
+                        rescale_by(Knew - K, tM, tD, nI);
+                        K = Knew;
+                    }
+                }
+                finish(kk, tM, tD, nI);
+                band_up((int)((~nib >> kk) & 1u), kk == 3);
+            }
+            ups += __popc(~nib & 15u);
+        } else { // the first four and the last anti-diagonals: start cell, end sums, no rescale
+            for (int kk = 0; kk < 4 && s + kk < s_end; kk++) {
+                f2 tM[P], tD[P], nI[P];
+                cells(s + kk, kk, true, tM, tD, nI);
+                finish(kk, tM, tD, nI);
+                if (s + kk < nd - 1) {
+                    const int up = (int)((~nib >> kk) & 1u);
+                    band_up(up, true);
+                    ups += up;
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < C; c++) st.rbp[c] += 4;
+        if (MODE == 1) wrow += 4 * RS;
+        if (MODE == 0 && lane == 0) kb[s >> 2] = K;
+    }
+}
+
+template <int C, int ROWS>
+__device__ __forceinline__ void backward_fused(const PairCtx &pc, const Coef &a, const LeanSmem &fsh, const int model, const LeanPair &lp,
+                                               int32_t *__restrict__ kb, unsigned char *__restrict__ ckpt_g,
+                                               float4 *__restrict__ raw_base, const unsigned rawk, volatile float *s_ftot, f2 *buf,
+                                               unsigned char *ckstage, const unsigned bar, unsigned &phase) {
+    constexpr int NSLOT = 32 * C;
+    constexpr int RS = C * kPlane;
+    constexpr int SEG = seg_rows<C>(), CKB = ckpt_bytes<C>();
+    constexpr int QSEG = SEG / 4; // backward blocks per segment
+    const int lane = threadIdx.x & 31;
+    const int Lt = pc.Lt, nd = pc.nd, W = 2 * pc.r;
+    const float fin_raw = s_ftot[0];
+    const int e_fin = (int)(__float_as_uint(fin_raw) >> 23) - 127;
+    const float boff = fin_raw > 0.f ? pow2i(max(-120, min(120, kProductExp - e_fin))) : 1.f;
+
+    // ---- forward rows of one segment, recomputed into the buffer ---------------------------------------
+    const unsigned ck_s = (unsigned)__cvta_generic_to_shared(ckstage);
+    auto prefetch_ckpt = [&](int k) { // forward state before row SEG*k - kSegBelow
+        if (k >= 1 && SEG * k - kSegBelow < nd) {
+            if (elect_one()) {
+                mbar_expect_tx(bar, (unsigned)CKB);
+                bulk_g2s(ck_s, ckpt_g + (size_t)k * CKB, (unsigned)CKB, bar);
+            }
+        }
+    };
+    auto load_segment = [&](int k) { // rows SEG*k - 4 .. SEG*k + SEG - 5 -> buffer rows 0 .. SEG-1
+        __syncwarp();
+        {   // the eight lowest rows (of the segment above) move to the top of the buffer
+            const float4 *src = reinterpret_cast<const float4 *>(buf);
+            float4 *dst = reinterpret_cast<float4 *>(buf + SEG * RS);
+            for (int w = lane; w < kSegKeep * RS / 2; w += 32) dst[w] = src[w];
+        }
+        __syncwarp();
+        const int s0 = SEG * k - kSegBelow;
+        int s_from = max(s0, 0);
+        int s_to = min(s0 + SEG, nd);
+        if (s_from < s_to) {
+            LeanFwd<C> st;
+            int K = 0, ups = 0;
+            if (k >= 1) {
+                mbar_wait(bar, phase & 1u);
+                phase ^= 1u;
+                const float4 *ck = reinterpret_cast<const float4 *>(ckstage);
+#pragma unroll
+                for (int p = 0; p < C / 2; p++) {
+                    const float4 v = ck[(2 * p) * 32 + lane], u = ck[(2 * p + 1) * 32 + lane];
+                    st.inMb[p] = mk2(v.x, v.y); st.inMa[p] = mk2(v.z, v.w); st.inD[p] = mk2(u.x, u.y); st.toI[p] = mk2(u.z, u.w);
+                }
+                ups = reinterpret_cast<const int *>(ckstage + C * 512)[0];
+                K = kb[(s0 >> 2) - 1];
+            } else {
+#pragma unroll
+                for (int p = 0; p < C / 2; p++) st.inMb[p] = st.inMa[p] = st.inD[p] = st.toI[p] = 0ull;
+            }
+            lean_seed<C>(fsh, st, lp, s_from, ups);
+            const LeanCoef la = load_lean_coef(fsh.cdup[model]); // live during the recomputation only
+            lean_forward<C, 1>(fsh, la, st, lp, s_from, s_to, K, ups, kb, nullptr, buf + (size_t)(s_from - s0) * RS + kPlaneHalo + lane, s_ftot);
+            __syncwarp();
+            // the first / last two entries of every plane are replicated past its other end
+            for (int w = lane; w < (s_to - s_from) * C * 2 * kPlaneHalo; w += 32) {
+                const int row = w / (C * 2 * kPlaneHalo), rem = w % (C * 2 * kPlaneHalo), c = rem / (2 * kPlaneHalo), t = rem % (2 * kPlaneHalo);
+                f2 *pl = buf + (size_t)(s_from - s0 + row) * RS + c * kPlane;
+                // t < halo: entry t -> 32 + t; else entry 32 - halo + (t - halo) -> that index - 32
+                if (t < kPlaneHalo) pl[kPlaneHalo + 32 + t] = pl[kPlaneHalo + t];
+                else pl[t - kPlaneHalo] = pl[32 + t - kPlaneHalo];
+            }
+        } else {
+            s_from = s_to = s0; // nothing to compute: every row of the segment reads as zero
+        }
+        // rows below anti-diagonal 0 and past the last one read as zero
+        for (int w = lane; w < (s_from - s0) * RS; w += 32) buf[w] = 0ull;
+        {
+            const int z0 = max(s_to - s0, 0);
+            for (int w = z0 * RS + lane; w < SEG * RS; w += 32) buf[w] = 0ull;
+        }
+        __syncwarp();
+        prefetch_ckpt(k - 1);
+    };
+
+    BwdState<C> st;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        const int sigma = lane * C + c;
+        const int d = (Lt - sigma) & (NSLOT - 1);
+        st.j[c] = Lt - d;
+        st.x[c] = d + pc.r;
+        st.tcB[c] = pc.sEM + ((unsigned)pc.Tb[st.j[c] + 1] << 5);
+        st.tcn[c] = pc.Tb[st.j[c] + 1 - NSLOT];
+        st.win[c] = 0u;
+        st.rbp[c] = lp.rb0 + (nd - st.j[c]); // row s - j + 1 at s = nd - 1
+        st.BI[c] = st.BMo[c] = st.inD[c] = st.inMa[c] = st.inMb[c] = 0.f;
+        st.Vs[c] = st.Vn[c] = 0.f;
+        st.S01[c] = st.S23[c] = st.N01[c] = st.N23[c] = 0ull;
+#pragma unroll
+        for (int e = 0; e < 3; e++) { st.Xp[c][e] = 0ull; st.Xm[c][e] = 0ull; }
+    }
+    auto flush_col = [&](int c) {
+        float4 *raw = raw_base + (size_t)(rawk + (unsigned)st.j[c] * 4u); // 32-bit offset: no 64-bit pointer lives across the steps
+        f2 *sg = reinterpret_cast<f2 *>(raw);
+        asm volatile("st.global.cg.b64 [%0], %1;" ::"l"(sg + 0), "l"(st.S01[c]) : "memory");
+        asm volatile("st.global.cg.b64 [%0], %1;" ::"l"(sg + 1), "l"(st.S23[c]) : "memory");
+        asm volatile("st.global.cg.b64 [%0], %1;" ::"l"(sg + 2), "l"(st.N01[c]) : "memory");
+        asm volatile("st.global.cg.b64 [%0], %1;" ::"l"(sg + 3), "l"(st.N23[c]) : "memory");
+        __stcg(raw + 2, make_float4(st.Vs[c], st.Vn[c], lo2(st.Xp[c][0]) + hi2(st.Xp[c][0]),
+                                                          lo2(st.Xp[c][1]) + hi2(st.Xp[c][1])));
+        __stcg(raw + 3, make_float4(lo2(st.Xp[c][2]) + hi2(st.Xp[c][2]), lo2(st.Xm[c][0]) + hi2(st.Xm[c][0]),
+                                                          lo2(st.Xm[c][1]) + hi2(st.Xm[c][1]), lo2(st.Xm[c][2]) + hi2(st.Xm[c][2])));
+    };
+    auto hand_off = [&](f2 (&bMD)[C]) {
+        const float rM = __shfl_sync(kFull, lo2(bMD[0]), (lane + 1) & 31);
+        const float rD = __shfl_sync(kFull, hi2(bMD[0]), (lane + 1) & 31);
+#pragma unroll
+        for (int c = 0; c < C - 1; c++) { st.inMb[c] = st.inMa[c]; st.inMa[c] = lo2(bMD[c + 1]); st.inD[c] = hi2(bMD[c + 1]); }
+        st.inMb[C - 1] = st.inMa[C - 1]; st.inMa[C - 1] = rM; st.inD[C - 1] = rD;
+    };
+    auto retire = [&]() {
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            if (st.x[c] < 0) {
+                if (st.j[c] >= 0) flush_col(c);
+                st.j[c] -= NSLOT;
+                st.x[c] += NSLOT;
+                st.rbp[c] += NSLOT;
+                st.tcB[c] = pc.sEM + (st.tcn[c] << 5);
+                st.tcn[c] = pc.Tb[st.j[c] + 1 - NSLOT];
+                clear2(st.S01[c]); clear2(st.S23[c]); clear2(st.N01[c]); clear2(st.N23[c]);
+                clear1(st.Vs[c]); clear1(st.Vn[c]);
+#pragma unroll
+                for (int e = 0; e < 3; e++) {
+                    if (ROWS == 14) clear2(st.Xp[c][e]); else st.Xp[c][e] = 0ull;
+                    if (ROWS == 14 || e == 0) clear2(st.Xm[c][e]); else st.Xm[c][e] = 0ull;
+                }
+            }
+        }
+    };
+    int base = 0; // anti-diagonal held by buffer row 0
+    auto slow_step = [&](int s) {
+        const f2 *rp = buf + (size_t)(s - base) * RS + kPlaneHalo + lane;
+        auto kfat = [&](int t) -> int { return kb[(t - 3) >> 2]; };
+        const int kcur = kfat(s);
+        const int kstep = kcur - kfat(s - 1);
+        float ce[7];
+#pragma unroll
+        for (int e = -3; e <= 3; e++) ce[e + 3] = pow2i(max(-126, min(126, kcur - kfat(s + e))));
+        f2 bMD[C];
+        if (s == nd - 1) bwd_step<C, ROWS, true, true, true>(pc, a, st, rp, W, ce, boff, bMD);
+        else bwd_step<C, ROWS, true, false, true>(pc, a, st, rp, W, ce, boff, bMD);
+#pragma unroll
+        for (int c = 0; c < C; c++) st.rbp[c] -= 1;
+        hand_off(bMD);
+        if (s > 0) {
+            if (kstep != 0) {
+                const float sc = pow2i(kstep);
+#pragma unroll
+                for (int c = 0; c < C; c++) { st.BI[c] *= sc; st.BMo[c] *= sc; st.inD[c] *= sc; st.inMa[c] *= sc; st.inMb[c] *= sc; }
+            }
+            const int dec = (int)(((pc.bw[(s - 1) >> 5] >> ((s - 1) & 31)) & 1u) ^ 1u);
+#pragma unroll
+            for (int c = 0; c < C; c++) st.x[c] -= dec;
+        }
+    };
+
+    const int q_top = (nd + 3) >> 2; // block of the last anti-diagonal
+    int kb1 = kb[q_top - 1], kb2 = kb[q_top - 2], kb3 = kb[q_top - 3];
+    auto load_nib = [&](int q) -> unsigned { // guide bits 4q-5 .. 4q-2 of block q >= 2
+        const int b0 = 4 * q - 5;
+        return __funnelshift_r(pc.bw[b0 >> 5], pc.bw[(b0 >> 5) + 1], b0 & 31);
+    };
+    unsigned nib_cur = 0u, nib_nxt = q_top >= 2 ? load_nib(q_top) : 0u;
+    auto preamble = [&](int q) -> bool {
+        nib_cur = nib_nxt;
+        if (q >= 3) nib_nxt = load_nib(q - 1);
+        const bool clean = kb1 == kb2 && kb2 == kb3;
+        kb1 = kb2; kb2 = kb3; kb3 = kb[q - 4];
+        return 4 * q - 1 <= nd - 2 && q >= 2 && clean;
+    };
+    // segment of block q: blocks QSEG*k + 1 .. QSEG*k + QSEG are the rows SEG*k .. SEG*k + SEG - 1
+    int k_have = (q_top - 1) / QSEG + 2;
+    prefetch_ckpt(k_have - 1);
+    for (int q = q_top; q >= 1;) {
+        const int kq = (q - 1) / QSEG;
+        if (k_have > kq) { // one call site: the two segments at the top first, then one per QSEG blocks
+            --k_have;
+            load_segment(k_have);
+            base = SEG * k_have - kSegBelow;
+            continue;
+        }
+        if (preamble(q)) {
+            const f2 *rp = buf + (size_t)(4 * q - 1 - base) * RS + kPlaneHalo + lane;
+            const unsigned nib = nib_cur;
+#pragma unroll kBwdUnroll
+            for (int k = 0; k < 4; k++) {
+                f2 bMD[C];
+                bwd_step<C, ROWS, false, false, true>(pc, a, st, rp - k * RS, W, nullptr, boff, bMD, k);
+                hand_off(bMD);
+                const int dec = (int)(((nib >> (3 - k)) & 1u) ^ 1u);
+#pragma unroll
+                for (int c = 0; c < C; c++) st.x[c] -= dec;
+            }
+#pragma unroll
+            for (int c = 0; c < C; c++) st.rbp[c] -= 4;
+        } else {
+            for (int s = min(4 * q - 1, nd - 1); s >= 4 * q - 4; --s) slow_step(s);
+        }
+        retire();
+        --q;
+    }
+#pragma unroll
+    for (int c = 0; c < C; c++)
+        if (st.j[c] >= 0) flush_col(c);
+}
+
+template <int C, int ROWS>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, fused_ctas_per_sm(C)) modtable_fused_kernel(KParams p) {
+    __shared__ LeanSmem fsh;
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    fill_lean_tables(fsh, p.models);
+    LeanSmem &bsh = fsh;
+    constexpr int NSLOT = 32 * C, RS = C * kPlane, PADR = NSLOT + 16;
+    constexpr int BUFB = seg_buf_rows<C>() * RS * 8, CKS = ckpt_stage_bytes<C>();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *wsm = dyn_smem + (size_t)warp * (BUFB + CKS + p.smem_rb);
+    f2 *buf = reinterpret_cast<f2 *>(wsm);
+    unsigned char *ckstage = wsm + BUFB;
+    unsigned char *rb_s = wsm + BUFB + CKS; // rb_s[i + PADR] = 4*idx of read row i
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&bsh.bar[warp]);
+    unsigned phase = 0u;
+    if (lane == 0) mbar_init(bar, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    const size_t wslot = (size_t)blockIdx.x * kWarpsPerCta + warp;
+    unsigned char *ckpt_g = reinterpret_cast<unsigned char *>(p.frows) + wslot * p.frow_stride; // frow_stride: BYTES per warp slot here
+    int32_t *kb = p.kf + wslot * p.kf_stride + 4;                                               // kb[q], q >= -4
+    volatile float *s_ftot = bsh.ftot[warp];
+    for (;;) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(p.counter, 1);
+        k = __shfl_sync(kFull, k, 0);
+        if (p.pair_lo + k >= p.pair_hi) break;
+        const int pi = pair_index(p, k);
+        const DevPair P = p.pairs[pi];
+        const int Lt = P.Lt, Lr = P.Lr, nd = Lt + Lr + 1;
+        const Coef a = load_coef(bsh.trans[P.model], bsh.cpair[P.model]);
+        unsigned *info = p.fwdinfo + (size_t)k * p.fwdinfo_stride;
+        {   // stage the read codes of this pair as compact table offsets
+            const uint8_t *Rb = p.codes + P.rb_off;
+            const int nr = Lr + 2 * PADR;
+            for (int w = lane; w < nr; w += 32) rb_s[w] = Rb[w - PADR];
+            if (lane < 4) { kb[lane - 4] = 0; s_ftot[lane] = 0.f; }
+        }
+        __syncwarp();
+        LeanPair lp;
+        lp.Tb = p.codes + P.tb_off; lp.bw = p.bits + P.bits_off; lp.rb0 = rb_s + PADR;
+        lp.Lt = Lt; lp.Lr = Lr; lp.nd = nd; lp.r = p.radius;
+        lp.sEM = (unsigned)__cvta_generic_to_shared(&fsh.em[P.model][0]);
+        lp.sEI = (unsigned)__cvta_generic_to_shared(&fsh.ei[P.model][0]);
+        int K = 0;
+        {   // ---- pass 1 ----
+            LeanFwd<C> st;
+#pragma unroll
+            for (int p = 0; p < C / 2; p++) st.inMb[p] = st.inMa[p] = st.inD[p] = st.toI[p] = 0ull;
+            int ups = 0;
+            lean_seed<C>(fsh, st, lp, 0, 0);
+            const LeanCoef la = load_lean_coef(fsh.cdup[P.model]);
+            lean_forward<C, 0>(fsh, la, st, lp, 0, nd, K, ups, kb, ckpt_g, nullptr, s_ftot);
+            for (int q = ((nd + 3) >> 2) + lane; q <= ((nd + 3) >> 2) + 2; q += 32) kb[q] = K; // blocks past the last row
+        }
+        __syncwarp();
+        const float fin = s_ftot[0];
+        if (lane < 4) info[lane] = __float_as_uint(s_ftot[lane]);
+        if (lane == 4) info[4] = (unsigned)K;
+        if (lane == 0) p.out_lk[pi] = fin > 0.f ? log((double)fin) - (double)K * 0.6931471805599453 : -INFINITY;
+        // the checkpoints were written through the generic proxy: order them before the async-proxy reads
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        __syncwarp();
+        // ---- pass 2 ----
+        const PairCtx pc = make_pair_ctx(p, P, bsh);
+        backward_fused<C, ROWS>(pc, a, fsh, P.model, lp, kb, ckpt_g, p.raw, (unsigned)k * (unsigned)p.raw_stride, s_ftot, buf, ckstage, bar, phase);
+        __syncwarp();
+    }
+}
+
 // host-callable launchers ---------------------------------------------------------------------------
 int cols_per_lane_for_radius(int radius) {
     // the slot ring must satisfy 2r + 4 <= 32*C
@@ -1225,6 +1770,52 @@ static cudaError_t launch_modtable_cr(const KParams &p, int grid_fwd, int grid_b
 template <int C>
 static cudaError_t launch_modtable_c(const KParams &p, int rows, int grid_fwd, int grid_bwd, cudaStream_t st) {
     return rows == 14 ? launch_modtable_cr<C, 14>(p, grid_fwd, grid_bwd, st) : launch_modtable_cr<C, 9>(p, grid_fwd, grid_bwd, st);
+}
+
+template <int C, int ROWS>
+static cudaError_t launch_fused_cr(const KParams &p, int grid, int dyn, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(modtable_fused_kernel<C, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    if (e != cudaSuccess) return e;
+    modtable_fused_kernel<C, ROWS><<<grid, kWarpsPerCta * 32, dyn, st>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    finalize_kernel<<<dim3((unsigned)((p.max_lt + kFinCols) / kFinCols), (unsigned)(p.pair_hi - p.pair_lo)), kFinCols, 0, st>>>(p);
+    return cudaGetLastError();
+}
+template <int C> static int fused_dyn_c(int smem_rb) { return kWarpsPerCta * (seg_buf_rows<C>() * C * kPlane * 8 + ckpt_stage_bytes<C>() + smem_rb); }
+// dynamic shared memory of one CTA of the fused kernel: per warp the row buffer, the checkpoint landing zone and the staged read codes
+int fused_dyn_smem(int C, int smem_rb) { return C == 2 ? fused_dyn_c<2>(smem_rb) : (C == 4 ? fused_dyn_c<4>(smem_rb) : fused_dyn_c<8>(smem_rb)); }
+// resident CTAs of the fused kernel on sm_count SMs (registers and shared memory decide; at most fused_ctas_per_sm(C) per SM)
+int fused_grid(int C, int rows, int dyn, int sm_count) {
+    int n = 0;
+    auto occ = [&](auto kern) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn) != cudaSuccess) { n = 0; return; }
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kWarpsPerCta * 32, (size_t)dyn) != cudaSuccess) n = 0;
+    };
+    switch (C) {
+    case 2: if (rows == 14) occ(modtable_fused_kernel<2, 14>); else occ(modtable_fused_kernel<2, 9>); break;
+    case 4: if (rows == 14) occ(modtable_fused_kernel<4, 14>); else occ(modtable_fused_kernel<4, 9>); break;
+    case 8: if (rows == 14) occ(modtable_fused_kernel<8, 14>); else occ(modtable_fused_kernel<8, 9>); break;
+    default: break;
+    }
+    return std::min(n, fused_ctas_per_sm(C)) * sm_count;
+}
+// bytes of checkpoints / ints of block exponents one warp slot needs for pairs of up to max_nd anti-diagonals
+size_t fused_ckpt_bytes(int C, int max_nd) {
+    const size_t seg = C == 2 ? seg_rows<2>() : seg_rows<4>(), ckb = C == 2 ? ckpt_bytes<2>() : (C == 4 ? ckpt_bytes<4>() : ckpt_bytes<8>());
+    return (((size_t)max_nd + kSegBelow) / seg + 2) * ckb;
+}
+size_t fused_kb_ints(int max_nd) { return (size_t)((max_nd + 3) >> 2) + 12; }
+
+// the fused modification table (v10): pairs [p.pair_lo, p.pair_hi), p.frows / p.frow_stride = checkpoint scratch (bytes per warp slot)
+cudaError_t launch_modtable_fused(const KParams &p, int C, int grid, cudaStream_t st) {
+    const int dyn = fused_dyn_smem(C, p.smem_rb);
+    switch (C) {
+    case 2: return p.rows == 14 ? launch_fused_cr<2, 14>(p, grid, dyn, st) : launch_fused_cr<2, 9>(p, grid, dyn, st);
+    case 4: return p.rows == 14 ? launch_fused_cr<4, 14>(p, grid, dyn, st) : launch_fused_cr<4, 9>(p, grid, dyn, st);
+    case 8: return p.rows == 14 ? launch_fused_cr<8, 14>(p, grid, dyn, st) : launch_fused_cr<8, 9>(p, grid, dyn, st);
+    default: return cudaErrorInvalidValue;
+    }
 }
 
 // one wave of the modification table: forward kernel, then backward kernel, pairs [p.pair_lo, p.pair_hi)

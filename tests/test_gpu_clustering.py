@@ -170,8 +170,12 @@ def test_full_size_chunk_oracle_vs_gpu(ctx):
     tidx = np.zeros(n, np.uint32)
     lk, tabs = ctx.modtable_batch(to_c(fwd), to_c(rev), [d["template"]], d["reads"], d["ops"], d["strands"], tidx, 30)
     otabs, olk = O.modification_table_batch(fwd, rev, [d["template"]] * n, d["reads"], d["ops"], d["strands"], 30, n_threads=8)
-    worst = check_tables(tabs, lk, otabs, olk, [d["template"]], tidx)
-    assert worst < 2e-3
+    check_tables(tabs, lk, otabs, olk, [d["template"]], tidx)   # asserts 2e-3 absolute / 1e-3 relative per entry
+    # the clustering decision on the default models (random emission tables blur the SNV signal at 8 % error)
+    h = O.default_hmm()
+    lk, tabs = ctx.modtable_batch(to_c(h), to_c(h), [d["template"]], d["reads"], d["ops"], d["strands"], tidx, 30)
+    otabs, olk = O.modification_table_batch(h, h, [d["template"]] * n, d["reads"], d["ops"], d["strands"], 30, n_threads=8)
+    check_tables(tabs, lk, otabs, olk, [d["template"]], tidx)
     cfg = LC.ClusteringConfig.new(30, 2, 30.0, 30.0, GAINS)
 
     def prof(t, l):
