@@ -1228,7 +1228,8 @@ constexpr int kSegKeep = 8;   // rows of the segment above that stay in the buff
 constexpr int kSegBelow = 4;  // a segment's rows start this far below its first backward row
 template <int C> __host__ __device__ constexpr int seg_buf_rows() { return seg_rows<C>() + kSegKeep; }
 template <int C> __host__ __device__ constexpr int ckpt_bytes() { return C * 512 + 16; }
-template <int C> __host__ __device__ constexpr int ckpt_stage_bytes() { return (ckpt_bytes<C>() + 127) & ~127; }
+// landing zone of a checkpoint in shared memory, followed by the warp's mbarrier (8 B at +0) and its four end sums (16 B at +16)
+template <int C> __host__ __device__ constexpr int ckpt_stage_bytes() { return (ckpt_bytes<C>() + 32 + 127) & ~127; }
 constexpr int fused_ctas_per_sm(int C) { return C == 2 ? 3 : (C == 4 ? 2 : 1); }
 
 // shared tables of the fused kernel (as BwdSmem): both passes look emissions up with the raw read-row code byte w = ctx<<5 | q<<2,
@@ -1258,6 +1259,13 @@ __device__ __forceinline__ void fill_lean_tables(LeanSmem &sh, const float *__re
     }
     __syncthreads();
 }
+
+// kb[q] of one warp slot as (kernel-parameter base, 32-bit offset): no 64-bit pointer has to stay in registers
+struct KbRef {
+    int32_t *base;
+    int off;
+    __device__ __forceinline__ int32_t &operator[](int i) const { return base[off + i]; }
+};
 
 struct LeanPair { // warp-uniform view of one pair for the lean forward pass
     const uint8_t *Tb;        // Tb[j] = code of t[j-1]
@@ -1317,8 +1325,8 @@ __device__ __forceinline__ void lean_seed(const LeanSmem &sh, LeanFwd<C> &st, co
 // (entry `lane` of plane 0 of row s_begin).
 template <int C, int MODE>
 __device__ __forceinline__ void lean_forward(const LeanSmem &sh, const LeanCoef &a, LeanFwd<C> &st, const LeanPair &lp, const int s_begin,
-                                             const int s_end, int &K, int &ups, int32_t *__restrict__ kb,
-                                             unsigned char *__restrict__ ckpt_g, f2 *wrow, volatile float *s_ftot) {
+                                             const int s_end, int &K, int &ups, const KbRef kb,
+                                             unsigned char *__restrict__ ckpt_g, f2 *wrow, volatile float *s_ftot, unsigned &ev) {
     constexpr int NSLOT = 32 * C, RS = C * kPlane, SEG = seg_rows<C>(), CKB = ckpt_bytes<C>(), P = C / 2;
     const int lane = threadIdx.x & 31, W = 2 * lp.r, nd = lp.nd;
     // the cells of one anti-diagonal: out-sums (toM, toD, toI) of the slot pairs
@@ -1412,6 +1420,7 @@ __device__ __forceinline__ void lean_forward(const LeanSmem &sh, const LeanCoef 
             }
             if (lane == 0) *reinterpret_cast<int4 *>(ck + C * 512) = make_int4(ups, K, 0, 0);
         }
+        if (MODE == 1) ev &= ~(1u << ((s >> 2) & 31)); // ev bit (b & 31): the forward pass rescaled at the end of block b
         if (s >= 4 && s + 3 < nd - 4) {
             const int Knew = (MODE == 1) ? kb[s >> 2] : 0;
 #pragma unroll
@@ -1435,6 +1444,7 @@ __device__ __forceinline__ void lean_forward(const LeanSmem &sh, const LeanCoef 
                     } else if (Knew != K) {
                         rescale_by(Knew - K, tM, tD, nI);
                         K = Knew;
+                        ev |= 1u << ((s >> 2) & 31);
                     }
                 }
                 finish(kk, tM, tD, nI);
@@ -1462,18 +1472,27 @@ __device__ __forceinline__ void lean_forward(const LeanSmem &sh, const LeanCoef 
 
 template <int C, int ROWS>
 __device__ __forceinline__ void backward_fused(const PairCtx &pc, const Coef &a, const LeanSmem &fsh, const int model, const LeanPair &lp,
-                                               int32_t *__restrict__ kb, unsigned char *__restrict__ ckpt_g,
-                                               float4 *__restrict__ raw_base, const unsigned rawk, volatile float *s_ftot, f2 *buf,
-                                               unsigned char *ckstage, const unsigned bar, unsigned &phase) {
+                                               const KbRef kb, const KParams &p, const unsigned wslot, const unsigned rawk,
+                                               unsigned char *wsm, unsigned &phase) {
+    // per-warp shared memory: [row buffer][checkpoint landing zone | mbarrier | end sums][staged read codes]
+    f2 *buf = reinterpret_cast<f2 *>(wsm);
+    unsigned char *ckstage = wsm + seg_buf_rows<C>() * (C * kPlane) * 8;
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(ckstage + ckpt_bytes<C>());
+    volatile float *s_ftot = reinterpret_cast<volatile float *>(ckstage + ckpt_bytes<C>() + 16);
+    float4 *raw_base = p.raw;
+    unsigned ev = 0u; // rescale events of the forward blocks in the buffer (set by the recomputation)
     constexpr int NSLOT = 32 * C;
     constexpr int RS = C * kPlane;
     constexpr int SEG = seg_rows<C>(), CKB = ckpt_bytes<C>();
     constexpr int QSEG = SEG / 4; // backward blocks per segment
     const int lane = threadIdx.x & 31;
     const int Lt = pc.Lt, nd = pc.nd, W = 2 * pc.r;
-    const float fin_raw = s_ftot[0];
-    const int e_fin = (int)(__float_as_uint(fin_raw) >> 23) - 127;
-    const float boff = fin_raw > 0.f ? pow2i(max(-120, min(120, kProductExp - e_fin))) : 1.f;
+    // B(Lr, Lt) = boff puts sum_cells F*B = fin * boff at about 2^kProductExp (read where it is used: the first step only)
+    auto boff_of = [&]() -> float {
+        const float fin_raw = s_ftot[0];
+        const int e_fin = (int)(__float_as_uint(fin_raw) >> 23) - 127;
+        return fin_raw > 0.f ? pow2i(max(-120, min(120, kProductExp - e_fin))) : 1.f;
+    };
 
     // ---- forward rows of one segment, recomputed into the buffer ---------------------------------------
     const unsigned ck_s = (unsigned)__cvta_generic_to_shared(ckstage);
@@ -1481,7 +1500,7 @@ __device__ __forceinline__ void backward_fused(const PairCtx &pc, const Coef &a,
         if (k >= 1 && SEG * k - kSegBelow < nd) {
             if (elect_one()) {
                 mbar_expect_tx(bar, (unsigned)CKB);
-                bulk_g2s(ck_s, ckpt_g + (size_t)k * CKB, (unsigned)CKB, bar);
+                bulk_g2s(ck_s, reinterpret_cast<const unsigned char *>(p.frows) + (size_t)wslot * p.frow_stride + (size_t)k * CKB, (unsigned)CKB, bar);
             }
         }
     };
@@ -1516,7 +1535,7 @@ __device__ __forceinline__ void backward_fused(const PairCtx &pc, const Coef &a,
             }
             lean_seed<C>(fsh, st, lp, s_from, ups);
             const LeanCoef la = load_lean_coef(fsh.cdup[model]); // live during the recomputation only
-            lean_forward<C, 1>(fsh, la, st, lp, s_from, s_to, K, ups, kb, nullptr, buf + (size_t)(s_from - s0) * RS + kPlaneHalo + lane, s_ftot);
+            lean_forward<C, 1>(fsh, la, st, lp, s_from, s_to, K, ups, kb, nullptr, buf + (size_t)(s_from - s0) * RS + kPlaneHalo + lane, s_ftot, ev);
             __syncwarp();
             // the first / last two entries of every plane are replicated past its other end
             for (int w = lane; w < (s_to - s_from) * C * 2 * kPlaneHalo; w += 32) {
@@ -1595,9 +1614,9 @@ __device__ __forceinline__ void backward_fused(const PairCtx &pc, const Coef &a,
             }
         }
     };
-    int base = 0; // anti-diagonal held by buffer row 0
+    int k_have = 0; // segment in the buffer; buffer row 0 holds anti-diagonal SEG * k_have - kSegBelow
     auto slow_step = [&](int s) {
-        const f2 *rp = buf + (size_t)(s - base) * RS + kPlaneHalo + lane;
+        const f2 *rp = buf + (size_t)(s - (SEG * k_have - kSegBelow)) * RS + kPlaneHalo + lane;
         auto kfat = [&](int t) -> int { return kb[(t - 3) >> 2]; };
         const int kcur = kfat(s);
         const int kstep = kcur - kfat(s - 1);
@@ -1605,8 +1624,8 @@ __device__ __forceinline__ void backward_fused(const PairCtx &pc, const Coef &a,
 #pragma unroll
         for (int e = -3; e <= 3; e++) ce[e + 3] = pow2i(max(-126, min(126, kcur - kfat(s + e))));
         f2 bMD[C];
-        if (s == nd - 1) bwd_step<C, ROWS, true, true, true>(pc, a, st, rp, W, ce, boff, bMD);
-        else bwd_step<C, ROWS, true, false, true>(pc, a, st, rp, W, ce, boff, bMD);
+        if (s == nd - 1) bwd_step<C, ROWS, true, true, true>(pc, a, st, rp, W, ce, boff_of(), bMD);
+        else bwd_step<C, ROWS, true, false, true>(pc, a, st, rp, W, ce, 0.f, bMD);
 #pragma unroll
         for (int c = 0; c < C; c++) st.rbp[c] -= 1;
         hand_off(bMD);
@@ -1623,7 +1642,6 @@ __device__ __forceinline__ void backward_fused(const PairCtx &pc, const Coef &a,
     };
 
     const int q_top = (nd + 3) >> 2; // block of the last anti-diagonal
-    int kb1 = kb[q_top - 1], kb2 = kb[q_top - 2], kb3 = kb[q_top - 3];
     auto load_nib = [&](int q) -> unsigned { // guide bits 4q-5 .. 4q-2 of block q >= 2
         const int b0 = 4 * q - 5;
         return __funnelshift_r(pc.bw[b0 >> 5], pc.bw[(b0 >> 5) + 1], b0 & 31);
@@ -1632,28 +1650,27 @@ __device__ __forceinline__ void backward_fused(const PairCtx &pc, const Coef &a,
     auto preamble = [&](int q) -> bool {
         nib_cur = nib_nxt;
         if (q >= 3) nib_nxt = load_nib(q - 1);
-        const bool clean = kb1 == kb2 && kb2 == kb3;
-        kb1 = kb2; kb2 = kb3; kb3 = kb[q - 4];
+        // block q touches forward rows 4q-7 .. 4q+2: exact corrections iff the forward pass rescaled at the end of block q-1 or q-2
+        const bool clean = (__funnelshift_r(ev, ev, (q - 2) & 31) & 3u) == 0u;
         return 4 * q - 1 <= nd - 2 && q >= 2 && clean;
     };
     // segment of block q: blocks QSEG*k + 1 .. QSEG*k + QSEG are the rows SEG*k .. SEG*k + SEG - 1
-    int k_have = (q_top - 1) / QSEG + 2;
+    k_have = (q_top - 1) / QSEG + 2;
     prefetch_ckpt(k_have - 1);
     for (int q = q_top; q >= 1;) {
         const int kq = (q - 1) / QSEG;
         if (k_have > kq) { // one call site: the two segments at the top first, then one per QSEG blocks
             --k_have;
             load_segment(k_have);
-            base = SEG * k_have - kSegBelow;
             continue;
         }
         if (preamble(q)) {
-            const f2 *rp = buf + (size_t)(4 * q - 1 - base) * RS + kPlaneHalo + lane;
+            const f2 *rp = buf + (size_t)(4 * q - 1 - (SEG * k_have - kSegBelow)) * RS + kPlaneHalo + lane;
             const unsigned nib = nib_cur;
 #pragma unroll kBwdUnroll
             for (int k = 0; k < 4; k++) {
                 f2 bMD[C];
-                bwd_step<C, ROWS, false, false, true>(pc, a, st, rp - k * RS, W, nullptr, boff, bMD, k);
+                bwd_step<C, ROWS, false, false, true>(pc, a, st, rp - k * RS, W, nullptr, 0.f, bMD, k);
                 hand_off(bMD);
                 const int dec = (int)(((nib >> (3 - k)) & 1u) ^ 1u);
 #pragma unroll
@@ -1685,15 +1702,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, fused_ctas_per_sm(C)) modta
     f2 *buf = reinterpret_cast<f2 *>(wsm);
     unsigned char *ckstage = wsm + BUFB;
     unsigned char *rb_s = wsm + BUFB + CKS; // rb_s[i + PADR] = 4*idx of read row i
-    const unsigned bar = (unsigned)__cvta_generic_to_shared(&bsh.bar[warp]);
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(ckstage + ckpt_bytes<C>());
     unsigned phase = 0u;
     if (lane == 0) mbar_init(bar, 1u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
     const size_t wslot = (size_t)blockIdx.x * kWarpsPerCta + warp;
     unsigned char *ckpt_g = reinterpret_cast<unsigned char *>(p.frows) + wslot * p.frow_stride; // frow_stride: BYTES per warp slot here
-    int32_t *kb = p.kf + wslot * p.kf_stride + 4;                                               // kb[q], q >= -4
-    volatile float *s_ftot = bsh.ftot[warp];
+    const KbRef kb = { p.kf, (int)(wslot * p.kf_stride) + 4 };                                 // kb[q], q >= -4
+    volatile float *s_ftot = reinterpret_cast<volatile float *>(ckstage + ckpt_bytes<C>() + 16);
     for (;;) {
         int k = 0;
         if (lane == 0) k = atomicAdd(p.counter, 1);
@@ -1724,7 +1741,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, fused_ctas_per_sm(C)) modta
             int ups = 0;
             lean_seed<C>(fsh, st, lp, 0, 0);
             const LeanCoef la = load_lean_coef(fsh.cdup[P.model]);
-            lean_forward<C, 0>(fsh, la, st, lp, 0, nd, K, ups, kb, ckpt_g, nullptr, s_ftot);
+            unsigned ev_unused = 0u;
+            lean_forward<C, 0>(fsh, la, st, lp, 0, nd, K, ups, kb, ckpt_g, nullptr, s_ftot, ev_unused);
             for (int q = ((nd + 3) >> 2) + lane; q <= ((nd + 3) >> 2) + 2; q += 32) kb[q] = K; // blocks past the last row
         }
         __syncwarp();
@@ -1737,7 +1755,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, fused_ctas_per_sm(C)) modta
         __syncwarp();
         // ---- pass 2 ----
         const PairCtx pc = make_pair_ctx(p, P, bsh);
-        backward_fused<C, ROWS>(pc, a, fsh, P.model, lp, kb, ckpt_g, p.raw, (unsigned)k * (unsigned)p.raw_stride, s_ftot, buf, ckstage, bar, phase);
+        backward_fused<C, ROWS>(pc, a, fsh, P.model, lp, kb, p, (unsigned)wslot, (unsigned)k * (unsigned)p.raw_stride, wsm, phase);
         __syncwarp();
     }
 }
