@@ -156,14 +156,28 @@ class ClockSampler:
                 "samples": len(sm), "source": "nvidia-smi -lms 200"}
 
 
-def ncu_traffic(n_pairs):
-    """DRAM bytes per modtable launch from the committed `ncu --set full` capture (profiles/r1_traffic.json:
-    dram__bytes_read.sum + dram__bytes_write.sum of one launch and the number of pairs in it), scaled to this launch."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+def ncu_traffic(n_pairs, variant):
+    """DRAM bytes per modification-table launch sequence of `variant` ("fused" | "rows") from the committed `ncu --set full`
+    captures (profiles/r2_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum and the number of pairs), scaled to
+    this launch."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if not os.path.exists(p):
         return None
     t = json.load(open(p))
-    return (t["dram_bytes_read"] + t["dram_bytes_write"]) * n_pairs / t["pairs_in_launch"]
+    if variant not in t:
+        return None
+    return (t[variant]["dram_bytes_read"] + t[variant]["dram_bytes_write"]) * n_pairs / t["pairs_in_launch"]
+
+
+KERNELS = {"fused": "modtable_fused_kernel<2,14> (pass 1: checkpoints; pass 2: forward rows recomputed per 16-row segment in shared "
+                    "memory + backward + table sums) + finalize_kernel",
+           "rows": "fwdrows_kernel<2> + bwdtable_kernel<2,14> + finalize_kernel (forward rows parked in HBM; bwdtable is ~65 % of it)"}
+TRAFFIC_NOTE = {"fused": "dram__bytes_read.sum + dram__bytes_write.sum of modtable_fused_kernel + finalize_kernel (ncu --set full, "
+                         "profiles/r2_traffic.json): checkpoints (65 B per anti-diagonal, written once, read once, partly from "
+                         "L2), the raw column sums between the two kernels and the profiles; no DP matrix",
+                "rows": "dram__bytes_read.sum + dram__bytes_write.sum of the three kernels (ncu --set full, profiles/r2_traffic.json): "
+                        "the forward-row scratch (2 x 2.3 MB per pair: written by fwdrows at 6.0 TB/s, read back by bwdtable), "
+                        "not the algorithmic bytes, see roofline.hbm"}
 
 
 def measured_peaks():
@@ -389,8 +403,9 @@ def workload_config(args):
                         f"{args.reads} ONT-like reads ({args.length} bp, 8% error), radius {RADIUS}, 14-row table + column stats, per GPU",
             "chunks_per_gpu": args.chunks, "reads_per_chunk": args.reads, "chunk_len": args.length, "radius": RADIUS,
             "rows": 14, "parallelism": "chunks sharded over ranks, no collective",
-            "l2": "no explicit flush: each step streams ~22 GB of forward rows + 0.5 GB of profiles per GPU through HBM "
-                  "(>> 126 MB L2), so the 25 MB of inputs are evicted between steps"}
+            "l2": "no explicit flush: each step writes 0.6 GB of raw column sums and 0.5 GB of profiles per GPU, plus 1.2 GB of "
+                  "checkpoints (fused variant) or 11 GB of forward rows (rows variant), all read back (>> 126 MB L2), so the "
+                  "25 MB of inputs are evicted between steps"}
 
 
 def main():
@@ -481,6 +496,37 @@ def main():
     wall_ms = (time.perf_counter() - t0) * 1e3
     launches = ctx.launch_count - l0
     ktimes = ctx.kernel_times()
+    variant = ctx.last_modtable_variant
+
+    # the other modification-table variant on the same batch (bit-identical tables, tests/test_gpu_parity.py), as an extra
+    variants = {}
+    if rank == 0:
+        saved = os.environ.get("JTK_MODTABLE")
+        for v in ("fused", "rows"):
+            os.environ["JTK_MODTABLE"] = v
+            try:
+                for _ in range(2):
+                    batch.modtable(fwd, rev, 14)
+                batch.sync()
+                ctx.kernel_times()
+                n_v = max(3, args.steps // 4)
+                for _ in range(n_v):
+                    batch.modtable(fwd, rev, 14)
+                batch.sync()
+                kt = ctx.kernel_times()
+                ms_v = float(np.mean(kt)) if len(kt) else None
+                variants[v] = {"kernel_ms": ms_v, "gcups_kernel": cells / (ms_v * 1e-3) / 1e9 if ms_v else None,
+                               "dram_bytes_per_launch": ncu_traffic(len(reads), v)}
+            except Exception as exc:  # e.g. not enough device memory for the forward rows of one wave
+                variants[v] = {"error": str(exc)}
+        if saved is None:
+            os.environ.pop("JTK_MODTABLE", None)
+        else:
+            os.environ["JTK_MODTABLE"] = saved
+        variants["default"] = variant
+        variants["note"] = ("fused: the DP matrices never touch HBM (checkpoints + recomputation in shared memory); rows: forward rows "
+                            "parked in HBM between two kernels (2.3 MB per pair). Same tables bit for bit; the library takes 'rows' "
+                            "when the whole batch fits its scratch budget as one wave (JTK_SCRATCH_MB, JTK_MODTABLE overrides)")
 
     # 9-row (clustering rows only) variant, reported as an extra
     for _ in range(2):
@@ -568,17 +614,14 @@ def main():
         ach_tflops = cells * FLOPS_PER_CELL / (k_ms * 1e-3) / 1e12
         prof_bytes = float(sum((len(templates[int(t)]) + 1) * 14 * 4 for t in tidx))
         in_bytes = float(batch.h2d_bytes)
-        roof = {"bound": "fp32", "kernel": "fwdrows_kernel<2> + bwdtable_kernel<2,14> + finalize_kernel (one modification-table "
-                                          "launch sequence; bwdtable is ~65 % of it)", "achieved": ach_tflops, "peak": ffma,
+        roof = {"bound": "fp32", "kernel": KERNELS.get(variant, variant), "variant": variant, "achieved": ach_tflops, "peak": ffma,
                 "unit": "TFLOP/s", "frac": ach_tflops / ffma if ffma else None,
                 "peak_source": "measured in this run: register-resident fma.rn.f32 loop on all SMs "
                                "(MEASURED_PEAKS.json holds only HBM and bf16 figures)",
                 "peak_ffma2": ffma2, "flops_per_cell_update": FLOPS_PER_CELL,
                 "cell_updates_per_launch": cells, "kernel_ms": k_ms, "gcups_kernel": cells / (k_ms * 1e-3) / 1e9,
-                "traffic": ncu_traffic(len(reads)),
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the three kernels of one launch sequence (ncu --set "
-                                "full, profiles/r1_traffic.json); it is the forward-row scratch (2 x 2.3 MB per pair: written by "
-                                "fwdrows at 6.0 TB/s, read back by bwdtable), not the algorithmic bytes, see roofline.hbm",
+                "traffic": ncu_traffic(len(reads), variant),
+                "traffic_note": TRAFFIC_NOTE.get(variant, ""),
                 "hbm": {"algorithmic_bytes_per_launch": prof_bytes + in_bytes,
                         "achieved_gbs": (prof_bytes + in_bytes) / (k_ms * 1e-3) / 1e9,
                         "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src}}
@@ -613,6 +656,7 @@ def main():
                       "wall_ms_per_step": wall_step,
                       "rows9": {"ms_per_step": ms9, "gcups": cells / (ms9 * 1e-3) / 1e9,
                                 "chunks_per_s": args.chunks / (ms9 * 1e-3), "note": "rank 0 only"},
+                      "modtable_variants": variants,
                       "chunks_phased": phased, **extras},
         }
         print(json.dumps(line), flush=True)

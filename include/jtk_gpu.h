@@ -79,6 +79,10 @@ int jtk_hmm_del_size(void);
 uint64_t jtk_ctx_launch_count(const jtk_ctx *ctx);
 /* device time (ms, CUDA events on the ctx stream) of the dominant kernel in the last batch call */
 float jtk_ctx_last_kernel_ms(const jtk_ctx *ctx);
+/* which modification-table variant the last table call ran: 1 = fused kernel (forward rows recomputed in shared memory, the DP
+ * matrices never touch HBM), 2 = forward rows parked in HBM between a forward and a backward kernel (bit-identical results;
+ * chosen when the whole batch fits the scratch budget as one wave, or by JTK_MODTABLE=rows|fused), 0 = none yet */
+int jtk_ctx_last_modtable_variant(const jtk_ctx *ctx);
 /* measurement helpers (bench.py): bracket a region of work on the ctx stream with CUDA events */
 int jtk_ctx_timer_start(jtk_ctx *ctx);
 int jtk_ctx_timer_stop(jtk_ctx *ctx, float *ms); /* synchronises the stream */

@@ -21,7 +21,7 @@ TABLE_NEG = -1.0e10
 
 EXPORTS = [
     "jtk_ctx_create", "jtk_ctx_destroy", "jtk_last_error", "jtk_hmm_num_row", "jtk_hmm_copy_size",
-    "jtk_hmm_del_size", "jtk_ctx_launch_count", "jtk_ctx_last_kernel_ms", "jtk_hmm_modtable_batch",
+    "jtk_hmm_del_size", "jtk_ctx_launch_count", "jtk_ctx_last_kernel_ms", "jtk_ctx_last_modtable_variant", "jtk_hmm_modtable_batch",
     "jtk_hmm_likelihood_batch", "jtk_band_cell_count", "jtk_batch_create", "jtk_batch_destroy",
     "jtk_batch_cell_updates", "jtk_batch_h2d_bytes", "jtk_batch_modtable", "jtk_batch_sync", "jtk_batch_fetch_lk",
     "jtk_batch_fetch_profile", "jtk_batch_colstats", "jtk_batch_gather", "jtk_ctx_timer_start", "jtk_ctx_timer_stop",
@@ -76,6 +76,8 @@ def lib() -> C.CDLL:
     L.jtk_ctx_launch_count.restype = C.c_uint64
     L.jtk_ctx_last_kernel_ms.argtypes = [C.c_void_p]
     L.jtk_ctx_last_kernel_ms.restype = C.c_float
+    L.jtk_ctx_last_modtable_variant.argtypes = [C.c_void_p]
+    L.jtk_ctx_last_modtable_variant.restype = C.c_int
     batch = [C.c_void_p, C.POINTER(HmmParams), C.POINTER(HmmParams), C.c_int, C.c_int, vp, u32p, vp, u32p, vp, u32p,
              vp, u32p, C.c_int, vp]
     L.jtk_hmm_modtable_batch.argtypes = batch + [vp, u64p]
@@ -158,6 +160,11 @@ class Context:
     @property
     def last_kernel_ms(self) -> float:
         return float(lib().jtk_ctx_last_kernel_ms(self._h))
+
+    @property
+    def last_modtable_variant(self) -> str:
+        """'fused' (DP matrices stay on chip) or 'rows' (forward rows parked in HBM) for the last table call, '' before it."""
+        return {1: "fused", 2: "rows"}.get(int(lib().jtk_ctx_last_modtable_variant(self._h)), "")
 
     def timer_start(self):
         self._check(lib().jtk_ctx_timer_start(self._h))

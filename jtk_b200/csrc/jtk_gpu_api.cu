@@ -288,6 +288,7 @@ struct SmallUpload {
 struct jtk_ctx {
     int device = 0;
     int sm_count = 0;
+    int last_variant = 0; // modification-table variant of the last table run: 1 fused (no DP matrix in HBM), 2 forward rows in HBM
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
     static constexpr int kRing = 256;
@@ -331,7 +332,8 @@ struct jtk_ctx {
     PinBuf<uint8_t> h_homop;
     PinBuf<uint8_t> h_raw;                 // raw reads | raw ops of the batch being created (device encoder)
     DevBuf<uint8_t> d_rawin;
-    DevBuf<uint32_t> d_raw_off;            // read_off | ops_off
+    DevBuf<uint32_t> d_raw_off;            // read_off | ops_off (| bootstrap: ops region offsets | ops_start | ops_len)
+    DevBuf<uint32_t> d_boot;               // bootstrap_ops_kernel: 2 traceback bits per band cell
     DevBuf<int32_t> d_enc_status;          // EncStatus per pair | the cell count (8 bytes)
     PinBuf<uint32_t> h_raw_off;
     PinBuf<int32_t> h_enc_status;
@@ -361,6 +363,7 @@ int jtk_hmm_del_size(void) { return JTK_DEL_SIZE; }
 const char *jtk_last_error(const jtk_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 uint64_t jtk_ctx_launch_count(const jtk_ctx *ctx) { return ctx ? ctx->launches : 0; }
 float jtk_ctx_last_kernel_ms(const jtk_ctx *ctx) { return ctx ? ctx->last_ms : 0.f; }
+int jtk_ctx_last_modtable_variant(const jtk_ctx *ctx) { return ctx ? ctx->last_variant : 0; }
 
 int jtk_ctx_create(int device, size_t workspace_bytes, jtk_ctx **out) {
     (void)workspace_bytes;
@@ -401,7 +404,7 @@ void jtk_ctx_destroy(jtk_ctx *ctx) {
     cudaSetDevice(ctx->device);
     ctx->d_models.release(); ctx->d_frows.release(); ctx->d_kf.release(); ctx->d_fwdinfo.release(); ctx->d_raw.release(); ctx->d_counter.release();
     ctx->d_minreq.release(); ctx->d_cols.release(); ctx->d_gather.release();
-    ctx->h_raw.release(); ctx->h_raw_off.release(); ctx->h_enc_status.release(); ctx->d_rawin.release(); ctx->d_raw_off.release(); ctx->d_enc_status.release();
+    ctx->h_raw.release(); ctx->h_raw_off.release(); ctx->h_enc_status.release(); ctx->d_rawin.release(); ctx->d_raw_off.release(); ctx->d_boot.release(); ctx->d_enc_status.release();
     ctx->d_mc_chains.release(); ctx->d_mc_f64.release(); ctx->d_mc_lk.release(); ctx->d_mc_u32.release(); ctx->d_mc_u8.release();
     ctx->d_mc_asn.release(); ctx->d_mc_rng.release(); ctx->d_mc_asn_off.release(); ctx->d_mc_err.release();
     ctx->d_tabs.release(); ctx->d_tab_off.release(); ctx->d_cand.release(); ctx->h_cand.release(); ctx->h_gather.release();
@@ -552,12 +555,91 @@ __device__ __forceinline__ unsigned enc_base_code(unsigned c) { // A/a 0, C/c 1,
     return c == 'C' ? 1u : (c == 'G' ? 2u : (c == 'T' ? 3u : 0u));
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Device twin of edit_ops(): the guide of the "bootstrap" likelihood (kiley likelihood_antidiagonal_bootstrap,
+// likelihood_gains.rs:27-28,282-283,301-302 -- the 1.8e5 / 1e6 calibration pairs of ~100 bp), SURVEY.md 8f N3.
+// One THREAD per pair: banded global edit distance (band |i-j| <= R = radius + |Lr-Lt|), row by row with two rolling rows in
+// local memory; the traceback preference of the host (diagonal, then Del, then Ins) is decided when a cell is filled -- its
+// three predecessors are final then -- and kept as 2 bits per band cell (16 cells per word); the traceback writes the ops
+// backwards into the pair's region of `out_ops` and reports where they start.  Same ops as the host, byte for byte
+// (tests/test_gpu_parity.py::test_device_bootstrap_equals_host_bootstrap).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kBootMaxR = 127;
+constexpr int kBootBand = 2 * kBootMaxR + 3;
+
+__global__ void __launch_bounds__(128) bootstrap_ops_kernel(const DevPair *__restrict__ pairs, int n_pairs,
+                                                            const uint8_t *__restrict__ raw_reads, const uint32_t *__restrict__ read_off,
+                                                            const uint8_t *__restrict__ codes, int radius,
+                                                            uint32_t *__restrict__ tb, const uint32_t *__restrict__ tb_off,
+                                                            uint8_t *__restrict__ out_ops, const uint32_t *__restrict__ cap_off,
+                                                            uint32_t *__restrict__ ops_start, uint32_t *__restrict__ ops_len) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const DevPair dp = pairs[p];
+    const int Lt = dp.Lt, Lr = dp.Lr;
+    const uint8_t *q = raw_reads + read_off[p];
+    const uint8_t *tcode = codes + dp.tb_off; // tcode[j] = code of t[j-1]
+    const int R = radius + abs(Lr - Lt), Wb = 2 * R + 1;
+    const int INF = 1 << 29;
+    int rowa[kBootBand], rowb[kBootBand];
+    int *prev = rowa, *cur = rowb; // prev[b] = D[i-1][j] with b = j - (i-1) + R, one extra cell on both sides
+    for (int b = 0; b < Wb + 2; b++) { prev[b] = INF; cur[b] = INF; }
+    uint32_t *tbw = tb + tb_off[p];
+    uint32_t word = 0u;
+    size_t idx = 0;
+    for (int i = 0; i <= Lr; i++) {
+        const unsigned qc = i > 0 ? enc_base_code(q[i - 1]) : 0u;
+        for (int b = 0; b < Wb; b++, idx++) {
+            const int j = i - R + b;
+            int v = INF;
+            unsigned dir = 0u; // 1 diagonal, 2 Del (left), 3 Ins (up)
+            if (j >= 0 && j <= Lt) {
+                if (i == 0 && j == 0) v = 0;
+                else {
+                    // cells of the row above sit one band slot to the right: (i-1, j-1) -> b, (i-1, j) -> b+1 (index + 1 for the pad)
+                    int vd = INF, vl = INF, vu = INF;
+                    if (i > 0 && j > 0) vd = prev[b + 1] + (qc != (unsigned)tcode[j] ? 1 : 0);
+                    if (j > 0) vl = cur[b] + 1;       // (i, j-1) -> b-1
+                    if (i > 0) vu = prev[b + 2] + 1;  // (i-1, j) -> b+1
+                    v = min(min(min(v, vd), vl), vu);
+                    dir = (i > 0 && j > 0 && vd == v) ? 1u : ((j > 0 && vl == v) ? 2u : 3u);
+                }
+            }
+            cur[b + 1] = v;
+            word |= dir << (2 * (idx & 15));
+            if ((idx & 15) == 15) { tbw[idx >> 4] = word; word = 0u; }
+        }
+        cur[0] = INF; cur[Wb + 1] = INF;
+        int *t = prev; prev = cur; cur = t;
+    }
+    if (idx & 15) tbw[idx >> 4] = word;
+    // traceback, written backwards from the end of the pair's region
+    uint8_t *out = out_ops + cap_off[p];
+    const int cap = Lr + Lt;
+    int i = Lr, j = Lt, n = 0;
+    while (i > 0 || j > 0) {
+        const size_t c = (size_t)i * Wb + (size_t)(j - i + R);
+        const unsigned dir = (tbw[c >> 4] >> (2 * (c & 15))) & 3u;
+        uint8_t op;
+        if (dir == 1u) { op = enc_base_code(q[i - 1]) != (unsigned)tcode[j] ? JTK_OP_MISMATCH : JTK_OP_MATCH; i--; j--; }
+        else if (dir == 2u) { op = JTK_OP_DEL; j--; }
+        else { op = JTK_OP_INS; i--; }
+        out[cap - 1 - n] = op;
+        n++;
+    }
+    ops_start[p] = cap_off[p] + (uint32_t)(cap - n);
+    ops_len[p] = (uint32_t)n;
+}
+
 __global__ void __launch_bounds__(128) encode_pairs_kernel(const DevPair *__restrict__ pairs, int n_pairs,
                                                            const uint8_t *__restrict__ raw_reads, const uint32_t *__restrict__ read_off,
                                                            const uint8_t *__restrict__ raw_ops, const uint32_t *__restrict__ ops_off,
                                                            uint8_t *__restrict__ codes, uint32_t *__restrict__ bits, int radius,
                                                            int words_per_warp, EncStatus *__restrict__ status,
-                                                           unsigned long long *__restrict__ cells) {
+                                                           unsigned long long *__restrict__ cells,
+                                                           const uint32_t *__restrict__ ops_start = nullptr,
+                                                           const uint32_t *__restrict__ ops_len = nullptr) {
     extern __shared__ uint32_t enc_sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -590,8 +672,9 @@ __global__ void __launch_bounds__(128) encode_pairs_kernel(const DevPair *__rest
         }
     }
     __syncwarp();
-    const uint8_t *ops = raw_ops + ops_off[p];
-    const int n_ops = (int)(ops_off[p + 1] - ops_off[p]);
+    // guide ops of the caller, or the ones bootstrap_ops_kernel left (start / length per pair)
+    const uint8_t *ops = raw_ops + (ops_start ? ops_start[p] : ops_off[p]);
+    const int n_ops = ops_len ? (int)ops_len[p] : (int)(ops_off[p + 1] - ops_off[p]);
     const unsigned long long full = (unsigned long long)(2 * radius + 1);
     auto width = [&](int cen, int d) -> unsigned long long {
         const int lo = max(max(cen - radius, 0), d - Lt), hi = min(min(cen + radius, Lr), d);
@@ -838,7 +921,7 @@ int pack_batch(jtk_ctx *ctx, jtk_batch *b, const uint8_t *tmpl_concat, const uin
     ctx->tmpl_code_off = b->tmpl_code_off;
     b->table_floats = tab;
     b->cell_updates = cells_total.load();
-    b->h2d_bytes = (device_encode ? tmpl_code_bytes + (size_t)read_off[n_pairs] + (size_t)ops_off[n_pairs] + 8 * ((size_t)n_pairs + 1)
+    b->h2d_bytes = (device_encode ? tmpl_code_bytes + (size_t)read_off[n_pairs] + (ops_off ? (size_t)ops_off[n_pairs] : 0) + 8 * ((size_t)n_pairs + 1)
                                   : cb + bwords * sizeof(uint32_t)) +
                    hb + sizeof(DevPair) * (size_t)n_pairs + sizeof(uint32_t) * (4 * (size_t)n_tmpl + 3 + (size_t)n_pairs);
     code_bytes = cb; bit_words = bwords; homop_bytes = hb;
@@ -856,7 +939,6 @@ int batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_conc
         return ctx->fail(JTK_EINVAL, "null argument");
     if (n_pairs > 0 && !allow_bootstrap && (!ops_concat || !ops_off)) return ctx->fail(JTK_EINVAL, "guide ops are required");
     const int C = cols_per_lane_for_radius(radius);
-    if (n_tmpl > 65535) return ctx->fail(JTK_EINVAL, "more than 65535 templates in one batch (the per-chunk kernels put the template on grid.y): split the call");
     if (radius < 0 || C == 0 || C > 8) return ctx->fail(JTK_EINVAL, "radius out of range (0..126)");
     CU(cudaSetDevice(ctx->device), "cudaSetDevice");
     jtk_batch *b = new jtk_batch();
@@ -868,6 +950,33 @@ int batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_conc
     // from the raw reads and ops; otherwise on the host threads (see encode_pairs_kernel)
     bool device_encode = ops_concat != nullptr && ctx->host_threads < 6;
     if (const char *env = std::getenv("JTK_DEVICE_ENCODE")) device_encode = ops_concat != nullptr && std::atoi(env) != 0;
+    // No guide ops (bootstrap likelihood, the calibration pairs of likelihood_gains.rs): the banded edit-distance alignment runs
+    // on the device too (bootstrap_ops_kernel, one thread per pair) when every pair fits its limits, and feeds the device
+    // encoder; JTK_DEVICE_BOOTSTRAP=0 keeps the alignment on the host threads.
+    bool device_bootstrap = false;
+    std::vector<uint32_t> boot_off; // per pair: first traceback word, then (second half) first byte of its ops region
+    size_t boot_words = 0, boot_ops = 0;
+    if (!ops_concat && n_pairs > 0) {
+        device_bootstrap = true;
+        if (const char *env = std::getenv("JTK_DEVICE_BOOTSTRAP")) device_bootstrap = std::atoi(env) != 0;
+        boot_off.resize(2 * ((size_t)n_pairs + 1));
+        for (int p = 0; p < n_pairs && device_bootstrap; p++) {
+            if (read_off[p + 1] < read_off[p] || tmpl_idx[p] >= (uint32_t)n_tmpl) { device_bootstrap = false; break; } // pack_batch reports it
+            const long Lr = (long)(read_off[p + 1] - read_off[p]), Lt = (long)(tmpl_off[tmpl_idx[p] + 1] - tmpl_off[tmpl_idx[p]]);
+            const long R = radius + std::labs(Lr - Lt);
+            if (R > kBootMaxR || Lr + Lt > 16384) { device_bootstrap = false; break; }
+            boot_off[p] = (uint32_t)boot_words;
+            boot_off[(size_t)n_pairs + 1 + p] = (uint32_t)boot_ops;
+            boot_words += ((size_t)(Lr + 1) * (size_t)(2 * R + 1) + 15) / 16;
+            boot_ops += (size_t)(Lr + Lt);
+            if (boot_words > ((size_t)1 << 29) || boot_ops > ((size_t)1 << 31)) device_bootstrap = false; // 2 GiB of traceback bits
+        }
+        if (device_bootstrap) {
+            boot_off[n_pairs] = (uint32_t)boot_words;
+            boot_off[2 * (size_t)n_pairs + 1] = (uint32_t)boot_ops;
+            device_encode = true;
+        }
+    }
     int rc = pack_batch(ctx, b, tmpl_concat, tmpl_off, read_concat, read_off, ops_concat, ops_off, strand, tmpl_idx,
                         code_bytes, bit_words, homop_bytes, device_encode, tmpl_code_bytes);
     if (rc) { b->release(); delete b; return rc; }
@@ -892,14 +1001,14 @@ int batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_conc
         CB(cudaMemcpyAsync(b->d_codes.p, ctx->h_codes.p, code_bytes, cudaMemcpyHostToDevice, st), "H2D codes");
         CB(cudaMemcpyAsync(b->d_bits.p, ctx->h_bits.p, bit_words * sizeof(uint32_t), cudaMemcpyHostToDevice, st), "H2D bits");
     } else {
-        const size_t rb = read_off[n_pairs], ob = ops_off[n_pairs];
+        const size_t rb = read_off[n_pairs], ob = device_bootstrap ? boot_ops : ops_off[n_pairs];
         const size_t rb_pad = (rb + 255) & ~(size_t)255;
-        CB(ctx->h_raw.reserve(rb_pad + ob + 64), "cudaMallocHost raw reads / ops");
+        CB(ctx->h_raw.reserve(rb_pad + (device_bootstrap ? 0 : ob) + 64), "cudaMallocHost raw reads / ops");
         CB(ctx->d_rawin.reserve(rb_pad + ob + 64), "cudaMalloc raw reads / ops");
-        CB(ctx->d_raw_off.reserve(2 * ((size_t)n_pairs + 1)), "cudaMalloc raw offsets");
+        CB(ctx->d_raw_off.reserve((device_bootstrap ? 5 : 2) * ((size_t)n_pairs + 1)), "cudaMalloc raw offsets");
         CB(ctx->d_enc_status.reserve((size_t)4 * n_pairs + 4), "cudaMalloc encoder status");
         { // the caller's buffers -> pinned staging, on the host threads (1 MiB pieces)
-            const size_t piece = (size_t)1 << 20, nr = (rb + piece - 1) / piece, no = (ob + piece - 1) / piece;
+            const size_t piece = (size_t)1 << 20, nr = (rb + piece - 1) / piece, no = device_bootstrap ? 0 : (ob + piece - 1) / piece;
             uint8_t *hr = ctx->h_raw.p;
             ctx->hpool->run((int)(nr + no), 1, [&](int k) {
                 if ((size_t)k < nr) { const size_t o = (size_t)k * piece; std::memcpy(hr + o, read_concat + o, std::min(piece, rb - o)); }
@@ -908,19 +1017,33 @@ int batch_create(jtk_ctx *ctx, int n_pairs, int n_tmpl, const uint8_t *tmpl_conc
         }
         unsigned long long *d_cells = reinterpret_cast<unsigned long long *>(ctx->d_enc_status.p + (size_t)4 * n_pairs);
         CB(cudaMemcpyAsync(b->d_codes.p, ctx->h_codes.p, tmpl_code_bytes, cudaMemcpyHostToDevice, st), "H2D template codes");
-        CB(cudaMemcpyAsync(ctx->d_rawin.p, ctx->h_raw.p, rb_pad + ob, cudaMemcpyHostToDevice, st), "H2D raw reads / ops");
+        CB(cudaMemcpyAsync(ctx->d_rawin.p, ctx->h_raw.p, rb_pad + (device_bootstrap ? 0 : ob), cudaMemcpyHostToDevice, st), "H2D raw reads / ops");
         // offsets through pinned staging too: a copy from pageable memory synchronises the stream before it starts
-        CB(ctx->h_raw_off.reserve(2 * ((size_t)n_pairs + 1)), "cudaMallocHost raw offsets");
-        std::memcpy(ctx->h_raw_off.p, read_off, sizeof(uint32_t) * ((size_t)n_pairs + 1));
-        std::memcpy(ctx->h_raw_off.p + n_pairs + 1, ops_off, sizeof(uint32_t) * ((size_t)n_pairs + 1));
-        CB(cudaMemcpyAsync(ctx->d_raw_off.p, ctx->h_raw_off.p, sizeof(uint32_t) * 2 * ((size_t)n_pairs + 1), cudaMemcpyHostToDevice, st), "H2D raw offsets");
+        // layout: read_off | ops_off (or the bootstrap's traceback offsets) | ops region offsets | ops_start | ops_len
+        const size_t n1 = (size_t)n_pairs + 1;
+        CB(ctx->h_raw_off.reserve(3 * n1), "cudaMallocHost raw offsets");
+        std::memcpy(ctx->h_raw_off.p, read_off, sizeof(uint32_t) * n1);
+        if (device_bootstrap) std::memcpy(ctx->h_raw_off.p + n1, boot_off.data(), sizeof(uint32_t) * 2 * n1);
+        else std::memcpy(ctx->h_raw_off.p + n1, ops_off, sizeof(uint32_t) * n1);
+        CB(cudaMemcpyAsync(ctx->d_raw_off.p, ctx->h_raw_off.p, sizeof(uint32_t) * (device_bootstrap ? 3 : 2) * n1, cudaMemcpyHostToDevice, st), "H2D raw offsets");
         CB(cudaMemsetAsync(d_cells, 0, sizeof(unsigned long long), st), "memset cell count");
+        const uint32_t *d_ops_start = nullptr, *d_ops_len = nullptr;
+        if (device_bootstrap) {
+            CB(ctx->d_boot.reserve(boot_words + 1), "cudaMalloc traceback bits");
+            uint32_t *start = ctx->d_raw_off.p + 3 * n1, *len = ctx->d_raw_off.p + 4 * n1;
+            bootstrap_ops_kernel<<<(n_pairs + 127) / 128, 128, 0, st>>>(
+                b->d_pairs.p, n_pairs, ctx->d_rawin.p, ctx->d_raw_off.p, b->d_codes.p, b->radius, ctx->d_boot.p, ctx->d_raw_off.p + n1,
+                ctx->d_rawin.p + rb_pad, ctx->d_raw_off.p + 2 * n1, start, len);
+            CB(cudaGetLastError(), "bootstrap launch");
+            ctx->launches++;
+            d_ops_start = start; d_ops_len = len;
+        }
         const int words = ((b->max_nd + 31) / 32 + 2 + 3) & ~3, warps = 4;
         const size_t dyn = (size_t)warps * words * sizeof(uint32_t);
         if (dyn > 48 * 1024) CB(cudaFuncSetAttribute(encode_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn), "encoder shared memory");
         encode_pairs_kernel<<<(n_pairs + warps - 1) / warps, warps * 32, dyn, st>>>(
             b->d_pairs.p, n_pairs, ctx->d_rawin.p, ctx->d_raw_off.p, ctx->d_rawin.p + rb_pad, ctx->d_raw_off.p + n_pairs + 1, b->d_codes.p,
-            b->d_bits.p, b->radius, words, reinterpret_cast<EncStatus *>(ctx->d_enc_status.p), d_cells);
+            b->d_bits.p, b->radius, words, reinterpret_cast<EncStatus *>(ctx->d_enc_status.p), d_cells, d_ops_start, d_ops_len);
         CB(cudaGetLastError(), "encoder launch");
         ctx->launches++;
     }
@@ -975,7 +1098,30 @@ int batch_run(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev
     // The modification table runs as waves of (forward kernel, backward kernel); the forward rows of every pair of a wave
     // live in HBM between the two kernels (2.3 MB per 2 kbp pair), so a wave holds as many pairs as the scratch budget allows.
     int per_wave = b->n_pairs;
-    const bool legacy = std::getenv("JTK_MODTABLE_LEGACY") != nullptr; // v9 three-kernel path with forward rows in HBM (A/B runs)
+    // Two bit-identical variants of the modification table:
+    //   fused  one kernel, forward rows recomputed per segment in shared memory: the DP matrices never touch HBM, scratch is
+    //          ~260 KB per resident WARP (checkpoints);
+    //   rows   forward kernel + backward kernel, forward rows parked in HBM in between: 2.3 MB of scratch per 2 kbp PAIR of a
+    //          wave and 40x the algorithmic HBM traffic, but ~25 % fewer instructions -- faster while HBM is not the bound.
+    // JTK_MODTABLE=fused|rows picks one; otherwise rows when the whole batch fits the scratch budget as ONE wave, else fused.
+    bool legacy = false;
+    if (table) {
+        const char *env = std::getenv("JTK_MODTABLE");
+        if (std::getenv("JTK_MODTABLE_LEGACY") || (env && std::strcmp(env, "rows") == 0)) legacy = true;
+        else if (env && std::strcmp(env, "fused") == 0) legacy = false;
+        else {
+            const size_t per_pair = (size_t)(b->max_nd + frow_extra_rows()) * frow_slots_per_row(b->C) * sizeof(float2) +
+                                    ((size_t)b->max_nd + 6) * sizeof(int32_t) + (size_t)4 * (b->max_lt + 1) * sizeof(float4);
+            const size_t need = (size_t)b->n_pairs * per_pair;
+            legacy = need <= ctx->scratch_bytes;
+            if (legacy && need > ctx->d_frows.cap * sizeof(float2)) { // the scratch would have to grow: does the device have it?
+                size_t free_b = 0, total_b = 0;
+                cudaMemGetInfo(&free_b, &total_b);
+                legacy = need <= (free_b + ctx->d_frows.cap * sizeof(float2)) / 2;
+            }
+        }
+        ctx->last_variant = legacy ? 2 : 1;
+    }
     int fused_blocks = 0;
     if (table && !legacy) {
         // v10: one fused kernel, forward rows recomputed in shared memory.  Per WARP SLOT: checkpoints + block exponents; per
@@ -1412,6 +1558,7 @@ int jtk_batch_colstats(jtk_batch *b, const float *min_req, int H, float pos_thr,
     CU(b->d_stats.reserve((size_t)total), "cudaMalloc stats");
     CU(ctx->up_minreq.put(ctx->d_minreq.p, min_req, sizeof(float) * 3 * (size_t)H, st), "H2D min_req");
     CU(b->up_stat_off.put(b->d_stat_off.p, stat_off, sizeof(uint64_t) * (size_t)b->n_tmpl, st), "H2D stat_off");
+    if (b->n_tmpl > 65535) return ctx->fail(JTK_EINVAL, "more than 65535 templates in one batch (the per-chunk kernels put the template on grid.y): split the call");
     dim3 grid((unsigned)(((size_t)(b->max_lt + 1) * kNumRow + 255) / 256), (unsigned)b->n_tmpl);
     colstats_kernel<<<grid, 256, 0, st>>>(b->d_delta.p, b->d_pairs.p, b->d_tp_start.p, b->d_tp_ids.p, b->d_tmpl_len.p,
                                          b->d_homop.p, b->d_homop_off.p, b->d_stat_off.p, ctx->d_minreq.p, H, pos_thr,
@@ -1588,6 +1735,7 @@ int run_candidates(jtk_batch *b, const jtk_gains *gains, const int32_t *copy_num
     a.tmpl_code_off = b->d_tmpl_code_off.p; a.min_req = ctx->d_minreq.p; a.expected = d_exp; a.H = H;
     a.pv = d_pv; a.pv_off = ctx->d_tab_off.p; a.prior = d_prior; a.prior_off = ctx->d_tab_off.p + n_tmpl;
     a.pos_thr = 1e-5f; a.out = ctx->d_cand.p; a.cap = cap; a.counter = ctx->d_counter.p;
+    if (b->n_tmpl > 65535) return ctx->fail(JTK_EINVAL, "more than 65535 templates in one batch (the per-chunk kernels put the template on grid.y): split the call");
     dim3 grid((unsigned)(((size_t)(b->max_lt + 1) * kNumRow + 255) / 256), (unsigned)n_tmpl);
     candidates_kernel<<<grid, 256, 0, st>>>(a);
     CU(cudaGetLastError(), "candidates launch");
@@ -1791,6 +1939,7 @@ int jtk_batch_colsums(jtk_batch *b, int take_num, double *out, const uint64_t *s
     CU(b->d_stat_off.reserve((size_t)b->n_tmpl), "cudaMalloc stat_off");
     CU(ctx->d_gather.reserve((size_t)total), "cudaMalloc sums");
     CU(b->up_stat_off.put(b->d_stat_off.p, stat_off, sizeof(uint64_t) * (size_t)b->n_tmpl, st), "H2D stat_off");
+    if (b->n_tmpl > 65535) return ctx->fail(JTK_EINVAL, "more than 65535 templates in one batch (the per-chunk kernels put the template on grid.y): split the call");
     dim3 grid((unsigned)(((size_t)(b->max_lt + 1) * kNumRow + 255) / 256), (unsigned)b->n_tmpl);
     colsums_kernel<<<grid, 256, 0, st>>>(b->d_delta.p, b->d_pairs.p, b->d_tp_start.p, b->d_tp_ids.p, b->d_tmpl_len.p,
                                         b->d_stat_off.p, take_num, ctx->d_gather.p);
@@ -1815,6 +1964,7 @@ int jtk_batch_best_edits(jtk_batch *b, int take_num, int ignore_edge, double min
     CU(ctx->d_mc_asn.reserve((size_t)total), "cudaMalloc best edits");
     if (out_gain) CU(ctx->d_gather.reserve((size_t)total), "cudaMalloc best gains");
     CU(b->up_stat_off.put(b->d_stat_off.p, col_off, sizeof(uint64_t) * (size_t)b->n_tmpl, st), "H2D col_off");
+    if (b->n_tmpl > 65535) return ctx->fail(JTK_EINVAL, "more than 65535 templates in one batch (the per-chunk kernels put the template on grid.y): split the call");
     dim3 grid((unsigned)((b->max_lt + 1 + 127) / 128), (unsigned)b->n_tmpl);
     best_edit_kernel<<<grid, 128, 0, st>>>(b->d_delta.p, b->d_pairs.p, b->d_tp_start.p, b->d_tp_ids.p, b->d_tmpl_len.p, b->d_codes.p,
                                            b->d_tmpl_code_off.p, b->d_stat_off.p, take_num, ignore_edge, min_gain,

@@ -370,6 +370,23 @@ __device__ __forceinline__ bool elect_one() {
     return p != 0u;
 }
 
+
+// Exact power-of-two corrections of one step of a block of four anti-diagonals (block q = rows 4q-4 .. 4q-1) next to forward
+// rescales.  The forward pass rescales on the LAST row of a block, so inside the rows 4q-7 .. 4q+2 a step can touch there are
+// two boundaries: 4q-6 | 4q-5 (amount kA, end of forward block q-2) and 4q-2 | 4q-1 (amount kB, block q-1).  Which of the
+// three zones row s = 4q-1-k and row s+e fall into is known at compile time: ce[e+3] = 2^(K(s) - K(s+e)) is one of
+// 1, fB = 2^kB, fBi = 2^-kB, fA = 2^kA.
+__device__ __forceinline__ void block_corrections(const int k, const float fA, const float fB, const float fBi, float (&ce)[7]) {
+    const int zs = (k == 0) ? 2 : 1;
+#pragma unroll
+    for (int e = -3; e <= 3; e++) {
+        const int r = -1 - k + e; // row s+e relative to 4q
+        const int zt = r <= -6 ? 0 : (r <= -2 ? 1 : 2);
+        ce[e + 3] = zs == zt ? 1.f : (zs == 2 ? fB : (zt == 2 ? fBi : fA));
+    }
+}
+__device__ __forceinline__ float pow2c(int k) { return pow2i(max(-126, min(126, k))); }
+
 template <int C> struct BwdState {
     int x[C], j[C];
     unsigned tcB[C], win[C];
@@ -470,10 +487,13 @@ __device__ __forceinline__ void bwd_step(const PairCtx &pc, const Coef &a, BwdSt
     }
 }
 
-template <int C, int ROWS>
+// STAGED: the read-row codes of the pair sit in shared memory (rb0[i] = code byte of read row i): no byte windows, no global
+// loads for them in the step loop.
+template <int C, int ROWS, bool STAGED>
 __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, const float2 *__restrict__ frow,
                                               const int32_t *__restrict__ kb, float4 *__restrict__ raw,
-                                              volatile float *s_ftot, f2 *ring, const unsigned bars, unsigned &phase) {
+                                              volatile float *s_ftot, f2 *ring, const unsigned bars, unsigned &phase,
+                                              const unsigned char *rb0) {
     constexpr int NSLOT = 32 * C;
     constexpr int RS = C * kPlane;
     constexpr unsigned RSB = RS * 8u; // bytes per forward row
@@ -521,6 +541,7 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
         st.tcB[c] = pc.sEM + ((unsigned)pc.Tb[st.j[c] + 1] << 5); // code of t[j]
         st.tcn[c] = pc.Tb[st.j[c] + 1 - NSLOT];
         st.win[c] = 0u;
+        st.rbp[c] = STAGED ? rb0 + (nd - st.j[c]) : nullptr; // row s - j + 1 at s = nd - 1
         st.BI[c] = st.BMo[c] = st.inD[c] = st.inMa[c] = st.inMb[c] = 0.f;
         st.Vs[c] = st.Vn[c] = 0.f;
         st.S01[c] = st.S23[c] = st.N01[c] = st.N23[c] = 0ull;
@@ -565,6 +586,7 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
                 if (st.j[c] >= 0) flush_col(c);
                 st.j[c] -= NSLOT;
                 st.x[c] += NSLOT;
+                if (STAGED) st.rbp[c] += NSLOT;
                 st.tcB[c] = pc.sEM + (st.tcn[c] << 5); // fetched one column-life ago; the window comes with the next reload
                 st.tcn[c] = pc.Tb[st.j[c] + 1 - NSLOT];
                 // reset = multiply by zero, one instruction per register pair (the sums are finite and >= 0); a plain
@@ -580,6 +602,7 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
         }
     };
     auto reload = [&](int s) {
+        if (STAGED) return;
 #pragma unroll
         for (int c = 0; c < C; c++) st.win[c] = win_down(pc.RbP, s - st.j[c] + 1);
     };
@@ -596,8 +619,12 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
 #pragma unroll
         for (int e = -3; e <= 3; e++) ce[e + 3] = pow2i(max(-126, min(126, kcur - kfat(s + e))));
         f2 bMD[C];
-        if (s == nd - 1) bwd_step<C, ROWS, true, true>(pc, a, st, rp, W, ce, boff, bMD);
-        else bwd_step<C, ROWS, true, false>(pc, a, st, rp, W, ce, boff, bMD);
+        if (s == nd - 1) bwd_step<C, ROWS, true, true, STAGED>(pc, a, st, rp, W, ce, boff, bMD);
+        else bwd_step<C, ROWS, true, false, STAGED>(pc, a, st, rp, W, ce, boff, bMD);
+        if (STAGED) {
+#pragma unroll
+            for (int c = 0; c < C; c++) st.rbp[c] -= 1;
+        }
         hand_off(bMD);
         if (s > 0) {
             if (kstep != 0) { // mirror of the forward rescale at step s
@@ -623,18 +650,46 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
     unsigned nib_cur = 0u, nib_nxt = q_top >= 2 ? load_nib(q_top) : 0u;
     // per-block preamble: guide bits one block ahead, the ring group this block reads below itself has landed, the next
     // copy is issued; returns whether block q takes the fast path
-    auto preamble = [&](int q) -> bool {
+    int kA = 0, kB = 0; // rescale amounts at the end of forward blocks q-2 and q-1 of the current block q
+    auto preamble = [&](int q) -> int { // 0: generic steps, 1: fast block, 2: fast block with exact corrections
         nib_cur = nib_nxt;
         if (q >= 3) nib_nxt = load_nib(q - 1);
         wait_group(q - 1);
         __syncwarp(); // every lane is done with the rows that the next copy overwrites
         if (q >= 2) issue_group(q - 2);
-        const bool clean = kb1 == kb2 && kb2 == kb3;
+        kB = kb1 - kb2; kA = kb2 - kb3;
         kb1 = kb2; kb2 = kb3; kb3 = kb[q - 4];
-        return 4 * q - 1 <= nd - 2 && q >= 2 && clean;
+        if (!(4 * q - 1 <= nd - 2 && q >= 2)) return 0;
+        return (kA | kB) == 0 ? 1 : 2;
     };
     for (int q = q_top; q >= 1; --q) {
-        if (preamble(q)) {
+        const int mode = preamble(q);
+        if (mode == 2) { // a rescale within reach: the fast block with the exact corrections of its cut products
+            const f2 *rp = ring + (size_t)(4 * (q & 3) + 3 + kRingMargin) * RS + kPlaneHalo + lane;
+            reload(4 * q - 1);
+            const unsigned nib = nib_cur;
+            const float fA = pow2c(kA), fB = pow2c(kB), fBi = pow2c(-kB);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                f2 bMD[C];
+                float ce[7];
+                block_corrections(k, fA, fB, fBi, ce);
+                bwd_step<C, ROWS, true, false, STAGED>(pc, a, st, rp - k * RS, W, ce, boff, bMD, k);
+                hand_off(bMD);
+                if (k == 0 && kB != 0) { // mirror of the forward rescale on row 4q-1
+                    const float sc = pow2i(kB);
+#pragma unroll
+                    for (int c = 0; c < C; c++) { st.BI[c] *= sc; st.BMo[c] *= sc; st.inD[c] *= sc; st.inMa[c] *= sc; st.inMb[c] *= sc; }
+                }
+                const int dec = (int)(((nib >> (3 - k)) & 1u) ^ 1u);
+#pragma unroll
+                for (int c = 0; c < C; c++) st.x[c] -= dec;
+            }
+            if (STAGED) {
+#pragma unroll
+                for (int c = 0; c < C; c++) st.rbp[c] -= 4;
+            }
+        } else if (mode == 1) {
             const f2 *rp = ring + (size_t)(4 * (q & 3) + 3 + kRingMargin) * RS + kPlaneHalo + lane;
             reload(4 * q - 1);
             // guide bits 4q-5 .. 4q-2 (fetched one block ahead): step k (s = 4q-1-k) moves on with bit 4q-2-k
@@ -642,11 +697,15 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
 #pragma unroll kBwdUnroll
             for (int k = 0; k < 4; k++) {
                 f2 bMD[C];
-                bwd_step<C, ROWS, false, false>(pc, a, st, rp - k * RS, W, nullptr, boff, bMD);
+                bwd_step<C, ROWS, false, false, STAGED>(pc, a, st, rp - k * RS, W, nullptr, boff, bMD, k);
                 hand_off(bMD);
                 const int dec = (int)(((nib >> (3 - k)) & 1u) ^ 1u);
 #pragma unroll
                 for (int c = 0; c < C; c++) st.x[c] -= dec;
+            }
+            if (STAGED) {
+#pragma unroll
+                for (int c = 0; c < C; c++) st.rbp[c] -= 4;
             }
         } else {
             for (int s = min(4 * q - 1, nd - 1); s >= 4 * q - 4; --s) slow_step(s);
@@ -929,14 +988,15 @@ __device__ __forceinline__ void fill_bwd_tables(BwdSmem &sh, const float *__rest
     __syncthreads();
 }
 
-template <int C, int ROWS>
+template <int C, int ROWS, bool STAGED>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, bwd_ctas_per_sm(C, ROWS)) bwdtable_kernel(KParams p) {
     __shared__ BwdSmem sh;
-    extern __shared__ __align__(128) unsigned char dyn_smem[]; // kWarpsPerCta rings of forward rows
+    extern __shared__ __align__(128) unsigned char dyn_smem[]; // kWarpsPerCta rings of forward rows (+ staged read codes)
     fill_bwd_tables(sh, p.models);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int RS = C * kPlane;
+    constexpr int RS = C * kPlane, PADR = 32 * C + 16;
     f2 *ring = reinterpret_cast<f2 *>(dyn_smem) + (size_t)warp * ring_floats2<C>();
+    unsigned char *rb_s = dyn_smem + (size_t)kWarpsPerCta * ring_floats2<C>() * sizeof(f2) + (size_t)warp * p.smem_rb; // rb_s[i + PADR]
     const unsigned bars = (unsigned)__cvta_generic_to_shared(&sh.bar[warp][0]);
     unsigned phase = 0u;
     if (lane < 4) mbar_init(bars + 8u * lane, 1u);
@@ -955,8 +1015,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, bwd_ctas_per_sm(C, ROWS)) b
         const int32_t *kb = p.kf + (size_t)k * p.kf_stride + 4;
         const unsigned *info = p.fwdinfo + (size_t)k * p.fwdinfo_stride;
         if (lane < 4) sh.ftot[warp][lane] = __uint_as_float(info[lane]);
+        if (STAGED) {
+            const uint8_t *Rb = p.codes + P.rb_off;
+            const int nr = P.Lr + 2 * PADR;
+            for (int w = lane; w < nr; w += 32) rb_s[w] = Rb[w - PADR];
+        }
         __syncwarp();
-        backward_pass<C, ROWS>(pc, a, frow, kb, p.raw + (size_t)k * p.raw_stride, sh.ftot[warp], ring, bars, phase);
+        backward_pass<C, ROWS, STAGED>(pc, a, frow, kb, p.raw + (size_t)k * p.raw_stride, sh.ftot[warp], ring, bars, phase, rb_s + PADR);
         __syncwarp();
     }
 }
@@ -1647,12 +1712,12 @@ __device__ __forceinline__ void backward_fused(const PairCtx &pc, const Coef &a,
         return __funnelshift_r(pc.bw[b0 >> 5], pc.bw[(b0 >> 5) + 1], b0 & 31);
     };
     unsigned nib_cur = 0u, nib_nxt = q_top >= 2 ? load_nib(q_top) : 0u;
-    auto preamble = [&](int q) -> bool {
+    auto preamble = [&](int q) -> int { // 0: generic steps, 1: fast block, 2: fast block with exact corrections
         nib_cur = nib_nxt;
         if (q >= 3) nib_nxt = load_nib(q - 1);
+        if (!(4 * q - 1 <= nd - 2 && q >= 2)) return 0;
         // block q touches forward rows 4q-7 .. 4q+2: exact corrections iff the forward pass rescaled at the end of block q-1 or q-2
-        const bool clean = (__funnelshift_r(ev, ev, (q - 2) & 31) & 3u) == 0u;
-        return 4 * q - 1 <= nd - 2 && q >= 2 && clean;
+        return (__funnelshift_r(ev, ev, (q - 2) & 31) & 3u) == 0u ? 1 : 2;
     };
     // segment of block q: blocks QSEG*k + 1 .. QSEG*k + QSEG are the rows SEG*k .. SEG*k + SEG - 1
     k_have = (q_top - 1) / QSEG + 2;
@@ -1664,7 +1729,8 @@ __device__ __forceinline__ void backward_fused(const PairCtx &pc, const Coef &a,
             load_segment(k_have);
             continue;
         }
-        if (preamble(q)) {
+        const int mode = preamble(q);
+        if (mode == 1) {
             const f2 *rp = buf + (size_t)(4 * q - 1 - (SEG * k_have - kSegBelow)) * RS + kPlaneHalo + lane;
             const unsigned nib = nib_cur;
 #pragma unroll kBwdUnroll
@@ -1672,6 +1738,29 @@ __device__ __forceinline__ void backward_fused(const PairCtx &pc, const Coef &a,
                 f2 bMD[C];
                 bwd_step<C, ROWS, false, false, true>(pc, a, st, rp - k * RS, W, nullptr, 0.f, bMD, k);
                 hand_off(bMD);
+                const int dec = (int)(((nib >> (3 - k)) & 1u) ^ 1u);
+#pragma unroll
+                for (int c = 0; c < C; c++) st.x[c] -= dec;
+            }
+#pragma unroll
+            for (int c = 0; c < C; c++) st.rbp[c] -= 4;
+        } else if (mode == 2) { // a rescale within reach: the same block with the exact corrections of its cut products
+            const f2 *rp = buf + (size_t)(4 * q - 1 - (SEG * k_have - kSegBelow)) * RS + kPlaneHalo + lane;
+            const unsigned nib = nib_cur;
+            const int k1 = kb[q - 1], k2 = kb[q - 2], k3 = kb[q - 3];
+            const float fA = pow2c(k2 - k3), fB = pow2c(k1 - k2), fBi = pow2c(k2 - k1);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                f2 bMD[C];
+                float ce[7];
+                block_corrections(k, fA, fB, fBi, ce);
+                bwd_step<C, ROWS, true, false, true>(pc, a, st, rp - k * RS, W, ce, 0.f, bMD, k);
+                hand_off(bMD);
+                if (k == 0 && k1 != k2) { // mirror of the forward rescale on row 4q-1
+                    const float sc = pow2i(k1 - k2);
+#pragma unroll
+                    for (int c = 0; c < C; c++) { st.BI[c] *= sc; st.BMo[c] *= sc; st.inD[c] *= sc; st.inMa[c] *= sc; st.inMb[c] *= sc; }
+                }
                 const int dec = (int)(((nib >> (3 - k)) & 1u) ^ 1u);
 #pragma unroll
                 for (int c = 0; c < C; c++) st.x[c] -= dec;
@@ -1770,8 +1859,13 @@ int cols_per_lane_for_radius(int radius) {
 
 template <int C, int ROWS>
 static cudaError_t launch_modtable_cr(const KParams &p, int grid_fwd, int grid_bwd, cudaStream_t st) {
-    const int dyn = kWarpsPerCta * ring_floats2<C>() * (int)sizeof(f2);
-    cudaError_t e = cudaFuncSetAttribute(bwdtable_kernel<C, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    const int dyn_ring = kWarpsPerCta * ring_floats2<C>() * (int)sizeof(f2);
+    // the read codes of a pair are staged next to the ring when they fit (they do up to ~10 kbp reads at radius <= 30)
+    const bool staged = dyn_ring + kWarpsPerCta * p.smem_rb <= 227 * 1024 - 2048 &&
+                        bwd_ctas_per_sm(C, ROWS) * (dyn_ring + kWarpsPerCta * p.smem_rb + 3072) <= 228 * 1024;
+    const int dyn = dyn_ring + (staged ? kWarpsPerCta * p.smem_rb : 0);
+    cudaError_t e = staged ? cudaFuncSetAttribute(bwdtable_kernel<C, ROWS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)
+                           : cudaFuncSetAttribute(bwdtable_kernel<C, ROWS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     if (e != cudaSuccess) return e;
     const int dyn_f = kWarpsPerCta * (p.smem_rb + p.smem_tb);
     e = cudaFuncSetAttribute(fwdrows_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_f);
@@ -1779,7 +1873,8 @@ static cudaError_t launch_modtable_cr(const KParams &p, int grid_fwd, int grid_b
     fwdrows_kernel<C><<<grid_fwd, kWarpsPerCta * 32, dyn_f, st>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    bwdtable_kernel<C, ROWS><<<grid_bwd, kWarpsPerCta * 32, dyn, st>>>(p);
+    if (staged) bwdtable_kernel<C, ROWS, true><<<grid_bwd, kWarpsPerCta * 32, dyn, st>>>(p);
+    else bwdtable_kernel<C, ROWS, false><<<grid_bwd, kWarpsPerCta * 32, dyn, st>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     finalize_kernel<<<dim3((unsigned)((p.max_lt + kFinCols) / kFinCols), (unsigned)(p.pair_hi - p.pair_lo)), kFinCols, 0, st>>>(p);

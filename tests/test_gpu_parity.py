@@ -11,7 +11,7 @@ import pytest
 import oracle_lib as O
 from jtk_b200 import synth
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("modtable_variant")]
 
 NEG = -1.0e9
 
@@ -331,3 +331,72 @@ def test_device_encoder_equals_host_encoder(monkeypatch):
     assert out["0"][0] == out["1"][0] > 0
     for k in (1, 2, 3):
         assert np.array_equal(out["0"][k], out["1"][k])
+
+
+def test_fused_and_rows_variants_are_bit_identical(ctx, monkeypatch):
+    """The fused kernel (forward rows recomputed in shared memory, nothing of the DP matrices in HBM) replays the forward pass
+    of the rows variant instruction for instruction: likelihoods and every table entry are equal BIT FOR BIT -- on a ragged
+    batch (lengths 1 .. 2 600, which also exercises the longest-first work queue), at radius 30 / 50 / 100 (2, 4, 8 column
+    slots per lane) and for the 9-row table."""
+    rng = np.random.default_rng(77)
+    h = to_c(random_hmm(5))
+    reads, ops, strands, tidx, templates = [], [], [], [], []
+    for k, L in enumerate((1, 2, 3, 7, 15, 16, 17, 40, 300, 900, 2600)):
+        t = synth.random_template(rng, L)
+        templates.append(t)
+        for r in range(3):
+            q, o = synth.mutate_read(rng, t, 0.1)
+            reads.append(q); ops.append(o); strands.append((k + r) % 2 == 0); tidx.append(k)
+    tidx = np.asarray(tidx, np.uint32)
+    strands = np.asarray(strands, np.uint8)
+    for radius, rows in ((30, 14), (30, 9), (50, 14), (100, 14)):
+        out = {}
+        for v in ("fused", "rows"):
+            monkeypatch.setenv("JTK_MODTABLE", v)
+            b = ctx.batch(templates, reads, ops, strands, tidx, radius)
+            b.modtable(h, h, rows)
+            b.sync()
+            assert ctx.last_modtable_variant == v
+            out[v] = (b.lk().copy(), [b.profile(k).copy() for k in range(len(reads))])
+            b.close()
+        assert np.array_equal(out["fused"][0], out["rows"][0]), (radius, rows)
+        for k in range(len(reads)):
+            assert np.array_equal(out["fused"][1][k], out["rows"][1][k]), (radius, rows, k)
+
+
+def test_variant_is_chosen_by_the_scratch_budget(ctx, monkeypatch):
+    """Without JTK_MODTABLE the library parks forward rows in HBM only when the whole batch fits its scratch budget as one wave."""
+    monkeypatch.delenv("JTK_MODTABLE", raising=False)
+    d = synth.diploid_chunk(5, length=400, n_reads=6)
+    h = to_c(O.default_hmm())
+    b = ctx.batch([d["template"]], d["reads"], d["ops"], d["strands"], np.zeros(6, np.uint32), 30)
+    b.modtable(h, h, 14)
+    b.sync()
+    assert ctx.last_modtable_variant == "rows"
+    b.close()
+
+
+def test_device_bootstrap_equals_host_bootstrap(ctx, monkeypatch):
+    """The banded edit-distance guide of likelihood_antidiagonal_bootstrap computed on the device (bootstrap_ops_kernel, one
+    thread per pair) is the host's alignment op for op: the likelihoods of the two paths are equal bit for bit,
+    on calibration-shaped pairs (~100 bp, radius 10), on unequal lengths and on longer pairs."""
+    rng = np.random.default_rng(123)
+    fwd, rev = random_hmm(8), random_hmm(9)
+    templates, reads, strands = [], [], []
+    for k, L in enumerate([103] * 200 + [1, 2, 5, 17, 64, 65, 300, 600, 1500]):
+        t = synth.random_template(rng, L)
+        q, _ = synth.mutate_read(rng, t, 0.12 if k % 3 else 0.25)
+        if k % 7 == 0 and L > 20:
+            q = q[: len(q) - 9]          # a read that ends early: |Lr - Lt| widens the alignment band
+        templates.append(t); reads.append(q); strands.append(k % 2 == 0)
+    tidx = np.arange(len(reads), dtype=np.uint32)
+    for R in (10, 30):
+        out = {}
+        for dev in ("0", "1"):
+            monkeypatch.setenv("JTK_DEVICE_BOOTSTRAP", dev)
+            n0 = ctx.launch_count
+            out[dev] = ctx.likelihood_batch(to_c(fwd), to_c(rev), templates, reads, None, strands, tidx, R)
+            # device path: bootstrap + encoder + likelihood kernels; host path: the likelihood kernel alone
+            assert ctx.launch_count - n0 == (3 if dev == "1" else 1)
+        assert np.array_equal(out["0"], out["1"]), R
+        assert np.isfinite(out["1"]).all()
