@@ -36,6 +36,8 @@ int warps_per_cta();
 int frow_slots_per_row(int C);
 int frow_extra_rows();
 int modtable_ctas_per_sm(int C, int rows);
+int modtable_warps_per_cta(int C);
+int modtable_dyn_smem(int C, int smem_rb);
 cudaError_t launch_fit(const KParams &p, int C, int grid, double *acc90, cudaStream_t st);
 cudaError_t launch_fp32_peak(int mode, int blocks, int threads, int iters, float *sink, cudaStream_t st);
 } // namespace jtk
@@ -1154,7 +1156,7 @@ int batch_run(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev
         kp.kf_stride = (size_t)b->max_nd + 6;
         kp.fwdinfo_stride = (size_t)fwdinfo_words();
         kp.smem_rb = ((b->max_lr + 2 * fwd_pad_rows(b->C)) + 15) & ~15;
-        kp.smem_tb = ((b->max_lt + 32 * b->C + 16) + 15) & ~15;
+        kp.smem_tb = 0;
         kp.raw_stride = (size_t)4 * (b->max_lt + 1);
         kp.max_lt = b->max_lt;
         const size_t per_pair = kp.frow_stride * sizeof(float2) + kp.kf_stride * sizeof(int32_t) + kp.fwdinfo_stride * 4 +
@@ -1168,9 +1170,9 @@ int batch_run(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev
         }
         per_wave = (int)std::max<size_t>(1, std::min<size_t>((size_t)b->n_pairs, budget / per_pair));
         per_wave = std::min(per_wave, 65535); // finalize_kernel puts the pair of a wave on grid.y
-        // the forward kernel stages the codes of one pair per warp in shared memory
-        if ((size_t)wpc * (size_t)(kp.smem_rb + kp.smem_tb) > (size_t)227 * 1024 - 4096)
-            return ctx->fail(JTK_EINVAL, "pair too long for the modification-table kernels: read + template length must stay below ~56 000 bases");
+        // both kernels stage the read codes of one pair per warp in shared memory (the backward kernel next to its ring)
+        if ((size_t)modtable_dyn_smem(b->C, kp.smem_rb) > (size_t)227 * 1024 - 6144)
+            return ctx->fail(JTK_EINVAL, "pair too long for the modification-table kernels: the read must stay below ~40 000 bases");
         CU(ctx->d_frows.reserve((size_t)per_wave * kp.frow_stride), "cudaMalloc forward rows");
         CU(ctx->d_kf.reserve((size_t)per_wave * kp.kf_stride), "cudaMalloc scale exponents");
         CU(ctx->d_fwdinfo.reserve((size_t)per_wave * kp.fwdinfo_stride), "cudaMalloc forward info");
@@ -1204,7 +1206,8 @@ int batch_run(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev
         } else if (table) {
             // persistent CTAs: one wave of resident CTAs pulls pairs from the queue
             const int gf = std::min(ctas, ctx->sm_count * fwdrows_ctas_per_sm(b->C));
-            const int gb = std::min(ctas, ctx->sm_count * modtable_ctas_per_sm(b->C, rows));
+            const int wpb = modtable_warps_per_cta(b->C);
+            const int gb = std::min((hi - lo + wpb - 1) / wpb, ctx->sm_count * modtable_ctas_per_sm(b->C, rows));
             CU(launch_modtable(kp, b->C, gf, gb, st), "kernel launch");
             ctx->launches += 3;
         } else {

@@ -35,7 +35,9 @@ constexpr int kEvBits = 4096;   // rescale-event map: one bit per block of four 
 constexpr int kEvWords = kEvBits / 32 + 2;
 // backward pass: per-warp shared-memory ring of forward rows, filled by bulk async copies
 constexpr int kRingRows = 16;   // row slots (four groups of four rows)
-constexpr int kRingMargin = 3;  // copies of the rows at the other end of the ring, on both sides
+// copies of the rows at the other end of the ring: as many as the cuts reach below (e = -1..-3: deletions) and above (copies)
+constexpr int ring_below(int rows) { return rows == 14 ? 3 : 1; }
+constexpr int ring_above(int rows) { return rows == 14 ? 3 : 0; }
 constexpr int kRowShift = 4;    // ring / group index of anti-diagonal s is rho = s + kRowShift (four zero rows below s = 0)
 constexpr int kRowsAbove = 8;   // rows past the last anti-diagonal that exist in the scratch (the first three read as zero)
 #ifndef JTK_BWD_UNROLL
@@ -51,16 +53,17 @@ constexpr int kBwdUnroll = JTK_BWD_UNROLL; // steps of the fast backward block u
 #ifndef JTK_BWD_CTAS9
 #define JTK_BWD_CTAS9 4
 #endif
-// C = 4 (radius 31..62): 255 registers and a 101 KB ring per CTA either way, two CTAs fit an SM
-// C = 8 (radius 63..126): the ring alone is 203 KB per CTA, one CTA per SM
-constexpr int bwd_ctas_per_sm(int C, int rows) { return C == 2 ? (rows == 14 ? JTK_BWD_CTAS14 : JTK_BWD_CTAS9) : (C == 4 ? 2 : 1); }
+// C = 4 (radius 31..62): a 107 KB ring per CTA of four warps, two CTAs per SM
+// C = 8 (radius 63..126): a ring is 53 KB per WARP: CTAs of two warps, two CTAs per SM
+constexpr int bwd_ctas_per_sm(int C, int rows) { return C == 2 ? (rows == 14 ? JTK_BWD_CTAS14 : JTK_BWD_CTAS9) : 2; }
+constexpr int bwd_warps_per_cta(int C) { return C == 8 ? 2 : 4; } // kWarpsPerCta, except where four rings do not fit an SM
 constexpr int kHalo = 4;        // (single-kernel forward_pass, STORE == 1) replicated slots on both sides of a row
-// Forward rows of the two-kernel modification table (v9): a row is C planes, plane c holds the slots sigma == c (mod C)
-// in slot order (plane c, index k = slot C*k + c), 32 entries + 2 replicated entries on both sides.  A backward lane
-// owns the C adjacent slots C*lane + c: its own entries and every neighbour sigma +- 1..3 sit at lane stride 8 bytes
-// (no shared-memory bank conflicts) at compile-time offsets from one per-lane pointer.
-constexpr int kPlaneHalo = 2;
-constexpr int kPlane = 32 + 2 * kPlaneHalo;
+// Forward rows of the modification table (v11): lane l owns the slots l + 32c; a row is C/2 pair planes, plane p holds per
+// entry k the 16 bytes (toM[k+64p], toM[k+64p+32], toD[k+64p], toD[k+64p+32]), 32 entries + 3 replicated entries on both sides
+// (k = -3..34, slot indices mod NSLOT).  A backward lane finds row s+e, slots sigma+e of both cells of a pair as ONE 128-bit
+// load at lane stride 16 bytes (conflict-free) and a compile-time offset from one per-lane pointer.
+constexpr int kPlaneHalo = 3;
+constexpr int kPlane = 32 + 2 * kPlaneHalo; // 16-byte entries per pair plane; a row is C/2 planes = C * kPlane f2
 
 // ---- small helpers --------------------------------------------------------------------------------------
 typedef unsigned long long f2; // two packed fp32 (lo, hi) in one 64-bit register pair
@@ -158,7 +161,7 @@ struct PairCtx { // warp-uniform view of one pair
     const uint8_t *RbP; // Rb - kCodePad
     const uint32_t *bw;
     int Lt, Lr, nd, r;
-    unsigned sEM, sEI, sEMT; // shared-space addresses of this pair's model tables
+    unsigned sEM, sEI, sEC;  // shared-space addresses of this pair's model tables (sEC: paired substitution emissions)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -387,118 +390,225 @@ __device__ __forceinline__ void block_corrections(const int k, const float fA, c
 }
 __device__ __forceinline__ float pow2c(int k) { return pow2i(max(-126, min(126, k))); }
 
+// ------------------------------------------------------------------------------------------------
+// Backward / table state (v11).  Lane l owns the slots sigma = l + 32c (c = 0..C-1); the cells of slots l + 64p and
+// l + 64p + 32 are packed into ONE fp32 pair (lo = the lower slot), so every arithmetic instruction of the step is a packed
+// one (FFMA2 / FMUL2) over two cells, the nine transition coefficients are plain scalars (the packed instructions take a
+// broadcast operand) and nothing is ever moved between the halves of a pair.  A forward row is laid out to match: per pair
+// p one plane of 16-byte entries, entry k = (toM[k+64p], toM[k+64p+32], toD[k+64p], toD[k+64p+32]), three replicated
+// entries past both ends -- so row s+e, slots sigma+e of BOTH cells is one conflict-free 128-bit load at a compile-time
+// offset from one per-lane pointer, for every e = -3..3.
+// ------------------------------------------------------------------------------------------------
 template <int C> struct BwdState {
+    static constexpr int P = C / 2;
     int x[C], j[C];
-    unsigned tcB[C], win[C];
-    const unsigned char *rbp[C]; // (fused kernel) staged code byte of read row s - j + 1 for the first step of the current block
-    unsigned tcn[C]; // template code of the column this slot takes next (j - NSLOT), loaded one column-life ahead
-    float BI[C], BMo[C], inD[C], inMa[C], inMb[C];
-    f2 S01[C], S23[C], N01[C], N23[C]; // substitution / insertion sums over the four bases
-    float Vs[C], Vn[C];
-    f2 Xp[C][3], Xm[C][3];             // (sum toM*gM, sum toD*gD) of the copy / deletion cuts
-    f2 cF[C][7];                       // forward-row entries slot c loaded on the previous step (c >= 1): slot c-1 reuses them
+    unsigned tcB[C];             // shared address of the eM row of the cell's column
+    unsigned tcn[C];             // template code of the column this slot takes next (j - NSLOT), loaded one column-life ahead
+    const unsigned char *rbp[C]; // staged code byte of read row s - j + 1 for the first step of the current block
+    f2 msk[P];                   // 1.0 where the cell is inside the band
+    f2 BI[P], BMo[P], inD[P], inMa[P], inMb[P];
+    f2 S01[C], S23[C], N01[C], N23[C]; // substitution / insertion sums over the four bases, per CELL: (b0, b1), (b2, b3)
+    f2 Vs[P], Vn[P];
+    f2 Xp[P][3], Xm[P][3];       // copy / deletion cuts (sum toM*gM + toD*gD)
 };
-
-// One anti-diagonal.  Backward slot mapping (v9): lane l owns the C adjacent slots sigma = C*l + c.  rp = entry `lane` of
-// plane 0 of forward row s inside the ring; row s+e, slot sigma+e is plane (c+e) mod C, index l + floor((c+e)/C).
-// Cells (i, j) [slot c, this step] and (i, j+1) [slot c+1, previous step] lie on the same read row, so the entries
-// slot c needs -- forward row s+e, slot sigma+e, e = -3..3 -- are the SAME ADDRESSES slot c+1 read one step earlier with
-// e-1: only slot C-1 loads its seven entries, every other slot loads one (e = -3) and takes six from the registers of
-// its right-hand neighbour (st.cF).  This is an address identity: it holds whatever columns the slots currently carry.
-// CORR: a rescale lies within rows s-2 .. s+3 (products that pair two rows get their exact power-of-two correction);
-// FIRST: s = nd-1, the terminal cell is injected (and nothing is carried yet).
-template <int C> __device__ __forceinline__ constexpr int frow_pos(int c, int e) {
-    // offset (in entries) of row s+e, slot sigma+e from rp, for slot c of the lane
-    return (((c + e) % C + C) % C) * kPlane + ((c + e) - (((c + e) % C + C) % C)) / C + e * (C * kPlane);
+struct BCoef { float mm, mi, md, im, ii, id, dm, di, dd; };
+__device__ __forceinline__ BCoef load_bcoef(const float *t) {
+    BCoef c;
+    c.mm = t[0]; c.mi = t[1]; c.md = t[2]; c.im = t[3]; c.ii = t[4]; c.id = t[5]; c.dm = t[6]; c.di = t[7]; c.dd = t[8];
+    return c;
+}
+__device__ __forceinline__ float half2f(f2 v, int h) { return h ? hi2(v) : lo2(v); }
+// zero one half of a pair with a multiply (the sums are finite and >= 0): one FMA-pipe instruction, no constant moves
+__device__ __forceinline__ void clear_half(f2 &v, int h) {
+    float lo = lo2(v), hi = hi2(v);
+    if (h) clear1(hi); else clear1(lo);
+    v = mk2(lo, hi);
 }
 
-// STAGED: the read-row codes come from the pair's staged copy in shared memory (st.rbp, step kk of the block) instead of the
-// byte windows st.win refilled from global memory.
-template <int C, int ROWS, bool CORR, bool FIRST, bool STAGED = false>
-__device__ __forceinline__ void bwd_step(const PairCtx &pc, const Coef &a, BwdState<C> &st, const f2 *rp, const int W,
-                                         const float *ce, const float boff, f2 (&bMD)[C], const int kk = 0) {
-    constexpr int NXM = (ROWS == 14) ? 3 : 1;
-    constexpr int NXP = (ROWS == 14) ? 3 : 0;
-    f2 F[C][7]; // F[c][e + 3] = forward row s+e, slot sigma+e
+template <int C> __device__ __forceinline__ void bwd_masks(BwdState<C> &st, const int W) {
 #pragma unroll
-    for (int c = C - 1; c >= 0; c--) {
-#pragma unroll
-        for (int e = -NXM; e <= NXP; e++) {
-            const bool reuse = !FIRST && c < C - 1 && e - 1 >= -NXM;
-            F[c][e + 3] = reuse ? st.cF[c + 1][e + 2] : rp[frow_pos<C>(c, e)];
-        }
-    }
+    for (int p = 0; p < C / 2; p++)
+        st.msk[p] = mk2((unsigned)st.x[2 * p] <= (unsigned)W ? 1.f : 0.f, (unsigned)st.x[2 * p + 1] <= (unsigned)W ? 1.f : 0.f);
+}
+
+template <int C> __device__ __forceinline__ void bwd_init(BwdState<C> &st, const PairCtx &pc, const unsigned char *rb0) {
+    constexpr int NSLOT = 32 * C;
+    const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int c = 0; c < C; c++) {
-        const bool valid = (unsigned)st.x[c] <= (unsigned)W;
-        unsigned w;
-        if (STAGED) w = st.rbp[c][-kk];
-        else { w = st.win[c]; st.win[c] = w >> 8; }
-        float em = lds_f32(st.tcB[c] | (w & 0x1cu));
-        float ei = lds_f32(STAGED ? pc.sEI + w : pc.sEI | (w & 0xffu));
-        f2 ec01, ec23;
-        lds_f32x4(pc.sEMT | ((w & 0x1cu) << 2), ec01, ec23);
+        const int sigma = lane + 32 * c;
+        const int d = (pc.Lt - sigma) & (NSLOT - 1);
+        st.j[c] = pc.Lt - d;   // largest column <= Lt owned by this slot
+        st.x[c] = d + pc.r;    // row i = Lr + d on the last anti-diagonal, window starts at row Lr - r
+        st.tcB[c] = pc.sEM + ((unsigned)pc.Tb[st.j[c] + 1] << 5); // code of t[j]
+        st.tcn[c] = pc.Tb[st.j[c] + 1 - NSLOT];
+        st.rbp[c] = rb0 + (pc.nd - st.j[c]); // row s - j + 1 at s = nd - 1
+    }
+#pragma unroll
+    for (int p = 0; p < C / 2; p++) {
+        st.BI[p] = st.BMo[p] = st.inD[p] = st.inMa[p] = st.inMb[p] = 0ull;
+        st.Vs[p] = st.Vn[p] = 0ull;
+#pragma unroll
+        for (int e = 0; e < 3; e++) { st.Xp[p][e] = 0ull; st.Xm[p][e] = 0ull; }
+    }
+#pragma unroll
+    for (int c = 0; c < C; c++) st.S01[c] = st.S23[c] = st.N01[c] = st.N23[c] = 0ull;
+    bwd_masks<C>(st, 2 * pc.r);
+}
+
+// One anti-diagonal.  rq = entry `lane` of pair plane 0 of forward row s (16-byte entries, RQ per row): row s+e, slots
+// sigma+e of pair p is rq[e * RQ + p * kPlane + e].
+// CORR: a rescale lies within rows s-2 .. s+3 (products that pair two rows get their exact power-of-two correction);
+// FIRST: s = nd-1, the terminal cell is injected (and nothing is carried yet).
+template <int C, int ROWS, bool CORR, bool FIRST>
+__device__ __forceinline__ void bwd_step(const PairCtx &pc, const BCoef &a, BwdState<C> &st, const ulonglong2 *rq, const float *ce,
+                                         const float boff, f2 (&bM)[C / 2], f2 (&bD)[C / 2], const int kk) {
+    constexpr int P = C / 2, RQ = P * kPlane;
+    constexpr int NXM = (ROWS == 14) ? 3 : 1;
+    constexpr int NXP = (ROWS == 14) ? 3 : 0;
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        const unsigned w0 = st.rbp[2 * p][-kk], w1 = st.rbp[2 * p + 1][-kk];
+        const f2 em = mk2(lds_f32(st.tcB[2 * p] | (w0 & 0x1cu)), lds_f32(st.tcB[2 * p + 1] | (w1 & 0x1cu)));
+        const f2 ei = mk2(lds_f32(pc.sEI + w0), lds_f32(pc.sEI + w1));
+        // eM(ref b, read base), b = 0..3, of each cell: the substitution / insertion sums are packed over b, not over the cells
+        f2 ea01, ea23, eb01, eb23;
+        lds_f32x4(pc.sEC | ((w0 & 0x1cu) << 2), ea01, ea23);
+        lds_f32x4(pc.sEC | ((w1 & 0x1cu) << 2), eb01, eb23);
         // a cell outside the band contributes nothing: its in-sums are masked (its forward values are zero already)
-        em = valid ? em : 0.f;
-        ei = valid ? ei : 0.f;
-        const float gD = valid ? st.inD[c] : 0.f;
-        const float gM = em * st.inMb[c], gI = ei * st.BI[c];
-        f2 md = fma2(a.bD, bc2(gD), fma2(a.bI, bc2(gI), mul2(a.bM, bc2(gM))));
-        float i_ = fmaf(a.b_id, gD, fmaf(a.b_ii, gI, a.b_im * gM));
+        const f2 m = st.msk[p];
+        const f2 gD = mul2(st.inD[p], m);
+        const f2 gM = mul2(mul2(em, m), st.inMb[p]);
+        const f2 gI = mul2(mul2(ei, m), st.BI[p]);
+        f2 m_ = fma2(bc2(a.md), gD, fma2(bc2(a.mi), gI, mul2(bc2(a.mm), gM)));
+        f2 d_ = fma2(bc2(a.dd), gD, fma2(bc2(a.di), gI, mul2(bc2(a.dm), gM)));
+        f2 i_ = fma2(bc2(a.id), gD, fma2(bc2(a.ii), gI, mul2(bc2(a.im), gM)));
         if (FIRST) { // B(Lr, Lt) = boff, everything else on the last anti-diagonal is outside the matrix
-            const bool term = st.j[c] == pc.Lt;
-            md = term ? bc2(boff) : 0ull;
-            i_ = term ? boff : 0.f;
+            m_ = mk2(st.j[2 * p] == pc.Lt ? boff : 0.f, st.j[2 * p + 1] == pc.Lt ? boff : 0.f);
+            d_ = m_; i_ = m_;
         }
-        // ---- table reduction for cell (i, j) ----
-        const f2 F0 = F[c][3];
-        const float f0m = lo2(F0), f0d = hi2(F0);
-        const f2 U = bc2(f0m * st.inMb[c]);
-        acc2(st.S01[c], U, ec01);
-        acc2(st.S23[c], U, ec23);
-        st.Vs[c] = fmaf(f0d, st.inD[c], st.Vs[c]);
-        const f2 U2 = bc2(f0m * st.BMo[c]);
-        acc2(st.N01[c], U2, ec01);
-        acc2(st.N23[c], U2, ec23);
-        st.Vn[c] = fmaf(f0d, hi2(md), st.Vn[c]);
+        // ---- table reduction for the cells (i, j) of the pair ----
+        const ulonglong2 F0 = rq[p * kPlane];
+        const f2 U = mul2(F0.x, st.inMb[p]);
+        acc2(st.S01[2 * p], bc2(lo2(U)), ea01); acc2(st.S23[2 * p], bc2(lo2(U)), ea23);
+        acc2(st.S01[2 * p + 1], bc2(hi2(U)), eb01); acc2(st.S23[2 * p + 1], bc2(hi2(U)), eb23);
+        acc2(st.Vs[p], F0.y, st.inD[p]);
+        const f2 U2 = mul2(F0.x, st.BMo[p]);
+        acc2(st.N01[2 * p], bc2(lo2(U2)), ea01); acc2(st.N23[2 * p], bc2(lo2(U2)), ea23);
+        acc2(st.N01[2 * p + 1], bc2(hi2(U2)), eb01); acc2(st.N23[2 * p + 1], bc2(hi2(U2)), eb23);
+        acc2(st.Vn[p], F0.y, d_);
         // cuts pairing this column's backward in-sums with forward columns j-1..j-3 (deletions) and j+1..j+3
         // (copies).  g is zero unless the cell is in band, and then slot+e of row s+e holds column j+e.
-        const f2 g = mk2(gM, gD);
 #pragma unroll
         for (int e = 1; e <= NXM; e++) {
-            const f2 Fe = F[c][3 - e];
-            if (CORR) acc2(st.Xm[c][e - 1], mul2(Fe, g), bc2(ce[3 - e]));
-            else acc2(st.Xm[c][e - 1], Fe, g);
+            const ulonglong2 Fe = rq[-e * RQ + p * kPlane - e];
+            if (CORR) { acc2(st.Xm[p][e - 1], mul2(Fe.x, gM), bc2(ce[3 - e])); acc2(st.Xm[p][e - 1], mul2(Fe.y, gD), bc2(ce[3 - e])); }
+            else { acc2(st.Xm[p][e - 1], Fe.x, gM); acc2(st.Xm[p][e - 1], Fe.y, gD); }
         }
 #pragma unroll
         for (int e = 1; e <= NXP; e++) {
-            const f2 Fe = F[c][3 + e];
-            if (CORR) acc2(st.Xp[c][e - 1], mul2(Fe, g), bc2(ce[3 + e]));
-            else acc2(st.Xp[c][e - 1], Fe, g);
+            const ulonglong2 Fe = rq[e * RQ + p * kPlane + e];
+            if (CORR) { acc2(st.Xp[p][e - 1], mul2(Fe.x, gM), bc2(ce[3 + e])); acc2(st.Xp[p][e - 1], mul2(Fe.y, gD), bc2(ce[3 + e])); }
+            else { acc2(st.Xp[p][e - 1], Fe.x, gM); acc2(st.Xp[p][e - 1], Fe.y, gD); }
         }
-        bMD[c] = md;
-        st.BI[c] = i_; st.BMo[c] = lo2(md);
-    }
-    // what the left-hand neighbour slot reuses on the next step
-#pragma unroll
-    for (int c = 1; c < C; c++) {
-#pragma unroll
-        for (int e = -NXM; e <= NXP - 1; e++) st.cF[c][e + 3] = F[c][e + 3];
+        bM[p] = m_; bD[p] = d_;
+        st.BI[p] = i_; st.BMo[p] = m_;
     }
 }
 
-// STAGED: the read-row codes of the pair sit in shared memory (rb0[i] = code byte of read row i): no byte windows, no global
-// loads for them in the step loop.
-template <int C, int ROWS, bool STAGED>
-__device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, const float2 *__restrict__ frow,
+// hand (B_M, B_D) to the left-hand neighbour column: slot sigma receives from slot sigma+1 = the same cell of lane+1; lane 31
+// receives from the NEXT cell of lane 0 (slot 32c + 31 -> 32(c+1), wrapping)
+template <int C> __device__ __forceinline__ void bwd_hand_off(BwdState<C> &st, const f2 (&bM)[C / 2], const f2 (&bD)[C / 2]) {
+    const int lane = threadIdx.x & 31;
+    const bool seam = lane == 31;
+    float rM[C], rD[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        rM[c] = __shfl_sync(kFull, half2f(bM[c / 2], c & 1), (lane + 1) & 31);
+        rD[c] = __shfl_sync(kFull, half2f(bD[c / 2], c & 1), (lane + 1) & 31);
+    }
+#pragma unroll
+    for (int p = 0; p < C / 2; p++) {
+        st.inMb[p] = st.inMa[p];
+        st.inMa[p] = mk2(seam ? rM[(2 * p + 1) % C] : rM[2 * p], seam ? rM[(2 * p + 2) % C] : rM[2 * p + 1]);
+        st.inD[p] = mk2(seam ? rD[(2 * p + 1) % C] : rD[2 * p], seam ? rD[(2 * p + 2) % C] : rD[2 * p + 1]);
+    }
+}
+template <int C> __device__ __forceinline__ void bwd_scale(BwdState<C> &st, const float sc) {
+#pragma unroll
+    for (int p = 0; p < C / 2; p++) {
+        st.BI[p] = mul2(st.BI[p], bc2(sc)); st.BMo[p] = mul2(st.BMo[p], bc2(sc)); st.inD[p] = mul2(st.inD[p], bc2(sc));
+        st.inMa[p] = mul2(st.inMa[p], bc2(sc)); st.inMb[p] = mul2(st.inMb[p], bc2(sc));
+    }
+}
+// anti-diagonal s -> s-1 when the centre stays (guide bit 0, dec = 1): every cell moves one row down inside the window
+template <int C> __device__ __forceinline__ void bwd_band_down(BwdState<C> &st, const int dec, const int W) {
+#pragma unroll
+    for (int c = 0; c < C; c++) st.x[c] -= dec;
+    bwd_masks<C>(st, W);
+}
+// a finished column leaves its 16 raw sums in the pair's scratch (64 B, one lane); finalize_kernel turns them into the 14
+// log-ratios of the table.  raw[j] = { S0 S1 S2 S3 | N0 N1 N2 N3 | Vs Vn Xp0 Xp1 | Xp2 Xm0 Xm1 Xm2 }
+template <int C> __device__ __forceinline__ void bwd_flush_col(const BwdState<C> &st, const int c, float4 *raw) {
+    const int p = c / 2, h = c & 1;
+    f2 *sg = reinterpret_cast<f2 *>(raw);
+    asm volatile("st.global.cg.v2.b64 [%0], {%1, %2};" ::"l"(sg + 0), "l"(st.S01[c]), "l"(st.S23[c]) : "memory");
+    asm volatile("st.global.cg.v2.b64 [%0], {%1, %2};" ::"l"(sg + 2), "l"(st.N01[c]), "l"(st.N23[c]) : "memory");
+    __stcg(raw + 2, make_float4(half2f(st.Vs[p], h), half2f(st.Vn[p], h), half2f(st.Xp[p][0], h), half2f(st.Xp[p][1], h)));
+    __stcg(raw + 3, make_float4(half2f(st.Xp[p][2], h), half2f(st.Xm[p][0], h), half2f(st.Xm[p][1], h), half2f(st.Xm[p][2], h)));
+}
+// Retirement, once per block of four anti-diagonals: a slot whose cell left the band at the bottom (x < 0) has seen its last
+// in-band cell.  It is masked like any cell outside the band until then; the ring has NSLOT - (W+1) >= 3 spare slots, and the
+// column j - NSLOT that the slot takes over cannot enter the band before the first step of the next block.  The (on average
+// two) slots that retire in one block are neighbouring lanes with the same c, so one pass through the flush code serves both.
+// RAW(j) = address of the column's raw sums.
+template <int C, int ROWS, typename RAW>
+__device__ __forceinline__ void bwd_retire(BwdState<C> &st, const PairCtx &pc, RAW raw_of) {
+    constexpr int NSLOT = 32 * C;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        if (st.x[c] < 0) {
+            const int p = c / 2, h = c & 1;
+            if (st.j[c] >= 0) bwd_flush_col<C>(st, c, raw_of(st.j[c]));
+            st.j[c] -= NSLOT;
+            st.x[c] += NSLOT;
+            st.rbp[c] += NSLOT;
+            st.tcB[c] = pc.sEM + (st.tcn[c] << 5); // fetched one column-life ago
+            st.tcn[c] = pc.Tb[st.j[c] + 1 - NSLOT];
+            clear2(st.S01[c]); clear2(st.S23[c]); clear2(st.N01[c]); clear2(st.N23[c]);
+            clear_half(st.Vs[p], h); clear_half(st.Vn[p], h);
+#pragma unroll
+            for (int e = 0; e < 3; e++) { // the 9-row kernel only accumulates Xm[0]: the others stay compile-time zeros
+                if (ROWS == 14) clear_half(st.Xp[p][e], h);
+                if (ROWS == 14 || e == 0) clear_half(st.Xm[p][e], h);
+            }
+        }
+    }
+    bwd_masks<C>(st, 2 * pc.r);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward pass fused with the modification-table reduction, forward rows in HBM (rows variant).  ROWS = 14 (all rows) or
+// 9 (rows 0-7 and the one-base deletion, the only rows local_clustering reads: pseudo_mcmc.rs:447).
+//
+// The forward rows come back from HBM through a per-warp shared-memory ring filled by bulk async copies
+// (cp.async.bulk, completion on an mbarrier), one group of four rows per copy, issued one block of four
+// anti-diagonals ahead of their first use: the inner loop sees shared-memory loads with immediate offsets only.
+// Ring geometry: row index rho = s + kRowShift; 16 row slots + 3 margin slots on both sides that hold copies of the
+// rows at the other end, so that rows rho-3 .. rho+3 are always contiguous around slot (rho & 15) + 3.
+// ------------------------------------------------------------------------------------------------
+template <int C, int ROWS>
+__device__ __forceinline__ void backward_pass(const PairCtx &pc, const BCoef &a, const float2 *__restrict__ frow,
                                               const int32_t *__restrict__ kb, float4 *__restrict__ raw,
                                               volatile float *s_ftot, f2 *ring, const unsigned bars, unsigned &phase,
                                               const unsigned char *rb0) {
-    constexpr int NSLOT = 32 * C;
-    constexpr int RS = C * kPlane;
+    constexpr int P = C / 2;
+    constexpr int RS = C * kPlane;    // f2 per forward row
+    constexpr int RQ = P * kPlane;    // 16-byte entries per forward row
     constexpr unsigned RSB = RS * 8u; // bytes per forward row
+    constexpr unsigned MB = ring_below(ROWS), MA = ring_above(ROWS);
     const int lane = threadIdx.x & 31;
-    const int Lt = pc.Lt, nd = pc.nd, W = 2 * pc.r;
+    const int nd = pc.nd, W = 2 * pc.r;
     // B(Lr,Lt) = boff puts sum_cells F*B = fin * boff at about 2^kProductExp
     const float fin_raw = s_ftot[0];
     const int e_fin = (int)(__float_as_uint(fin_raw) >> 23) - 127;
@@ -506,16 +616,17 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
 
     // ---- ring of forward rows ------------------------------------------------------------------------
     const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+    const ulonglong2 *ring_q = reinterpret_cast<const ulonglong2 *>(ring);
     const float2 *grow0 = frow - (ptrdiff_t)kRowShift * RS; // global row rho = 0
     auto issue_group = [&](int q) { // rows rho = 4q .. 4q+3
         if (elect_one()) {
             const unsigned g = (unsigned)q & 3u;
             const unsigned bar = bars + 8u * g;
             const float2 *src = grow0 + (size_t)(4 * q) * RS;
-            mbar_expect_tx(bar, (g == 0u || g == 3u) ? 7u * RSB : 4u * RSB);
-            bulk_g2s(ring_s + (4u * g + kRingMargin) * RSB, src, 4u * RSB, bar);
-            if (g == 3u) bulk_g2s(ring_s, src + RS, 3u * RSB, bar);                                // rows 13..15 below slot 0
-            if (g == 0u) bulk_g2s(ring_s + (kRingRows + kRingMargin) * RSB, src, 3u * RSB, bar);  // rows 0..2 above slot 15
+            mbar_expect_tx(bar, (4u + (g == 3u ? MB : 0u) + (g == 0u ? MA : 0u)) * RSB);
+            bulk_g2s(ring_s + (4u * g + MB) * RSB, src, 4u * RSB, bar);
+            if (g == 3u) bulk_g2s(ring_s, src + (4 - (int)MB) * RS, MB * RSB, bar);                    // rows 16-MB..15 below slot 0
+            if (MA > 0u && g == 0u) bulk_g2s(ring_s + (kRingRows + MB) * RSB, src, MA * RSB, bar);    // rows 0..MA-1 above slot 15
         }
     };
     auto wait_group = [&](int q) {
@@ -532,84 +643,12 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
     issue_group(q_top - 1);
 
     BwdState<C> st;
-#pragma unroll
-    for (int c = 0; c < C; c++) {
-        const int sigma = lane * C + c;
-        const int d = (Lt - sigma) & (NSLOT - 1);
-        st.j[c] = Lt - d;      // largest column <= Lt owned by this slot
-        st.x[c] = d + pc.r;    // row i = Lr + d on the last anti-diagonal, window starts at row Lr - r
-        st.tcB[c] = pc.sEM + ((unsigned)pc.Tb[st.j[c] + 1] << 5); // code of t[j]
-        st.tcn[c] = pc.Tb[st.j[c] + 1 - NSLOT];
-        st.win[c] = 0u;
-        st.rbp[c] = STAGED ? rb0 + (nd - st.j[c]) : nullptr; // row s - j + 1 at s = nd - 1
-        st.BI[c] = st.BMo[c] = st.inD[c] = st.inMa[c] = st.inMb[c] = 0.f;
-        st.Vs[c] = st.Vn[c] = 0.f;
-        st.S01[c] = st.S23[c] = st.N01[c] = st.N23[c] = 0ull;
-#pragma unroll
-        for (int e = 0; e < 3; e++) { st.Xp[c][e] = 0ull; st.Xm[c][e] = 0ull; }
-    }
+    bwd_init<C>(st, pc, rb0);
+    auto raw_of = [&](int j) -> float4 * { return raw + (size_t)j * 4; };
 
-    // a finished column leaves its 16 raw sums in the pair's scratch (64 B, one lane); finalize_kernel turns them into the
-    // 14 log-ratios of the table
-    // raw[j] = { S0 S1 | S2 S3 | N0 N1 | N2 N3 | Vs Vn Xp0 Xp1 | Xp2 Xm0 Xm1 Xm2 }: the packed accumulators go out as they
-    // sit in their register pairs (8-byte stores), only the cut sums are assembled
-    auto flush_col = [&](int c) {
-        f2 *sg = reinterpret_cast<f2 *>(raw + (size_t)st.j[c] * 4);
-        asm volatile("st.global.cg.b64 [%0], %1;" ::"l"(sg + 0), "l"(st.S01[c]) : "memory");
-        asm volatile("st.global.cg.b64 [%0], %1;" ::"l"(sg + 1), "l"(st.S23[c]) : "memory");
-        asm volatile("st.global.cg.b64 [%0], %1;" ::"l"(sg + 2), "l"(st.N01[c]) : "memory");
-        asm volatile("st.global.cg.b64 [%0], %1;" ::"l"(sg + 3), "l"(st.N23[c]) : "memory");
-        __stcg(raw + (size_t)st.j[c] * 4 + 2, make_float4(st.Vs[c], st.Vn[c], lo2(st.Xp[c][0]) + hi2(st.Xp[c][0]),
-                                                          lo2(st.Xp[c][1]) + hi2(st.Xp[c][1])));
-        __stcg(raw + (size_t)st.j[c] * 4 + 3, make_float4(lo2(st.Xp[c][2]) + hi2(st.Xp[c][2]), lo2(st.Xm[c][0]) + hi2(st.Xm[c][0]),
-                                                          lo2(st.Xm[c][1]) + hi2(st.Xm[c][1]), lo2(st.Xm[c][2]) + hi2(st.Xm[c][2])));
-    };
-    // hand (B_M, B_D) to the left-hand neighbour column: slot sigma receives from slot sigma+1 -- the next slot of the same
-    // lane, or slot 0 of lane+1 (wrapping) for the last one: one pair of shuffles per lane and step
-    auto hand_off = [&](f2 (&bMD)[C]) {
-        const float rM = __shfl_sync(kFull, lo2(bMD[0]), (lane + 1) & 31);
-        const float rD = __shfl_sync(kFull, hi2(bMD[0]), (lane + 1) & 31);
-#pragma unroll
-        for (int c = 0; c < C - 1; c++) { st.inMb[c] = st.inMa[c]; st.inMa[c] = lo2(bMD[c + 1]); st.inD[c] = hi2(bMD[c + 1]); }
-        st.inMb[C - 1] = st.inMa[C - 1]; st.inMa[C - 1] = rM; st.inD[C - 1] = rD;
-    };
-    // Anti-diagonal s -> s-1 when the centre stays (guide bit 0): every cell moves one row down inside the window
-    // (x--), and the slot at the bottom of the band has seen its last in-band cell.  Retirement is DEFERRED to the end of
-    // the block of four anti-diagonals: a slot with x < 0 is masked like any cell outside the band, the ring has
-    // NSLOT - (W+1) >= 3 spare slots, and the column j - NSLOT that the slot takes over cannot enter the band before the
-    // first step of the next block.  The (on average two) slots that retire in one block are neighbouring lanes with the
-    // same c, so one pass through the flush code serves them all.
-    auto retire = [&]() {
-#pragma unroll
-        for (int c = 0; c < C; c++) {
-            if (st.x[c] < 0) {
-                if (st.j[c] >= 0) flush_col(c);
-                st.j[c] -= NSLOT;
-                st.x[c] += NSLOT;
-                if (STAGED) st.rbp[c] += NSLOT;
-                st.tcB[c] = pc.sEM + (st.tcn[c] << 5); // fetched one column-life ago; the window comes with the next reload
-                st.tcn[c] = pc.Tb[st.j[c] + 1 - NSLOT];
-                // reset = multiply by zero, one instruction per register pair (the sums are finite and >= 0); a plain
-                // "= 0" went through 22 uniform-register moves + 22 copies in SASS
-                clear2(st.S01[c]); clear2(st.S23[c]); clear2(st.N01[c]); clear2(st.N23[c]);
-                clear1(st.Vs[c]); clear1(st.Vn[c]);
-#pragma unroll
-                for (int e = 0; e < 3; e++) { // the 9-row kernel only accumulates Xm[0]: leave the others to the compiler
-                    if (ROWS == 14) clear2(st.Xp[c][e]); else st.Xp[c][e] = 0ull;
-                    if (ROWS == 14 || e == 0) clear2(st.Xm[c][e]); else st.Xm[c][e] = 0ull;
-                }
-            }
-        }
-    };
-    auto reload = [&](int s) {
-        if (STAGED) return;
-#pragma unroll
-        for (int c = 0; c < C; c++) st.win[c] = win_down(pc.RbP, s - st.j[c] + 1);
-    };
     // generic step: any s, exact corrections, ring slot computed from s
     auto slow_step = [&](int s) {
-        const f2 *rp = ring + (size_t)(((s + kRowShift) & (kRingRows - 1)) + kRingMargin) * RS + kPlaneHalo + lane;
-        if (s == nd - 1 || (s & 3) == 3) reload(s);
+        const ulonglong2 *rq = ring_q + (size_t)(((s + kRowShift) & (kRingRows - 1)) + MB) * RQ + kPlaneHalo + lane;
         // cumulative scale exponent of forward row t: rescales happen on the last row of a block of four, kb[q] = exponent
         // after block q
         auto kfat = [&](int t) -> int { return kb[(t - 3) >> 2]; };
@@ -618,23 +657,16 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
         float ce[7];
 #pragma unroll
         for (int e = -3; e <= 3; e++) ce[e + 3] = pow2i(max(-126, min(126, kcur - kfat(s + e))));
-        f2 bMD[C];
-        if (s == nd - 1) bwd_step<C, ROWS, true, true, STAGED>(pc, a, st, rp, W, ce, boff, bMD);
-        else bwd_step<C, ROWS, true, false, STAGED>(pc, a, st, rp, W, ce, boff, bMD);
-        if (STAGED) {
+        f2 bM[P], bD[P];
+        if (s == nd - 1) bwd_step<C, ROWS, true, true>(pc, a, st, rq, ce, boff, bM, bD, 0);
+        else bwd_step<C, ROWS, true, false>(pc, a, st, rq, ce, boff, bM, bD, 0);
 #pragma unroll
-            for (int c = 0; c < C; c++) st.rbp[c] -= 1;
-        }
-        hand_off(bMD);
+        for (int c = 0; c < C; c++) st.rbp[c] -= 1;
+        bwd_hand_off<C>(st, bM, bD);
         if (s > 0) {
-            if (kstep != 0) { // mirror of the forward rescale at step s
-                const float sc = pow2i(kstep);
-#pragma unroll
-                for (int c = 0; c < C; c++) { st.BI[c] *= sc; st.BMo[c] *= sc; st.inD[c] *= sc; st.inMa[c] *= sc; st.inMb[c] *= sc; }
-            }
+            if (kstep != 0) bwd_scale<C>(st, pow2i(kstep)); // mirror of the forward rescale at step s
             const int dec = (int)(((pc.bw[(s - 1) >> 5] >> ((s - 1) & 31)) & 1u) ^ 1u);
-#pragma unroll
-            for (int c = 0; c < C; c++) st.x[c] -= dec;
+            bwd_band_down<C>(st, dec, W);
         }
     };
 
@@ -665,57 +697,43 @@ __device__ __forceinline__ void backward_pass(const PairCtx &pc, const Coef &a, 
     for (int q = q_top; q >= 1; --q) {
         const int mode = preamble(q);
         if (mode == 2) { // a rescale within reach: the fast block with the exact corrections of its cut products
-            const f2 *rp = ring + (size_t)(4 * (q & 3) + 3 + kRingMargin) * RS + kPlaneHalo + lane;
-            reload(4 * q - 1);
+            const ulonglong2 *rq = ring_q + (size_t)(4 * (q & 3) + 3 + MB) * RQ + kPlaneHalo + lane;
             const unsigned nib = nib_cur;
             const float fA = pow2c(kA), fB = pow2c(kB), fBi = pow2c(-kB);
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                f2 bMD[C];
+                f2 bM[P], bD[P];
                 float ce[7];
                 block_corrections(k, fA, fB, fBi, ce);
-                bwd_step<C, ROWS, true, false, STAGED>(pc, a, st, rp - k * RS, W, ce, boff, bMD, k);
-                hand_off(bMD);
-                if (k == 0 && kB != 0) { // mirror of the forward rescale on row 4q-1
-                    const float sc = pow2i(kB);
-#pragma unroll
-                    for (int c = 0; c < C; c++) { st.BI[c] *= sc; st.BMo[c] *= sc; st.inD[c] *= sc; st.inMa[c] *= sc; st.inMb[c] *= sc; }
-                }
-                const int dec = (int)(((nib >> (3 - k)) & 1u) ^ 1u);
-#pragma unroll
-                for (int c = 0; c < C; c++) st.x[c] -= dec;
+                bwd_step<C, ROWS, true, false>(pc, a, st, rq - k * RQ, ce, boff, bM, bD, k);
+                bwd_hand_off<C>(st, bM, bD);
+                if (k == 0 && kB != 0) bwd_scale<C>(st, pow2i(kB)); // mirror of the forward rescale on row 4q-1
+                bwd_band_down<C>(st, (int)(((nib >> (3 - k)) & 1u) ^ 1u), W);
             }
-            if (STAGED) {
 #pragma unroll
-                for (int c = 0; c < C; c++) st.rbp[c] -= 4;
-            }
+            for (int c = 0; c < C; c++) st.rbp[c] -= 4;
         } else if (mode == 1) {
-            const f2 *rp = ring + (size_t)(4 * (q & 3) + 3 + kRingMargin) * RS + kPlaneHalo + lane;
-            reload(4 * q - 1);
+            const ulonglong2 *rq = ring_q + (size_t)(4 * (q & 3) + 3 + MB) * RQ + kPlaneHalo + lane;
             // guide bits 4q-5 .. 4q-2 (fetched one block ahead): step k (s = 4q-1-k) moves on with bit 4q-2-k
             const unsigned nib = nib_cur;
 #pragma unroll kBwdUnroll
             for (int k = 0; k < 4; k++) {
-                f2 bMD[C];
-                bwd_step<C, ROWS, false, false, STAGED>(pc, a, st, rp - k * RS, W, nullptr, boff, bMD, k);
-                hand_off(bMD);
-                const int dec = (int)(((nib >> (3 - k)) & 1u) ^ 1u);
-#pragma unroll
-                for (int c = 0; c < C; c++) st.x[c] -= dec;
+                f2 bM[P], bD[P];
+                bwd_step<C, ROWS, false, false>(pc, a, st, rq - k * RQ, nullptr, boff, bM, bD, k);
+                bwd_hand_off<C>(st, bM, bD);
+                bwd_band_down<C>(st, (int)(((nib >> (3 - k)) & 1u) ^ 1u), W);
             }
-            if (STAGED) {
 #pragma unroll
-                for (int c = 0; c < C; c++) st.rbp[c] -= 4;
-            }
+            for (int c = 0; c < C; c++) st.rbp[c] -= 4;
         } else {
             for (int s = min(4 * q - 1, nd - 1); s >= 4 * q - 4; --s) slow_step(s);
         }
-        retire();
+        bwd_retire<C, ROWS>(st, pc, raw_of);
     }
     // the columns still in the window after s = 0 (0 .. r) are complete
 #pragma unroll
     for (int c = 0; c < C; c++)
-        if (st.j[c] >= 0) flush_col(c);
+        if (st.j[c] >= 0) bwd_flush_col<C>(st, c, raw_of(st.j[c]));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -730,273 +748,52 @@ __device__ __forceinline__ PairCtx make_pair_ctx(const KParams &p, const DevPair
     pc.Lt = P.Lt; pc.Lr = P.Lr; pc.nd = P.Lt + P.Lr + 1; pc.r = p.radius;
     pc.sEM = (unsigned)__cvta_generic_to_shared(&sh.em[P.model][0]);
     pc.sEI = (unsigned)__cvta_generic_to_shared(&sh.ei[P.model][0]);
-    pc.sEMT = (unsigned)__cvta_generic_to_shared(&sh.emt[P.model][0]);
+    pc.sEC = 0u;
+    return pc;
+}
+// ... of a kernel that runs the backward / table step (its tables hold the paired substitution emissions)
+template <typename SM>
+__device__ __forceinline__ PairCtx make_pair_ctx_bwd(const KParams &p, const DevPair &P, SM &sh) {
+    PairCtx pc = make_pair_ctx(p, P, sh);
+    pc.sEC = (unsigned)__cvta_generic_to_shared(&sh.ecp[P.model][0]);
     return pc;
 }
 
-template <int C> constexpr int ring_floats2() { return (kRingRows + 2 * kRingMargin) * (C * kPlane); }
-
-// ------------------------------------------------------------------------------------------------
-// Kernel 1 of the modification table: the forward pass of every pair of the wave (v7).
-//   * read codes and template codes of the pair are staged in shared memory once (compact one-byte table offsets), so
-//     the step body has no window registers, no reloads and one integer instruction per emission lookup;
-//   * a cell outside the band is handled by multiplying its three out-sums with a per-slot 0/1 float that is
-//     recomputed only when the band moves (FMA pipe instead of per-cell compares and selects);
-//   * the guide bits are consumed four at a time, slots are retargeted once per block of four anti-diagonals;
-//   * the scale exponent is kept per BLOCK (rescales only happen on the last step of a block): kb[q].
-// Writes the forward rows (toM, toD of every cell), kb, the four end sums and the likelihood.
-// ------------------------------------------------------------------------------------------------
-constexpr int kIdxModel = 25;   // compact read-code index = model*25 + ctx*5 + q  (q, ctx in 0..4, 4 = none)
-constexpr int kEm2Stride = 52;  // floats per template-code row of em2
-struct __align__(16) FwdSmem {
-    float em2[5][kEm2Stride];      // [tc][idx] = eM(model(idx); tc, q(idx)), zero for tc = 4 or q = 4
-    float ei2[kEm2Stride];         // [idx]     = eI(model(idx); ctx(idx), q(idx))
-    unsigned char lut[2][256];     // global read-code byte (ctx<<5 | q<<2) -> byte offset 4*idx
-    float trans[2][12];
-    unsigned long long cpair[2][6];
-    float ftot[kWarpsPerCta][4];
-};
-
-__device__ __forceinline__ void fill_fwd_tables(FwdSmem &sh, const float *__restrict__ models) {
-    for (int k = threadIdx.x; k < 5 * kEm2Stride; k += blockDim.x) {
-        const int tc = k / kEm2Stride, idx = k % kEm2Stride;
-        float v = 0.f, w = 0.f;
-        if (idx < 2 * kIdxModel) {
-            const int m = idx / kIdxModel, ctx = (idx % kIdxModel) / 5, q = idx % 5;
-            if (tc < 4 && q < 4) v = models[m * kModelFloats + kOffEM + tc * 8 + q];
-            if (q < 4) w = models[m * kModelFloats + kOffEI + ctx * 8 + q];
-        }
-        sh.em2[tc][idx] = v;
-        if (tc == 0) sh.ei2[idx] = w;
-    }
-    for (int k = threadIdx.x; k < 512; k += blockDim.x) {
-        const int m = k >> 8, b = k & 255;
-        const int ctx = min(b >> 5, 4), q = min((b >> 2) & 7, 4);
-        sh.lut[m][b] = (unsigned char)(4 * (m * kIdxModel + ctx * 5 + q));
-    }
-    for (int k = threadIdx.x; k < 24; k += blockDim.x) {
-        const int m = k / 12, e = k % 12;
-        sh.trans[m][e] = models[m * kModelFloats + e];
-        if (e < 6) {
-            const int lo_i[6] = { 0, 3, 6, 0, 1, 2 }, hi_i[6] = { 2, 5, 8, 6, 7, 8 };
-            sh.cpair[m][e] = mk2(models[m * kModelFloats + lo_i[e]], models[m * kModelFloats + hi_i[e]]);
-        }
-    }
-    __syncthreads();
-}
-
-constexpr int fwd_ctas_per_sm(int C) { return C == 2 ? 6 : (C == 4 ? 3 : 2); }
-template <int C>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, fwd_ctas_per_sm(C)) fwdrows_kernel(KParams p) {
-    __shared__ FwdSmem sh;
-    extern __shared__ __align__(128) unsigned char dyn_smem[];
-    fill_fwd_tables(sh, p.models);
-    constexpr int NSLOT = 32 * C;
-    constexpr int RS = C * kPlane;   // a row is C planes of 32 + 2*2 entries (see kPlane)
-    constexpr int PADR = NSLOT + 16; // staged read rows: -PADR .. Lr + PADR
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char *rb_s = dyn_smem + (size_t)warp * (p.smem_rb + p.smem_tb); // rb_s[i + PADR] = 4*idx of read row i
-    unsigned char *tb_s = rb_s + p.smem_rb;                                  // tb_s[j] = template code of column j (t[j-1])
-    volatile float *s_ftot = sh.ftot[warp];
-    const int W = 2 * p.radius;
-    for (;;) {
-        int k = 0;
-        if (lane == 0) k = atomicAdd(p.counter, 1);
-        k = __shfl_sync(kFull, k, 0);
-        if (p.pair_lo + k >= p.pair_hi) break;
-        const int pi = pair_index(p, k);
-        const DevPair P = p.pairs[pi];
-        const int Lt = P.Lt, Lr = P.Lr, nd = Lt + Lr + 1;
-        const Coef a = load_coef(sh.trans[P.model], sh.cpair[P.model]);
-        float2 *frow = p.frows + (size_t)k * p.frow_stride + kRowShift * RS; // row 0 (kRowShift zero rows below)
-        int32_t *kb = p.kf + (size_t)k * p.kf_stride + 4;                    // kb[q], q >= -4
-        unsigned *info = p.fwdinfo + (size_t)k * p.fwdinfo_stride;
-        // ---- stage the codes of this pair ----
-        {
-            const uint8_t *Rb = p.codes + P.rb_off;
-            const uint8_t *Tb = p.codes + P.tb_off;
-            const unsigned char *lut = sh.lut[P.model];
-            const int nr = Lr + 2 * PADR, nt = Lt + NSLOT + 16;
-            for (int w = lane; w < nr; w += 32) rb_s[w] = lut[Rb[w - PADR]];
-            for (int w = lane; w < nt; w += 32) tb_s[w] = Tb[w];
-            // rows -kRowShift..-1 (before the first anti-diagonal) read as zero, exponent 0
-            for (int w = lane; w < kRowShift * RS; w += 32) frow[w - kRowShift * RS] = make_float2(0.f, 0.f);
-            if (lane < 4) { kb[lane - 4] = 0; s_ftot[lane] = 0.f; }
-        }
-        __syncwarp();
-        // ---- per-slot state ----
-        int x[C];                 // offset of the slot's cell inside the band window of the current anti-diagonal
-        const unsigned char *rbp[C]; // staged read code of the slot's cell (row s - j)
-        const unsigned char *tbp[C]; // staged template code of the slot's column
-        const char *emrow[C];     // em2 row of the slot's column
-        float msk[C], toI[C], inD[C], inMa[C], inMb[C];
-#pragma unroll
-        for (int c = 0; c < C; c++) {
-            const int j = lane * C + c;
-            x[c] = p.radius - j;
-            rbp[c] = rb_s + PADR - j;
-            tbp[c] = tb_s + j;
-            emrow[c] = reinterpret_cast<const char *>(sh.em2[min((int)tbp[c][0], 4)]);
-            msk[c] = (unsigned)x[c] <= (unsigned)W ? 1.f : 0.f;
-            toI[c] = inD[c] = inMa[c] = inMb[c] = 0.f;
-        }
-        f2 *wrow = reinterpret_cast<f2 *>(frow) + kPlaneHalo + lane; // entry `lane` of plane 0 in row 0; slot c is in plane c
-        const int halo = (lane < kPlaneHalo) ? 32 : ((lane >= 32 - kPlaneHalo) ? -32 : 0);
-        int K = 0;
-        const uint32_t *bw = p.bits + P.bits_off;
-
-        // one anti-diagonal; kk = row offset inside the current block (immediate in the unrolled loop)
-        auto step = [&](const int s, const int kk, const bool special, const bool rescale) {
-            f2 tMD[C];
-            float nI[C];
-#pragma unroll
-            for (int c = 0; c < C; c++) {
-                const unsigned w = rbp[c][kk];
-                const float em = *reinterpret_cast<const float *>(emrow[c] + w);
-                const float ei = *reinterpret_cast<const float *>(reinterpret_cast<const char *>(sh.ei2) + w);
-                float M = em * inMb[c];
-                const float I = ei * toI[c];
-                const float D = inD[c];
-                if (special && s == 0 && lane * C + c == 0) M = 1.f;
-                tMD[c] = mul2(fma2(a.fD, bc2(D), fma2(a.fI, bc2(I), mul2(a.fM, bc2(M)))), bc2(msk[c]));
-                nI[c] = fmaf(a.f_di, D, fmaf(a.f_ii, I, a.f_mi * M)) * msk[c];
-                if (special && s >= nd - 4 && msk[c] != 0.f) {
-                    const int j = (int)(tbp[c] - tb_s);
-                    if (s - j == Lr && j >= Lt - 3) s_ftot[Lt - j] = M + I + D;
-                }
-            }
-            if (rescale) {
-                float v = lo2(tMD[0]);
-#pragma unroll
-                for (int c = 1; c < C; c++) v = fmaxf(v, lo2(tMD[c]));
-                const unsigned mx = __reduce_max_sync(kFull, __float_as_uint(v));
-                const int e = (int)(mx >> 23) - 127;
-                if (mx != 0u && e < kScaleLow) {
-                    const int kx = min(kScaleTarget - e, kScaleStep);
-                    const float sc = pow2i(kx);
-#pragma unroll
-                    for (int c = 0; c < C; c++) { tMD[c] = mul2(tMD[c], bc2(sc)); nI[c] *= sc; inMa[c] *= sc; }
-                    K += kx;
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < C; c++)
-                asm volatile("st.global.b64 [%0], %1;" ::"l"(wrow + kk * RS + c * kPlane), "l"(tMD[c]) : "memory");
-            if (halo != 0) { // the first / last entries of every plane are replicated past its other end
-#pragma unroll
-                for (int c = 0; c < C; c++)
-                    asm volatile("st.global.b64 [%0], %1;" ::"l"(wrow + kk * RS + c * kPlane + halo), "l"(tMD[c]) : "memory");
-            }
-            // hand (toM, toD) to the right-hand neighbour column (slot+1, wrapping)
-            const float rM = __shfl_sync(kFull, lo2(tMD[C - 1]), (lane + 31) & 31);
-            const float rD = __shfl_sync(kFull, hi2(tMD[C - 1]), (lane + 31) & 31);
-#pragma unroll
-            for (int c = C - 1; c >= 1; c--) { inMb[c] = inMa[c]; inMa[c] = lo2(tMD[c - 1]); inD[c] = hi2(tMD[c - 1]); }
-            inMb[0] = inMa[0]; inMa[0] = rM; inD[0] = rD;
-#pragma unroll
-            for (int c = 0; c < C; c++) toI[c] = nI[c];
-        };
-        // anti-diagonal s -> s+1 when the centre stays (guide bit 0): every cell moves one row up inside the window
-        auto band_up = [&]() {
-#pragma unroll
-            for (int c = 0; c < C; c++) { x[c]++; msk[c] = (unsigned)x[c] <= (unsigned)W ? 1.f : 0.f; }
-        };
-        // a slot whose cell left the band at the top (x > W) moves on to column j + NSLOT; it has NSLOT - (W+1) >= 3 band
-        // moves of slack, and until then its mask is zero
-        auto retarget = [&]() {
-#pragma unroll
-            for (int c = 0; c < C; c++) {
-                if (x[c] > W) {
-                    x[c] -= NSLOT; rbp[c] -= NSLOT; tbp[c] += NSLOT;
-                    emrow[c] = reinterpret_cast<const char *>(sh.em2[min((int)tbp[c][0], 4)]);
-                    msk[c] = (unsigned)x[c] <= (unsigned)W ? 1.f : 0.f;
-                }
-            }
-        };
-        auto advance = [&](int n) {
-#pragma unroll
-            for (int c = 0; c < C; c++) rbp[c] += n;
-            wrow += n * RS;
-        };
-        int s = 0;
-        // prologue: the first four anti-diagonals (the start cell is injected at s = 0)
-        for (; s < 4 && s < nd; ++s) {
-            step(s, 0, true, false);
-            advance(1);
-            if (s < nd - 1) { if (((bw[s >> 5] >> (s & 31)) & 1u) == 0u) band_up(); retarget(); }
-        }
-        if (lane == 0) kb[0] = 0;
-        // main loop: blocks of four anti-diagonals, guide bits four at a time
-        unsigned bword = bw[0];
-        for (; s + 3 < nd - 4; s += 4) {
-            if ((s & 31) == 0) bword = bw[s >> 5];
-            const unsigned nib = bword >> (s & 31);
-            step(s, 0, false, false);     if ((nib & 1u) == 0u) band_up();
-            step(s + 1, 1, false, false); if ((nib & 2u) == 0u) band_up();
-            step(s + 2, 2, false, false); if ((nib & 4u) == 0u) band_up();
-            step(s + 3, 3, false, s + 3 < nd - 8); if ((nib & 8u) == 0u) band_up();
-            retarget();
-            advance(4);
-            if (lane == 0) kb[s >> 2] = K;
-        }
-        // epilogue: the last anti-diagonals also record the delete-to-end terms
-        for (; s < nd; ++s) {
-            step(s, 0, true, false);
-            advance(1);
-            if (s < nd - 1) { if (((bw[s >> 5] >> (s & 31)) & 1u) == 0u) band_up(); retarget(); }
-        }
-        // rows just past the last anti-diagonal read as zero; the exponent stays at K
-        for (int w = lane; w < kRowsAbove * RS; w += 32) frow[(size_t)nd * RS + w] = make_float2(0.f, 0.f);
-        {
-            const int q0 = (nd - 8) >> 2; // blocks from here on cannot rescale
-            for (int q = max(q0, 0) + lane; q <= ((nd + 3) >> 2) + 2; q += 32) kb[q] = K;
-        }
-        __syncwarp();
-        const float fin = s_ftot[0];
-        if (lane < 4) info[lane] = __float_as_uint(s_ftot[lane]);
-        if (lane == 4) info[4] = (unsigned)K;
-        if (lane == 0)
-            p.out_lk[pi] = fin > 0.f ? log((double)fin) - (double)K * 0.6931471805599453 : -INFINITY;
-        __syncwarp();
-    }
-}
+template <int C, int ROWS> constexpr int ring_floats2() { return (kRingRows + ring_below(ROWS) + ring_above(ROWS)) * (C * kPlane); }
 
 // Kernel 2: backward pass fused with the table reduction, reading the forward rows of kernel 1.  Finished columns leave
-// their 16 raw sums in the pair's scratch; kernel 3 (finalize) turns them into the table.  No staging buffer and a ring
-// without spare rows: 128 registers and 13 KB of shared memory per warp => 16 warps per SM.
+// their 16 raw sums in the pair's scratch; kernel 3 (finalize) turns them into the table.
 struct __align__(256) BwdSmem {
-    float em[2][64];  // [tc*8 + qc]   byte offset tc*32 + qc*4
-    float ei[2][64];  // [ctx*8 + qc]  byte offset = the read-row code byte (ctx<<5 | qc<<2)
-    float emt[2][32]; // [qc*4 + b]    eM(ref b, query qc)
+    float ecp[2][32];  // [qc*4 + b] = eM(ref b, read base qc)
+    float em[2][64];   // [tc*8 + qc]   byte offset tc*32 + qc*4
+    float ei[2][64];   // [ctx*8 + qc]  byte offset = the read-row code byte (ctx<<5 | qc<<2)
     float trans[2][12];
-    unsigned long long cpair[2][6];
     float ftot[kWarpsPerCta][4];
     unsigned long long bar[kWarpsPerCta][4];       // mbarriers of the four ring groups
 };
+template <typename SM> __device__ __forceinline__ void fill_ecp(SM &sh, const float *__restrict__ models) {
+    for (int k = threadIdx.x; k < 2 * 32; k += blockDim.x) sh.ecp[k >> 5][k & 31] = models[(k >> 5) * kModelFloats + kOffEMT + (k & 31)];
+}
 __device__ __forceinline__ void fill_bwd_tables(BwdSmem &sh, const float *__restrict__ models) {
+    fill_ecp(sh, models);
     for (int k = threadIdx.x; k < 2 * 64; k += blockDim.x) {
         const int m = k >> 6, e = k & 63;
         sh.em[m][e] = models[m * kModelFloats + kOffEM + e];
         sh.ei[m][e] = models[m * kModelFloats + kOffEI + e];
-        if (e < 32) sh.emt[m][e] = models[m * kModelFloats + kOffEMT + e];
         if (e < 12) sh.trans[m][e] = models[m * kModelFloats + e];
-        if (e < 6) {
-            const int lo_i[6] = { 0, 3, 6, 0, 1, 2 }, hi_i[6] = { 2, 5, 8, 6, 7, 8 };
-            sh.cpair[m][e] = mk2(models[m * kModelFloats + lo_i[e]], models[m * kModelFloats + hi_i[e]]);
-        }
     }
     __syncthreads();
 }
 
-template <int C, int ROWS, bool STAGED>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, bwd_ctas_per_sm(C, ROWS)) bwdtable_kernel(KParams p) {
+template <int C, int ROWS>
+__global__ void __launch_bounds__(bwd_warps_per_cta(C) * 32, bwd_ctas_per_sm(C, ROWS)) bwdtable_kernel(KParams p) {
     __shared__ BwdSmem sh;
-    extern __shared__ __align__(128) unsigned char dyn_smem[]; // kWarpsPerCta rings of forward rows (+ staged read codes)
+    extern __shared__ __align__(128) unsigned char dyn_smem[]; // kWarpsPerCta rings of forward rows + staged read codes
     fill_bwd_tables(sh, p.models);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int RS = C * kPlane, PADR = 32 * C + 16;
-    f2 *ring = reinterpret_cast<f2 *>(dyn_smem) + (size_t)warp * ring_floats2<C>();
-    unsigned char *rb_s = dyn_smem + (size_t)kWarpsPerCta * ring_floats2<C>() * sizeof(f2) + (size_t)warp * p.smem_rb; // rb_s[i + PADR]
+    f2 *ring = reinterpret_cast<f2 *>(dyn_smem) + (size_t)warp * ring_floats2<C, ROWS>();
+    unsigned char *rb_s = dyn_smem + (size_t)bwd_warps_per_cta(C) * ring_floats2<C, ROWS>() * sizeof(f2) + (size_t)warp * p.smem_rb; // rb_s[i + PADR]
     const unsigned bars = (unsigned)__cvta_generic_to_shared(&sh.bar[warp][0]);
     unsigned phase = 0u;
     if (lane < 4) mbar_init(bars + 8u * lane, 1u);
@@ -1009,19 +806,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, bwd_ctas_per_sm(C, ROWS)) b
         if (p.pair_lo + k >= p.pair_hi) break;
         const int pi = pair_index(p, k);
         const DevPair P = p.pairs[pi];
-        const PairCtx pc = make_pair_ctx(p, P, sh);
-        const Coef a = load_coef(sh.trans[P.model], sh.cpair[P.model]);
+        const PairCtx pc = make_pair_ctx_bwd(p, P, sh);
+        const BCoef a = load_bcoef(sh.trans[P.model]);
         const float2 *frow = p.frows + (size_t)k * p.frow_stride + kRowShift * RS;
         const int32_t *kb = p.kf + (size_t)k * p.kf_stride + 4;
         const unsigned *info = p.fwdinfo + (size_t)k * p.fwdinfo_stride;
         if (lane < 4) sh.ftot[warp][lane] = __uint_as_float(info[lane]);
-        if (STAGED) {
+        {   // stage the read-row codes of the pair
             const uint8_t *Rb = p.codes + P.rb_off;
             const int nr = P.Lr + 2 * PADR;
             for (int w = lane; w < nr; w += 32) rb_s[w] = Rb[w - PADR];
         }
         __syncwarp();
-        backward_pass<C, ROWS, STAGED>(pc, a, frow, kb, p.raw + (size_t)k * p.raw_stride, sh.ftot[warp], ring, bars, phase, rb_s + PADR);
+        backward_pass<C, ROWS>(pc, a, frow, kb, p.raw + (size_t)k * p.raw_stride, sh.ftot[warp], ring, bars, phase, rb_s + PADR);
         __syncwarp();
     }
 }
@@ -1274,19 +1071,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) fit_kernel(KParams p, doubl
 
 
 // ------------------------------------------------------------------------------------------------
-// v10: the modification table as ONE kernel whose DP matrices never touch HBM (north star: "the backward pass is fused with
-// the modification-table reduction so the full DP matrix never touches HBM").
+// The lean forward pass (all three modification-table kernels) and the fused kernel (v10 / v11): the modification table as
+// ONE kernel whose DP matrices never touch HBM (north star: "the backward pass is fused with the modification-table
+// reduction so the full DP matrix never touches HBM").
 //
-//   pass 1   lean forward pass (the v7 step body, no row stores): likelihood, one scale exponent per block of four
-//            anti-diagonals (kb, 1 int / 4 rows) and a CHECKPOINT of the forward state every SEG anti-diagonals
-//            (inMb, inMa, inD, toI of every slot + the band offset: C*512 + 16 bytes, i.e. 65 B per row instead of 576 B);
+//   pass 1   lean forward pass (no row stores): likelihood, one scale exponent per block of four anti-diagonals (kb, 1 int /
+//            4 rows) and a CHECKPOINT of the forward state every SEG anti-diagonals (inMb, inMa, inD, toI of every slot + the
+//            band offset: C*512 + 16 bytes, i.e. 65 B per row instead of the 608 B of a forward row);
 //   pass 2   top-down over segments of SEG anti-diagonals: the forward rows of the segment are RECOMPUTED from its
-//            checkpoint into a per-warp shared-memory buffer (same plane layout as the v9 ring), then the v9 backward /
-//            table step runs over them.  The cuts reach three rows up and down, so the buffer keeps the eight lowest rows of
-//            the segment above (moved up by one shared-memory copy per segment) and a segment's rows start four rows below
-//            its first backward row.  Checkpoint k+1... are fetched one segment ahead by a bulk async copy (mbarrier).
+//            checkpoint into a per-warp shared-memory buffer (same row layout as the ring of the rows variant), then the
+//            backward / table step runs over them.  The cuts reach three rows up and down, so the buffer keeps the eight
+//            lowest rows of the segment above (moved up by one shared-memory copy per segment) and a segment's rows start four
+//            rows below its first backward row.  Checkpoints are fetched one segment ahead by a bulk async copy (mbarrier).
 // The recomputation replays pass 1 instruction for instruction (explicit fma / mul intrinsics) and takes its rescale decisions
-// from kb, so the rows are the ones pass 1 saw.  FP32 work per cell: 11 (pass 1) + 11 (recompute) + 11 + 24 (backward, table).
+// from kb, so the rows are the ones pass 1 saw.  The rows variant runs the same forward code once, with the rows going to HBM.
 // ------------------------------------------------------------------------------------------------
 template <int C> __host__ __device__ constexpr int seg_rows() { return C == 2 ? 16 : 8; }
 constexpr int kSegKeep = 8;   // rows of the segment above that stay in the buffer
@@ -1297,31 +1095,36 @@ template <int C> __host__ __device__ constexpr int ckpt_bytes() { return C * 512
 template <int C> __host__ __device__ constexpr int ckpt_stage_bytes() { return (ckpt_bytes<C>() + 32 + 127) & ~127; }
 constexpr int fused_ctas_per_sm(int C) { return C == 2 ? 3 : (C == 4 ? 2 : 1); }
 
-// shared tables of the fused kernel (as BwdSmem): both passes look emissions up with the raw read-row code byte w = ctx<<5 | q<<2,
-// eM at (row of the column's base) | (w & 0x1c), eI at base + w: every distinct address of a warp sits in its own bank
-struct __align__(256) LeanSmem {
+// shared tables of the forward kernel: emissions are looked up with the raw read-row code byte w = ctx<<5 | q<<2, eM at
+// (row of the column's base) | (w & 0x1c), eI at base + w: every distinct address of a warp sits in its own bank
+struct __align__(256) FwdTabSmem {
     float em[2][64];  // [tc*8 + qc]
     float ei[2][64];  // [ctx*8 + qc], byte offset = the read-row code byte
-    float emt[2][32]; // backward: [qc*4 + b]
+    unsigned long long cdup[2][9]; // (t[k], t[k]): the nine transitions as broadcast pairs
+    float ftot[kWarpsPerCta][4];
+};
+// ... of the fused kernel: the same + what the backward / table step needs
+struct __align__(256) LeanSmem {
+    float ecp[2][32];  // backward: [qc*4 + b] = eM(ref b, read base qc)
+    float em[2][64];
+    float ei[2][64];
     float trans[2][12];
-    unsigned long long cpair[2][6];
-    unsigned long long cdup[2][9]; // (t[k], t[k]): the nine transitions as broadcast pairs (slot-paired forward step)
+    unsigned long long cdup[2][9];
     float ftot[kWarpsPerCta][4];
     unsigned long long bar[kWarpsPerCta];
 };
-__device__ __forceinline__ void fill_lean_tables(LeanSmem &sh, const float *__restrict__ models) {
+template <typename SM> __device__ __forceinline__ void fill_fwd_part(SM &sh, const float *__restrict__ models) {
     for (int k = threadIdx.x; k < 2 * 64; k += blockDim.x) {
         const int m = k >> 6, e = k & 63;
         sh.em[m][e] = models[m * kModelFloats + kOffEM + e];
         sh.ei[m][e] = models[m * kModelFloats + kOffEI + e];
-        if (e < 32) sh.emt[m][e] = models[m * kModelFloats + kOffEMT + e];
-        if (e < 12) sh.trans[m][e] = models[m * kModelFloats + e];
         if (e < 9) sh.cdup[m][e] = mk2(models[m * kModelFloats + e], models[m * kModelFloats + e]);
-        if (e < 6) {
-            const int lo_i[6] = { 0, 3, 6, 0, 1, 2 }, hi_i[6] = { 2, 5, 8, 6, 7, 8 };
-            sh.cpair[m][e] = mk2(models[m * kModelFloats + lo_i[e]], models[m * kModelFloats + hi_i[e]]);
-        }
     }
+}
+__device__ __forceinline__ void fill_lean_tables(LeanSmem &sh, const float *__restrict__ models) {
+    fill_fwd_part(sh, models);
+    fill_ecp(sh, models);
+    for (int k = threadIdx.x; k < 24; k += blockDim.x) sh.trans[k / 12][k % 12] = models[(k / 12) * kModelFloats + k % 12];
     __syncthreads();
 }
 
@@ -1340,8 +1143,9 @@ struct LeanPair { // warp-uniform view of one pair for the lean forward pass
     int Lt, Lr, nd, r;
 };
 
-// Forward state with the two adjacent slots 2p, 2p+1 of a lane packed into one fp32 pair (lo = slot 2p): every arithmetic
-// instruction of the step is a packed one, the coefficients are (v, v) pairs and nothing has to be broadcast.
+// Forward state: lane l owns the slots l + 32c; the cells of slots l + 64p and l + 64p + 32 are packed into one fp32 pair
+// (lo = the lower slot): every arithmetic instruction of the step is a packed one, the coefficients are (v, v) pairs and
+// nothing moves between the halves of a pair (the hand-off to the right-hand neighbour column is lane -> lane+1 for both).
 template <int C> struct LeanFwd {
     static constexpr int P = C / 2;
     int x[C];
@@ -1363,13 +1167,13 @@ __device__ __forceinline__ void set_hi(f2 &v, float x) { v = mk2(lo2(v), x); }
 // slot state of anti-diagonal s0 (a multiple of four) from the number of band moves so far: the slot holds the one column
 // j == sigma (mod NSLOT) with x <= W, which is what the per-block retargeting of the forward pass leaves at block boundaries
 template <int C>
-__device__ __forceinline__ void lean_seed(const LeanSmem &sh, LeanFwd<C> &st, const LeanPair &lp, const int s0, const int ups) {
+__device__ __forceinline__ void lean_seed(LeanFwd<C> &st, const LeanPair &lp, const int s0, const int ups) {
     constexpr int NSLOT = 32 * C;
     const int lane = threadIdx.x & 31, W = 2 * lp.r;
     float m[C];
 #pragma unroll
     for (int c = 0; c < C; c++) {
-        const int sigma = lane * C + c;
+        const int sigma = lane + 32 * c;
         const int t = lp.r - sigma + ups;
         const int w = t > W ? (t - W + NSLOT - 1) / NSLOT : 0;
         const int j = sigma + w * NSLOT;
@@ -1385,15 +1189,19 @@ __device__ __forceinline__ void lean_seed(const LeanSmem &sh, LeanFwd<C> &st, co
 }
 
 // Rows [s_begin, s_end) of the forward pass, s_begin a multiple of four, s_end a multiple of four or nd.
-// MODE 0 (pass 1): rescale decisions by warp maximum, kb[q] and checkpoints written, end sums recorded.
-// MODE 1 (recompute): rescales replayed from kb, (toM, toD) of every cell written to the shared-memory rows at `wrow`
-// (entry `lane` of plane 0 of row s_begin).
+// MODE 0 (fused, pass 1): rescale decisions by warp maximum, kb[q] and checkpoints written, end sums recorded.
+// MODE 1 (fused, recompute): rescales replayed from kb, (toM, toD) of every cell written to the shared-memory rows at `wrow`
+// MODE 2 (rows variant): decisions and kb as MODE 0, no checkpoints, rows written to global memory at `wrow`
+// (wrow = entry `lane` of pair plane 0 of row s_begin, as f2 *).
 template <int C, int MODE>
-__device__ __forceinline__ void lean_forward(const LeanSmem &sh, const LeanCoef &a, LeanFwd<C> &st, const LeanPair &lp, const int s_begin,
+__device__ __forceinline__ void lean_forward(const LeanCoef &a, LeanFwd<C> &st, const LeanPair &lp, const int s_begin,
                                              const int s_end, int &K, int &ups, const KbRef kb,
                                              unsigned char *__restrict__ ckpt_g, f2 *wrow, volatile float *s_ftot, unsigned &ev) {
     constexpr int NSLOT = 32 * C, RS = C * kPlane, SEG = seg_rows<C>(), CKB = ckpt_bytes<C>(), P = C / 2;
+    constexpr bool DECIDE = MODE != 1; // this pass takes the rescale decisions (and records the end sums)
     const int lane = threadIdx.x & 31, W = 2 * lp.r, nd = lp.nd;
+    // the replicated entries past the ends of a plane: lanes 0..2 also write entry 32 + lane, lanes 29..31 entry lane - 32
+    const int halo = (lane < kPlaneHalo) ? 64 : ((lane >= 32 - kPlaneHalo) ? -64 : 0); // in f2
     // the cells of one anti-diagonal: out-sums (toM, toD, toI) of the slot pairs
     auto cells = [&](const int s, const int kk, const bool special, f2 (&tM)[P], f2 (&tD)[P], f2 (&nI)[P]) {
 #pragma unroll
@@ -1408,7 +1216,7 @@ __device__ __forceinline__ void lean_forward(const LeanSmem &sh, const LeanCoef 
             tM[p] = mul2(fma2(a.dm, D, fma2(a.im, I, mul2(a.mm, M))), st.msk[p]);
             tD[p] = mul2(fma2(a.dd, D, fma2(a.id, I, mul2(a.md, M))), st.msk[p]);
             nI[p] = mul2(fma2(a.di, D, fma2(a.ii, I, mul2(a.mi, M))), st.msk[p]);
-            if (MODE == 0 && special && s >= nd - 4) { // the end sums F(Lr, Lt - d), d = 0..3
+            if (DECIDE && special && s >= nd - 4) { // the end sums F(Lr, Lt - d), d = 0..3
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int j = (int)(st.tnext[2 * p + h] - lp.Tb) - 2 * NSLOT;
@@ -1425,28 +1233,48 @@ __device__ __forceinline__ void lean_forward(const LeanSmem &sh, const LeanCoef 
         for (int p = 0; p < P; p++) { tM[p] = mul2(tM[p], sc); tD[p] = mul2(tD[p], sc); nI[p] = mul2(nI[p], sc); st.inMa[p] = mul2(st.inMa[p], sc); }
     };
     auto finish = [&](const int kk, f2 (&tM)[P], f2 (&tD)[P], f2 (&nI)[P]) {
-        if (MODE == 1) { // plane c, entry lane = (toM, toD) of slot C*lane + c (the replicated plane ends are filled per segment)
+        auto cM = [&](int c) -> float { c = (c + C) % C; return (c & 1) ? hi2(tM[c / 2]) : lo2(tM[c / 2]); };
+        auto cD = [&](int c) -> float { c = (c + C) % C; return (c & 1) ? hi2(tD[c / 2]) : lo2(tD[c / 2]); };
+        if (MODE >= 1) { // pair plane p, entry lane = (toM, toD) of the slots lane + 64p and lane + 64p + 32
             f2 *w = wrow + kk * RS;
 #pragma unroll
-            for (int p = 0; p < P; p++) {
-                w[(2 * p) * kPlane] = mk2(lo2(tM[p]), lo2(tD[p]));
-                w[(2 * p + 1) * kPlane] = mk2(hi2(tM[p]), hi2(tD[p]));
+            for (int p = 0; p < P; p++) *reinterpret_cast<ulonglong2 *>(w + p * 2 * kPlane) = make_ulonglong2(tM[p], tD[p]);
+            // entry 32 + t holds the slots (32 + t + 64p, 64 + t + 64p) = cells (2p+1, 2p+2) of lane t; entry -1 - t the
+            // slots (64p - 1 - t, 64p + 31 - t) = cells (2p-1, 2p) of lane 31 - t
+            if (C == 2) {
+                if (halo != 0)
+                    *reinterpret_cast<ulonglong2 *>(w + halo) = make_ulonglong2(mk2(cM(1), cM(0)), mk2(cD(1), cD(0)));
+            } else {
+                if (lane < kPlaneHalo) {
+#pragma unroll
+                    for (int p = 0; p < P; p++)
+                        *reinterpret_cast<ulonglong2 *>(w + p * 2 * kPlane + 64) =
+                            make_ulonglong2(mk2(cM(2 * p + 1), cM(2 * p + 2)), mk2(cD(2 * p + 1), cD(2 * p + 2)));
+                }
+                if (lane >= 32 - kPlaneHalo) {
+#pragma unroll
+                    for (int p = 0; p < P; p++)
+                        *reinterpret_cast<ulonglong2 *>(w + p * 2 * kPlane - 64) =
+                            make_ulonglong2(mk2(cM(2 * p - 1), cM(2 * p)), mk2(cD(2 * p - 1), cD(2 * p)));
+                }
             }
         }
-        // hand (toM, toD) to the right-hand neighbour column (slot+1, wrapping): the new in-pair is (left neighbour, own lo)
-        const float rM = __shfl_sync(kFull, hi2(tM[P - 1]), (lane + 31) & 31);
-        const float rD = __shfl_sync(kFull, hi2(tD[P - 1]), (lane + 31) & 31);
+        // hand (toM, toD) to the right-hand neighbour column: slot sigma+1 = the same cell of lane+1; lane 0 receives from the
+        // PREVIOUS cell of lane 31 (slot 32c - 1, wrapping)
+        float rM[C], rD[C];
 #pragma unroll
-        for (int p = P - 1; p >= 1; p--) {
-            st.inMb[p] = st.inMa[p];
-            st.inMa[p] = mk2(hi2(tM[p - 1]), lo2(tM[p]));
-            st.inD[p] = mk2(hi2(tD[p - 1]), lo2(tD[p]));
+        for (int c = 0; c < C; c++) {
+            rM[c] = __shfl_sync(kFull, cM(c), (lane + 31) & 31);
+            rD[c] = __shfl_sync(kFull, cD(c), (lane + 31) & 31);
         }
-        st.inMb[0] = st.inMa[0];
-        st.inMa[0] = mk2(rM, lo2(tM[0]));
-        st.inD[0] = mk2(rD, lo2(tD[0]));
+        const bool seam = lane == 0;
 #pragma unroll
-        for (int p = 0; p < P; p++) st.toI[p] = nI[p];
+        for (int p = 0; p < P; p++) {
+            st.inMb[p] = st.inMa[p];
+            st.inMa[p] = mk2(seam ? rM[(2 * p - 1 + C) % C] : rM[2 * p], seam ? rM[2 * p] : rM[2 * p + 1]);
+            st.inD[p] = mk2(seam ? rD[(2 * p - 1 + C) % C] : rD[2 * p], seam ? rD[2 * p] : rD[2 * p + 1]);
+            st.toI[p] = nI[p];
+        }
     };
     // anti-diagonal s -> s+1: when the centre stays (guide bit 0, up = 1) every cell moves one row up inside the window.
     // Unconditional: a predicated version issues its dozen instructions whether or not the band moves.
@@ -1493,7 +1321,7 @@ __device__ __forceinline__ void lean_forward(const LeanSmem &sh, const LeanCoef 
                 f2 tM[P], tD[P], nI[P];
                 cells(s + kk, kk, false, tM, tD, nI);
                 if (kk == 3) {
-                    if (MODE == 0) {
+                    if (DECIDE) {
                         if (s + 3 < nd - 8) {
                             float v = fmaxf(lo2(tM[0]), hi2(tM[0]));
 #pragma unroll
@@ -1530,28 +1358,92 @@ __device__ __forceinline__ void lean_forward(const LeanSmem &sh, const LeanCoef 
         }
 #pragma unroll
         for (int c = 0; c < C; c++) st.rbp[c] += 4;
-        if (MODE == 1) wrow += 4 * RS;
-        if (MODE == 0 && lane == 0) kb[s >> 2] = K;
+        if (MODE >= 1) wrow += 4 * RS;
+        if (DECIDE && lane == 0) kb[s >> 2] = K;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 1 of the rows variant: the forward pass of every pair of the wave.  Writes the forward rows ((toM, toD) of every
+// cell, 608 B per anti-diagonal at C = 2), kb, the four end sums and the likelihood.  HBM-write bound.
+// ------------------------------------------------------------------------------------------------
+constexpr int fwd_ctas_per_sm(int C) { return C == 2 ? 6 : (C == 4 ? 3 : 2); }
+template <int C>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, fwd_ctas_per_sm(C)) fwdrows_kernel(KParams p) {
+    __shared__ FwdTabSmem sh;
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    fill_fwd_part(sh, p.models);
+    __syncthreads();
+    constexpr int NSLOT = 32 * C, RS = C * kPlane, PADR = NSLOT + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *rb_s = dyn_smem + (size_t)warp * p.smem_rb; // rb_s[i + PADR] = code byte of read row i
+    volatile float *s_ftot = sh.ftot[warp];
+    for (;;) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(p.counter, 1);
+        k = __shfl_sync(kFull, k, 0);
+        if (p.pair_lo + k >= p.pair_hi) break;
+        const int pi = pair_index(p, k);
+        const DevPair P = p.pairs[pi];
+        const int Lt = P.Lt, Lr = P.Lr, nd = Lt + Lr + 1;
+        float2 *frow = p.frows + (size_t)k * p.frow_stride + kRowShift * RS; // row 0 (kRowShift zero rows below)
+        const KbRef kb = { p.kf, (int)((size_t)k * p.kf_stride) + 4 };      // kb[q], q >= -4
+        unsigned *info = p.fwdinfo + (size_t)k * p.fwdinfo_stride;
+        {   // stage the read codes of this pair; rows -kRowShift..-1 (before the first anti-diagonal) read as zero, exponent 0
+            const uint8_t *Rb = p.codes + P.rb_off;
+            const int nr = Lr + 2 * PADR;
+            for (int w = lane; w < nr; w += 32) rb_s[w] = Rb[w - PADR];
+            for (int w = lane; w < kRowShift * RS; w += 32) frow[w - kRowShift * RS] = make_float2(0.f, 0.f);
+            if (lane < 4) { kb[lane - 4] = 0; s_ftot[lane] = 0.f; }
+        }
+        __syncwarp();
+        LeanPair lp;
+        lp.Tb = p.codes + P.tb_off; lp.bw = p.bits + P.bits_off; lp.rb0 = rb_s + PADR;
+        lp.Lt = Lt; lp.Lr = Lr; lp.nd = nd; lp.r = p.radius;
+        lp.sEM = (unsigned)__cvta_generic_to_shared(&sh.em[P.model][0]);
+        lp.sEI = (unsigned)__cvta_generic_to_shared(&sh.ei[P.model][0]);
+        int K = 0;
+        {
+            LeanFwd<C> st;
+#pragma unroll
+            for (int q = 0; q < C / 2; q++) st.inMb[q] = st.inMa[q] = st.inD[q] = st.toI[q] = 0ull;
+            int ups = 0;
+            lean_seed<C>(st, lp, 0, 0);
+            const LeanCoef la = load_lean_coef(sh.cdup[P.model]);
+            unsigned ev_unused = 0u;
+            lean_forward<C, 2>(la, st, lp, 0, nd, K, ups, kb, nullptr, reinterpret_cast<f2 *>(frow) + 2 * (kPlaneHalo + lane), s_ftot, ev_unused);
+        }
+        // rows just past the last anti-diagonal read as zero; the exponent stays at K
+        for (int w = lane; w < kRowsAbove * RS; w += 32) frow[(size_t)nd * RS + w] = make_float2(0.f, 0.f);
+        for (int q = ((nd + 3) >> 2) + lane; q <= ((nd + 3) >> 2) + 2; q += 32) kb[q] = K;
+        __syncwarp();
+        const float fin = s_ftot[0];
+        if (lane < 4) info[lane] = __float_as_uint(s_ftot[lane]);
+        if (lane == 4) info[4] = (unsigned)K;
+        if (lane == 0)
+            p.out_lk[pi] = fin > 0.f ? log((double)fin) - (double)K * 0.6931471805599453 : -INFINITY;
+        __syncwarp();
     }
 }
 
 template <int C, int ROWS>
-__device__ __forceinline__ void backward_fused(const PairCtx &pc, const Coef &a, const LeanSmem &fsh, const int model, const LeanPair &lp,
+__device__ __forceinline__ void backward_fused(const PairCtx &pc, const BCoef &a, const LeanSmem &fsh, const int model, const LeanPair &lp,
                                                const KbRef kb, const KParams &p, const unsigned wslot, const unsigned rawk,
                                                unsigned char *wsm, unsigned &phase) {
     // per-warp shared memory: [row buffer][checkpoint landing zone | mbarrier | end sums][staged read codes]
     f2 *buf = reinterpret_cast<f2 *>(wsm);
+    const ulonglong2 *buf_q = reinterpret_cast<const ulonglong2 *>(wsm);
     unsigned char *ckstage = wsm + seg_buf_rows<C>() * (C * kPlane) * 8;
     const unsigned bar = (unsigned)__cvta_generic_to_shared(ckstage + ckpt_bytes<C>());
     volatile float *s_ftot = reinterpret_cast<volatile float *>(ckstage + ckpt_bytes<C>() + 16);
     float4 *raw_base = p.raw;
     unsigned ev = 0u; // rescale events of the forward blocks in the buffer (set by the recomputation)
-    constexpr int NSLOT = 32 * C;
-    constexpr int RS = C * kPlane;
+    constexpr int P = C / 2;
+    constexpr int RS = C * kPlane, RQ = P * kPlane;
     constexpr int SEG = seg_rows<C>(), CKB = ckpt_bytes<C>();
     constexpr int QSEG = SEG / 4; // backward blocks per segment
     const int lane = threadIdx.x & 31;
-    const int Lt = pc.Lt, nd = pc.nd, W = 2 * pc.r;
+    const int nd = pc.nd, W = 2 * pc.r;
     // B(Lr, Lt) = boff puts sum_cells F*B = fin * boff at about 2^kProductExp (read where it is used: the first step only)
     auto boff_of = [&]() -> float {
         const float fin_raw = s_ftot[0];
@@ -1588,28 +1480,19 @@ __device__ __forceinline__ void backward_fused(const PairCtx &pc, const Coef &a,
                 phase ^= 1u;
                 const float4 *ck = reinterpret_cast<const float4 *>(ckstage);
 #pragma unroll
-                for (int p = 0; p < C / 2; p++) {
-                    const float4 v = ck[(2 * p) * 32 + lane], u = ck[(2 * p + 1) * 32 + lane];
-                    st.inMb[p] = mk2(v.x, v.y); st.inMa[p] = mk2(v.z, v.w); st.inD[p] = mk2(u.x, u.y); st.toI[p] = mk2(u.z, u.w);
+                for (int q = 0; q < P; q++) {
+                    const float4 v = ck[(2 * q) * 32 + lane], u = ck[(2 * q + 1) * 32 + lane];
+                    st.inMb[q] = mk2(v.x, v.y); st.inMa[q] = mk2(v.z, v.w); st.inD[q] = mk2(u.x, u.y); st.toI[q] = mk2(u.z, u.w);
                 }
                 ups = reinterpret_cast<const int *>(ckstage + C * 512)[0];
                 K = kb[(s0 >> 2) - 1];
             } else {
 #pragma unroll
-                for (int p = 0; p < C / 2; p++) st.inMb[p] = st.inMa[p] = st.inD[p] = st.toI[p] = 0ull;
+                for (int q = 0; q < P; q++) st.inMb[q] = st.inMa[q] = st.inD[q] = st.toI[q] = 0ull;
             }
-            lean_seed<C>(fsh, st, lp, s_from, ups);
+            lean_seed<C>(st, lp, s_from, ups);
             const LeanCoef la = load_lean_coef(fsh.cdup[model]); // live during the recomputation only
-            lean_forward<C, 1>(fsh, la, st, lp, s_from, s_to, K, ups, kb, nullptr, buf + (size_t)(s_from - s0) * RS + kPlaneHalo + lane, s_ftot, ev);
-            __syncwarp();
-            // the first / last two entries of every plane are replicated past its other end
-            for (int w = lane; w < (s_to - s_from) * C * 2 * kPlaneHalo; w += 32) {
-                const int row = w / (C * 2 * kPlaneHalo), rem = w % (C * 2 * kPlaneHalo), c = rem / (2 * kPlaneHalo), t = rem % (2 * kPlaneHalo);
-                f2 *pl = buf + (size_t)(s_from - s0 + row) * RS + c * kPlane;
-                // t < halo: entry t -> 32 + t; else entry 32 - halo + (t - halo) -> that index - 32
-                if (t < kPlaneHalo) pl[kPlaneHalo + 32 + t] = pl[kPlaneHalo + t];
-                else pl[t - kPlaneHalo] = pl[32 + t - kPlaneHalo];
-            }
+            lean_forward<C, 1>(la, st, lp, s_from, s_to, K, ups, kb, nullptr, buf + (size_t)(s_from - s0) * RS + 2 * (kPlaneHalo + lane), s_ftot, ev);
         } else {
             s_from = s_to = s0; // nothing to compute: every row of the segment reads as zero
         }
@@ -1624,85 +1507,28 @@ __device__ __forceinline__ void backward_fused(const PairCtx &pc, const Coef &a,
     };
 
     BwdState<C> st;
-#pragma unroll
-    for (int c = 0; c < C; c++) {
-        const int sigma = lane * C + c;
-        const int d = (Lt - sigma) & (NSLOT - 1);
-        st.j[c] = Lt - d;
-        st.x[c] = d + pc.r;
-        st.tcB[c] = pc.sEM + ((unsigned)pc.Tb[st.j[c] + 1] << 5);
-        st.tcn[c] = pc.Tb[st.j[c] + 1 - NSLOT];
-        st.win[c] = 0u;
-        st.rbp[c] = lp.rb0 + (nd - st.j[c]); // row s - j + 1 at s = nd - 1
-        st.BI[c] = st.BMo[c] = st.inD[c] = st.inMa[c] = st.inMb[c] = 0.f;
-        st.Vs[c] = st.Vn[c] = 0.f;
-        st.S01[c] = st.S23[c] = st.N01[c] = st.N23[c] = 0ull;
-#pragma unroll
-        for (int e = 0; e < 3; e++) { st.Xp[c][e] = 0ull; st.Xm[c][e] = 0ull; }
-    }
-    auto flush_col = [&](int c) {
-        float4 *raw = raw_base + (size_t)(rawk + (unsigned)st.j[c] * 4u); // 32-bit offset: no 64-bit pointer lives across the steps
-        f2 *sg = reinterpret_cast<f2 *>(raw);
-        asm volatile("st.global.cg.b64 [%0], %1;" ::"l"(sg + 0), "l"(st.S01[c]) : "memory");
-        asm volatile("st.global.cg.b64 [%0], %1;" ::"l"(sg + 1), "l"(st.S23[c]) : "memory");
-        asm volatile("st.global.cg.b64 [%0], %1;" ::"l"(sg + 2), "l"(st.N01[c]) : "memory");
-        asm volatile("st.global.cg.b64 [%0], %1;" ::"l"(sg + 3), "l"(st.N23[c]) : "memory");
-        __stcg(raw + 2, make_float4(st.Vs[c], st.Vn[c], lo2(st.Xp[c][0]) + hi2(st.Xp[c][0]),
-                                                          lo2(st.Xp[c][1]) + hi2(st.Xp[c][1])));
-        __stcg(raw + 3, make_float4(lo2(st.Xp[c][2]) + hi2(st.Xp[c][2]), lo2(st.Xm[c][0]) + hi2(st.Xm[c][0]),
-                                                          lo2(st.Xm[c][1]) + hi2(st.Xm[c][1]), lo2(st.Xm[c][2]) + hi2(st.Xm[c][2])));
-    };
-    auto hand_off = [&](f2 (&bMD)[C]) {
-        const float rM = __shfl_sync(kFull, lo2(bMD[0]), (lane + 1) & 31);
-        const float rD = __shfl_sync(kFull, hi2(bMD[0]), (lane + 1) & 31);
-#pragma unroll
-        for (int c = 0; c < C - 1; c++) { st.inMb[c] = st.inMa[c]; st.inMa[c] = lo2(bMD[c + 1]); st.inD[c] = hi2(bMD[c + 1]); }
-        st.inMb[C - 1] = st.inMa[C - 1]; st.inMa[C - 1] = rM; st.inD[C - 1] = rD;
-    };
-    auto retire = [&]() {
-#pragma unroll
-        for (int c = 0; c < C; c++) {
-            if (st.x[c] < 0) {
-                if (st.j[c] >= 0) flush_col(c);
-                st.j[c] -= NSLOT;
-                st.x[c] += NSLOT;
-                st.rbp[c] += NSLOT;
-                st.tcB[c] = pc.sEM + (st.tcn[c] << 5);
-                st.tcn[c] = pc.Tb[st.j[c] + 1 - NSLOT];
-                clear2(st.S01[c]); clear2(st.S23[c]); clear2(st.N01[c]); clear2(st.N23[c]);
-                clear1(st.Vs[c]); clear1(st.Vn[c]);
-#pragma unroll
-                for (int e = 0; e < 3; e++) {
-                    if (ROWS == 14) clear2(st.Xp[c][e]); else st.Xp[c][e] = 0ull;
-                    if (ROWS == 14 || e == 0) clear2(st.Xm[c][e]); else st.Xm[c][e] = 0ull;
-                }
-            }
-        }
-    };
+    bwd_init<C>(st, pc, lp.rb0);
+    // 32-bit offset: no 64-bit pointer lives across the steps
+    auto raw_of = [&](int j) -> float4 * { return raw_base + (size_t)(rawk + (unsigned)j * 4u); };
     int k_have = 0; // segment in the buffer; buffer row 0 holds anti-diagonal SEG * k_have - kSegBelow
     auto slow_step = [&](int s) {
-        const f2 *rp = buf + (size_t)(s - (SEG * k_have - kSegBelow)) * RS + kPlaneHalo + lane;
+        const ulonglong2 *rq = buf_q + (size_t)(s - (SEG * k_have - kSegBelow)) * RQ + kPlaneHalo + lane;
         auto kfat = [&](int t) -> int { return kb[(t - 3) >> 2]; };
         const int kcur = kfat(s);
         const int kstep = kcur - kfat(s - 1);
         float ce[7];
 #pragma unroll
         for (int e = -3; e <= 3; e++) ce[e + 3] = pow2i(max(-126, min(126, kcur - kfat(s + e))));
-        f2 bMD[C];
-        if (s == nd - 1) bwd_step<C, ROWS, true, true, true>(pc, a, st, rp, W, ce, boff_of(), bMD);
-        else bwd_step<C, ROWS, true, false, true>(pc, a, st, rp, W, ce, 0.f, bMD);
+        f2 bM[P], bD[P];
+        if (s == nd - 1) bwd_step<C, ROWS, true, true>(pc, a, st, rq, ce, boff_of(), bM, bD, 0);
+        else bwd_step<C, ROWS, true, false>(pc, a, st, rq, ce, 0.f, bM, bD, 0);
 #pragma unroll
         for (int c = 0; c < C; c++) st.rbp[c] -= 1;
-        hand_off(bMD);
+        bwd_hand_off<C>(st, bM, bD);
         if (s > 0) {
-            if (kstep != 0) {
-                const float sc = pow2i(kstep);
-#pragma unroll
-                for (int c = 0; c < C; c++) { st.BI[c] *= sc; st.BMo[c] *= sc; st.inD[c] *= sc; st.inMa[c] *= sc; st.inMb[c] *= sc; }
-            }
+            if (kstep != 0) bwd_scale<C>(st, pow2i(kstep));
             const int dec = (int)(((pc.bw[(s - 1) >> 5] >> ((s - 1) & 31)) & 1u) ^ 1u);
-#pragma unroll
-            for (int c = 0; c < C; c++) st.x[c] -= dec;
+            bwd_band_down<C>(st, dec, W);
         }
     };
 
@@ -1731,51 +1557,43 @@ __device__ __forceinline__ void backward_fused(const PairCtx &pc, const Coef &a,
         }
         const int mode = preamble(q);
         if (mode == 1) {
-            const f2 *rp = buf + (size_t)(4 * q - 1 - (SEG * k_have - kSegBelow)) * RS + kPlaneHalo + lane;
+            const ulonglong2 *rq = buf_q + (size_t)(4 * q - 1 - (SEG * k_have - kSegBelow)) * RQ + kPlaneHalo + lane;
             const unsigned nib = nib_cur;
 #pragma unroll kBwdUnroll
             for (int k = 0; k < 4; k++) {
-                f2 bMD[C];
-                bwd_step<C, ROWS, false, false, true>(pc, a, st, rp - k * RS, W, nullptr, 0.f, bMD, k);
-                hand_off(bMD);
-                const int dec = (int)(((nib >> (3 - k)) & 1u) ^ 1u);
-#pragma unroll
-                for (int c = 0; c < C; c++) st.x[c] -= dec;
+                f2 bM[P], bD[P];
+                bwd_step<C, ROWS, false, false>(pc, a, st, rq - k * RQ, nullptr, 0.f, bM, bD, k);
+                bwd_hand_off<C>(st, bM, bD);
+                bwd_band_down<C>(st, (int)(((nib >> (3 - k)) & 1u) ^ 1u), W);
             }
 #pragma unroll
             for (int c = 0; c < C; c++) st.rbp[c] -= 4;
         } else if (mode == 2) { // a rescale within reach: the same block with the exact corrections of its cut products
-            const f2 *rp = buf + (size_t)(4 * q - 1 - (SEG * k_have - kSegBelow)) * RS + kPlaneHalo + lane;
+            const ulonglong2 *rq = buf_q + (size_t)(4 * q - 1 - (SEG * k_have - kSegBelow)) * RQ + kPlaneHalo + lane;
             const unsigned nib = nib_cur;
             const int k1 = kb[q - 1], k2 = kb[q - 2], k3 = kb[q - 3];
             const float fA = pow2c(k2 - k3), fB = pow2c(k1 - k2), fBi = pow2c(k2 - k1);
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                f2 bMD[C];
+                f2 bM[P], bD[P];
                 float ce[7];
                 block_corrections(k, fA, fB, fBi, ce);
-                bwd_step<C, ROWS, true, false, true>(pc, a, st, rp - k * RS, W, ce, 0.f, bMD, k);
-                hand_off(bMD);
-                if (k == 0 && k1 != k2) { // mirror of the forward rescale on row 4q-1
-                    const float sc = pow2i(k1 - k2);
-#pragma unroll
-                    for (int c = 0; c < C; c++) { st.BI[c] *= sc; st.BMo[c] *= sc; st.inD[c] *= sc; st.inMa[c] *= sc; st.inMb[c] *= sc; }
-                }
-                const int dec = (int)(((nib >> (3 - k)) & 1u) ^ 1u);
-#pragma unroll
-                for (int c = 0; c < C; c++) st.x[c] -= dec;
+                bwd_step<C, ROWS, true, false>(pc, a, st, rq - k * RQ, ce, 0.f, bM, bD, k);
+                bwd_hand_off<C>(st, bM, bD);
+                if (k == 0 && k1 != k2) bwd_scale<C>(st, pow2i(k1 - k2)); // mirror of the forward rescale on row 4q-1
+                bwd_band_down<C>(st, (int)(((nib >> (3 - k)) & 1u) ^ 1u), W);
             }
 #pragma unroll
             for (int c = 0; c < C; c++) st.rbp[c] -= 4;
         } else {
             for (int s = min(4 * q - 1, nd - 1); s >= 4 * q - 4; --s) slow_step(s);
         }
-        retire();
+        bwd_retire<C, ROWS>(st, pc, raw_of);
         --q;
     }
 #pragma unroll
     for (int c = 0; c < C; c++)
-        if (st.j[c] >= 0) flush_col(c);
+        if (st.j[c] >= 0) bwd_flush_col<C>(st, c, raw_of(st.j[c]));
 }
 
 template <int C, int ROWS>
@@ -1783,14 +1601,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, fused_ctas_per_sm(C)) modta
     __shared__ LeanSmem fsh;
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     fill_lean_tables(fsh, p.models);
-    LeanSmem &bsh = fsh;
     constexpr int NSLOT = 32 * C, RS = C * kPlane, PADR = NSLOT + 16;
     constexpr int BUFB = seg_buf_rows<C>() * RS * 8, CKS = ckpt_stage_bytes<C>();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *wsm = dyn_smem + (size_t)warp * (BUFB + CKS + p.smem_rb);
-    f2 *buf = reinterpret_cast<f2 *>(wsm);
     unsigned char *ckstage = wsm + BUFB;
-    unsigned char *rb_s = wsm + BUFB + CKS; // rb_s[i + PADR] = 4*idx of read row i
+    unsigned char *rb_s = wsm + BUFB + CKS; // rb_s[i + PADR] = code byte of read row i
     const unsigned bar = (unsigned)__cvta_generic_to_shared(ckstage + ckpt_bytes<C>());
     unsigned phase = 0u;
     if (lane == 0) mbar_init(bar, 1u);
@@ -1808,9 +1624,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, fused_ctas_per_sm(C)) modta
         const int pi = pair_index(p, k);
         const DevPair P = p.pairs[pi];
         const int Lt = P.Lt, Lr = P.Lr, nd = Lt + Lr + 1;
-        const Coef a = load_coef(bsh.trans[P.model], bsh.cpair[P.model]);
+        const BCoef a = load_bcoef(fsh.trans[P.model]);
         unsigned *info = p.fwdinfo + (size_t)k * p.fwdinfo_stride;
-        {   // stage the read codes of this pair as compact table offsets
+        {   // stage the read codes of this pair
             const uint8_t *Rb = p.codes + P.rb_off;
             const int nr = Lr + 2 * PADR;
             for (int w = lane; w < nr; w += 32) rb_s[w] = Rb[w - PADR];
@@ -1826,12 +1642,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, fused_ctas_per_sm(C)) modta
         {   // ---- pass 1 ----
             LeanFwd<C> st;
 #pragma unroll
-            for (int p = 0; p < C / 2; p++) st.inMb[p] = st.inMa[p] = st.inD[p] = st.toI[p] = 0ull;
+            for (int q = 0; q < C / 2; q++) st.inMb[q] = st.inMa[q] = st.inD[q] = st.toI[q] = 0ull;
             int ups = 0;
-            lean_seed<C>(fsh, st, lp, 0, 0);
+            lean_seed<C>(st, lp, 0, 0);
             const LeanCoef la = load_lean_coef(fsh.cdup[P.model]);
             unsigned ev_unused = 0u;
-            lean_forward<C, 0>(fsh, la, st, lp, 0, nd, K, ups, kb, ckpt_g, nullptr, s_ftot, ev_unused);
+            lean_forward<C, 0>(la, st, lp, 0, nd, K, ups, kb, ckpt_g, nullptr, s_ftot, ev_unused);
             for (int q = ((nd + 3) >> 2) + lane; q <= ((nd + 3) >> 2) + 2; q += 32) kb[q] = K; // blocks past the last row
         }
         __syncwarp();
@@ -1843,7 +1659,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, fused_ctas_per_sm(C)) modta
         asm volatile("fence.proxy.async.global;" ::: "memory");
         __syncwarp();
         // ---- pass 2 ----
-        const PairCtx pc = make_pair_ctx(p, P, bsh);
+        const PairCtx pc = make_pair_ctx_bwd(p, P, fsh);
         backward_fused<C, ROWS>(pc, a, fsh, P.model, lp, kb, p, (unsigned)wslot, (unsigned)k * (unsigned)p.raw_stride, wsm, phase);
         __syncwarp();
     }
@@ -1857,24 +1673,20 @@ int cols_per_lane_for_radius(int radius) {
     return 0;
 }
 
+// dynamic shared memory of one CTA of the backward kernel: per warp the ring of forward rows and the staged read codes
+template <int C, int ROWS> static int bwd_dyn_c(int smem_rb) { return bwd_warps_per_cta(C) * (ring_floats2<C, ROWS>() * (int)sizeof(f2) + smem_rb); }
 template <int C, int ROWS>
 static cudaError_t launch_modtable_cr(const KParams &p, int grid_fwd, int grid_bwd, cudaStream_t st) {
-    const int dyn_ring = kWarpsPerCta * ring_floats2<C>() * (int)sizeof(f2);
-    // the read codes of a pair are staged next to the ring when they fit (they do up to ~10 kbp reads at radius <= 30)
-    const bool staged = dyn_ring + kWarpsPerCta * p.smem_rb <= 227 * 1024 - 2048 &&
-                        bwd_ctas_per_sm(C, ROWS) * (dyn_ring + kWarpsPerCta * p.smem_rb + 3072) <= 228 * 1024;
-    const int dyn = dyn_ring + (staged ? kWarpsPerCta * p.smem_rb : 0);
-    cudaError_t e = staged ? cudaFuncSetAttribute(bwdtable_kernel<C, ROWS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)
-                           : cudaFuncSetAttribute(bwdtable_kernel<C, ROWS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    const int dyn = bwd_dyn_c<C, ROWS>(p.smem_rb);
+    cudaError_t e = cudaFuncSetAttribute(bwdtable_kernel<C, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     if (e != cudaSuccess) return e;
-    const int dyn_f = kWarpsPerCta * (p.smem_rb + p.smem_tb);
+    const int dyn_f = kWarpsPerCta * p.smem_rb;
     e = cudaFuncSetAttribute(fwdrows_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_f);
     if (e != cudaSuccess) return e;
     fwdrows_kernel<C><<<grid_fwd, kWarpsPerCta * 32, dyn_f, st>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    if (staged) bwdtable_kernel<C, ROWS, true><<<grid_bwd, kWarpsPerCta * 32, dyn, st>>>(p);
-    else bwdtable_kernel<C, ROWS, false><<<grid_bwd, kWarpsPerCta * 32, dyn, st>>>(p);
+    bwdtable_kernel<C, ROWS><<<grid_bwd, bwd_warps_per_cta(C) * 32, dyn, st>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     finalize_kernel<<<dim3((unsigned)((p.max_lt + kFinCols) / kFinCols), (unsigned)(p.pair_hi - p.pair_lo)), kFinCols, 0, st>>>(p);
@@ -1977,6 +1789,9 @@ int warps_per_cta() { return kWarpsPerCta; }
 int frow_slots_per_row(int C) { return C * kPlane; }
 int frow_extra_rows() { return kRowShift + kRowsAbove; }
 int modtable_ctas_per_sm(int C, int rows) { return bwd_ctas_per_sm(C, rows); }
+int modtable_warps_per_cta(int C) { return bwd_warps_per_cta(C); }
+// dynamic shared memory of one CTA of the backward kernel of the rows variant
+int modtable_dyn_smem(int C, int smem_rb) { return C == 2 ? bwd_dyn_c<2, 14>(smem_rb) : (C == 4 ? bwd_dyn_c<4, 14>(smem_rb) : bwd_dyn_c<8, 14>(smem_rb)); }
 int fwdrows_ctas_per_sm(int C) { return fwd_ctas_per_sm(C); }
 int fwdinfo_words() { return 16; }
 int fwd_pad_rows(int C) { return 32 * C + 16; }
