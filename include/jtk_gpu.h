@@ -311,6 +311,14 @@ int jtk_lc_nonmatch_columns_batch(int n, const uint8_t *ops_concat, const uint64
                                   const uint64_t *read_off, const uint8_t *tmpl_concat, const uint64_t *tmpl_off,
                                   const uint32_t *tmpl_idx, int32_t *out);
 
+/* K6 (kiley::gen_seq `Generate::gen`, call sites haplotyper/src/likelihood_gains.rs:20-21,276-279): one read
+ * per source sequence sampled from the pair HMM `hmm45` (HMMParam order) on the host threads; kiley is absent, so this is our
+ * own sampler of the same model, not kiley's generator stream.  Read k is drawn from source s = src_idx[k] =
+ * src_concat[src_off[s] .. src_off[s+1]) with its own Xoshiro256** stream seeded with seed + k; it goes to out[k * cap ..]
+ * (at most cap bases), its length to out_len[k]. */
+int jtk_lc_gen_reads(const double *hmm45, int n, const uint8_t *src_concat, const uint64_t *src_off, const uint32_t *src_idx,
+                     uint64_t seed, int cap, uint8_t *out, uint32_t *out_len);
+
 /* The k-means + MCMC restarts of pseudo_mcmc::mcmc_clustering (haplotyper/src/local_clustering/pseudo_mcmc.rs:649-670:
  * `restarts` = 20 x (misc::kmeans + mcmc_with_filter) on one generator, keeping the last maximum) for n_chains independent
  * problems at once, one warp per chain.  Chain c: variants data_concat[data_off[c] ..] as n_rows[c] x

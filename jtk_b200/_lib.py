@@ -119,7 +119,9 @@ def _u8(a) -> np.ndarray:
 
 
 def concat(seqs):
-    """list of uint8 arrays -> (concat uint8, offsets uint32[n+1])."""
+    """list of uint8 arrays -> (concat uint8, offsets uint32[n+1]); a (concat, offsets) tuple passes through."""
+    if isinstance(seqs, tuple) and len(seqs) == 2 and isinstance(seqs[0], np.ndarray) and seqs[0].dtype == np.uint8:
+        return np.ascontiguousarray(seqs[0]), np.ascontiguousarray(seqs[1], dtype=np.uint32)
     lens = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=len(seqs))
     off = np.zeros(len(seqs) + 1, dtype=np.int64)
     np.cumsum(lens, out=off[1:])
@@ -215,10 +217,11 @@ class Context:
         return lk, tables
 
     def likelihood_batch(self, fwd: HmmParams, rev: HmmParams, templates, reads, ops, strands, tmpl_idx, radius):
-        """jtk_hmm_likelihood_batch; ops=None selects the bootstrap guide."""
-        n = len(reads)
+        """jtk_hmm_likelihood_batch; ops=None selects the bootstrap guide.  templates / reads / ops: lists of uint8 arrays or
+        (concatenated uint8, uint32 offsets[n+1]) tuples (large calibration batches arrive flat)."""
         tcat, toff = concat(templates)
         rcat, roff = concat(reads)
+        n = len(roff) - 1
         ocat = ooff = None
         if ops is not None:
             ocat, ooff = concat(ops)
@@ -226,7 +229,7 @@ class Context:
         tmpl_idx = np.ascontiguousarray(tmpl_idx, dtype=np.uint32)
         lk = np.empty(n, dtype=np.float64)
         self._check(lib().jtk_hmm_likelihood_batch(
-            self._h, C.byref(fwd), C.byref(rev), n, len(templates), _ptr(tcat), _ptr(toff), _ptr(rcat), _ptr(roff),
+            self._h, C.byref(fwd), C.byref(rev), n, len(toff) - 1, _ptr(tcat), _ptr(toff), _ptr(rcat), _ptr(roff),
             _ptr(ocat), _ptr(ooff), _ptr(strands), _ptr(tmpl_idx), radius, _ptr(lk)))
         return lk
 
@@ -377,3 +380,22 @@ def pack_inputs(templates, reads, ops, strands, tmpl_idx):
 def band_cell_count(ops, Lt: int, Lr: int, radius: int) -> int:
     ops = _u8(ops)
     return int(lib().jtk_band_cell_count(_ptr(ops), len(ops), Lt, Lr, radius))
+
+
+def gen_reads(hmm45: np.ndarray, sources, src_idx, seed: int, cap: int):
+    """jtk_lc_gen_reads: read k sampled from the pair HMM `hmm45` (45 doubles, HMMParam order) along sources[src_idx[k]], own
+    generator stream seed + k, on the host threads.  Returns (uint8[n, cap], uint32[n] lengths)."""
+    L = lib()
+    vp = C.c_void_p
+    L.jtk_lc_gen_reads.argtypes = [vp, C.c_int, vp, vp, vp, C.c_uint64, C.c_int, vp, vp]
+    scat, soff = concat(sources)
+    soff = soff.astype(np.uint64)
+    src_idx = np.ascontiguousarray(src_idx, dtype=np.uint32)
+    h = np.ascontiguousarray(hmm45, dtype=np.float64)
+    n = len(src_idx)
+    out = np.empty((n, cap), dtype=np.uint8)
+    lens = np.zeros(n, dtype=np.uint32)
+    rc = L.jtk_lc_gen_reads(_ptr(h), n, _ptr(scat), _ptr(soff), _ptr(src_idx), seed, cap, _ptr(out), _ptr(lens))
+    if rc != 0:
+        raise JtkError(rc, "jtk_lc_gen_reads")
+    return out, lens

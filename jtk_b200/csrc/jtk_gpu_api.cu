@@ -37,6 +37,9 @@ int frow_slots_per_row(int C);
 int frow_extra_rows();
 int modtable_ctas_per_sm(int C, int rows);
 int modtable_warps_per_cta(int C);
+int likelihood_pairs2_max_radius();
+int likelihood_pairs2_pad_rows();
+cudaError_t launch_likelihood_pairs2(const KParams &p, int grid, cudaStream_t st);
 int modtable_dyn_smem(int C, int smem_rb);
 cudaError_t launch_fit(const KParams &p, int C, int grid, double *acc90, cudaStream_t st);
 cudaError_t launch_fp32_peak(int mode, int blocks, int threads, int iters, float *sink, cudaStream_t st);
@@ -1212,7 +1215,16 @@ int batch_run(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev
             ctx->launches += 3;
         } else {
             kp.n_pairs = b->n_pairs;
-            CU(launch_likelihood(kp, b->C, std::min(ctas, ctx->sm_count * 4), st), "kernel launch");
+            // at a small radius two pairs share a warp (calibration batches: 1e5..1e6 pairs of ~100 bp)
+            kp.smem_rb = ((b->max_lr + 2 * likelihood_pairs2_pad_rows()) + 15) & ~15;
+            const bool packed = b->radius <= likelihood_pairs2_max_radius() && (size_t)wpc * 2 * kp.smem_rb <= (size_t)200 * 1024 &&
+                                !std::getenv("JTK_LIKELIHOOD_UNPACKED");
+            if (packed) {
+                const int ctas2 = ((hi - lo + 1) / 2 + wpc - 1) / wpc;
+                CU(launch_likelihood_pairs2(kp, std::min(ctas2, ctx->sm_count * 8), st), "kernel launch");
+            } else {
+                CU(launch_likelihood(kp, b->C, std::min(ctas, ctx->sm_count * 4), st), "kernel launch");
+            }
             ctx->launches++;
         }
     }

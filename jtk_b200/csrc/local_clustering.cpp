@@ -1245,6 +1245,59 @@ int jtk_lc_nonmatch_columns_batch(int n, const uint8_t *ops_concat, const uint64
     return JTK_OK;
 }
 
+// SURVEY 8a K6 (kiley::gen_seq `Generate::gen`; kiley is absent, so the order in which it consumes the generator is unknown:
+// this is OUR sampler of the same model, jtk_b200/likelihood_gains.py::gen_reads on host threads).  One read per source
+// sequence: start in Match, transitions row-normalised; Match emits by mat_emit[template base], Ins by ins_emit[previous
+// read base] (4 = none), Del emits nothing; the read ends when the template is consumed.  Read k is drawn from source
+// src_idx[k] and has its own generator
+// (Xoshiro256** seeded with seed + k), so the result does not depend on the thread count.
+int jtk_lc_gen_reads(const double *hmm45, int n, const uint8_t *src_concat, const uint64_t *src_off, const uint32_t *src_idx,
+                     uint64_t seed, int cap, uint8_t *out, uint32_t *out_len) {
+    if (!hmm45 || n < 0 || cap <= 0 || (n > 0 && (!src_concat || !src_off || !src_idx || !out || !out_len))) return JTK_EINVAL;
+    double tc[3][3], mc[4][4], ic[5][4];
+    auto cum = [](const double *row, int m, double *dst) {
+        double tot = 0; for (int k = 0; k < m; k++) tot += row[k];
+        double acc = 0; for (int k = 0; k < m; k++) { acc += row[k] / tot; dst[k] = acc; }
+    };
+    for (int r = 0; r < 3; r++) cum(hmm45 + 3 * r, 3, tc[r]);
+    for (int r = 0; r < 4; r++) cum(hmm45 + 9 + 4 * r, 4, mc[r]);
+    for (int r = 0; r < 5; r++) cum(hmm45 + 25 + 4 * r, 4, ic[r]);
+    static const uint8_t kAcgt[4] = { 'A', 'C', 'G', 'T' };
+    auto code = [](uint8_t b) -> int { switch (b | 0x20) { case 'a': return 0; case 'c': return 1; case 'g': return 2; default: return 3; } };
+    auto pick = [](const double *c, int m, double u) -> int { int k = 0; while (k < m - 1 && u > c[k]) k++; return k; };
+    auto range = [&](int lo, int hi) {
+        for (int k = lo; k < hi; k++) {
+            Rng rng(seed + (uint64_t)k);
+            auto unif = [&]() -> double { return (double)(rng.next_u64() >> 11) * (1.0 / 9007199254740992.0); };
+            const uint32_t si = src_idx[k];
+            const uint8_t *t = src_concat + src_off[si];
+            const size_t L = (size_t)(src_off[si + 1] - src_off[si]);
+            uint8_t *o = out + (size_t)k * (size_t)cap;
+            size_t j = 0; int state = 0, prev = 4; uint32_t len = 0;
+            while (j < L) {
+                const int nxt = pick(tc[state], 3, unif());
+                const double v = unif();
+                if (nxt == 0) { const int e = pick(mc[code(t[j])], 4, v); if (len < (uint32_t)cap) { o[len++] = kAcgt[e]; prev = e; } j++; }
+                else if (nxt == 1) { const int e = pick(ic[prev], 4, v); if (len < (uint32_t)cap) { o[len++] = kAcgt[e]; prev = e; } }
+                else j++;
+                state = nxt;
+            }
+            out_len[k] = len;
+        }
+    };
+    int nt = (int)std::thread::hardware_concurrency();
+    if (const char *env = std::getenv("JTK_CLUSTER_THREADS")) nt = std::atoi(env);
+    else if (const char *env2 = std::getenv("JTK_HOST_THREADS")) nt = std::atoi(env2);
+    nt = std::max(1, std::min(std::min(nt, 32), n / 256));
+    if (nt <= 1) { range(0, n); return JTK_OK; }
+    std::vector<std::thread> th;
+    const int per = (n + nt - 1) / nt;
+    for (int t = 1; t < nt; t++) th.emplace_back(range, std::min(n, t * per), std::min(n, (t + 1) * per));
+    range(0, std::min(n, per));
+    for (auto &x : th) x.join();
+    return JTK_OK;
+}
+
 int jtk_lc_homopolymer_length(const uint8_t *xs, int n, uint32_t *out) {
     const std::vector<size_t> h = homopolymer_length(xs, (size_t)n);
     for (int i = 0; i < n; i++) out[i] = (uint32_t)h[(size_t)i];

@@ -1426,6 +1426,150 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, fwd_ctas_per_sm(C)) fwdrows
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// likelihood of many SHORT pairs at a small radius (the calibrations of likelihood_gains.rs:6-39,253-315:
+// 1.8e5 / 1e6 pairs of ~100 bp at radius 10 / 12), TWO pairs per warp.  At radius <= 14 the slot ring needs 2r + 4 <= 32 slots,
+// so lane l owns slot l of pair A AND slot l of pair B: the lo half of every fp32 pair belongs to A, the hi half to B, every
+// arithmetic instruction is a packed one, the transition coefficients are (A's model, B's model) pairs, the hand-off to the
+// right-hand neighbour column is lane -> lane+1 for both (no seam).  Band bits, rescale decisions and end sums are per pair; a
+// pair that is shorter than its partner stops moving once its last anti-diagonal is done.  Same arithmetic per cell as
+// lean_forward (fwdrows_kernel); likelihood_kernel may rescale one block earlier, which moves ln(fin) - K ln 2 in its last bits.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPackRadiusMax = 14;
+__global__ void __launch_bounds__(kWarpsPerCta * 32) likelihood_pairs2_kernel(KParams p) {
+    __shared__ FwdTabSmem sh;
+    __shared__ float ftot2[kWarpsPerCta][8];
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    fill_fwd_part(sh, p.models);
+    __syncthreads();
+    constexpr int NSLOT = 32, PADR = NSLOT + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *rbs = dyn_smem + (size_t)warp * 2 * p.smem_rb;
+    volatile float *s_ftot = ftot2[warp];
+    const int W = 2 * p.radius, r = p.radius;
+    for (;;) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(p.counter, 1);
+        k = __shfl_sync(kFull, k, 0);
+        if (2 * k >= p.n_pairs) break;
+        const bool two = 2 * k + 1 < p.n_pairs;
+        int pi[2];
+        pi[0] = p.order ? (int)p.order[2 * k] : 2 * k;
+        pi[1] = two ? (p.order ? (int)p.order[2 * k + 1] : 2 * k + 1) : pi[0];
+        int nd[2], Lt[2], Lr[2], x[2], K[2] = { 0, 0 };
+        const unsigned char *rbp[2];
+        const uint8_t *Tb[2], *tnext[2];
+        const uint32_t *bw[2];
+        unsigned emrow[2], tcn[2], sEM[2], sEI[2];
+        LeanCoef a;
+        {
+            const DevPair PA = p.pairs[pi[0]], PB = p.pairs[pi[1]];
+            const DevPair *PP[2] = { &PA, &PB };
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const DevPair &P = *PP[h];
+                Lt[h] = P.Lt; Lr[h] = P.Lr; nd[h] = P.Lt + P.Lr + 1;
+                Tb[h] = p.codes + P.tb_off; bw[h] = p.bits + P.bits_off;
+                sEM[h] = (unsigned)__cvta_generic_to_shared(&sh.em[P.model][0]);
+                sEI[h] = (unsigned)__cvta_generic_to_shared(&sh.ei[P.model][0]);
+                const uint8_t *Rb = p.codes + P.rb_off;
+                unsigned char *dst = rbs + (size_t)h * p.smem_rb;
+                const int nr = P.Lr + 2 * PADR;
+                for (int w = lane; w < nr; w += 32) dst[w] = Rb[w - PADR];
+                // slot state of anti-diagonal 0 (lean_seed): slot sigma = lane holds column j = lane
+                x[h] = r - lane;
+                rbp[h] = dst + PADR - lane;
+                emrow[h] = sEM[h] + ((unsigned)Tb[h][lane] << 5);
+                tcn[h] = Tb[h][lane + NSLOT];
+                tnext[h] = Tb[h] + lane + 2 * NSLOT;
+            }
+            const float *tA = p.models + PA.model * kModelFloats, *tB = p.models + PB.model * kModelFloats;
+            a.mm = mk2(tA[0], tB[0]); a.mi = mk2(tA[1], tB[1]); a.md = mk2(tA[2], tB[2]);
+            a.im = mk2(tA[3], tB[3]); a.ii = mk2(tA[4], tB[4]); a.id = mk2(tA[5], tB[5]);
+            a.dm = mk2(tA[6], tB[6]); a.di = mk2(tA[7], tB[7]); a.dd = mk2(tA[8], tB[8]);
+        }
+        if (lane < 8) s_ftot[lane] = 0.f;
+        __syncwarp();
+        f2 toI = 0ull, inD = 0ull, inMa = 0ull, inMb = 0ull;
+        auto mask2 = [&]() -> f2 { return mk2((unsigned)x[0] <= (unsigned)W ? 1.f : 0.f, (unsigned)x[1] <= (unsigned)W ? 1.f : 0.f); };
+        f2 msk = mask2();
+        const int nd_max = max(nd[0], nd[1]);
+        for (int s0 = 0; s0 < nd_max; s0 += 4) {
+            unsigned nib[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) nib[h] = s0 < nd[h] ? bw[h][s0 >> 5] >> (s0 & 31) : 0xfu;
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                const int s = s0 + kk;
+                const unsigned w0 = rbp[0][kk], w1 = rbp[1][kk];
+                const f2 em = mk2(lds_f32(emrow[0] | (w0 & 0x1cu)), lds_f32(emrow[1] | (w1 & 0x1cu)));
+                const f2 ei = mk2(lds_f32(sEI[0] + w0), lds_f32(sEI[1] + w1));
+                f2 M = mul2(em, inMb);
+                const f2 I = mul2(ei, toI);
+                const f2 D = inD;
+                if (s == 0 && lane == 0) M = mk2(1.f, 1.f); // F_M(0, 0) = 1
+                f2 tM = mul2(fma2(a.dm, D, fma2(a.im, I, mul2(a.mm, M))), msk);
+                f2 tD = mul2(fma2(a.dd, D, fma2(a.id, I, mul2(a.md, M))), msk);
+                f2 nI = mul2(fma2(a.di, D, fma2(a.ii, I, mul2(a.mi, M))), msk);
+#pragma unroll
+                for (int h = 0; h < 2; h++) { // the end sums F(Lr, Lt - d), d = 0..3
+                    if (s >= nd[h] - 4 && s < nd[h]) {
+                        const int j = (int)(tnext[h] - Tb[h]) - 2 * NSLOT;
+                        if (half2f(msk, h) != 0.f && s - j == Lr[h] && j >= Lt[h] - 3 && (h == 0 || two))
+                            s_ftot[4 * h + Lt[h] - j] = half2f(M, h) + half2f(I, h) + half2f(D, h);
+                    }
+                }
+                if (kk == 3 && s0 >= 4) { // rescale decisions, one per pair (as lean_forward: never in the first block, never in the last eight rows)
+                    float sc[2] = { 1.f, 1.f };
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        if (s < nd[h] - 8) {
+                            const unsigned mx = __reduce_max_sync(kFull, __float_as_uint(half2f(tM, h)));
+                            const int e = (int)(mx >> 23) - 127;
+                            if (mx != 0u && e < kScaleLow) {
+                                const int kx = min(kScaleTarget - e, kScaleStep);
+                                sc[h] = pow2i(kx);
+                                K[h] += kx;
+                            }
+                        }
+                    }
+                    if (sc[0] != 1.f || sc[1] != 1.f) {
+                        const f2 sc2 = mk2(sc[0], sc[1]);
+                        tM = mul2(tM, sc2); tD = mul2(tD, sc2); nI = mul2(nI, sc2); inMa = mul2(inMa, sc2);
+                    }
+                }
+                // hand (toM, toD) to the right-hand neighbour column (slot+1 = lane+1, wrapping) of both pairs
+                const float rM0 = __shfl_sync(kFull, lo2(tM), (lane + 31) & 31), rM1 = __shfl_sync(kFull, hi2(tM), (lane + 31) & 31);
+                const float rD0 = __shfl_sync(kFull, lo2(tD), (lane + 31) & 31), rD1 = __shfl_sync(kFull, hi2(tD), (lane + 31) & 31);
+                inMb = inMa; inMa = mk2(rM0, rM1); inD = mk2(rD0, rD1); toI = nI;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    if (s < nd[h] - 1) {
+                        x[h] += (int)((~nib[h] >> kk) & 1u);
+                        if (x[h] > W) { // the slot's cell left the band at the top: on to column j + NSLOT
+                            x[h] -= NSLOT; rbp[h] -= NSLOT;
+                            emrow[h] = sEM[h] + (tcn[h] << 5);
+                            tcn[h] = *tnext[h];
+                            tnext[h] += NSLOT;
+                        }
+                    }
+                }
+                msk = mask2();
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+                if (s0 + 4 < nd[h] + 4) rbp[h] += 4; // a finished pair stops moving
+        }
+        __syncwarp();
+        if (lane < 2 && (lane == 0 || two)) {
+            const float fin = s_ftot[4 * lane];
+            const int Kl = lane ? K[1] : K[0];
+            p.out_lk[lane ? pi[1] : pi[0]] = fin > 0.f ? log((double)fin) - (double)Kl * 0.6931471805599453 : -INFINITY;
+        }
+        __syncwarp();
+    }
+}
+
 template <int C, int ROWS>
 __device__ __forceinline__ void backward_fused(const PairCtx &pc, const BCoef &a, const LeanSmem &fsh, const int model, const LeanPair &lp,
                                                const KbRef kb, const KParams &p, const unsigned wslot, const unsigned rawk,
@@ -1760,6 +1904,17 @@ cudaError_t launch_likelihood(const KParams &p, int C, int grid, cudaStream_t st
     case 8: likelihood_kernel<8><<<grid, kWarpsPerCta * 32, 0, st>>>(p); break;
     default: return cudaErrorInvalidValue;
     }
+    return cudaGetLastError();
+}
+
+// two short pairs per warp (radius <= likelihood_pairs2_max_radius()); p.smem_rb = staged read codes per PAIR
+int likelihood_pairs2_max_radius() { return kPackRadiusMax; }
+int likelihood_pairs2_pad_rows() { return 32 + 16; }
+cudaError_t launch_likelihood_pairs2(const KParams &p, int grid, cudaStream_t st) {
+    const int dyn = kWarpsPerCta * 2 * p.smem_rb;
+    cudaError_t e = cudaFuncSetAttribute(likelihood_pairs2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    if (e != cudaSuccess) return e;
+    likelihood_pairs2_kernel<<<grid, kWarpsPerCta * 32, dyn, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -101,55 +101,63 @@ def gen_reads(model: PairHiddenMarkovModel, templates: Sequence[np.ndarray], rng
     return [out[k, :olen[k]].copy() for k in range(n)]
 
 
-def _lk_bootstrap(hmm: PairHiddenMarkovModelOnStrands, templates, reads, strands, band: int, ctx) -> np.ndarray:
-    """likelihood_antidiagonal_bootstrap for many (template, read) pairs in slices of 200 k pairs."""
+def _flatten(out: np.ndarray, lens: np.ndarray, fallback: Sequence[np.ndarray], fb_idx: np.ndarray):
+    """(uint8[n, cap], lengths) -> (concatenated reads, uint32 offsets[n+1]); an empty read is replaced by the first base of
+    its source (a zero-length read has no alignment)."""
+    lens = lens.astype(np.int64)
+    empty = np.flatnonzero(lens == 0)
+    for k in empty:
+        out[k, 0] = fallback[int(fb_idx[k])][0]
+        lens[k] = 1
+    mask = np.arange(out.shape[1])[None, :] < lens[:, None]
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    return out[mask], off.astype(np.uint32)
+
+
+def _lk_bootstrap(hmm: PairHiddenMarkovModelOnStrands, templates, reads, strands, tmpl_idx, band: int, ctx) -> np.ndarray:
+    """likelihood_antidiagonal_bootstrap for many (template, read) pairs in ONE jtk_hmm_likelihood_batch; templates is a list
+    of the distinct templates, pair k uses templates[tmpl_idx[k]]; reads a list or a (concat, offsets) tuple."""
     f, r = hmm.forward().to_c(), hmm.reverse().to_c()
-    out = np.empty(len(reads), dtype=np.float64)
-    step = 200_000
-    for a in range(0, len(reads), step):
-        b = min(len(reads), a + step)
-        idx = np.arange(b - a, dtype=np.uint32)
-        out[a:b] = ctx.likelihood_batch(f, r, templates[a:b], reads[a:b], None, strands[a:b], idx, band)
-    return out
+    return ctx.likelihood_batch(f, r, templates, reads, None, strands, tmpl_idx, band)
 
 
 def estimate_gain(hmm: PairHiddenMarkovModelOnStrands, seed: int, seq_len: int, band: int, homop_len: int,
                   ctx: Optional[_lib.Context] = None, sample_num: int = 100, seq_num: int = 50) -> Gains:
-    """likelihood_gains.rs:162-184 with gain_of (:253-315) for every (type, length); all likelihood calls in one batch."""
+    """likelihood_gains.rs:162-184 with gain_of (:253-315) for every (type, length): the 2 * sample_num * seq_num * 9 * ...
+    likelihood calls of the calibration (1.8e5 by default) are ONE GPU batch (two pairs per warp); the reads
+    are sampled on the host threads (jtk_lc_gen_reads)."""
     ctx = ctx or default_context()
     gain_pos, prob_pos = sample_num // 10, sample_num * 2 // 3
     meta = []  # (type, len, sample) in generation order
-    pairs = []  # (template, diff) per meta entry
+    seqs = []  # sequences: 2m = template of sample m, 2m + 1 = the same with the variant
     for dt in (SUBST, DEL, INS):
         for length in range(1, homop_len + 1):
             for i in range(sample_num):
                 rng = np.random.default_rng(i + seed)  # one stream per sample, as the reference seeds them (:269)
                 seg1, seg2 = generate_seq(rng, seq_len // 2), generate_seq(rng, seq_len // 2)
                 hap1, hap2 = gen_diff_haplotypes(rng, length, dt)
-                pairs.append((np.concatenate([seg1, hap1, seg2]), np.concatenate([seg1, hap2, seg2])))
+                seqs += [np.concatenate([seg1, hap1, seg2]), np.concatenate([seg1, hap2, seg2])]
                 meta.append((dt, length, i))
-    # reads: per sample seq_num from the variant haplotype (expected gain) then seq_num from the template (null),
-    # even t from the forward model, odd t from the reverse model (:276-279); sampled for all samples at once
-    n_f, n_r = (seq_num + 1) // 2, seq_num // 2
-    rng = np.random.default_rng(seed)
-    src_f = [src for (template, diff) in pairs for src in [diff] * n_f + [template] * n_f]
-    src_r = [src for (template, diff) in pairs for src in [diff] * n_r + [template] * n_r]
-    reads_f = gen_reads(hmm.forward(), src_f, rng)
-    reads_r = gen_reads(hmm.reverse(), src_r, rng)
-    tmpls, reads, strands = [], [], []
-    for m, (template, diff) in enumerate(pairs):
-        for which in (0, 1):  # 0: reads from diff, 1: reads from template
-            for t in range(seq_num):
-                if t % 2 == 0:
-                    rd, st = reads_f[(2 * m + which) * n_f + t // 2], 1
-                else:
-                    rd, st = reads_r[(2 * m + which) * n_r + t // 2], 0
-                if len(rd) == 0:
-                    rd = template[:1].copy()
-                tmpls += [template, diff]
-                reads += [rd, rd]
-                strands += [st, st]
-    lk = _lk_bootstrap(hmm, tmpls, reads, np.array(strands, dtype=np.uint8), band, ctx).reshape(len(meta), 2, seq_num, 2)
+    n_s = len(meta)
+    # reads: per sample seq_num from the variant haplotype (expected gain) then seq_num from the template (null), even t from
+    # the forward model, odd t from the reverse model (:276-279).  Read index = ((m * 2 + which) * seq_num + t)
+    m_i, which, t_i = np.meshgrid(np.arange(n_s), np.arange(2), np.arange(seq_num), indexing="ij")
+    src = (2 * m_i + (1 - which)).ravel().astype(np.uint32)       # which = 0: reads of the variant sequence 2m + 1
+    is_fwd = (t_i.ravel() % 2 == 0)
+    cap = int(max(len(x) for x in seqs)) * 3 + 32
+    out = np.empty((len(src), cap), dtype=np.uint8)
+    lens = np.empty(len(src), dtype=np.uint32)
+    for model, sel, sd in ((hmm.forward(), is_fwd, seed), (hmm.reverse(), ~is_fwd, seed + 0x9E3779B9)):
+        idx = np.flatnonzero(sel)
+        o, l = _lib.gen_reads(model.as_array(), seqs, src[idx], sd, cap)
+        out[idx] = o
+        lens[idx] = l
+    # every read is scored against the template (2m) and against the variant (2m + 1)
+    rcat, roff = _flatten(np.repeat(out, 2, axis=0), np.repeat(lens, 2), seqs, np.repeat(2 * m_i.ravel(), 2))
+    tmpl_idx = (2 * np.repeat(m_i.ravel(), 2) + np.tile(np.arange(2), len(src))).astype(np.uint32)
+    strands = np.repeat(is_fwd, 2).astype(np.uint8)
+    lk = _lk_bootstrap(hmm, seqs, (rcat, roff), strands, tmpl_idx, band, ctx).reshape(n_s, 2, seq_num, 2)
     gain = np.zeros((3, homop_len))
     prob = np.zeros((3, homop_len))
     per = {}
@@ -174,27 +182,34 @@ def estimate_gain_default(hmm: PairHiddenMarkovModelOnStrands, ctx: Optional[_li
 
 def estimate_minimum_gain(hmm: PairHiddenMarkovModelOnStrands, ctx: Optional[_lib.Context] = None, sample_num: int = 1000,
                           seq_num: int = 500) -> float:
-    """likelihood_gains.rs:6-39: 1000 templates x 500 reads x 2 likelihoods at 100 bp, band 25."""
+    """likelihood_gains.rs:6-39: 1000 templates x 500 reads x 2 likelihoods at 100 bp, band 25 -- 1e6 pairs, in slices of
+    100 templates (1e5 pairs per GPU batch)."""
     ctx = ctx or default_context()
     seed0, length, band, min_req = 23908, 100, 25, 1.0
     medians = []
-    block = 50
+    block = 100
     for s0 in range(0, sample_num, block):
-        tmpls, reads, strands = [], [], []
         n_here = min(block, sample_num - s0)
+        seqs = []
         for s in range(s0, s0 + n_here):
             rng = np.random.default_rng(seed0 + s)
             hap1 = generate_seq(rng, length)
             pos = int(rng.integers(0, length))
-            hap2 = np.delete(hap1, pos)  # introduce_errors(hap1, rng, 0, 1, 0): one deletion
-            for model, st, k in ((hmm.forward(), 1, (seq_num + 1) // 2), (hmm.reverse(), 0, seq_num // 2)):
-                for rd in gen_reads(model, [hap1] * k, rng):
-                    if len(rd) == 0:
-                        rd = hap1[:1].copy()
-                    tmpls += [hap1, hap2]
-                    reads += [rd, rd]
-                    strands += [st, st]
-        lk = _lk_bootstrap(hmm, tmpls, reads, np.array(strands, dtype=np.uint8), band, ctx).reshape(n_here, seq_num, 2)
+            seqs += [hap1, np.delete(hap1, pos)]  # introduce_errors(hap1, rng, 0, 1, 0): one deletion
+        m_i, t_i = np.meshgrid(np.arange(n_here), np.arange(seq_num), indexing="ij")
+        src = (2 * m_i).ravel().astype(np.uint32)  # reads come from hap1
+        is_fwd = t_i.ravel() < (seq_num + 1) // 2
+        cap = length * 3 + 32
+        out = np.empty((len(src), cap), dtype=np.uint8)
+        lens = np.empty(len(src), dtype=np.uint32)
+        for model, sel, sd in ((hmm.forward(), is_fwd, seed0 + s0), (hmm.reverse(), ~is_fwd, seed0 + s0 + 0x9E3779B9)):
+            idx = np.flatnonzero(sel)
+            o, l = _lib.gen_reads(model.as_array(), seqs, src[idx], sd, cap)
+            out[idx] = o
+            lens[idx] = l
+        rcat, roff = _flatten(np.repeat(out, 2, axis=0), np.repeat(lens, 2), seqs, np.repeat(src, 2))
+        tmpl_idx = (np.repeat(src, 2) + np.tile(np.arange(2, dtype=np.uint32), len(src))).astype(np.uint32)
+        lk = _lk_bootstrap(hmm, seqs, (rcat, roff), np.repeat(is_fwd, 2).astype(np.uint8), tmpl_idx, band, ctx).reshape(n_here, seq_num, 2)
         d = lk[:, :, 0] - lk[:, :, 1]
         medians += [float(np.sort(row)[seq_num // 2]) for row in d]
     medians.sort()

@@ -400,3 +400,35 @@ def test_device_bootstrap_equals_host_bootstrap(ctx, monkeypatch):
             assert ctx.launch_count - n0 == (3 if dev == "1" else 1)
         assert np.array_equal(out["0"], out["1"]), R
         assert np.isfinite(out["1"]).all()
+
+
+def test_packed_likelihood_kernel_on_calibration_pairs(ctx, monkeypatch):
+    """at radius <= 14 two pairs share a warp (likelihood_pairs2_kernel).  1 201 calibration-shaped pairs
+    (likelihood_gains.rs:253-315: ~100 bp, radius 10; ragged lengths, both strand models, an odd pair count) against
+    O.likelihood_bootstrap pair by pair, against the guided oracle likelihood, and against the one-pair-per-warp kernel
+    (JTK_LIKELIHOOD_UNPACKED=1; the two place their power-of-two rescales on different anti-diagonals, so ln(fin) - K ln 2 agrees to
+    the last bits of the f64 logarithm, not bit for bit)."""
+    rng = np.random.default_rng(2024)
+    fwd, rev = random_hmm(21), random_hmm(22)
+    lens = [100 + int(rng.integers(-8, 9)) for _ in range(1100)] + [int(rng.integers(1, 260)) for _ in range(101)]
+    templates, reads, ops, strands = [], [], [], []
+    for k, L in enumerate(lens):
+        t = synth.random_template(rng, L)
+        q, o = synth.mutate_read(rng, t, 0.08 if k % 4 else 0.2)
+        templates.append(t); reads.append(q); ops.append(o); strands.append(k % 2 == 0)
+    tidx = np.arange(len(reads), dtype=np.uint32)
+    for R in (10, 14):
+        got = {}
+        for unpacked in (False, True):
+            if unpacked: monkeypatch.setenv("JTK_LIKELIHOOD_UNPACKED", "1")
+            else: monkeypatch.delenv("JTK_LIKELIHOOD_UNPACKED", raising=False)
+            got[unpacked] = (ctx.likelihood_batch(to_c(fwd), to_c(rev), templates, reads, None, strands, tidx, R),
+                             ctx.likelihood_batch(to_c(fwd), to_c(rev), templates, reads, ops, strands, tidx, R))
+        assert np.allclose(got[False][0], got[True][0], rtol=1e-12, atol=0) and np.allclose(got[False][1], got[True][1], rtol=1e-12, atol=0), R
+        for k in range(len(reads)):
+            h = fwd if strands[k] else rev
+            wantb = O.likelihood_bootstrap(h, templates[k], reads[k], R)
+            want = O.likelihood(h, templates[k], reads[k], ops[k], R)
+            assert abs(got[False][0][k] - wantb) <= 2e-5 * abs(wantb) + 1e-6, (R, k, got[False][0][k], wantb)
+            assert abs(got[False][1][k] - want) <= 2e-5 * abs(want) + 1e-6, (R, k, got[False][1][k], want)
+    monkeypatch.delenv("JTK_LIKELIHOOD_UNPACKED", raising=False)

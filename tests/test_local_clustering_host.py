@@ -182,3 +182,34 @@ def test_exact_score_bounds_the_mcmc_score():
         assert max((a == hap).mean(), (a != hap).mean()) >= 0.95
         e = asn.astype(int)
         assert max((e == hap).mean(), (e != hap).mean()) >= 0.95
+
+
+def test_gen_reads_samples_the_pair_hmm():
+    """jtk_lc_gen_reads (SURVEY 8a K6, our sampler of kiley's Generate::gen): deterministic per (seed, read index) whatever the
+    thread count, reads follow their source (length and identity as the model's error rates imply), and a model that never
+    leaves Match with an identity emission matrix copies the source."""
+    import os
+    from jtk_b200 import _lib, hmm
+    rng = np.random.default_rng(5)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    srcs = [acgt[rng.integers(0, 4, size=L)] for L in (100, 101, 99, 37, 1)]
+    idx = np.arange(3000, dtype=np.uint32) % len(srcs)
+    model = hmm.PairHiddenMarkovModelOnStrands.default().forward().as_array()
+    out, lens = _lib.gen_reads(model, srcs, idx, 77, 400)
+    os.environ["JTK_CLUSTER_THREADS"] = "1"
+    try:
+        out1, lens1 = _lib.gen_reads(model, srcs, idx, 77, 400)
+    finally:
+        del os.environ["JTK_CLUSTER_THREADS"]
+    assert np.array_equal(lens, lens1) and all(np.array_equal(out[k, :lens[k]], out1[k, :lens1[k]]) for k in range(0, 3000, 97))
+    src_len = np.array([len(srcs[i]) for i in idx])
+    assert abs(float(np.mean(lens / src_len)) - 1.0) < 0.05
+    assert len({bytes(out[k, :lens[k]]) for k in range(0, 3000, 5)}) > 300          # not one read repeated
+    same = [np.mean(out[k, :min(lens[k], 100)][:20] == srcs[idx[k]][:20]) for k in range(0, 3000, 5) if src_len[k] >= 99]
+    assert np.mean(same) > 0.7                                                        # the first bases mostly agree
+    exact = np.zeros(45)
+    exact[[0, 3, 6]] = 1.0
+    exact[9:25] = np.eye(4).ravel()
+    exact[25:45] = 0.25
+    o2, l2 = _lib.gen_reads(exact, srcs, idx[:50], 1, 400)
+    assert all(np.array_equal(o2[k, :l2[k]], srcs[idx[k]]) for k in range(50))
