@@ -193,8 +193,10 @@ typedef struct {
 int jtk_batch_candidates(jtk_batch *b, const jtk_gains *gains, const int32_t *copy_num /* n_tmpl */, double coverage,
                          jtk_candidate *out, int cap, int *out_n);
 /*
- * pseudo_mcmc::search_variants (pseudo_mcmc.rs:109-138) for every chunk of the batch: candidates on the device, their
- * values gathered on the device, greedy pick_filtered_profiles (:516-575) on the host.
+ * pseudo_mcmc::search_variants (pseudo_mcmc.rs:109-138) for every chunk of the batch, all of it on the device: candidates
+ * (filter_profiles, :426-474), their values, and the greedy pick_filtered_profiles (:516-575: one warp per chunk, same
+ * decisions as the host twin bit for bit; JTK_HOST_PICK=1 keeps the pick on the host).  Only the picks and the n x D
+ * variant columns come back.
  * out_n_probes[t] selected columns of chunk t, their flat positions at out_probe_pos[t*probe_cap ..], and for every pair p
  * (batch order) the compressed profile values at out_variants[p*probe_cap ..] (filter_by, :70-75); probe_cap >=
  * 3*max(copy_num, 2).  Chunks with copy_num < 2 are skipped (pseudo_mcmc.rs:86-88).

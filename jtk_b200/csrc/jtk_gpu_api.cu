@@ -321,6 +321,8 @@ struct jtk_ctx {
     DevBuf<double> d_tabs;        // p-value / prior / expected-gain tables of the candidate kernel
     DevBuf<uint32_t> d_tab_off;
     DevBuf<jtk_candidate> d_cand;
+    DevBuf<uint32_t> d_pick;      // pick_probes_kernel: chunk offsets / copy numbers in, picks out
+    DevBuf<double> d_var;         // pick_probes_kernel: the picked columns of every pair
     // k-means / MCMC restarts on the device (jtk_mcmc_restarts_batch)
     DevBuf<McmcChain> d_mc_chains;
     DevBuf<double> d_mc_f64, d_mc_lk;
@@ -344,6 +346,7 @@ struct jtk_ctx {
     PinBuf<int32_t> h_enc_status;
     PinBuf<jtk_candidate> h_cand;
     PinBuf<double> h_gather;
+    PinBuf<uint32_t> h_pick;
     // host scratch
     std::vector<uint32_t> tmpl_code_off;
     std::vector<uint8_t> tmp_ops;
@@ -1441,6 +1444,94 @@ __global__ void gather_all_kernel(const float *__restrict__ delta, const DevPair
     }
 }
 
+// pick_filtered_profiles on the device (pseudo_mcmc.rs:516-575): ONE WARP PER CHUNK.  The chunk's candidates are
+// cand[first_m[t] ..] in position order, their values vals[val_off[t] + r * M + m] (read r of the chunk, gather_all_kernel).
+// ROUND = 3 rounds of max(copy_num, 2) picks: find_next_variants = the unselected candidate with the largest score, the LAST one
+// among equals (Iterator::max_by); then every candidate still in play is removed for good when it lies within MASK_LENGTH = 7 bp
+// of the pick, or suppressed for the round when its Sokal-Michener or |cosine| similarity with the pick exceeds 0.8.  A lane
+// computes the two similarities of one candidate sequentially over the reads, in the reference's order, with explicit
+// round-to-nearest f64 operations (no contraction): the same decisions as the host twin, bit for bit.
+// Out: n_pick[t], pick_pos[t * probe_cap + d] (flat positions, ascending) and the picked columns of every read of the chunk,
+// variants[pair * probe_cap + d] (filter_by, :70-75).  status[t] = 1 when the chunk has more candidates than the kernel's
+// shared-memory flags hold (the host twin takes that chunk), 2 when more columns were picked than probe_cap.
+constexpr int kPickMaxCand = 2048;
+__global__ void __launch_bounds__(32) pick_probes_kernel(const jtk_candidate *__restrict__ cand, const uint32_t *__restrict__ first_m,
+                                                         const uint32_t *__restrict__ val_off, const double *__restrict__ vals,
+                                                         const int32_t *__restrict__ copy_num, const uint32_t *__restrict__ tp_start,
+                                                         const uint32_t *__restrict__ tp_ids, int probe_cap, uint32_t *__restrict__ n_pick,
+                                                         uint32_t *__restrict__ pick_pos, double *__restrict__ variants,
+                                                         uint32_t *__restrict__ status) {
+    __shared__ unsigned char sel[kPickMaxCand];
+    const uint32_t t = blockIdx.x, lane = threadIdx.x;
+    const uint32_t m0 = first_m[t], M = first_m[t + 1] - m0;
+    if (lane == 0) { n_pick[t] = 0; status[t] = 0; }
+    if (M == 0 || copy_num[t] < 2) return; // pseudo_mcmc.rs:86-88: single-copy chunks are not searched
+    if (M > (uint32_t)kPickMaxCand) { if (lane == 0) status[t] = 1; return; }
+    const uint32_t r0 = tp_start[t], nr = tp_start[t + 1] - r0;
+    const double *v = vals + val_off[t];
+    const jtk_candidate *c = cand + m0;
+    for (uint32_t m = lane; m < M; m += 32) sel[m] = 0;
+    __syncwarp();
+    const int picks = max(copy_num[t], 2);
+    for (int round = 0; round < 3; round++) {
+        for (uint32_t m = lane; m < M; m += 32) if (sel[m] == 3) sel[m] = 0;
+        __syncwarp();
+        for (int it = 0; it < picks; it++) {
+            // find_next_variants (:590-600)
+            double best = 0.0; uint32_t next = 0xffffffffu;
+            for (uint32_t m = lane; m < M; m += 32)
+                if (sel[m] == 0 && (next == 0xffffffffu || !(c[m].lk < best))) { next = m; best = c[m].lk; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const uint32_t on = __shfl_xor_sync(0xffffffffu, next, o);
+                // the later candidate wins among equal scores
+                if (on != 0xffffffffu && (next == 0xffffffffu || best < ob || (!(ob < best) && on > next))) { best = ob; next = on; }
+            }
+            if (next == 0xffffffffu) break;
+            const uint32_t picked_bp = c[next].pos / (uint32_t)kNumRow;
+            __syncwarp();
+            if (lane == 0) sel[next] = 1;
+            __syncwarp();
+            for (uint32_t m = lane; m < M; m += 32) {
+                if (!(sel[m] == 0 || sel[m] == 3)) continue;
+                const uint32_t bp = c[m].pos / (uint32_t)kNumRow;
+                const uint32_t diff = max(bp, picked_bp) - min(bp, picked_bp);
+                if (diff < 7u) { sel[m] = 2; continue; }
+                double ip = 0.0, isq = 0.0, jsq = 0.0;
+                uint32_t mat = 0, mism = 0;
+                for (uint32_t r = 0; r < nr; r++) {
+                    const double x = v[(size_t)r * M + next], y = v[(size_t)r * M + m];
+                    if (0.00001 < fabs(x) && 0.00001 < fabs(y)) {
+                        const double xy = __dmul_rn(x, y);
+                        ip = __dadd_rn(ip, xy); isq = __dadd_rn(isq, __dmul_rn(x, x)); jsq = __dadd_rn(jsq, __dmul_rn(y, y));
+                        if (0.0 < xy) mat++; else mism++;
+                    }
+                }
+                const uint32_t total = mat + mism;
+                const double sok = total == 0 ? 0.0 : __ddiv_rn((double)max(mism, mat), (double)total);
+                const double cs = isq == 0.0 ? 0.0 : __ddiv_rn(__ddiv_rn(ip, __dsqrt_rn(isq)), __dsqrt_rn(jsq));
+                if (0.8 < sok || 0.8 < fabs(cs)) sel[m] = 3;
+            }
+            __syncwarp();
+        }
+    }
+    // the selected candidates in candidate (position) order; their columns for every read of the chunk
+    uint32_t base = 0;
+    for (uint32_t m_lo = 0; m_lo < M; m_lo += 32) {
+        const uint32_t m = m_lo + lane;
+        const bool on = m < M && sel[m] == 1;
+        const unsigned ball = __ballot_sync(0xffffffffu, on);
+        const uint32_t d = base + __popc(ball & ((1u << lane) - 1u));
+        if (on && d < (uint32_t)probe_cap) {
+            pick_pos[(size_t)t * probe_cap + d] = c[m].pos;
+            for (uint32_t r = 0; r < nr; r++) variants[(size_t)tp_ids[r0 + r] * probe_cap + d] = v[(size_t)r * M + m];
+        }
+        base += __popc(ball);
+    }
+    if (lane == 0) { n_pick[t] = min(base, (uint32_t)probe_cap); if (base > (uint32_t)probe_cap) status[t] = 2; }
+}
+
 // plain per-column sums over the first `take` reads of each template (polish loop)
 __global__ void colsums_kernel(const float *__restrict__ delta, const DevPair *__restrict__ pairs,
                                const uint32_t *__restrict__ tp_start, const uint32_t *__restrict__ tp_ids,
@@ -1857,16 +1948,56 @@ int jtk_batch_search_variants(jtk_batch *b, const jtk_gains *gains, const int32_
                                                  ctx->d_gather.p);
     CU(cudaGetLastError(), "gather launch");
     ctx->launches++;
+    // 3. greedy pick per chunk (pseudo_mcmc.rs:516-575) and filter_by (:70-75): on the device, one warp per chunk -- only the
+    //    picked positions and the n x D variant columns cross PCIe.  JTK_HOST_PICK=1 keeps the host twin.
+    const bool host_pick = std::getenv("JTK_HOST_PICK") != nullptr;
+    std::vector<uint8_t> on_host((size_t)n_tmpl, host_pick ? 1 : 0);
+    bool any_host = host_pick;
+    if (!host_pick) {
+        // sorted candidates back to the device, chunk offsets and copy numbers behind the gather meta
+        std::vector<uint32_t> aux((size_t)3 * n_tmpl + 2);
+        std::copy(first_m.begin(), first_m.end(), aux.begin());
+        std::copy(val_off.begin(), val_off.end(), aux.begin() + n_tmpl + 1);
+        for (int t = 0; t < n_tmpl; t++) aux[(size_t)2 * n_tmpl + 2 + t] = (uint32_t)copy_num[t];
+        const size_t n_out = (size_t)2 * n_tmpl + (size_t)n_tmpl * probe_cap; // n_pick | status | pick_pos
+        CU(ctx->d_pick.reserve(aux.size() + n_out), "cudaMalloc pick buffers");
+        CU(ctx->h_pick.reserve(n_out), "cudaMallocHost pick buffers");
+        CU(ctx->d_var.reserve((size_t)b->n_pairs * probe_cap), "cudaMalloc variants");
+        CU(ctx->h_gather.reserve(std::max(n_val, (size_t)b->n_pairs * probe_cap)), "cudaMallocHost variants");
+        CU(cudaMemcpyAsync(ctx->d_cand.p, cand, sizeof(jtk_candidate) * (size_t)n, cudaMemcpyHostToDevice, st), "H2D sorted candidates");
+        CU(cudaMemcpyAsync(ctx->d_pick.p, aux.data(), sizeof(uint32_t) * aux.size(), cudaMemcpyHostToDevice, st), "H2D pick meta");
+        CU(cudaMemsetAsync(ctx->d_var.p, 0, sizeof(double) * (size_t)b->n_pairs * probe_cap, st), "memset variants");
+        uint32_t *d_aux = ctx->d_pick.p, *d_out = ctx->d_pick.p + aux.size();
+        pick_probes_kernel<<<(unsigned)n_tmpl, 32, 0, st>>>(ctx->d_cand.p, d_aux, d_aux + n_tmpl + 1, ctx->d_gather.p,
+                                                           reinterpret_cast<const int32_t *>(d_aux + 2 * (size_t)n_tmpl + 2),
+                                                           b->d_tp_start.p, b->d_tp_ids.p, probe_cap, d_out, d_out + 2 * (size_t)n_tmpl,
+                                                           ctx->d_var.p, d_out + n_tmpl);
+        CU(cudaGetLastError(), "pick launch");
+        ctx->launches++;
+        CU(cudaMemcpyAsync(ctx->h_pick.p, d_out, sizeof(uint32_t) * n_out, cudaMemcpyDeviceToHost, st), "D2H picks");
+        CU(cudaMemcpyAsync(ctx->h_gather.p, ctx->d_var.p, sizeof(double) * (size_t)b->n_pairs * probe_cap, cudaMemcpyDeviceToHost, st), "D2H variants");
+        rc = batch_sync(b);
+        if (rc) return rc;
+        std::memcpy(out_variants, ctx->h_gather.p, sizeof(double) * (size_t)b->n_pairs * probe_cap);
+        const uint32_t *npk = ctx->h_pick.p, *stt = ctx->h_pick.p + n_tmpl, *ppos = ctx->h_pick.p + 2 * (size_t)n_tmpl;
+        for (int t = 0; t < n_tmpl; t++) {
+            if (stt[t] == 2) return ctx->fail(JTK_EINVAL, "probe_cap too small");
+            if (stt[t] == 1) { on_host[(size_t)t] = 1; any_host = true; continue; } // more candidates than the kernel's flags hold
+            out_n_probes[t] = npk[t];
+            for (uint32_t d = 0; d < npk[t]; d++) out_probe_pos[(size_t)t * probe_cap + d] = ppos[(size_t)t * probe_cap + d];
+        }
+    }
+    if (!any_host) return JTK_OK;
+    CU(ctx->h_gather.reserve(n_val), "cudaMallocHost candidate values");
     CU(cudaMemcpyAsync(ctx->h_gather.p, ctx->d_gather.p, sizeof(double) * n_val, cudaMemcpyDeviceToHost, st), "D2H candidate values");
     rc = batch_sync(b);
     if (rc) return rc;
-    // 3. greedy pick per chunk (host, pseudo_mcmc.rs:516-575) and filter_by (:70-75)
     std::vector<uint32_t> pos;
     std::vector<double> lk;
     try {
         for (int t = 0; t < n_tmpl; t++) {
             const uint32_t m0 = first_m[t], Mt = first_m[t + 1] - m0;
-            if (Mt == 0 || copy_num[t] < 2) continue; // pseudo_mcmc.rs:86-88: single-copy chunks are not searched
+            if (!on_host[(size_t)t] || Mt == 0 || copy_num[t] < 2) continue; // pseudo_mcmc.rs:86-88: single-copy chunks are not searched
             const uint32_t r0 = b->tp_start[(size_t)t], nr = b->tp_start[(size_t)t + 1] - r0;
             pos.resize(Mt); lk.resize(Mt);
             for (uint32_t m = 0; m < Mt; m++) { pos[m] = cand[m0 + m].pos; lk[m] = cand[m0 + m].lk; }

@@ -261,3 +261,33 @@ def test_device_mcmc_restarts_equal_the_host_twin(ctx):
         assert np.array_equal(asn[c], ha), c
         assert lk[c] == hlk, (c, lk[c], hlk)
         assert np.array_equal(st[c], hst), c
+
+
+def test_device_pick_filtered_profiles_equals_the_host_twin(ctx, monkeypatch):
+    """pick_filtered_profiles on the device (pick_probes_kernel, one warp per chunk: pseudo_mcmc.rs:516-575 with
+    find_next_variants' last-maximum rule, the 7 bp mask, Sokal-Michener and cosine sweeps in the reference's summation order)
+    against the host twin on the same candidates: identical probe counts, positions and variant columns -- diploid chunks at
+    configs[1] size, a triploid one and two repeat-heavy copy_num 8 chunks (hundreds of candidates)."""
+    chunks = [synth.diploid_chunk(700 + c, length=2000, n_reads=60, error_rate=0.08, n_snv=3 + 2 * c) for c in range(4)]
+    chunks += [synth.paralog_chunk(4300 + c, length=1200, n_reads=160) for c in range(2)]
+    h = O.default_hmm()
+    templates = [c["template"] for c in chunks]
+    reads = [r for c in chunks for r in c["reads"]]
+    ops = [o for c in chunks for o in c["ops"]]
+    strands = np.concatenate([c["strands"] for c in chunks])
+    tidx = np.repeat(np.arange(len(chunks), dtype=np.uint32), [len(c["reads"]) for c in chunks])
+    copy_num = np.array([2, 2, 3, 2, 8, 8], dtype=np.int32)
+    b = ctx.batch(templates, reads, ops, strands, tidx, 30)
+    b.modtable(to_c(h), to_c(h), 9)
+    out = {}
+    for host in (False, True):
+        if host: monkeypatch.setenv("JTK_HOST_PICK", "1")
+        else: monkeypatch.delenv("JTK_HOST_PICK", raising=False)
+        n0 = ctx.launch_count
+        out[host] = b.search_variants(GAINS.gain, GAINS.prob, copy_num, 25.0)
+        assert ctx.launch_count - n0 == (2 if host else 3)     # candidates, gather (+ pick)
+    monkeypatch.delenv("JTK_HOST_PICK", raising=False)
+    assert out[False][0].sum() >= 6 and (out[False][0][4:] >= 2).all()
+    for a, c in zip(out[False], out[True]):
+        assert np.array_equal(a, c)
+    b.close()
