@@ -235,6 +235,10 @@ int jtk_polish_until_converge_batch(jtk_ctx *ctx, const jtk_hmm_params *fwd, con
                                     const uint8_t *strand, const uint32_t *tmpl_idx, const jtk_polish_config *cfg,
                                     uint8_t *out_cons, const uint64_t *cons_pos, const uint32_t *cons_cap,
                                     uint32_t *out_len, int32_t *out_iters);
+/* Host helper of the call above: moves n byte runs (run k: len[k] bytes at buf + pos[k], pos ascending, disjoint) to the
+ * front of buf, back to back; out_off[k] = new start of run k, out_off[n] = total bytes.  Turns the padded per-read ops slots
+ * into one compact array. */
+int jtk_compact_runs(uint8_t *buf, const uint64_t *pos, const uint32_t *len, int n, uint64_t *out_off);
 /* per-column sums over the first take_num reads of every template of a batch (device reduction used by the
  * polish loop): out[stat_off[t] + e] = sum_r profile_r[e] */
 int jtk_batch_colsums(jtk_batch *b, int take_num, double *out, const uint64_t *stat_off);

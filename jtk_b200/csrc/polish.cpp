@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <memory>
 #include <vector>
 
 namespace {
@@ -126,7 +127,12 @@ extern "C" int jtk_polish_until_converge_batch(jtk_ctx *ctx, const jtk_hmm_param
     }
     std::vector<int> iters((size_t)n_chunks, 0);
     std::vector<uint8_t> active((size_t)n_chunks, 1);
-    std::vector<uint8_t> t_cat, r_cat, o_cat, s_vec;
+    std::vector<uint8_t> t_cat, s_vec;
+    struct RawBuf { // staging bytes that are always overwritten: no value-initialisation (a resize() of 0.5 GB is a memset)
+        std::unique_ptr<uint8_t[]> p; size_t cap = 0;
+        uint8_t *data() { return p.get(); }
+        void need(size_t n) { if (n > cap) { cap = n + n / 8 + 64; p.reset(new uint8_t[cap]); } }
+    } r_cat, o_cat;
     std::vector<uint32_t> t_off, r_off, o_off, t_idx, chunk_of;
     std::vector<uint64_t> stat_off;
     std::vector<int8_t> best_rows;
@@ -141,33 +147,55 @@ extern "C" int jtk_polish_until_converge_batch(jtk_ctx *ctx, const jtk_hmm_param
     for (int round = 0; round < kMaxIter; round++) {
         const auto p0 = now();
         // batch of the voting reads of every chunk that is still changing
-        t_cat.clear(); r_cat.clear(); o_cat.clear(); s_vec.clear();
+        t_cat.clear(); s_vec.clear();
         if (round == 0) { // the first round carries every chunk: size the staging vectors once (growth by doubling copied ~3x the bytes)
             size_t tb = 0, ob = 0;
             for (int c = 0; c < n_chunks; c++) tb += tmpl[(size_t)c].size();
             for (int p = 0; p < n_pairs; p++) ob += n_ops[p];
-            t_cat.reserve(tb + 64 * (size_t)n_chunks); r_cat.reserve(read_off[n_pairs]); o_cat.reserve(ob + 64 * (size_t)n_pairs);
+            t_cat.reserve(tb + 64 * (size_t)n_chunks); r_cat.need(read_off[n_pairs]); o_cat.need(ob + 64 * (size_t)n_pairs);
             s_vec.reserve((size_t)n_pairs); t_idx.reserve((size_t)n_pairs); r_off.reserve((size_t)n_pairs + 1); o_off.reserve((size_t)n_pairs + 1);
         }
         t_off.assign(1, 0); r_off.assign(1, 0); o_off.assign(1, 0); t_idx.clear(); chunk_of.clear(); stat_off.clear();
         uint64_t so = 0;
+        // pass 1: the layout (offsets of every template / read / ops run of the batch); pass 2 copies the bytes on a few threads
+        std::vector<uint32_t> src_pair;
         for (int c = 0; c < n_chunks; c++) {
             if (!active[(size_t)c]) continue;
             const uint32_t bt = (uint32_t)chunk_of.size();
             chunk_of.push_back((uint32_t)c);
-            t_cat.insert(t_cat.end(), tmpl[(size_t)c].begin(), tmpl[(size_t)c].end());
-            t_off.push_back((uint32_t)t_cat.size());
+            t_off.push_back(t_off.back() + (uint32_t)tmpl[(size_t)c].size());
             stat_off.push_back(so);
             so += (uint64_t)tmpl[(size_t)c].size() + 1;
             const size_t take = std::min<size_t>((size_t)std::max(cfg->take_num, 0), members[(size_t)c].size());
             for (size_t m = 0; m < take; m++) {
                 const uint32_t p = members[(size_t)c][m];
-                r_cat.insert(r_cat.end(), read_concat + read_off[p], read_concat + read_off[p + 1]);
-                r_off.push_back((uint32_t)r_cat.size());
-                o_cat.insert(o_cat.end(), ops_buf + ops_pos[p], ops_buf + ops_pos[p] + n_ops[p]);
-                o_off.push_back((uint32_t)o_cat.size());
+                src_pair.push_back(p);
+                r_off.push_back(r_off.back() + (read_off[p + 1] - read_off[p]));
+                o_off.push_back(o_off.back() + n_ops[p]);
                 s_vec.push_back(strand[p]);
                 t_idx.push_back(bt);
+            }
+        }
+        t_cat.resize(t_off.back()); r_cat.need(r_off.back()); o_cat.need(o_off.back());
+        {
+            const size_t np = src_pair.size(), nc = chunk_of.size();
+            auto copy_range = [&](size_t lo, size_t hi) {
+                for (size_t k = lo; k < hi; k++) {
+                    const uint32_t p = src_pair[k];
+                    std::memcpy(r_cat.data() + r_off[k], read_concat + read_off[p], r_off[k + 1] - r_off[k]);
+                    std::memcpy(o_cat.data() + o_off[k], ops_buf + ops_pos[p], o_off[k + 1] - o_off[k]);
+                }
+            };
+            for (size_t bt = 0; bt < nc; bt++) std::memcpy(t_cat.data() + t_off[bt], tmpl[chunk_of[bt]].data(), t_off[bt + 1] - t_off[bt]);
+            const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+            const size_t nt = std::min<size_t>(hw, (np + 2047) / 2048);
+            if (nt <= 1) copy_range(0, np);
+            else {
+                std::vector<std::thread> th;
+                const size_t per = (np + nt - 1) / nt;
+                for (size_t t = 1; t < nt; t++) th.emplace_back(copy_range, std::min(np, t * per), std::min(np, (t + 1) * per));
+                copy_range(0, std::min(np, per));
+                for (auto &x : th) x.join();
             }
         }
         if (chunk_of.empty()) break;
@@ -233,5 +261,21 @@ extern "C" int jtk_polish_until_converge_batch(jtk_ctx *ctx, const jtk_hmm_param
         out_len[c] = (uint32_t)tmpl[(size_t)c].size();
         if (out_iters) out_iters[c] = iters[(size_t)c];
     }
+    return JTK_OK;
+}
+
+// Moves n byte runs (run k: len[k] bytes at buf + pos[k], pos ascending, runs disjoint) to the front of buf, back to back;
+// out_off[k] = new start of run k, out_off[n] = total.  The host mirror uses it to hand the patched guide paths of
+// jtk_polish_until_converge_batch back as one compact array instead of n padded slots.
+extern "C" int jtk_compact_runs(uint8_t *buf, const uint64_t *pos, const uint32_t *len, int n, uint64_t *out_off) {
+    if (n < 0 || (n > 0 && (!buf || !pos || !len)) || !out_off) return JTK_EINVAL;
+    uint64_t w = 0;
+    for (int k = 0; k < n; k++) {
+        if (pos[k] < w) return JTK_EINVAL;
+        out_off[k] = w;
+        if (pos[k] != w) std::memmove(buf + w, buf + pos[k], len[k]);
+        w += len[k];
+    }
+    out_off[n] = w;
     return JTK_OK;
 }

@@ -162,15 +162,21 @@ def polish_chunks(models: PairHiddenMarkovModelOnStrands, drafts: Sequence, read
     np.cumsum(caps, out=pos[1:])
     # every read's ops at pos[k] with room to grow (caps[k]): one concatenate of (ops, zero padding) pieces instead of a
     # Python-level copy per read (120 000 reads per call at 2 000 chunks)
-    ops8 = [_lib._u8(o) for o in ops]
-    n_ops = np.fromiter((len(o) for o in ops8), dtype=np.uint32, count=n_pairs)
+    n_ops = np.fromiter(map(len, ops), dtype=np.uint32, count=n_pairs)
     if (n_ops > caps).any():
         raise ValueError("ops longer than read + 2 * draft + 64")
-    zeros = np.zeros(int((caps - n_ops).max()) if n_pairs else 0, dtype=np.uint8)
+    room = (caps - n_ops).tolist()
+    zeros = np.zeros(max(room) if n_pairs else 0, dtype=np.uint8)
     pieces = [None] * (2 * n_pairs)
-    pieces[0::2] = ops8
-    pieces[1::2] = [zeros[:int(c)] for c in (caps - n_ops)]
-    buf = np.concatenate(pieces) if n_pairs else np.zeros(0, dtype=np.uint8)
+    pieces[0::2] = ops
+    pieces[1::2] = [zeros[:c] for c in room]
+    try:
+        buf = np.concatenate(pieces) if n_pairs else np.zeros(0, dtype=np.uint8)
+        if buf.dtype != np.uint8:
+            raise TypeError
+    except (TypeError, ValueError):
+        pieces[0::2] = [_lib._u8(o) for o in ops]
+        buf = np.concatenate(pieces)
     ccap = (2 * dlen + 64).astype(np.uint32)
     cpos = np.zeros(n_chunks + 1, dtype=np.uint64)
     np.cumsum(ccap, out=cpos[1:])
@@ -188,7 +194,12 @@ def polish_chunks(models: PairHiddenMarkovModelOnStrands, drafts: Sequence, read
                                                  p(roff), p(buf), p(pos), p(caps), p(n_ops), p(st), p(tmpl_idx),
                                                  C.byref(cfg), p(cons), p(cpos), p(ccap), p(clen), p(iters)))
     out_cons = [cons[int(cpos[c]):int(cpos[c]) + int(clen[c])].copy() for c in range(n_chunks)]
-    out_ops = [buf[int(pos[k]):int(pos[k]) + int(n_ops[k])].copy() for k in range(n_pairs)]
+    # the patched guide paths as views into ONE compact copy (120 000 per-read copies cost more than the kernels of a round)
+    off = np.zeros(n_pairs + 1, dtype=np.uint64)
+    L.jtk_compact_runs.argtypes = [vp, vp, vp, C.c_int, vp]
+    ctx._check(L.jtk_compact_runs(p(buf), p(pos), p(n_ops), n_pairs, p(off)))
+    compact = buf[:int(off[-1])].copy()
+    out_ops = np.split(compact, off[1:-1].astype(np.int64)) if n_pairs else []
     return out_cons, out_ops, iters
 
 

@@ -1,4 +1,2 @@
-mkdir -p gpurun_out
-timeout 2400 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "small or wide_band or ragged or packed or bit_identical or very_long" > gpurun_out/v11_memcheck.log 2>&1
-echo "memcheck rc=$?" >> gpurun_out/v11_memcheck.log
-tail -15 gpurun_out/v11_memcheck.log
+timeout 600 python -m pytest tests/test_polish.py tests/test_consensus.py tests/test_gpu_pipeline.py -x -q -m gpu 2>&1 | tail -2
+JTK_TIMING=1 timeout 900 python tools/phase_scale.py --chunks 2000 2>&1 | grep -E "polish:|phases_s" | tail -3
