@@ -176,7 +176,7 @@ TRAFFIC_NOTE = {"fused": "dram__bytes_read.sum + dram__bytes_write.sum of modtab
                          "profiles/r2_traffic.json): checkpoints (65 B per anti-diagonal, written once, read once, partly from "
                          "L2), the raw column sums between the two kernels and the profiles; no DP matrix",
                 "rows": "dram__bytes_read.sum + dram__bytes_write.sum of the three kernels (ncu --set full, profiles/r2_traffic.json): "
-                        "the forward-row scratch (2 x 2.3 MB per pair: written by fwdrows at 6.0 TB/s, read back by bwdtable), "
+                        "the forward-row scratch (2 x 2.4 MB per pair: written by fwdrows at 5.8 TB/s, read back by bwdtable), "
                         "not the algorithmic bytes, see roofline.hbm"}
 
 
@@ -404,7 +404,7 @@ def workload_config(args):
             "chunks_per_gpu": args.chunks, "reads_per_chunk": args.reads, "chunk_len": args.length, "radius": RADIUS,
             "rows": 14, "parallelism": "chunks sharded over ranks, no collective",
             "l2": "no explicit flush: each step writes 0.6 GB of raw column sums and 0.5 GB of profiles per GPU, plus 1.2 GB of "
-                  "checkpoints (fused variant) or 11 GB of forward rows (rows variant), all read back (>> 126 MB L2), so the "
+                  "checkpoints (fused variant) or 11.7 GB of forward rows (rows variant), all read back (>> 126 MB L2), so the "
                   "25 MB of inputs are evicted between steps"}
 
 
@@ -525,7 +525,7 @@ def main():
             os.environ["JTK_MODTABLE"] = saved
         variants["default"] = variant
         variants["note"] = ("fused: the DP matrices never touch HBM (checkpoints + recomputation in shared memory); rows: forward rows "
-                            "parked in HBM between two kernels (2.3 MB per pair). Same tables bit for bit; the library takes 'rows' "
+                            "parked in HBM between two kernels (2.4 MB per pair). Same tables bit for bit; the library takes 'rows' "
                             "when the whole batch fits its scratch budget as one wave (JTK_SCRATCH_MB, JTK_MODTABLE overrides)")
 
     # 9-row (clustering rows only) variant, reported as an extra
