@@ -616,6 +616,194 @@ static void mcmc_restarts(const Mat &data, size_t k, double cov, Rng &rng, int r
         if (!any || !(lk < best_lk)) { best = asn; best_lk = lk; any = true; } // max_by keeps the last maximum
     }
 }
+// ---- Host twin of the SPECULATIVE schedule of mcmc_speculative_kernel (mcmc_kernels.cu), two clusters.
+// mcmc_with_filter (:704-762) rejects almost every proposal once the chain has settled, and a rejected proposal leaves
+// the chain where it was except for the rounding of its flip / flip-back round trip ((a - x) + x).  So up to kSpec
+// proposals are evaluated side by side: the draws are generated ahead into a ring, parsed into proposals under the
+// assumption that every earlier proposal of the round is rejected (then each consumes exactly one acceptance draw),
+// proposal j starts from the state after the round trips of proposals 0..j-1, and the round commits up to and including
+// the first accepted proposal.  The stream position moves by exactly the draws the sequential chain would have consumed,
+// so assignments, likelihoods and the generator state are the sequential chain's, bit for bit
+// (tests/test_local_clustering_host.py::test_speculative_schedule_equals_the_sequential_chain).
+struct SpecStats { uint64_t rounds = 0, proposals = 0, slow = 0; };
+constexpr int kSpec = 4, kSpecRing = 64, kSpecBlock = 16;
+struct SpecStream { // draws generated ahead in blocks of kSpecBlock; snapshots of the generator at the last four block starts
+    Rng &rng;
+    uint64_t ring[kSpecRing];
+    uint64_t snap[4][4];
+    uint64_t head = 0, gen = 0; // absolute stream positions: next draw to consume / next draw to generate
+    explicit SpecStream(Rng &r) : rng(r) {}
+    void gen_block() {
+        std::memcpy(snap[(gen / kSpecBlock) & 3], rng.s, 32);
+        for (int i = 0; i < kSpecBlock; i++) ring[(gen + i) & (kSpecRing - 1)] = rng.next_u64();
+        gen += kSpecBlock;
+    }
+    uint64_t at(uint64_t pos) const { return ring[pos & (kSpecRing - 1)]; }
+    void rewind_generator() { // leaves rng where the sequential chain's generator is: at `head`
+        if (head == gen) return;
+        const uint64_t b = head / kSpecBlock;
+        std::memcpy(rng.s, snap[b & 3], 32);
+        for (uint64_t p = b * kSpecBlock; p < head; p++) (void)rng.next_u64();
+        gen = head;
+    }
+};
+static double mcmc_with_filter_spec2(const Mat &data, std::vector<size_t> &assign, double cov, Rng &rng, SpecStats &stats, int kSpecWindow) {
+    const size_t n = data.size(), D = n ? data[0].size() : 0;
+    std::vector<double> s2l;
+    for (size_t x = 0; x <= n; x++) s2l.push_back(max_poisson_lk(x, cov, 1, 2));
+    std::vector<double> X(n * D);
+    std::vector<uint8_t> CL(n * D);
+    for (size_t i = 0; i < n; i++)
+        for (size_t d = 0; d < D; d++) {
+            const double x = data[i][d];
+            X[i * D + d] = x;
+            CL[i * D + d] = (uint8_t)((POS_THR < x ? 1 : 0) | ((!(POS_THR < x) && x < -POS_THR) ? 2 : 0));
+        }
+    auto ratio_ok = [&](int64_t p, int64_t q) -> bool { return 0.70 < (double)p / ((double)(p + q) + 0.0000001); };
+    struct St { std::vector<double> t0, t1; };
+    std::vector<double> tot0(D, 0.0), tot1(D, 0.0);
+    std::vector<int64_t> np0(D, 0), np1(D, 0), nn0(D, 0), nn1(D, 0);
+    int64_t c0 = 0, c1 = 0;
+    for (size_t i = 0; i < n; i++)
+        for (size_t d = 0; d < D; d++) {
+            const double x = X[i * D + d]; const unsigned cl = CL[i * D + d];
+            if (assign[i] == 0) { if (d == 0) c0++; tot0[d] += x; np0[d] += cl & 1u; nn0[d] += cl >> 1; }
+            else { if (d == 0) c1++; tot1[d] += x; np1[d] += cl & 1u; nn1[d] += cl >> 1; }
+        }
+    // get_lk (:785-795) with get_used_columns (:847-869) of a state given as column arrays
+    auto lk_of = [&](const std::vector<double> &a0, const std::vector<double> &a1, const std::vector<int64_t> &p0, const std::vector<int64_t> &p1,
+                     const std::vector<int64_t> &q0, const std::vector<int64_t> &q1, int64_t k0, int64_t k1) -> double {
+        double lk = s2l[(size_t)k0] + s2l[(size_t)k1];
+        std::vector<uint8_t> use(D);
+        for (size_t d = 0; d < D; d++) {
+            const bool pos0 = 0.0 < a0[d], pos1 = 0.0 < a1[d];
+            const bool u = (pos0 && ratio_ok(p0[d], q0[d])) || (pos1 && ratio_ok(p1[d], q1[d]));
+            const int64_t in_use = (pos0 ? p0[d] : 0) + (pos1 ? p1[d] : 0), in_neg = ((a0[d] <= 0.0) ? p0[d] : 0) + ((a1[d] <= 0.0) ? p1[d] : 0);
+            use[d] = u && 2 * in_neg < in_use;
+        }
+        for (size_t d = 0; d < D; d++) lk += use[d] ? (a0[d] < 0.0 ? 0.0 : a0[d]) : 0.0;
+        for (size_t d = 0; d < D; d++) lk += use[d] ? (a1[d] < 0.0 ? 0.0 : a1[d]) : 0.0;
+        return lk;
+    };
+    double lk = lk_of(tot0, tot1, np0, np1, nn0, nn1, c0, c1);
+    double mx = lk;
+    std::vector<size_t> argmax = assign;
+    SpecStream S(rng);
+    const uint64_t range = n, zone = (range << __builtin_clzll(range)) - 1;
+    const uint64_t total = 2000ull * n;
+    uint64_t t = 0;
+    while (t < total) {
+        while (S.gen - S.head < (uint64_t)kSpecWindow) S.gen_block();
+        // the window of kSpecWindow draws: which could end a gen_range (maskA), which a gen_index(1) (maskB)
+        uint32_t maskA = 0, maskB = 0;
+        for (int L = 0; L < kSpecWindow; L++) {
+            const uint64_t v = S.at(S.head + L);
+            const unsigned __int128 m = (unsigned __int128)v * range;
+            if ((uint64_t)m <= zone) maskA |= 1u << L;
+            if (!(v >> 63)) maskB |= 1u << L;
+        }
+        const int want = (int)std::min<uint64_t>(kSpec, total - t);
+        int nvalid = 0, pos_idx[kSpec], pos_acc[kSpec];
+        for (int j = 0, p = 0; j < want; j++) {
+            if (p >= kSpecWindow) break;
+            const uint32_t ma = maskA >> p;
+            if (!ma) break;
+            const int a = p + __builtin_ctz(ma);
+            if (a + 1 >= kSpecWindow) break;
+            const uint32_t mb = maskB >> (a + 1);
+            if (!mb) break;
+            const int b = a + 1 + __builtin_ctz(mb);
+            if (b + 1 >= kSpecWindow) break;
+            pos_idx[j] = a; pos_acc[j] = b + 1; p = b + 2; nvalid++;
+        }
+        size_t idx[kSpec];
+        if (nvalid == 0) { // the first proposal does not end inside the window: scan it draw by draw (never in practice)
+            stats.slow++;
+            auto take = [&]() -> uint64_t { if (S.head == S.gen) S.gen_block(); return S.at(S.head++); };
+            for (;;) { const unsigned __int128 m = (unsigned __int128)take() * range; if ((uint64_t)m <= zone) { idx[0] = (size_t)(m >> 64); break; } }
+            while (take() >> 63) { }
+            if (S.head == S.gen) S.gen_block();
+            pos_acc[0] = 0; nvalid = 1;
+        } else {
+            for (int j = 0; j < nvalid; j++) idx[j] = (size_t)(((unsigned __int128)S.at(S.head + pos_idx[j]) * range) >> 64);
+        }
+        stats.rounds++;
+        // state j = the chain after the round trips of proposals 0..j-1 (every one of them rejected)
+        std::vector<St> st(nvalid + 1);
+        st[0].t0 = tot0; st[0].t1 = tot1;
+        std::vector<std::vector<double>> s(nvalid, std::vector<double>(D));
+        size_t old[kSpec];
+        for (int m = 0; m < nvalid; m++) {
+            old[m] = assign[idx[m]];
+            st[m + 1].t0.resize(D); st[m + 1].t1.resize(D);
+            for (size_t d = 0; d < D; d++) {
+                const double x = X[idx[m] * D + d];
+                s[m][d] = old[m] == 0 ? -x : x;
+                st[m + 1].t0[d] = (st[m].t0[d] + s[m][d]) + (-s[m][d]);
+                st[m + 1].t1[d] = (st[m].t1[d] + (-s[m][d])) + s[m][d];
+            }
+        }
+        int jstar = -1, used = 0;
+        double proposed_star = 0;
+        for (int j = 0; j < nvalid && jstar < 0; j++) { // (side by side on the device; only the first acceptance counts)
+            std::vector<double> f0(D), f1(D);
+            std::vector<int64_t> p0 = np0, p1 = np1, q0 = nn0, q1 = nn1;
+            const int64_t sg = old[j] == 0 ? -1 : 1;
+            for (size_t d = 0; d < D; d++) {
+                const unsigned cl = CL[idx[j] * D + d];
+                f0[d] = st[j].t0[d] + s[j][d]; f1[d] = st[j].t1[d] + (-s[j][d]);
+                p0[d] += sg * (int64_t)(cl & 1u); p1[d] -= sg * (int64_t)(cl & 1u);
+                q0[d] += sg * (int64_t)(cl >> 1); q1[d] -= sg * (int64_t)(cl >> 1);
+            }
+            const double proposed = lk_of(f0, f1, p0, p1, q0, q1, c0 + sg, c1 - sg);
+            const double diff = proposed - lk;
+            bool accept; int consumed;
+            if (0.0 < diff) { accept = true; consumed = 0; }
+            else if (diff < -45.0) { accept = false; consumed = 1; }
+            else {
+                const double p = std::exp(diff);
+                if (p == 1.0) { accept = true; consumed = 0; }
+                else {
+                    if (!(p >= 0.0 && p < 1.0)) throw Panic("gen_bool: p is outside range [0.0, 1.0]");
+                    accept = S.at(S.head + pos_acc[j]) < (uint64_t)(p * 18446744073709551616.0);
+                    consumed = 1;
+                }
+            }
+            if (accept) {
+                jstar = j; used = consumed; proposed_star = proposed;
+                tot0 = f0; tot1 = f1; np0 = p0; np1 = p1; nn0 = q0; nn1 = q1; c0 += sg; c1 -= sg;
+            }
+        }
+        if (jstar >= 0) {
+            assign[idx[jstar]] = 1 - old[jstar];
+            lk = proposed_star;
+            if (mx < lk) { mx = proposed_star; argmax = assign; }
+            S.head += (uint64_t)pos_acc[jstar] + used;
+            t += jstar + 1; stats.proposals += jstar + 1;
+        } else {
+            tot0 = st[nvalid].t0; tot1 = st[nvalid].t1;
+            S.head += (uint64_t)pos_acc[nvalid - 1] + 1;
+            t += nvalid; stats.proposals += nvalid;
+        }
+    }
+    S.rewind_generator();
+    assign = argmax;
+    LKs chk_lks; std::vector<size_t> chk_clusters;
+    build_lks(data, assign, 2, chk_lks, chk_clusters);
+    const double chk = get_lk(chk_lks, chk_clusters, s2l);
+    JTK_ASSERT(std::fabs(mx - chk) < 0.0001, "(max - lk).abs() < 0.0001");
+    return mx;
+}
+static void mcmc_restarts_spec2(const Mat &data, double cov, Rng &rng, int restarts, std::vector<size_t> &best, double &best_lk, SpecStats &stats, int window) {
+    bool any = false;
+    best.clear(); best_lk = 0;
+    for (int t = 0; t < restarts; t++) {
+        std::vector<size_t> asn = kmeans(data, 2, rng);
+        const double lk = mcmc_with_filter_spec2(data, asn, cov, rng, stats, window);
+        if (!any || !(lk < best_lk)) { best = asn; best_lk = lk; any = true; }
+    }
+}
+
 static ClusterOut mcmc_finish(const Mat &data, size_t k, double cov, const std::vector<size_t> &best, double best_lk) {
     ClusterOut o; o.asn = best;
     get_read_lk_gains(data, o.asn, k, o.used, o.read_gains);
@@ -1054,6 +1242,26 @@ int jtk_lc_mcmc_restarts_host(const double *data, int n, int D, int k, double co
         std::memcpy(state4, rng.s, 32);
         for (int i = 0; i < n; i++) out_asn[i] = (uint8_t)best[(size_t)i];
         *out_lk = best_lk;
+        return JTK_OK;
+    } catch (const std::exception &e) { g_lc_error = e.what(); return JTK_EINVAL; }
+}
+// Host twin of the speculative schedule of mcmc_speculative_kernel (two clusters): the same results as
+// jtk_lc_mcmc_restarts_host; out_stats = { rounds, proposals, slow-path rounds } (proposals / rounds = the speed-up of a round)
+int jtk_lc_mcmc_restarts_spec_host(const double *data, int n, int D, double cov, int restarts, int window, uint64_t *state4,
+                                   uint8_t *out_asn, double *out_lk, uint64_t *out_stats) {
+    try {
+        if (!data || !state4 || !out_asn || !out_lk || n < 1 || D < 1 || window < 3 || window > 32) { g_lc_error = "bad argument"; return JTK_EINVAL; }
+        Mat m((size_t)n);
+        for (int i = 0; i < n; i++) m[(size_t)i].assign(data + (size_t)i * D, data + (size_t)(i + 1) * D);
+        Rng rng(0);
+        std::memcpy(rng.s, state4, 32);
+        std::vector<size_t> best; double best_lk = 0;
+        SpecStats stats;
+        mcmc_restarts_spec2(m, cov, rng, restarts, best, best_lk, stats, window);
+        std::memcpy(state4, rng.s, 32);
+        for (int i = 0; i < n; i++) out_asn[i] = (uint8_t)best[(size_t)i];
+        *out_lk = best_lk;
+        if (out_stats) { out_stats[0] = stats.rounds; out_stats[1] = stats.proposals; out_stats[2] = stats.slow; }
         return JTK_OK;
     } catch (const std::exception &e) { g_lc_error = e.what(); return JTK_EINVAL; }
 }

@@ -20,7 +20,10 @@
 #include "../../include/jtk_gpu.h"
 #include "mcmc_dev.cuh"
 
+#include <algorithm>
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 #include <cuda_runtime.h>
 
 namespace jtk {
@@ -598,6 +601,405 @@ __global__ void __launch_bounds__(128, 2) mcmc_diploid_kernel(const McmcChain *_
     for (uint32_t i = g; i < n; i += kSubLanes) oa[i] = c.best[i];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Two clusters, at most eight columns, SPECULATIVE: one chain per warp PAIR.  The evaluator warp runs up to four proposals of
+// the chain side by side on its four 8-lane groups and commits up to and including the first acceptance; the helper warp
+// runs the chain's generator AHEAD of it.  mcmc_with_filter rejects almost every proposal once the chain has settled
+// (3.8-4.0 of 4 speculated proposals commit on diploid chunks), and a rejected proposal leaves the chain where it was except
+// for the rounding of its flip / flip-back round trip (a + s) + (-s):
+//   * helper: blocks of 16 draws into a 128-entry ring (every lane advances the state, lane i keeps s1 of step i and computes
+//     draw i, its gen_range(n) result and two flags: could it end gen_range(n) -- low word of v*n inside the zone --, could it
+//     end gen_index(1) -- top bit clear), the generator state at the last eight block starts kept for the rewind at the end of
+//     the chain (k-means of the next restart continues at the stream position).  Hand-off through release / acquire words in
+//     shared memory: GEN (draws published), HEAD (draws consumed: the helper stays < 128 ahead), CMD / ACK (start, stop, exit);
+//   * evaluator, lane L: "a proposal that starts at draw head+L ends where?" from two ballots of the flags and two bit scans
+//     (index draw(s), choose draw(s), ONE acceptance draw -- exactly what a rejected proposal consumes); four dependent
+//     shuffles chain the proposals of the round;
+//   * every lane replays the round trips of proposals 0..3 on its column (group j starts from the state after j of them);
+//     group j then evaluates proposal j like mcmc_diploid_kernel (same f64 operations in the same order);
+//   * first acceptance j*: the state of group j* is broadcast, the stream moves to behind its acceptance draw (or to the
+//     draw itself when the acceptance consumed none: diff > 0 or exp(diff) == 1), j* + 1 proposals are done.  None: the
+//     state after all round trips, all proposals done.
+// The schedule is restated on the host (local_clustering.cpp, mcmc_with_filter_spec2) and checked against the sequential
+// chain there; this kernel is checked against the sequential host twin (tests/test_gpu_clustering.py).  A window that
+// does not hold one whole proposal (never at 32 draws; forced by a small `window` in the tests) is scanned draw by draw.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSpec = 4, kSpecRing = 128, kSpecBlock = 16, kSpecSnaps = kSpecRing / kSpecBlock;
+enum { kCmdStart = 1, kCmdStop = 2, kCmdExit = 3 };
+struct SpecLayout { uint32_t x, cl, s2l, ratio, assign, argmax, best, xch, centers, dists, cum, counts, ring, flags, snap, start, ctrl, total, rwords; };
+__host__ __device__ inline SpecLayout spec_layout(uint32_t n, uint32_t DP) {
+    SpecLayout L;
+    uint32_t o = 0;
+    auto take = [&](uint32_t bytes) { const uint32_t at = o; o += (bytes + 15u) & ~15u; return at; };
+    L.rwords = (n + 1 + 31) / 32;
+    L.x = take(8u * (n + 1) * DP);            // one spare row: lanes past the last column read (and ignore) the next entries
+    L.s2l = take(8u * (n + 1));
+    L.xch = take(8u * 2 * kSpec * 2 * DP);
+    L.ring = take(8u * kSpecRing);
+    L.flags = take(4u * kSpecRing);
+    L.snap = take(32u * kSpecSnaps);
+    L.start = take(32u);
+    L.ctrl = take(32u);                       // GEN, HEAD, CMD, ACK, LIVE
+    L.centers = take(8u * 2 * DP);
+    L.dists = take(8u * n);
+    L.cum = take(8u * n);
+    L.ratio = take(4u * (n + 1) * L.rwords);
+    L.counts = take(16);
+    L.cl = take((n + 1) * DP);
+    L.assign = take(n);
+    L.argmax = take(n);
+    L.best = take(n);
+    L.total = o;
+    return L;
+}
+__device__ __forceinline__ uint32_t ld_acquire_smem(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_smem(uint32_t *p, uint32_t v) {
+    asm volatile("st.relaxed.cta.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_smem(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+
+// The helper warp of one chain: commands in CTRL[2] = (sequence << 2) | type.
+__device__ __noinline__ void spec_helper(uint64_t *RING, uint32_t *FLAGS, uint64_t *SNAP, uint64_t *START, uint32_t *CTRL, uint32_t n, int lane) {
+    const uint32_t r32 = n;
+    const uint64_t zone = ((uint64_t)n << __clzll((long long)n)) - 1;
+    uint32_t seen = 0;
+    for (;;) {
+        uint32_t cmd;
+        do { cmd = ld_acquire_smem(CTRL + 2); } while (cmd == seen);
+        seen = cmd;
+        if ((cmd & 3u) == kCmdExit) return;
+        if ((cmd & 3u) != kCmdStart) continue;
+        DevRng rng{ START[0], START[1], START[2], START[3] };
+        uint32_t gen = 0;
+        for (;;) {
+            for (;;) { // room for another block, or a new command
+                cmd = ld_acquire_smem(CTRL + 2);
+                if (cmd != seen) break;
+                const uint32_t hp = ld_acquire_smem(CTRL + 1);
+                if (gen + kSpecBlock <= (hp & ~(uint32_t)(kSpecBlock - 1)) + kSpecRing) break;
+            }
+            if (cmd != seen) break;
+            if (lane < 4) SNAP[((gen / kSpecBlock) & (kSpecSnaps - 1)) * 4 + lane] = lane == 0 ? rng.s0 : lane == 1 ? rng.s1 : lane == 2 ? rng.s2 : rng.s3;
+            uint64_t mine = 0;
+#pragma unroll
+            for (int i = 0; i < kSpecBlock; i++) {
+                if (lane == i) mine = rng.s1;
+                const uint64_t t = rng.s1 << 17;
+                rng.s2 ^= rng.s0; rng.s3 ^= rng.s1; rng.s1 ^= rng.s2; rng.s0 ^= rng.s3;
+                rng.s2 ^= t;
+                rng.s3 = DevRng::rotl(rng.s3, 45);
+            }
+            if (lane < kSpecBlock) {
+                const uint64_t v = DevRng::rotl(mine * 5, 7) * 9;
+                const uint64_t t0 = (uint64_t)(uint32_t)v * r32;
+                const uint64_t u = (uint64_t)(uint32_t)(v >> 32) * r32 + (t0 >> 32);
+                const uint64_t lo = (u << 32) | (uint32_t)t0;
+                RING[(gen + lane) & (kSpecRing - 1)] = v;
+                FLAGS[(gen + lane) & (kSpecRing - 1)] = (uint32_t)(u >> 32) | (lo <= zone ? 0x100u : 0u) | (!(v >> 63) ? 0x200u : 0u);
+            }
+            gen += kSpecBlock;
+            __syncwarp();
+            if (lane == 0) st_release_smem(CTRL, gen);
+        }
+        // stopped: leave the live state and how far it got, acknowledge
+        if (lane == 0) { START[0] = rng.s0; START[1] = rng.s1; START[2] = rng.s2; START[3] = rng.s3; CTRL[4] = gen; st_release_smem(CTRL + 3, cmd); }
+        seen = cmd;
+        if ((cmd & 3u) == kCmdExit) return;
+    }
+}
+
+template <int DP>
+__global__ void __launch_bounds__(256, 2) mcmc_speculative_kernel(const McmcChain *__restrict__ chains, const int *__restrict__ ids,
+                                                                  int n_ids, const double *__restrict__ wf64, uint64_t *rng_state,
+                                                                  uint8_t *out_asn, const uint64_t *__restrict__ asn_off,
+                                                                  double *out_lk, int *out_err, int restarts, int smem_per_chain,
+                                                                  int window) {
+    extern __shared__ __align__(16) unsigned char mcmc_smem[];
+    const int n_pairs = blockDim.x >> 6;                      // warps 0..n_pairs-1 evaluate, warp n_pairs + w helps warp w
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = warp % n_pairs;
+    const bool helper = warp >= n_pairs;
+    const int g = lane & 7, grp = lane >> 3;
+    const int slot = blockIdx.x * n_pairs + pair;
+    const bool active = slot < n_ids;                         // (only the last CTA has idle pairs; they stay for the barrier)
+    const int chain = ids[active ? slot : 0];
+    const McmcChain ch = chains[chain];
+    const uint32_t n = ch.n, D = ch.D;
+    unsigned char *sm = mcmc_smem + (size_t)pair * smem_per_chain;
+    const SpecLayout L = spec_layout(n, DP);
+    uint64_t *RING = reinterpret_cast<uint64_t *>(sm + L.ring);
+    uint32_t *FLAGS = reinterpret_cast<uint32_t *>(sm + L.flags);
+    uint64_t *SNAP = reinterpret_cast<uint64_t *>(sm + L.snap);
+    uint64_t *START = reinterpret_cast<uint64_t *>(sm + L.start);
+    uint32_t *CTRL = reinterpret_cast<uint32_t *>(sm + L.ctrl);
+    if (!helper && lane < 8) CTRL[lane] = 0;                  // the control words of the pair, before its helper polls them
+    __syncthreads();
+    if (!active) return;
+    if (helper) { spec_helper(RING, FLAGS, SNAP, START, CTRL, n, lane); return; }
+    double *X = reinterpret_cast<double *>(sm + L.x);
+    double *S2L = reinterpret_cast<double *>(sm + L.s2l);
+    double *XCH = reinterpret_cast<double *>(sm + L.xch);
+    uint32_t *RAT = reinterpret_cast<uint32_t *>(sm + L.ratio);
+    uint8_t *CL = sm + L.cl;
+    const uint32_t RW = L.rwords;
+    ChainView c;
+    c.n = n; c.D = D; c.k = 2; c.ld = DP;
+    c.flat = X; c.size_to_lk = S2L; c.pinc = nullptr; c.ninc = nullptr; c.ratio_ok = nullptr;
+    c.centers = reinterpret_cast<double *>(sm + L.centers);
+    c.dists = reinterpret_cast<double *>(sm + L.dists);
+    c.cum = reinterpret_cast<double *>(sm + L.cum);
+    c.counts = reinterpret_cast<uint32_t *>(sm + L.counts);
+    c.assign = sm + L.assign; c.argmax = sm + L.argmax; c.best = sm + L.best;
+    { // stage the chain: data (padded to DP columns, one spare zero row), sign classes, size prior, the ratio table as bits
+        const double *f = wf64 + ch.off_f64;
+        for (uint32_t e = lane; e < (n + 1) * DP; e += 32) {
+            const uint32_t i = e / DP, d = e % DP;
+            const double x = (d < D && i < n) ? f[(size_t)i * D + d] : 0.0;
+            X[e] = x;
+            CL[e] = (uint8_t)((kPosThr < x ? 1 : 0) | ((!(kPosThr < x) && x < -kPosThr) ? 2 : 0));
+        }
+        for (uint32_t i = lane; i <= n; i += 32) S2L[i] = f[(size_t)n * D + i];
+        for (uint32_t e = lane; e < (n + 1) * RW; e += 32) {
+            const uint32_t p = e / RW, w = e % RW;
+            uint32_t bits = 0;
+            for (uint32_t b = 0; b < 32; b++) {
+                const uint32_t q = w * 32 + b;
+                if (q + p <= n && 0.70 < __ddiv_rn((double)p, __dadd_rn((double)(p + q), 0.0000001))) bits |= 1u << b;
+            }
+            RAT[e] = bits;
+        }
+    }
+    __syncwarp();
+    DevRng rng{ rng_state[4 * chain], rng_state[4 * chain + 1], rng_state[4 * chain + 2], rng_state[4 * chain + 3] };
+    const bool col = (uint32_t)g < D;        // lanes g >= DP shadow column 0 and never publish a term
+    const bool pub = g < DP;
+    const int gg = pub ? g : 0;
+    auto ratio_ok = [&](uint32_t p, uint32_t q) -> unsigned { return (RAT[p * RW + (q >> 5)] >> (q & 31u)) & 1u; };
+    uint32_t head = 0, seq = 0;              // stream position relative to the start of this restart's chain; command counter
+    double tot0 = 0.0, tot1 = 0.0; uint32_t np0 = 0, np1 = 0, nn0 = 0, nn1 = 0, c0 = 0, c1 = 0;
+    auto build = [&]() {
+        tot0 = tot1 = 0.0; np0 = np1 = nn0 = nn1 = c0 = c1 = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t a = c.assign[i];
+            const double x = X[i * DP + gg];
+            const uint32_t cl = CL[i * DP + gg];
+            if (a == 0) { c0++; tot0 = __dadd_rn(tot0, x); np0 += cl & 1u; nn0 += cl >> 1; }
+            else { c1++; tot1 = __dadd_rn(tot1, x); np1 += cl & 1u; nn1 += cl >> 1; }
+        }
+    };
+    unsigned buf = 0;
+    // get_lk (:785-795) with get_used_columns (:847-869) of the state the GROUP holds (one column per lane)
+    auto group_lk = [&](double a0, double a1, uint32_t p0, uint32_t p1, uint32_t q0, uint32_t q1, uint32_t k0, uint32_t k1) -> double {
+        const bool pos0 = 0.0 < a0, pos1 = 0.0 < a1;
+        const unsigned u = ((unsigned)pos0 & ratio_ok(p0, q0)) | ((unsigned)pos1 & ratio_ok(p1, q1));
+        const uint32_t in_use = (pos0 ? p0 : 0u) + (pos1 ? p1 : 0u);
+        const uint32_t in_neg = ((a0 <= 0.0) ? p0 : 0u) + ((a1 <= 0.0) ? p1 : 0u);
+        const bool use = col && u != 0u && 2u * in_neg < in_use; // the reference compares the same integers as f64
+        double *T = XCH + (buf * kSpec + grp) * (2 * DP);
+        buf ^= 1u;
+        if (pub) {
+            T[g] = use ? (a0 < 0.0 ? 0.0 : a0) : 0.0;
+            T[DP + g] = use ? (a1 < 0.0 ? 0.0 : a1) : 0.0;
+        }
+        __syncwarp();
+        double lk = __dadd_rn(S2L[k0], S2L[k1]);
+#pragma unroll
+        for (int d = 0; d < 2 * DP; d++) lk = __dadd_rn(lk, T[d]);
+        return lk;
+    };
+    auto command = [&](uint32_t type) { seq++; __syncwarp(); if (lane == 0) st_release_smem(CTRL + 2, (seq << 2) | type); };
+    double best_lk = 0.0;
+    bool any = false;
+    int err = kMcmcOk;
+    for (int rs = 0; rs < restarts && err == kMcmcOk; rs++) { // mcmc_clustering (:649-670): max_by keeps the last maximum
+        if (lane == 0) err = kmeans(c, rng);
+        __syncwarp();
+        err = __shfl_sync(kFullMask, err, 0);
+        rng.s0 = __shfl_sync(kFullMask, rng.s0, 0); rng.s1 = __shfl_sync(kFullMask, rng.s1, 0);
+        rng.s2 = __shfl_sync(kFullMask, rng.s2, 0); rng.s3 = __shfl_sync(kFullMask, rng.s3, 0);
+        if (err != kMcmcOk) break;
+        // ---- mcmc_with_filter (:704-762), k = 2, speculative schedule ----
+        head = 0;
+        if (lane == 0) { START[0] = rng.s0; START[1] = rng.s1; START[2] = rng.s2; START[3] = rng.s3; CTRL[0] = 0; CTRL[1] = 0; }
+        command(kCmdStart);
+        build();
+        double lk = group_lk(tot0, tot1, np0, np1, nn0, nn1, c0, c1);
+        double mx = lk;
+        for (uint32_t i = lane; i < n; i += 32) c.argmax[i] = c.assign[i];
+        const uint64_t total = 2000ull * n;
+        uint64_t t = 0;
+        while (t < total) {
+            while (ld_acquire_smem(CTRL) - head < (uint32_t)window) { }
+            // ---- lane L: a proposal that starts at draw head + L ends where? ----
+            const uint32_t fl = FLAGS[(head + lane) & (kSpecRing - 1)];
+            const uint32_t maskA = __ballot_sync(kFullMask, lane < window && (fl & 0x100u)), maskB = __ballot_sync(kFullMask, lane < window && (fl & 0x200u));
+            uint32_t word;
+            {
+                const uint32_t ma = maskA >> lane;
+                const int a = lane + __ffs((int)ma) - 1;                 // (ma == 0: a = lane - 1, not used)
+                const uint32_t mb = (ma != 0u && a + 1 < 32) ? maskB >> (a + 1) : 0u;
+                const int b = a + __ffs((int)mb);
+                const uint32_t my_idx = __shfl_sync(kFullMask, fl & 0xffu, a & 31);
+                word = (mb != 0u && b + 1 < window) ? (my_idx | ((uint32_t)(b + 1) << 8) | 0x10000u) : 0u;
+            }
+            const int want = (int)(total - t < (uint64_t)kSpec ? total - t : (uint64_t)kSpec);
+            int nvalid = 0, pc[kSpec];
+            uint32_t idx[kSpec];
+            {
+                bool alive = true; int p = 0;
+#pragma unroll
+                for (int j = 0; j < kSpec; j++) {
+                    const uint32_t w = __shfl_sync(kFullMask, word, p & 31);
+                    alive = alive && j < want && p < window && (w & 0x10000u);
+                    idx[j] = alive ? (w & 0xffu) : 0u;
+                    pc[j] = alive ? (int)((w >> 8) & 0xffu) : 0;
+                    nvalid += alive ? 1 : 0;
+                    p = pc[j] + 1;
+                }
+            }
+            if (nvalid == 0) { // the first proposal does not end inside the window: scan it draw by draw
+                uint32_t hi = 0;
+                for (;;) {
+                    while (ld_acquire_smem(CTRL) == head) { }
+                    const uint32_t f1 = FLAGS[head & (kSpecRing - 1)]; head++;
+                    __syncwarp();
+                    if (lane == 0) st_release_smem(CTRL + 1, head);
+                    if (f1 & 0x100u) { hi = f1 & 0xffu; break; }
+                }
+                for (;;) {
+                    while (ld_acquire_smem(CTRL) == head) { }
+                    const uint32_t f1 = FLAGS[head & (kSpecRing - 1)]; head++;
+                    __syncwarp();
+                    if (lane == 0) st_release_smem(CTRL + 1, head);
+                    if (f1 & 0x200u) break;
+                }
+                while (ld_acquire_smem(CTRL) == head) { }
+                nvalid = 1;
+#pragma unroll
+                for (int j = 0; j < kSpec; j++) { idx[j] = hi; pc[j] = 0; }
+            }
+            // ---- states: every lane replays the round trips of the four proposals on its column; group j keeps state j ----
+            double st0[kSpec + 1], st1[kSpec + 1];
+            double s_own = 0.0; uint32_t cl_own = 0, old_own = 0, old_all[kSpec];
+            st0[0] = tot0; st1[0] = tot1;
+#pragma unroll
+            for (int m = 0; m < kSpec; m++) {
+                const uint32_t old = c.assign[idx[m]];
+                const double x = X[idx[m] * DP + gg];
+                const double s = old == 0u ? -x : x;
+                old_all[m] = old;
+                if (m == grp) { s_own = s; cl_own = CL[idx[m] * DP + gg]; old_own = old; }
+                st0[m + 1] = __dadd_rn(__dadd_rn(st0[m], s), -s);
+                st1[m + 1] = __dadd_rn(__dadd_rn(st1[m], -s), s);
+            }
+            double b0 = st0[0], b1 = st1[0];
+#pragma unroll
+            for (int m = 1; m < kSpec; m++) if (m == grp) { b0 = st0[m]; b1 = st1[m]; }
+            // ---- proposal grp: flip (:764-783), get_lk, acceptance ----
+            const int dp = old_own == 0u ? -(int)(cl_own & 1u) : (int)(cl_own & 1u);
+            const int dn = old_own == 0u ? -(int)(cl_own >> 1) : (int)(cl_own >> 1);
+            const int dc = old_own == 0u ? -1 : 1;
+            const double f0 = __dadd_rn(b0, s_own), f1 = __dadd_rn(b1, -s_own);
+            const uint32_t P0 = np0 + dp, P1 = np1 - dp, Q0 = nn0 + dn, Q1 = nn1 - dn, K0 = c0 + dc, K1 = c1 - dc;
+            const double proposed = group_lk(f0, f1, P0, P1, Q0, Q1, K0, K1);
+            const double diff = __dsub_rn(proposed, lk);
+            int pc_own = pc[0];
+#pragma unroll
+            for (int m = 1; m < kSpec; m++) if (m == grp) pc_own = pc[m];
+            bool accept = false, bad = false;
+            uint32_t used = 1;
+            if (0.0 < diff) { accept = true; used = 0; }
+            else if (diff < -45.0) { accept = false; } // threshold 0: the draw is consumed, never accepted
+            else {
+                const uint64_t r = RING[(head + pc_own) & (kSpecRing - 1)];
+                bool decided = false;
+                if (diff < -0.001) { // exp(diff) < 1: exactly one draw, compared with trunc(exp(diff) * 2^64)
+                    float pf;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pf) : "f"((float)diff * 1.4426950408889634f));
+                    const double rh = (double)(uint32_t)(r >> 32);
+                    const double ub = __dadd_rn(__dmul_rn((double)(pf * 1.0001f), 4294967296.0), 2.0);
+                    const double lb = __dadd_rn(__dmul_rn((double)(pf * 0.9999f), 4294967296.0), -2.0);
+                    if (rh >= ub) { decided = true; accept = false; }
+                    else if (__dadd_rn(rh, 1.0) <= lb) { decided = true; accept = true; }
+                }
+                if (!decided) {
+                    const double p = exp(diff);
+                    if (p == 1.0) { accept = true; used = 0; }               // Bernoulli ALWAYS_TRUE: no draw
+                    else if (!(p >= 0.0 && p < 1.0)) { accept = true; bad = true; } // NaN: the reference panics (if the chain gets here)
+                    else accept = r < __double2ull_rz(__dmul_rn(p, 18446744073709551616.0));
+                }
+            }
+            const uint32_t accmask = __ballot_sync(kFullMask, accept && grp < nvalid);
+            if (accmask) {
+                const int src = __ffs((int)accmask) - 1;   // first lane of the first accepting group (its lanes agree)
+                const int js = src >> 3;
+                if (__shfl_sync(kFullMask, (int)bad, src)) { err = kMcmcBadProb; break; }
+                tot0 = shfl_f64(f0, js * 8 + g); tot1 = shfl_f64(f1, js * 8 + g);
+                np0 = __shfl_sync(kFullMask, P0, js * 8 + g); np1 = __shfl_sync(kFullMask, P1, js * 8 + g);
+                nn0 = __shfl_sync(kFullMask, Q0, js * 8 + g); nn1 = __shfl_sync(kFullMask, Q1, js * 8 + g);
+                c0 = __shfl_sync(kFullMask, K0, src); c1 = __shfl_sync(kFullMask, K1, src);
+                lk = shfl_f64(proposed, src);
+                const uint32_t used_s = __shfl_sync(kFullMask, used, src);
+                uint32_t idx_s = idx[0], old_s = old_all[0]; int pc_s = pc[0];
+#pragma unroll
+                for (int m = 1; m < kSpec; m++) if (m == js) { idx_s = idx[m]; old_s = old_all[m]; pc_s = pc[m]; }
+                __syncwarp();                                  // every lane has read assign[] for this round
+                if (lane == 0) c.assign[idx_s] = (uint8_t)(1u - old_s);
+                __syncwarp();
+                if (mx < lk) {
+                    mx = lk;
+                    for (uint32_t i = lane; i < n; i += 32) c.argmax[i] = c.assign[i];
+                }
+                head += (uint32_t)pc_s + used_s;
+                t += (uint64_t)js + 1;
+            } else {
+                tot0 = st0[1]; tot1 = st1[1];
+#pragma unroll
+                for (int m = 2; m <= kSpec; m++) if (m == nvalid) { tot0 = st0[m]; tot1 = st1[m]; }
+                int pc_l = pc[0];
+#pragma unroll
+                for (int m = 1; m < kSpec; m++) if (m == nvalid - 1) pc_l = pc[m];
+                head += (uint32_t)pc_l + 1u;
+                t += (uint64_t)nvalid;
+            }
+            if (lane == 0) st_relaxed_smem(CTRL + 1, head); // (every read of the ring fed a ballot of this round: they are done)
+        }
+        // the generator of the sequential chain stands at `head`: stop the helper, take the block start before head, replay
+        command(kCmdStop);
+        while (ld_acquire_smem(CTRL + 3) != ((seq << 2) | kCmdStop)) { }
+        if (head == CTRL[4]) { rng.s0 = START[0]; rng.s1 = START[1]; rng.s2 = START[2]; rng.s3 = START[3]; }
+        else {
+            const uint32_t b = head / kSpecBlock, q = (b & (kSpecSnaps - 1)) * 4;
+            rng.s0 = SNAP[q]; rng.s1 = SNAP[q + 1]; rng.s2 = SNAP[q + 2]; rng.s3 = SNAP[q + 3];
+            for (uint32_t p = b * kSpecBlock; p < head; p++) (void)rng.next_u64();
+        }
+        if (err != kMcmcOk) break;
+        __syncwarp();
+        for (uint32_t i = lane; i < n; i += 32) c.assign[i] = c.argmax[i];
+        __syncwarp();
+        build();
+        const double chk = group_lk(tot0, tot1, np0, np1, nn0, nn1, c0, c1);
+        if (!(fabs(__dsub_rn(mx, chk)) < 0.0001)) { err = kMcmcLkMismatch; break; }
+        if (!any || !(mx < best_lk)) { for (uint32_t i = lane; i < n; i += 32) c.best[i] = c.assign[i]; best_lk = mx; any = true; }
+        __syncwarp();
+    }
+    command(kCmdExit);
+    __syncwarp();
+    if (lane == 0) {
+        rng_state[4 * chain] = rng.s0; rng_state[4 * chain + 1] = rng.s1; rng_state[4 * chain + 2] = rng.s2; rng_state[4 * chain + 3] = rng.s3;
+        out_lk[chain] = best_lk;
+        out_err[chain] = err;
+    }
+    uint8_t *oa = out_asn + asn_off[chain];
+    for (uint32_t i = lane; i < n; i += 32) oa[i] = c.best[i];
+}
+
 size_t mcmc_smem_bytes(uint32_t n, uint32_t D, uint32_t k) {
     return (sizeof(double) * ((size_t)k * D + 2 * (size_t)n) + sizeof(uint32_t) * ((k + 1) & ~1u) + 3 * (size_t)n + 15) & ~(size_t)15;
 }
@@ -618,6 +1020,23 @@ static cudaError_t launch_diploid(const McmcChain *chains, const int *ids, int n
     return cudaGetLastError();
 }
 
+template <int DP>
+static cudaError_t launch_speculative(const McmcChain *chains, const int *ids, int n_ids, uint32_t n_max, const double *wf64, uint64_t *rng_state,
+                                      uint8_t *out_asn, const uint64_t *asn_off, double *out_lk, int *out_err, int restarts, int window,
+                                      cudaStream_t st) {
+    const size_t per_chain = spec_layout(n_max, DP).total;
+    // few chains: one warp pair per CTA spreads them over the SMs (a warp alone on its scheduler has the lowest latency)
+    int pairs = n_ids > 2 * 148 ? 4 : n_ids > 148 ? 2 : 1;
+    while (pairs > 1 && (size_t)pairs * per_chain > 100 * 1024) pairs >>= 1; // two CTAs per SM when they fit
+    const size_t dyn = (size_t)pairs * per_chain;
+    if (dyn > 220 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(mcmc_speculative_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+    mcmc_speculative_kernel<DP><<<(n_ids + pairs - 1) / pairs, pairs * 64, dyn, st>>>(chains, ids, n_ids, wf64, rng_state, out_asn, asn_off,
+                                                                                      out_lk, out_err, restarts, (int)per_chain, window);
+    return cudaGetLastError();
+}
+
 // Chains with two clusters and at most eight columns (class_of >= 0) go to the sub-warp kernel of their padded width;
 // everything else runs one warp per chain.  ids: device array of n_chains ints, the chain indices grouped by class
 // (class_count[c] of them for class c = 0..4: widths 2, 4, 6, 8, then the general kernel), each group sorted by read count.
@@ -631,6 +1050,13 @@ cudaError_t launch_mcmc_restarts(const McmcChain *chains, const McmcChain *host_
                                  uint8_t *out_asn, const uint64_t *asn_off, double *out_lk, int *out_err, int restarts,
                                  size_t smem_per_chain, cudaStream_t st) {
     if (n_chains <= 0) return cudaSuccess;
+    // JTK_MCMC_KERNEL = auto (default) | speculative | subwarp: which kernel takes the two-cluster chains.  The speculative
+    // kernel holds 8 chains per SM (1 184 per wave) at 0.50 s per 20 restarts of 60 reads (0.86 s with all 8), the sub-warp
+    // kernel 32 per SM (4 736) at 1.4 s: auto takes the speculative kernel whenever the chains of a class fit one wave of it.
+    // JTK_MCMC_WINDOW (tests) shrinks the draw window so that the draw-by-draw path runs.
+    int variant = 2, window = 32;
+    if (const char *v = std::getenv("JTK_MCMC_KERNEL")) variant = std::strcmp(v, "subwarp") == 0 ? 0 : std::strcmp(v, "speculative") == 0 ? 1 : 2;
+    if (const char *v = std::getenv("JTK_MCMC_WINDOW")) { window = std::atoi(v); window = window < 3 ? 3 : window > 32 ? 32 : window; }
     int at = 0;
     for (int cls = 0; cls < 4; cls++) {
         const int cnt = class_count[cls];
@@ -638,6 +1064,20 @@ cudaError_t launch_mcmc_restarts(const McmcChain *chains, const McmcChain *host_
             uint32_t n_max = 0;
             for (int q = 0; q < cnt; q++) n_max = n_max > host_chains[host_ids[at + q]].n ? n_max : host_chains[host_ids[at + q]].n;
             cudaError_t e = cudaSuccess;
+            static const int widths[4] = { 2, 4, 6, 8 };
+            const size_t spec_bytes = spec_layout(n_max, (uint32_t)widths[cls]).total;
+            const size_t spec_per_sm = std::min<size_t>(8, (220 * 1024) / spec_bytes);
+            if (variant == 1 || (variant == 2 && (size_t)cnt <= 148 * spec_per_sm)) { // speculative: one chain per warp pair
+                switch (cls) {
+                case 0: e = launch_speculative<2>(chains, ids + at, cnt, n_max, wf64, rng_state, out_asn, asn_off, out_lk, out_err, restarts, window, st); break;
+                case 1: e = launch_speculative<4>(chains, ids + at, cnt, n_max, wf64, rng_state, out_asn, asn_off, out_lk, out_err, restarts, window, st); break;
+                case 2: e = launch_speculative<6>(chains, ids + at, cnt, n_max, wf64, rng_state, out_asn, asn_off, out_lk, out_err, restarts, window, st); break;
+                default: e = launch_speculative<8>(chains, ids + at, cnt, n_max, wf64, rng_state, out_asn, asn_off, out_lk, out_err, restarts, window, st); break;
+                }
+                if (e != cudaSuccess) return e;
+                at += cnt;
+                continue;
+            }
             switch (cls) {
             case 0: e = launch_diploid<2>(chains, ids + at, cnt, n_max, wf64, rng_state, out_asn, asn_off, out_lk, out_err, restarts, st); break;
             case 1: e = launch_diploid<4>(chains, ids + at, cnt, n_max, wf64, rng_state, out_asn, asn_off, out_lk, out_err, restarts, st); break;

@@ -496,23 +496,43 @@ def host_threads() -> int:
 
 
 GPU_MCMC_CAPACITY = 4736   # diploid chains one B200 runs side by side (148 SMs x 8 warps x 4 chains, mcmc_diploid_kernel)
-GPU_MCMC_HOST_EQUIV = 8    # chunks one host thread clusters in the time the GPU takes for its (concurrent) chains (~1.3 s)
+GPU_MCMC_HOST_S = 0.17     # seconds of one host thread per chunk (20 restarts x 2000 x 60 proposals, csrc/local_clustering.cpp)
+
+
+def gpu_mcmc_seconds(n_chains: int) -> float:
+    """Measured latency of jtk_mcmc_restarts_batch for n diploid chains of 60 reads (profiles/r2_mcmc_speculative.txt):
+    the speculative kernel (one chain per warp pair, <= 1 184 chains) 0.50 s up to 4 chains per SM, 0.86 s at 8; beyond
+    that the sub-warp kernel (four chains per warp), 1.4 s for up to 4 736 chains."""
+    if n_chains <= 0:
+        return 0.0
+    if n_chains <= 592:
+        return 0.50
+    if n_chains <= 1184:
+        return 0.50 + 0.36 * (n_chains - 592) / 592
+    return 1.4 * -(-n_chains // GPU_MCMC_CAPACITY)
 
 
 def gpu_mcmc_share(n_chunks: int) -> int:
-    """How many of n_chunks go to jtk_mcmc_restarts_batch: none for small calls (a chain takes 25x longer on a warp than
-    on a core), otherwise as many as the GPU runs concurrently, leaving the host threads an equal-time share.
-    JTK_GPU_MCMC=0 / 1 forces none / all."""
+    """How many of n_chunks go to jtk_mcmc_restarts_batch: the split that lets the GPU chains (concurrent: their latency
+    hardly depends on their number) and the host threads (GPU_MCMC_HOST_S per chunk and thread) finish together; none
+    for calls the host threads absorb in less than the latency of one GPU chain.  JTK_GPU_MCMC=0 / 1 forces none / all."""
     import os
     mode = os.environ.get("JTK_GPU_MCMC", "auto")
     if mode == "0":
         return 0
     if mode == "1":
         return n_chunks
-    host_share = GPU_MCMC_HOST_EQUIV * host_threads()
-    if n_chunks <= host_share:
-        return 0
-    return min(n_chunks - host_share, GPU_MCMC_CAPACITY)
+    threads = host_threads()
+    best, best_t = 0, n_chunks * GPU_MCMC_HOST_S / threads
+    for t_gpu in (1.4, 0.86, 0.74, 0.62, 0.50):       # (ties: the larger host share)
+        host = int(t_gpu / GPU_MCMC_HOST_S) * threads           # chunks the host threads finish in that time
+        n_gpu = max(0, n_chunks - host)
+        if n_gpu == 0:
+            continue
+        t = max(gpu_mcmc_seconds(n_gpu), -(-(n_chunks - n_gpu) // threads) * GPU_MCMC_HOST_S)
+        if t < best_t:
+            best, best_t = n_gpu, t
+    return min(best, GPU_MCMC_CAPACITY)
 
 
 def _cluster_pileups(ctx, hmm, gains: Gains, coverage: float, read_type: str, pile: Dict[int, Tuple[List[Node], Chunk]]):

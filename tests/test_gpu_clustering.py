@@ -236,9 +236,11 @@ def _host_restarts(data, k, cov, state, restarts):
     return asn, lk.value, st
 
 
-def test_device_mcmc_restarts_equal_the_host_twin(ctx):
-    """jtk_mcmc_restarts_batch (two clusters and <= 8 columns: four chains per warp, mcmc_diploid_kernel; otherwise
-    one warp per chain) against the host restatement of mcmc_clustering's
+@pytest.mark.parametrize("kernel", ["speculative", "speculative-window-6", "subwarp"])
+def test_device_mcmc_restarts_equal_the_host_twin(ctx, monkeypatch, kernel):
+    """jtk_mcmc_restarts_batch (two clusters and <= 8 columns: mcmc_speculative_kernel, one chain per warp with
+    four proposals side by side -- also with a 6-draw window, which sends many rounds through its draw-by-draw path -- or
+    mcmc_diploid_kernel, four chains per warp; otherwise one warp per chain) against the host restatement of mcmc_clustering's
     restart loop on the same variants and generator states: assignments, likelihood and the generator state after the
     restarts must be identical, bit for bit (the generator state proves that every accept / reject went the same way)."""
     from jtk_b200 import pipeline as P
@@ -254,6 +256,9 @@ def test_device_mcmc_restarts_equal_the_host_twin(ctx):
             v = rng.normal(0, 1.5, (n, D))  # no structure: the chain wanders, many acceptances through exp()
         datas.append(v); ks.append(k); covs.append(n / k); states.append(P._rng_seed(1000 + 7 * c))
     restarts = 3
+    monkeypatch.setenv("JTK_MCMC_KERNEL", kernel.split("-")[0])
+    if kernel.endswith("window-6"): monkeypatch.setenv("JTK_MCMC_WINDOW", "6")
+    else: monkeypatch.delenv("JTK_MCMC_WINDOW", raising=False)
     asn, lk, err, st = ctx.mcmc_restarts(datas, ks, covs, np.array(states), restarts)
     assert (err == 0).all(), err
     for c in range(len(datas)):

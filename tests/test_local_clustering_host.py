@@ -125,6 +125,47 @@ def test_host_restarts_twin_is_deterministic_and_splits_two_haplotypes():
     assert (a == hap).all() or (a == 1 - hap).all()
 
 
+def test_speculative_schedule_equals_the_sequential_chain():
+    """The schedule of mcmc_speculative_kernel restated on the host (jtk_lc_mcmc_restarts_spec_host: up to four proposals of a
+    chain evaluated from the same state, earlier rejections replayed as their rounding round trips, commit up to the first
+    acceptance, draws parsed from a look-ahead ring) against the sequential twin of mcmc_clustering's restart loop
+    (pseudo_mcmc.rs:649-670,704-762): same assignments, likelihood and generator state, bit for bit -- on structured and
+    structure-free matrices, tiny and 255-read chains, with the full 32-draw window and with windows so small that many
+    rounds take the draw-by-draw path."""
+    import ctypes as C
+    from jtk_b200 import _lib, pipeline as P
+    L = _lib.lib()
+    vp = C.c_void_p
+    L.jtk_lc_mcmc_restarts_host.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, vp, C.POINTER(C.c_double)]
+    L.jtk_lc_mcmc_restarts_spec_host.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_double), vp]
+    rng = np.random.default_rng(17)
+    shapes = [(60, 6), (24, 1), (12, 5), (33, 2), (60, 6), (64, 7), (100, 8), (31, 2), (63, 4), (255, 8), (3, 1), (17, 3), (60, 6)]
+    slow_rounds = 0
+    for c, (n, D) in enumerate(shapes):
+        hap = rng.integers(0, 2, n)
+        sign = np.where(rng.random((2, D)) < 0.5, 1.0, -1.0)
+        v = sign[hap] * rng.normal(6, 2, (n, D))
+        v[rng.random((n, D)) < 0.15] = 0.0
+        if c in (4, 11):
+            v = rng.normal(0, 1.5, (n, D))  # no structure: many acceptances through exp()
+        v = np.ascontiguousarray(v)
+        st0 = P._rng_seed(1000 + 7 * c)
+        st = st0.copy(); asn = np.zeros(n, dtype=np.uint8); lk = C.c_double()
+        assert L.jtk_lc_mcmc_restarts_host(_lib._ptr(v), n, D, 2, n / 2, 2, _lib._ptr(st), _lib._ptr(asn), C.byref(lk)) == 0
+        for window in (32, 7, 3):
+            st2 = st0.copy(); asn2 = np.zeros(n, dtype=np.uint8); lk2 = C.c_double(); stats = np.zeros(3, dtype=np.uint64)
+            assert L.jtk_lc_mcmc_restarts_spec_host(_lib._ptr(v), n, D, n / 2, 2, window, _lib._ptr(st2), _lib._ptr(asn2), C.byref(lk2),
+                                                    _lib._ptr(stats)) == 0
+            assert np.array_equal(asn, asn2) and lk.value == lk2.value and np.array_equal(st, st2), (c, window)
+            assert stats[1] == 2 * 2000 * n and stats[0] <= stats[1]
+            if window == 32:
+                assert stats[2] == 0
+                if c == 0: assert stats[1] / stats[0] > 3.5      # a settled diploid chain commits almost four proposals per round
+            else:
+                slow_rounds += int(stats[2])
+    assert slow_rounds > 10000
+
+
 def _brute_exact(v, k):
     """Independent restatement of exact_clustering.rs:7-77 in plain Python (tiny sizes only)."""
     n, d = v.shape
