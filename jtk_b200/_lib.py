@@ -118,8 +118,36 @@ def _u8(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.uint8)
 
 
+class Packed:
+    """Byte sequences that are already one array: `cat` uint8 and `off` uint32[n + 1].  Behaves like the list of its pieces
+    (len, indexing, slices give views) and passes through `concat` without another 1e5-piece concatenate."""
+    __slots__ = ("cat", "off", "_o")
+
+    def __init__(self, cat: np.ndarray, off: np.ndarray):
+        self.cat = np.ascontiguousarray(cat, dtype=np.uint8)
+        self.off = np.ascontiguousarray(off, dtype=np.uint32)
+        self._o = self.off.tolist()
+
+    def __len__(self):
+        return len(self._o) - 1
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            o, c = self._o, self.cat
+            return [c[o[i]:o[i + 1]] for i in range(*k.indices(len(o) - 1))]
+        if k < 0:
+            k += len(self._o) - 1
+        return self.cat[self._o[k]:self._o[k + 1]]
+
+    def __iter__(self):
+        o, c = self._o, self.cat
+        return (c[o[i]:o[i + 1]] for i in range(len(o) - 1))
+
+
 def concat(seqs):
-    """list of uint8 arrays -> (concat uint8, offsets uint32[n+1]); a (concat, offsets) tuple passes through."""
+    """list of uint8 arrays -> (concat uint8, offsets uint32[n+1]); a Packed or a (concat, offsets) tuple passes through."""
+    if isinstance(seqs, Packed):
+        return seqs.cat, seqs.off
     if isinstance(seqs, tuple) and len(seqs) == 2 and isinstance(seqs[0], np.ndarray) and seqs[0].dtype == np.uint8:
         return np.ascontiguousarray(seqs[0]), np.ascontiguousarray(seqs[1], dtype=np.uint32)
     n = len(seqs)

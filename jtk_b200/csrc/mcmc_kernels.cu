@@ -664,84 +664,107 @@ __device__ __forceinline__ void st_release_smem(uint32_t *p, uint32_t v) {
     asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
 
-// The helper warp of one chain: commands in CTRL[2] = (sequence << 2) | type.
-__device__ __noinline__ void spec_helper(uint64_t *RING, uint32_t *FLAGS, uint64_t *SNAP, uint64_t *START, uint32_t *CTRL, uint32_t n, int lane) {
+// A helper warp: lane group q (4 lanes) runs the generator of chain 8h + q of the CTA.  The eight groups poll their chains'
+// control words and generate a block whenever one of them has room: the state update is the same instruction stream for
+// all of them (a chain that has no room computes and discards), so one block costs the warp what it cost for one chain.
+// Commands in CTRL[2] = (sequence << 2) | type; lane l of a group computes draws l, l + 4, l + 8 and l + 12 of a block.
+constexpr int kHelpLanes = 4, kHelpChains = 32 / kHelpLanes, kHelpDraws = kSpecBlock / kHelpLanes;
+struct SpecShared { uint64_t *RING, *SNAP, *START; uint32_t *FLAGS, *CTRL; };
+__device__ __forceinline__ SpecShared spec_shared(unsigned char *sm, const SpecLayout &L) {
+    SpecShared S;
+    S.RING = reinterpret_cast<uint64_t *>(sm + L.ring); S.SNAP = reinterpret_cast<uint64_t *>(sm + L.snap);
+    S.START = reinterpret_cast<uint64_t *>(sm + L.start); S.FLAGS = reinterpret_cast<uint32_t *>(sm + L.flags);
+    S.CTRL = reinterpret_cast<uint32_t *>(sm + L.ctrl);
+    return S;
+}
+__device__ __noinline__ void spec_helper(const SpecShared S, uint32_t n, bool valid, int lane) {
+    const int l8 = lane & (kHelpLanes - 1);
     const uint32_t r32 = n;
     const uint64_t zone = ((uint64_t)n << __clzll((long long)n)) - 1;
-    uint32_t seen = 0;
+    uint32_t seen = 0, gen = 0;
+    int phase = valid ? 0 : 2;             // 0 idle, 1 running, 2 done
+    DevRng rng{ 0, 0, 0, 0 };
     for (;;) {
-        uint32_t cmd;
-        do { cmd = ld_acquire_smem(CTRL + 2); } while (cmd == seen);
-        seen = cmd;
-        if ((cmd & 3u) == kCmdExit) return;
-        if ((cmd & 3u) != kCmdStart) continue;
-        DevRng rng{ START[0], START[1], START[2], START[3] };
-        uint32_t gen = 0;
-        for (;;) {
-            for (;;) { // room for another block, or a new command
-                cmd = ld_acquire_smem(CTRL + 2);
-                if (cmd != seen) break;
-                const uint32_t hp = ld_acquire_smem(CTRL + 1);
-                if (gen + kSpecBlock <= (hp & ~(uint32_t)(kSpecBlock - 1)) + kSpecRing) break;
+        if (phase != 2) {
+            const uint32_t cmd = ld_acquire_smem(S.CTRL + 2);
+            if (cmd != seen) {
+                if (phase == 1) { // stop (or exit) while running: leave the live state and how far it got, acknowledge
+                    if (l8 == 0) {
+                        S.START[0] = rng.s0; S.START[1] = rng.s1; S.START[2] = rng.s2; S.START[3] = rng.s3; S.CTRL[4] = gen;
+                        st_release_smem(S.CTRL + 3, cmd);
+                    }
+                    phase = 0;
+                }
+                seen = cmd;
+                if ((cmd & 3u) == kCmdStart) { rng.s0 = S.START[0]; rng.s1 = S.START[1]; rng.s2 = S.START[2]; rng.s3 = S.START[3]; gen = 0; phase = 1; }
+                else if ((cmd & 3u) == kCmdExit) phase = 2;
             }
-            if (cmd != seen) break;
-            if (lane < 4) SNAP[((gen / kSpecBlock) & (kSpecSnaps - 1)) * 4 + lane] = lane == 0 ? rng.s0 : lane == 1 ? rng.s1 : lane == 2 ? rng.s2 : rng.s3;
-            uint64_t mine = 0;
+        }
+        bool run = false;
+        if (phase == 1) {
+            const uint32_t hp = ld_acquire_smem(S.CTRL + 1);
+            run = gen + kSpecBlock <= (hp & ~(uint32_t)(kSpecBlock - 1)) + kSpecRing;
+        }
+        if (__all_sync(kFullMask, phase == 2)) return;
+        if (!__any_sync(kFullMask, run)) { __nanosleep(64); continue; }
+        if (run && l8 < 4) S.SNAP[((gen / kSpecBlock) & (kSpecSnaps - 1)) * 4 + l8] = l8 == 0 ? rng.s0 : l8 == 1 ? rng.s1 : l8 == 2 ? rng.s2 : rng.s3;
+        DevRng t = rng;
+        uint64_t mine[kHelpDraws];
 #pragma unroll
-            for (int i = 0; i < kSpecBlock; i++) {
-                if (lane == i) mine = rng.s1;
-                const uint64_t t = rng.s1 << 17;
-                rng.s2 ^= rng.s0; rng.s3 ^= rng.s1; rng.s1 ^= rng.s2; rng.s0 ^= rng.s3;
-                rng.s2 ^= t;
-                rng.s3 = DevRng::rotl(rng.s3, 45);
-            }
-            if (lane < kSpecBlock) {
-                const uint64_t v = DevRng::rotl(mine * 5, 7) * 9;
+        for (int i = 0; i < kHelpDraws; i++) mine[i] = 0;
+#pragma unroll
+        for (int i = 0; i < kSpecBlock; i++) {
+            if (l8 == (i & (kHelpLanes - 1))) mine[i / kHelpLanes] = t.s1;
+            const uint64_t sh = t.s1 << 17;
+            t.s2 ^= t.s0; t.s3 ^= t.s1; t.s1 ^= t.s2; t.s0 ^= t.s3;
+            t.s2 ^= sh;
+            t.s3 = DevRng::rotl(t.s3, 45);
+        }
+        if (run) {
+            rng = t;
+#pragma unroll
+            for (int h = 0; h < kHelpDraws; h++) {
+                const uint64_t v = DevRng::rotl(mine[h] * 5, 7) * 9;
                 const uint64_t t0 = (uint64_t)(uint32_t)v * r32;
                 const uint64_t u = (uint64_t)(uint32_t)(v >> 32) * r32 + (t0 >> 32);
                 const uint64_t lo = (u << 32) | (uint32_t)t0;
-                RING[(gen + lane) & (kSpecRing - 1)] = v;
-                FLAGS[(gen + lane) & (kSpecRing - 1)] = (uint32_t)(u >> 32) | (lo <= zone ? 0x100u : 0u) | (!(v >> 63) ? 0x200u : 0u);
+                const uint32_t at = (gen + kHelpLanes * h + l8) & (kSpecRing - 1);
+                S.RING[at] = v;
+                S.FLAGS[at] = (uint32_t)(u >> 32) | (lo <= zone ? 0x100u : 0u) | (!(v >> 63) ? 0x200u : 0u);
             }
             gen += kSpecBlock;
-            __syncwarp();
-            if (lane == 0) st_release_smem(CTRL, gen);
         }
-        // stopped: leave the live state and how far it got, acknowledge
-        if (lane == 0) { START[0] = rng.s0; START[1] = rng.s1; START[2] = rng.s2; START[3] = rng.s3; CTRL[4] = gen; st_release_smem(CTRL + 3, cmd); }
-        seen = cmd;
-        if ((cmd & 3u) == kCmdExit) return;
+        __syncwarp();
+        if (run && l8 == 0) st_release_smem(S.CTRL, gen);
     }
 }
 
 template <int DP>
-__global__ void __launch_bounds__(256, 2) mcmc_speculative_kernel(const McmcChain *__restrict__ chains, const int *__restrict__ ids,
+__global__ void __maxnreg__(112) mcmc_speculative_kernel(const McmcChain *__restrict__ chains, const int *__restrict__ ids,
                                                                   int n_ids, const double *__restrict__ wf64, uint64_t *rng_state,
                                                                   uint8_t *out_asn, const uint64_t *__restrict__ asn_off,
                                                                   double *out_lk, int *out_err, int restarts, int smem_per_chain,
-                                                                  int window) {
+                                                                  int win_arg, int n_eval) {
     extern __shared__ __align__(16) unsigned char mcmc_smem[];
-    const int n_pairs = blockDim.x >> 6;                      // warps 0..n_pairs-1 evaluate, warp n_pairs + w helps warp w
+    // warps 0..n_eval-1 evaluate one chain each; helper warp n_eval + h runs the generators of chains 8h..8h+7 (4 lanes each)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pair = warp % n_pairs;
-    const bool helper = warp >= n_pairs;
+    const bool helper = warp >= n_eval;
+    const int mine = helper ? kHelpChains * (warp - n_eval) + lane / kHelpLanes : warp;   // the chain of the CTA this lane works for
     const int g = lane & 7, grp = lane >> 3;
-    const int slot = blockIdx.x * n_pairs + pair;
-    const bool active = slot < n_ids;                         // (only the last CTA has idle pairs; they stay for the barrier)
+    const int slot = blockIdx.x * n_eval + mine;
+    const bool active = mine < n_eval && slot < n_ids;        // (idle evaluators / lane groups stay for the barrier)
     const int chain = ids[active ? slot : 0];
     const McmcChain ch = chains[chain];
     const uint32_t n = ch.n, D = ch.D;
-    unsigned char *sm = mcmc_smem + (size_t)pair * smem_per_chain;
+    unsigned char *sm = mcmc_smem + (size_t)(mine < n_eval ? mine : 0) * smem_per_chain;
     const SpecLayout L = spec_layout(n, DP);
-    uint64_t *RING = reinterpret_cast<uint64_t *>(sm + L.ring);
-    uint32_t *FLAGS = reinterpret_cast<uint32_t *>(sm + L.flags);
-    uint64_t *SNAP = reinterpret_cast<uint64_t *>(sm + L.snap);
-    uint64_t *START = reinterpret_cast<uint64_t *>(sm + L.start);
-    uint32_t *CTRL = reinterpret_cast<uint32_t *>(sm + L.ctrl);
-    if (!helper && lane < 8) CTRL[lane] = 0;                  // the control words of the pair, before its helper polls them
+    const SpecShared S = spec_shared(sm, L);
+    uint64_t *RING = S.RING, *SNAP = S.SNAP, *START = S.START;
+    uint32_t *FLAGS = S.FLAGS, *CTRL = S.CTRL;
+    if (!helper && lane < 8) CTRL[lane] = 0;                  // the control words of the chain, before its helper polls them
     __syncthreads();
+    if (helper) { spec_helper(S, n, active, lane); return; }
     if (!active) return;
-    if (helper) { spec_helper(RING, FLAGS, SNAP, START, CTRL, n, lane); return; }
     double *X = reinterpret_cast<double *>(sm + L.x);
     double *S2L = reinterpret_cast<double *>(sm + L.s2l);
     double *XCH = reinterpret_cast<double *>(sm + L.xch);
@@ -835,7 +858,10 @@ __global__ void __launch_bounds__(256, 2) mcmc_speculative_kernel(const McmcChai
         const uint64_t total = 2000ull * n;
         uint64_t t = 0;
         while (t < total) {
-            while (ld_acquire_smem(CTRL) - head < (uint32_t)window) { }
+            // the draws the helper has published: 24 are enough to go on (four proposals take 16.4 on average), 32 are looked at
+            uint32_t avail;
+            while ((avail = ld_acquire_smem(CTRL) - head) < (uint32_t)(win_arg < 24 ? win_arg : 24)) __nanosleep(20);
+            const int window = (int)avail < win_arg ? (int)avail : win_arg;
             // ---- lane L: a proposal that starts at draw head + L ends where? ----
             const uint32_t fl = FLAGS[(head + lane) & (kSpecRing - 1)];
             const uint32_t maskA = __ballot_sync(kFullMask, lane < window && (fl & 0x100u)), maskB = __ballot_sync(kFullMask, lane < window && (fl & 0x200u));
@@ -1020,20 +1046,25 @@ static cudaError_t launch_diploid(const McmcChain *chains, const int *ids, int n
     return cudaGetLastError();
 }
 
+constexpr int kSpecMaxEval = 14; // evaluator warps per CTA: 14 + 2 helpers = 16 warps x 112 registers fill the register file of an SM
+static int spec_chains_per_sm(size_t per_chain) { return (int)std::min<size_t>(kSpecMaxEval, (220 * 1024) / per_chain); }
 template <int DP>
 static cudaError_t launch_speculative(const McmcChain *chains, const int *ids, int n_ids, uint32_t n_max, const double *wf64, uint64_t *rng_state,
                                       uint8_t *out_asn, const uint64_t *asn_off, double *out_lk, int *out_err, int restarts, int window,
                                       cudaStream_t st) {
     const size_t per_chain = spec_layout(n_max, DP).total;
-    // few chains: one warp pair per CTA spreads them over the SMs (a warp alone on its scheduler has the lowest latency)
-    int pairs = n_ids > 2 * 148 ? 4 : n_ids > 148 ? 2 : 1;
-    while (pairs > 1 && (size_t)pairs * per_chain > 100 * 1024) pairs >>= 1; // two CTAs per SM when they fit
-    const size_t dyn = (size_t)pairs * per_chain;
-    if (dyn > 220 * 1024) return cudaErrorInvalidValue;
+    if (per_chain > 220 * 1024) return cudaErrorInvalidValue;
+    // few chains: small CTAs spread them over the SMs (an evaluator alone on its scheduler has the lowest latency)
+    int n_eval = n_ids > 8 * 148 ? kSpecMaxEval : n_ids > 4 * 148 ? 8 : n_ids > 2 * 148 ? 4 : n_ids > 148 ? 2 : 1;
+    n_eval = std::min(n_eval, spec_chains_per_sm(per_chain));
+    const size_t dyn = (size_t)n_eval * per_chain;
     cudaError_t e = cudaFuncSetAttribute(mcmc_speculative_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
-    mcmc_speculative_kernel<DP><<<(n_ids + pairs - 1) / pairs, pairs * 64, dyn, st>>>(chains, ids, n_ids, wf64, rng_state, out_asn, asn_off,
-                                                                                      out_lk, out_err, restarts, (int)per_chain, window);
+    e = cudaFuncSetAttribute(mcmc_speculative_kernel<DP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    const int warps = n_eval + (n_eval + kHelpChains - 1) / kHelpChains;
+    mcmc_speculative_kernel<DP><<<(n_ids + n_eval - 1) / n_eval, warps * 32, dyn, st>>>(chains, ids, n_ids, wf64, rng_state, out_asn, asn_off,
+                                                                                        out_lk, out_err, restarts, (int)per_chain, window, n_eval);
     return cudaGetLastError();
 }
 
@@ -1051,8 +1082,8 @@ cudaError_t launch_mcmc_restarts(const McmcChain *chains, const McmcChain *host_
                                  size_t smem_per_chain, cudaStream_t st) {
     if (n_chains <= 0) return cudaSuccess;
     // JTK_MCMC_KERNEL = auto (default) | speculative | subwarp: which kernel takes the two-cluster chains.  The speculative
-    // kernel holds 8 chains per SM (1 184 per wave) at 0.50 s per 20 restarts of 60 reads (0.86 s with all 8), the sub-warp
-    // kernel 32 per SM (4 736) at 1.4 s: auto takes the speculative kernel whenever the chains of a class fit one wave of it.
+    // kernel holds 14 chains per SM (2 072 per wave), the sub-warp kernel 32 per SM (4 736) at 1.4 s per 20 restarts of 60
+    // reads: auto takes the speculative kernel whenever the chains of a class fit one wave of it.
     // JTK_MCMC_WINDOW (tests) shrinks the draw window so that the draw-by-draw path runs.
     int variant = 2, window = 32;
     if (const char *v = std::getenv("JTK_MCMC_KERNEL")) variant = std::strcmp(v, "subwarp") == 0 ? 0 : std::strcmp(v, "speculative") == 0 ? 1 : 2;
@@ -1066,8 +1097,7 @@ cudaError_t launch_mcmc_restarts(const McmcChain *chains, const McmcChain *host_
             cudaError_t e = cudaSuccess;
             static const int widths[4] = { 2, 4, 6, 8 };
             const size_t spec_bytes = spec_layout(n_max, (uint32_t)widths[cls]).total;
-            const size_t spec_per_sm = std::min<size_t>(8, (220 * 1024) / spec_bytes);
-            if (variant == 1 || (variant == 2 && (size_t)cnt <= 148 * spec_per_sm)) { // speculative: one chain per warp pair
+            if (variant == 1 || (variant == 2 && cnt <= 148 * spec_chains_per_sm(spec_bytes))) { // speculative: one wave of it
                 switch (cls) {
                 case 0: e = launch_speculative<2>(chains, ids + at, cnt, n_max, wf64, rng_state, out_asn, asn_off, out_lk, out_err, restarts, window, st); break;
                 case 1: e = launch_speculative<4>(chains, ids + at, cnt, n_max, wf64, rng_state, out_asn, asn_off, out_lk, out_err, restarts, window, st); break;

@@ -198,8 +198,7 @@ def polish_chunks(models: PairHiddenMarkovModelOnStrands, drafts: Sequence, read
     off = np.zeros(n_pairs + 1, dtype=np.uint64)
     L.jtk_compact_runs.argtypes = [vp, vp, vp, C.c_int, vp]
     ctx._check(L.jtk_compact_runs(p(buf), p(pos), p(n_ops), n_pairs, p(off)))
-    compact = buf[:int(off[-1])].copy()
-    out_ops = np.split(compact, off[1:-1].astype(np.int64)) if n_pairs else []
+    out_ops = _lib.Packed(buf[:int(off[-1])].copy(), off.astype(np.uint32))   # behaves like the list of the per-read ops
     return out_cons, out_ops, iters
 
 

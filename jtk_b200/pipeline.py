@@ -482,7 +482,8 @@ def _pack_ops_chunk(ops_list):
 def _unpack_ops_chunk(packed):
     lens, b = packed
     flat = _unpack_ops((int(lens.sum()), b))
-    return np.split(flat, np.cumsum(lens)[:-1]) if len(lens) else []
+    ends = np.cumsum(lens).tolist()
+    return [flat[a:e] for a, e in zip([0] + ends[:-1], ends)]   # views (np.split costs 6x as much per piece)
 
 
 LAST_TIMING: Dict[str, float] = {}  # seconds spent in the phases of the last _cluster_pileups call (diagnostics)
@@ -496,19 +497,23 @@ def host_threads() -> int:
 
 
 GPU_MCMC_CAPACITY = 4736   # diploid chains one B200 runs side by side (148 SMs x 8 warps x 4 chains, mcmc_diploid_kernel)
-GPU_MCMC_HOST_S = 0.17     # seconds of one host thread per chunk (20 restarts x 2000 x 60 proposals, csrc/local_clustering.cpp)
+GPU_MCMC_HOST_S = 0.24     # seconds of one host thread per chunk (20 restarts x 2000 x 60 proposals: 0.18 s alone, 0.24 s with all cores busy)
+
+
+GPU_MCMC_SPEC_CAPACITY = 2072  # chains mcmc_speculative_kernel holds in one wave (148 SMs x 14 evaluator warps)
+_GPU_MCMC_LATENCY = ((296, 0.54), (592, 0.67), (1184, 0.78), (1872, 0.88), (2072, 0.90))
 
 
 def gpu_mcmc_seconds(n_chains: int) -> float:
-    """Measured latency of jtk_mcmc_restarts_batch for n diploid chains of 60 reads (profiles/r2_mcmc_speculative.txt):
-    the speculative kernel (one chain per warp pair, <= 1 184 chains) 0.50 s up to 4 chains per SM, 0.86 s at 8; beyond
-    that the sub-warp kernel (four chains per warp), 1.4 s for up to 4 736 chains."""
+    """Measured latency of jtk_mcmc_restarts_batch for n diploid chains of 60 reads x 20 restarts
+    (profiles/r2_mcmc_speculative.txt): the speculative kernel (one chain per evaluator warp, up to 2 072 chains a wave)
+    0.54 s with one or two chains per SM, 0.90 s with 14; beyond that the sub-warp kernel (four chains per warp), 1.4 s
+    for up to 4 736 chains."""
     if n_chains <= 0:
         return 0.0
-    if n_chains <= 592:
-        return 0.50
-    if n_chains <= 1184:
-        return 0.50 + 0.36 * (n_chains - 592) / 592
+    for cap, sec in _GPU_MCMC_LATENCY:
+        if n_chains <= cap:
+            return sec
     return 1.4 * -(-n_chains // GPU_MCMC_CAPACITY)
 
 
@@ -523,8 +528,8 @@ def gpu_mcmc_share(n_chunks: int) -> int:
     if mode == "1":
         return n_chunks
     threads = host_threads()
-    best, best_t = 0, n_chunks * GPU_MCMC_HOST_S / threads
-    for t_gpu in (1.4, 0.86, 0.74, 0.62, 0.50):       # (ties: the larger host share)
+    best, best_t = 0, -(-n_chunks // threads) * GPU_MCMC_HOST_S
+    for t_gpu in (1.4,) + tuple(sec for _, sec in reversed(_GPU_MCMC_LATENCY)):   # (ties: the larger host share)
         host = int(t_gpu / GPU_MCMC_HOST_S) * threads           # chunks the host threads finish in that time
         n_gpu = max(0, n_chunks - host)
         if n_gpu == 0:
@@ -555,6 +560,7 @@ def _cluster_pileups(ctx, hmm, gains: Gains, coverage: float, read_type: str, pi
         tidx = np.repeat(np.arange(len(cids), dtype=np.uint32), counts)
         # HMMPolishConfig::new(band_width / 2, seqs.len(), 3): every read of a chunk votes (mod.rs:105)
         t0 = time.perf_counter()
+        reads = _lib.Packed(*_lib.concat(reads))   # one concatenate of the 1e5 reads of a call, shared by the polish and table batches
         cons, new_ops, _ = polish_chunks(hmm, drafts, reads, ops, strands, tidx, HMMPolishConfig.new(radius, max(counts), 3), ctx=ctx)
         tm["polish"] += time.perf_counter() - t0
         first = np.concatenate([[0], np.cumsum(counts)])
@@ -571,9 +577,12 @@ def _cluster_pileups(ctx, hmm, gains: Gains, coverage: float, read_type: str, pi
         firsts: Dict[int, ClusteringResult] = {}
         if small:
             t0 = time.perf_counter()
-            sub_reads = [reads[k] for g in small for k in range(first[g], first[g + 1])]
-            sub_ops = [new_ops[k] for g in small for k in range(first[g], first[g + 1])]
-            sub_str = [strands[k] for g in small for k in range(first[g], first[g + 1])]
+            if len(small) == len(cids):              # (the usual call: every chunk) the packed arrays as they are
+                sub_reads, sub_ops, sub_str = reads, new_ops, strands
+            else:
+                sub_reads = [reads[k] for g in small for k in range(first[g], first[g + 1])]
+                sub_ops = [new_ops[k] for g in small for k in range(first[g], first[g + 1])]
+                sub_str = [strands[k] for g in small for k in range(first[g], first[g + 1])]
             sub_idx = np.repeat(np.arange(len(small), dtype=np.uint32), [counts[g] for g in small])
             b = ctx.batch([cons[g] for g in small], sub_reads, sub_ops, np.asarray(sub_str, dtype=np.uint8), sub_idx, radius)
             try:
@@ -620,6 +629,10 @@ def _cluster_pileups(ctx, hmm, gains: Gains, coverage: float, read_type: str, pi
         t0 = time.perf_counter()
         for g, c in enumerate(cids):
             sl = slice(first[g], first[g + 1])
+            r = firsts.get(g)
+            if r is not None and cfgs[g].copy_num < UPPER_COPY_NUM:   # clustered in the batch above: arrays as they are
+                res[c] = (cons[g], r.score, r.k, r.assignments, r.posterior, new_ops[sl])
+                continue
             state = _rng_seed(pile[c][1].id * 3490)
             asn, post, score, k = clustering_recursive(ctx, cons[g], reads[sl], new_ops[sl], strands[sl], state, hmm, cfgs[g],
                                                        first=firsts.get(g))

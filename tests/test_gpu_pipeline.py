@@ -93,7 +93,7 @@ def test_sharded_driver_equals_single_rank(ctx):
     assert set(merged) == set(whole)
     for cid in whole:
         a, b = whole[cid], merged[cid]
-        assert np.array_equal(a[0], b[0]) and a[1] == b[1] and a[2] == b[2] and a[3] == b[3]
+        assert np.array_equal(a[0], b[0]) and a[1] == b[1] and a[2] == b[2] and np.array_equal(np.asarray(a[3]), np.asarray(b[3]))
         assert np.array_equal(np.array(a[4]), np.array(b[4]))
 
 
