@@ -239,6 +239,10 @@ int jtk_polish_until_converge_batch(jtk_ctx *ctx, const jtk_hmm_params *fwd, con
  * front of buf, back to back; out_off[k] = new start of run k, out_off[n] = total bytes.  Turns the padded per-read ops slots
  * into one compact array. */
 int jtk_compact_runs(uint8_t *buf, const uint64_t *pos, const uint32_t *len, int n, uint64_t *out_off);
+/* Guide ops (0..3) at 2 bits per column, four per byte, lowest bits first: the form in which a rank's per-chunk results travel
+ * to rank 0 in the host gather.  pack2 writes (n_ops + 3) / 4 bytes; unpack2 needs room for 4 * ((n_ops + 3) / 4) bytes. */
+int jtk_ops_pack2(const uint8_t *ops, uint64_t n_ops, uint8_t *out);
+int jtk_ops_unpack2(const uint8_t *packed, uint64_t n_ops, uint8_t *out);
 /* per-column sums over the first take_num reads of every template of a batch (device reduction used by the
  * polish loop): out[stat_off[t] + e] = sum_r profile_r[e] */
 int jtk_batch_colsums(jtk_batch *b, int take_num, double *out, const uint64_t *stat_off);

@@ -1687,6 +1687,7 @@ int jtk_mcmc_restarts_batch(jtk_ctx *ctx, int n_chains, const double *data_conca
         return ctx->fail(JTK_EINVAL, "null argument");
     CU(cudaSetDevice(ctx->device), "cudaSetDevice");
     cudaStream_t st = ctx->stream;
+    const auto t_begin = std::chrono::steady_clock::now();
     std::vector<McmcChain> chains((size_t)n_chains);
     std::vector<uint64_t> asn_off((size_t)n_chains);
     size_t f64 = 0, u8 = 0, asn = 0, s2l = 0, smem = 0;
@@ -1746,6 +1747,10 @@ int jtk_mcmc_restarts_batch(jtk_ctx *ctx, int n_chains, const double *data_conca
     CU(cudaMemcpyAsync(out_lk, ctx->d_mc_lk.p, sizeof(double) * (size_t)n_chains, cudaMemcpyDeviceToHost, st), "D2H mcmc lk");
     CU(cudaMemcpyAsync(out_err, ctx->d_mc_err.p, sizeof(int) * (size_t)n_chains, cudaMemcpyDeviceToHost, st), "D2H mcmc status");
     CU(cudaStreamSynchronize(st), "mcmc execution");
+    if (std::getenv("JTK_MCMC_DEBUG"))
+        std::fprintf(stderr, "[jtk] mcmc_restarts: %d chains, classes (2,4,6,8 columns, general) = %d %d %d %d %d, %.3f s from upload to results\n",
+                     n_chains, class_count[0], class_count[1], class_count[2], class_count[3], class_count[4],
+                     std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count());
     return JTK_OK;
 }
 

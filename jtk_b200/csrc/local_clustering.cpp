@@ -1269,6 +1269,24 @@ void jtk_lc_size_to_lk(int n, double cov, int k, double *out) { // max_poisson_l
     for (int x = 0; x <= n; x++) out[x] = max_poisson_lk((size_t)x, cov, 1, (size_t)k);
 }
 
+// Independent per-chunk host work of the batch call below on a few threads (the first exception is rethrown on the caller).
+static void parallel_chunks(size_t n, const std::function<void(size_t)> &fn) {
+    unsigned hw = std::thread::hardware_concurrency();
+    if (const char *v = std::getenv("JTK_CLUSTER_THREADS")) { const int t = std::atoi(v); if (t > 0) hw = (unsigned)t; }
+    const size_t T = std::min<size_t>({ (size_t)(hw ? hw : 1), (size_t)8, (n + 63) / 64 });
+    if (T <= 1) { for (size_t i = 0; i < n; i++) fn(i); return; }
+    std::vector<std::thread> th;
+    std::vector<std::string> errs(T);
+    std::vector<char> failed(T, 0);
+    for (size_t t = 0; t < T; t++)
+        th.emplace_back([&, t]() {
+            try { for (size_t i = t; i < n; i += T) fn(i); }
+            catch (const std::exception &e) { errs[t] = e.what(); failed[t] = 1; }
+        });
+    for (auto &x : th) x.join();
+    for (size_t t = 0; t < T; t++) if (failed[t]) throw Panic(errs[t]);
+}
+
 // pseudo_mcmc::clustering after search_variants (clustering_variants_impl) for MANY chunks, with the k-means / MCMC
 // restarts of every chunk on the GPU (jtk_mcmc_restarts_batch): cluster_filtered_variants (:213-274) is walked level by
 // level -- all chunks that still try cluster number k run their 20 restarts side by side, then each decides on the host
@@ -1292,13 +1310,14 @@ int jtk_lc_clustering_variants_batch(jtk_ctx *ctx, int n_chunks, const double *v
             DevResult res;
         };
         std::vector<Job> jobs((size_t)n_chunks);
-        for (int g = 0; g < n_chunks; g++) {
+        parallel_chunks((size_t)n_chunks, [&](size_t gi) {
+            const int g = (int)gi;
             Job &j = jobs[(size_t)g];
             const size_t n = (size_t)n_reads[g], D = (size_t)n_probes[g];
             j.copy_num = (size_t)cfgs[g].copy_num; j.coverage = cfgs[g].coverage; j.per_cluster = cfgs[g].local_coverage;
             if (j.copy_num < 2) { // clustering (:86-88)
                 j.res = { std::vector<size_t>(n, 0), Mat(n, std::vector<double>(1, 0.0)), 0.0, 1 };
-                continue;
+                return;
             }
             const uint8_t *tmpl = tmpl_concat + tmpl_off[g];
             const size_t Lt = (size_t)(tmpl_off[g + 1] - tmpl_off[g]);
@@ -1313,14 +1332,14 @@ int jtk_lc_clustering_variants_batch(jtk_ctx *ctx, int n_chunks, const double *v
             // cluster_filtered_variants (:213-274), the part before the loop
             if (D == 0 || n <= j.copy_num) {
                 j.res = { std::vector<size_t>(n, 0), Mat(n, std::vector<double>(1, 0.0)), 0.0, 1 };
-                continue;
+                return;
             }
             j.assignments.assign(n, 0);
             j.prev_used.assign(D, false);
             j.end = std::min(j.copy_num, 1 + 2 * j.vt.size());
             j.k = std::max<size_t>(j.end, 5) - 3;
             j.active = j.k <= j.end;
-        }
+        });
         for (;;) { // one level: every active chunk runs the restarts for its current k
             std::vector<int> act;
             for (int g = 0; g < n_chunks; g++) if (jobs[(size_t)g].active) act.push_back(g);
@@ -1343,15 +1362,15 @@ int jtk_lc_clustering_variants_batch(jtk_ctx *ctx, int n_chunks, const double *v
             const int rc = jtk_mcmc_restarts_batch(ctx, (int)act.size(), data.data(), doff.data(), nr.data(), nc.data(), kk.data(),
                                                    s2l.data(), 20, rng.data(), asn.data(), lk.data(), err.data());
             if (rc) { g_lc_error = std::string("jtk_mcmc_restarts_batch: ") + jtk_last_error(ctx); return rc; }
-            size_t apos = 0;
-            for (size_t a = 0; a < act.size(); a++) {
+            std::vector<size_t> apos_of(act.size() + 1, 0);
+            for (size_t a = 0; a < act.size(); a++) apos_of[a + 1] = apos_of[a] + jobs[(size_t)act[a]].vars.size();
+            parallel_chunks(act.size(), [&](size_t a) {
                 Job &j = jobs[(size_t)act[a]];
-                const size_t n = j.vars.size();
+                const size_t n = j.vars.size(), apos = apos_of[a];
                 if (err[a] != 0) throw Panic("assertion failed on the device (mcmc status " + std::to_string(err[a]) + ")");
                 std::memcpy(states + 4 * (size_t)act[a], &rng[4 * a], 32);
                 std::vector<size_t> best(n);
                 for (size_t i = 0; i < n; i++) best[i] = asn[apos + i];
-                apos += n;
                 ClusterOut c = mcmc_finish(j.vars, j.k, j.coverage, best, lk[a]);
                 if (j.k == 2) {
                     ClusterOut h = use_highest_gain(j.vars);
@@ -1365,9 +1384,12 @@ int jtk_lc_clustering_variants_batch(jtk_ctx *ctx, int n_chunks, const double *v
                     j.active = j.k <= j.end;
                 } else j.active = false;
                 if (!j.active) j.res = { j.assignments, get_likelihood_gain(j.vars, j.assignments, j.max_k), j.mx, j.max_k };
-            }
+            });
         }
-        for (int g = 0; g < n_chunks; g++) { // clustering (:77-107): re-assignment to the best cluster, log-posteriors
+        for (int g = 0; g < n_chunks; g++)
+            if ((int)jobs[(size_t)g].res.k > post_stride) { g_lc_error = "post_stride smaller than the cluster number"; return JTK_EINVAL; }
+        parallel_chunks((size_t)n_chunks, [&](size_t gi) { // clustering (:77-107): re-assignment to the best cluster, log-posteriors
+            const int g = (int)gi;
             Job &j = jobs[(size_t)g];
             DevResult &r = j.res;
             if (j.copy_num >= 2) {
@@ -1379,13 +1401,12 @@ int jtk_lc_clustering_variants_batch(jtk_ctx *ctx, int n_chunks, const double *v
                 }
                 for (auto &xs : r.gains) { const double tot = logsumexp(xs); for (double &x : xs) x -= tot; }
             }
-            if ((int)r.k > post_stride) { g_lc_error = "post_stride smaller than the cluster number"; return JTK_EINVAL; }
             for (size_t i = 0; i < r.asn.size(); i++) {
                 out_asn_concat[asn_off[g] + i] = r.asn[i];
                 for (size_t c = 0; c < r.k; c++) out_post_concat[post_off[g] + i * (size_t)post_stride + c] = r.gains[i][c];
             }
             out_score[g] = r.score; out_k[g] = (int32_t)r.k;
-        }
+        });
         return JTK_OK;
     } catch (const std::exception &e) {
         g_lc_error = e.what();

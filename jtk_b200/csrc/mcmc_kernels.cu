@@ -1088,48 +1088,69 @@ cudaError_t launch_mcmc_restarts(const McmcChain *chains, const McmcChain *host_
     int variant = 2, window = 32;
     if (const char *v = std::getenv("JTK_MCMC_KERNEL")) variant = std::strcmp(v, "subwarp") == 0 ? 0 : std::strcmp(v, "speculative") == 0 ? 1 : 2;
     if (const char *v = std::getenv("JTK_MCMC_WINDOW")) { window = std::atoi(v); window = window < 3 ? 3 : window > 32 ? 32 : window; }
+    // One kernel per class.  A chain takes the same ~0.5-1.4 s whatever the size of its launch, so the classes of a mixed
+    // batch (chunks with 2, 4, 6 probes, some with three clusters) run side by side on their own streams, forked from and
+    // joined to the caller's stream by events.
+    int n_classes = 0;
+    for (int cls = 0; cls < 5; cls++) n_classes += class_count[cls] > 0 ? 1 : 0;
+    const bool fork = n_classes > 1;
+    cudaEvent_t ready = nullptr;
+    if (fork) {
+        cudaError_t e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+        e = cudaEventRecord(ready, st);
+        if (e != cudaSuccess) { cudaEventDestroy(ready); return e; }
+    }
+    cudaError_t result = cudaSuccess;
     int at = 0;
-    for (int cls = 0; cls < 4; cls++) {
+    for (int cls = 0; cls < 5 && result == cudaSuccess; cls++) {
         const int cnt = class_count[cls];
-        if (cnt > 0) {
+        if (cnt <= 0) continue;
+        cudaStream_t cs = st;
+        if (fork) {
+            result = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+            if (result != cudaSuccess) break;
+            result = cudaStreamWaitEvent(cs, ready, 0);
+        }
+        if (result == cudaSuccess && cls < 4) {
             uint32_t n_max = 0;
             for (int q = 0; q < cnt; q++) n_max = n_max > host_chains[host_ids[at + q]].n ? n_max : host_chains[host_ids[at + q]].n;
-            cudaError_t e = cudaSuccess;
             static const int widths[4] = { 2, 4, 6, 8 };
             const size_t spec_bytes = spec_layout(n_max, (uint32_t)widths[cls]).total;
-            if (variant == 1 || (variant == 2 && cnt <= 148 * spec_chains_per_sm(spec_bytes))) { // speculative: one wave of it
-                switch (cls) {
-                case 0: e = launch_speculative<2>(chains, ids + at, cnt, n_max, wf64, rng_state, out_asn, asn_off, out_lk, out_err, restarts, window, st); break;
-                case 1: e = launch_speculative<4>(chains, ids + at, cnt, n_max, wf64, rng_state, out_asn, asn_off, out_lk, out_err, restarts, window, st); break;
-                case 2: e = launch_speculative<6>(chains, ids + at, cnt, n_max, wf64, rng_state, out_asn, asn_off, out_lk, out_err, restarts, window, st); break;
-                default: e = launch_speculative<8>(chains, ids + at, cnt, n_max, wf64, rng_state, out_asn, asn_off, out_lk, out_err, restarts, window, st); break;
-                }
-                if (e != cudaSuccess) return e;
-                at += cnt;
-                continue;
-            }
+            const bool spec = variant == 1 || (variant == 2 && cnt <= 148 * spec_chains_per_sm(spec_bytes)); // one wave of it
+#define JTK_MCMC_LAUNCH(DPV)                                                                                                          \
+    (spec ? launch_speculative<DPV>(chains, ids + at, cnt, n_max, wf64, rng_state, out_asn, asn_off, out_lk, out_err, restarts, window, cs) \
+          : launch_diploid<DPV>(chains, ids + at, cnt, n_max, wf64, rng_state, out_asn, asn_off, out_lk, out_err, restarts, cs))
             switch (cls) {
-            case 0: e = launch_diploid<2>(chains, ids + at, cnt, n_max, wf64, rng_state, out_asn, asn_off, out_lk, out_err, restarts, st); break;
-            case 1: e = launch_diploid<4>(chains, ids + at, cnt, n_max, wf64, rng_state, out_asn, asn_off, out_lk, out_err, restarts, st); break;
-            case 2: e = launch_diploid<6>(chains, ids + at, cnt, n_max, wf64, rng_state, out_asn, asn_off, out_lk, out_err, restarts, st); break;
-            default: e = launch_diploid<8>(chains, ids + at, cnt, n_max, wf64, rng_state, out_asn, asn_off, out_lk, out_err, restarts, st); break;
+            case 0: result = JTK_MCMC_LAUNCH(2); break;
+            case 1: result = JTK_MCMC_LAUNCH(4); break;
+            case 2: result = JTK_MCMC_LAUNCH(6); break;
+            default: result = JTK_MCMC_LAUNCH(8); break;
             }
-            if (e != cudaSuccess) return e;
+#undef JTK_MCMC_LAUNCH
+        } else if (result == cudaSuccess) {
+            int warps = 4;
+            while (warps > 1 && warps * smem_per_chain > 200 * 1024) warps >>= 1;
+            const size_t dyn = warps * smem_per_chain;
+            result = cudaFuncSetAttribute(mcmc_restarts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            if (result == cudaSuccess) {
+                mcmc_restarts_kernel<<<(cnt + warps - 1) / warps, warps * 32, dyn, cs>>>(chains, ids + at, cnt, wf64, wu8, rng_state, out_asn, asn_off,
+                                                                                        out_lk, out_err, restarts, (int)smem_per_chain);
+                result = cudaGetLastError();
+            }
+        }
+        if (fork) { // join: the caller's stream waits for this class; the stream and the event are released when their work is done
+            cudaEvent_t done = nullptr;
+            if (result == cudaSuccess) result = cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
+            if (result == cudaSuccess) result = cudaEventRecord(done, cs);
+            if (result == cudaSuccess) result = cudaStreamWaitEvent(st, done, 0);
+            if (done) cudaEventDestroy(done);
+            cudaStreamDestroy(cs);
         }
         at += cnt;
     }
-    const int rest = class_count[4];
-    if (rest > 0) {
-        int warps = 4;
-        while (warps > 1 && warps * smem_per_chain > 200 * 1024) warps >>= 1;
-        const size_t dyn = warps * smem_per_chain;
-        cudaError_t e = cudaFuncSetAttribute(mcmc_restarts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        if (e != cudaSuccess) return e;
-        mcmc_restarts_kernel<<<(rest + warps - 1) / warps, warps * 32, dyn, st>>>(chains, ids + at, rest, wf64, wu8, rng_state, out_asn, asn_off,
-                                                                                   out_lk, out_err, restarts, (int)smem_per_chain);
-        return cudaGetLastError();
-    }
-    return cudaSuccess;
+    if (ready) cudaEventDestroy(ready);
+    return result;
 }
 
 } // namespace jtk

@@ -279,3 +279,33 @@ extern "C" int jtk_compact_runs(uint8_t *buf, const uint64_t *pos, const uint32_
     out_off[n] = w;
     return JTK_OK;
 }
+
+// Guide ops (values 0..3) at 2 bits per column, four per byte, lowest bits first -- the form in which the per-chunk results
+// of a rank travel to rank 0 (the reference's Node.cigar is run-length coded for the same reason).  n_ops ops in, (n_ops + 3) / 4
+// bytes out, and back.  `out` of jtk_ops_unpack2 needs room for 4 * ((n_ops + 3) / 4) bytes.
+extern "C" int jtk_ops_pack2(const uint8_t *ops, uint64_t n_ops, uint8_t *out) {
+    if (n_ops > 0 && (!ops || !out)) return JTK_EINVAL;
+    const uint64_t full = n_ops / 4;
+    for (uint64_t i = 0; i < full; i++) {
+        const uint8_t *o = ops + 4 * i;
+        out[i] = (uint8_t)((o[0] & 3) | ((o[1] & 3) << 2) | ((o[2] & 3) << 4) | ((o[3] & 3) << 6));
+    }
+    if (n_ops % 4) {
+        uint8_t b = 0;
+        for (uint64_t k = 0; k < n_ops % 4; k++) b |= (uint8_t)((ops[4 * full + k] & 3) << (2 * k));
+        out[full] = b;
+    }
+    return JTK_OK;
+}
+extern "C" int jtk_ops_unpack2(const uint8_t *packed, uint64_t n_ops, uint8_t *out) {
+    if (n_ops > 0 && (!packed || !out)) return JTK_EINVAL;
+    static uint32_t lut[256];
+    static bool ready = false;
+    if (!ready) { // (idempotent: two threads racing here write the same values)
+        for (uint32_t b = 0; b < 256; b++) lut[b] = (b & 3u) | (((b >> 2) & 3u) << 8) | (((b >> 4) & 3u) << 16) | (((b >> 6) & 3u) << 24);
+        ready = true;
+    }
+    const uint64_t bytes = (n_ops + 3) / 4;
+    for (uint64_t i = 0; i < bytes; i++) std::memcpy(out + 4 * i, &lut[packed[i]], 4);
+    return JTK_OK;
+}

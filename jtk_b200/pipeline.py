@@ -451,29 +451,39 @@ def local_clustering_selected(ds: DataSet, selection: Iterable[int], gains: Opti
     normalize_local_clustering(ds)
     LAST_TIMING.clear()
     LAST_TIMING.update(inner)
-    LAST_TIMING.update({"group_nodes": t_group, "gather_wait": max(0.0, t_run - sum(v for k, v in inner.items() if k != "gpu_mcmc_chunks")),
+    LAST_TIMING.update({"group_nodes": t_group, "gather_wait": max(0.0, t_run - sum(v for k, v in inner.items() if k not in ("gpu_mcmc_chunks", "mcmc_gpu_side", "mcmc_host_side"))),
                         "write_back": time.perf_counter() - t0})
     return out
 
 
 def _pack_ops(ops: np.ndarray):
-    """Guide ops (values 0..3) as 2 bits per column for the host gather: (column count, packed bytes)."""
-    o = np.asarray(ops, dtype=np.uint8)
-    pad = (-len(o)) % 4
-    q = np.concatenate([o, np.zeros(pad, dtype=np.uint8)]).reshape(-1, 4)
-    return len(o), (q[:, 0] | (q[:, 1] << 2) | (q[:, 2] << 4) | (q[:, 3] << 6)).astype(np.uint8)
-
-
-_UNPACK_LUT = (np.arange(256, dtype=np.uint32)[:, None] >> (2 * np.arange(4, dtype=np.uint32))[None, :] & 3).astype(np.uint8).view(np.uint32).ravel()
+    """Guide ops (values 0..3) as 2 bits per column for the host gather: (column count, packed bytes) -- jtk_ops_pack2."""
+    o = np.ascontiguousarray(ops, dtype=np.uint8)
+    out = np.empty((len(o) + 3) // 4, dtype=np.uint8)
+    L = _lib.lib()
+    L.jtk_ops_pack2.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    if L.jtk_ops_pack2(_lib._ptr(o), len(o), _lib._ptr(out)) != 0:
+        raise ValueError("jtk_ops_pack2")
+    return len(o), out
 
 
 def _unpack_ops(packed) -> np.ndarray:
     n, b = packed
-    return _UNPACK_LUT[b].view(np.uint8)[:n]   # one table look-up per packed byte: four ops at a time
+    b = np.ascontiguousarray(b, dtype=np.uint8)
+    if len(b) != (n + 3) // 4:
+        raise ValueError("packed ops: wrong length")
+    out = np.empty(4 * len(b), dtype=np.uint8)
+    L = _lib.lib()
+    L.jtk_ops_unpack2.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    if L.jtk_ops_unpack2(_lib._ptr(b), n, _lib._ptr(out)) != 0:
+        raise ValueError("jtk_ops_unpack2")
+    return out[:n]
 
 
 def _pack_ops_chunk(ops_list):
-    """All guide ops of one chunk in one packed array: (lengths int32[n], packed bytes) -- one numpy pass per chunk."""
+    """All guide ops of one chunk in one packed array: (lengths int32[n], packed bytes) -- one pass per chunk."""
+    if isinstance(ops_list, _lib.Packed):
+        raise TypeError("slice the Packed ops first")
     lens = np.fromiter((len(o) for o in ops_list), dtype=np.int32, count=len(ops_list))
     cat = np.concatenate(ops_list) if len(ops_list) else np.zeros(0, dtype=np.uint8)
     return lens, _pack_ops(cat)[1]
@@ -611,16 +621,20 @@ def _cluster_pileups(ctx, hmm, gains: Gains, coverage: float, read_type: str, pi
             host_part = [sg for sg in todo if sg[0] not in gpu_set]
 
             def gpu_side():
+                t_g = time.perf_counter()
                 jobs = []
                 for s, g in gpu_part:
                     d = int(n_probes[s])
                     jobs.append((variants[off[s]:off[s + 1], :d], probe_pos[s, :d], cons[g], cfgs[g],
                                  _rng_seed(pile[cids[g]][1].id * 3490)))
-                return _clustering_variants_batch_gpu(ctx, jobs)
+                out = _clustering_variants_batch_gpu(ctx, jobs)
+                tm["mcmc_gpu_side"] = tm.get("mcmc_gpu_side", 0.0) + time.perf_counter() - t_g
+                return out
             with ThreadPoolExecutor(max_workers=host_threads() + 1) as pool:
                 fut = pool.submit(gpu_side) if gpu_part else None
                 for g, r in pool.map(one, host_part):
                     firsts[g] = r
+                tm["mcmc_host_side"] = tm.get("mcmc_host_side", 0.0) + time.perf_counter() - t0
                 if fut is not None:
                     for (s, g), r in zip(gpu_part, fut.result()):
                         firsts[g] = r
