@@ -555,7 +555,9 @@ def main():
         h2d_bytes, d2h_bytes = step_e2e(ctx)
     barrier()
     t1 = time.perf_counter()
-    e2e_steps = max(10, args.steps // 2)  # at least 20 pipelined batches: the first encode cannot overlap anything
+    # at least 25 batches per mode (50 pipelined: ~0.4 s): the first encode cannot overlap anything, and with the MAX over the
+    # ranks one descheduled thread in a 0.15 s region of 8 ranks x 6 threads on 32 cores halves the figure (seen once at --steps 20)
+    e2e_steps = max(25, args.steps)
     for _ in range(e2e_steps):
         step_e2e(ctx)
     barrier()
@@ -567,7 +569,8 @@ def main():
     ctx2 = _lib.Context(local_rank)
     workers = [ctx, ctx2]
     with ThreadPoolExecutor(max_workers=2) as pool:
-        list(pool.map(step_e2e, workers))  # warm the second context
+        for _ in range(2):
+            list(pool.map(step_e2e, workers))  # warm the second context (its pools and pinned staging reach their size)
         barrier()
         t1 = time.perf_counter()
         futs = [pool.submit(step_e2e, workers[k % 2]) for k in range(2 * e2e_steps)]

@@ -860,7 +860,7 @@ __global__ void __maxnreg__(112) mcmc_speculative_kernel(const McmcChain *__rest
         while (t < total) {
             // the draws the helper has published: 24 are enough to go on (four proposals take 16.4 on average), 32 are looked at
             uint32_t avail;
-            while ((avail = ld_acquire_smem(CTRL) - head) < (uint32_t)(win_arg < 24 ? win_arg : 24)) __nanosleep(20);
+            while ((avail = ld_acquire_smem(CTRL) - head) < (uint32_t)(win_arg < 24 ? win_arg : 24)) __nanosleep(100); // (leave the issue slots to the helper)
             const int window = (int)avail < win_arg ? (int)avail : win_arg;
             // ---- lane L: a proposal that starts at draw head + L ends where? ----
             const uint32_t fl = FLAGS[(head + lane) & (kSpecRing - 1)];
@@ -872,21 +872,22 @@ __global__ void __maxnreg__(112) mcmc_speculative_kernel(const McmcChain *__rest
                 const uint32_t mb = (ma != 0u && a + 1 < 32) ? maskB >> (a + 1) : 0u;
                 const int b = a + __ffs((int)mb);
                 const uint32_t my_idx = __shfl_sync(kFullMask, fl & 0xffu, a & 31);
-                word = (mb != 0u && b + 1 < window) ? (my_idx | ((uint32_t)(b + 1) << 8) | 0x10000u) : 0u;
+                word = (mb != 0u && b + 1 < window) ? (my_idx | ((uint32_t)(b + 2) << 8) | 0x10000u) : 0u; // index | next start | valid
             }
             const int want = (int)(total - t < (uint64_t)kSpec ? total - t : (uint64_t)kSpec);
             int nvalid = 0, pc[kSpec];
             uint32_t idx[kSpec];
             {
-                bool alive = true; int p = 0;
+                uint32_t alive = 1u; int p = 0;
 #pragma unroll
                 for (int j = 0; j < kSpec; j++) {
-                    const uint32_t w = __shfl_sync(kFullMask, word, p & 31);
-                    alive = alive && j < want && p < window && (w & 0x10000u);
-                    idx[j] = alive ? (w & 0xffu) : 0u;
-                    pc[j] = alive ? (int)((w >> 8) & 0xffu) : 0;
-                    nvalid += alive ? 1 : 0;
-                    p = pc[j] + 1;
+                    uint32_t w = __shfl_sync(kFullMask, word, p & 31);
+                    alive &= (uint32_t)(j < want) & (uint32_t)(p < window) & (w >> 16);
+                    w = alive ? w : 0x100u;                  // (not valid: index 0, acceptance draw 0 -- reads nobody uses)
+                    idx[j] = w & 0xffu;
+                    p = (int)((w >> 8) & 0xffu);
+                    pc[j] = p - 1;
+                    nvalid += (int)alive;
                 }
             }
             if (nvalid == 0) { // the first proposal does not end inside the window: scan it draw by draw
@@ -985,13 +986,16 @@ __global__ void __maxnreg__(112) mcmc_speculative_kernel(const McmcChain *__rest
                 head += (uint32_t)pc_s + used_s;
                 t += (uint64_t)js + 1;
             } else {
-                tot0 = st0[1]; tot1 = st1[1];
+                if (nvalid == kSpec) { // (the usual round; nvalid is the same in every lane)
+                    tot0 = st0[kSpec]; tot1 = st1[kSpec];
+                    head += (uint32_t)pc[kSpec - 1] + 1u;
+                } else {
+                    tot0 = st0[1]; tot1 = st1[1];
+                    int pc_l = pc[0];
 #pragma unroll
-                for (int m = 2; m <= kSpec; m++) if (m == nvalid) { tot0 = st0[m]; tot1 = st1[m]; }
-                int pc_l = pc[0];
-#pragma unroll
-                for (int m = 1; m < kSpec; m++) if (m == nvalid - 1) pc_l = pc[m];
-                head += (uint32_t)pc_l + 1u;
+                    for (int m = 2; m < kSpec; m++) if (m == nvalid) { tot0 = st0[m]; tot1 = st1[m]; pc_l = pc[m - 1]; }
+                    head += (uint32_t)pc_l + 1u;
+                }
                 t += (uint64_t)nvalid;
             }
             if (lane == 0) st_relaxed_smem(CTRL + 1, head); // (every read of the ring fed a ballot of this round: they are done)

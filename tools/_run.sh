@@ -1,11 +1,7 @@
 mkdir -p gpurun_out
-timeout -s KILL 1500 python -m pytest tests -m gpu -q > gpurun_out/r2y_tests.log 2>&1; tail -3 gpurun_out/r2y_tests.log
-timeout -s KILL 900 python bench.py > gpurun_out/r2y_bench.json 2> gpurun_out/r2y_bench.err; tail -c 300 gpurun_out/r2y_bench.err
-timeout -s KILL 900 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r2y_bench_ref.json 2>> gpurun_out/r2y_bench.err
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r2y_bench.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ('value','ms_per_step','chunks_per_s','gpu_launches')}, 'e2e', d['e2e']['value'], 'roofline', d['roofline']['frac'], 'cpu', d['cpu_baseline']['value'], d['clocks'])
-print(d['extra']['chunks_phased']['phases_s'])
-r=json.loads(open('gpurun_out/r2y_bench_ref.json').read().strip().splitlines()[-1]); print('ref', r['value'], r['cpu_baseline'])
-PY
+timeout -s KILL 300 python -m pytest tests/test_gpu_clustering.py -k "mcmc" -x -q 2>&1 | tail -2
+for n in 250 1872 2072; do
+  echo "== speculative $n"; JTK_MCMC_KERNEL=speculative timeout -s KILL 120 python tools/mcmc_bench.py --chains $n --host 1 2>&1 | tail -2 | head -1
+done
+JTK_MCMC_DEBUG=1 JTK_CLUSTER_THREADS=4 timeout -s KILL 600 python tools/phase_scale.py --chunks 250 2>&1 | grep "jtk\]" | tail -1
+JTK_MCMC_DEBUG=1 timeout -s KILL 600 python tools/phase_scale.py --chunks 2000 2>&1 | tail -2
