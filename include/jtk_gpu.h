@@ -239,6 +239,9 @@ int jtk_polish_until_converge_batch(jtk_ctx *ctx, const jtk_hmm_params *fwd, con
  * front of buf, back to back; out_off[k] = new start of run k, out_off[n] = total bytes.  Turns the padded per-read ops slots
  * into one compact array. */
 int jtk_compact_runs(uint8_t *buf, const uint64_t *pos, const uint32_t *len, int n, uint64_t *out_off);
+/* The inverse: run k (src[src_off[k] .. src_off[k + 1])) is copied to buf + pos[k] -- fills the padded per-read ops slots of
+ * jtk_polish_until_converge_batch from one compact array, on a few host threads. */
+int jtk_scatter_runs(const uint8_t *src, const uint32_t *src_off, int n, uint8_t *buf, const uint64_t *pos);
 /* Guide ops (0..3) at 2 bits per column, four per byte, lowest bits first: the form in which a rank's per-chunk results travel
  * to rank 0 in the host gather.  pack2 writes (n_ops + 3) / 4 bytes; unpack2 needs room for 4 * ((n_ops + 3) / 4) bytes. */
 int jtk_ops_pack2(const uint8_t *ops, uint64_t n_ops, uint8_t *out);

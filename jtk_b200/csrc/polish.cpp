@@ -280,6 +280,23 @@ extern "C" int jtk_compact_runs(uint8_t *buf, const uint64_t *pos, const uint32_
     return JTK_OK;
 }
 
+// The inverse staging step: run k (src[src_off[k] .. src_off[k + 1])) is copied to buf + pos[k] (the padded per-read ops slots
+// of jtk_polish_until_converge_batch), on a few threads -- 1e5 reads x 2 KB per call; the gaps are left as they are.
+extern "C" int jtk_scatter_runs(const uint8_t *src, const uint32_t *src_off, int n, uint8_t *buf, const uint64_t *pos) {
+    if (n < 0 || (n > 0 && (!src || !src_off || !buf || !pos))) return JTK_EINVAL;
+    unsigned hw = std::thread::hardware_concurrency();
+    const int T = std::max(1, std::min({ (int)(hw ? hw : 1), 8, (n + 4095) / 4096 }));
+    auto work = [&](int t) {
+        const int lo = (int)((long long)n * t / T), hi = (int)((long long)n * (t + 1) / T);
+        for (int k = lo; k < hi; k++) std::memcpy(buf + pos[k], src + src_off[k], (size_t)(src_off[k + 1] - src_off[k]));
+    };
+    if (T == 1) { work(0); return JTK_OK; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++) th.emplace_back(work, t);
+    for (auto &x : th) x.join();
+    return JTK_OK;
+}
+
 // Guide ops (values 0..3) at 2 bits per column, four per byte, lowest bits first -- the form in which the per-chunk results
 // of a rank travel to rank 0 (the reference's Node.cigar is run-length coded for the same reason).  n_ops ops in, (n_ops + 3) / 4
 // bytes out, and back.  `out` of jtk_ops_unpack2 needs room for 4 * ((n_ops + 3) / 4) bytes.
