@@ -347,11 +347,11 @@ int jtk_mcmc_restarts_batch(jtk_ctx *ctx, int n_chains, const double *data_conca
 /* Host twin of one chain of jtk_mcmc_restarts_batch (parity tests) and the size_to_lk table both use. */
 int jtk_lc_mcmc_restarts_host(const double *data, int n, int D, int k, double cov, int restarts, uint64_t *state4,
                               uint8_t *out_asn, double *out_lk);
-/* Host twin of the speculative schedule of mcmc_speculative_kernel (two clusters; up to four proposals of one chain
+/* Host twin of the speculative schedule of mcmc_speculative_kernel (two clusters; up to `spec` = 4 or 8 proposals of one chain
  * evaluated side by side, committed up to the first acceptance): the results of jtk_lc_mcmc_restarts_host, bit for bit.
  * window = draws looked at per round (32 in the kernel; 3..31 makes rounds take the draw-by-draw path: tests).
  * out_stats (may be NULL) = { rounds, proposals, rounds that took the draw-by-draw path }. */
-int jtk_lc_mcmc_restarts_spec_host(const double *data, int n, int D, double cov, int restarts, int window, uint64_t *state4,
+int jtk_lc_mcmc_restarts_spec_host(const double *data, int n, int D, double cov, int restarts, int window, int spec, uint64_t *state4,
                                    uint8_t *out_asn, double *out_lk, uint64_t *out_stats);
 void jtk_lc_size_to_lk(int n, double cov, int k, double *out);
 /* jtk_lc_clustering_variants_rng for many chunks with the restarts of every chunk on the GPU: chunk g has n_reads[g] x

@@ -626,7 +626,7 @@ static void mcmc_restarts(const Mat &data, size_t k, double cov, Rng &rng, int r
 // so assignments, likelihoods and the generator state are the sequential chain's, bit for bit
 // (tests/test_local_clustering_host.py::test_speculative_schedule_equals_the_sequential_chain).
 struct SpecStats { uint64_t rounds = 0, proposals = 0, slow = 0; };
-constexpr int kSpec = 4, kSpecRing = 64, kSpecBlock = 16;
+constexpr int kSpec = 8, kSpecRing = 64, kSpecBlock = 16; // kSpec: the widest round (the kernel runs 4 or 8 proposals side by side)
 struct SpecStream { // draws generated ahead in blocks of kSpecBlock; snapshots of the generator at the last four block starts
     Rng &rng;
     uint64_t ring[kSpecRing];
@@ -647,7 +647,7 @@ struct SpecStream { // draws generated ahead in blocks of kSpecBlock; snapshots 
         gen = head;
     }
 };
-static double mcmc_with_filter_spec2(const Mat &data, std::vector<size_t> &assign, double cov, Rng &rng, SpecStats &stats, int kSpecWindow) {
+static double mcmc_with_filter_spec2(const Mat &data, std::vector<size_t> &assign, double cov, Rng &rng, SpecStats &stats, int kSpecWindow, int spec) {
     const size_t n = data.size(), D = n ? data[0].size() : 0;
     std::vector<double> s2l;
     for (size_t x = 0; x <= n; x++) s2l.push_back(max_poisson_lk(x, cov, 1, 2));
@@ -702,7 +702,7 @@ static double mcmc_with_filter_spec2(const Mat &data, std::vector<size_t> &assig
             if ((uint64_t)m <= zone) maskA |= 1u << L;
             if (!(v >> 63)) maskB |= 1u << L;
         }
-        const int want = (int)std::min<uint64_t>(kSpec, total - t);
+        const int want = (int)std::min<uint64_t>((uint64_t)spec, total - t);
         int nvalid = 0, pos_idx[kSpec], pos_acc[kSpec];
         for (int j = 0, p = 0; j < want; j++) {
             if (p >= kSpecWindow) break;
@@ -794,12 +794,12 @@ static double mcmc_with_filter_spec2(const Mat &data, std::vector<size_t> &assig
     JTK_ASSERT(std::fabs(mx - chk) < 0.0001, "(max - lk).abs() < 0.0001");
     return mx;
 }
-static void mcmc_restarts_spec2(const Mat &data, double cov, Rng &rng, int restarts, std::vector<size_t> &best, double &best_lk, SpecStats &stats, int window) {
+static void mcmc_restarts_spec2(const Mat &data, double cov, Rng &rng, int restarts, std::vector<size_t> &best, double &best_lk, SpecStats &stats, int window, int spec) {
     bool any = false;
     best.clear(); best_lk = 0;
     for (int t = 0; t < restarts; t++) {
         std::vector<size_t> asn = kmeans(data, 2, rng);
-        const double lk = mcmc_with_filter_spec2(data, asn, cov, rng, stats, window);
+        const double lk = mcmc_with_filter_spec2(data, asn, cov, rng, stats, window, spec);
         if (!any || !(lk < best_lk)) { best = asn; best_lk = lk; any = true; }
     }
 }
@@ -1247,17 +1247,17 @@ int jtk_lc_mcmc_restarts_host(const double *data, int n, int D, int k, double co
 }
 // Host twin of the speculative schedule of mcmc_speculative_kernel (two clusters): the same results as
 // jtk_lc_mcmc_restarts_host; out_stats = { rounds, proposals, slow-path rounds } (proposals / rounds = the speed-up of a round)
-int jtk_lc_mcmc_restarts_spec_host(const double *data, int n, int D, double cov, int restarts, int window, uint64_t *state4,
+int jtk_lc_mcmc_restarts_spec_host(const double *data, int n, int D, double cov, int restarts, int window, int spec, uint64_t *state4,
                                    uint8_t *out_asn, double *out_lk, uint64_t *out_stats) {
     try {
-        if (!data || !state4 || !out_asn || !out_lk || n < 1 || D < 1 || window < 3 || window > 32) { g_lc_error = "bad argument"; return JTK_EINVAL; }
+        if (!data || !state4 || !out_asn || !out_lk || n < 1 || D < 1 || window < 3 || window > 32 || spec < 1 || spec > kSpec) { g_lc_error = "bad argument"; return JTK_EINVAL; }
         Mat m((size_t)n);
         for (int i = 0; i < n; i++) m[(size_t)i].assign(data + (size_t)i * D, data + (size_t)(i + 1) * D);
         Rng rng(0);
         std::memcpy(rng.s, state4, 32);
         std::vector<size_t> best; double best_lk = 0;
         SpecStats stats;
-        mcmc_restarts_spec2(m, cov, rng, restarts, best, best_lk, stats, window);
+        mcmc_restarts_spec2(m, cov, rng, restarts, best, best_lk, stats, window, spec);
         std::memcpy(state4, rng.s, 32);
         for (int i = 0; i < n; i++) out_asn[i] = (uint8_t)best[(size_t)i];
         *out_lk = best_lk;

@@ -624,7 +624,11 @@ __global__ void __launch_bounds__(128, 2) mcmc_diploid_kernel(const McmcChain *_
 // chain there; this kernel is checked against the sequential host twin (tests/test_gpu_clustering.py).  A window that
 // does not hold one whole proposal (never at 32 draws; forced by a small `window` in the tests) is scanned draw by draw.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSpec = 4, kSpecRing = 128, kSpecBlock = 16, kSpecSnaps = kSpecRing / kSpecBlock;
+#ifndef JTK_SPEC_NARROW
+#define JTK_SPEC_NARROW 0
+#endif
+constexpr bool kSpecNarrow = JTK_SPEC_NARROW != 0; // eight proposals per round for chains of <= 4 columns (measured: see DESIGN 3.4)
+constexpr int kSpecMax = 8, kSpecRing = 128, kSpecBlock = 16, kSpecSnaps = kSpecRing / kSpecBlock;
 enum { kCmdStart = 1, kCmdStop = 2, kCmdExit = 3 };
 struct SpecLayout { uint32_t x, cl, s2l, ratio, assign, argmax, best, xch, centers, dists, cum, counts, ring, flags, snap, start, ctrl, total, rwords; };
 __host__ __device__ inline SpecLayout spec_layout(uint32_t n, uint32_t DP) {
@@ -634,7 +638,7 @@ __host__ __device__ inline SpecLayout spec_layout(uint32_t n, uint32_t DP) {
     L.rwords = (n + 1 + 31) / 32;
     L.x = take(8u * (n + 1) * DP);            // one spare row: lanes past the last column read (and ignore) the next entries
     L.s2l = take(8u * (n + 1));
-    L.xch = take(8u * 2 * kSpec * 2 * DP);
+    L.xch = take(8u * 2 * kSpecMax * 2 * DP);
     L.ring = take(8u * kSpecRing);
     L.flags = take(4u * kSpecRing);
     L.snap = take(32u * kSpecSnaps);
@@ -750,7 +754,10 @@ __global__ void __maxnreg__(112) mcmc_speculative_kernel(const McmcChain *__rest
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool helper = warp >= n_eval;
     const int mine = helper ? kHelpChains * (warp - n_eval) + lane / kHelpLanes : warp;   // the chain of the CTA this lane works for
-    const int g = lane & 7, grp = lane >> 3;
+    // SPEC proposals side by side on groups of GL lanes: eight 4-lane groups for chains of <= 4 columns (they accept 10-20 % of
+    // their proposals once settled: 4.0 of 8 commit per round where 3.0 of 4 did), four 8-lane groups otherwise
+    constexpr int SPEC = (kSpecNarrow && DP <= 4) ? 8 : 4, GL = 32 / SPEC;
+    const int g = lane & (GL - 1), grp = lane / GL;
     const int slot = blockIdx.x * n_eval + mine;
     const bool active = mine < n_eval && slot < n_ids;        // (idle evaluators / lane groups stay for the barrier)
     const int chain = ids[active ? slot : 0];
@@ -824,7 +831,7 @@ __global__ void __maxnreg__(112) mcmc_speculative_kernel(const McmcChain *__rest
         const uint32_t in_use = (pos0 ? p0 : 0u) + (pos1 ? p1 : 0u);
         const uint32_t in_neg = ((a0 <= 0.0) ? p0 : 0u) + ((a1 <= 0.0) ? p1 : 0u);
         const bool use = col && u != 0u && 2u * in_neg < in_use; // the reference compares the same integers as f64
-        double *T = XCH + (buf * kSpec + grp) * (2 * DP);
+        double *T = XCH + (buf * SPEC + grp) * (2 * DP);
         buf ^= 1u;
         if (pub) {
             T[g] = use ? (a0 < 0.0 ? 0.0 : a0) : 0.0;
@@ -874,19 +881,18 @@ __global__ void __maxnreg__(112) mcmc_speculative_kernel(const McmcChain *__rest
                 const uint32_t my_idx = __shfl_sync(kFullMask, fl & 0xffu, a & 31);
                 word = (mb != 0u && b + 1 < window) ? (my_idx | ((uint32_t)(b + 2) << 8) | 0x10000u) : 0u; // index | next start | valid
             }
-            const int want = (int)(total - t < (uint64_t)kSpec ? total - t : (uint64_t)kSpec);
-            int nvalid = 0, pc[kSpec];
-            uint32_t idx[kSpec];
+            const int want = (int)(total - t < (uint64_t)SPEC ? total - t : (uint64_t)SPEC);
+            int nvalid = 0;
+            uint32_t info[SPEC];                                 // per proposal: read index | (acceptance draw + 1) << 8
             {
                 uint32_t alive = 1u; int p = 0;
 #pragma unroll
-                for (int j = 0; j < kSpec; j++) {
+                for (int j = 0; j < SPEC; j++) {
                     uint32_t w = __shfl_sync(kFullMask, word, p & 31);
                     alive &= (uint32_t)(j < want) & (uint32_t)(p < window) & (w >> 16);
                     w = alive ? w : 0x100u;                  // (not valid: index 0, acceptance draw 0 -- reads nobody uses)
-                    idx[j] = w & 0xffu;
+                    info[j] = w & 0xffffu;
                     p = (int)((w >> 8) & 0xffu);
-                    pc[j] = p - 1;
                     nvalid += (int)alive;
                 }
             }
@@ -909,25 +915,27 @@ __global__ void __maxnreg__(112) mcmc_speculative_kernel(const McmcChain *__rest
                 while (ld_acquire_smem(CTRL) == head) { }
                 nvalid = 1;
 #pragma unroll
-                for (int j = 0; j < kSpec; j++) { idx[j] = hi; pc[j] = 0; }
+                for (int j = 0; j < SPEC; j++) info[j] = hi | 0x100u;
             }
-            // ---- states: every lane replays the round trips of the four proposals on its column; group j keeps state j ----
-            double st0[kSpec + 1], st1[kSpec + 1];
-            double s_own = 0.0; uint32_t cl_own = 0, old_own = 0, old_all[kSpec];
-            st0[0] = tot0; st1[0] = tot1;
+            // ---- this group's proposal ----
+            uint32_t my = info[0];
 #pragma unroll
-            for (int m = 0; m < kSpec; m++) {
-                const uint32_t old = c.assign[idx[m]];
-                const double x = X[idx[m] * DP + gg];
-                const double s = old == 0u ? -x : x;
-                old_all[m] = old;
-                if (m == grp) { s_own = s; cl_own = CL[idx[m] * DP + gg]; old_own = old; }
-                st0[m + 1] = __dadd_rn(__dadd_rn(st0[m], s), -s);
-                st1[m + 1] = __dadd_rn(__dadd_rn(st1[m], -s), s);
+            for (int m = 1; m < SPEC; m++) if (m == grp) my = info[m];
+            const uint32_t idx_own = my & 0xffu;
+            const int pc_own = (int)(my >> 8) - 1;
+            const uint32_t old_own = c.assign[idx_own], cl_own = CL[idx_own * DP + gg];
+            // ---- states: every lane replays the round trips of the proposals on its column; group j starts from state j ----
+            double a0 = tot0, a1 = tot1, b0 = tot0, b1 = tot1, e0 = tot0, e1 = tot1, s_own = 0.0;
+#pragma unroll
+            for (int m = 0; m < SPEC; m++) {
+                const uint32_t im = info[m] & 0xffu;
+                const double x = X[im * DP + gg];
+                const double s = c.assign[im] == 0u ? -x : x;
+                if (m == grp) { b0 = a0; b1 = a1; s_own = s; }
+                a0 = __dadd_rn(__dadd_rn(a0, s), -s);
+                a1 = __dadd_rn(__dadd_rn(a1, -s), s);
+                if (m + 1 == nvalid) { e0 = a0; e1 = a1; }
             }
-            double b0 = st0[0], b1 = st1[0];
-#pragma unroll
-            for (int m = 1; m < kSpec; m++) if (m == grp) { b0 = st0[m]; b1 = st1[m]; }
             // ---- proposal grp: flip (:764-783), get_lk, acceptance ----
             const int dp = old_own == 0u ? -(int)(cl_own & 1u) : (int)(cl_own & 1u);
             const int dn = old_own == 0u ? -(int)(cl_own >> 1) : (int)(cl_own >> 1);
@@ -936,9 +944,6 @@ __global__ void __maxnreg__(112) mcmc_speculative_kernel(const McmcChain *__rest
             const uint32_t P0 = np0 + dp, P1 = np1 - dp, Q0 = nn0 + dn, Q1 = nn1 - dn, K0 = c0 + dc, K1 = c1 - dc;
             const double proposed = group_lk(f0, f1, P0, P1, Q0, Q1, K0, K1);
             const double diff = __dsub_rn(proposed, lk);
-            int pc_own = pc[0];
-#pragma unroll
-            for (int m = 1; m < kSpec; m++) if (m == grp) pc_own = pc[m];
             bool accept = false, bad = false;
             uint32_t used = 1;
             if (0.0 < diff) { accept = true; used = 0; }
@@ -965,17 +970,16 @@ __global__ void __maxnreg__(112) mcmc_speculative_kernel(const McmcChain *__rest
             const uint32_t accmask = __ballot_sync(kFullMask, accept && grp < nvalid);
             if (accmask) {
                 const int src = __ffs((int)accmask) - 1;   // first lane of the first accepting group (its lanes agree)
-                const int js = src >> 3;
+                const int js = src / GL;
                 if (__shfl_sync(kFullMask, (int)bad, src)) { err = kMcmcBadProb; break; }
-                tot0 = shfl_f64(f0, js * 8 + g); tot1 = shfl_f64(f1, js * 8 + g);
-                np0 = __shfl_sync(kFullMask, P0, js * 8 + g); np1 = __shfl_sync(kFullMask, P1, js * 8 + g);
-                nn0 = __shfl_sync(kFullMask, Q0, js * 8 + g); nn1 = __shfl_sync(kFullMask, Q1, js * 8 + g);
+                tot0 = shfl_f64(f0, js * GL + g); tot1 = shfl_f64(f1, js * GL + g);
+                np0 = __shfl_sync(kFullMask, P0, js * GL + g); np1 = __shfl_sync(kFullMask, P1, js * GL + g);
+                nn0 = __shfl_sync(kFullMask, Q0, js * GL + g); nn1 = __shfl_sync(kFullMask, Q1, js * GL + g);
                 c0 = __shfl_sync(kFullMask, K0, src); c1 = __shfl_sync(kFullMask, K1, src);
                 lk = shfl_f64(proposed, src);
                 const uint32_t used_s = __shfl_sync(kFullMask, used, src);
-                uint32_t idx_s = idx[0], old_s = old_all[0]; int pc_s = pc[0];
-#pragma unroll
-                for (int m = 1; m < kSpec; m++) if (m == js) { idx_s = idx[m]; old_s = old_all[m]; pc_s = pc[m]; }
+                const uint32_t idx_s = __shfl_sync(kFullMask, idx_own, src), old_s = __shfl_sync(kFullMask, old_own, src);
+                const int pc_s = __shfl_sync(kFullMask, pc_own, src);
                 __syncwarp();                                  // every lane has read assign[] for this round
                 if (lane == 0) c.assign[idx_s] = (uint8_t)(1u - old_s);
                 __syncwarp();
@@ -986,16 +990,14 @@ __global__ void __maxnreg__(112) mcmc_speculative_kernel(const McmcChain *__rest
                 head += (uint32_t)pc_s + used_s;
                 t += (uint64_t)js + 1;
             } else {
-                if (nvalid == kSpec) { // (the usual round; nvalid is the same in every lane)
-                    tot0 = st0[kSpec]; tot1 = st1[kSpec];
-                    head += (uint32_t)pc[kSpec - 1] + 1u;
-                } else {
-                    tot0 = st0[1]; tot1 = st1[1];
-                    int pc_l = pc[0];
+                tot0 = e0; tot1 = e1;
+                uint32_t last = info[SPEC - 1];                // (the usual round: every proposal of the round was valid)
+                if (nvalid != SPEC) {
+                    last = info[0];
 #pragma unroll
-                    for (int m = 2; m < kSpec; m++) if (m == nvalid) { tot0 = st0[m]; tot1 = st1[m]; pc_l = pc[m - 1]; }
-                    head += (uint32_t)pc_l + 1u;
+                    for (int m = 1; m < SPEC - 1; m++) if (m == nvalid - 1) last = info[m];
                 }
+                head += last >> 8;                             // behind the acceptance draw of the last proposal
                 t += (uint64_t)nvalid;
             }
             if (lane == 0) st_relaxed_smem(CTRL + 1, head); // (every read of the ring fed a ballot of this round: they are done)

@@ -511,14 +511,15 @@ GPU_MCMC_HOST_S = 0.24     # seconds of one host thread per chunk (20 restarts x
 
 
 GPU_MCMC_SPEC_CAPACITY = 2072  # chains mcmc_speculative_kernel holds in one wave (148 SMs x 14 evaluator warps)
-_GPU_MCMC_LATENCY = ((296, 0.54), (592, 0.67), (1184, 0.78), (1872, 0.88), (2072, 0.90))
+_GPU_MCMC_LATENCY = ((296, 0.60), (592, 0.70), (1184, 0.85), (2072, 1.00))
 
 
 def gpu_mcmc_seconds(n_chains: int) -> float:
-    """Measured latency of jtk_mcmc_restarts_batch for n diploid chains of 60 reads x 20 restarts
-    (profiles/r2_mcmc_speculative.txt): the speculative kernel (one chain per evaluator warp, up to 2 072 chains a wave)
-    0.54 s with one or two chains per SM, 0.90 s with 14; beyond that the sub-warp kernel (four chains per warp), 1.4 s
-    for up to 4 736 chains."""
+    """Latency of jtk_mcmc_restarts_batch for n diploid chains of 60 reads x 20 restarts, as the share model uses it: the
+    speculative kernel (one chain per evaluator warp, up to 2 072 chains a wave) takes 0.46 s (up to 2 chains per SM) to
+    0.82 s (14 per SM) on settled six-column chains (profiles/r2_mcmc_speculative.txt) and 0.64 to 1.03 s on the one- and
+    two-column chains of the bench's chunks (they accept more proposals: fewer commit per round); beyond one wave the
+    sub-warp kernel (four chains per warp), 1.4 s for up to 4 736 chains."""
     if n_chains <= 0:
         return 0.0
     for cap, sec in _GPU_MCMC_LATENCY:

@@ -137,7 +137,7 @@ def test_speculative_schedule_equals_the_sequential_chain():
     L = _lib.lib()
     vp = C.c_void_p
     L.jtk_lc_mcmc_restarts_host.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, vp, C.POINTER(C.c_double)]
-    L.jtk_lc_mcmc_restarts_spec_host.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_double), vp]
+    L.jtk_lc_mcmc_restarts_spec_host.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_double), vp]
     rng = np.random.default_rng(17)
     shapes = [(60, 6), (24, 1), (12, 5), (33, 2), (60, 6), (64, 7), (100, 8), (31, 2), (63, 4), (255, 8), (3, 1), (17, 3), (60, 6)]
     slow_rounds = 0
@@ -152,15 +152,16 @@ def test_speculative_schedule_equals_the_sequential_chain():
         st0 = P._rng_seed(1000 + 7 * c)
         st = st0.copy(); asn = np.zeros(n, dtype=np.uint8); lk = C.c_double()
         assert L.jtk_lc_mcmc_restarts_host(_lib._ptr(v), n, D, 2, n / 2, 2, _lib._ptr(st), _lib._ptr(asn), C.byref(lk)) == 0
-        for window in (32, 7, 3):
+        for window, spec in ((32, 4), (32, 8), (7, 4), (3, 8)):
             st2 = st0.copy(); asn2 = np.zeros(n, dtype=np.uint8); lk2 = C.c_double(); stats = np.zeros(3, dtype=np.uint64)
-            assert L.jtk_lc_mcmc_restarts_spec_host(_lib._ptr(v), n, D, n / 2, 2, window, _lib._ptr(st2), _lib._ptr(asn2), C.byref(lk2),
-                                                    _lib._ptr(stats)) == 0
-            assert np.array_equal(asn, asn2) and lk.value == lk2.value and np.array_equal(st, st2), (c, window)
+            assert L.jtk_lc_mcmc_restarts_spec_host(_lib._ptr(v), n, D, n / 2, 2, window, spec, _lib._ptr(st2), _lib._ptr(asn2),
+                                                    C.byref(lk2), _lib._ptr(stats)) == 0
+            assert np.array_equal(asn, asn2) and lk.value == lk2.value and np.array_equal(st, st2), (c, window, spec)
             assert stats[1] == 2 * 2000 * n and stats[0] <= stats[1]
             if window == 32:
                 assert stats[2] == 0
-                if c == 0: assert stats[1] / stats[0] > 3.5      # a settled diploid chain commits almost four proposals per round
+                if c == 0 and spec == 4: assert stats[1] / stats[0] > 3.5      # a settled diploid chain commits almost four of four
+                if c == 0 and spec == 8: assert stats[1] / stats[0] > 6.0      # ... and most of eight (they have to fit 32 draws)
             else:
                 slow_rounds += int(stats[2])
     assert slow_rounds > 10000
