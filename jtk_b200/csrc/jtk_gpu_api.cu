@@ -1211,9 +1211,12 @@ int batch_run(jtk_batch *b, const jtk_hmm_params *fwd, const jtk_hmm_params *rev
             ctx->launches += 2;
         } else if (table) {
             // persistent CTAs: one wave of resident CTAs pulls pairs from the queue
-            const int gf = std::min(ctas, ctx->sm_count * fwdrows_ctas_per_sm(b->C));
+            int cap_f = fwdrows_ctas_per_sm(b->C), cap_b = modtable_ctas_per_sm(b->C, rows);
+            if (const char *v = std::getenv("JTK_GRID_FWD")) cap_f = std::max(1, std::min(cap_f, std::atoi(v))); // (tuning: CTAs per SM)
+            if (const char *v = std::getenv("JTK_GRID_BWD")) cap_b = std::max(1, std::min(cap_b, std::atoi(v)));
+            const int gf = std::min(ctas, ctx->sm_count * cap_f);
             const int wpb = modtable_warps_per_cta(b->C);
-            const int gb = std::min((hi - lo + wpb - 1) / wpb, ctx->sm_count * modtable_ctas_per_sm(b->C, rows));
+            const int gb = std::min((hi - lo + wpb - 1) / wpb, ctx->sm_count * cap_b);
             CU(launch_modtable(kp, b->C, gf, gb, st), "kernel launch");
             ctx->launches += 3;
         } else {
