@@ -152,3 +152,64 @@ def test_ops_travel_packed_two_bits_per_column():
     ops = [rng.integers(0, 4, n).astype(np.uint8) for n in (5, 0, 2047, 3)]
     back = P._unpack_ops_chunk(P._pack_ops_chunk(ops))
     assert len(back) == 4 and all(np.array_equal(a, b) for a, b in zip(ops, back))
+
+
+def test_packed_sequences_behave_like_the_list_of_their_pieces():
+    """_lib.Packed: the reads / guide ops of a call as ONE array + offsets (what the C ABI takes), indexable like the list."""
+    from jtk_b200 import _lib
+    rng = np.random.default_rng(3)
+    xs = [rng.integers(0, 4, n).astype(np.uint8) for n in (3, 0, 5, 2, 0, 7)]
+    pk = _lib.Packed(*_lib.concat(xs))
+    assert len(pk) == len(xs) and [len(a) for a in pk] == [len(x) for x in xs]
+    assert all(np.array_equal(a, x) for a, x in zip(pk, xs))
+    assert np.array_equal(pk[-1], xs[-1]) and np.array_equal(pk[2], xs[2])
+    assert [a.tolist() for a in pk[1:4]] == [x.tolist() for x in xs[1:4]]
+    cat, off = _lib.concat(pk)            # passes through: no second concatenate
+    assert cat is pk.cat and off is pk.off
+    assert off.tolist() == np.concatenate([[0], np.cumsum([len(x) for x in xs])]).tolist()
+
+
+def test_scatter_and_compact_runs_are_inverse():
+    """jtk_scatter_runs spreads the compact ops of a call over the padded per-read slots of the polish staging buffer (the gaps
+    stay untouched); jtk_compact_runs brings the patched runs back to the front."""
+    import ctypes as C
+    from jtk_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(4)
+    runs = [rng.integers(0, 4, n).astype(np.uint8) for n in rng.integers(0, 300, 9000)]   # > 4096 runs: the threaded path
+    cat, off = _lib.concat(runs)
+    caps = np.array([len(r) + int(g) for r, g in zip(runs, rng.integers(0, 50, len(runs)))], dtype=np.uint64)
+    pos = np.zeros(len(runs) + 1, dtype=np.uint64)
+    np.cumsum(caps, out=pos[1:])
+    buf = np.full(int(pos[-1]) + 7, 9, dtype=np.uint8)
+    L.jtk_scatter_runs.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    assert L.jtk_scatter_runs(_lib._ptr(cat), _lib._ptr(off), len(runs), _lib._ptr(buf), _lib._ptr(pos)) == 0
+    for k in (0, 1, 17, 4095, 4096, len(runs) - 1):
+        a = int(pos[k])
+        assert np.array_equal(buf[a:a + len(runs[k])], runs[k])
+        assert (buf[a + len(runs[k]):int(pos[k + 1])] == 9).all()      # the gap was not written
+    lens = np.array([len(r) for r in runs], dtype=np.uint32)
+    out_off = np.zeros(len(runs) + 1, dtype=np.uint64)
+    L.jtk_compact_runs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    assert L.jtk_compact_runs(_lib._ptr(buf), _lib._ptr(pos), _lib._ptr(lens), len(runs), _lib._ptr(out_off)) == 0
+    assert out_off.tolist() == off.astype(np.uint64).tolist()
+    assert np.array_equal(buf[:int(out_off[-1])], cat)
+    assert L.jtk_scatter_runs(None, None, 0, None, None) == 0
+
+
+def test_gpu_mcmc_share_balances_the_device_and_the_host_threads(monkeypatch):
+    """pipeline.gpu_mcmc_share: no GPU chains for calls the host threads absorb faster than one GPU chain runs; otherwise the
+    host keeps what it finishes in the GPU's latency and the rest goes to the device (one wave of the speculative kernel, the
+    sub-warp kernel beyond)."""
+    monkeypatch.delenv("JTK_GPU_MCMC", raising=False)
+    monkeypatch.setenv("JTK_CLUSTER_THREADS", "16")
+    assert P.gpu_mcmc_share(20) == 0
+    for n in (80, 250, 2000, 3750):
+        g = P.gpu_mcmc_share(n)
+        assert 0 < g <= n and g <= P.GPU_MCMC_CAPACITY
+        host = n - g
+        assert -(-host // 16) * P.GPU_MCMC_HOST_S <= max(P.gpu_mcmc_seconds(g), 1.4) + 1e-9   # the host side does not finish last
+    assert P.gpu_mcmc_share(2000) <= P.GPU_MCMC_SPEC_CAPACITY          # configs[2]: one wave of the speculative kernel
+    assert P.gpu_mcmc_seconds(100) < P.gpu_mcmc_seconds(2000) < P.gpu_mcmc_seconds(3000)
+    monkeypatch.setenv("JTK_GPU_MCMC", "0"); assert P.gpu_mcmc_share(5000) == 0
+    monkeypatch.setenv("JTK_GPU_MCMC", "1"); assert P.gpu_mcmc_share(5000) == 5000
