@@ -13,6 +13,8 @@ def main():
     ap.add_argument("--chains", type=int, default=640)
     ap.add_argument("--host", type=int, default=4, help="chains also run on the host twin (one thread) for comparison")
     ap.add_argument("--restarts", type=int, default=20)
+    ap.add_argument("--cols", type=int, default=6, help="variant columns per chain (the bench's diploid chunks have 1-2)")
+    ap.add_argument("--zero-reads", type=float, default=0.0, help="fraction of reads without a call in any column")
     args = ap.parse_args()
     from jtk_b200 import _lib, pipeline as P
     from test_gpu_clustering import _host_restarts
@@ -21,8 +23,10 @@ def main():
     datas, states = [], []
     for c in range(args.chains):
         hap = rng.integers(0, 2, 60)
-        v = np.where(hap[:, None] == 1, rng.normal(8, 2, (60, 6)), -rng.normal(8, 2, (60, 6)))
-        v[rng.random((60, 6)) < 0.1] = 0.0
+        D = args.cols
+        v = np.where(hap[:, None] == 1, rng.normal(8, 2, (60, D)), -rng.normal(8, 2, (60, D)))
+        v[rng.random((60, D)) < 0.1] = 0.0
+        v[rng.random(60) < args.zero_reads] = 0.0
         datas.append(v); states.append(P._rng_seed(3490 * (c + 1)))
     ks, covs = [2] * args.chains, [30.0] * args.chains
     ctx.mcmc_restarts(datas[:4], ks[:4], covs[:4], np.array(states[:4]), 1)
